@@ -1,0 +1,121 @@
+/* unetca_b200.h — C ABI of libunetca_b200.so: the B200-native U-Net-CA hot path.
+ *
+ * The reference (Createroner/InSAR-Unet-CA) has no FFI; its hot path is reached through the torch.nn.Module
+ * protocol (Unet-ChannalAttention.py, "UCA" below).  This ABI is what a drop-in nn.Module binds instead of the
+ * ATen ops that UCA's modules dispatch to; each entry cites the reference call site it replaces.
+ *
+ * Rules for every function:
+ *   - plain pointers and sizes only; every pointer is a CUDA *device* pointer unless stated otherwise;
+ *   - the caller owns all memory (tensors, scratch); the library allocates nothing and keeps no state
+ *     besides the implementation switch below;
+ *   - stream-ordered on `stream` (a cudaStream_t), no host synchronisation, no exceptions;
+ *   - returns 0 (or a documented non-negative count) on success, <0 on error; unetca_last_error() returns the
+ *     thread-local message.  There is no CPU fallback: without a CUDA device every op fails.
+ *   - activations are NHWC: element (b,h,w,c) at ((b*H+h)*W+w)*ld + c with ld >= C (a tensor may be a channel
+ *     slice of a concat buffer); `dtype` selects their storage: UNETCA_DTYPE_F32 (fp32 parity mode, FFMA
+ *     contractions) or UNETCA_DTYPE_BF16 (tcgen05 contractions, fp32 accumulate).  Parameters, statistics,
+ *     gradients of parameters, logits and the loss are always fp32.
+ *   - `parts` arguments are fp32 scratch for deterministic two-stage reductions; they must hold
+ *     unetca_max_parts(B) rows of the documented width.
+ *
+ * This header is parsed by the Python binding (one declaration per statement, `name(type arg, ...)`).
+ */
+#ifndef UNETCA_B200_H
+#define UNETCA_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNETCA_DTYPE_F32 0
+#define UNETCA_DTYPE_BF16 1
+
+/* ---- runtime ------------------------------------------------------------------------------------------- */
+const char* unetca_last_error(void);
+int unetca_abi_version(void);
+int unetca_num_sms(void);
+int unetca_max_parts(int B);
+/* 0 (default): bf16 -> tcgen05 kernels, fp32 -> FFMA kernels; 1: FFMA kernels for both (cross-check only) */
+void unetca_set_conv_impl(int impl);
+int unetca_get_conv_impl(void);
+void unetca_tc_force_block_n(int n);
+
+/* ---- module boundary: layout and parameter packing ------------------------------------------------------ */
+/* network input (B,Cin,H,W) NCHW fp32 (UCA:343 `model(images)`) -> im2col rows [B*H*W][Kpad], k = tap*Cin + c */
+int unetca_im2col3x3_nchw(int dtype, const float* x, void* col, int B, int Cin, int H, int W, int Kpad, void* stream);
+int unetca_nchw_to_nhwc(int dtype, const float* x, void* y, int ld, int B, int C, int H, int W, void* stream);
+int unetca_nhwc_to_nchw(int dtype, const void* x, int ld, float* y, int B, int C, int H, int W, void* stream);
+/* nn.Conv2d weight (O,C,3,3) -> wf [O][ldk] (k = tap*C + c, zero padded) and optional dgrad operand wd [C][9*O] */
+int unetca_pack_conv3x3_weight(int dtype, const float* w, void* wf, int ldk, void* wd, int O, int C, void* stream);
+/* nn.ConvTranspose2d weight (Cin,Cout,2,2) -> wf [4*Cout][Cin] and wd [Cin][4*Cout] */
+int unetca_pack_convT_weight(int dtype, const float* w, void* wf, void* wd, int Cin, int Cout, void* stream);
+
+/* ---- contractions (tensor pipe) -------------------------------------------------------------------------- */
+/* nn.Conv2d(k=3,pad=1) forward without bias, UCA:81,84; also its dgrad (pass dy, wd and swap C/O).
+ * stat_parts (optional) receives partial per-channel sum / sum-of-squares of y: [*nparts][2][O]. */
+int unetca_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream);
+/* first conv (K = 9*Cin): out[m][n] = sum_k A[m][k] * Bw[n][k] over im2col rows */
+int unetca_gemm_nt(int dtype, const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K, float* stat_parts, int* nparts, void* stream);
+/* weight gradient of conv3x3 -> dw (O,C,3,3) fp32; ws: split-K scratch (ws_floats floats) */
+int unetca_conv3x3_wgrad(int dtype, const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H, int W, int C, int O, float* dw, void* stream);
+int unetca_im2col_wgrad(int dtype, const void* dy, int lddy, const void* col, int Kpad, float* ws, long ws_floats, long npix, int Cin, int O, float* dw, void* stream);
+/* nn.ConvTranspose2d(k=2,s=2), UCA:112,115,118,121 (+bias); out may be the upper half of a concat buffer */
+int unetca_convT2x2_fwd(int dtype, const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h, int wd, int Cin, int Cout, void* stream);
+int unetca_convT2x2_dgrad(int dtype, const void* dout, int ldd, const void* wdg, void* dx, int ldx, int B, int h, int wd, int Cin, int Cout, void* stream);
+int unetca_convT2x2_wgrad(int dtype, const void* x, int ldx, const void* dout, int ldd, float* ws, long ws_floats, int B, int h, int wd, int Cin, int Cout, float* dw, void* stream);
+
+/* ---- BatchNorm2d + ReLU, UCA:82-83,85-86 ------------------------------------------------------------------ */
+int unetca_chan_stats(int dtype, const void* y, int ld, int C, long npix, float* parts, int* nparts, void* stream);
+/* train: batch statistics (biased var to normalise, unbiased into running_var, momentum), fused affine
+ * scale = gamma*invstd, shift = beta - mean*scale; conv_bias only shifts running_mean (BN cancels it) */
+int unetca_bn_finalize_train(const float* parts, int nparts, int C, long count, const float* conv_bias, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale, float* shift, void* stream);
+/* eval (UCA:276): scale = gamma/sqrt(running_var+eps), shift = beta + (conv_bias - running_mean)*scale */
+int unetca_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const float* beta, const float* running_mean, const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* out = relu(scale*y+shift) and/or per-image channel sums of it (SE squeeze): pool_parts [B][*nparts][C] */
+int unetca_bn_relu(int dtype, const void* y, int ldy, void* out, int ldo, int B, long pix_per_img, int C, const float* scale, const float* shift, float* pool_parts, int* nparts, void* stream);
+int unetca_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, const float* mean, const float* invstd, const float* s, const float* dp, float* parts, int* nparts, void* stream);
+int unetca_bn_bwd_finalize(const float* parts, int nparts, int C, long count, const float* gamma, const float* invstd, float* dgamma, float* dbeta, float* coef, void* stream);
+int unetca_bn_bwd_apply(int dtype, const void* dout, int ldd, const void* y, int ldy, void* dy, int lddy, int B, long pix_per_img, int C, const float* scale, const float* shift, const float* mean, const float* invstd, const float* s, const float* dp, const float* coef, void* stream);
+
+/* ---- SELayer, UCA:45-72, and MaxPool2d(2), UCA:106-109 ----------------------------------------------------- */
+/* p = mean_hw, z = relu(W1 p), s = sigmoid(W2 z) from the squeeze partial sums */
+int unetca_se_fc(const float* pool_parts, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2, float* p, float* z, float* s, void* stream);
+/* out = relu(scale*y+shift) * s[b,c] (s null: no SE); pooled/pos non-null: fused 2x2 max-pool of out with
+ * torch's first-max / NaN rule, pos = 1-byte window position dh*2+dw */
+int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, void* pooled, int ldp, uint8_t* pos, int B, int H, int W, int C, const float* scale, const float* shift, const float* s, void* stream);
+/* standalone pool; idx64 (optional) = torch's (B,C,H/2,W/2) int64 flat indices h*W+w */
+int unetca_maxpool2x2(int dtype, const void* x, int ldx, void* pooled, int ldp, uint8_t* pos, long long* idx64, int B, int H, int W, int C, void* stream);
+int unetca_pool_bwd_add(int dtype, const void* skip_grad, int lds, const void* dpooled, int ldp, const uint8_t* pos, void* dx, int ldx, int B, int H, int W, int C, void* stream);
+int unetca_se_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, float* parts, int* nparts, void* stream);
+int unetca_se_fc_bwd(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2, const float* p, const float* z, const float* s, float* dpre2, float* dz, float* dp, float* dw1, float* dw2, void* stream);
+int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* parts, float* out, void* stream);
+
+/* ---- outc 1x1 conv -> class logits (UCA:125,162), CrossEntropyLoss(ignore_index) (UCA:465,344), argmax (UCA:220) */
+int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, const float* bias, int nc, float* logits, int B, long HW, void* stream);
+int unetca_outc_bwd(int dtype, const float* g, const float* gscale, const void* x, int ldx, void* dx, int lddx, int C, const float* w, int nc, int B, long HW, float* parts, float* dw, float* db, void* stream);
+/* loss_out[0] = mean CE over valid pixels (NaN when none), loss_out[1] = #valid; g = un-normalised dlogits;
+ * gscale_out[0] = upstream/#valid; mask = argmax class map (first maximum wins); target/g/mask optional */
+int unetca_cross_entropy(const float* logits, const long long* target, int nc, int B, long HW, long long ignore_index, const float* upstream, float* g, long long* mask, float* parts, float* loss_out, float* gscale_out, void* stream);
+
+/* ---- implementation-specific contraction entry points (exported for the cross-check tests) ----------------- */
+int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, void* stream);
+int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K, float* stat_parts, void* stream);
+int unetca_tc_convT_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h, int wd, int Cin, int Cout, void* stream);
+int unetca_tc_convT_dgrad(const void* dout, int ldd, const void* wdg, void* dx, int ldx, int B, int h, int wd, int Cin, int Cout, void* stream);
+int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H, int W, int C, int O, void* stream);
+int unetca_tc_gemm_tn(const void* A, int lda, const void* Bm, int ldb, float* ws, long ws_floats, int M, int N, long K, void* stream);
+int unetca_tc_convT_wgrad(const void* x, int ldx, const void* dout, int ldd, float* ws, long ws_floats, int B, int h, int wd, int Cin, int Cout, void* stream);
+int unetca_simt_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, void* stream);
+int unetca_simt_gemm_nt(int dtype, const void* A, int lda, const void* Bm, int ldb, void* out, int ldo, int M, int N, int K, void* stream);
+int unetca_simt_conv3x3_wgrad(int dtype, const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H, int W, int C, int O, void* stream);
+int unetca_simt_gemm_tn(int dtype, const void* A, int lda, const void* Bm, int ldb, float* ws, long ws_floats, int M, int N, long K, void* stream);
+int unetca_simt_convT_fwd(int dtype, const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h, int wd, int Cin, int Cout, void* stream);
+int unetca_simt_convT_dgrad(int dtype, const void* dout, int ldd, const void* w, void* dx, int ldx, int B, int h, int wd, int Cin, int Cout, void* stream);
+int unetca_simt_convT_wgrad(int dtype, const void* x, int ldx, const void* dout, int ldd, float* ws, long ws_floats, int B, int h, int wd, int Cin, int Cout, void* stream);
+int unetca_wgrad_reduce(const float* ws, int nsplit, long split_stride, int mode, int D0, int D1, int ldn, float* dw, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,109 @@
+// api.cu — the contraction entry points of the C ABI (see include/unetca_b200.h).
+//
+// Each op picks its implementation from the storage type: bf16 -> tcgen05/TMEM/TMA kernels (conv_tc.cu),
+// fp32 -> CUDA-core FFMA parity kernels (gemm_simt.cu).  unetca_set_conv_impl(1) forces the FFMA kernels for
+// bf16 as well; the GPU tests use that to cross-check the tensor-core path on identical bf16 operands.
+// There is no CPU path: every op needs a CUDA device and fails with an error string otherwise.
+#include "common.cuh"
+
+extern "C" {
+int unetca_tc_conv3x3_fwd(const void*, int, const void*, int, void*, int, int, int, int, int, int, float*, void*);
+int unetca_tc_gemm_nt(const void*, int, const void*, int, void*, int, long, int, int, float*, void*);
+int unetca_tc_convT_fwd(const void*, int, const void*, const float*, void*, int, int, int, int, int, int, void*);
+int unetca_tc_convT_dgrad(const void*, int, const void*, void*, int, int, int, int, int, int, void*);
+int unetca_tc_conv3x3_wgrad(const void*, int, const void*, int, float*, long, int, int, int, int, int, void*);
+int unetca_tc_gemm_tn(const void*, int, const void*, int, float*, long, int, int, long, void*);
+int unetca_tc_convT_wgrad(const void*, int, const void*, int, float*, long, int, int, int, int, int, void*);
+int unetca_simt_conv3x3_fwd(int, const void*, int, const void*, int, void*, int, int, int, int, int, int, void*);
+int unetca_simt_gemm_nt(int, const void*, int, const void*, int, void*, int, int, int, int, void*);
+int unetca_simt_conv3x3_wgrad(int, const void*, int, const void*, int, float*, long, int, int, int, int, int, void*);
+int unetca_simt_gemm_tn(int, const void*, int, const void*, int, float*, long, int, int, long, void*);
+int unetca_simt_convT_fwd(int, const void*, int, const void*, const float*, void*, int, int, int, int, int, int, void*);
+int unetca_simt_convT_dgrad(int, const void*, int, const void*, void*, int, int, int, int, int, int, void*);
+int unetca_simt_convT_wgrad(int, const void*, int, const void*, int, float*, long, int, int, int, int, int, void*);
+int unetca_chan_stats(int, const void*, int, int, long, float*, int*, void*);
+int unetca_wgrad_reduce(const float*, int, long, int, int, int, int, float*, void*);
+}
+
+static int g_conv_impl = 0;   // 0: by dtype, 1: force FFMA kernels
+static bool use_tc(int dtype) { return dtype == UNETCA_DTYPE_BF16 && g_conv_impl == 0; }
+
+extern "C" {
+
+void unetca_set_conv_impl(int impl) { g_conv_impl = impl; }
+int unetca_get_conv_impl(void) { return g_conv_impl; }
+
+// y = conv3x3(x, pad 1) without bias; NHWC, w packed [O][ldk] with k = tap*C + c.            UCA:81,84
+// stat_parts (optional): partial per-channel sum / sum-of-squares of y, layout [*nparts][2][O].
+// Also the dgrad: call with (dy, w_dgrad [C][9*O]) and C/O swapped.
+int unetca_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W,
+                       int C, int O, float* stat_parts, int* nparts, void* stream) {
+    int rc;
+    if (use_tc(dtype)) {
+        rc = unetca_tc_conv3x3_fwd(x, ldx, w, ldk, y, ldy, B, H, W, C, O, stat_parts, stream);
+        if (rc < 0) return rc;
+        if (nparts) *nparts = rc;
+        return 0;
+    }
+    rc = unetca_simt_conv3x3_fwd(dtype, x, ldx, w, ldk, y, ldy, B, H, W, C, O, stream);
+    if (rc < 0) return rc;
+    if (stat_parts) return unetca_chan_stats(dtype, y, ldy, O, (long)B * H * W, stat_parts, nparts, stream);
+    return 0;
+}
+
+// out[m][n] = sum_k A[m][k] * Bw[n][k]  (first conv on im2col rows, K = Kpad)
+int unetca_gemm_nt(int dtype, const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K,
+                   float* stat_parts, int* nparts, void* stream) {
+    int rc;
+    if (use_tc(dtype)) {
+        rc = unetca_tc_gemm_nt(A, lda, Bw, ldb, out, ldo, M, N, K, stat_parts, stream);
+        if (rc < 0) return rc;
+        if (nparts) *nparts = rc;
+        return 0;
+    }
+    rc = unetca_simt_gemm_nt(dtype, A, lda, Bw, ldb, out, ldo, (int)M, N, K, stream);
+    if (rc < 0) return rc;
+    if (stat_parts) return unetca_chan_stats(dtype, out, ldo, N, M, stat_parts, nparts, stream);
+    return 0;
+}
+
+// dW (O,C,3,3) fp32 = sum_p dy[p][o] * x[p+s(tap)][c]; ws = split-K scratch of ws_floats floats
+int unetca_conv3x3_wgrad(int dtype, const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B,
+                         int H, int W, int C, int O, float* dw, void* stream) {
+    int ns = use_tc(dtype) ? unetca_tc_conv3x3_wgrad(dy, lddy, x, ldx, ws, ws_floats, B, H, W, C, O, stream)
+                           : unetca_simt_conv3x3_wgrad(dtype, dy, lddy, x, ldx, ws, ws_floats, B, H, W, C, O, stream);
+    if (ns < 0) return ns;
+    return unetca_wgrad_reduce(ws, ns, (long)O * 9 * C, 0, O, C, 9 * C, dw, stream);
+}
+
+// first conv: dW (O,Cin,3,3) fp32 = sum_p dy[p][o] * col[p][tap*Cin+c], col rows of width Kpad
+int unetca_im2col_wgrad(int dtype, const void* dy, int lddy, const void* col, int Kpad, float* ws, long ws_floats,
+                        long npix, int Cin, int O, float* dw, void* stream) {
+    int ns = use_tc(dtype) ? unetca_tc_gemm_tn(dy, lddy, col, Kpad, ws, ws_floats, O, Kpad, npix, stream)
+                           : unetca_simt_gemm_tn(dtype, dy, lddy, col, Kpad, ws, ws_floats, O, Kpad, npix, stream);
+    if (ns < 0) return ns;
+    return unetca_wgrad_reduce(ws, ns, (long)O * Kpad, 0, O, Cin, Kpad, dw, stream);
+}
+
+// ConvTranspose2d(k=2,s=2): out[b,2i+d,2j+e,o] = sum_c x[b,i,j,c] w[(d*2+e)*Cout+o][c] + bias[o]     UCA:112..121
+// `out` may point into the upper channel half of a concat buffer (ldo = 2*Cout): torch.cat becomes free.
+int unetca_convT2x2_fwd(int dtype, const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B,
+                        int h, int wd, int Cin, int Cout, void* stream) {
+    if (use_tc(dtype)) return unetca_tc_convT_fwd(x, ldx, w, bias, out, ldo, B, h, wd, Cin, Cout, stream);
+    return unetca_simt_convT_fwd(dtype, x, ldx, w, bias, out, ldo, B, h, wd, Cin, Cout, stream);
+}
+int unetca_convT2x2_dgrad(int dtype, const void* dout, int ldd, const void* wdg, void* dx, int ldx, int B, int h, int wd,
+                          int Cin, int Cout, void* stream) {
+    if (use_tc(dtype)) return unetca_tc_convT_dgrad(dout, ldd, wdg, dx, ldx, B, h, wd, Cin, Cout, stream);
+    return unetca_simt_convT_dgrad(dtype, dout, ldd, wdg, dx, ldx, B, h, wd, Cin, Cout, stream);
+}
+// dW (Cin,Cout,2,2) fp32
+int unetca_convT2x2_wgrad(int dtype, const void* x, int ldx, const void* dout, int ldd, float* ws, long ws_floats, int B,
+                          int h, int wd, int Cin, int Cout, float* dw, void* stream) {
+    int ns = use_tc(dtype) ? unetca_tc_convT_wgrad(x, ldx, dout, ldd, ws, ws_floats, B, h, wd, Cin, Cout, stream)
+                           : unetca_simt_convT_wgrad(dtype, x, ldx, dout, ldd, ws, ws_floats, B, h, wd, Cin, Cout, stream);
+    if (ns < 0) return ns;
+    return unetca_wgrad_reduce(ws, ns, (long)Cin * 4 * Cout, 1, Cin, Cout, 4 * Cout, dw, stream);
+}
+
+}  // extern "C"

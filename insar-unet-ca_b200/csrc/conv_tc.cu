@@ -1,0 +1,736 @@
+// conv_tc.cu — tcgen05 / TMEM / TMA implicit-GEMM engine for the dense contractions of U-Net-CA (sm_100a).
+//
+//   conv3x3 fwd + dgrad    UCA:81,84 / autograd     out[p][n]  = sum_{tap,c} X[p+s(tap)][c] * Wk[n][tap*C+c]
+//   ConvTranspose k2s2 fwd UCA:112..121             out[(p,de)][o] = sum_c X[p][c] * Wk[de*Cout+o][c] + b[o]
+//   ConvTranspose dgrad                             dX[p][c]   = sum_{de,o} dOut[(p,de)][o] * Wd[c][de*Cout+o]
+//   first conv (K=9*Cin)   UCA:81 (via im2col rows) out[p][n]  = sum_k col[p][k] * Wk[n][k]
+//   conv3x3 / convT / first-conv wgrad              dW[m][n]   = sum_p A[p][m] * B[p][n]       (K = pixels)
+//
+// Design (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0   TMA producer: every operand tile is ONE cp.async.bulk.tensor box of [pixels][64 channels] bf16
+//            (128-byte rows, SWIZZLE_128B) out of a 4-D (C,W,H,B) tensor map over the NHWC activation.  A 3x3
+//            tap is the same box at coordinates shifted by (dh,dw); TMA's out-of-bounds zero fill *is* the
+//            conv padding, and the stride-2 pixel lattice of the transposed conv is just a tensor map with
+//            doubled pixel strides.  No im2col buffer exists for C >= 64.
+//   warp 1   MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16) on
+//            shared-memory descriptors; fp32 accumulators live in TMEM, double-buffered (2 x BLOCK_N columns) so
+//            the epilogue of tile i overlaps the MMAs of tile i+1.  K-major descriptors for the forward-like
+//            problems, MN-major descriptors (same smem boxes, a_major=b_major=1) for the weight gradients.
+//   warps 2-5 epilogue: tcgen05.ld (32x32b) -> registers -> bf16 -> swizzled smem staging -> TMA store; the
+//            per-channel sum / sum-of-squares that BatchNorm needs are taken from the staged tile and kept in
+//            shared memory across the CTA's tiles, then written once per CTA (deterministic, no atomics).
+//            Weight-gradient tiles are written as fp32 split-K partials.
+#include "common.cuh"
+#include <cuda.h>
+#include <string.h>
+
+namespace unetca {
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra.uni WAIT_DONE;\n"
+        "bra.uni WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_128B.  Fields in 16-byte units:
+//   [0,14) start address, [16,30) leading byte offset, [32,46) stride byte offset, [46,48) version = 1,
+//   [61,64) layout type = 2 (SWIZZLE_128B).
+// K-major operand (rows = M/N index, 128-byte row = 64 bf16 along K): SBO = 1024 (8 rows), LBO unused.
+// MN-major operand (128-byte row = 64 bf16 along M/N, rows = K index): SBO = 1024 (8 K-rows), LBO = byte
+// distance between consecutive 64-element M/N blocks (one TMA box here).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// Instruction descriptor, kind::f16: c_format F32 (bit 4), a/b format BF16 (bits 7, 10), a/b major (bits 15, 16),
+// N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel parameters
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) TcParams {
+    CUtensorMap mapA[4];
+    CUtensorMap mapB[4];
+    CUtensorMap mapOut[4];
+    int num_m_blocks, num_n_blocks;
+    int tilesW, tilesH, nimg;      // pixel tiling: M tiles (forward-like) or K tiles (weight gradient)
+    int TW, TH, H, W;
+    // forward-like
+    int ntaps, cchunks;
+    signed char dh[12], dw[12], amap[12];
+    int n_blocks_per_outmap;
+    const float* bias;
+    int bias_mod;
+    float* stat_parts;
+    int N;
+    // weight gradient
+    int a_chunks, a_cchunks, b_chunks_per_map;
+    int nsplit, ktiles_total;
+    float* ws;
+    long long split_stride;
+    int ldn, store_transposed, m_valid;
+};
+
+constexpr int kTcThreads = 192;
+constexpr int kBoxBytesFwd = 128 * 128;   // [128 pixels][64 bf16]
+constexpr int kBoxBytesWg = 64 * 128;     // [64 pixels][64 bf16]
+
+template <int BLOCK_N, bool WGRAD> struct TcCfg {
+    static constexpr int A_BYTES = WGRAD ? 2 * kBoxBytesWg : kBoxBytesFwd;
+    static constexpr int B_BYTES = WGRAD ? (BLOCK_N / 64) * kBoxBytesWg : BLOCK_N * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int OUT_BYTES = WGRAD ? 0 : (BLOCK_N / 64) * kBoxBytesFwd;
+    static constexpr int STAT_BYTES = WGRAD ? 0 : 2 * 1024 * 4;        // up to 1024 output channels
+    static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - OUT_BYTES - STAT_BYTES;
+    static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + OUT_BYTES + STAT_BYTES + 256;
+    static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+};
+
+template <int BLOCK_N, bool WGRAD>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
+    using Cfg = TcCfg<BLOCK_N, WGRAD>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* stage_base = smem;
+    uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;
+    float* sm_stats = reinterpret_cast<float*>(out_stage + Cfg::OUT_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::OUT_BYTES + Cfg::STAT_BYTES);
+    uint64_t* full_bar = bars;                  // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        fence_barrier_init();
+        prefetch_tmap(&p.mapA[0]);
+        prefetch_tmap(&p.mapB[0]);
+        if (!WGRAD) prefetch_tmap(&p.mapOut[0]);
+    }
+    if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+    if (!WGRAD && p.stat_parts) {
+        for (int i = threadIdx.x; i < 2 * p.N; i += kTcThreads) sm_stats[i] = 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const long num_work = WGRAD ? (long)p.num_m_blocks * p.num_n_blocks * p.nsplit
+                                : (long)p.num_m_blocks * p.num_n_blocks;
+    const int kt_per_split = WGRAD ? (p.ktiles_total + p.nsplit - 1) / p.nsplit : 0;
+    const int kblocks_fwd = p.ntaps * p.cchunks;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                if (!WGRAD) {
+                    const int nb = (int)(t % p.num_n_blocks);
+                    const int mt = (int)(t / p.num_n_blocks);
+                    const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
+                    const int w0 = tw * p.TW, h0 = th * p.TH;
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const CUtensorMap* ma = &p.mapA[p.amap[tap]];
+                        for (int cc = 0; cc < p.cchunks; ++cc) {
+                            mbar_wait(&empty_bar[s], ph ^ 1);
+                            uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
+                            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+                            tma_load_4d(ma, &full_bar[s], sa, cc * 64, w0 + p.dw[tap], h0 + p.dh[tap], b);
+                            tma_load_4d(&p.mapB[0], &full_bar[s], sa + Cfg::A_BYTES, (tap * p.cchunks + cc) * 64,
+                                        nb * BLOCK_N, 0, 0);
+                            if (++s == STAGES) { s = 0; ph ^= 1; }
+                        }
+                    }
+                } else {
+                    const int z = (int)(t % p.nsplit);
+                    const int nb = (int)((t / p.nsplit) % p.num_n_blocks);
+                    const int mb = (int)(t / ((long)p.nsplit * p.num_n_blocks));
+                    int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                    if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                    for (int kt = kt0; kt < kt1; ++kt) {
+                        const int tw = kt % p.tilesW, th = (kt / p.tilesW) % p.tilesH, b = kt / tiles_per_img;
+                        const int w0 = tw * p.TW, h0 = th * p.TH;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+#pragma unroll
+                        for (int i = 0; i < 2; ++i) {
+                            int q = mb * 2 + i; if (q >= p.a_chunks) q = p.a_chunks - 1;
+                            const int tap = q / p.a_cchunks, cc = q % p.a_cchunks;
+                            tma_load_4d(&p.mapA[p.amap[tap]], &full_bar[s], sa + i * kBoxBytesWg, cc * 64,
+                                        w0 + p.dw[tap], h0 + p.dh[tap], b);
+                        }
+#pragma unroll
+                        for (int j = 0; j < BLOCK_N / 64; ++j) {
+                            const int q = nb * (BLOCK_N / 64) + j;
+                            tma_load_4d(&p.mapB[q / p.b_chunks_per_map], &full_bar[s],
+                                        sa + Cfg::A_BYTES + j * kBoxBytesWg, (q % p.b_chunks_per_map) * 64, w0, h0, b);
+                        }
+                        if (++s == STAGES) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BLOCK_N, WGRAD ? 1 : 0, WGRAD ? 1 : 0);
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                int nk;
+                if (!WGRAD) nk = kblocks_fwd;
+                else {
+                    const int z = (int)(t % p.nsplit);
+                    int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                    if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                    nk = kt1 - kt0;
+                }
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
+                    const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint64_t da, db;
+                        if (!WGRAD) {
+                            da = make_smem_desc(sa + k * 32, 16, 1024);
+                            db = make_smem_desc(sb + k * 32, 16, 1024);
+                        } else {
+                            da = make_smem_desc(sa + k * 2048, kBoxBytesWg, 1024);
+                            db = make_smem_desc(sb + k * 2048, kBoxBytesWg, 1024);
+                        }
+                        umma_bf16(d_tmem, da, db, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) { s = 0; ph ^= 1; }
+                }
+                if (nk == 0) {
+                    // nothing accumulated: the epilogue treats the tile as zero (flag via tfull arrive only)
+                }
+                umma_commit(&tfull_bar[as]);
+                as ^= 1; if (as == 0) aph ^= 1;
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 2..5) ================================
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;             // accumulator row owned by this thread
+        const int ep_tid = threadIdx.x - 64;     // 0..127
+        int as = 0; uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            mbar_wait(&tfull_bar[as], aph);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+            if (!WGRAD) {
+                const int nb = (int)(t % p.num_n_blocks);
+                const int mt = (int)(t / p.num_n_blocks);
+                const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
+                const int w0 = tw * p.TW, h0 = th * p.TH;
+                const bool valid = (h0 + r / p.TW) < p.H && (w0 + r % p.TW) < p.W;
+                // the staging buffer must have been drained by the previous tile's TMA store
+                if (ep_tid == 0) tma_store_wait_read();
+                named_bar_sync(1, 128);
+#pragma unroll
+                for (int j = 0; j < BLOCK_N / 64; ++j) {
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        tmem_ld32(t_addr + j * 64 + half * 32, v);
+                        tmem_wait_ld();
+                        const int ncol0 = nb * BLOCK_N + j * 64 + half * 32;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float f[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                f[i] = __uint_as_float(v[c * 8 + i]);
+                                if (p.bias) f[i] += __ldg(p.bias + (ncol0 + c * 8 + i) % p.bias_mod);
+                                if (!valid) f[i] = 0.f;
+                            }
+                            uint4 pk;
+                            pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
+                            pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
+                            const int chunk = half * 4 + c;
+                            *reinterpret_cast<uint4*>(out_stage + j * kBoxBytesFwd + r * 128 + ((chunk ^ (r & 7)) << 4)) = pk;
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (ep_tid == 0) {
+                    const int om = nb / p.n_blocks_per_outmap;
+                    const int c0 = (nb % p.n_blocks_per_outmap) * BLOCK_N;
+#pragma unroll
+                    for (int j = 0; j < BLOCK_N / 64; ++j)
+                        tma_store_4d(&p.mapOut[om], out_stage + j * kBoxBytesFwd, c0 + j * 64, w0, h0, b);
+                    tma_store_commit();
+                }
+                if (p.stat_parts) {
+                    for (int col = ep_tid; col < BLOCK_N; col += 128) {
+                        const uint8_t* base = out_stage + (col >> 6) * kBoxBytesFwd + (col & 7) * 2;
+                        const int chunk = (col & 63) >> 3;
+                        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                        for (int rr = 0; rr < 128; ++rr) {
+                            const float x = __bfloat162float(
+                                *reinterpret_cast<const bf16*>(base + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
+                            s1 += x; s2 = fmaf(x, x, s2);
+                        }
+                        sm_stats[nb * BLOCK_N + col] += s1;
+                        sm_stats[p.N + nb * BLOCK_N + col] += s2;
+                    }
+                }
+            } else {
+                const int z = (int)(t % p.nsplit);
+                const int nb = (int)((t / p.nsplit) % p.num_n_blocks);
+                const int mb = (int)(t / ((long)p.nsplit * p.num_n_blocks));
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                const bool have = kt1 > kt0;
+                const int m = mb * 128 + r;
+                const bool mvalid = m < p.m_valid;
+                float* wsz = p.ws + (long long)z * p.split_stride;
+#pragma unroll
+                for (int c32 = 0; c32 < BLOCK_N / 32; ++c32) {
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + c32 * 32, v);
+                    tmem_wait_ld();
+                    const int n0 = nb * BLOCK_N + c32 * 32;
+                    if (mvalid) {
+                        if (p.store_transposed) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                wsz[(long long)(n0 + i) * p.ldn + m] = have ? __uint_as_float(v[i]) : 0.f;
+                        } else {
+                            float4* dst = reinterpret_cast<float4*>(wsz + (long long)m * p.ldn + n0);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                dst[i] = have ? make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                            __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+                tcgen05_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            }
+            as ^= 1; if (as == 0) aph ^= 1;
+        }
+        if (!WGRAD) {
+            if (ep_tid == 0) tma_store_wait_all();
+            named_bar_sync(1, 128);
+            if (p.stat_parts) {
+                float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
+                for (int i = ep_tid; i < 2 * p.N; i += 128) dst[i] = sm_stats[i];
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: tensor maps, tiling, launch
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// 4-D bf16 map: dims (C, W, H, B) with element strides (1, sw, sh, sb); box (64, bw, bh, 1); SWIZZLE_128B.
+static int make_map(CUtensorMap* m, const void* base, long C, long W, long H, long B, long sw, long sh, long sb,
+                    int bw, int bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return UNETCA_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (((uintptr_t)base & 15) || (strides[0] & 15) || (strides[1] & 15) || (strides[2] & 15)) {
+        set_error("tensor map: base/strides must be 16-byte aligned");
+        return UNETCA_ERR_ARG;
+    }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): dims %ld %ld %ld %ld strides %ld %ld %ld box %d %d", (int)r, C, W,
+                  H, B, sw, sh, sb, bw, bh);
+        return UNETCA_ERR_CUDA;
+    }
+    return 0;
+}
+
+// pick a (TW, TH) pixel box with TW*TH == npx minimising padded work
+static void pick_tile(int H, int W, int npx, int* TW, int* TH) {
+    long best = -1;
+    for (int tw = 8; tw <= npx && tw <= 256; tw *= 2) {
+        const int th = npx / tw;
+        if (th > 256) continue;
+        const long work = (long)ceil_div(W, tw) * tw * ceil_div(H, th) * th;
+        if (best < 0 || work < best || (work == best && tw > *TW)) { best = work; *TW = tw; *TH = th; }
+    }
+}
+
+template <int BLOCK_N, bool WGRAD>
+static int launch_tc(const TcParams& p, long num_work, cudaStream_t st, const char* what) {
+    using Cfg = TcCfg<BLOCK_N, WGRAD>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    long grid = num_work < num_sms() ? num_work : num_sms();
+    if (grid < 1) grid = 1;
+    tc_kernel<BLOCK_N, WGRAD><<<(int)grid, kTcThreads, Cfg::SMEM_BYTES, st>>>(p);
+    int rc = check_launch(what);
+    return rc < 0 ? rc : (int)grid;
+}
+
+template <bool WGRAD>
+static int launch_tc_n(int block_n, const TcParams& p, long num_work, cudaStream_t st, const char* what) {
+    switch (block_n) {
+        case 64: return launch_tc<64, WGRAD>(p, num_work, st, what);
+        case 128: return launch_tc<128, WGRAD>(p, num_work, st, what);
+        case 256: return launch_tc<256, WGRAD>(p, num_work, st, what);
+    }
+    set_error("%s: BLOCK_N %d unsupported", what, block_n);
+    return UNETCA_ERR_ARG;
+}
+
+static int g_force_block_n = 0;
+static int pick_block_n(int N) {
+    if (g_force_block_n && N % g_force_block_n == 0) return g_force_block_n;
+    if (N % 128 == 0) return 128;
+    return 64;
+}
+
+static void set_taps3x3(TcParams& p) {
+    for (int t = 0; t < 9; ++t) { p.dh[t] = (signed char)(t / 3 - 1); p.dw[t] = (signed char)(t % 3 - 1); p.amap[t] = 0; }
+}
+
+}  // namespace unetca
+
+using namespace unetca;
+
+extern "C" {
+
+void unetca_tc_force_block_n(int n) { g_force_block_n = n; }
+
+// y[p][n] = sum_{tap,c} x[p+s(tap)][c] * w[n][tap*C+c]   (bf16 NHWC in/out, fp32 accumulate).
+// stat_parts != null: per-CTA partial per-channel sum / sum-of-squares of the *stored* bf16 outputs,
+// layout [ret][2][O]; returns the number of partial rows (>0) or <0 on error.
+int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C,
+                          int O, float* stat_parts, void* stream) {
+    UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0 && O <= 1024, "tc_conv3x3: C=%d O=%d must be multiples of 64 (O<=1024)", C, O);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    int TW = 0, TH = 0;
+    pick_tile(H, W, 128, &TW, &TH);
+    int rc;
+    if ((rc = make_map(&p.mapA[0], x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, TW, TH)) < 0) return rc;
+    const int BN = pick_block_n(O);
+    // weights as a (K, N, 1, 1) tensor, box (64, BN)
+    if ((rc = make_map(&p.mapB[0], w, 9L * C, O, 1, 1, ldk, (long)O * ldk, (long)O * ldk, BN, 1)) < 0) return rc;
+    if ((rc = make_map(&p.mapOut[0], y, O, W, H, B, ldy, (long)W * ldy, (long)H * W * ldy, TW, TH)) < 0) return rc;
+    p.tilesW = ceil_div(W, TW); p.tilesH = ceil_div(H, TH); p.nimg = B;
+    p.TW = TW; p.TH = TH; p.H = H; p.W = W;
+    p.num_m_blocks = p.tilesW * p.tilesH * B;
+    p.num_n_blocks = O / BN;
+    p.ntaps = 9; p.cchunks = C / 64;
+    set_taps3x3(p);
+    p.n_blocks_per_outmap = p.num_n_blocks;
+    p.stat_parts = stat_parts; p.N = O;
+    return launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_conv3x3_fwd");
+}
+
+// out[m][n] = sum_k A[m][k] * Bw[n][k], K a multiple of 64 (first conv on im2col rows)
+int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K,
+                      float* stat_parts, void* stream) {
+    UNETCA_REQUIRE(K % 64 == 0 && N % 64 == 0 && N <= 1024, "tc_gemm_nt: K=%d N=%d must be multiples of 64", K, N);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    int rc;
+    // rows as a (K, 128-row strips, M/128 ...) map: use W = M, H = 1
+    UNETCA_REQUIRE(M < (1L << 31), "tc_gemm_nt: M too large");
+    if ((rc = make_map(&p.mapA[0], A, K, M, 1, 1, lda, (long)M * lda, (long)M * lda, 128, 1)) < 0) return rc;
+    const int BN = pick_block_n(N);
+    if ((rc = make_map(&p.mapB[0], Bw, K, N, 1, 1, ldb, (long)N * ldb, (long)N * ldb, BN, 1)) < 0) return rc;
+    if ((rc = make_map(&p.mapOut[0], out, N, M, 1, 1, ldo, (long)M * ldo, (long)M * ldo, 128, 1)) < 0) return rc;
+    p.tilesW = ceil_div(M, 128); p.tilesH = 1; p.nimg = 1;
+    p.TW = 128; p.TH = 1; p.H = 1; p.W = (int)M;
+    p.num_m_blocks = p.tilesW;
+    p.num_n_blocks = N / BN;
+    p.ntaps = 1; p.cchunks = K / 64;
+    p.n_blocks_per_outmap = p.num_n_blocks;
+    p.stat_parts = stat_parts; p.N = N;
+    return launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_gemm_nt");
+}
+
+// ConvTranspose2d k2 s2: out[b,2i+d,2j+e,o] = sum_c x[b,i,j,c] * w[(d*2+e)*Cout+o][c] + bias[o]
+int unetca_tc_convT_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h,
+                        int wd, int Cin, int Cout, void* stream) {
+    UNETCA_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_convT: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    int TW = 0, TH = 0;
+    pick_tile(h, wd, 128, &TW, &TH);
+    int rc;
+    if ((rc = make_map(&p.mapA[0], x, Cin, wd, h, B, ldx, (long)wd * ldx, (long)h * wd * ldx, TW, TH)) < 0) return rc;
+    const int BN = pick_block_n(Cout);
+    if ((rc = make_map(&p.mapB[0], w, Cin, 4L * Cout, 1, 1, Cin, 4L * Cout * Cin, 4L * Cout * Cin, BN, 1)) < 0) return rc;
+    for (int de = 0; de < 4; ++de) {
+        const bf16* base = (const bf16*)out + ((long)(de >> 1) * 2 * wd + (de & 1)) * ldo;
+        if ((rc = make_map(&p.mapOut[de], base, Cout, wd, h, B, 2L * ldo, 4L * wd * ldo, 4L * h * wd * ldo, TW, TH)) < 0) return rc;
+    }
+    p.tilesW = ceil_div(wd, TW); p.tilesH = ceil_div(h, TH); p.nimg = B;
+    p.TW = TW; p.TH = TH; p.H = h; p.W = wd;
+    p.num_m_blocks = p.tilesW * p.tilesH * B;
+    p.num_n_blocks = 4 * Cout / BN;
+    p.ntaps = 1; p.cchunks = Cin / 64;
+    p.n_blocks_per_outmap = Cout / BN;
+    p.bias = bias; p.bias_mod = Cout;
+    p.N = 4 * Cout;
+    int r2 = launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_convT_fwd");
+    return r2 < 0 ? r2 : 0;
+}
+
+// dx[b,i,j,c] = sum_{de,o} dout[b,2i+d,2j+e,o] * wdg[c][de*Cout+o]
+int unetca_tc_convT_dgrad(const void* dout, int ldd, const void* wdg, void* dx, int ldx, int B, int h, int wd, int Cin,
+                          int Cout, void* stream) {
+    UNETCA_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_convT: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    int TW = 0, TH = 0;
+    pick_tile(h, wd, 128, &TW, &TH);
+    int rc;
+    for (int de = 0; de < 4; ++de) {
+        const bf16* base = (const bf16*)dout + ((long)(de >> 1) * 2 * wd + (de & 1)) * ldd;
+        if ((rc = make_map(&p.mapA[de], base, Cout, wd, h, B, 2L * ldd, 4L * wd * ldd, 4L * h * wd * ldd, TW, TH)) < 0) return rc;
+        p.amap[de] = (signed char)de;
+    }
+    const int BN = pick_block_n(Cin);
+    if ((rc = make_map(&p.mapB[0], wdg, 4L * Cout, Cin, 1, 1, 4L * Cout, 4L * Cout * Cin, 4L * Cout * Cin, BN, 1)) < 0) return rc;
+    if ((rc = make_map(&p.mapOut[0], dx, Cin, wd, h, B, ldx, (long)wd * ldx, (long)h * wd * ldx, TW, TH)) < 0) return rc;
+    p.tilesW = ceil_div(wd, TW); p.tilesH = ceil_div(h, TH); p.nimg = B;
+    p.TW = TW; p.TH = TH; p.H = h; p.W = wd;
+    p.num_m_blocks = p.tilesW * p.tilesH * B;
+    p.num_n_blocks = Cin / BN;
+    p.ntaps = 4; p.cchunks = Cout / 64;
+    p.n_blocks_per_outmap = p.num_n_blocks;
+    p.N = Cin;
+    int r2 = launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_convT_dgrad");
+    return r2 < 0 ? r2 : 0;
+}
+
+static int pick_nsplit(long tiles, int ktiles, long stride_floats, long ws_floats) {
+    long s = (2L * num_sms() + tiles - 1) / tiles;
+    if (s > ktiles / 4) s = ktiles / 4;
+    if (s < 1) s = 1;
+    if (s * stride_floats > ws_floats) s = ws_floats / stride_floats;
+    return (int)s;
+}
+
+// ws[z][o][tap*C+c] = sum_{p in split z} dy[p][o] * x[p+s(tap)][c]; returns nsplit
+int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H,
+                            int W, int C, int O, void* stream) {
+    UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0, "tc_conv3x3_wgrad: C=%d O=%d must be multiples of 64", C, O);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    int TW = 0, TH = 0;
+    pick_tile(H, W, 64, &TW, &TH);
+    int rc;
+    if ((rc = make_map(&p.mapA[0], x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, TW, TH)) < 0) return rc;
+    if ((rc = make_map(&p.mapB[0], dy, O, W, H, B, lddy, (long)W * lddy, (long)H * W * lddy, TW, TH)) < 0) return rc;
+    const int BN = pick_block_n(O);
+    p.tilesW = ceil_div(W, TW); p.tilesH = ceil_div(H, TH); p.nimg = B;
+    p.TW = TW; p.TH = TH; p.H = H; p.W = W;
+    set_taps3x3(p);
+    p.a_chunks = 9 * (C / 64); p.a_cchunks = C / 64; p.b_chunks_per_map = O / 64;
+    p.num_m_blocks = (p.a_chunks + 1) / 2;
+    p.num_n_blocks = O / BN;
+    p.ktiles_total = p.tilesW * p.tilesH * B;
+    p.split_stride = (long long)O * 9 * C;
+    p.nsplit = pick_nsplit((long)p.num_m_blocks * p.num_n_blocks, p.ktiles_total, p.split_stride, ws_floats);
+    if (p.nsplit < 1) { set_error("tc_conv3x3_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+    p.ws = ws; p.ldn = 9 * C; p.store_transposed = 1; p.m_valid = 9 * C;
+    int r2 = launch_tc_n<true>(BN, p, (long)p.num_m_blocks * p.num_n_blocks * p.nsplit, (cudaStream_t)stream, "tc_conv3x3_wgrad");
+    return r2 < 0 ? r2 : p.nsplit;
+}
+
+// ws[z][m][n] = sum_k A[k][m] * Bm[k][n]   (A: [K][M], Bm: [K][N], both channel-contiguous; M, N multiples of 64).
+// First-conv wgrad: A = dY [npix][O], Bm = im2col rows [npix][Kpad] -> ws[z][O][Kpad].  returns nsplit
+int unetca_tc_gemm_tn(const void* A, int lda, const void* Bm, int ldb, float* ws, long ws_floats, int M, int N, long K,
+                      void* stream) {
+    UNETCA_REQUIRE(M % 64 == 0 && N % 64 == 0, "tc_gemm_tn: M=%d N=%d must be multiples of 64", M, N);
+    UNETCA_REQUIRE(K < (1L << 31), "tc_gemm_tn: K too large");
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    int rc;
+    // accumulator rows <- Bm's channels (n), accumulator columns <- A's channels (m); stored transposed
+    if ((rc = make_map(&p.mapA[0], Bm, N, K, 1, 1, ldb, K * ldb, K * ldb, 64, 1)) < 0) return rc;
+    if ((rc = make_map(&p.mapB[0], A, M, K, 1, 1, lda, K * lda, K * lda, 64, 1)) < 0) return rc;
+    const int BN = pick_block_n(M);
+    p.tilesW = ceil_div(K, 64); p.tilesH = 1; p.nimg = 1;
+    p.TW = 64; p.TH = 1; p.H = 1; p.W = (int)K;
+    p.a_chunks = N / 64; p.a_cchunks = N / 64; p.b_chunks_per_map = M / 64;
+    p.num_m_blocks = (p.a_chunks + 1) / 2;
+    p.num_n_blocks = M / BN;
+    p.ktiles_total = p.tilesW;
+    p.split_stride = (long long)M * N;
+    p.nsplit = pick_nsplit((long)p.num_m_blocks * p.num_n_blocks, p.ktiles_total, p.split_stride, ws_floats);
+    if (p.nsplit < 1) { set_error("tc_gemm_tn: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+    p.ws = ws; p.ldn = N; p.store_transposed = 1; p.m_valid = N;
+    int r2 = launch_tc_n<true>(BN, p, (long)p.num_m_blocks * p.num_n_blocks * p.nsplit, (cudaStream_t)stream, "tc_gemm_tn");
+    return r2 < 0 ? r2 : p.nsplit;
+}
+
+// ws[z][cin][de*Cout+o] = sum_p x[p][cin] * dout[(p,de)][o]; returns nsplit
+int unetca_tc_convT_wgrad(const void* x, int ldx, const void* dout, int ldd, float* ws, long ws_floats, int B, int h,
+                          int wd, int Cin, int Cout, void* stream) {
+    UNETCA_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_convT_wgrad: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    int TW = 0, TH = 0;
+    pick_tile(h, wd, 64, &TW, &TH);
+    int rc;
+    if ((rc = make_map(&p.mapA[0], x, Cin, wd, h, B, ldx, (long)wd * ldx, (long)h * wd * ldx, TW, TH)) < 0) return rc;
+    for (int de = 0; de < 4; ++de) {
+        const bf16* base = (const bf16*)dout + ((long)(de >> 1) * 2 * wd + (de & 1)) * ldd;
+        if ((rc = make_map(&p.mapB[de], base, Cout, wd, h, B, 2L * ldd, 4L * wd * ldd, 4L * h * wd * ldd, TW, TH)) < 0) return rc;
+    }
+    const int BN = pick_block_n(Cout);
+    p.tilesW = ceil_div(wd, TW); p.tilesH = ceil_div(h, TH); p.nimg = B;
+    p.TW = TW; p.TH = TH; p.H = h; p.W = wd;
+    p.a_chunks = Cin / 64; p.a_cchunks = Cin / 64; p.b_chunks_per_map = Cout / 64;
+    p.num_m_blocks = (p.a_chunks + 1) / 2;
+    p.num_n_blocks = 4 * Cout / BN;
+    p.ktiles_total = p.tilesW * p.tilesH * B;
+    p.split_stride = (long long)Cin * 4 * Cout;
+    p.nsplit = pick_nsplit((long)p.num_m_blocks * p.num_n_blocks, p.ktiles_total, p.split_stride, ws_floats);
+    if (p.nsplit < 1) { set_error("tc_convT_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+    p.ws = ws; p.ldn = 4 * Cout; p.store_transposed = 0; p.m_valid = Cin;
+    int r2 = launch_tc_n<true>(BN, p, (long)p.num_m_blocks * p.num_n_blocks * p.nsplit, (cudaStream_t)stream, "tc_convT_wgrad");
+    return r2 < 0 ? r2 : p.nsplit;
+}
+
+}  // extern "C"

@@ -1,0 +1,1161 @@
+// elementwise.cu — the HBM-bound half of the U-Net-CA hot path (everything that is not a contraction).
+//
+// Reference semantics restated here (file:line into /root/reference/Unet-ChannalAttention.py, "UCA"):
+//   BatchNorm2d train/eval ......... UCA:82,85     ReLU ............... UCA:83,86
+//   SELayer (pool, FC, sigmoid, scale) UCA:45-72   MaxPool2d(2) ....... UCA:106-109
+//   outc 1x1 conv -> class logits ... UCA:125,162  CrossEntropyLoss(ignore_index=255) UCA:465,344
+//   torch.max(outputs,1) argmax mask  UCA:220
+// plus the autograd derivatives of each (UCA:345).
+//
+// All kernels share one thread mapping ("pixel rows"): a 256-thread block owns a contiguous range of
+// NHWC pixels; thread (r, cv) walks pixels r, r+rows, ... and always touches the same 16-byte channel
+// vector cv, so per-channel parameters are loaded once per thread and every warp-level access is a run of
+// whole 128-byte pixel rows (fully coalesced).  Reductions are two-stage and deterministic: per-block
+// partials in a caller-provided fp32 scratch, then a tiny finalize kernel that sums them in double.
+#include "common.cuh"
+#include <math.h>
+
+namespace unetca {
+
+constexpr int kThreads = 256;
+constexpr int kMaxParts = 1184;  // 148 SMs x 8
+
+struct RowMap {
+    int vpr;    // 16-byte vectors per pixel row
+    int rows;   // pixel rows processed concurrently by one block
+};
+template <typename T> static inline RowMap row_map(int C) {
+    RowMap m;
+    m.vpr = C / VecTraits<T>::N;
+    m.rows = kThreads / m.vpr;
+    return m;
+}
+// pixels per block for an elementwise pass / a reduction pass
+template <typename T> static inline long ew_chunk(int C, long npix) {
+    (void)npix;
+    return (long)row_map<T>(C).rows * 16;
+}
+template <typename T> static inline long red_chunk(int C, long npix) {
+    long c = (long)row_map<T>(C).rows * 16;
+    long c2 = (npix + kMaxParts - 1) / kMaxParts;
+    return c > c2 ? c : c2;
+}
+
+// Sum `acc[s][*]` over the block's pixel rows and write out[s*C + c]; all threads must call.
+template <int NSTAT, int VEC>
+__device__ __forceinline__ void block_reduce_rows(float (&acc)[NSTAT][VEC], int C, int vpr, int rows, float* out) {
+    __shared__ float red[kThreads * 8];
+    const int tid = threadIdx.x;
+    const int r = tid / vpr, cv = tid % vpr;
+#pragma unroll
+    for (int s = 0; s < NSTAT; ++s) {
+        __syncthreads();
+        if (r < rows) {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) red[r * C + cv * VEC + i] = acc[s][i];
+        }
+        __syncthreads();
+        for (int c = tid; c < C; c += kThreads) {
+            float t = 0.f;
+            for (int rr = 0; rr < rows; ++rr) t += red[rr * C + c];
+            out[s * C + c] = t;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-channel sum / sum of squares of a conv output (used when the producing GEMM does not fuse them)
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) chan_stats_kernel(const T* __restrict__ y, int ld, int C, long npix,
+                                                              long chunk, float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > npix) p1 = npix;
+    float acc[2][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+    if (r < rows) {
+#pragma unroll 4
+        for (long p = p0 + r; p < p1; p += rows) {
+            float v[VEC];
+            load_vec(y + p * ld + cv * VEC, v);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) { acc[0][i] += v[i]; acc[1][i] += v[i] * v[i]; }
+        }
+    }
+    block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + (long)blockIdx.x * 2 * C);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// BN finalize (train): batch mean / biased var from partial sums, running-stat update with the unbiased
+// variance (momentum 0.1), and the fused affine a = gamma*invstd, b = beta - mean*a.      UCA:82,85
+// The pre-BN conv bias never enters the conv: in train mode BN cancels it, so it only shifts the batch mean
+// that goes into running_mean.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_train_kernel(const float* __restrict__ parts, int nparts, int C, double count,
+                                         const float* __restrict__ conv_bias, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float* running_mean, float* running_var,
+                                         float momentum, float eps, float* mean_out, float* invstd_out,
+                                         float* scale_out, float* shift_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nparts; ++i) {
+        s += (double)parts[(long)i * 2 * C + c];
+        q += (double)parts[(long)i * 2 * C + C + c];
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+    const float a = gamma[c] * invstd;
+    mean_out[c] = (float)mean;
+    invstd_out[c] = invstd;
+    scale_out[c] = a;
+    shift_out[c] = beta[c] - (float)mean * a;
+    if (running_mean) {
+        const float bm = (float)mean + (conv_bias ? conv_bias[c] : 0.f);
+        const float uv = (float)(var * (count / (count - 1.0)));
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * bm;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * uv;
+    }
+}
+
+// eval: a = gamma / sqrt(running_var + eps), b = beta + (conv_bias - running_mean) * a    UCA:276
+__global__ void bn_fold_eval_kernel(int C, const float* __restrict__ conv_bias, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ running_mean,
+                                    const float* __restrict__ running_var, float eps, float* scale_out,
+                                    float* shift_out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float a = gamma[c] / sqrtf(running_var[c] + eps);
+    scale_out[c] = a;
+    shift_out[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - running_mean[c]) * a;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out = relu(a*y + b)                      (first conv of a DoubleConv, or second conv when use_se=False)
+// POOLSUM: additionally / instead accumulate per-(image, channel) sums of relu(a*y+b) for the SE squeeze.
+//   grid = (blocks per image, B); WRITE selects whether `out` is written.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, bool WRITE, bool POOLSUM>
+__global__ void __launch_bounds__(kThreads) bn_relu_kernel(const T* __restrict__ y, int ldy, T* __restrict__ out,
+                                                           int ldo, int C, long pix_per_img, long chunk,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const long base = (long)blockIdx.y * pix_per_img;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    float acc[1][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = 0.f;
+    if (r < rows) {
+        float a[VEC], b[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { a[i] = scale[cv * VEC + i]; b[i] = shift[cv * VEC + i]; }
+#pragma unroll 4
+        for (long p = p0 + r; p < p1; p += rows) {
+            float v[VEC];
+            load_vec(y + (base + p) * ldy + cv * VEC, v);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                v[i] = fmaxf(fmaf(a[i], v[i], b[i]), 0.f);
+                if (POOLSUM) acc[0][i] += v[i];
+            }
+            if (WRITE) store_vec(out + (base + p) * ldo + cv * VEC, v);
+        }
+    }
+    if (POOLSUM)
+        block_reduce_rows<1, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * C);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SE excitation: p = mean_hw, z = relu(W1 p), s = sigmoid(W2 z)      UCA:54-59,65-68   (one block per image)
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ parts, int nparts, int C, int Cr,
+                                                    float inv_hw, const float* __restrict__ w1,
+                                                    const float* __restrict__ w2, float* __restrict__ p_out,
+                                                    float* __restrict__ z_out, float* __restrict__ s_out) {
+    extern __shared__ float sm[];
+    float* p = sm;          // [C]
+    float* z = sm + C;      // [Cr]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int c = tid; c < C; c += blockDim.x) {
+        double t = 0.0;
+        for (int i = 0; i < nparts; ++i) t += (double)parts[((long)b * nparts + i) * C + c];
+        const float v = (float)t * inv_hw;
+        p[c] = v;
+        p_out[(long)b * C + c] = v;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < Cr; j += nwarps) {
+        float t = 0.f;
+        for (int c = lane; c < C; c += 32) t = fmaf(w1[(long)j * C + c], p[c], t);
+        t = warp_sum(t);
+        if (lane == 0) { t = fmaxf(t, 0.f); z[j] = t; z_out[(long)b * Cr + j] = t; }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int j = 0; j < Cr; ++j) t = fmaf(w2[(long)c * Cr + j], z[j], t);
+        s_out[(long)b * C + c] = 1.f / (1.f + expf(-t));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Block output: o = relu(a*y+b) * s[b,c]  (s == nullptr: plain relu(bn)), written with stride ldo (e.g. straight
+// into the skip half of the decoder's concat buffer -> torch.cat at UCA:140.. costs nothing), and optionally
+// the fused MaxPool2d(2) of o: pooled value + 1-byte window position (dh*2+dw).       UCA:72, UCA:106-109
+// Tie-break / NaN rule of nn.MaxPool2d: scan (0,0),(0,1),(1,0),(1,1); take when v > best || isnan(v).
+// One thread = one 2x2 pixel quad x one channel vector.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, bool POOL>
+__global__ void __launch_bounds__(kThreads) se_scale_pool_kernel(const T* __restrict__ y, int ldy,
+                                                                 T* __restrict__ out, int ldo,
+                                                                 T* __restrict__ pooled, int ldp,
+                                                                 uint8_t* __restrict__ pos, int B, int H, int W, int C,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 const float* __restrict__ s) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long nquad = (long)B * Ho * Wo;
+    const long gid = (long)blockIdx.x * kThreads + threadIdx.x;
+    const long q = gid / vpr;
+    const int cv = (int)(gid % vpr);
+    if (q >= nquad) return;
+    const int wo = (int)(q % Wo);
+    const int ho = (int)((q / Wo) % Ho);
+    const int b = (int)(q / ((long)Wo * Ho));
+    float a[VEC], sh[VEC], g[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        a[i] = scale[cv * VEC + i];
+        sh[i] = shift[cv * VEC + i];
+        g[i] = s ? s[(long)b * C + cv * VEC + i] : 1.f;
+    }
+    float v[4][VEC];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long p = ((long)b * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1);
+        load_vec(y + p * ldy + cv * VEC, v[k]);
+    }
+    float best[VEC];
+    uint8_t code[VEC];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long p = ((long)b * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            float t = fmaxf(fmaf(a[i], v[k][i], sh[i]), 0.f) * g[i];
+            t = round_to(t, (const T*)nullptr);
+            v[k][i] = t;
+            if (POOL) {
+                if (k == 0) { best[i] = t; code[i] = 0; }
+                else if (t > best[i] || t != t) { best[i] = t; code[i] = (uint8_t)k; }
+            }
+        }
+        store_vec(out + p * ldo + cv * VEC, v[k]);
+    }
+    if (POOL) {
+        store_vec(pooled + q * ldp + cv * VEC, best);
+        uint8_t* dst = pos + q * C + cv * VEC;
+        if (VEC == 8) {
+            uint2 t;
+            t.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+            t.y = code[4 % VEC] | (code[5 % VEC] << 8) | (code[6 % VEC] << 16) | (code[7 % VEC] << 24);
+            *reinterpret_cast<uint2*>(dst) = t;
+        } else {
+            *reinterpret_cast<uint32_t*>(dst) = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+        }
+    }
+}
+
+// Standalone MaxPool2d(2) over an NHWC tensor: pooled values, 1-byte window positions and (optionally) the
+// int64 flat indices h*W+w that torch's max_pool2d(return_indices=True) reports.          UCA:106-109
+template <typename T>
+__global__ void __launch_bounds__(kThreads) maxpool_kernel(const T* __restrict__ x, int ldx, T* __restrict__ pooled,
+                                                           int ldp, uint8_t* __restrict__ pos,
+                                                           long long* __restrict__ idx64, int B, int H, int W, int C) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long nquad = (long)B * Ho * Wo;
+    const long gid = (long)blockIdx.x * kThreads + threadIdx.x;
+    const long q = gid / vpr;
+    const int cv = (int)(gid % vpr);
+    if (q >= nquad) return;
+    const int wo = (int)(q % Wo);
+    const int ho = (int)((q / Wo) % Ho);
+    const int b = (int)(q / ((long)Wo * Ho));
+    float best[VEC];
+    int code[VEC];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long p = ((long)b * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1);
+        float v[VEC];
+        load_vec(x + p * ldx + cv * VEC, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            if (k == 0) { best[i] = v[i]; code[i] = 0; }
+            else if (v[i] > best[i] || v[i] != v[i]) { best[i] = v[i]; code[i] = k; }
+        }
+    }
+    store_vec(pooled + q * ldp + cv * VEC, best);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        if (pos) pos[q * C + cv * VEC + i] = (uint8_t)code[i];
+        // NCHW-shaped (B,C,Ho,Wo) int64 output, value = flat offset into the (H,W) input plane
+        if (idx64)
+            idx64[(((long)b * C + cv * VEC + i) * Ho + ho) * Wo + wo] =
+                (long long)(2 * ho + (code[i] >> 1)) * W + 2 * wo + (code[i] & 1);
+    }
+}
+
+// dx = skip_grad + unpool(dpooled): the gradient of a skip tensor that feeds both the decoder concat and the
+// next level's MaxPool.  skip_grad may be null (0).  One thread = one 2x2 quad x one channel vector.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pool_bwd_add_kernel(const T* __restrict__ skip_grad, int lds,
+                                                                const T* __restrict__ dpooled, int ldp,
+                                                                const uint8_t* __restrict__ pos, T* __restrict__ dx,
+                                                                int ldx, int B, int H, int W, int C) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long nquad = (long)B * Ho * Wo;
+    const long gid = (long)blockIdx.x * kThreads + threadIdx.x;
+    const long q = gid / vpr;
+    const int cv = (int)(gid % vpr);
+    if (q >= nquad) return;
+    const int wo = (int)(q % Wo);
+    const int ho = (int)((q / Wo) % Ho);
+    const int b = (int)(q / ((long)Wo * Ho));
+    float g[VEC];
+    load_vec(dpooled + q * ldp + cv * VEC, g);
+    uint8_t code[VEC];
+    const uint8_t* src = pos + q * C + cv * VEC;
+    if (VEC == 8) {
+        uint2 t = *reinterpret_cast<const uint2*>(src);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { code[i] = (t.x >> (8 * i)) & 0xff; code[(4 + i) % VEC] = (t.y >> (8 * i)) & 0xff; }
+    } else {
+        uint32_t t = *reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) code[i] = (t >> (8 * i)) & 0xff;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const long p = ((long)b * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1);
+        float v[VEC];
+        if (skip_grad) load_vec(skip_grad + p * lds + cv * VEC, v);
+        else {
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) if (code[i] == k) v[i] += g[i];
+        store_vec(dx + p * ldx + cv * VEC, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SE backward, stage 1: ds[b,c] = sum_hw dO * relu(a*y+b)         (partials per image; grid = (nblk, B))
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads) se_bwd_reduce_kernel(const T* __restrict__ dout, int ldd,
+                                                                 const T* __restrict__ y, int ldy, int C,
+                                                                 long pix_per_img, long chunk,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const long base = (long)blockIdx.y * pix_per_img;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    float acc[1][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = 0.f;
+    if (r < rows) {
+        float a[VEC], b[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { a[i] = scale[cv * VEC + i]; b[i] = shift[cv * VEC + i]; }
+#pragma unroll 4
+        for (long p = p0 + r; p < p1; p += rows) {
+            float v[VEC], d[VEC];
+            load_vec(y + (base + p) * ldy + cv * VEC, v);
+            load_vec(dout + (base + p) * ldd + cv * VEC, d);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[0][i] = fmaf(d[i], fmaxf(fmaf(a[i], v[i], b[i]), 0.f), acc[0][i]);
+        }
+    }
+    block_reduce_rows<1, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * C);
+}
+
+// SE backward, stage 2 (one block per image): ds -> d(pre-sigmoid) -> dz -> dp.    derivative of UCA:54-59
+//   dpre2[b,c] = ds*s*(1-s);  dz[b,j] = (sum_c dpre2[c] W2[c,j]) * (z>0);  dp[b,c] = sum_j dz[j] W1[j,c]
+__global__ void __launch_bounds__(256) se_fc_bwd_kernel(const float* __restrict__ parts, int nparts, int C, int Cr,
+                                                        const float* __restrict__ w1, const float* __restrict__ w2,
+                                                        const float* __restrict__ z, const float* __restrict__ s,
+                                                        float* __restrict__ dpre2_out, float* __restrict__ dz_out,
+                                                        float* __restrict__ dp_out) {
+    extern __shared__ float sm[];
+    float* dpre2 = sm;       // [C]
+    float* dz = sm + C;      // [Cr]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int c = tid; c < C; c += blockDim.x) {
+        double t = 0.0;
+        for (int i = 0; i < nparts; ++i) t += (double)parts[((long)b * nparts + i) * C + c];
+        const float sv = s[(long)b * C + c];
+        const float v = (float)t * sv * (1.f - sv);
+        dpre2[c] = v;
+        dpre2_out[(long)b * C + c] = v;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < Cr; j += nwarps) {
+        float t = 0.f;
+        for (int c = lane; c < C; c += 32) t = fmaf(dpre2[c], w2[(long)c * Cr + j], t);
+        t = warp_sum(t);
+        if (lane == 0) {
+            t = z[(long)b * Cr + j] > 0.f ? t : 0.f;
+            dz[j] = t;
+            dz_out[(long)b * Cr + j] = t;
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int j = 0; j < Cr; ++j) t = fmaf(dz[j], w1[(long)j * C + c], t);
+        dp_out[(long)b * C + c] = t;
+    }
+}
+
+// SE FC weight grads: dW2[c,j] = sum_b dpre2[b,c] z[b,j];  dW1[j,c] = sum_b dz[b,j] p[b,c]   (K = batch)
+__global__ void se_fc_wgrad_kernel(int B, int C, int Cr, const float* __restrict__ dpre2,
+                                   const float* __restrict__ dz, const float* __restrict__ p,
+                                   const float* __restrict__ z, float* __restrict__ dw1, float* __restrict__ dw2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C * Cr) return;
+    {   // dW2 is (C, Cr)
+        const int c = i / Cr, j = i % Cr;
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) t = fmaf(dpre2[(long)b * C + c], z[(long)b * Cr + j], t);
+        dw2[i] = t;
+    }
+    {   // dW1 is (Cr, C)
+        const int j = i / C, c = i % C;
+        float t = 0.f;
+        for (int b = 0; b < B; ++b) t = fmaf(dz[(long)b * Cr + j], p[(long)b * C + c], t);
+        dw1[i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ReLU + BN backward (train).  dz = dA * (a*y+b > 0) with, when SE follows (s != null),
+// dA = dO*s[b,c] + dp[b,c]/HW (the SE scale and squeeze derivatives folded in).
+//   stage 1: per-channel sum(dz), sum(dz*xhat)      stage 2 (finalize): dgamma, dbeta, c1, c2
+//   stage 3: dY = gamma*invstd * (dz - c1 - xhat*c2)
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, bool SE, bool APPLY>
+__global__ void __launch_bounds__(kThreads) bn_bwd_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ y,
+                                                          int ldy, T* __restrict__ dy, int lddy, int C,
+                                                          long pix_per_img, long chunk, float inv_hw,
+                                                          const float* __restrict__ scale,
+                                                          const float* __restrict__ shift,
+                                                          const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd,
+                                                          const float* __restrict__ s, const float* __restrict__ dp,
+                                                          const float* __restrict__ coef /* [3][C]: g, c1, c2 */,
+                                                          float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const long base = (long)blockIdx.y * pix_per_img;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    float acc[2][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+    if (r < rows) {
+        float a[VEC], b[VEC], mu[VEC], is[VEC], sv[VEC], dpv[VEC], g[VEC], c1[VEC], c2[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int c = cv * VEC + i;
+            a[i] = scale[c]; b[i] = shift[c]; mu[i] = mean[c]; is[i] = invstd[c];
+            if (SE) { sv[i] = s[(long)blockIdx.y * C + c]; dpv[i] = dp[(long)blockIdx.y * C + c] * inv_hw; }
+            if (APPLY) { g[i] = coef[c]; c1[i] = coef[C + c]; c2[i] = coef[2 * C + c]; }
+        }
+#pragma unroll 4
+        for (long p = p0 + r; p < p1; p += rows) {
+            float v[VEC], d[VEC];
+            load_vec(y + (base + p) * ldy + cv * VEC, v);
+            load_vec(dout + (base + p) * ldd + cv * VEC, d);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float da = SE ? fmaf(d[i], sv[i], dpv[i]) : d[i];
+                const float dz = fmaf(a[i], v[i], b[i]) > 0.f ? da : 0.f;
+                const float xh = (v[i] - mu[i]) * is[i];
+                if (APPLY) d[i] = g[i] * (dz - c1[i] - xh * c2[i]);
+                else { acc[0][i] += dz; acc[1][i] = fmaf(dz, xh, acc[1][i]); }
+            }
+            if (APPLY) store_vec(dy + (base + p) * lddy + cv * VEC, d);
+        }
+    }
+    if (!APPLY)
+        block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ parts, int nparts, int C, double count,
+                                       const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ coef) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < nparts; ++i) {
+        s += (double)parts[(long)i * 2 * C + c];
+        q += (double)parts[(long)i * 2 * C + C + c];
+    }
+    dbeta[c] = (float)s;
+    dgamma[c] = (float)q;
+    coef[c] = gamma[c] * invstd[c];
+    coef[C + c] = (float)(s / count);
+    coef[2 * C + c] = (float)(q / count);
+}
+
+// per-channel sum over pixels (ConvTranspose2d bias gradient)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) chan_sum_kernel(const T* __restrict__ x, int ld, int C, long npix,
+                                                            long chunk, float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > npix) p1 = npix;
+    float acc[1][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = 0.f;
+    if (r < rows) {
+#pragma unroll 4
+        for (long p = p0 + r; p < p1; p += rows) {
+            float v[VEC];
+            load_vec(x + p * ld + cv * VEC, v);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[0][i] += v[i];
+        }
+    }
+    block_reduce_rows<1, VEC>(acc, C, vpr, rows, parts + (long)blockIdx.x * C);
+}
+// out[i] = scale * sum_parts parts[p][i]      (generic deterministic second stage)
+__global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, int n, const float* __restrict__ scale_ptr,
+                                 float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0.0;
+    for (int p = 0; p < nparts; ++p) t += (double)parts[(long)p * n + i];
+    out[i] = (float)(t * (scale_ptr ? (double)*scale_ptr : 1.0));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// outc: 1x1 conv C -> NC class logits, NHWC T in, NCHW fp32 out.                       UCA:125,162
+// 8 lanes share one pixel (16 B each), shuffle-reduce, then the warp's 32 pixels are written coalesced.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int NC>
+__global__ void __launch_bounds__(kThreads) outc_fwd_kernel(const T* __restrict__ x, int ldx, int C,
+                                                            const float* __restrict__ w, const float* __restrict__ bias,
+                                                            int nc, float* __restrict__ logits, long npix, long HW) {
+    constexpr int VEC = VecTraits<T>::N;
+    extern __shared__ float wsm[];   // [NC][C]
+    for (int i = threadIdx.x; i < NC * C; i += kThreads) wsm[i] = (i / C) < nc ? w[i] : 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
+    const long warp_pix0 = ((long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
+    float keep[NC];
+#pragma unroll
+    for (int o = 0; o < NC; ++o) keep[o] = 0.f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const long p = warp_pix0 + it * 4 + grp;
+        float acc[NC];
+#pragma unroll
+        for (int o = 0; o < NC; ++o) acc[o] = 0.f;
+        if (p < npix) {
+            for (int c0 = sub * VEC; c0 < C; c0 += 8 * VEC) {
+                float v[VEC];
+                load_vec(x + p * ldx + c0, v);
+#pragma unroll
+                for (int o = 0; o < NC; ++o)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) acc[o] = fmaf(v[i], wsm[o * C + c0 + i], acc[o]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < NC; ++o) {
+            float t = acc[o];
+            t += __shfl_xor_sync(0xffffffffu, t, 1);
+            t += __shfl_xor_sync(0xffffffffu, t, 2);
+            t += __shfl_xor_sync(0xffffffffu, t, 4);
+            // lane L finally owns pixel warp_pix0 + L = it*4 + grp  ->  it = L/4, grp = L%4
+            const float got = __shfl_sync(0xffffffffu, t, (lane & 3) * 8);
+            if ((lane >> 2) == it) keep[o] = got;
+        }
+    }
+    const long p = warp_pix0 + lane;
+    if (p < npix) {
+        const long b = p / HW, hw = p % HW;
+#pragma unroll
+        for (int o = 0; o < NC; ++o)
+            if (o < nc) logits[(b * nc + o) * HW + hw] = keep[o] + bias[o];
+    }
+}
+
+// outc backward: g (B,NC,H,W) fp32 = un-normalised dlogits, *gscale = 1/N_valid * upstream grad.
+//   dx[p,c] = gscale * sum_o g[o,p] W[o,c]            (NHWC T)
+//   parts[blk][o][c] = sum_p g[o,p] x[p,c],  parts[blk][NC*C + o] = sum_p g[o,p]   (finalize multiplies by gscale)
+template <typename T, int NC>
+__global__ void __launch_bounds__(kThreads) outc_bwd_kernel(const float* __restrict__ g, const float* __restrict__ gscale,
+                                                            const T* __restrict__ x, int ldx, T* __restrict__ dx, int lddx,
+                                                            int C, const float* __restrict__ w, int nc, long npix, long HW,
+                                                            long chunk, float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > npix) p1 = npix;
+    const float gs = *gscale;
+    float acc[NC][VEC];
+    float accb[NC];
+    float wv[NC][VEC];
+#pragma unroll
+    for (int o = 0; o < NC; ++o) {
+        accb[o] = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { acc[o][i] = 0.f; wv[o][i] = (o < nc && r < rows) ? w[o * C + cv * VEC + i] : 0.f; }
+    }
+    if (r < rows) {
+#pragma unroll 2
+        for (long p = p0 + r; p < p1; p += rows) {
+            const long b = p / HW, hw = p % HW;
+            float gv[NC];
+#pragma unroll
+            for (int o = 0; o < NC; ++o) gv[o] = o < nc ? g[(b * nc + o) * HW + hw] : 0.f;
+            float v[VEC], d[VEC];
+            load_vec(x + p * ldx + cv * VEC, v);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) d[i] = 0.f;
+#pragma unroll
+            for (int o = 0; o < NC; ++o) {
+                if (cv == 0) accb[o] += gv[o];
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    d[i] = fmaf(gv[o], wv[o][i], d[i]);
+                    acc[o][i] = fmaf(gv[o], v[i], acc[o][i]);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) d[i] *= gs;
+            store_vec(dx + p * lddx + cv * VEC, d);
+        }
+    }
+    float* out = parts + (long)blockIdx.x * (NC * C + NC);
+    block_reduce_rows<NC, VEC>(acc, C, vpr, rows, out);
+    // bias partial: only cv == 0 threads hold it
+    __shared__ float bred[kThreads];
+#pragma unroll
+    for (int o = 0; o < NC; ++o) {
+        __syncthreads();
+        bred[threadIdx.x] = (r < rows && cv == 0) ? accb[o] : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int i = 0; i < kThreads; ++i) t += bred[i];
+            out[NC * C + o] = t;
+        }
+    }
+}
+// finalize: dW[o][c] (nc x C) and db[o] from parts laid out with the padded NC
+__global__ void outc_bwd_finalize_kernel(const float* __restrict__ parts, int nparts, int NCpad, int nc, int C,
+                                         const float* __restrict__ gscale, float* __restrict__ dw,
+                                         float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int stride = NCpad * C + NCpad;
+    const double gs = (double)*gscale;
+    if (i < nc * C) {
+        double t = 0.0;
+        for (int p = 0; p < nparts; ++p) t += (double)parts[(long)p * stride + i];
+        dw[i] = (float)(t * gs);
+    } else if (i < nc * C + nc) {
+        const int o = i - nc * C;
+        double t = 0.0;
+        for (int p = 0; p < nparts; ++p) t += (double)parts[(long)p * stride + NCpad * C + o];
+        db[o] = (float)(t * gs);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// softmax cross-entropy, ignore_index, mean over valid pixels.                         UCA:465,344
+//   g[b,o,h,w] = (softmax - onehot) * valid   (un-normalised dlogits, fp32 NCHW)
+//   parts[blk] = {sum of -log p[target] over valid pixels, number of valid pixels}
+// ce_finalize: loss = sum/N (0/0 -> NaN like torch), gscale = upstream/N.
+// Also emits the argmax class map (first maximum wins, UCA:220) when `mask` is non-null.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                                      int nc, long npix, long HW, long long ignore_index,
+                                                      float* __restrict__ g, long long* __restrict__ mask,
+                                                      float* __restrict__ parts) {
+    float lsum = 0.f, lcnt = 0.f;
+    for (long p = (long)blockIdx.x * kThreads + threadIdx.x; p < npix; p += (long)gridDim.x * kThreads) {
+        const long b = p / HW, hw = p % HW;
+        const float* lp = logits + b * nc * HW + hw;
+        float m = lp[0];
+        int am = 0;
+        for (int o = 1; o < nc; ++o) {
+            const float v = lp[o * HW];
+            if (v > m || (v != v && m == m)) { m = v; am = o; }   // first max wins; NaN propagates like torch.max
+        }
+        if (mask) mask[p] = am;
+        if (!target) continue;
+        float se = 0.f;
+        for (int o = 0; o < nc; ++o) se += expf(lp[o * HW] - m);
+        const float lse = m + logf(se);
+        long long t = target[p];
+        const bool valid = t != ignore_index;
+        if (valid && (t < 0 || t >= nc)) { lsum = nanf(""); t = 0; }   // torch asserts here; poison the loss instead
+        if (valid) { lsum += lse - lp[t * HW]; lcnt += 1.f; }
+        if (g) {
+            float* gp = g + b * nc * HW + hw;
+            for (int o = 0; o < nc; ++o) {
+                const float pr = expf(lp[o * HW] - lse);
+                gp[o * HW] = valid ? pr - (o == t ? 1.f : 0.f) : 0.f;
+            }
+        }
+    }
+    __shared__ float rs[kThreads / 32], rc[kThreads / 32];
+    lsum = warp_sum(lsum);
+    lcnt = warp_sum(lcnt);
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = lsum; rc[threadIdx.x >> 5] = lcnt; }
+    __syncthreads();
+    if (threadIdx.x == 0 && parts) {
+        float a = 0.f, c = 0.f;
+        for (int i = 0; i < kThreads / 32; ++i) { a += rs[i]; c += rc[i]; }
+        parts[2 * blockIdx.x] = a;
+        parts[2 * blockIdx.x + 1] = c;
+    }
+}
+__global__ void ce_finalize_kernel(const float* __restrict__ parts, int nparts, const float* __restrict__ upstream,
+                                   float* __restrict__ loss, float* __restrict__ gscale) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double a = 0.0, c = 0.0;
+    for (int i = 0; i < nparts; ++i) { a += (double)parts[2 * i]; c += (double)parts[2 * i + 1]; }
+    const float n = (float)c;
+    loss[0] = (float)a / n;
+    loss[1] = n;
+    gscale[0] = (upstream ? *upstream : 1.f) / n;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// layout conversion at the module boundary and weight packing
+// ---------------------------------------------------------------------------------------------------------
+// im2col of the (B,Cin,H,W) NCHW fp32 network input for the first 3x3 conv: col[p][tap*Cin + c], zero padded to
+// Kpad columns (K = 9*Cin is not a multiple of the MMA K; the padding exists only in this staging buffer).
+template <typename T>
+__global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, T* __restrict__ col, int B, int Cin, int H, int W,
+                                      int Kpad) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)B * H * W * Kpad;
+    if (i >= total) return;
+    const int k = (int)(i % Kpad);
+    const long p = i / Kpad;
+    float v = 0.f;
+    if (k < 9 * Cin) {
+        const int tap = k / Cin, c = k % Cin;
+        const int w = (int)(p % W), h = (int)((p / W) % H);
+        const long b = p / ((long)W * H);
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((b * Cin + c) * H + hh) * W + ww];
+    }
+    col[i] = from_float<T>(v);
+}
+// NCHW fp32 -> NHWC T (generic; used for inputs with Cin a multiple of the vector width and in tests)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int ld, int B, int C, int H, int W) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)B * C * H * W;
+    if (i >= total) return;
+    const int c = (int)(i % C);
+    const long p = i / C;
+    const long hw = p % ((long)H * W), b = p / ((long)H * W);
+    y[p * ld + c] = from_float<T>(x[(b * C + c) * H * W + hw]);
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int ld, float* __restrict__ y, int B, int C, int H, int W) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long total = (long)B * C * H * W;
+    if (i >= total) return;
+    const long hw = i % ((long)H * W);
+    const int c = (int)((i / ((long)H * W)) % C);
+    const long b = i / ((long)H * W * C);
+    y[i] = to_float(x[(b * H * W + hw) * ld + c]);
+}
+// Conv2d weight (O,C,3,3) fp32 -> forward operand [O][ldk] with k = tap*C + c (zero padded), and optionally the
+// dgrad operand [C][9*O] with k = tap'*O + o, tap' = 8 - tap (180-degree rotated filter).
+template <typename T>
+__global__ void pack_conv3x3_kernel(const float* __restrict__ w, T* __restrict__ wf, int ldk, T* __restrict__ wd, int O,
+                                    int C) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)O * ldk) return;
+    const int k = (int)(i % ldk), o = (int)(i / ldk);
+    float v = 0.f;
+    if (k < 9 * C) {
+        const int tap = k / C, c = k % C;
+        v = w[((long)o * C + c) * 9 + tap];
+        if (wd) wd[(long)c * 9 * O + (long)(8 - tap) * O + o] = from_float<T>(v);
+    }
+    wf[i] = from_float<T>(v);
+}
+// ConvTranspose2d weight (Cin,Cout,2,2) fp32 -> forward operand [4*Cout][Cin] (n = (d*2+e)*Cout + o, k = cin) and
+// dgrad operand [Cin][4*Cout] (k = (d*2+e)*Cout + o).
+template <typename T>
+__global__ void pack_convT_kernel(const float* __restrict__ w, T* __restrict__ wf, T* __restrict__ wd, int Cin, int Cout) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)Cin * Cout * 4) return;
+    const int de = (int)(i % 4);
+    const int o = (int)((i / 4) % Cout);
+    const int ci = (int)(i / (4L * Cout));
+    const T v = from_float<T>(w[i]);
+    if (wf) wf[((long)de * Cout + o) * Cin + ci] = v;
+    if (wd) wd[(long)ci * 4 * Cout + (long)de * Cout + o] = v;
+}
+// split-K partial reduction with layout change, fp32 out in the parameter's own layout.
+//  mode 0: ws[s][O][ldn] with n = tap*C + c  ->  dW (O,C,3,3)
+//  mode 1: ws[s][Cin][4*Cout] with n = de*Cout + o -> dW (Cin,Cout,2,2)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int nsplit, long split_stride, int mode, int D0,
+                                    int D1, int ldn, float* __restrict__ dw) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long src;
+    if (mode == 0) {            // D0 = O, D1 = C
+        if (i >= (long)D0 * D1 * 9) return;
+        const int tap = (int)(i % 9), c = (int)((i / 9) % D1), o = (int)(i / (9L * D1));
+        src = (long)o * ldn + (long)tap * D1 + c;
+    } else {                    // D0 = Cin, D1 = Cout
+        if (i >= (long)D0 * D1 * 4) return;
+        const int de = (int)(i % 4), o = (int)((i / 4) % D1), ci = (int)(i / (4L * D1));
+        src = (long)ci * ldn + (long)de * D1 + o;
+    }
+    float t = 0.f;
+    for (int s = 0; s < nsplit; ++s) t += ws[(long)s * split_stride + src];
+    dw[i] = t;
+}
+
+}  // namespace unetca
+
+// =========================================================================================================
+// C ABI
+// =========================================================================================================
+using namespace unetca;
+
+#define DISPATCH_T(dtype, ...)                                                          \
+    do {                                                                                \
+        if ((dtype) == UNETCA_DTYPE_F32) { typedef float T; __VA_ARGS__; }              \
+        else if ((dtype) == UNETCA_DTYPE_BF16) { typedef bf16 T; __VA_ARGS__; }         \
+        else { set_error("bad dtype %d", (int)(dtype)); return UNETCA_ERR_ARG; }        \
+    } while (0)
+
+template <typename T> static bool chan_ok(int C, int ld) {
+    const int V = VecTraits<T>::N;
+    return C > 0 && C % V == 0 && C / V <= kThreads && ld % V == 0 && ld >= C;
+}
+#define REQ_CHAN(C, ld) UNETCA_REQUIRE(chan_ok<T>(C, ld), "%s: C=%d ld=%d unsupported (C must be a multiple of %d, <= %d)", \
+                                       __func__, C, ld, VecTraits<T>::N, kThreads * VecTraits<T>::N)
+
+extern "C" {
+
+// capacity (in partial rows) every `parts` scratch argument must provide for a batch of B images
+int unetca_max_parts(int B) { return kMaxParts + B; }
+
+int unetca_chan_stats(int dtype, const void* y, int ld, int C, long npix, float* parts, int* nparts, void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ld);
+        const long chunk = red_chunk<T>(C, npix);
+        const int nblk = ceil_div(npix, chunk);
+        chan_stats_kernel<T><<<nblk, kThreads, 0, (cudaStream_t)stream>>>((const T*)y, ld, C, npix, chunk, parts);
+        *nparts = nblk;
+    });
+    return check_launch("chan_stats");
+}
+
+int unetca_bn_finalize_train(const float* parts, int nparts, int C, long count, const float* conv_bias,
+                             const float* gamma, const float* beta, float* running_mean, float* running_var,
+                             float momentum, float eps, float* mean, float* invstd, float* scale, float* shift,
+                             void* stream) {
+    UNETCA_REQUIRE(count > 1, "Expected more than 1 value per channel when training, got %ld", count);
+    bn_finalize_train_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+        parts, nparts, C, (double)count, conv_bias, gamma, beta, running_mean, running_var, momentum, eps, mean, invstd,
+        scale, shift);
+    return check_launch("bn_finalize_train");
+}
+
+int unetca_bn_fold_eval(int C, const float* conv_bias, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* scale, float* shift, void* stream) {
+    bn_fold_eval_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(C, conv_bias, gamma, beta, running_mean,
+                                                                           running_var, eps, scale, shift);
+    return check_launch("bn_fold_eval");
+}
+
+// out = relu(scale*y+shift) (out may be null when only the SE squeeze sums are wanted);
+// pool_parts != null: per-image partial sums [B][*nparts][C]
+int unetca_bn_relu(int dtype, const void* y, int ldy, void* out, int ldo, int B, long pix_per_img, int C,
+                   const float* scale, const float* shift, float* pool_parts, int* nparts, void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldy);
+        if (out) REQ_CHAN(C, ldo);
+        const long chunk = pool_parts ? red_chunk<T>(C, pix_per_img * B) : ew_chunk<T>(C, pix_per_img);
+        dim3 grid(ceil_div(pix_per_img, chunk), B);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (out && pool_parts)
+            bn_relu_kernel<T, true, true><<<grid, kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, C, pix_per_img, chunk, scale, shift, pool_parts);
+        else if (out)
+            bn_relu_kernel<T, true, false><<<grid, kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, C, pix_per_img, chunk, scale, shift, nullptr);
+        else if (pool_parts)
+            bn_relu_kernel<T, false, true><<<grid, kThreads, 0, st>>>((const T*)y, ldy, nullptr, 0, C, pix_per_img, chunk, scale, shift, pool_parts);
+        else { set_error("bn_relu: nothing to do"); return UNETCA_ERR_ARG; }
+        if (nparts) *nparts = grid.x;
+    });
+    return check_launch("bn_relu");
+}
+
+int unetca_se_fc(const float* pool_parts, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,
+                 float* p, float* z, float* s, void* stream) {
+    se_fc_kernel<<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_parts, nparts, C, Cr, 1.f / (float)hw,
+                                                                           w1, w2, p, z, s);
+    return check_launch("se_fc");
+}
+
+// o = relu(scale*y+shift) * s[b,c] -> out (stride ldo); pooled/pos non-null: fused MaxPool2d(2)
+int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, void* pooled, int ldp, uint8_t* pos,
+                         int B, int H, int W, int C, const float* scale, const float* shift, const float* s,
+                         void* stream) {
+    UNETCA_REQUIRE(H % 2 == 0 && W % 2 == 0, "se_scale_pool: H, W must be even (got %d x %d)", H, W);
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldy); REQ_CHAN(C, ldo);
+        const long nthr = (long)B * (H / 2) * (W / 2) * (C / VecTraits<T>::N);
+        const int nblk = ceil_div(nthr, kThreads);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (pooled) {
+            REQ_CHAN(C, ldp);
+            se_scale_pool_kernel<T, true><<<nblk, kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, pos, B, H, W, C, scale, shift, s);
+        } else
+            se_scale_pool_kernel<T, false><<<nblk, kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, nullptr, 0, nullptr, B, H, W, C, scale, shift, s);
+    });
+    return check_launch("se_scale_pool");
+}
+
+int unetca_maxpool2x2(int dtype, const void* x, int ldx, void* pooled, int ldp, uint8_t* pos, long long* idx64, int B,
+                      int H, int W, int C, void* stream) {
+    UNETCA_REQUIRE(H >= 2 && W >= 2, "maxpool2x2: input %d x %d too small", H, W);
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldx); REQ_CHAN(C, ldp);
+        const long nthr = (long)B * (H / 2) * (W / 2) * (C / VecTraits<T>::N);
+        maxpool_kernel<T><<<ceil_div(nthr, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const T*)x, ldx, (T*)pooled, ldp, pos, idx64, B, H, W, C);
+    });
+    return check_launch("maxpool2x2");
+}
+
+int unetca_pool_bwd_add(int dtype, const void* skip_grad, int lds, const void* dpooled, int ldp, const uint8_t* pos,
+                        void* dx, int ldx, int B, int H, int W, int C, void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldp); REQ_CHAN(C, ldx);
+        if (skip_grad) REQ_CHAN(C, lds);
+        const long nthr = (long)B * (H / 2) * (W / 2) * (C / VecTraits<T>::N);
+        pool_bwd_add_kernel<T><<<ceil_div(nthr, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const T*)skip_grad, lds, (const T*)dpooled, ldp, pos, (T*)dx, ldx, B, H, W, C);
+    });
+    return check_launch("pool_bwd_add");
+}
+
+int unetca_se_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C,
+                         const float* scale, const float* shift, float* parts, int* nparts, void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
+        const long chunk = red_chunk<T>(C, pix_per_img * B);
+        dim3 grid(ceil_div(pix_per_img, chunk), B);
+        se_bwd_reduce_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)dout, ldd, (const T*)y, ldy, C, pix_per_img, chunk, scale, shift, parts);
+        *nparts = grid.x;
+    });
+    return check_launch("se_bwd_reduce");
+}
+
+int unetca_se_fc_bwd(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2,
+                     const float* p, const float* z, const float* s, float* dpre2, float* dz, float* dp, float* dw1,
+                     float* dw2, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    se_fc_bwd_kernel<<<B, 256, (C + Cr) * sizeof(float), st>>>(parts, nparts, C, Cr, w1, w2, z, s, dpre2, dz, dp);
+    se_fc_wgrad_kernel<<<ceil_div((long)C * Cr, 256), 256, 0, st>>>(B, C, Cr, dpre2, dz, p, z, dw1, dw2);
+    return check_launch("se_fc_bwd");
+}
+
+// stage 1 of ReLU+BN backward (s/dp null: no SE in front).  parts: [B * *nparts][2][C]
+int unetca_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C,
+                         const float* scale, const float* shift, const float* mean, const float* invstd,
+                         const float* s, const float* dp, float* parts, int* nparts, void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
+        const long chunk = red_chunk<T>(C, pix_per_img * B);
+        dim3 grid(ceil_div(pix_per_img, chunk), B);
+        cudaStream_t st = (cudaStream_t)stream;
+        const float ihw = 1.f / (float)pix_per_img;
+        if (s)
+            bn_bwd_kernel<T, true, false><<<grid, kThreads, 0, st>>>((const T*)dout, ldd, (const T*)y, ldy, nullptr, 0, C, pix_per_img, chunk, ihw, scale, shift, mean, invstd, s, dp, nullptr, parts);
+        else
+            bn_bwd_kernel<T, false, false><<<grid, kThreads, 0, st>>>((const T*)dout, ldd, (const T*)y, ldy, nullptr, 0, C, pix_per_img, chunk, ihw, scale, shift, mean, invstd, nullptr, nullptr, nullptr, parts);
+        *nparts = grid.x * B;
+    });
+    return check_launch("bn_bwd_reduce");
+}
+
+int unetca_bn_bwd_finalize(const float* parts, int nparts, int C, long count, const float* gamma, const float* invstd,
+                           float* dgamma, float* dbeta, float* coef, void* stream) {
+    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(parts, nparts, C, (double)count, gamma,
+                                                                             invstd, dgamma, dbeta, coef);
+    return check_launch("bn_bwd_finalize");
+}
+
+int unetca_bn_bwd_apply(int dtype, const void* dout, int ldd, const void* y, int ldy, void* dy, int lddy, int B,
+                        long pix_per_img, int C, const float* scale, const float* shift, const float* mean,
+                        const float* invstd, const float* s, const float* dp, const float* coef, void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldd); REQ_CHAN(C, ldy); REQ_CHAN(C, lddy);
+        const long chunk = ew_chunk<T>(C, pix_per_img);
+        dim3 grid(ceil_div(pix_per_img, chunk), B);
+        cudaStream_t st = (cudaStream_t)stream;
+        const float ihw = 1.f / (float)pix_per_img;
+        if (s)
+            bn_bwd_kernel<T, true, true><<<grid, kThreads, 0, st>>>((const T*)dout, ldd, (const T*)y, ldy, (T*)dy, lddy, C, pix_per_img, chunk, ihw, scale, shift, mean, invstd, s, dp, coef, nullptr);
+        else
+            bn_bwd_kernel<T, false, true><<<grid, kThreads, 0, st>>>((const T*)dout, ldd, (const T*)y, ldy, (T*)dy, lddy, C, pix_per_img, chunk, ihw, scale, shift, mean, invstd, nullptr, nullptr, coef, nullptr);
+    });
+    return check_launch("bn_bwd_apply");
+}
+
+// out[c] = sum over pixels of x[p][c]  (parts scratch: unetca_max_parts()*C floats)
+int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* parts, float* out, void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ld);
+        const long chunk = red_chunk<T>(C, npix);
+        const int nblk = ceil_div(npix, chunk);
+        cudaStream_t st = (cudaStream_t)stream;
+        chan_sum_kernel<T><<<nblk, kThreads, 0, st>>>((const T*)x, ld, C, npix, chunk, parts);
+        sum_parts_kernel<<<ceil_div(C, 128), 128, 0, st>>>(parts, nblk, C, nullptr, out);
+    });
+    return check_launch("chan_sum");
+}
+
+static int nc_pad(int nc) { return nc <= 2 ? 2 : nc <= 4 ? 4 : 8; }
+
+int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, const float* bias, int nc, float* logits,
+                    int B, long HW, void* stream) {
+    UNETCA_REQUIRE(nc >= 1 && nc <= 8, "outc: num_classes %d unsupported (1..8)", nc);
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldx);
+        const long npix = (long)B * HW;
+        const int nblk = ceil_div(npix, kThreads);
+        cudaStream_t st = (cudaStream_t)stream;
+        const int ncp = nc_pad(nc);
+        const size_t sm = (size_t)ncp * C * sizeof(float);
+        if (ncp == 2) outc_fwd_kernel<T, 2><<<nblk, kThreads, sm, st>>>((const T*)x, ldx, C, w, bias, nc, logits, npix, HW);
+        else if (ncp == 4) outc_fwd_kernel<T, 4><<<nblk, kThreads, sm, st>>>((const T*)x, ldx, C, w, bias, nc, logits, npix, HW);
+        else outc_fwd_kernel<T, 8><<<nblk, kThreads, sm, st>>>((const T*)x, ldx, C, w, bias, nc, logits, npix, HW);
+    });
+    return check_launch("outc_fwd");
+}
+
+// parts scratch: unetca_max_parts() * (8*C + 8) floats
+int unetca_outc_bwd(int dtype, const float* g, const float* gscale, const void* x, int ldx, void* dx, int lddx, int C,
+                    const float* w, int nc, int B, long HW, float* parts, float* dw, float* db, void* stream) {
+    UNETCA_REQUIRE(nc >= 1 && nc <= 8, "outc: num_classes %d unsupported (1..8)", nc);
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldx); REQ_CHAN(C, lddx);
+        const long npix = (long)B * HW;
+        const long chunk = red_chunk<T>(C, npix);
+        const int nblk = ceil_div(npix, chunk);
+        cudaStream_t st = (cudaStream_t)stream;
+        const int ncp = nc_pad(nc);
+        if (ncp == 2) outc_bwd_kernel<T, 2><<<nblk, kThreads, 0, st>>>(g, gscale, (const T*)x, ldx, (T*)dx, lddx, C, w, nc, npix, HW, chunk, parts);
+        else if (ncp == 4) outc_bwd_kernel<T, 4><<<nblk, kThreads, 0, st>>>(g, gscale, (const T*)x, ldx, (T*)dx, lddx, C, w, nc, npix, HW, chunk, parts);
+        else outc_bwd_kernel<T, 8><<<nblk, kThreads, 0, st>>>(g, gscale, (const T*)x, ldx, (T*)dx, lddx, C, w, nc, npix, HW, chunk, parts);
+        outc_bwd_finalize_kernel<<<ceil_div(nc * C + nc, 128), 128, 0, st>>>(parts, nblk, ncp, nc, C, gscale, dw, db);
+    });
+    return check_launch("outc_bwd");
+}
+
+// loss_out[0] = mean CE over valid pixels, loss_out[1] = number of valid pixels; gscale_out[0] = upstream / N.
+// g (un-normalised dlogits), mask (argmax), target may each be null.  parts scratch: 2*unetca_max_parts() floats.
+int unetca_cross_entropy(const float* logits, const long long* target, int nc, int B, long HW, long long ignore_index,
+                         const float* upstream, float* g, long long* mask, float* parts, float* loss_out,
+                         float* gscale_out, void* stream) {
+    const long npix = (long)B * HW;
+    int nblk = ceil_div(npix, kThreads * 4);
+    if (nblk > kMaxParts) nblk = kMaxParts;
+    if (nblk < 1) nblk = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    ce_kernel<<<nblk, kThreads, 0, st>>>(logits, target, nc, npix, HW, ignore_index, g, mask, parts);
+    if (target && loss_out) ce_finalize_kernel<<<1, 32, 0, st>>>(parts, nblk, upstream, loss_out, gscale_out);
+    return check_launch("cross_entropy");
+}
+
+int unetca_im2col3x3_nchw(int dtype, const float* x, void* col, int B, int Cin, int H, int W, int Kpad, void* stream) {
+    UNETCA_REQUIRE(Kpad >= 9 * Cin, "im2col: Kpad %d < 9*Cin", Kpad);
+    DISPATCH_T(dtype, {
+        const long total = (long)B * H * W * Kpad;
+        im2col3x3_nchw_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)col, B, Cin, H, W, Kpad);
+    });
+    return check_launch("im2col3x3_nchw");
+}
+int unetca_nchw_to_nhwc(int dtype, const float* x, void* y, int ld, int B, int C, int H, int W, void* stream) {
+    DISPATCH_T(dtype, {
+        const long total = (long)B * C * H * W;
+        nchw_to_nhwc_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)y, ld, B, C, H, W);
+    });
+    return check_launch("nchw_to_nhwc");
+}
+int unetca_nhwc_to_nchw(int dtype, const void* x, int ld, float* y, int B, int C, int H, int W, void* stream) {
+    DISPATCH_T(dtype, {
+        const long total = (long)B * C * H * W;
+        nhwc_to_nchw_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, ld, y, B, C, H, W);
+    });
+    return check_launch("nhwc_to_nchw");
+}
+int unetca_pack_conv3x3_weight(int dtype, const float* w, void* wf, int ldk, void* wd, int O, int C, void* stream) {
+    UNETCA_REQUIRE(ldk >= 9 * C, "pack_conv3x3: ldk %d < 9*C", ldk);
+    DISPATCH_T(dtype, {
+        const long total = (long)O * ldk;
+        pack_conv3x3_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, ldk, (T*)wd, O, C);
+    });
+    return check_launch("pack_conv3x3_weight");
+}
+int unetca_pack_convT_weight(int dtype, const float* w, void* wf, void* wd, int Cin, int Cout, void* stream) {
+    DISPATCH_T(dtype, {
+        const long total = (long)Cin * Cout * 4;
+        pack_convT_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, (T*)wd, Cin, Cout);
+    });
+    return check_launch("pack_convT_weight");
+}
+int unetca_wgrad_reduce(const float* ws, int nsplit, long split_stride, int mode, int D0, int D1, int ldn, float* dw,
+                        void* stream) {
+    const long total = (long)D0 * D1 * (mode == 0 ? 9 : 4);
+    wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(ws, nsplit, split_stride, mode, D0, D1,
+                                                                               ldn, dw);
+    return check_launch("wgrad_reduce");
+}
+
+}  // extern "C"

@@ -1,0 +1,575 @@
+"""Drop-in `UNet` / `DoubleConv` / `SELayer` for the reference's U-Net-CA (Unet-ChannalAttention.py:45-163).
+
+Same constructor signatures, same attribute tree and therefore the same 154 (136 without SE) `state_dict` keys and
+OIHW fp32 parameter layout as the reference, same NCHW float input -> NCHW float class-logit output, same
+train()/eval() BatchNorm semantics.  The child modules (nn.Conv2d, nn.BatchNorm2d, ...) are only parameter
+containers: `UNet.forward` never calls them.  Forward and backward run as hand-written sm_100a CUDA kernels behind
+the C ABI in include/unetca_b200.h (NHWC activations; tcgen05 implicit-GEMM convolutions in bf16 mode, FFMA in fp32
+parity mode), driven by one `torch.autograd.Function`.  PyTorch only owns memory and the stream.
+
+There is no CPU path and no ATen fallback: CPU tensors, a missing shared library or an unsupported shape raise.
+
+Extra, beyond the reference API:
+  * `model.precision` / `model.set_precision('bf16' | 'fp32')` — storage type of activations and contraction
+    operands ('fp32' is the bit-exact-mask parity mode);
+  * `model.loss(images, masks, ignore_index=255)` — fused forward + softmax cross-entropy (UCA:343-344); the
+    logits of that call stay available as `model.last_logits`;
+  * `model.predict_mask(images)` — argmax class map of UCA:220.
+"""
+from __future__ import annotations
+
+import ctypes
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_WIDTHS = (64, 128, 256, 512, 1024)
+_WS_FLOATS = 48 * 1024 * 1024          # split-K scratch for the weight gradients (192 MB)
+
+
+class SELayer(nn.Module):
+    """Squeeze-and-excitation channel attention; parameters as in the reference (UCA:45-59)."""
+
+    def __init__(self, channel: int, reduction: int = 16):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(
+            nn.Linear(channel, channel // reduction, bias=False),
+            nn.ReLU(inplace=True),
+            nn.Linear(channel // reduction, channel, bias=False),
+            nn.Sigmoid(),
+        )
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        raise RuntimeError("unetca_b200.SELayer is a parameter container of UNet; its arithmetic runs fused inside "
+                           "UNet.forward (kernels unetca_bn_relu / unetca_se_fc / unetca_se_scale_pool)")
+
+
+class DoubleConv(nn.Module):
+    """(conv3x3 -> BN -> ReLU) x 2 [-> SE]; parameters as in the reference (UCA:75-94)."""
+
+    def __init__(self, in_channels: int, out_channels: int, use_se: bool = False):
+        super().__init__()
+        layers = [
+            nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+            nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1),
+            nn.BatchNorm2d(out_channels),
+            nn.ReLU(inplace=True),
+        ]
+        if use_se:
+            layers.append(SELayer(out_channels))
+        self.double_conv = nn.Sequential(*layers)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        raise RuntimeError("unetca_b200.DoubleConv is a parameter container of UNet; its arithmetic runs inside "
+                           "UNet.forward")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Block:
+    """Static description of one DoubleConv: where its parameters live and its shapes."""
+
+    def __init__(self, name, mod: DoubleConv, cin, cout, level, first=False):
+        self.name = name
+        seq = mod.double_conv
+        self.conv1, self.bn1, self.conv2, self.bn2 = seq[0], seq[1], seq[3], seq[4]
+        self.se = seq[6] if len(seq) > 6 else None
+        self.cin, self.cout, self.level, self.first = cin, cout, level, first
+        self.prefix = name
+
+
+class _Engine:
+    """Per-model execution state: packed operand copies of the weights and scratch buffers."""
+
+    def __init__(self, model: "UNet"):
+        self.model = model
+        self._packed = {}
+        self._scratch = {}
+
+    # ---- scratch -------------------------------------------------------------------------------------
+    def scratch(self, key, numel, dtype, device):
+        t = self._scratch.get(key)
+        if t is None or t.numel() < numel or t.device != device or t.dtype != dtype:
+            t = torch.empty(numel, dtype=dtype, device=device)
+            self._scratch[key] = t
+        return t
+
+    def parts(self, B, device):
+        rows = _lib.load().unetca_max_parts(B)
+        return self.scratch("parts", rows * 2 * 1024, torch.float32, device)
+
+    def ws(self, device):
+        return self.scratch("ws", _WS_FLOATS, torch.float32, device)
+
+    # ---- packed weights ------------------------------------------------------------------------------
+    def _cached(self, key, param, tdt, build):
+        ent = self._packed.get(key)
+        ver = (param._version, param.data_ptr(), tdt)
+        if ent is None or ent[0] != ver:
+            ent = (ver, build())
+            self._packed[key] = ent
+        return ent[1]
+
+    def conv_w(self, conv: nn.Conv2d, dt, tdt, first):
+        w = conv.weight
+        O, C = w.shape[0], w.shape[1]
+
+        def build():
+            ldk = ((9 * C + 63) // 64) * 64 if first else 9 * C
+            wf = torch.empty(O, ldk, dtype=tdt, device=w.device)
+            wd = None if first else torch.empty(C, 9 * O, dtype=tdt, device=w.device)
+            _lib.call("unetca_pack_conv3x3_weight", dt, _ptr(w), _ptr(wf), ldk, _ptr(wd), O, C, _stream())
+            return wf, wd, ldk
+        return self._cached(("c", id(conv)), w, tdt, build)
+
+    def convT_w(self, up: nn.ConvTranspose2d, dt, tdt):
+        w = up.weight
+        Cin, Cout = w.shape[0], w.shape[1]
+
+        def build():
+            wf = torch.empty(4 * Cout, Cin, dtype=tdt, device=w.device)
+            wd = torch.empty(Cin, 4 * Cout, dtype=tdt, device=w.device)
+            _lib.call("unetca_pack_convT_weight", dt, _ptr(w), _ptr(wf), _ptr(wd), Cin, Cout, _stream())
+            return wf, wd
+        return self._cached(("t", id(up)), w, tdt, build)
+
+
+def _check_input(model, x):
+    if not isinstance(x, torch.Tensor) or x.dim() != 4:
+        raise ValueError("UNet expects a 4-D (B, C, H, W) tensor")
+    if not x.is_cuda:
+        raise RuntimeError("unetca_b200.UNet runs only on CUDA tensors (sm_100a); there is no CPU fallback")
+    if x.shape[1] != model.in_channels:
+        raise RuntimeError(f"expected input with {model.in_channels} channels, got {x.shape[1]}")
+    H, W = x.shape[2], x.shape[3]
+    if H % 16 or W % 16:
+        raise NotImplementedError(
+            f"input {H}x{W}: H and W must be multiples of 16; the reference's bilinear resize guard "
+            "(Unet-ChannalAttention.py:138-157) is not implemented on the CUDA path")
+    if x.requires_grad:
+        raise NotImplementedError("gradient w.r.t. the input image is not implemented (the reference never needs it)")
+
+
+# =======================================================================================================
+# forward
+# =======================================================================================================
+def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train, dt, tdt, keep):
+    """One DoubleConv (+SE, + the following MaxPool when `pooled` is given).  Returns what backward needs."""
+    dev = out_view.device
+    st = _stream()
+    C, O = blk.cin, blk.cout
+    npix = B * Hl * Wl
+    parts = eng.parts(B, dev)
+    nparts = ctypes.c_int(0)
+    sv = SimpleNamespace(blk=blk, xin=xin if keep else None, col=col if keep else None, B=B, H=Hl, W=Wl)
+
+    def bn_params(bn, conv, tag):
+        mean = torch.empty(O, dtype=torch.float32, device=dev)
+        invstd = torch.empty_like(mean)
+        scale = torch.empty_like(mean)
+        shift = torch.empty_like(mean)
+        if train:
+            _lib.call("unetca_bn_finalize_train", _ptr(parts), nparts.value, O, npix, _ptr(conv.bias), _ptr(bn.weight),
+                      _ptr(bn.bias), _ptr(bn.running_mean), _ptr(bn.running_var), float(bn.momentum), float(bn.eps),
+                      _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), st)
+            bn.num_batches_tracked += 1
+        else:
+            _lib.call("unetca_bn_fold_eval", O, _ptr(conv.bias), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean),
+                      _ptr(bn.running_var), float(bn.eps), _ptr(scale), _ptr(shift), st)
+        setattr(sv, "mean" + tag, mean); setattr(sv, "invstd" + tag, invstd)
+        setattr(sv, "scale" + tag, scale); setattr(sv, "shift" + tag, shift)
+        return scale, shift
+
+    sp = _ptr(parts) if train else None
+    # ---- conv1 -> BN -> ReLU
+    wf1, _, ldk1 = eng.conv_w(blk.conv1, dt, tdt, blk.first)
+    y1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
+    if blk.first:
+        _lib.call("unetca_gemm_nt", dt, _ptr(col), col.shape[1], _ptr(wf1), ldk1, _ptr(y1), O, npix, O, col.shape[1],
+                  sp, ctypes.byref(nparts), st)
+    else:
+        _lib.call("unetca_conv3x3_fwd", dt, _ptr(xin), xin.stride(2), _ptr(wf1), ldk1, _ptr(y1), O, B, Hl, Wl, C, O,
+                  sp, ctypes.byref(nparts), st)
+    scale1, shift1 = bn_params(blk.bn1, blk.conv1, "1")
+    a1 = torch.empty_like(y1)
+    _lib.call("unetca_bn_relu", dt, _ptr(y1), O, _ptr(a1), O, B, Hl * Wl, O, _ptr(scale1), _ptr(shift1), None, None, st)
+    # ---- conv2 -> BN -> ReLU [-> SE] [-> MaxPool]
+    wf2, _, ldk2 = eng.conv_w(blk.conv2, dt, tdt, False)
+    y2 = torch.empty_like(y1)
+    _lib.call("unetca_conv3x3_fwd", dt, _ptr(a1), O, _ptr(wf2), ldk2, _ptr(y2), O, B, Hl, Wl, O, O, sp,
+              ctypes.byref(nparts), st)
+    scale2, shift2 = bn_params(blk.bn2, blk.conv2, "2")
+    s = None
+    if blk.se is not None:
+        w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
+        Cr = w1.shape[0]
+        _lib.call("unetca_bn_relu", dt, _ptr(y2), O, None, 0, B, Hl * Wl, O, _ptr(scale2), _ptr(shift2), _ptr(parts),
+                  ctypes.byref(nparts), st)
+        p = torch.empty(B, O, dtype=torch.float32, device=dev)
+        z = torch.empty(B, Cr, dtype=torch.float32, device=dev)
+        s = torch.empty(B, O, dtype=torch.float32, device=dev)
+        _lib.call("unetca_se_fc", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(p), _ptr(z),
+                  _ptr(s), st)
+        sv.p, sv.z, sv.s = p, z, s
+    _lib.call("unetca_se_scale_pool", dt, _ptr(y2), O, _ptr(out_view), out_view.stride(2), _ptr(pooled),
+              pooled.stride(2) if pooled is not None else 0, _ptr(pos), B, Hl, Wl, O, _ptr(scale2), _ptr(shift2),
+              _ptr(s), st)
+    if keep:
+        sv.y1, sv.a1, sv.y2 = y1, a1, y2
+    return sv
+
+
+def _forward(model: "UNet", x: torch.Tensor, keep: bool):
+    """UNet.forward (UCA:127-163).  Returns (logits NCHW fp32, saved-state or None)."""
+    _check_input(model, x)
+    eng = model._engine()
+    dt, tdt = model._dt()
+    train = model.training
+    dev = x.device
+    st = _stream()
+    B, Cin, H, W = x.shape
+    if train and B * (H // 16) * (W // 16) <= 1:
+        raise ValueError(f"Expected more than 1 value per channel when training, got input size "
+                         f"{[B, 1024, H // 16, W // 16]}")
+    xf = x.detach()
+    if xf.dtype != torch.float32 or not xf.is_contiguous():
+        xf = xf.float().contiguous()
+    Kpad = ((9 * Cin + 63) // 64) * 64
+    col = torch.empty(B * H * W, Kpad, dtype=tdt, device=dev)
+    _lib.call("unetca_im2col3x3_nchw", dt, _ptr(xf), _ptr(col), B, Cin, H, W, Kpad, st)
+
+    sv = SimpleNamespace(enc=[], dec=[], up_in=[], cat=[], pos=[], B=B, H=H, W=W)
+    cat = [torch.empty(B, H >> l, W >> l, 2 * _WIDTHS[l], dtype=tdt, device=dev) for l in range(4)]
+    # ---- encoder
+    xin = None
+    for l, blk in enumerate(model._enc_blocks):
+        Hl, Wl, Cl = H >> l, W >> l, _WIDTHS[l]
+        if l < 4:
+            out_view = cat[l][..., :Cl]
+            pooled = torch.empty(B, Hl // 2, Wl // 2, Cl, dtype=tdt, device=dev)
+            pos = torch.empty(B, Hl // 2, Wl // 2, Cl, dtype=torch.uint8, device=dev)
+        else:
+            out_view = torch.empty(B, Hl, Wl, Cl, dtype=tdt, device=dev)
+            pooled = pos = None
+        s = _double_conv_fwd(eng, blk, xin, col if l == 0 else None, B, Hl, Wl, out_view, pooled, pos, train, dt, tdt,
+                             keep)
+        sv.enc.append(s)
+        sv.pos.append(pos)
+        xin = pooled if l < 4 else out_view
+    # ---- decoder
+    h = xin
+    for i, (up, blk) in enumerate(zip(model._ups, model._dec_blocks)):
+        l = 3 - i
+        Hl, Wl, Cl = H >> l, W >> l, _WIDTHS[l]
+        wf, _ = eng.convT_w(up, dt, tdt)
+        _lib.call("unetca_convT2x2_fwd", dt, _ptr(h), h.stride(2), _ptr(wf), _ptr(up.bias), _ptr(cat[l][..., Cl:]),
+                  2 * Cl, B, Hl // 2, Wl // 2, 2 * Cl, Cl, st)
+        sv.up_in.append(h if keep else None)
+        out = torch.empty(B, Hl, Wl, Cl, dtype=tdt, device=dev)
+        s = _double_conv_fwd(eng, blk, cat[l], None, B, Hl, Wl, out, None, None, train, dt, tdt, keep)
+        sv.dec.append(s)
+        h = out
+    # ---- outc
+    nc = model.num_classes
+    logits = torch.empty(B, nc, H, W, dtype=torch.float32, device=dev)
+    _lib.call("unetca_outc_fwd", dt, _ptr(h), h.stride(2), 64, _ptr(model.outc.weight), _ptr(model.outc.bias), nc,
+              _ptr(logits), B, H * W, st)
+    if not keep:
+        return logits, None
+    sv.cat = cat
+    sv.dec_out = h
+    return logits, sv
+
+
+# =======================================================================================================
+# backward
+# =======================================================================================================
+def _double_conv_bwd(eng, sv, dout, grads, dt, tdt, need_dx):
+    """Gradient of one DoubleConv block; dout is d(loss)/d(block output) (NHWC view).  Returns d/d(block input)."""
+    blk = sv.blk
+    B, Hl, Wl = sv.B, sv.H, sv.W
+    C, O = blk.cin, blk.cout
+    dev = dout.device
+    st = _stream()
+    npix = B * Hl * Wl
+    parts = eng.parts(B, dev)
+    ws = eng.ws(dev)
+    nparts = ctypes.c_int(0)
+    pre = blk.prefix
+    s = dp = None
+    if blk.se is not None:
+        w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
+        Cr = w1.shape[0]
+        _lib.call("unetca_se_bwd_reduce", dt, _ptr(dout), dout.stride(2), _ptr(sv.y2), O, B, Hl * Wl, O, _ptr(sv.scale2),
+                  _ptr(sv.shift2), _ptr(parts), ctypes.byref(nparts), st)
+        dpre2 = torch.empty(B, O, dtype=torch.float32, device=dev)
+        dz = torch.empty(B, Cr, dtype=torch.float32, device=dev)
+        dp = torch.empty(B, O, dtype=torch.float32, device=dev)
+        dw1 = torch.empty_like(w1)
+        dw2 = torch.empty_like(w2)
+        _lib.call("unetca_se_fc_bwd", _ptr(parts), nparts.value, B, O, Cr, _ptr(w1), _ptr(w2), _ptr(sv.p), _ptr(sv.z),
+                  _ptr(sv.s), _ptr(dpre2), _ptr(dz), _ptr(dp), _ptr(dw1), _ptr(dw2), st)
+        grads[pre + ".6.fc.0.weight"] = dw1
+        grads[pre + ".6.fc.2.weight"] = dw2
+        s = sv.s
+
+    def bn_relu_bwd(d_in, ld_in, y, tag, s_, dp_, bn_idx):
+        scale, shift = getattr(sv, "scale" + tag), getattr(sv, "shift" + tag)
+        mean, invstd = getattr(sv, "mean" + tag), getattr(sv, "invstd" + tag)
+        bn = blk.bn1 if tag == "1" else blk.bn2
+        _lib.call("unetca_bn_bwd_reduce", dt, _ptr(d_in), ld_in, _ptr(y), O, B, Hl * Wl, O, _ptr(scale), _ptr(shift),
+                  _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(parts), ctypes.byref(nparts), st)
+        dgamma = torch.empty(O, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(O, dtype=torch.float32, device=dev)
+        coef = torch.empty(3, O, dtype=torch.float32, device=dev)
+        _lib.call("unetca_bn_bwd_finalize", _ptr(parts), nparts.value, O, npix, _ptr(bn.weight), _ptr(invstd),
+                  _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
+        dy = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
+        _lib.call("unetca_bn_bwd_apply", dt, _ptr(d_in), ld_in, _ptr(y), O, _ptr(dy), O, B, Hl * Wl, O, _ptr(scale),
+                  _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(coef), st)
+        grads[f"{pre}.{bn_idx}.weight"] = dgamma
+        grads[f"{pre}.{bn_idx}.bias"] = dbeta
+        return dy
+
+    # ---- [SE ->] ReLU -> BN2 backward
+    dy2 = bn_relu_bwd(dout, dout.stride(2), sv.y2, "2", s, dp, 4)
+    # a conv bias in front of a train-mode BatchNorm has an analytically zero gradient (BN removes the mean)
+    grads[pre + ".3.bias"] = torch.zeros(O, dtype=torch.float32, device=dev)
+    grads[pre + ".0.bias"] = torch.zeros(O, dtype=torch.float32, device=dev)
+    # ---- conv2 wgrad + dgrad
+    dw = torch.empty_like(blk.conv2.weight)
+    _lib.call("unetca_conv3x3_wgrad", dt, _ptr(dy2), O, _ptr(sv.a1), O, _ptr(ws), ws.numel(), B, Hl, Wl, O, O, _ptr(dw), st)
+    grads[pre + ".3.weight"] = dw
+    _, wd2, _ = eng.conv_w(blk.conv2, dt, tdt, False)
+    da1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
+    _lib.call("unetca_conv3x3_fwd", dt, _ptr(dy2), O, _ptr(wd2), 9 * O, _ptr(da1), O, B, Hl, Wl, O, O, None, None, st)
+    del dy2
+    # ---- ReLU -> BN1 backward
+    dy1 = bn_relu_bwd(da1, O, sv.y1, "1", None, None, 1)
+    del da1
+    # ---- conv1 wgrad (+ dgrad)
+    dw = torch.empty_like(blk.conv1.weight)
+    if blk.first:
+        _lib.call("unetca_im2col_wgrad", dt, _ptr(dy1), O, _ptr(sv.col), sv.col.shape[1], _ptr(ws), ws.numel(), npix, C, O,
+                  _ptr(dw), st)
+    else:
+        _lib.call("unetca_conv3x3_wgrad", dt, _ptr(dy1), O, _ptr(sv.xin), sv.xin.stride(2), _ptr(ws), ws.numel(), B, Hl,
+                  Wl, C, O, _ptr(dw), st)
+    grads[pre + ".0.weight"] = dw
+    if not need_dx or blk.first:
+        return None
+    _, wd1, _ = eng.conv_w(blk.conv1, dt, tdt, False)
+    dx = torch.empty(B, Hl, Wl, C, dtype=tdt, device=dev)
+    _lib.call("unetca_conv3x3_fwd", dt, _ptr(dy1), O, _ptr(wd1), 9 * O, _ptr(dx), C, B, Hl, Wl, O, C, None, None, st)
+    return dx
+
+
+def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
+    """loss.backward() (UCA:345) for every parameter.  g: (B,nc,H,W) fp32 dlogits up to the factor *gscale."""
+    eng = model._engine()
+    dt, tdt = model._dt()
+    dev = g.device
+    st = _stream()
+    B, H, W = sv.B, sv.H, sv.W
+    grads = {}
+    nc = model.num_classes
+    parts = eng.parts(B, dev)
+    ws = eng.ws(dev)
+    # ---- outc
+    h = sv.dec_out
+    dcur = torch.empty(B, H, W, 64, dtype=tdt, device=dev)
+    dw = torch.empty_like(model.outc.weight)
+    db = torch.empty_like(model.outc.bias)
+    _lib.call("unetca_outc_bwd", dt, _ptr(g), _ptr(gscale), _ptr(h), h.stride(2), _ptr(dcur), 64, 64,
+              _ptr(model.outc.weight), nc, B, H * W, _ptr(parts), _ptr(dw), _ptr(db), st)
+    grads["outc.weight"], grads["outc.bias"] = dw, db
+    # ---- decoder, shallow to deep
+    skip_grads = [None] * 4
+    for l in range(4):
+        i = 3 - l
+        up, name = model._ups[i], model._up_names[i]
+        Hl, Wl, Cl = H >> l, W >> l, _WIDTHS[l]
+        dcat = _double_conv_bwd(eng, sv.dec[i], dcur, grads, dt, tdt, True)      # (B,Hl,Wl,2Cl)
+        du = dcat[..., Cl:]
+        skip_grads[l] = dcat[..., :Cl]
+        dbias = torch.empty_like(up.bias)
+        _lib.call("unetca_chan_sum", dt, _ptr(du), 2 * Cl, Cl, B * Hl * Wl, _ptr(parts), _ptr(dbias), st)
+        grads[name + ".bias"] = dbias
+        up_in = sv.up_in[i]
+        dwu = torch.empty_like(up.weight)
+        _lib.call("unetca_convT2x2_wgrad", dt, _ptr(up_in), up_in.stride(2), _ptr(du), 2 * Cl, _ptr(ws), ws.numel(), B,
+                  Hl // 2, Wl // 2, 2 * Cl, Cl, _ptr(dwu), st)
+        grads[name + ".weight"] = dwu
+        _, wd = eng.convT_w(up, dt, tdt)
+        dcur = torch.empty(B, Hl // 2, Wl // 2, 2 * Cl, dtype=tdt, device=dev)
+        _lib.call("unetca_convT2x2_dgrad", dt, _ptr(du), 2 * Cl, _ptr(wd), _ptr(dcur), 2 * Cl, B, Hl // 2, Wl // 2, 2 * Cl,
+                  Cl, st)
+    # ---- encoder, deep to shallow
+    for l in range(4, -1, -1):
+        dpooled = _double_conv_bwd(eng, sv.enc[l], dcur, grads, dt, tdt, l > 0)
+        if l == 0:
+            break
+        Hp, Wp, Cp = H >> (l - 1), W >> (l - 1), _WIDTHS[l - 1]
+        dcur = torch.empty(B, Hp, Wp, Cp, dtype=tdt, device=dev)
+        sg = skip_grads[l - 1]
+        _lib.call("unetca_pool_bwd_add", dt, _ptr(sg), sg.stride(2), _ptr(dpooled), Cp, _ptr(sv.pos[l - 1]), _ptr(dcur),
+                  Cp, B, Hp, Wp, Cp, st)
+    return grads
+
+
+class _UNetFn(torch.autograd.Function):
+    """logits = UNet(x); backward receives dlogits from whatever criterion follows (UCA:343-345)."""
+
+    @staticmethod
+    def forward(ctx, model, x, keep, *params):
+        logits, sv = _forward(model, x, keep)
+        ctx.model, ctx.sv = model, sv
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model, sv = ctx.model, ctx.sv
+        if sv is None:
+            raise RuntimeError("backward through a forward that ran without grad")
+        g = dlogits.contiguous().float()
+        one = torch.ones(1, dtype=torch.float32, device=g.device)
+        grads = _backward(model, sv, g, one)
+        ctx.sv = None
+        return (None, None, None) + tuple(grads[n] for n in model._param_names)
+
+
+class _UNetLossFn(torch.autograd.Function):
+    """Fused model + nn.CrossEntropyLoss(ignore_index) (UCA:343-344, 465)."""
+
+    @staticmethod
+    def forward(ctx, model, x, target, ignore_index, keep, *params):
+        logits, sv = _forward(model, x, keep)
+        B, nc, H, W = logits.shape
+        dev = logits.device
+        if target.shape != (B, H, W) or target.dtype != torch.int64 or not target.is_cuda:
+            raise ValueError(f"target must be a CUDA int64 tensor of shape {(B, H, W)}")
+        target = target.contiguous()
+        eng = model._engine()
+        parts = eng.parts(B, dev)
+        g = torch.empty_like(logits) if keep else None
+        out = torch.empty(2, dtype=torch.float32, device=dev)
+        gscale = torch.empty(1, dtype=torch.float32, device=dev)
+        _lib.call("unetca_cross_entropy", _ptr(logits), _ptr(target), nc, B, H * W, int(ignore_index), None, _ptr(g),
+                  None, _ptr(parts), _ptr(out), _ptr(gscale), _stream())
+        model.last_logits = logits
+        ctx.model, ctx.sv, ctx.g, ctx.gscale = model, sv, g, gscale
+        return out[0].clone()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        model, sv = ctx.model, ctx.sv
+        if sv is None:
+            raise RuntimeError("backward through a forward that ran without grad")
+        gscale = ctx.gscale * dloss.reshape(1).float()
+        grads = _backward(model, sv, ctx.g, gscale)
+        ctx.sv = ctx.g = None
+        return (None, None, None, None, None) + tuple(grads[n] for n in model._param_names)
+
+
+class UNet(nn.Module):
+    """U-Net with optional channel attention; constructor and attribute tree of the reference (UCA:100-125)."""
+
+    def __init__(self, in_channels: int = 1, num_classes: int = 2, use_se: bool = False):
+        super().__init__()
+        self.inc = DoubleConv(in_channels, 64, use_se=use_se)
+        self.down1 = nn.Sequential(nn.MaxPool2d(2), DoubleConv(64, 128, use_se=use_se))
+        self.down2 = nn.Sequential(nn.MaxPool2d(2), DoubleConv(128, 256, use_se=use_se))
+        self.down3 = nn.Sequential(nn.MaxPool2d(2), DoubleConv(256, 512, use_se=use_se))
+        self.down4 = nn.Sequential(nn.MaxPool2d(2), DoubleConv(512, 1024, use_se=use_se))
+        self.up1 = nn.ConvTranspose2d(1024, 512, kernel_size=2, stride=2)
+        self.conv1 = DoubleConv(1024, 512, use_se=use_se)
+        self.up2 = nn.ConvTranspose2d(512, 256, kernel_size=2, stride=2)
+        self.conv2 = DoubleConv(512, 256, use_se=use_se)
+        self.up3 = nn.ConvTranspose2d(256, 128, kernel_size=2, stride=2)
+        self.conv3 = DoubleConv(256, 128, use_se=use_se)
+        self.up4 = nn.ConvTranspose2d(128, 64, kernel_size=2, stride=2)
+        self.conv4 = DoubleConv(128, 64, use_se=use_se)
+        self.outc = nn.Conv2d(64, num_classes, kernel_size=1)
+
+        object.__setattr__(self, "in_channels", in_channels)
+        object.__setattr__(self, "num_classes", num_classes)
+        object.__setattr__(self, "use_se", use_se)
+        object.__setattr__(self, "precision", "bf16")
+        object.__setattr__(self, "last_logits", None)
+        object.__setattr__(self, "_eng", None)
+        enc = [("inc.double_conv", self.inc), ("down1.1.double_conv", self.down1[1]),
+               ("down2.1.double_conv", self.down2[1]), ("down3.1.double_conv", self.down3[1]),
+               ("down4.1.double_conv", self.down4[1])]
+        cin = in_channels
+        blocks = []
+        for l, (name, mod) in enumerate(enc):
+            blocks.append(_Block(name, mod, cin, _WIDTHS[l], l, first=(l == 0)))
+            cin = _WIDTHS[l]
+        object.__setattr__(self, "_enc_blocks", blocks)
+        dec = [("conv1.double_conv", self.conv1, 3), ("conv2.double_conv", self.conv2, 2),
+               ("conv3.double_conv", self.conv3, 1), ("conv4.double_conv", self.conv4, 0)]
+        object.__setattr__(self, "_dec_blocks", [_Block(n, m, 2 * _WIDTHS[l], _WIDTHS[l], l) for n, m, l in dec])
+        object.__setattr__(self, "_ups", [self.up1, self.up2, self.up3, self.up4])
+        object.__setattr__(self, "_up_names", ["up1", "up2", "up3", "up4"])
+        object.__setattr__(self, "_param_names", [n for n, _ in self.named_parameters()])
+
+    # ---- configuration --------------------------------------------------------------------------------
+    def set_precision(self, precision: str) -> "UNet":
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        object.__setattr__(self, "precision", precision)
+        return self
+
+    def _dt(self):
+        return (_lib.BF16, torch.bfloat16) if self.precision == "bf16" else (_lib.F32, torch.float32)
+
+    def _engine(self) -> _Engine:
+        if self._eng is None:
+            object.__setattr__(self, "_eng", _Engine(self))
+        return self._eng
+
+    def _keep(self) -> bool:
+        """Will this forward be differentiated?  (decided here: autograd.Function.forward always runs in no-grad mode)"""
+        keep = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if keep and not self.training:
+            raise NotImplementedError("backward in eval() mode (running-stat BatchNorm) is not implemented; the "
+                                      "reference only differentiates in train() mode (UCA:333,345)")
+        return keep
+
+    def _params(self):
+        return [p for _, p in self.named_parameters()]
+
+    # ---- reference API --------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """(B,Cin,H,W) float -> class logits (B,num_classes,H,W), like the reference's UNet.forward (UCA:127-163)."""
+        _check_input(self, x)
+        out = _UNetFn.apply(self, x, self._keep(), *self._params())
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    # ---- fused extras ---------------------------------------------------------------------------------
+    def loss(self, images: torch.Tensor, masks: torch.Tensor, ignore_index: int = 255) -> torch.Tensor:
+        """criterion(model(images), masks) with nn.CrossEntropyLoss(ignore_index) semantics, fused."""
+        _check_input(self, images)
+        return _UNetLossFn.apply(self, images, masks, ignore_index, self._keep(), *self._params())
+
+    @torch.no_grad()
+    def predict_mask(self, images: torch.Tensor) -> torch.Tensor:
+        """torch.max(model(images), 1)[1] (UCA:220): int64 class map, ties -> lowest class."""
+        logits = self.forward(images).float().contiguous()
+        B, nc, H, W = logits.shape
+        mask = torch.empty(B, H, W, dtype=torch.int64, device=logits.device)
+        _lib.call("unetca_cross_entropy", _ptr(logits), None, nc, B, H * W, -1, None, None, _ptr(mask), None, None, None,
+                  _stream())
+        return mask

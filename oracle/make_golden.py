@@ -1,0 +1,96 @@
+"""oracle/make_golden.py — TEST INFRASTRUCTURE ONLY.
+
+Generates tests/golden/*.npz by running the UNMODIFIED reference classes (`UNet`, `nn.CrossEntropyLoss`) imported
+by path from /root/reference/Unet-ChannalAttention.py on CPU, fp32, on the seeded fixtures of
+oracle/unet_ca_port.py (`make_state_dict`, `make_batch`).  Run in the build container only (the GPU box has no
+/root/reference):  python oracle/make_golden.py
+
+The reference ships no tests or golden vectors of its own, so these files are what pins the oracle.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import unet_ca_port as port  # noqa: E402
+
+REF = "/root/reference/Unet-ChannalAttention.py"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_reference():
+    spec = importlib.util.spec_from_file_location("unet_ca_reference", REF)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_case(ref, name, seed, B, H, W, use_se, full):
+    torch.manual_seed(0)
+    sd = port.make_state_dict(seed=seed, use_se=use_se)
+    x, y = port.make_batch(seed, B, H, W)
+    model = ref.UNet(in_channels=3, num_classes=2, use_se=use_se)
+    missing = model.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    model.train()
+    crit = torch.nn.CrossEntropyLoss(ignore_index=255)
+    # pool indices as autograd would save them: hook the MaxPool2d inputs
+    pool_in = []
+    hooks = [m.register_forward_hook(lambda m_, i, o: pool_in.append(i[0].detach().clone()))
+             for m in model.modules() if isinstance(m, torch.nn.MaxPool2d)]
+    logits = model(x)
+    loss = crit(logits, y)
+    loss.backward()
+    for h in hooks:
+        h.remove()
+    out = {
+        "keys": np.array(list(model.state_dict().keys())),
+        "loss": np.float32(loss.item()),
+        "argmax_packed": np.packbits(torch.max(logits, 1)[1].numpy().astype(np.uint8)),
+        "grad_norms": np.array([p.grad.norm().item() for _, p in model.named_parameters()], dtype=np.float64),
+        "param_names": np.array([n for n, _ in model.named_parameters()]),
+    }
+    if full:
+        out["logits"] = logits.detach().numpy()
+        for i, t in enumerate(pool_in):
+            _, idx = torch.nn.functional.max_pool2d(t, 2, return_indices=True)
+            out[f"pool_idx{i}"] = idx.numpy().astype(np.int32)
+        named = dict(model.named_parameters())
+        for k in ("outc.weight", "outc.bias", "inc.double_conv.1.weight", "inc.double_conv.1.bias",
+                  "inc.double_conv.0.weight", "conv4.double_conv.4.weight", "up4.bias"):
+            out["grad:" + k] = named[k].grad.numpy()
+        if use_se:
+            for k in ("inc.double_conv.6.fc.0.weight", "inc.double_conv.6.fc.2.weight"):
+                out["grad:" + k] = named[k].grad.numpy()
+        bufs = dict(model.named_buffers())
+        for k in ("inc.double_conv.1.running_mean", "inc.double_conv.1.running_var",
+                  "down4.1.double_conv.4.running_mean", "down4.1.double_conv.4.running_var"):
+            out["buf:" + k] = bufs[k].numpy()
+    else:
+        out["logits_sub"] = logits.detach().numpy()[:, :, ::8, ::8].copy()
+    # eval-mode forward with the updated running stats
+    model.eval()
+    with torch.no_grad():
+        ev = model(x)
+    out["eval_logits_sub" if not full else "eval_logits"] = ev.numpy() if full else ev.numpy()[:, :, ::8, ::8].copy()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, **out)
+    print(name, "loss", loss.item(), "->", path, os.path.getsize(path) // 1024, "KiB")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = load_reference()
+    run_case(ref, "unetca_se_b2_32", seed=0, B=2, H=32, W=32, use_se=True, full=True)
+    run_case(ref, "unet_plain_b2_32", seed=1, B=2, H=32, W=48, use_se=False, full=True)
+    run_case(ref, "unetca_se_b4_256", seed=0, B=4, H=256, W=256, use_se=True, full=False)   # BASELINE configs[0]
+
+
+if __name__ == "__main__":
+    main()

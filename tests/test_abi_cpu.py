@@ -1,0 +1,67 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol the header
+declares; the nn.Module mirrors the reference's constructor / state_dict; and nothing falls back to the CPU."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet_ca_port as port
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    import unetca_b200
+    decls = unetca_b200._lib.parse_header()
+    assert len(decls) >= 45
+    for name in decls:
+        assert hasattr(built_lib, name), name
+    assert built_lib.unetca_abi_version() == 1
+    assert built_lib.unetca_max_parts(4) > 4
+
+
+def test_sass_is_blackwell_native(built_lib):
+    """The tensor-core path must be tcgen05/TMA (UTCHMMA / UTMALDG / UTMASTG / LDTM in SASS), not mma.sync (HMMA)."""
+    import subprocess
+    import unetca_b200
+    sass = subprocess.run(["cuobjdump", "-sass", unetca_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM"):
+        assert mnem in sass, mnem
+    assert "HMMA." not in sass.replace("UTCHMMA", "")
+
+
+def test_module_mirrors_reference_state_dict(golden_dir):
+    import unetca_b200
+    g = np.load(os.path.join(golden_dir, "unetca_se_b2_32.npz"))
+    m = unetca_b200.UNet(in_channels=3, num_classes=2, use_se=True)
+    assert list(m.state_dict().keys()) == [str(k) for k in g["keys"]]
+    assert sum(p.numel() for p in m.parameters()) == 31_261_698
+    sd = port.make_state_dict(seed=0)
+    m.load_state_dict(sd, strict=True)                               # reference checkpoints load unchanged
+    for k, v in m.state_dict().items():
+        assert v.shape == sd[k].shape and v.dtype == sd[k].dtype, k
+    g2 = np.load(os.path.join(golden_dir, "unet_plain_b2_32.npz"))
+    m2 = unetca_b200.UNet(3, 2)                                      # use_se defaults to False like the reference
+    assert list(m2.state_dict().keys()) == [str(k) for k in g2["keys"]]
+    m3 = unetca_b200.UNet()                                          # defaults: in_channels=1, num_classes=2
+    assert m3.inc.double_conv[0].weight.shape == (64, 1, 3, 3)
+    assert m3.outc.weight.shape == (2, 64, 1, 1)
+
+
+def test_no_cpu_fallback():
+    import unetca_b200
+    m = unetca_b200.UNet(3, 2, True)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 3, 32, 32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.loss(torch.zeros(1, 3, 32, 32), torch.zeros(1, 32, 32, dtype=torch.int64))
+
+
+def test_product_does_not_import_oracle():
+    """The product path may not route through oracle/ (it is test infrastructure)."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for d in ("insar-unet-ca_b200", "unetca_b200"):
+        for dirpath, _, files in os.walk(os.path.join(root, d)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")):
+                    src = open(os.path.join(dirpath, f)).read()
+                    assert "oracle" not in src.replace("no oracle", ""), os.path.join(dirpath, f)

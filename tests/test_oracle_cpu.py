@@ -1,0 +1,112 @@
+"""CPU tests that pin the oracle (oracle/unet_ca_port.py, oracle/np_ops.py) to the golden vectors produced by the
+unmodified reference (oracle/make_golden.py), and the numpy restatement to the torch port."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_ops
+from oracle import unet_ca_port as port
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+@pytest.mark.parametrize("name,seed,B,H,W,use_se", [
+    ("unetca_se_b2_32", 0, 2, 32, 32, True),
+    ("unet_plain_b2_32", 1, 2, 32, 48, False),
+])
+def test_port_matches_reference_golden(golden_dir, name, seed, B, H, W, use_se):
+    g = _load(golden_dir, name)
+    sd = port.make_state_dict(seed=seed, use_se=use_se)
+    assert list(sd.keys()) == [str(k) for k in g["keys"]]            # state_dict key parity (154 / 136 keys)
+    assert len(sd) == (154 if use_se else 136)
+    x, y = port.make_batch(seed, B, H, W)
+    logits, loss, grads, bufs, aux = port.train_step_grads(sd, x, y, use_se=use_se)
+    np.testing.assert_allclose(logits.numpy(), g["logits"], rtol=1e-4, atol=1e-5)
+    assert abs(loss.item() - float(g["loss"])) < 1e-6
+    names = [str(n) for n in g["param_names"]]
+    norms = np.array([grads[n].norm().item() for n in names])
+    np.testing.assert_allclose(norms, g["grad_norms"], rtol=2e-3, atol=1e-7)
+    for k in g.files:
+        if k.startswith("grad:"):
+            np.testing.assert_allclose(grads[k[5:]].numpy(), g[k], rtol=1e-3, atol=1e-6)
+        if k.startswith("buf:"):
+            np.testing.assert_allclose(bufs[k[4:]].numpy(), g[k], rtol=1e-5, atol=1e-6)
+    for i, idx in enumerate(aux["pool_idx"]):
+        assert np.array_equal(idx.numpy().astype(np.int32), g[f"pool_idx{i}"])          # bit-exact
+    mask = torch.max(logits, 1)[1].numpy().astype(np.uint8)
+    assert np.array_equal(np.packbits(mask), g["argmax_packed"])                        # bit-exact
+    # eval-mode forward with the updated running statistics
+    p = {k: v.clone() for k, v in sd.items()}
+    p.update(bufs)
+    ev = port.unet_forward(x, p, use_se=use_se, train=False)
+    np.testing.assert_allclose(ev.numpy(), g["eval_logits"], rtol=1e-4, atol=1e-5)
+
+
+def test_port_matches_reference_configs0(golden_dir):
+    """BASELINE.json configs[0]: B=4, 3x256x256, fp32 — forward only here (the backward is covered at 32x32)."""
+    g = _load(golden_dir, "unetca_se_b4_256")
+    sd = port.make_state_dict(seed=0)
+    x, y = port.make_batch(0, 4, 256, 256)
+    p = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        logits = port.unet_forward(x, p, train=True)
+        loss = port.loss_fn(logits, y)
+    np.testing.assert_allclose(logits.numpy()[:, :, ::8, ::8], g["logits_sub"], rtol=1e-4, atol=1e-5)
+    assert abs(loss.item() - float(g["loss"])) < 1e-6
+    mask = torch.max(logits, 1)[1].numpy().astype(np.uint8)
+    assert np.array_equal(np.packbits(mask), g["argmax_packed"])
+
+
+def test_numpy_restatement_matches_port():
+    """oracle/np_ops.py (pure numpy, float64 arbiter) against the torch port, forward and every gradient."""
+    sd = port.make_state_dict(seed=3)
+    x, y = port.make_batch(3, 2, 16, 32)
+    logits, loss, grads, bufs, aux = port.train_step_grads(sd, x, y, dtype=torch.float64)
+    sdn = {k: v.double().numpy() for k, v in sd.items()}
+    lg, cache, new_stats, pool_idx = np_ops.unet_forward(x.double().numpy(), sdn)
+    np.testing.assert_allclose(lg, logits.numpy(), rtol=1e-9, atol=1e-10)
+    l, ce_cache = np_ops.cross_entropy_fwd(lg, y.numpy())
+    assert abs(l - loss.item()) < 1e-10
+    g = np_ops.unet_backward(np_ops.cross_entropy_bwd(ce_cache), cache, sdn)
+    for k, v in grads.items():
+        np.testing.assert_allclose(g[k], v.numpy(), rtol=1e-6, atol=1e-10, err_msg=k)
+    for a, b in zip(pool_idx, aux["pool_idx"]):
+        assert np.array_equal(a, b.numpy())
+    for k, v in new_stats.items():
+        np.testing.assert_allclose(v, bufs[k].numpy(), rtol=1e-9, atol=1e-12, err_msg=k)
+    assert np.array_equal(np_ops.argmax_mask(lg), torch.max(logits, 1)[1].numpy())
+
+
+def test_maxpool_tie_and_nan_rule():
+    """First maximum in window order wins, NaN propagates — numpy restatement vs torch."""
+    rs = np.random.RandomState(0)
+    x = rs.randint(0, 3, (2, 4, 8, 8)).astype(np.float32)           # many exact ties (ReLU zeros in practice)
+    x[0, 0, 0, 1] = np.nan
+    x[1, 2, 5, 4] = np.nan
+    y, idx = np_ops.maxpool2x2_fwd(x)
+    ty, tidx = torch.nn.functional.max_pool2d(torch.from_numpy(x), 2, return_indices=True)
+    assert np.array_equal(idx, tidx.numpy())
+    np.testing.assert_array_equal(y, ty.numpy())
+
+
+def test_cross_entropy_ignore_and_all_ignored():
+    rs = np.random.RandomState(1)
+    lg = rs.standard_normal((2, 2, 4, 4)).astype(np.float32)
+    t = rs.randint(0, 2, (2, 4, 4)).astype(np.int64)
+    t[0, 0, :2] = 255
+    loss, cache = np_ops.cross_entropy_fwd(lg, t)
+    ref = torch.nn.functional.cross_entropy(torch.from_numpy(lg).requires_grad_(True), torch.from_numpy(t), ignore_index=255)
+    assert abs(loss - ref.item()) < 1e-6
+    t[:] = 255
+    loss, _ = np_ops.cross_entropy_fwd(lg, t)
+    assert np.isnan(loss)                                            # all-ignored -> NaN like torch
+    assert torch.isnan(torch.nn.functional.cross_entropy(torch.from_numpy(lg), torch.from_numpy(t), ignore_index=255))
+
+
+def test_bn_train_needs_more_than_one_value():
+    with pytest.raises(ValueError):
+        np_ops.bn_train_fwd(np.zeros((1, 4, 1, 1)), np.ones(4), np.zeros(4), np.zeros(4), np.ones(4))
