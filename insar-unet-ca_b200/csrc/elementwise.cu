@@ -280,6 +280,36 @@ __global__ void __launch_bounds__(kThreads) se_scale_pool_kernel(const T* __rest
     }
 }
 
+// out = relu(a*y+b) * s[b,c] without pooling (any H, W): plain pixel-row pass; grid = (blocks per image, B)
+template <typename T>
+__global__ void __launch_bounds__(kThreads) se_scale_kernel(const T* __restrict__ y, int ldy, T* __restrict__ out, int ldo,
+                                                            int C, long pix_per_img, long chunk,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift,
+                                                            const float* __restrict__ s) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    if (r >= rows) return;
+    const long base = (long)blockIdx.y * pix_per_img;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    float a[VEC], b[VEC], g[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        a[i] = scale[cv * VEC + i]; b[i] = shift[cv * VEC + i];
+        g[i] = s ? s[(long)blockIdx.y * C + cv * VEC + i] : 1.f;
+    }
+#pragma unroll 4
+    for (long p = p0 + r; p < p1; p += rows) {
+        float v[VEC];
+        load_vec(y + (base + p) * ldy + cv * VEC, v);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = fmaxf(fmaf(a[i], v[i], b[i]), 0.f) * g[i];
+        store_vec(out + (base + p) * ldo + cv * VEC, v);
+    }
+}
+
 // Standalone MaxPool2d(2) over an NHWC tensor: pooled values, 1-byte window positions and (optionally) the
 // int64 flat indices h*W+w that torch's max_pool2d(return_indices=True) reports.          UCA:106-109
 template <typename T>
@@ -946,17 +976,20 @@ int unetca_se_fc(const float* pool_parts, int nparts, int B, int C, int Cr, long
 int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, void* pooled, int ldp, uint8_t* pos,
                          int B, int H, int W, int C, const float* scale, const float* shift, const float* s,
                          void* stream) {
-    UNETCA_REQUIRE(H % 2 == 0 && W % 2 == 0, "se_scale_pool: H, W must be even (got %d x %d)", H, W);
+    UNETCA_REQUIRE(!pooled || (H % 2 == 0 && W % 2 == 0), "se_scale_pool: H, W must be even to pool (got %d x %d)", H, W);
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldy); REQ_CHAN(C, ldo);
-        const long nthr = (long)B * (H / 2) * (W / 2) * (C / VecTraits<T>::N);
-        const int nblk = ceil_div(nthr, kThreads);
         cudaStream_t st = (cudaStream_t)stream;
         if (pooled) {
             REQ_CHAN(C, ldp);
-            se_scale_pool_kernel<T, true><<<nblk, kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, pos, B, H, W, C, scale, shift, s);
-        } else
-            se_scale_pool_kernel<T, false><<<nblk, kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, nullptr, 0, nullptr, B, H, W, C, scale, shift, s);
+            const long nthr = (long)B * (H / 2) * (W / 2) * (C / VecTraits<T>::N);
+            se_scale_pool_kernel<T, true><<<ceil_div(nthr, kThreads), kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, pos, B, H, W, C, scale, shift, s);
+        } else {
+            const long hw = (long)H * W;
+            const long chunk = ew_chunk<T>(C, hw);
+            dim3 grid(ceil_div(hw, chunk), B);
+            se_scale_kernel<T><<<grid, kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, C, hw, chunk, scale, shift, s);
+        }
     });
     return check_launch("se_scale_pool");
 }

@@ -1,0 +1,172 @@
+"""-m gpu: whole-model parity of the CUDA path (through the drop-in nn.Module -> C ABI) against the oracle and the
+golden vectors of the unmodified reference.  Tolerances are the ones BASELINE.json's north_star states:
+logits 1e-3 rel (fp32 mode) / 2e-2 (bf16); loss and gradient norms 1e-2 rel; pool indices and argmax masks bit-exact
+in fp32 mode."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import unet_ca_port as port  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    built_lib.unetca_set_conv_impl(0)
+    yield
+    torch.cuda.synchronize()
+
+
+def _model(sd, prec, use_se=True, train=True):
+    import unetca_b200
+    m = unetca_b200.UNet(3, 2, use_se=use_se).cuda().set_precision(prec)
+    m.load_state_dict(sd)
+    m.train(train)
+    return m
+
+
+def _rel(a, b):
+    return ((a - b).abs().max() / b.abs().max()).item()
+
+
+@pytest.mark.parametrize("prec,ltol,gtol", [("fp32", 1e-3, 1e-2), ("bf16", 2e-2, 1e-2)])
+@pytest.mark.parametrize("name,seed,B,H,W,use_se", [
+    ("unetca_se_b2_32", 0, 2, 32, 32, True),
+    ("unet_plain_b2_32", 1, 2, 32, 48, False),
+])
+def test_train_step_matches_reference_golden(golden_dir, prec, ltol, gtol, name, seed, B, H, W, use_se):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    sd = port.make_state_dict(seed=seed, use_se=use_se)
+    x, y = port.make_batch(seed, B, H, W)
+    m = _model(sd, prec, use_se)
+    # plain reference call sequence: criterion(model(x), y).backward()   (UCA:343-345)
+    logits = m(x.cuda())
+    loss = torch.nn.CrossEntropyLoss(ignore_index=255)(logits, y.cuda())
+    loss.backward()
+    ref_logits = torch.from_numpy(g["logits"])
+    assert logits.shape == ref_logits.shape and logits.dtype == torch.float32
+    assert _rel(logits.detach().cpu(), ref_logits) < ltol
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < 1e-2
+    names = [str(n) for n in g["param_names"]]
+    params = dict(m.named_parameters())
+    norms = np.array([params[n].grad.float().norm().item() for n in names])
+    ref_norms = g["grad_norms"]
+    total, ref_total = np.sqrt((norms ** 2).sum()), np.sqrt((ref_norms ** 2).sum())
+    assert abs(total - ref_total) / ref_total < gtol
+    big = ref_norms > 1e-6 * ref_total          # the 18 pre-BN conv biases have analytically zero gradients
+    tol_each = 1e-2 if prec == "fp32" else 6e-2
+    assert np.all(np.abs(norms[big] - ref_norms[big]) / ref_norms[big] < tol_each), \
+        [(n, a, b) for n, a, b in zip(np.array(names)[big], norms[big], ref_norms[big]) if abs(a - b) / b >= tol_each]
+    assert np.all(norms[~big] < 1e-5 * ref_total)
+    for k in g.files:
+        if k.startswith("grad:"):
+            ref = torch.from_numpy(g[k])
+            if ref.abs().max() < 1e-6:
+                continue
+            assert _rel(params[k[5:]].grad.cpu(), ref) < (1e-2 if prec == "fp32" else 8e-2), k
+        if k.startswith("buf:"):
+            assert _rel(dict(m.named_buffers())[k[4:]].cpu(), torch.from_numpy(g[k])) < (1e-4 if prec == "fp32" else 2e-2), k
+    assert int(m.inc.double_conv[1].num_batches_tracked) == 1
+    # fused loss path gives the same numbers
+    m2 = _model(sd, prec, use_se)
+    l2 = m2.loss(x.cuda(), y.cuda())
+    l2.backward()
+    assert abs(l2.item() - loss.item()) < 1e-5
+    p2 = dict(m2.named_parameters())
+    for n in names:
+        assert torch.allclose(p2[n].grad, params[n].grad, rtol=1e-4, atol=1e-7), n
+    if prec == "fp32":
+        mask = torch.max(logits.detach(), 1)[1].cpu().numpy().astype(np.uint8)
+        nbad = int((np.unpackbits(np.packbits(mask)) != np.unpackbits(g["argmax_packed"])).sum())
+        assert nbad == 0, f"{nbad} argmax-mask mismatches in fp32 mode"
+    # eval-mode forward (running-stat BN folded into scale/shift), no_grad like validate_model (UCA:273-276)
+    m.eval()
+    with torch.no_grad():
+        ev = m(x.cuda())
+    assert _rel(ev.cpu(), torch.from_numpy(g["eval_logits"])) < (2e-3 if prec == "fp32" else 3e-2)
+    assert torch.equal(m.predict_mask(x.cuda()).cpu(), torch.max(ev, 1)[1].cpu())
+
+
+def test_configs0_fp32_masks_bit_exact(golden_dir):
+    """BASELINE configs[0] (B=4, 3x256x256, fp32 mode): logits 1e-3, argmax mask bit-exact vs the reference."""
+    g = np.load(os.path.join(golden_dir, "unetca_se_b4_256.npz"))
+    sd = port.make_state_dict(seed=0)
+    x, y = port.make_batch(0, 4, 256, 256)
+    m = _model(sd, "fp32")
+    loss = m.loss(x.cuda(), y.cuda())
+    loss.backward()
+    logits = m.last_logits.cpu()
+    assert _rel(logits[:, :, ::8, ::8], torch.from_numpy(g["logits_sub"])) < 1e-3
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < 1e-3
+    mask = torch.max(logits, 1)[1].numpy().astype(np.uint8)
+    nbad = int((np.unpackbits(np.packbits(mask)) != np.unpackbits(g["argmax_packed"])).sum())
+    assert nbad == 0, f"{nbad} of {mask.size} argmax-mask pixels differ from the reference in fp32 mode"
+    names = [str(n) for n in g["param_names"]]
+    params = dict(m.named_parameters())
+    norms = np.array([params[n].grad.norm().item() for n in names])
+    total, ref_total = np.sqrt((norms ** 2).sum()), np.sqrt((g["grad_norms"] ** 2).sum())
+    assert abs(total - ref_total) / ref_total < 1e-2
+
+
+def test_configs0_bf16(golden_dir):
+    g = np.load(os.path.join(golden_dir, "unetca_se_b4_256.npz"))
+    sd = port.make_state_dict(seed=0)
+    x, y = port.make_batch(0, 4, 256, 256)
+    m = _model(sd, "bf16")
+    loss = m.loss(x.cuda(), y.cuda())
+    loss.backward()
+    logits = m.last_logits.cpu()
+    assert _rel(logits[:, :, ::8, ::8], torch.from_numpy(g["logits_sub"])) < 2e-2
+    assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < 1e-2
+    names = [str(n) for n in g["param_names"]]
+    params = dict(m.named_parameters())
+    norms = np.array([params[n].grad.norm().item() for n in names])
+    total, ref_total = np.sqrt((norms ** 2).sum()), np.sqrt((g["grad_norms"] ** 2).sum())
+    assert abs(total - ref_total) / ref_total < 1e-2
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_adam_trajectory_100_steps(prec):
+    """100 Adam(lr=1e-4) steps on the same seeded batches: loss and global grad norm within 1e-2 rel of the oracle
+    at every step (UCA:342-346, 466)."""
+    B, H, W, steps = 2, 32, 32, 100
+    sd = port.make_state_dict(seed=7)
+    m = _model(sd, prec)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    # oracle: the torch port driven by the same optimizer on CPU
+    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    ropt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4)
+    worst_l = worst_g = 0.0
+    for s in range(steps):
+        x, y = port.make_batch(100 + s % 4, B, H, W)
+        ropt.zero_grad()
+        rl = port.loss_fn(port.unet_forward(x, p, train=True), y)
+        rl.backward()
+        rg = torch.sqrt(sum((v.grad ** 2).sum() for v in p.values() if v.requires_grad)).item()
+        ropt.step()
+        opt.zero_grad()
+        l = m.loss(x.cuda(), y.cuda())
+        l.backward()
+        gn = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in m.parameters())).item()
+        opt.step()
+        worst_l = max(worst_l, abs(l.item() - rl.item()) / abs(rl.item()))
+        worst_g = max(worst_g, abs(gn - rg) / rg)
+    assert worst_l < 1e-2, worst_l
+    assert worst_g < (1e-2 if prec == "fp32" else 3e-2), worst_g
+
+
+def test_error_behaviour():
+    import unetca_b200
+    m = unetca_b200.UNet(3, 2, True).cuda()
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 40, 40, device="cuda"))                  # resize guard path (UCA:138-157) not on CUDA path
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 1, 32, 32, device="cuda"))                  # wrong channel count
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 3, 16, 16, device="cuda"))                  # train-mode BN with 1 value per channel

@@ -1,0 +1,327 @@
+"""-m gpu: per-op parity of every kernel behind the C ABI against the matching torch op on CPU (the oracle's ops),
+on identical inputs.  Integer results (pool indices, argmax masks) must be bit-exact; floating point within the
+tolerance written at each assert (fp32 storage: 1e-4..1e-3 rel; bf16 storage: 1e-2 rel, one bf16 ulp = 2^-8)."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from gpu_util import *  # noqa: E402,F401,F403
+
+DTS = [F32, BF16]
+TOL = {F32: 2e-4, BF16: 1.2e-2}
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    call("unetca_set_conv_impl", 0)
+    yield
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 8, 16), (1, 192, 6, 4), (3, 1024, 2, 2)])
+def test_maxpool_bit_exact(dt, B, C, H, W):
+    rs = np.random.RandomState(0)
+    x = torch.from_numpy(rs.randint(0, 3, (B, C, H, W)).astype(np.float32))      # many exact ties
+    x[0, 0, 0, 1] = float("nan")
+    x[-1, C - 1, H - 1, W - 2] = float("nan")
+    xd = to_nhwc(x, dt)
+    pooled = torch.empty(B, H // 2, W // 2, C, dtype=TDT[dt], device="cuda")
+    pos = torch.empty(B, H // 2, W // 2, C, dtype=torch.uint8, device="cuda")
+    idx = torch.empty(B, C, H // 2, W // 2, dtype=torch.int64, device="cuda")
+    call("unetca_maxpool2x2", dt, ptr(xd), C, ptr(pooled), C, ptr(pos), ptr(idx), B, H, W, C, stream())
+    ry, ridx = F.max_pool2d(x, 2, return_indices=True)
+    assert torch.equal(idx.cpu(), ridx)                                          # bit-exact indices
+    got = from_nhwc(pooled)
+    assert torch.equal(torch.isnan(got), torch.isnan(ry))
+    assert torch.equal(torch.nan_to_num(got), torch.nan_to_num(ry))
+    # backward: unpool + skip add
+    dpool = torch.from_numpy(rs.standard_normal((B, C, H // 2, W // 2)).astype(np.float32))
+    skip = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    dx = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    dpd, skd = to_nhwc(dpool, dt), to_nhwc(skip, dt)
+    call("unetca_pool_bwd_add", dt, ptr(skd), C, ptr(dpd), C, ptr(pos), ptr(dx), C, B, H, W, C, stream())
+    ref = rounded(skip, dt) + F.max_unpool2d(rounded(dpool, dt), ridx, 2, output_size=(H, W))
+    assert relerr(from_nhwc(dx), ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 16, 16), (3, 128, 8, 4)])
+def test_bn_relu_train_and_backward(dt, B, C, H, W):
+    rs = np.random.RandomState(1)
+    y = torch.from_numpy((rs.standard_normal((B, C, H, W)) * 2 + 0.5).astype(np.float32))
+    yr = rounded(y, dt)
+    gamma = torch.from_numpy((1 + 0.1 * rs.standard_normal(C)).astype(np.float32))
+    beta = torch.from_numpy((0.1 * rs.standard_normal(C)).astype(np.float32))
+    cbias = torch.from_numpy((0.3 * rs.standard_normal(C)).astype(np.float32))
+    rm, rv = torch.zeros(C), torch.ones(C)
+    yd = to_nhwc(y, dt)
+    parts = parts_buf(B)
+    n = cint()
+    call("unetca_chan_stats", dt, ptr(yd), C, C, B * H * W, ptr(parts), ctypes.byref(n), stream())
+    g = {k: v.cuda() for k, v in dict(gamma=gamma, beta=beta, cbias=cbias, rm=rm.clone(), rv=rv.clone()).items()}
+    mean, invstd, scale, shift = (torch.empty(C, device="cuda") for _ in range(4))
+    call("unetca_bn_finalize_train", ptr(parts), n.value, C, B * H * W, ptr(g["cbias"]), ptr(g["gamma"]), ptr(g["beta"]),
+         ptr(g["rm"]), ptr(g["rv"]), 0.1, 1e-5, ptr(mean), ptr(invstd), ptr(scale), ptr(shift), stream())
+    out = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    call("unetca_bn_relu", dt, ptr(yd), C, ptr(out), C, B, H * W, C, ptr(scale), ptr(shift), None, None, stream())
+    # reference: conv output = yr + bias, BN train, ReLU
+    yin = (yr + cbias[None, :, None, None]).requires_grad_(True)
+    rrm, rrv = rm.clone(), rv.clone()
+    ref = F.relu(F.batch_norm(yin, rrm, rrv, gamma, beta, True, 0.1, 1e-5))
+    assert relerr(from_nhwc(out), ref.detach()) < TOL[dt]
+    assert relerr(g["rm"].cpu(), rrm) < 1e-5 and relerr(g["rv"].cpu(), rrv) < 1e-5
+    # backward
+    dout = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    dor = rounded(dout, dt)
+    gw = torch.autograd.grad(ref, [yin], dor, retain_graph=True)[0]
+    gam = gamma.clone().requires_grad_(True); bet = beta.clone().requires_grad_(True)
+    ref2 = F.relu(F.batch_norm(yin.detach(), None, None, gam, bet, True, 0.1, 1e-5))
+    dgam, dbet = torch.autograd.grad(ref2, [gam, bet], dor)
+    dd = to_nhwc(dout, dt)
+    call("unetca_bn_bwd_reduce", dt, ptr(dd), C, ptr(yd), C, B, H * W, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd),
+         None, None, ptr(parts), ctypes.byref(n), stream())
+    dgamma, dbeta = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    coef = torch.empty(3, C, device="cuda")
+    call("unetca_bn_bwd_finalize", ptr(parts), n.value, C, B * H * W, ptr(g["gamma"]), ptr(invstd), ptr(dgamma), ptr(dbeta),
+         ptr(coef), stream())
+    dy = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    call("unetca_bn_bwd_apply", dt, ptr(dd), C, ptr(yd), C, ptr(dy), C, B, H * W, C, ptr(scale), ptr(shift), ptr(mean),
+         ptr(invstd), None, None, ptr(coef), stream())
+    assert relerr(dgamma.cpu(), dgam) < 1e-3 and relerr(dbeta.cpu(), dbet) < 1e-3
+    assert relerr(from_nhwc(dy), gw) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,C,H,W,pool", [(2, 64, 16, 16, True), (3, 128, 4, 8, False)])
+def test_se_block_forward_backward(dt, B, C, H, W, pool):
+    """relu(bn) -> SE (squeeze, FC, sigmoid, scale) [-> maxpool] and its backward, fused kernels vs torch ops."""
+    rs = np.random.RandomState(2)
+    Cr = C // 16
+    y = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    yr = rounded(y, dt)
+    scale = torch.from_numpy((1 + 0.2 * rs.standard_normal(C)).astype(np.float32))
+    shift = torch.from_numpy((0.2 * rs.standard_normal(C)).astype(np.float32))
+    w1 = torch.from_numpy((rs.standard_normal((Cr, C)) / np.sqrt(C)).astype(np.float32))
+    w2 = torch.from_numpy((rs.standard_normal((C, Cr)) / np.sqrt(Cr)).astype(np.float32))
+    yd = to_nhwc(y, dt)
+    sc, sh, w1d, w2d = scale.cuda(), shift.cuda(), w1.cuda(), w2.cuda()
+    parts = parts_buf(B)
+    n = cint()
+    call("unetca_bn_relu", dt, ptr(yd), C, None, 0, B, H * W, C, ptr(sc), ptr(sh), ptr(parts), ctypes.byref(n), stream())
+    p, z, s = torch.empty(B, C, device="cuda"), torch.empty(B, Cr, device="cuda"), torch.empty(B, C, device="cuda")
+    call("unetca_se_fc", ptr(parts), n.value, B, C, Cr, H * W, ptr(w1d), ptr(w2d), ptr(p), ptr(z), ptr(s), stream())
+    # output into the lower channel half of a 2C-wide concat buffer (skip-first torch.cat, UCA:140)
+    cat = torch.zeros(B, H, W, 2 * C, dtype=TDT[dt], device="cuda")
+    pooled = torch.empty(B, H // 2, W // 2, C, dtype=TDT[dt], device="cuda") if pool else None
+    pos = torch.empty(B, H // 2, W // 2, C, dtype=torch.uint8, device="cuda") if pool else None
+    call("unetca_se_scale_pool", dt, ptr(yd), C, ptr(cat), 2 * C, ptr(pooled), C if pool else 0, ptr(pos), B, H, W, C,
+         ptr(sc), ptr(sh), ptr(s), stream())
+    # reference
+    a = F.relu(yr * scale[None, :, None, None] + shift[None, :, None, None]).requires_grad_(True)
+    w1r, w2r = w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+    sr = torch.sigmoid(F.linear(F.relu(F.linear(a.mean((2, 3)), w1r)), w2r))
+    o = a * sr[:, :, None, None]
+    assert relerr(s.cpu(), sr.detach()) < 1e-4
+    got = from_nhwc(cat[..., :C])
+    assert relerr(got, o.detach()) < TOL[dt]
+    assert cat[..., C:].abs().max().item() == 0
+    if pool:
+        ry, ridx = F.max_pool2d(got, 2, return_indices=True)                     # pool of the *stored* values
+        assert torch.equal(from_nhwc(pooled), ry)
+        code = pos.cpu().permute(0, 3, 1, 2).long()
+        ho = torch.arange(H // 2)[None, None, :, None]; wo = torch.arange(W // 2)[None, None, None, :]
+        assert torch.equal((2 * ho + code // 2) * W + 2 * wo + code % 2, ridx)   # bit-exact window positions
+    # backward
+    dout = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    dor = rounded(dout, dt)
+    da, dw1, dw2 = torch.autograd.grad(o, [a, w1r, w2r], dor)
+    dz_ref = da * (a > 0)
+    dd = to_nhwc(dout, dt)
+    call("unetca_se_bwd_reduce", dt, ptr(dd), C, ptr(yd), C, B, H * W, C, ptr(sc), ptr(sh), ptr(parts), ctypes.byref(n),
+         stream())
+    dpre2, dzz, dp = torch.empty(B, C, device="cuda"), torch.empty(B, Cr, device="cuda"), torch.empty(B, C, device="cuda")
+    gw1, gw2 = torch.empty(Cr, C, device="cuda"), torch.empty(C, Cr, device="cuda")
+    call("unetca_se_fc_bwd", ptr(parts), n.value, B, C, Cr, ptr(w1d), ptr(w2d), ptr(p), ptr(z), ptr(s), ptr(dpre2), ptr(dzz),
+         ptr(dp), ptr(gw1), ptr(gw2), stream())
+    assert relerr(gw1.cpu(), dw1) < 2e-3 and relerr(gw2.cpu(), dw2) < 2e-3
+    # the SE-scale / squeeze derivative folded into the BN backward: with mean=0, invstd=1 the "xhat" sums are
+    # just sum(dz*y); check sum(dz) per channel and dy through a BN with gamma*invstd = 1, c1 = c2 = 0
+    zeros, ones = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    call("unetca_bn_bwd_reduce", dt, ptr(dd), C, ptr(yd), C, B, H * W, C, ptr(sc), ptr(sh), ptr(zeros), ptr(ones), ptr(s),
+         ptr(dp), ptr(parts), ctypes.byref(n), stream())
+    sums = parts[: n.value * 2 * C].view(n.value, 2, C).sum(0).cpu()
+    assert relerr(sums[0], dz_ref.sum((0, 2, 3))) < 2e-3
+    assert relerr(sums[1], (dz_ref * yr).sum((0, 2, 3))) < 2e-3
+    coef = torch.stack([ones, zeros, zeros]).contiguous()
+    dy = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    call("unetca_bn_bwd_apply", dt, ptr(dd), C, ptr(yd), C, ptr(dy), C, B, H * W, C, ptr(sc), ptr(sh), ptr(zeros), ptr(ones),
+         ptr(s), ptr(dp), ptr(coef), stream())
+    assert relerr(from_nhwc(dy), dz_ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("nc", [2, 3])
+def test_outc_and_cross_entropy(dt, nc):
+    rs = np.random.RandomState(3)
+    B, C, H, W = 2, 64, 16, 24
+    x = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    xr = rounded(x, dt).requires_grad_(True)
+    w = torch.from_numpy((rs.standard_normal((nc, C, 1, 1)) / 8).astype(np.float32)).requires_grad_(True)
+    b = torch.from_numpy((0.1 * rs.standard_normal(nc)).astype(np.float32)).requires_grad_(True)
+    t = torch.from_numpy(rs.randint(0, nc, (B, H, W)).astype(np.int64))
+    t[0, :2, :] = 255
+    xd = to_nhwc(x, dt)
+    wd, bd, td = w.detach().cuda(), b.detach().cuda(), t.cuda()
+    logits = torch.empty(B, nc, H, W, device="cuda")
+    call("unetca_outc_fwd", dt, ptr(xd), C, C, ptr(wd), ptr(bd), nc, ptr(logits), B, H * W, stream())
+    ref = F.conv2d(xr, w, b)
+    assert relerr(logits.cpu(), ref.detach()) < 1e-5
+    loss_ref = F.cross_entropy(ref, t, ignore_index=255)
+    loss_ref.backward()
+    g = torch.empty_like(logits)
+    mask = torch.empty(B, H, W, dtype=torch.int64, device="cuda")
+    parts = parts_buf(B)
+    out, gs = torch.empty(2, device="cuda"), torch.empty(1, device="cuda")
+    call("unetca_cross_entropy", ptr(logits), ptr(td), nc, B, H * W, 255, None, ptr(g), ptr(mask), ptr(parts), ptr(out),
+         ptr(gs), stream())
+    assert abs(out[0].item() - loss_ref.item()) < 1e-5 * max(1, abs(loss_ref.item()))
+    assert out[1].item() == (t != 255).sum().item()
+    assert torch.equal(mask.cpu(), torch.max(logits.cpu(), 1)[1])                # bit-exact argmax (UCA:220)
+    dx = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    dw, db = torch.empty(nc, C, 1, 1, device="cuda"), torch.empty(nc, device="cuda")
+    call("unetca_outc_bwd", dt, ptr(g), ptr(gs), ptr(xd), C, ptr(dx), C, C, ptr(wd), nc, B, H * W, ptr(parts), ptr(dw),
+         ptr(db), stream())
+    assert relerr(dw.cpu(), w.grad) < 1e-4 and relerr(db.cpu(), b.grad) < 1e-4
+    assert relerr(from_nhwc(dx), xr.grad) < TOL[dt]
+    # all-ignored -> NaN, like torch
+    td.fill_(255)
+    call("unetca_cross_entropy", ptr(logits), ptr(td), nc, B, H * W, 255, None, None, None, ptr(parts), ptr(out), ptr(gs),
+         stream())
+    assert torch.isnan(out[0]).item()
+
+
+def _conv_case(dt, impl, B, C, O, H, W, seed=4):
+    rs = np.random.RandomState(seed)
+    call("unetca_set_conv_impl", impl)
+    x = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((O, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32))
+    dy = torch.from_numpy(rs.standard_normal((B, O, H, W)).astype(np.float32))
+    xr, wr, dyr = rounded(x, dt).requires_grad_(True), rounded(w, dt).requires_grad_(True), rounded(dy, dt)
+    ref = F.conv2d(xr, wr, None, padding=1)
+    ref.backward(dyr)
+    xd, dyd, wdev = to_nhwc(x, dt), to_nhwc(dy, dt), w.cuda()
+    wf = torch.empty(O, 9 * C, dtype=TDT[dt], device="cuda")
+    wdg = torch.empty(C, 9 * O, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_conv3x3_weight", dt, ptr(wdev), ptr(wf), 9 * C, ptr(wdg), O, C, stream())
+    y = torch.empty(B, H, W, O, dtype=TDT[dt], device="cuda")
+    parts = parts_buf(B)
+    n = cint()
+    call("unetca_conv3x3_fwd", dt, ptr(xd), C, ptr(wf), 9 * C, ptr(y), O, B, H, W, C, O, ptr(parts), ctypes.byref(n), stream())
+    tol = TOL[dt]
+    got = from_nhwc(y)
+    assert relerr(got, ref.detach()) < tol, "fwd"
+    st = parts[: n.value * 2 * O].view(n.value, 2, O).sum(0).cpu()
+    assert relerr(st[0], got.sum((0, 2, 3))) < 1e-3 and relerr(st[1], (got * got).sum((0, 2, 3))) < 1e-3, "stats"
+    dx = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    call("unetca_conv3x3_fwd", dt, ptr(dyd), O, ptr(wdg), 9 * O, ptr(dx), C, B, H, W, O, C, None, None, stream())
+    assert relerr(from_nhwc(dx), xr.grad) < tol, "dgrad"
+    ws = torch.empty(8 * 1024 * 1024, device="cuda")
+    dw = torch.empty(O, C, 3, 3, device="cuda")
+    call("unetca_conv3x3_wgrad", dt, ptr(dyd), O, ptr(xd), C, ptr(ws), ws.numel(), B, H, W, C, O, ptr(dw), stream())
+    assert relerr(dw.cpu(), wr.grad) < 2e-3, "wgrad"
+
+
+@pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 64, 16, 16), (1, 128, 64, 8, 24), (2, 64, 192, 4, 4)])
+@pytest.mark.parametrize("dt", DTS)
+def test_conv3x3_ffma(dt, B, C, O, H, W):
+    _conv_case(dt, 1, B, C, O, H, W)
+
+
+@pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 64, 16, 16), (1, 128, 64, 8, 24), (2, 64, 192, 4, 4),
+                                       (2, 128, 256, 32, 32), (3, 256, 128, 16, 48), (1, 64, 64, 128, 128)])
+def test_conv3x3_tcgen05(B, C, O, H, W):
+    _conv_case(BF16, 0, B, C, O, H, W)
+
+
+def _convT_case(dt, impl, B, Cin, Cout, h, w_, seed=5):
+    rs = np.random.RandomState(seed)
+    call("unetca_set_conv_impl", impl)
+    x = torch.from_numpy(rs.standard_normal((B, Cin, h, w_)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((Cin, Cout, 2, 2)) / np.sqrt(Cin)).astype(np.float32))
+    b = torch.from_numpy((0.1 * rs.standard_normal(Cout)).astype(np.float32))
+    dy = torch.from_numpy(rs.standard_normal((B, Cout, 2 * h, 2 * w_)).astype(np.float32))
+    xr, wr, dyr = rounded(x, dt).requires_grad_(True), rounded(w, dt).requires_grad_(True), rounded(dy, dt)
+    ref = F.conv_transpose2d(xr, wr, b, stride=2)
+    ref.backward(dyr)
+    xd, wdev, bd = to_nhwc(x, dt), w.cuda(), b.cuda()
+    wf = torch.empty(4 * Cout, Cin, dtype=TDT[dt], device="cuda")
+    wdg = torch.empty(Cin, 4 * Cout, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_convT_weight", dt, ptr(wdev), ptr(wf), ptr(wdg), Cin, Cout, stream())
+    cat = torch.zeros(B, 2 * h, 2 * w_, 2 * Cout, dtype=TDT[dt], device="cuda")      # write the upper channel half
+    call("unetca_convT2x2_fwd", dt, ptr(xd), Cin, ptr(wf), ptr(bd), ptr(cat[..., Cout:]), 2 * Cout, B, h, w_, Cin, Cout,
+         stream())
+    tol = TOL[dt]
+    assert relerr(from_nhwc(cat[..., Cout:]), ref.detach()) < tol, "fwd"
+    assert cat[..., :Cout].abs().max().item() == 0
+    dcat = torch.zeros(B, 2 * h, 2 * w_, 2 * Cout, dtype=TDT[dt], device="cuda")
+    dcat[..., Cout:] = to_nhwc(dy, dt)
+    dx = torch.empty(B, h, w_, Cin, dtype=TDT[dt], device="cuda")
+    call("unetca_convT2x2_dgrad", dt, ptr(dcat[..., Cout:]), 2 * Cout, ptr(wdg), ptr(dx), Cin, B, h, w_, Cin, Cout, stream())
+    assert relerr(from_nhwc(dx), xr.grad) < tol, "dgrad"
+    ws = torch.empty(8 * 1024 * 1024, device="cuda")
+    dw = torch.empty(Cin, Cout, 2, 2, device="cuda")
+    call("unetca_convT2x2_wgrad", dt, ptr(xd), Cin, ptr(dcat[..., Cout:]), 2 * Cout, ptr(ws), ws.numel(), B, h, w_, Cin, Cout,
+         ptr(dw), stream())
+    assert relerr(dw.cpu(), wr.grad) < 2e-3, "wgrad"
+    dbias = torch.empty(Cout, device="cuda")
+    call("unetca_chan_sum", dt, ptr(dcat[..., Cout:]), 2 * Cout, Cout, B * 4 * h * w_, ptr(parts_buf(B)), ptr(dbias), stream())
+    assert relerr(dbias.cpu(), dyr.sum((0, 2, 3))) < 1e-3, "dbias"
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_convT_ffma(dt):
+    _convT_case(dt, 1, 2, 128, 64, 8, 8)
+
+
+@pytest.mark.parametrize("B,Cin,Cout,h,w_", [(2, 128, 64, 8, 8), (1, 256, 128, 16, 32), (3, 1024, 512, 2, 2)])
+def test_convT_tcgen05(B, Cin, Cout, h, w_):
+    _convT_case(BF16, 0, B, Cin, Cout, h, w_)
+
+
+@pytest.mark.parametrize("dt,impl", [(F32, 1), (BF16, 1), (BF16, 0)])
+def test_first_conv_im2col(dt, impl):
+    """K = 9*Cin = 27 first conv: im2col rows + NT GEMM forward, TN GEMM weight gradient."""
+    rs = np.random.RandomState(6)
+    call("unetca_set_conv_impl", impl)
+    B, Cin, O, H, W = 2, 3, 64, 16, 24
+    x = torch.from_numpy(rs.standard_normal((B, Cin, H, W)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((O, Cin, 3, 3)) / np.sqrt(27)).astype(np.float32))
+    dy = torch.from_numpy(rs.standard_normal((B, O, H, W)).astype(np.float32))
+    xr, wr, dyr = rounded(x, dt), rounded(w, dt).requires_grad_(True), rounded(dy, dt)
+    ref = F.conv2d(xr, wr, None, padding=1)
+    ref.backward(dyr)
+    Kpad = 64
+    col = torch.empty(B * H * W, Kpad, dtype=TDT[dt], device="cuda")
+    call("unetca_im2col3x3_nchw", dt, ptr(x.cuda()), ptr(col), B, Cin, H, W, Kpad, stream())
+    wf = torch.empty(O, Kpad, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_conv3x3_weight", dt, ptr(w.cuda()), ptr(wf), Kpad, None, O, Cin, stream())
+    y = torch.empty(B, H, W, O, dtype=TDT[dt], device="cuda")
+    parts = parts_buf(B)
+    n = cint()
+    call("unetca_gemm_nt", dt, ptr(col), Kpad, ptr(wf), Kpad, ptr(y), O, B * H * W, O, Kpad, ptr(parts), ctypes.byref(n),
+         stream())
+    assert relerr(from_nhwc(y), ref.detach()) < TOL[dt]
+    dyd = to_nhwc(dy, dt)
+    ws = torch.empty(4 * 1024 * 1024, device="cuda")
+    dw = torch.empty(O, Cin, 3, 3, device="cuda")
+    call("unetca_im2col_wgrad", dt, ptr(dyd), O, ptr(col), Kpad, ptr(ws), ws.numel(), B * H * W, Cin, O, ptr(dw), stream())
+    assert relerr(dw.cpu(), wr.grad) < 2e-3
