@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py — U-Net-CA training throughput on B200 (BASELINE.json: "U-Net-CA train img/s @512^2 bf16").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A step is one pass of the hot path over one batch of synthetic input: forward + softmax-CE loss + backward through
+the drop-in `unetca_b200.UNet` (C ABI -> sm_100a kernels), the bucketed gradient all-reduce when N > 1, and
+torch.optim.Adam(lr=1e-4) — the reference's train step (Unet-ChannalAttention.py:338-346).  Workload at every N
+(weak scaling): BASELINE.json configs[1], U-Net-CA (use_se=True), bf16 mode, batch 64 per GPU, 3x512x512, 2 classes.
+
+One JSON line on stdout (rank 0).  `value` = images/s with the batch resident in HBM; `e2e` = the same step fed
+from pinned host memory (H2D copy of images+masks every step, prefetched on a side stream, and the loss read back
+every step); `roofline` = the tcgen05 contraction kernels' algorithmic FLOP/s, timed with CUDA events around their
+launches inside the timed region, against the measured bf16 peak; `roofline_hbm` = the same for the memory-bound
+kernels against the measured copy bandwidth; `cpu_baseline` = the oracle port of the reference (ATen CPU kernels)
+timed on this box's host cores on a bounded sample.
+
+--impl reference: the reference's CPU implementation of the same step (oracle/unet_ca_port.py — /root/reference does
+not exist on the GPU box; the port calls the same ATen CPU kernels as the reference's modules) on all host threads,
+on a bounded sample of the workload (2 images of 3x512x512 per step).
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "unet_ca_train_images_per_sec_512x512_bf16"
+UNIT = "img/s"
+TRAIN_GFLOP_PER_IMG_512 = 1155.21       # BASELINE.md §4 (true shapes, no padding)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# per-kernel-class accounting: algorithmic FLOPs / bytes of every C-ABI call, CUDA events around the launches
+# ------------------------------------------------------------------------------------------------------------
+def _work(name, a, e, cin):
+    """(class, algorithmic flops, algorithmic bytes) of one call; e = bytes per activation element."""
+    if name == "unetca_conv3x3_fwd":
+        B, H, W, C, O = a[7:12]
+        return "tensor", 2.0 * B * H * W * 9 * C * O, 0
+    if name == "unetca_conv3x3_wgrad":
+        B, H, W, C, O = a[7:12]
+        return "tensor", 2.0 * B * H * W * 9 * C * O, 0
+    if name == "unetca_gemm_nt":
+        M, N = a[7], a[8]
+        return "tensor", 2.0 * M * N * 9 * cin, 0
+    if name == "unetca_im2col_wgrad":
+        npix, Cin, O = a[7:10]
+        return "tensor", 2.0 * npix * 9 * Cin * O, 0
+    if name in ("unetca_convT2x2_fwd", "unetca_convT2x2_dgrad"):
+        off = 7 if name.endswith("fwd") else 6
+        B, h, w, Cin, Cout = a[off:off + 5]
+        return "tensor", 2.0 * B * h * w * Cin * 4 * Cout, 0
+    if name == "unetca_convT2x2_wgrad":
+        B, h, w, Cin, Cout = a[7:12]
+        return "tensor", 2.0 * B * h * w * Cin * 4 * Cout, 0
+    if name == "unetca_bn_relu":
+        B, hw, C = a[5:8]
+        n = B * hw * C
+        return "hbm", 0, n * e * (2 if a[3] else 1)
+    if name == "unetca_se_scale_pool":
+        B, H, W, C = a[8:12]
+        n = B * H * W * C
+        return "hbm", 0, 2 * n * e + ((n // 4) * (e + 1) if a[5] else 0)
+    if name in ("unetca_se_bwd_reduce", "unetca_bn_bwd_reduce"):
+        B, hw, C = a[5:8]
+        return "hbm", 0, 2 * B * hw * C * e
+    if name == "unetca_bn_bwd_apply":
+        B, hw, C = a[7:10]
+        return "hbm", 0, 3 * B * hw * C * e
+    if name == "unetca_pool_bwd_add":
+        B, H, W, C = a[8:12]
+        n = B * H * W * C
+        return "hbm", 0, 2 * n * e + (n // 4) * (e + 1)
+    if name == "unetca_chan_sum":
+        return "hbm", 0, a[4] * a[3] * e
+    if name == "unetca_outc_fwd":
+        C, nc, B, HW = a[3], a[6], a[8], a[9]
+        return "hbm", 0, B * HW * (C * e + nc * 4)
+    if name == "unetca_outc_bwd":
+        C, nc, B, HW = a[7], a[9], a[10], a[11]
+        return "hbm", 0, B * HW * (2 * C * e + nc * 4)
+    if name == "unetca_cross_entropy":
+        nc, B, HW = a[2], a[3], a[4]
+        return "hbm", 0, B * HW * (nc * 4 * 2 + 8)
+    if name == "unetca_im2col3x3_nchw":
+        B, Cin, H, W, Kpad = a[3:8]
+        return "hbm", 0, B * H * W * (Cin * 4 + Kpad * e)
+    return "other", 0, 0
+
+
+class KernelAccount:
+    def __init__(self, e, cin):
+        self.e, self.cin, self.records, self.enabled = e, cin, [], False
+
+    @contextlib.contextmanager
+    def __call__(self, name, args):
+        if not self.enabled:
+            yield
+            return
+        s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        yield
+        t.record()
+        self.records.append((name, args, s, t))
+
+    def summary(self):
+        out = {}
+        for name, args, s, t in self.records:
+            cls, fl, by = _work(name, args, self.e, self.cin)
+            d = out.setdefault(name, {"class": cls, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "calls": 0})
+            d["ms"] += s.elapsed_time(t); d["flops"] += fl; d["bytes"] += by; d["calls"] += 1
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference on host cores, bounded sample
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_time(steps, warmup, size, sample_b=2):
+    from oracle import unet_ca_port as port        # test infrastructure; bench.py's baseline legs only
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = port.make_state_dict(seed=0)
+    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4)
+    x, y = port.make_batch(0, sample_b, size, size)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = port.loss_fn(port.unet_forward(x, p, train=True), y)
+        loss.backward()
+        opt.step()
+        _ = loss.item()
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times, sample_b
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    times, sb = cpu_reference_step_time(args.steps, args.warmup, args.size)
+    total = sum(times)
+    v = sb * len(times) / total
+    cores = torch.get_num_threads()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"U-Net-CA (use_se) train step fwd+CE+bwd+Adam, 3x{args.size}x{args.size}, 2 classes; "
+                               f"reference CPU path on a bounded sample of {sb} images per step"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sb} images of 3x{args.size}x{args.size} per step, fp32, {len(times)} timed steps "
+                                   f"after {args.warmup} warm-up, ATen CPU kernels via oracle/unet_ca_port.py"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--kernel-table", default=None, help="write the per-kernel table (JSON) to this path")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    import unetca_b200
+    from unetca_b200 import _lib, parallel
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    B, S = args.batch, args.size
+    torch.manual_seed(0)
+    model = unetca_b200.UNet(3, 2, use_se=True).to(dev).set_precision(args.precision)
+    model.train()
+    if world > 1:
+        parallel.GradBuckets(model)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x = torch.randn(B, 3, S, S, device=dev, generator=g)
+    y = torch.randint(0, 2, (B, S, S), device=dev, generator=g)
+
+    def step(xb, yb):
+        opt.zero_grad(set_to_none=True)
+        loss = model.loss(xb, yb)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    acct = KernelAccount(2 if args.precision == "bf16" else 4, 3)
+    _lib.set_hook(acct)
+    for _ in range(args.warmup):
+        step(x, y)
+    # ---- timed region 1: batch resident in HBM ------------------------------------------------------------
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    acct.enabled = True
+    n0 = _lib.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x, y)
+    e1.record()
+    barrier()
+    acct.enabled = False
+    launches = _lib.launch_count - n0
+    clk = clocks.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    value = world * B * args.steps / (ms / 1e3)
+    final_loss = loss.item()
+
+    # ---- timed region 2: end to end from pinned host memory ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hx = [torch.randn(B, 3, S, S).pin_memory() for _ in range(2)]
+        hy = [torch.randint(0, 2, (B, S, S)).pin_memory() for _ in range(2)]
+        dx = [torch.empty_like(x) for _ in range(2)]
+        dy = [torch.empty_like(y) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
+
+        def upload(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(free[b])
+                dx[b].copy_(hx[b], non_blocking=True)
+                dy[b].copy_(hy[b], non_blocking=True)
+                ready[b].record(copy_stream)
+
+        for b in range(2):
+            free[b].record()
+        barrier()
+        t0 = time.perf_counter()
+        upload(0)
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                upload(i + 1)
+            b = i % 2
+            torch.cuda.current_stream().wait_event(ready[b])
+            l = step(dx[b], dy[b])
+            free[b].record()
+            _ = l.item()                       # device -> host read of the step's result, every step
+        barrier()
+        dt_e2e = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_e2e = t.item()
+        e2e = {"value": world * B * args.steps / dt_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 8), "d2h_bytes_per_step": 4}
+
+    _lib.set_hook(None)
+    # ---- rooflines -------------------------------------------------------------------------------------------
+    pk = peaks()
+    table = acct.summary()
+    tms = sum(d["ms"] for d in table.values() if d["class"] == "tensor")
+    tfl = sum(d["flops"] for d in table.values() if d["class"] == "tensor")
+    hms = sum(d["ms"] for d in table.values() if d["class"] == "hbm")
+    hby = sum(d["bytes"] for d in table.values() if d["class"] == "hbm")
+    ncalls_t = sum(d["calls"] for d in table.values() if d["class"] == "tensor")
+    ncalls_h = sum(d["calls"] for d in table.values() if d["class"] == "hbm")
+    ach_t = tfl / (tms * 1e-3) / 1e12 if tms else 0.0
+    ach_h = hby / (hms * 1e-3) / 1e9 if hms else 0.0
+    roof = {"bound": "tensor", "achieved": ach_t, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+            "frac": ach_t / pk["tflops_sustained"], "traffic": None,
+            "kernel": "tc_kernel<BLOCK_N,WGRAD> (tcgen05 implicit-GEMM conv3x3 fwd/dgrad/wgrad, ConvTranspose2d)",
+            "launches": ncalls_t, "avg_launch_ms": tms / max(ncalls_t, 1), "share_of_step": tms / ms,
+            "flops_per_launch_avg": tfl / max(ncalls_t, 1), "peak_source": pk["source"] + " bf16_tflops_sustained"}
+    roof_h = {"bound": "hbm", "achieved": ach_h, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_h / pk["hbm_gbs"],
+              "traffic": None, "kernel": "BN/ReLU/SE/max-pool/outc/CE elementwise and reduction kernels (aggregate)",
+              "launches": ncalls_h, "share_of_step": hms / ms, "peak_source": pk["source"] + " hbm_gbs"}
+    if args.kernel_table and rank == 0:
+        with open(args.kernel_table, "w") as f:
+            json.dump({k: {**v, "ms_per_step": v["ms"] / args.steps} for k, v in table.items()}, f, indent=1)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        times, sb = cpu_reference_step_time(2, 1, S)
+        v = sb * len(times) / sum(times)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{sb} images of 3x{S}x{S} per step (of the {B}-image batch), fp32 fwd+CE+bwd+Adam, 2 timed steps "
+                         f"after 1 warm-up, ATen CPU kernels via oracle/unet_ca_port.py"}
+
+    if rank == 0:
+        gflop_img = TRAIN_GFLOP_PER_IMG_512 * (S * S) / (512 * 512)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: U-Net-CA (use_se=True) train step fwd+CE+bwd+Adam(lr=1e-4), "
+                                   f"batch {B}/GPU, 3x{S}x{S}, 2 classes, {args.precision} mode",
+                       "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "working set (~50 GB of activations per step) >> 126 MB L2; no explicit flush"},
+            "tensor_util_step": value / world * gflop_img * 1e9 / (pk["tflops_sustained"] * 1e12),
+            "roofline": roof, "roofline_hbm": roof_h, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clk, "final_loss": final_loss,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -75,10 +75,31 @@ def last_error() -> str:
     return load().unetca_last_error().decode()
 
 
+# kernels launched per entry point (default 1) — used for the launch count bench.py reports
+_LAUNCHES = {
+    "unetca_conv3x3_wgrad": 2, "unetca_im2col_wgrad": 2, "unetca_convT2x2_wgrad": 2, "unetca_chan_sum": 2,
+    "unetca_se_fc_bwd": 2, "unetca_outc_bwd": 2, "unetca_cross_entropy": 2,
+}
+launch_count = 0
+_hook = None
+
+
+def set_hook(fn):
+    """fn(name, args) -> context manager entered around the call (bench.py times kernels with CUDA events)."""
+    global _hook
+    _hook = fn
+
+
 def call(name: str, *args):
     """Call an int-returning entry point; negative return -> RuntimeError with the library's message."""
+    global launch_count
     fn = getattr(load(), name)
-    rc = fn(*args)
+    launch_count += _LAUNCHES.get(name, 1)
+    if _hook is not None:
+        with _hook(name, args):
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
     if rc is not None and rc < 0:
         raise RuntimeError(f"{name} failed ({rc}): {last_error()}")
     return rc

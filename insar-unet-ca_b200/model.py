@@ -296,8 +296,16 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
 # =======================================================================================================
 # backward
 # =======================================================================================================
-def _double_conv_bwd(eng, sv, dout, grads, dt, tdt, need_dx):
-    """Gradient of one DoubleConv block; dout is d(loss)/d(block output) (NHWC view).  Returns d/d(block input)."""
+def _block_grad_order(pre, use_se):
+    """Order in which _double_conv_bwd completes the parameter gradients of one block (DP buckets follow it)."""
+    out = [pre + ".6.fc.0.weight", pre + ".6.fc.2.weight"] if use_se else []
+    return out + [pre + ".4.weight", pre + ".4.bias", pre + ".3.bias", pre + ".0.bias", pre + ".3.weight",
+                  pre + ".1.weight", pre + ".1.bias", pre + ".0.weight"]
+
+
+def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
+    """Gradient of one DoubleConv block; dout is d(loss)/d(block output) (NHWC view).  Returns d/d(block input).
+    G: gradient sink with alloc(name, like) -> tensor to write into and put(name) once it is complete."""
     blk = sv.blk
     B, Hl, Wl = sv.B, sv.H, sv.W
     C, O = blk.cin, blk.cout
@@ -317,12 +325,12 @@ def _double_conv_bwd(eng, sv, dout, grads, dt, tdt, need_dx):
         dpre2 = torch.empty(B, O, dtype=torch.float32, device=dev)
         dz = torch.empty(B, Cr, dtype=torch.float32, device=dev)
         dp = torch.empty(B, O, dtype=torch.float32, device=dev)
-        dw1 = torch.empty_like(w1)
-        dw2 = torch.empty_like(w2)
+        dw1 = G.alloc(pre + ".6.fc.0.weight", w1)
+        dw2 = G.alloc(pre + ".6.fc.2.weight", w2)
         _lib.call("unetca_se_fc_bwd", _ptr(parts), nparts.value, B, O, Cr, _ptr(w1), _ptr(w2), _ptr(sv.p), _ptr(sv.z),
                   _ptr(sv.s), _ptr(dpre2), _ptr(dz), _ptr(dp), _ptr(dw1), _ptr(dw2), st)
-        grads[pre + ".6.fc.0.weight"] = dw1
-        grads[pre + ".6.fc.2.weight"] = dw2
+        G.put(pre + ".6.fc.0.weight")
+        G.put(pre + ".6.fc.2.weight")
         s = sv.s
 
     def bn_relu_bwd(d_in, ld_in, y, tag, s_, dp_, bn_idx):
@@ -331,27 +339,29 @@ def _double_conv_bwd(eng, sv, dout, grads, dt, tdt, need_dx):
         bn = blk.bn1 if tag == "1" else blk.bn2
         _lib.call("unetca_bn_bwd_reduce", dt, _ptr(d_in), ld_in, _ptr(y), O, B, Hl * Wl, O, _ptr(scale), _ptr(shift),
                   _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(parts), ctypes.byref(nparts), st)
-        dgamma = torch.empty(O, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(O, dtype=torch.float32, device=dev)
+        dgamma = G.alloc(f"{pre}.{bn_idx}.weight", bn.weight)
+        dbeta = G.alloc(f"{pre}.{bn_idx}.bias", bn.bias)
         coef = torch.empty(3, O, dtype=torch.float32, device=dev)
         _lib.call("unetca_bn_bwd_finalize", _ptr(parts), nparts.value, O, npix, _ptr(bn.weight), _ptr(invstd),
                   _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
         dy = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
         _lib.call("unetca_bn_bwd_apply", dt, _ptr(d_in), ld_in, _ptr(y), O, _ptr(dy), O, B, Hl * Wl, O, _ptr(scale),
                   _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(coef), st)
-        grads[f"{pre}.{bn_idx}.weight"] = dgamma
-        grads[f"{pre}.{bn_idx}.bias"] = dbeta
+        G.put(f"{pre}.{bn_idx}.weight")
+        G.put(f"{pre}.{bn_idx}.bias")
         return dy
 
     # ---- [SE ->] ReLU -> BN2 backward
     dy2 = bn_relu_bwd(dout, dout.stride(2), sv.y2, "2", s, dp, 4)
     # a conv bias in front of a train-mode BatchNorm has an analytically zero gradient (BN removes the mean)
-    grads[pre + ".3.bias"] = torch.zeros(O, dtype=torch.float32, device=dev)
-    grads[pre + ".0.bias"] = torch.zeros(O, dtype=torch.float32, device=dev)
+    G.alloc(pre + ".3.bias", blk.conv2.bias).zero_()
+    G.put(pre + ".3.bias")
+    G.alloc(pre + ".0.bias", blk.conv1.bias).zero_()
+    G.put(pre + ".0.bias")
     # ---- conv2 wgrad + dgrad
-    dw = torch.empty_like(blk.conv2.weight)
+    dw = G.alloc(pre + ".3.weight", blk.conv2.weight)
     _lib.call("unetca_conv3x3_wgrad", dt, _ptr(dy2), O, _ptr(sv.a1), O, _ptr(ws), ws.numel(), B, Hl, Wl, O, O, _ptr(dw), st)
-    grads[pre + ".3.weight"] = dw
+    G.put(pre + ".3.weight")
     _, wd2, _ = eng.conv_w(blk.conv2, dt, tdt, False)
     da1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
     _lib.call("unetca_conv3x3_fwd", dt, _ptr(dy2), O, _ptr(wd2), 9 * O, _ptr(da1), O, B, Hl, Wl, O, O, None, None, st)
@@ -360,14 +370,14 @@ def _double_conv_bwd(eng, sv, dout, grads, dt, tdt, need_dx):
     dy1 = bn_relu_bwd(da1, O, sv.y1, "1", None, None, 1)
     del da1
     # ---- conv1 wgrad (+ dgrad)
-    dw = torch.empty_like(blk.conv1.weight)
+    dw = G.alloc(pre + ".0.weight", blk.conv1.weight)
     if blk.first:
         _lib.call("unetca_im2col_wgrad", dt, _ptr(dy1), O, _ptr(sv.col), sv.col.shape[1], _ptr(ws), ws.numel(), npix, C, O,
                   _ptr(dw), st)
     else:
         _lib.call("unetca_conv3x3_wgrad", dt, _ptr(dy1), O, _ptr(sv.xin), sv.xin.stride(2), _ptr(ws), ws.numel(), B, Hl,
                   Wl, C, O, _ptr(dw), st)
-    grads[pre + ".0.weight"] = dw
+    G.put(pre + ".0.weight")
     if not need_dx or blk.first:
         return None
     _, wd1, _ = eng.conv_w(blk.conv1, dt, tdt, False)
@@ -376,49 +386,81 @@ def _double_conv_bwd(eng, sv, dout, grads, dt, tdt, need_dx):
     return dx
 
 
+class _GradSink:
+    """Default gradient sink: fresh tensors, nothing to do when one completes.  parallel.GradBuckets replaces it with
+    views into flat all-reduce buckets and launches the collective as each bucket fills."""
+
+    def __init__(self):
+        self.grads = {}
+
+    def alloc(self, name, like):
+        t = torch.empty_like(like)
+        self.grads[name] = t
+        return t
+
+    def put(self, name):
+        pass
+
+    def finish(self):
+        return self.grads
+
+
+def grad_order(model: "UNet"):
+    """Parameter names in the order _backward completes their gradients."""
+    names = ["outc.weight", "outc.bias"]
+    for l in range(4):
+        i = 3 - l
+        names += _block_grad_order(model._dec_blocks[i].prefix, model.use_se)
+        names += [model._up_names[i] + ".bias", model._up_names[i] + ".weight"]
+    for l in range(4, -1, -1):
+        names += _block_grad_order(model._enc_blocks[l].prefix, model.use_se)
+    return names
+
+
 def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
     """loss.backward() (UCA:345) for every parameter.  g: (B,nc,H,W) fp32 dlogits up to the factor *gscale."""
+    G = model._grad_sink_factory() if model._grad_sink_factory is not None else _GradSink()
     eng = model._engine()
     dt, tdt = model._dt()
     dev = g.device
     st = _stream()
     B, H, W = sv.B, sv.H, sv.W
-    grads = {}
     nc = model.num_classes
     parts = eng.parts(B, dev)
     ws = eng.ws(dev)
     # ---- outc
     h = sv.dec_out
     dcur = torch.empty(B, H, W, 64, dtype=tdt, device=dev)
-    dw = torch.empty_like(model.outc.weight)
-    db = torch.empty_like(model.outc.bias)
+    dw = G.alloc("outc.weight", model.outc.weight)
+    db = G.alloc("outc.bias", model.outc.bias)
     _lib.call("unetca_outc_bwd", dt, _ptr(g), _ptr(gscale), _ptr(h), h.stride(2), _ptr(dcur), 64, 64,
               _ptr(model.outc.weight), nc, B, H * W, _ptr(parts), _ptr(dw), _ptr(db), st)
-    grads["outc.weight"], grads["outc.bias"] = dw, db
+    G.put("outc.weight")
+    G.put("outc.bias")
     # ---- decoder, shallow to deep
     skip_grads = [None] * 4
     for l in range(4):
         i = 3 - l
         up, name = model._ups[i], model._up_names[i]
         Hl, Wl, Cl = H >> l, W >> l, _WIDTHS[l]
-        dcat = _double_conv_bwd(eng, sv.dec[i], dcur, grads, dt, tdt, True)      # (B,Hl,Wl,2Cl)
+        dcat = _double_conv_bwd(eng, sv.dec[i], dcur, G, dt, tdt, True)          # (B,Hl,Wl,2Cl)
         du = dcat[..., Cl:]
         skip_grads[l] = dcat[..., :Cl]
-        dbias = torch.empty_like(up.bias)
+        dbias = G.alloc(name + ".bias", up.bias)
         _lib.call("unetca_chan_sum", dt, _ptr(du), 2 * Cl, Cl, B * Hl * Wl, _ptr(parts), _ptr(dbias), st)
-        grads[name + ".bias"] = dbias
+        G.put(name + ".bias")
         up_in = sv.up_in[i]
-        dwu = torch.empty_like(up.weight)
+        dwu = G.alloc(name + ".weight", up.weight)
         _lib.call("unetca_convT2x2_wgrad", dt, _ptr(up_in), up_in.stride(2), _ptr(du), 2 * Cl, _ptr(ws), ws.numel(), B,
                   Hl // 2, Wl // 2, 2 * Cl, Cl, _ptr(dwu), st)
-        grads[name + ".weight"] = dwu
+        G.put(name + ".weight")
         _, wd = eng.convT_w(up, dt, tdt)
         dcur = torch.empty(B, Hl // 2, Wl // 2, 2 * Cl, dtype=tdt, device=dev)
         _lib.call("unetca_convT2x2_dgrad", dt, _ptr(du), 2 * Cl, _ptr(wd), _ptr(dcur), 2 * Cl, B, Hl // 2, Wl // 2, 2 * Cl,
                   Cl, st)
     # ---- encoder, deep to shallow
     for l in range(4, -1, -1):
-        dpooled = _double_conv_bwd(eng, sv.enc[l], dcur, grads, dt, tdt, l > 0)
+        dpooled = _double_conv_bwd(eng, sv.enc[l], dcur, G, dt, tdt, l > 0)
         if l == 0:
             break
         Hp, Wp, Cp = H >> (l - 1), W >> (l - 1), _WIDTHS[l - 1]
@@ -426,7 +468,7 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
         sg = skip_grads[l - 1]
         _lib.call("unetca_pool_bwd_add", dt, _ptr(sg), sg.stride(2), _ptr(dpooled), Cp, _ptr(sv.pos[l - 1]), _ptr(dcur),
                   Cp, B, Hp, Wp, Cp, st)
-    return grads
+    return G.finish()
 
 
 class _UNetFn(torch.autograd.Function):
@@ -509,6 +551,7 @@ class UNet(nn.Module):
         object.__setattr__(self, "precision", "bf16")
         object.__setattr__(self, "last_logits", None)
         object.__setattr__(self, "_eng", None)
+        object.__setattr__(self, "_grad_sink_factory", None)     # set by parallel.GradBuckets (data parallel)
         enc = [("inc.double_conv", self.inc), ("down1.1.double_conv", self.down1[1]),
                ("down2.1.double_conv", self.down2[1]), ("down3.1.double_conv", self.down3[1]),
                ("down4.1.double_conv", self.down4[1])]
