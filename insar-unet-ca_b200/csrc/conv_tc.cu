@@ -165,7 +165,8 @@ template <int BLOCK_N, bool WGRAD> struct TcCfg {
     static constexpr int B_BYTES = WGRAD ? (BLOCK_N / 64) * kBoxBytesWg : BLOCK_N * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_BYTES = WGRAD ? 0 : (BLOCK_N / 64) * kBoxBytesFwd;
-    static constexpr int STAT_BYTES = WGRAD ? 0 : 2 * 1024 * 4;        // up to 1024 output channels
+    // per-CTA BatchNorm partial sums (up to 1024 channels) + bias[BLOCK_N] + per-warp partials [4][2][BLOCK_N]
+    static constexpr int STAT_BYTES = WGRAD ? 0 : 2 * 1024 * 4 + BLOCK_N * 4 + 8 * BLOCK_N * 4;
     static constexpr int BUDGET = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/ - OUT_BYTES - STAT_BYTES;
     static constexpr int STAGES_RAW = BUDGET / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -182,6 +183,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
     uint8_t* stage_base = smem;
     uint8_t* out_stage = smem + STAGES * Cfg::STAGE_BYTES;
     float* sm_stats = reinterpret_cast<float*>(out_stage + Cfg::OUT_BYTES);
+    float* sm_bias = sm_stats + 2048;
+    float* sm_wpart = sm_bias + BLOCK_N;
     uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::OUT_BYTES + Cfg::STAT_BYTES);
     uint64_t* full_bar = bars;                  // [STAGES]
     uint64_t* empty_bar = bars + STAGES;        // [STAGES]
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
                                 : (long)p.num_m_blocks * p.num_n_blocks;
     const int kt_per_split = WGRAD ? (p.ktiles_total + p.nsplit - 1) / p.nsplit : 0;
     const int kblocks_fwd = p.ntaps * p.cchunks;
+    const long mn_items = (long)p.num_m_blocks * p.num_n_blocks;   // weight gradient: the split index is the slow one
 
     if (warp == 0) {
         // ================================ TMA producer ================================
@@ -237,9 +241,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
                         }
                     }
                 } else {
-                    const int z = (int)(t % p.nsplit);
-                    const int nb = (int)((t / p.nsplit) % p.num_n_blocks);
-                    const int mb = (int)(t / ((long)p.nsplit * p.num_n_blocks));
+                    const int z = (int)(t / mn_items);
+                    const int nb = (int)((t % mn_items) % p.num_n_blocks);
+                    const int mb = (int)((t % mn_items) / p.num_n_blocks);
                     int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
                     if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
                     for (int kt = kt0; kt < kt1; ++kt) {
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
                 int nk;
                 if (!WGRAD) nk = kblocks_fwd;
                 else {
-                    const int z = (int)(t % p.nsplit);
+                    const int z = (int)(t / mn_items);
                     int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
                     if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
                     nk = kt1 - kt0;
@@ -329,29 +333,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
                 const bool valid = (h0 + r / p.TW) < p.H && (w0 + r % p.TW) < p.W;
                 // the staging buffer must have been drained by the previous tile's TMA store
                 if (ep_tid == 0) tma_store_wait_read();
+                if (ep_tid < BLOCK_N)
+                    sm_bias[ep_tid] = p.bias ? __ldg(p.bias + (nb * BLOCK_N + ep_tid) % p.bias_mod) : 0.f;
                 named_bar_sync(1, 128);
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < BLOCK_N / 64; ++j) {
+                    uint32_t v[2][32];
+                    tmem_ld32(t_addr + j * 64, v[0]);
+                    tmem_ld32(t_addr + j * 64 + 32, v[1]);
+                    tmem_wait_ld();
+                    uint8_t* row = out_stage + j * kBoxBytesFwd + r * 128;
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
-                        uint32_t v[32];
-                        tmem_ld32(t_addr + j * 64 + half * 32, v);
-                        tmem_wait_ld();
-                        const int ncol0 = nb * BLOCK_N + j * 64 + half * 32;
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(sm_bias + j * 64 + half * 32 + c * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(sm_bias + j * 64 + half * 32 + c * 8 + 4);
+                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
                             float f[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                f[i] = __uint_as_float(v[c * 8 + i]);
-                                if (p.bias) f[i] += __ldg(p.bias + (ncol0 + c * 8 + i) % p.bias_mod);
-                                if (!valid) f[i] = 0.f;
-                            }
+                            for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(v[half][c * 8 + i]) + bb[i] : 0.f;
                             uint4 pk;
                             pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
                             pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
                             const int chunk = half * 4 + c;
-                            *reinterpret_cast<uint4*>(out_stage + j * kBoxBytesFwd + r * 128 + ((chunk ^ (r & 7)) << 4)) = pk;
+                            *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = pk;
                         }
                     }
                 }
@@ -363,30 +369,64 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
                 if (ep_tid == 0) {
                     const int om = nb / p.n_blocks_per_outmap;
                     const int c0 = (nb % p.n_blocks_per_outmap) * BLOCK_N;
-#pragma unroll
+#pragma unroll 1
                     for (int j = 0; j < BLOCK_N / 64; ++j)
                         tma_store_4d(&p.mapOut[om], out_stage + j * kBoxBytesFwd, c0 + j * 64, w0, h0, b);
                     tma_store_commit();
                 }
                 if (p.stat_parts) {
-                    for (int col = ep_tid; col < BLOCK_N; col += 128) {
-                        const uint8_t* base = out_stage + (col >> 6) * kBoxBytesFwd + (col & 7) * 2;
-                        const int chunk = (col & 63) >> 3;
-                        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-                        for (int rr = 0; rr < 128; ++rr) {
-                            const float x = __bfloat162float(
-                                *reinterpret_cast<const bf16*>(base + rr * 128 + ((chunk ^ (rr & 7)) << 4)));
-                            s1 += x; s2 = fmaf(x, x, s2);
+                    // per-channel sum / sum-of-squares of the staged bf16 tile: thread -> one 16-byte chunk (8 channels)
+                    // of every RSTEP-th row; lanes sharing a chunk are folded by shuffles, warps by shared memory.
+                    constexpr int NCH = BLOCK_N / 8;            // chunks per pixel row over all boxes
+                    constexpr int RSTEP = 128 / NCH;            // threads per chunk
+                    const int ch = ep_tid % NCH, r0 = ep_tid / NCH;
+                    const uint8_t* base = out_stage + (ch >> 3) * kBoxBytesFwd;
+                    float s1[8], s2[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+#pragma unroll 4
+                    for (int rr = r0; rr < 128; rr += RSTEP) {
+                        const uint4 t4 = *reinterpret_cast<const uint4*>(base + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4));
+                        const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xffff0000u);
+                            s1[2 * i] += lo; s2[2 * i] = fmaf(lo, lo, s2[2 * i]);
+                            s1[2 * i + 1] += hi; s2[2 * i + 1] = fmaf(hi, hi, s2[2 * i + 1]);
                         }
-                        sm_stats[nb * BLOCK_N + col] += s1;
-                        sm_stats[p.N + nb * BLOCK_N + col] += s2;
+                    }
+                    if (NCH < 32) {
+#pragma unroll
+                        for (int off = NCH; off < 32; off <<= 1) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+                                s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+                            }
+                        }
+                    }
+                    // one partial per (warp, chunk); for NCH == 32 every lane owns a distinct chunk
+                    const int ew = ep_tid >> 5;
+                    if (lane < NCH || NCH >= 32) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            sm_wpart[(ew * 2 + 0) * BLOCK_N + ch * 8 + i] = s1[i];
+                            sm_wpart[(ew * 2 + 1) * BLOCK_N + ch * 8 + i] = s2[i];
+                        }
+                    }
+                    named_bar_sync(1, 128);
+                    for (int i = ep_tid; i < 2 * BLOCK_N; i += 128) {
+                        const int which = i / BLOCK_N, col = i % BLOCK_N;
+                        float tsum = 0.f;
+#pragma unroll
+                        for (int w4i = 0; w4i < 4; ++w4i) tsum += sm_wpart[(w4i * 2 + which) * BLOCK_N + col];
+                        sm_stats[which * p.N + nb * BLOCK_N + col] += tsum;
                     }
                 }
             } else {
-                const int z = (int)(t % p.nsplit);
-                const int nb = (int)((t / p.nsplit) % p.num_n_blocks);
-                const int mb = (int)(t / ((long)p.nsplit * p.num_n_blocks));
+                const int z = (int)(t / mn_items);
+                const int nb = (int)((t % mn_items) % p.num_n_blocks);
+                const int mb = (int)((t % mn_items) / p.num_n_blocks);
                 int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
                 if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
                 const bool have = kt1 > kt0;

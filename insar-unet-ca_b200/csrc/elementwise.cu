@@ -89,6 +89,38 @@ __global__ void __launch_bounds__(kThreads) chan_stats_kernel(const T* __restric
     block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + (long)blockIdx.x * 2 * C);
 }
 
+
+// Sum NSTAT interleaved partial rows parts[i][s][C] over i for 32 consecutive channels per block: thread (cl, pl) walks
+// parts pl, pl+8, ... (coalesced 128-byte reads), then the 8 part-lanes are folded through shared memory in double.
+// blockDim = 256, grid = ceil(C/32).  Returns the totals of channel c = blockIdx.x*32 + (tid & 31) to threads < 32.
+template <int NSTAT>
+__device__ __forceinline__ bool sum_parts32(const float* __restrict__ parts, int nparts, int C, double (&tot)[NSTAT]) {
+    __shared__ double red[NSTAT][8][32];
+    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double acc[NSTAT];
+#pragma unroll
+    for (int s = 0; s < NSTAT; ++s) acc[s] = 0.0;
+    if (c < C) {
+        for (int i = pl; i < nparts; i += 8) {
+#pragma unroll
+            for (int s = 0; s < NSTAT; ++s) acc[s] += (double)parts[((long)i * NSTAT + s) * C + c];
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NSTAT; ++s) red[s][pl][cl] = acc[s];
+    __syncthreads();
+    if (pl != 0 || c >= C) return false;
+#pragma unroll
+    for (int s = 0; s < NSTAT; ++s) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[s][k][cl];
+        tot[s] = t;
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // BN finalize (train): batch mean / biased var from partial sums, running-stat update with the unbiased
 // variance (momentum 0.1), and the fused affine a = gamma*invstd, b = beta - mean*a.      UCA:82,85
@@ -100,13 +132,10 @@ __global__ void bn_finalize_train_kernel(const float* __restrict__ parts, int np
                                          const float* __restrict__ beta, float* running_mean, float* running_var,
                                          float momentum, float eps, float* mean_out, float* invstd_out,
                                          float* scale_out, float* shift_out) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int i = 0; i < nparts; ++i) {
-        s += (double)parts[(long)i * 2 * C + c];
-        q += (double)parts[(long)i * 2 * C + C + c];
-    }
+    double tot[2];
+    if (!sum_parts32<2>(parts, nparts, C, tot)) return;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const double s = tot[0], q = tot[1];
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -550,13 +579,10 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ parts, int npar
                                        const float* __restrict__ gamma, const float* __restrict__ invstd,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int i = 0; i < nparts; ++i) {
-        s += (double)parts[(long)i * 2 * C + c];
-        q += (double)parts[(long)i * 2 * C + C + c];
-    }
+    double tot[2];
+    if (!sum_parts32<2>(parts, nparts, C, tot)) return;
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    const double s = tot[0], q = tot[1];
     dbeta[c] = (float)s;
     dgamma[c] = (float)q;
     coef[c] = gamma[c] * invstd[c];
@@ -590,11 +616,10 @@ __global__ void __launch_bounds__(kThreads) chan_sum_kernel(const T* __restrict_
 // out[i] = scale * sum_parts parts[p][i]      (generic deterministic second stage)
 __global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, int n, const float* __restrict__ scale_ptr,
                                  float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double t = 0.0;
-    for (int p = 0; p < nparts; ++p) t += (double)parts[(long)p * n + i];
-    out[i] = (float)(t * (scale_ptr ? (double)*scale_ptr : 1.0));
+    double tot[1];
+    if (!sum_parts32<1>(parts, nparts, n, tot)) return;
+    const int i = blockIdx.x * 32 + (threadIdx.x & 31);
+    out[i] = (float)(tot[0] * (scale_ptr ? (double)*scale_ptr : 1.0));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -718,18 +743,18 @@ __global__ void __launch_bounds__(kThreads) outc_bwd_kernel(const float* __restr
 __global__ void outc_bwd_finalize_kernel(const float* __restrict__ parts, int nparts, int NCpad, int nc, int C,
                                          const float* __restrict__ gscale, float* __restrict__ dw,
                                          float* __restrict__ db) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per output element; lanes stride over the partial rows
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= nc * C + nc) return;
     const int stride = NCpad * C + NCpad;
-    const double gs = (double)*gscale;
-    if (i < nc * C) {
-        double t = 0.0;
-        for (int p = 0; p < nparts; ++p) t += (double)parts[(long)p * stride + i];
-        dw[i] = (float)(t * gs);
-    } else if (i < nc * C + nc) {
-        const int o = i - nc * C;
-        double t = 0.0;
-        for (int p = 0; p < nparts; ++p) t += (double)parts[(long)p * stride + NCpad * C + o];
-        db[o] = (float)(t * gs);
+    const int src = i < nc * C ? i : NCpad * C + (i - nc * C);
+    double t = 0.0;
+    for (int p = lane; p < nparts; p += 32) t += (double)parts[(long)p * stride + src];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) {
+        const float v = (float)(t * (double)*gscale);
+        if (i < nc * C) dw[i] = v; else db[i - nc * C] = v;
     }
 }
 
@@ -785,9 +810,13 @@ __global__ void __launch_bounds__(kThreads) ce_kernel(const float* __restrict__ 
 }
 __global__ void ce_finalize_kernel(const float* __restrict__ parts, int nparts, const float* __restrict__ upstream,
                                    float* __restrict__ loss, float* __restrict__ gscale) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    // one warp
+    const int lane = threadIdx.x;
     double a = 0.0, c = 0.0;
-    for (int i = 0; i < nparts; ++i) { a += (double)parts[2 * i]; c += (double)parts[2 * i + 1]; }
+    for (int i = lane; i < nparts; i += 32) { a += (double)parts[2 * i]; c += (double)parts[2 * i + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); c += __shfl_xor_sync(0xffffffffu, c, o); }
+    if (lane != 0) return;
     const float n = (float)c;
     loss[0] = (float)a / n;
     loss[1] = n;
@@ -802,20 +831,30 @@ __global__ void ce_finalize_kernel(const float* __restrict__ parts, int nparts, 
 template <typename T>
 __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, T* __restrict__ col, int B, int Cin, int H, int W,
                                       int Kpad) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int cpr = Kpad / VEC;                                   // 16-byte chunks per im2col row
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long total = (long)B * H * W * Kpad;
+    const long total = (long)B * H * W * cpr;
     if (i >= total) return;
-    const int k = (int)(i % Kpad);
-    const long p = i / Kpad;
-    float v = 0.f;
-    if (k < 9 * Cin) {
-        const int tap = k / Cin, c = k % Cin;
+    const int j = (int)(i % cpr);
+    const long p = i / cpr;
+    float v[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) v[e] = 0.f;
+    if (j * VEC < 9 * Cin) {
         const int w = (int)(p % W), h = (int)((p / W) % H);
         const long b = p / ((long)W * H);
-        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
-        if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = x[((b * Cin + c) * H + hh) * W + ww];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+            const int k = j * VEC + e;
+            if (k < 9 * Cin) {
+                const int tap = k / Cin, c = k % Cin;
+                const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) v[e] = __ldg(x + ((b * Cin + c) * H + hh) * W + ww);
+            }
+        }
     }
-    col[i] = from_float<T>(v);
+    store_vec(col + p * Kpad + j * VEC, v);
 }
 // NCHW fp32 -> NHWC T (generic; used for inputs with Cin a multiple of the vector width and in tests)
 template <typename T>
@@ -930,7 +969,7 @@ int unetca_bn_finalize_train(const float* parts, int nparts, int C, long count, 
                              float momentum, float eps, float* mean, float* invstd, float* scale, float* shift,
                              void* stream) {
     UNETCA_REQUIRE(count > 1, "Expected more than 1 value per channel when training, got %ld", count);
-    bn_finalize_train_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+    bn_finalize_train_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(
         parts, nparts, C, (double)count, conv_bias, gamma, beta, running_mean, running_var, momentum, eps, mean, invstd,
         scale, shift);
     return check_launch("bn_finalize_train");
@@ -1058,7 +1097,7 @@ int unetca_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, in
 
 int unetca_bn_bwd_finalize(const float* parts, int nparts, int C, long count, const float* gamma, const float* invstd,
                            float* dgamma, float* dbeta, float* coef, void* stream) {
-    bn_bwd_finalize_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(parts, nparts, C, (double)count, gamma,
+    bn_bwd_finalize_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(parts, nparts, C, (double)count, gamma,
                                                                              invstd, dgamma, dbeta, coef);
     return check_launch("bn_bwd_finalize");
 }
@@ -1088,7 +1127,7 @@ int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* p
         const int nblk = ceil_div(npix, chunk);
         cudaStream_t st = (cudaStream_t)stream;
         chan_sum_kernel<T><<<nblk, kThreads, 0, st>>>((const T*)x, ld, C, npix, chunk, parts);
-        sum_parts_kernel<<<ceil_div(C, 128), 128, 0, st>>>(parts, nblk, C, nullptr, out);
+        sum_parts_kernel<<<ceil_div(C, 32), 256, 0, st>>>(parts, nblk, C, nullptr, out);
     });
     return check_launch("chan_sum");
 }
@@ -1126,7 +1165,7 @@ int unetca_outc_bwd(int dtype, const float* g, const float* gscale, const void* 
         if (ncp == 2) outc_bwd_kernel<T, 2><<<nblk, kThreads, 0, st>>>(g, gscale, (const T*)x, ldx, (T*)dx, lddx, C, w, nc, npix, HW, chunk, parts);
         else if (ncp == 4) outc_bwd_kernel<T, 4><<<nblk, kThreads, 0, st>>>(g, gscale, (const T*)x, ldx, (T*)dx, lddx, C, w, nc, npix, HW, chunk, parts);
         else outc_bwd_kernel<T, 8><<<nblk, kThreads, 0, st>>>(g, gscale, (const T*)x, ldx, (T*)dx, lddx, C, w, nc, npix, HW, chunk, parts);
-        outc_bwd_finalize_kernel<<<ceil_div(nc * C + nc, 128), 128, 0, st>>>(parts, nblk, ncp, nc, C, gscale, dw, db);
+        outc_bwd_finalize_kernel<<<ceil_div((long)(nc * C + nc) * 32, 128), 128, 0, st>>>(parts, nblk, ncp, nc, C, gscale, dw, db);
     });
     return check_launch("outc_bwd");
 }
@@ -1149,7 +1188,8 @@ int unetca_cross_entropy(const float* logits, const long long* target, int nc, i
 int unetca_im2col3x3_nchw(int dtype, const float* x, void* col, int B, int Cin, int H, int W, int Kpad, void* stream) {
     UNETCA_REQUIRE(Kpad >= 9 * Cin, "im2col: Kpad %d < 9*Cin", Kpad);
     DISPATCH_T(dtype, {
-        const long total = (long)B * H * W * Kpad;
+        UNETCA_REQUIRE(Kpad % VecTraits<T>::N == 0, "im2col: Kpad %d must be a multiple of %d", Kpad, VecTraits<T>::N);
+        const long total = (long)B * H * W * (Kpad / VecTraits<T>::N);
         im2col3x3_nchw_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)col, B, Cin, H, W, Kpad);
     });
     return check_launch("im2col3x3_nchw");
