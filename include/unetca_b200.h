@@ -104,6 +104,7 @@ int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out
 int unetca_tc_convT_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h, int wd, int Cin, int Cout, void* stream);
 int unetca_tc_convT_dgrad(const void* dout, int ldd, const void* wdg, void* dx, int ldx, int B, int h, int wd, int Cin, int Cout, void* stream);
 int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H, int W, int C, int O, void* stream);
+int unetca_tc_conv3x3_wgrad_generic(const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H, int W, int C, int O, void* stream);
 int unetca_tc_gemm_tn(const void* A, int lda, const void* Bm, int ldb, float* ws, long ws_floats, int M, int N, long K, void* stream);
 int unetca_tc_convT_wgrad(const void* x, int ldx, const void* dout, int ldd, float* ws, long ws_floats, int B, int h, int wd, int Cin, int Cout, void* stream);
 int unetca_simt_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, void* stream);

@@ -373,6 +373,162 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// conv3x3 weight gradient with tap reuse from ONE haloed activation tile                        (UCA:345)
+//   dW[o][tap][c] = sum_p dY[p][o] * X[p + s(tap)][c]
+// A 16x8-pixel tile of dY ([128 px][64 o], 16 KB) and the 18x10 haloed tile of X ([180 px][64 c], 23 KB) are
+// loaded ONCE per k-tile; all 9 taps are then issued from that single X tile by shifting the start address of
+// the MN-major descriptor by whole 128-byte pixel rows ((kh*18 + kw) rows) — the tcgen05 SWIZZLE_128B XOR is a
+// function of the absolute shared-memory address, so any row shift (and any LBO/SBO that is a multiple of 128 B)
+// addresses the data TMA wrote (verified on B200 by tools/umma_shift_probe.cu, profiles/r1_umma_shift_probe.txt).
+// The M=128 rows of one MMA are TWO taps x 64 channels: the second 64-row block is the same tile shifted by
+// LBO = (s(tap') - s(tap)) * 128 bytes.  Five such M-blocks ((0,1),(2,3),(4,5),(6,7),(7,8)) x N=64 output channels
+// = 320 TMEM columns hold the whole 9-tap gradient of a (64 c, 64 o) block while the CTA streams its pixel range.
+// Shared-memory fill drops from 9 boxes per tap-set to 1.4, which is what bounded the generic kernel (L2->SM).
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) Wg3Params {
+    CUtensorMap mapX, mapDY;
+    int cchunks, oblocks;
+    int tilesW, tilesH, nimg;
+    int ktiles_total, nsplit;
+    float* ws;
+    long long split_stride;
+    int ldn, C;
+};
+constexpr int kWgTW = 16, kWgTH = 8, kWgPitch = kWgTW + 2;
+constexpr int kWgXBox = kWgPitch * (kWgTH + 2) * 128;      // 23040 bytes actually written by TMA
+constexpr int kWgXBytes = 24 * 1024;                       // slot (keeps every tile 1024-byte aligned)
+constexpr int kWgYBytes = kWgTW * kWgTH * 128;             // 16 KB
+constexpr int kWgStageBytes = kWgXBytes + kWgYBytes;
+constexpr int kWgStages = 5;
+constexpr int kWgSmemBytes = 1024 + kWgStages * kWgStageBytes + 256;
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_kernel(const __grid_constant__ Wg3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWgStages * kWgStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWgStages;
+    uint64_t* tfull_bar = bars + 2 * kWgStages;
+    uint64_t* tempty_bar = bars + 2 * kWgStages + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapDY);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const long items = (long)p.cchunks * p.oblocks;
+    const long num_work = items * p.nsplit;
+    const int kt_per_split = (p.ktiles_total + p.nsplit - 1) / p.nsplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / items), item = (int)(t % items);
+                const int ob = item % p.oblocks, cc = item / p.oblocks;
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    const int tw = kt % p.tilesW, th = (kt / p.tilesW) % p.tilesH, b = kt / tiles_per_img;
+                    const int w0 = tw * kWgTW, h0 = th * kWgTH;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* xs = smem + s * kWgStageBytes;
+                    mbar_expect_tx(&full_bar[s], kWgXBox + kWgYBytes);
+                    tma_load_4d(&p.mapX, &full_bar[s], xs, cc * 64, w0 - 1, h0 - 1, b);
+                    tma_load_4d(&p.mapDY, &full_bar[s], xs + kWgXBytes, ob * 64, w0, h0, b);
+                    if (++s == kWgStages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
+            int s = 0; uint32_t ph = 0, aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / items);
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                mbar_wait(tempty_bar, aph ^ 1);
+                tcgen05_fence_after();
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t xs = smem_u32(smem + s * kWgStageBytes);
+                    const uint32_t ys = xs + kWgXBytes;
+#pragma unroll 1
+                    for (int hh = 0; hh < kWgTH; ++hh) {
+                        const uint64_t db = make_smem_desc(ys + hh * (kWgTW * 128), 8192, 1024);
+                        const uint32_t xrow = xs + hh * (kWgPitch * 128);
+                        const uint32_t acc = (kt > kt0 || hh > 0) ? 1u : 0u;
+                        // tap pairs (0,1) (2,3) (4,5) (6,7) (7,8): first-tap row shift kh*18+kw, LBO = shift difference
+                        umma_bf16(tmem_base + 0 * 64, make_smem_desc(xrow + (0 * kWgPitch + 0) * 128, 128, 1024), db, idesc, acc);
+                        umma_bf16(tmem_base + 1 * 64, make_smem_desc(xrow + (0 * kWgPitch + 2) * 128, (kWgPitch - 2) * 128, 1024), db, idesc, acc);
+                        umma_bf16(tmem_base + 2 * 64, make_smem_desc(xrow + (1 * kWgPitch + 1) * 128, 128, 1024), db, idesc, acc);
+                        umma_bf16(tmem_base + 3 * 64, make_smem_desc(xrow + (2 * kWgPitch + 0) * 128, 128, 1024), db, idesc, acc);
+                        umma_bf16(tmem_base + 4 * 64, make_smem_desc(xrow + (2 * kWgPitch + 1) * 128, 128, 1024), db, idesc, acc);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == kWgStages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull_bar);
+                aph ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int z = (int)(t / items), item = (int)(t % items);
+            const int ob = item % p.oblocks, cc = item / p.oblocks;
+            int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+            if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+            const bool have = kt1 > kt0;
+            mbar_wait(tfull_bar, aph);
+            tcgen05_fence_after();
+            float* wsz = p.ws + (long long)z * p.split_stride + (long long)(ob * 64) * p.ldn + cc * 64 + (r & 63);
+#pragma unroll 1
+            for (int mbk = 0; mbk < 5; ++mbk) {
+                const int tap = (mbk < 4 ? 2 * mbk : 7) + (r >> 6);
+                const bool rvalid = !(mbk == 4 && r < 64);
+                float* dst = wsz + tap * p.C;
+#pragma unroll
+                for (int c32 = 0; c32 < 2; ++c32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + mbk * 64 + c32 * 32, v);
+                    tmem_wait_ld();
+                    if (rvalid) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            dst[(long long)(c32 * 32 + i) * p.ldn] = have ? __uint_as_float(v[i]) : 0.f;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
+            aph ^= 1;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side: tensor maps, tiling, launch
 // ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -587,8 +743,41 @@ static int pick_nsplit(long tiles, int ktiles, long stride_floats, long ws_float
     return (int)s;
 }
 
-// ws[z][o][tap*C+c] = sum_{p in split z} dy[p][o] * x[p+s(tap)][c]; returns nsplit
+// ws[z][o][tap*C+c] = sum_{p in split z} dy[p][o] * x[p+s(tap)][c]; returns nsplit.  Halo-reuse kernel.
 int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H,
+                            int W, int C, int O, void* stream) {
+    UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0, "tc_conv3x3_wgrad: C=%d O=%d must be multiples of 64", C, O);
+    Wg3Params p;
+    memset(&p, 0, sizeof(p));
+    int rc;
+    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kWgPitch, kWgTH + 2)) < 0) return rc;
+    if ((rc = make_map(&p.mapDY, dy, O, W, H, B, lddy, (long)W * lddy, (long)H * W * lddy, kWgTW, kWgTH)) < 0) return rc;
+    p.cchunks = C / 64; p.oblocks = O / 64;
+    p.tilesW = ceil_div(W, kWgTW); p.tilesH = ceil_div(H, kWgTH); p.nimg = B;
+    p.ktiles_total = p.tilesW * p.tilesH * B;
+    p.split_stride = (long long)O * 9 * C;
+    const long items = (long)p.cchunks * p.oblocks;
+    long ns = (6L * num_sms() + items - 1) / items;
+    if (ns > p.ktiles_total / 16) ns = p.ktiles_total / 16;
+    if (ns < 1) ns = 1;
+    if (ns * p.split_stride > ws_floats) ns = ws_floats / p.split_stride;
+    if (ns < 1) { set_error("tc_conv3x3_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+    p.nsplit = (int)ns;
+    p.ws = ws; p.ldn = 9 * C; p.C = C;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+        if (e != cudaSuccess) { set_error("tc_conv3x3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    long grid = items * ns < num_sms() ? items * ns : num_sms();
+    tc_wgrad3x3_kernel<<<(int)grid, kTcThreads, kWgSmemBytes, (cudaStream_t)stream>>>(p);
+    rc = check_launch("tc_conv3x3_wgrad");
+    return rc < 0 ? rc : p.nsplit;
+}
+
+// the generic (one box per tap) kernel, kept for cross-checks
+int unetca_tc_conv3x3_wgrad_generic(const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H,
                             int W, int C, int O, void* stream) {
     UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0, "tc_conv3x3_wgrad: C=%d O=%d must be multiples of 64", C, O);
     TcParams p;

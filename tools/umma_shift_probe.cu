@@ -50,6 +50,14 @@ __global__ void __launch_bounds__(128, 1) probe(const __grid_constant__ Args a) 
                 uint64_t db = make_smem_desc(smem_u32(sB) + k * 32, 16, 1024);
                 umma_bf16(tmem, da, db, idesc, k != 0);
             }
+        } else if (a.mode == 2) {
+            // MN-major A with M = 128 made of TWO ROW-SHIFTED views of the same tile: LBO = lbo_rows * 128 bytes
+            constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
+            for (int k = 0; k < 4; ++k) {
+                uint64_t da = make_smem_desc(smem_u32(sA) + (a.r0 + k * 16) * 128, a.sbo /* = LBO here */, 1024);
+                uint64_t db = make_smem_desc(smem_u32(sB) + k * 2048, 8192, 1024);
+                umma_bf16(tmem, da, db, idesc, k != 0);
+            }
         } else {
             constexpr uint32_t idesc = make_idesc(128, 64, 1, 1);
             for (int k = 0; k < 4; ++k) {      // K = 64 rows
@@ -120,6 +128,9 @@ int main() {
                 if (mode == 0) {
                     const int row = r0 + (m / 8) * (sbo / 128) + (m % 8);
                     for (int k = 0; k < 64; ++k) ref += A[row * 64 + k] * Bm[n * 64 + k];
+                } else if (mode == 2) {
+                    // D[m][n] = sum_k A[r0 + (m/64)*lbo_rows + k][m%64] * B[k][n]
+                    for (int k = 0; k < 64; ++k) ref += A[(r0 + (m / 64) * (sbo / 128) + k) * 64 + (m % 64)] * Bm[k * 64 + n];
                 } else {
                     // D[m][n] = sum_k Aop[k][m] * Bop[r0 + k][n]; Aop box0 = rows 0..255 (m < 64 -> col m), box1 = rows 256.. (col m-64)
                     for (int k = 0; k < 64; ++k) {
@@ -130,10 +141,13 @@ int main() {
                 }
                 if (fabs(ref - O[m * 64 + n]) > 1e-3) ++bad;
             }
-        printf("mode %d (%s) r0=%2d base_offset=%d sbo=%4d : %s (%d / 8192 wrong)\n", mode, mode ? "MN-major B shifted in K" : "K-major A shifted rows",
+        printf("mode %d (%s) r0=%2d base_offset=%d sbo|lbo=%4d : %s (%d / 8192 wrong)\n", mode,
+               mode == 2 ? "MN-major A, M-blocks = row-shifted views (LBO)" : mode ? "MN-major B shifted in K" : "K-major A shifted rows",
                r0, bo, sbo, bad ? "MISMATCH" : "ok", bad);
         return bad;
     };
+    for (int lbo_rows : {1, 2, 16, 18, 0})
+        for (int r0 : {0, 1, 19, 38}) run(2, r0, 0, lbo_rows * 128);
     const int shifts[] = {0, 8, 1, 2, 3, 5, 9, 10, 11, 18, 23};
     for (int mode = 0; mode < 2; ++mode)
         for (int r0 : shifts) {
