@@ -264,6 +264,8 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
 
+    if os.environ.get("UNETCA_BLOCK_N"):                 # tuning knob: force the tcgen05 tile width where it divides N
+        _lib.load().unetca_tc_force_block_n(int(os.environ["UNETCA_BLOCK_N"]))
     B, S = args.batch, args.size
     torch.manual_seed(0)
     model = unetca_b200.UNet(3, 2, use_se=True).to(dev).set_precision(args.precision)

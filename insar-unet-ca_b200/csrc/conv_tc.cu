@@ -613,6 +613,7 @@ static int launch_tc_n(int block_n, const TcParams& p, long num_work, cudaStream
 static int g_force_block_n = 0;
 static int pick_block_n(int N) {
     if (g_force_block_n && N % g_force_block_n == 0) return g_force_block_n;
+    if (N % 256 == 0) return 256;    // 128x256 tiles: 96 B/cycle/SM of operand fill instead of 128 (L2->SM is the limit)
     if (N % 128 == 0) return 128;
     return 64;
 }

@@ -32,7 +32,7 @@ def main():
     starts = [i for i, r in enumerate(rows) if "im2col3x3" in r["Kernel Name"]]
     i0 = starts[0]; i1 = starts[1] if len(starts) > 1 else len(rows)
     step = rows[i0:i1]
-    tc = [(r["Kernel Name"].split("(")[0].replace("void unetca::", ""), ms(r)) for r in step if "tc_kernel" in r["Kernel Name"]]
+    tc = [(r["Kernel Name"].split("(")[0].replace("void unetca::", ""), ms(r)) for r in step if "tc_kernel" in r["Kernel Name"] or "tc_wgrad3x3" in r["Kernel Name"]]
     exp = expected_calls(B, S)
     print(f"{len(tc)} tc launches in the step, {len(exp)} expected; step total {sum(ms(r) for r in step):.1f} ms (serialised, cold)")
     tot_ms = tot_fl = 0

@@ -1,0 +1,65 @@
+"""Data-parallel parity check, run under torchrun with N >= 2 GPUs of one box:
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py
+Every rank runs its shard of a global batch through the CUDA path with the bucketed, overlapped NCCL all-reduce
+(unetca_b200.parallel.GradBuckets) and compares the resulting parameter gradients with the mean of the per-shard
+gradients of the CPU oracle — fp32 mode 1e-2 on every gradient norm, bf16 1e-2 on the global norm."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import unetca_b200  # noqa: E402
+from unetca_b200 import parallel  # noqa: E402
+from oracle import unet_ca_port as port  # noqa: E402  (checker only)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    per, H, W = 2, 32, 48
+    sd = port.make_state_dict(seed=9)
+    x, y = port.make_batch(9, per * world, H, W)
+    ref = None
+    for r in range(world):                                     # oracle: reference per shard, averaged on host
+        _, _, g, _, _ = port.train_step_grads(sd, x[r * per:(r + 1) * per], y[r * per:(r + 1) * per])
+        ref = g if ref is None else {k: ref[k] + g[k] for k in g}
+    ref = {k: v / world for k, v in ref.items()}
+    ok = True
+    for prec in ("fp32", "bf16"):
+        torch.manual_seed(1000 + rank)                         # deliberately different init: broadcast must fix it
+        m = unetca_b200.UNet(3, 2, True).cuda().set_precision(prec)
+        if rank == 0:
+            m.load_state_dict(sd)
+        parallel.GradBuckets(m)
+        m.train()
+        xs, ys = parallel.shard_batch(x, rank, world).cuda(), parallel.shard_batch(y, rank, world).cuda()
+        loss = m.loss(xs, ys)
+        loss.backward()
+        torch.cuda.synchronize()
+        params = dict(m.named_parameters())
+        tot = torch.sqrt(sum((p.grad.float().cpu() ** 2).sum() for p in params.values())).item()
+        rtot = torch.sqrt(sum((v ** 2).sum() for v in ref.values())).item()
+        worst = 0.0
+        for k, v in ref.items():
+            if v.norm() > 1e-6 * rtot:
+                worst = max(worst, abs(params[k].grad.float().cpu().norm().item() - v.norm().item()) / v.norm().item())
+        good = abs(tot - rtot) / rtot < 1e-2 and (worst < 1e-2 if prec == "fp32" else worst < 0.25)
+        # every rank must hold identical averaged gradients
+        probe = torch.stack([p.grad.flatten()[0] for p in params.values()])
+        gathered = [torch.zeros_like(probe) for _ in range(world)]
+        dist.all_gather(gathered, probe)
+        same = all(torch.equal(gathered[0], t) for t in gathered)
+        print(f"[rank {rank}] {prec}: global grad norm {tot:.6f} vs oracle mean-of-shards {rtot:.6f}, worst per-param "
+              f"norm rel err {worst:.3e}, identical across ranks: {same} -> {'OK' if good and same else 'FAIL'}", flush=True)
+        ok = ok and good and same
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
