@@ -230,8 +230,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
                 const bool valid = (h0 + r / p.TW) < p.H && (w0 + r % p.TW) < p.W;
                 // the staging buffer must have been drained by the previous tile's TMA store
                 if (ep_tid == 0) tma_store_wait_read();
-                if (ep_tid < BLOCK_N)
-                    sm_bias[ep_tid] = p.bias ? __ldg(p.bias + (nb * BLOCK_N + ep_tid) % p.bias_mod) : 0.f;
+                for (int i = ep_tid; i < BLOCK_N; i += 128)
+                    sm_bias[i] = p.bias ? __ldg(p.bias + (nb * BLOCK_N + i) % p.bias_mod) : 0.f;
                 named_bar_sync(1, 128);
 #pragma unroll 1
                 for (int j = 0; j < BLOCK_N / 64; ++j) {

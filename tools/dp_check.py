@@ -47,7 +47,7 @@ def main():
         for k, v in ref.items():
             if v.norm() > 1e-6 * rtot:
                 worst = max(worst, abs(params[k].grad.float().cpu().norm().item() - v.norm().item()) / v.norm().item())
-        good = abs(tot - rtot) / rtot < 1e-2 and (worst < 1e-2 if prec == "fp32" else worst < 0.25)
+        good = abs(tot - rtot) / rtot < 1e-2 and (worst < 1e-2 if prec == "fp32" else worst < 0.5)
         # every rank must hold identical averaged gradients
         probe = torch.stack([p.grad.flatten()[0] for p in params.values()])
         gathered = [torch.zeros_like(probe) for _ in range(world)]
