@@ -1,0 +1,84 @@
+"""BASELINE.json configs[4]: channel-attention + max-pool kernel sweep (C=64..1024, H=W=32..512) vs the HBM roofline,
+with the plain max-pool (use_se=False ablation) beside it.  Calls the C ABI directly, times with CUDA events, tensor
+>= 256 MB per case so the 126 MB L2 cannot hold it.  usage: python tools/se_pool_sweep.py [out.json]"""
+import ctypes
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from unetca_b200 import _lib  # noqa: E402
+
+
+def peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return json.load(open(p))["hbm_gbs"] if os.path.exists(p) else 6650.0
+
+
+def time_ms(fn, iters=10):
+    for _ in range(3):
+        fn()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    st = lambda: torch.cuda.current_stream().cuda_stream  # noqa: E731
+    peak = peak_gbs()
+    rows = []
+    for dt, tdt, e in ((_lib.BF16, torch.bfloat16, 2), (_lib.F32, torch.float32, 4)):
+        for C in (64, 128, 256, 512, 1024):
+            for S in (32, 64, 128, 256, 512):
+                B = max(1, -(-(256 << 20) // (C * S * S * e)))
+                if B * C * S * S * e > (6 << 30):
+                    continue
+                N = B * C * S * S
+                y = torch.randn(B, S, S, C, device="cuda").to(tdt)
+                out = torch.empty_like(y)
+                pooled = torch.empty(B, S // 2, S // 2, C, dtype=tdt, device="cuda")
+                pos = torch.empty(B, S // 2, S // 2, C, dtype=torch.uint8, device="cuda")
+                scale, shift = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+                w1 = torch.randn(C // 16, C, device="cuda") / C ** 0.5
+                w2 = torch.randn(C, C // 16, device="cuda") / (C // 16) ** 0.5
+                parts = torch.empty(_lib.load().unetca_max_parts(B) * 2048, device="cuda")
+                p_, z_, s_ = torch.empty(B, C, device="cuda"), torch.empty(B, C // 16, device="cuda"), torch.empty(B, C, device="cuda")
+                n = ctypes.c_int(0)
+
+                def se(pool):
+                    _lib.call("unetca_bn_relu", dt, y.data_ptr(), C, None, 0, B, S * S, C, scale.data_ptr(), shift.data_ptr(),
+                              parts.data_ptr(), ctypes.byref(n), st())
+                    _lib.call("unetca_se_fc", parts.data_ptr(), n.value, B, C, C // 16, S * S, w1.data_ptr(), w2.data_ptr(),
+                              p_.data_ptr(), z_.data_ptr(), s_.data_ptr(), st())
+                    _lib.call("unetca_se_scale_pool", dt, y.data_ptr(), C, out.data_ptr(), C, pooled.data_ptr() if pool else None,
+                              C if pool else 0, pos.data_ptr() if pool else None, B, S, S, C, scale.data_ptr(), shift.data_ptr(),
+                              s_.data_ptr(), st())
+
+                def pool_only():
+                    _lib.call("unetca_maxpool2x2", dt, y.data_ptr(), C, pooled.data_ptr(), C, pos.data_ptr(), None, B, S, S, C, st())
+
+                cases = (("se_fwd", lambda: se(False), 3 * N * e),
+                         ("se_fwd+maxpool", lambda: se(True), 3 * N * e + (N // 4) * (e + 1)),
+                         ("maxpool_only", pool_only, N * e + (N // 4) * (e + 1)))
+                for name, fn, nbytes in cases:
+                    ms = time_ms(fn)
+                    gbs = nbytes / ms / 1e6
+                    rows.append({"dtype": "bf16" if e == 2 else "f32", "C": C, "HW": S, "B": B, "kernel": name, "ms": ms,
+                                 "algorithmic_bytes": nbytes, "GBps": gbs, "frac_of_hbm_peak": gbs / peak})
+                    print(f"{rows[-1]['dtype']:4s} C={C:4d} HW={S:3d} B={B:4d} {name:16s} {ms:7.3f} ms {gbs:7.0f} GB/s "
+                          f"{100 * gbs / peak:5.1f}% of {peak:.0f}", flush=True)
+                del y, out, pooled, pos
+    if len(sys.argv) > 1:
+        json.dump({"hbm_peak_gbs": peak, "rows": rows}, open(sys.argv[1], "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
