@@ -40,6 +40,7 @@ int unetca_max_parts(int B);
 void unetca_set_conv_impl(int impl);
 int unetca_get_conv_impl(void);
 void unetca_tc_force_block_n(int n);
+void unetca_tc_force_wgrad_narrow(int on);
 
 /* ---- module boundary: layout and parameter packing ------------------------------------------------------ */
 /* network input (B,Cin,H,W) NCHW fp32 (UCA:343 `model(images)`) -> im2col rows [B*H*W][Kpad], k = tap*Cin + c */

@@ -529,6 +529,140 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// conv3x3 weight gradient, wide variant (C and O multiples of 128): one work item = (128 c, 128 o, filter row kh).
+// M = 128 = two 64-channel X chunks (LBO = chunk tile), N = 128 = two dY chunks, the three taps kw = 0..2 of filter
+// row kh are three 128-column accumulators fed from the same 18x8 haloed X tiles by row-shifted descriptors.
+// Shared-memory operand reads per MMA: 4 KB (A) + 4 KB (B) per 64 cycles = 128 B/cycle — the SS-mode limit, versus
+// 192 B/cycle needed by the N=64 variant above (which therefore tops out at 2/3 of the MMA rate).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWg2XBytes = kWgPitch * kWgTH * 128;          // 18 KB per 64-channel chunk (no vertical halo needed)
+constexpr int kWg2StageBytes = 2 * kWg2XBytes + 2 * kWgYBytes;
+constexpr int kWg2Stages = 3;
+constexpr int kWg2SmemBytes = 1024 + kWg2Stages * kWg2StageBytes + 256;
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide_kernel(const __grid_constant__ Wg3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWg2Stages * kWg2StageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWg2Stages;
+    uint64_t* tfull_bar = bars + 2 * kWg2Stages;
+    uint64_t* tempty_bar = bars + 2 * kWg2Stages + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWg2Stages + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWg2Stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapDY);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const int cpairs = p.cchunks / 2, opairs = p.oblocks / 2;
+    const long items = (long)cpairs * opairs * 3;
+    const long num_work = items * p.nsplit;
+    const int kt_per_split = (p.ktiles_total + p.nsplit - 1) / p.nsplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / items), item = (int)(t % items);
+                const int kh = item % 3, op = (item / 3) % opairs, cp = item / (3 * opairs);
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    const int tw = kt % p.tilesW, th = (kt / p.tilesW) % p.tilesH, b = kt / tiles_per_img;
+                    const int w0 = tw * kWgTW, h0 = th * kWgTH;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* xs = smem + s * kWg2StageBytes;
+                    mbar_expect_tx(&full_bar[s], kWg2StageBytes);
+                    tma_load_4d(&p.mapX, &full_bar[s], xs, cp * 128, w0 - 1, h0 - 1 + kh, b);
+                    tma_load_4d(&p.mapX, &full_bar[s], xs + kWg2XBytes, cp * 128 + 64, w0 - 1, h0 - 1 + kh, b);
+                    tma_load_4d(&p.mapDY, &full_bar[s], xs + 2 * kWg2XBytes, op * 128, w0, h0, b);
+                    tma_load_4d(&p.mapDY, &full_bar[s], xs + 2 * kWg2XBytes + kWgYBytes, op * 128 + 64, w0, h0, b);
+                    if (++s == kWg2Stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 128, 1, 1);
+            int s = 0; uint32_t ph = 0, aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / items);
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                mbar_wait(tempty_bar, aph ^ 1);
+                tcgen05_fence_after();
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t xs = smem_u32(smem + s * kWg2StageBytes);
+                    const uint32_t ys = xs + 2 * kWg2XBytes;
+#pragma unroll 1
+                    for (int hh = 0; hh < kWgTH; ++hh) {
+                        const uint64_t db = make_smem_desc(ys + hh * (kWgTW * 128), kWgYBytes, 1024);
+                        const uint32_t xrow = xs + hh * (kWgPitch * 128);
+                        const uint32_t acc = (kt > kt0 || hh > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw)
+                            umma_bf16(tmem_base + kw * 128, make_smem_desc(xrow + kw * 128, kWg2XBytes, 1024), db, idesc, acc);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == kWg2Stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull_bar);
+                aph ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int z = (int)(t / items), item = (int)(t % items);
+            const int kh = item % 3, op = (item / 3) % opairs, cp = item / (3 * opairs);
+            int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+            if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+            const bool have = kt1 > kt0;
+            mbar_wait(tfull_bar, aph);
+            tcgen05_fence_after();
+            float* wsz = p.ws + (long long)z * p.split_stride + (long long)(op * 128) * p.ldn + cp * 128 + r;
+#pragma unroll 1
+            for (int kw = 0; kw < 3; ++kw) {
+                float* dst = wsz + (kh * 3 + kw) * p.C;
+#pragma unroll 1
+                for (int c32 = 0; c32 < 4; ++c32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kw * 128 + c32 * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        dst[(long long)(c32 * 32 + i) * p.ldn] = have ? __uint_as_float(v[i]) : 0.f;
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
+            aph ^= 1;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // host side: tensor maps, tiling, launch
 // ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -611,6 +745,7 @@ static int launch_tc_n(int block_n, const TcParams& p, long num_work, cudaStream
 }
 
 static int g_force_block_n = 0;
+static int g_wgrad_narrow = 0;
 static int pick_block_n(int N) {
     if (g_force_block_n && N % g_force_block_n == 0) return g_force_block_n;
     if (N % 256 == 0) return 256;    // 128x256 tiles: 96 B/cycle/SM of operand fill instead of 128 (L2->SM is the limit)
@@ -629,6 +764,7 @@ using namespace unetca;
 extern "C" {
 
 void unetca_tc_force_block_n(int n) { g_force_block_n = n; }
+void unetca_tc_force_wgrad_narrow(int on) { g_wgrad_narrow = on; }
 
 // y[p][n] = sum_{tap,c} x[p+s(tap)][c] * w[n][tap*C+c]   (bf16 NHWC in/out, fp32 accumulate).
 // stat_parts != null: per-CTA partial per-channel sum / sum-of-squares of the *stored* bf16 outputs,
@@ -751,13 +887,14 @@ int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, fl
     Wg3Params p;
     memset(&p, 0, sizeof(p));
     int rc;
-    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kWgPitch, kWgTH + 2)) < 0) return rc;
+    const bool wide = (C % 128 == 0) && (O % 128 == 0) && !g_wgrad_narrow;
+    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kWgPitch, wide ? kWgTH : kWgTH + 2)) < 0) return rc;
     if ((rc = make_map(&p.mapDY, dy, O, W, H, B, lddy, (long)W * lddy, (long)H * W * lddy, kWgTW, kWgTH)) < 0) return rc;
     p.cchunks = C / 64; p.oblocks = O / 64;
     p.tilesW = ceil_div(W, kWgTW); p.tilesH = ceil_div(H, kWgTH); p.nimg = B;
     p.ktiles_total = p.tilesW * p.tilesH * B;
     p.split_stride = (long long)O * 9 * C;
-    const long items = (long)p.cchunks * p.oblocks;
+    const long items = wide ? (long)(C / 128) * (O / 128) * 3 : (long)p.cchunks * p.oblocks;
     long ns = (6L * num_sms() + items - 1) / items;
     if (ns > p.ktiles_total / 16) ns = p.ktiles_total / 16;
     if (ns < 1) ns = 1;
@@ -768,11 +905,14 @@ int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, fl
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc_wgrad3x3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWg2SmemBytes);
         if (e != cudaSuccess) { set_error("tc_conv3x3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
         attr_done = true;
     }
     long grid = items * ns < num_sms() ? items * ns : num_sms();
-    tc_wgrad3x3_kernel<<<(int)grid, kTcThreads, kWgSmemBytes, (cudaStream_t)stream>>>(p);
+    if (wide) tc_wgrad3x3_wide_kernel<<<(int)grid, kTcThreads, kWg2SmemBytes, (cudaStream_t)stream>>>(p);
+    else tc_wgrad3x3_kernel<<<(int)grid, kTcThreads, kWgSmemBytes, (cudaStream_t)stream>>>(p);
     rc = check_launch("tc_conv3x3_wgrad");
     return rc < 0 ? rc : p.nsplit;
 }

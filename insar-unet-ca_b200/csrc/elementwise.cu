@@ -527,7 +527,7 @@ __global__ void se_fc_wgrad_kernel(int B, int C, int Cr, const float* __restrict
 //   stage 3: dY = gamma*invstd * (dz - c1 - xhat*c2)
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, bool SE, bool APPLY>
-__global__ void __launch_bounds__(kThreads) bn_bwd_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ y,
+__global__ void __launch_bounds__(kThreads, APPLY ? 3 : 4) bn_bwd_kernel(const T* __restrict__ dout, int ldd, const T* __restrict__ y,
                                                           int ldy, T* __restrict__ dy, int lddy, int C,
                                                           long pix_per_img, long chunk, float inv_hw,
                                                           const float* __restrict__ scale,
@@ -537,6 +537,9 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_kernel(const T* __restrict__ 
                                                           const float* __restrict__ s, const float* __restrict__ dp,
                                                           const float* __restrict__ coef /* [3][C]: g, c1, c2 */,
                                                           float* __restrict__ parts) {
+    // reduce:  acc0 = sum dz, acc1 = sum dz*(y-mean)            (invstd is applied by the finalize kernel)
+    // apply:   dY = g*dz - y*k2 + k0  with  k2 = g*c2*invstd,  k0 = mean*k2 - g*c1
+    //          and, when SE follows, g*dz = mask * (dO*(g*s) + g*dp/HW)
     constexpr int VEC = VecTraits<T>::N;
     const int vpr = C / VEC, rows = kThreads / vpr;
     const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
@@ -547,13 +550,21 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_kernel(const T* __restrict__ 
 #pragma unroll
     for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
     if (r < rows) {
-        float a[VEC], b[VEC], mu[VEC], is[VEC], sv[VEC], dpv[VEC], g[VEC], c1[VEC], c2[VEC];
+        float a[VEC], b[VEC], m0[VEC], m1[VEC], k2[VEC], k0[VEC];
 #pragma unroll
         for (int i = 0; i < VEC; ++i) {
             const int c = cv * VEC + i;
-            a[i] = scale[c]; b[i] = shift[c]; mu[i] = mean[c]; is[i] = invstd[c];
-            if (SE) { sv[i] = s[(long)blockIdx.y * C + c]; dpv[i] = dp[(long)blockIdx.y * C + c] * inv_hw; }
-            if (APPLY) { g[i] = coef[c]; c1[i] = coef[C + c]; c2[i] = coef[2 * C + c]; }
+            a[i] = scale[c]; b[i] = shift[c];
+            float sv = 1.f, dpv = 0.f;
+            if (SE) { sv = s[(long)blockIdx.y * C + c]; dpv = dp[(long)blockIdx.y * C + c] * inv_hw; }
+            if (APPLY) {
+                const float g = coef[c], c1 = coef[C + c], c2 = coef[2 * C + c];
+                k2[i] = g * c2 * invstd[c];
+                k0[i] = mean[c] * k2[i] - g * c1;
+                m0[i] = g * sv; m1[i] = g * dpv;
+            } else {
+                m0[i] = sv; m1[i] = dpv; k2[i] = mean[c]; k0[i] = 0.f;
+            }
         }
 #pragma unroll 4
         for (long p = p0 + r; p < p1; p += rows) {
@@ -562,11 +573,10 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_kernel(const T* __restrict__ 
             load_vec(dout + (base + p) * ldd + cv * VEC, d);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                float da = SE ? fmaf(d[i], sv[i], dpv[i]) : d[i];
+                const float da = SE ? fmaf(d[i], m0[i], m1[i]) : (APPLY ? d[i] * m0[i] : d[i]);
                 const float dz = fmaf(a[i], v[i], b[i]) > 0.f ? da : 0.f;
-                const float xh = (v[i] - mu[i]) * is[i];
-                if (APPLY) d[i] = g[i] * (dz - c1[i] - xh * c2[i]);
-                else { acc[0][i] += dz; acc[1][i] = fmaf(dz, xh, acc[1][i]); }
+                if (APPLY) d[i] = fmaf(-v[i], k2[i], dz) + k0[i];
+                else { acc[0][i] += dz; acc[1][i] = fmaf(dz, v[i] - k2[i], acc[1][i]); }
             }
             if (APPLY) store_vec(dy + (base + p) * lddy + cv * VEC, d);
         }
@@ -582,7 +592,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ parts, int npar
     double tot[2];
     if (!sum_parts32<2>(parts, nparts, C, tot)) return;
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-    const double s = tot[0], q = tot[1];
+    const double s = tot[0], q = tot[1] * (double)invstd[c];
     dbeta[c] = (float)s;
     dgamma[c] = (float)q;
     coef[c] = gamma[c] * invstd[c];
@@ -828,6 +838,38 @@ __global__ void ce_finalize_kernel(const float* __restrict__ parts, int nparts, 
 // ---------------------------------------------------------------------------------------------------------
 // im2col of the (B,Cin,H,W) NCHW fp32 network input for the first 3x3 conv: col[p][tap*Cin + c], zero padded to
 // Kpad columns (K = 9*Cin is not a multiple of the MMA K; the padding exists only in this staging buffer).
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) im2col3x3_small_kernel(const float* __restrict__ x, T* __restrict__ col, int B, int H,
+                                                               int W, int Kpad) {
+    // Cin <= 4: one thread per pixel gathers its 9*Cin inputs with warp-coalesced loads (lanes = consecutive w),
+    // then writes the whole Kpad-wide row as 16-byte stores.
+    constexpr int VEC = VecTraits<T>::N;
+    constexpr int K = 9 * CIN;
+    const long p = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= (long)B * H * W) return;
+    const int w = (int)(p % W), h = (int)((p / W) % H);
+    const long b = p / ((long)W * H);
+    float v[K];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+        const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) v[tap * CIN + c] = in ? __ldg(x + ((b * CIN + c) * H + hh) * W + ww) : 0.f;
+    }
+    T* dst = col + p * Kpad;
+#pragma unroll
+    for (int j = 0; j < (K + VEC - 1) / VEC; ++j) {
+        float o[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o[e] = (j * VEC + e) < K ? v[(j * VEC + e) < K ? (j * VEC + e) : 0] : 0.f;
+        store_vec(dst + j * VEC, o);
+    }
+    float z[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) z[e] = 0.f;
+    for (int j = (K + VEC - 1) / VEC; j < Kpad / VEC; ++j) store_vec(dst + j * VEC, z);
+}
 template <typename T>
 __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, T* __restrict__ col, int B, int Cin, int H, int W,
                                       int Kpad) {
@@ -1189,8 +1231,12 @@ int unetca_im2col3x3_nchw(int dtype, const float* x, void* col, int B, int Cin, 
     UNETCA_REQUIRE(Kpad >= 9 * Cin, "im2col: Kpad %d < 9*Cin", Kpad);
     DISPATCH_T(dtype, {
         UNETCA_REQUIRE(Kpad % VecTraits<T>::N == 0, "im2col: Kpad %d must be a multiple of %d", Kpad, VecTraits<T>::N);
-        const long total = (long)B * H * W * (Kpad / VecTraits<T>::N);
-        im2col3x3_nchw_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(x, (T*)col, B, Cin, H, W, Kpad);
+        const long npix = (long)B * H * W;
+        const long total = npix * (Kpad / VecTraits<T>::N);
+        cudaStream_t st = (cudaStream_t)stream;
+        if (Cin == 1) im2col3x3_small_kernel<T, 1><<<ceil_div(npix, 256), 256, 0, st>>>(x, (T*)col, B, H, W, Kpad);
+        else if (Cin == 3) im2col3x3_small_kernel<T, 3><<<ceil_div(npix, 256), 256, 0, st>>>(x, (T*)col, B, H, W, Kpad);
+        else im2col3x3_nchw_kernel<T><<<ceil_div(total, 256), 256, 0, st>>>(x, (T*)col, B, Cin, H, W, Kpad);
     });
     return check_launch("im2col3x3_nchw");
 }

@@ -1,0 +1,66 @@
+"""Micro-benchmark of the tcgen05 contraction kernels on one U-Net-CA layer shape (C ABI, CUDA events).
+usage: python tools/conv_bench.py [--layers all|C,O,S ...] [--B 64] [--what fwd,wgrad] [--iters 10] [--block-n N]"""
+import argparse
+import ctypes
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from unetca_b200 import _lib  # noqa: E402
+
+LAYERS = [(64, 64, 512), (128, 64, 512), (64, 128, 256), (128, 128, 256), (256, 128, 256), (128, 256, 128),
+          (256, 256, 128), (512, 256, 128), (256, 512, 64), (512, 512, 64), (1024, 512, 64), (512, 1024, 32),
+          (1024, 1024, 32)]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", nargs="*", default=["all"])
+    ap.add_argument("--B", type=int, default=64)
+    ap.add_argument("--what", default="fwd,wgrad")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--block-n", type=int, default=0)
+    a = ap.parse_args()
+    lib = _lib.load()
+    lib.unetca_tc_force_block_n(a.block_n)
+    layers = LAYERS if a.layers == ["all"] else [tuple(int(v) for v in s.split(",")) for s in a.layers]
+    st = torch.cuda.current_stream().cuda_stream
+    B = a.B
+    ws = torch.empty(48 << 20, device="cuda")
+    parts = torch.empty(lib.unetca_max_parts(B) * 2048, device="cuda")
+    n = ctypes.c_int(0)
+    for C, O, S in layers:
+        x = torch.randn(B, S, S, C, device="cuda").bfloat16()
+        dy = torch.randn(B, S, S, O, device="cuda").bfloat16()
+        y = torch.empty(B, S, S, O, device="cuda", dtype=torch.bfloat16)
+        wf = (torch.randn(O, 9 * C, device="cuda") / (9 * C) ** 0.5).bfloat16()
+        dw = torch.empty(O, C, 3, 3, device="cuda")
+        fl = 2.0 * B * S * S * 9 * C * O
+        res = []
+        for what in a.what.split(","):
+            if what == "fwd":
+                fn = lambda: _lib.call("unetca_conv3x3_fwd", 1, x.data_ptr(), C, wf.data_ptr(), 9 * C, y.data_ptr(), O, B, S, S,
+                                       C, O, parts.data_ptr(), ctypes.byref(n), st)  # noqa: E731
+            else:
+                fn = lambda: _lib.call("unetca_conv3x3_wgrad", 1, dy.data_ptr(), O, x.data_ptr(), C, ws.data_ptr(), ws.numel(),
+                                       B, S, S, C, O, dw.data_ptr(), st)  # noqa: E731
+            for _ in range(3):
+                fn()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(a.iters):
+                fn()
+            e.record()
+            torch.cuda.synchronize()
+            ms = s.elapsed_time(e) / a.iters
+            res.append(f"{what} {ms:7.3f} ms {fl / ms / 1e9:7.1f} TFLOP/s")
+        print(f"conv {C:4d}->{O:4d} @{S:3d} B={B}: " + " | ".join(res), flush=True)
+        del x, dy, y
+
+
+if __name__ == "__main__":
+    main()
