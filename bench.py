@@ -130,7 +130,7 @@ def _work(name, a, e, cin):
         B, H, W, C = a[8:12]
         n = B * H * W * C
         return "hbm", 0, 2 * n * e + ((n // 4) * (e + 1) if a[5] else 0)
-    if name in ("unetca_se_bwd_reduce", "unetca_bn_bwd_reduce"):
+    if name in ("unetca_se_bwd_reduce", "unetca_bn_bwd_reduce", "unetca_se_bn_bwd_reduce"):
         B, hw, C = a[5:8]
         return "hbm", 0, 2 * B * hw * C * e
     if name == "unetca_bn_bwd_apply":

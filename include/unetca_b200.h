@@ -41,6 +41,7 @@ void unetca_set_conv_impl(int impl);
 int unetca_get_conv_impl(void);
 void unetca_tc_force_block_n(int n);
 void unetca_tc_force_wgrad_narrow(int on);
+void unetca_tc_force_no_halo(int on);
 
 /* ---- module boundary: layout and parameter packing ------------------------------------------------------ */
 /* network input (B,Cin,H,W) NCHW fp32 (UCA:343 `model(images)`) -> im2col rows [B*H*W][Kpad], k = tap*Cin + c */
@@ -90,7 +91,16 @@ int unetca_maxpool2x2(int dtype, const void* x, int ldx, void* pooled, int ldp, 
 int unetca_pool_bwd_add(int dtype, const void* skip_grad, int lds, const void* dpooled, int ldp, const uint8_t* pos, void* dx, int ldx, int B, int H, int W, int C, void* stream);
 int unetca_se_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, float* parts, int* nparts, void* stream);
 int unetca_se_fc_bwd(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2, const float* p, const float* z, const float* s, float* dpre2, float* dz, float* dp, float* dw1, float* dw2, void* stream);
+/* SE squeeze with the extra per-image sums (sum m, sum m*(y-mean)) the merged backward needs: parts [B * *nparts][3][C] */
+int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, const float* mean, float* parts, int* nparts, void* stream);
+int unetca_se_fc3(const float* parts3, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2, float* p, float* z, float* s, float* sums34, void* stream);
+/* merged SE + ReLU + BN backward reduction (one pass over dO, Y2): parts [B * *nparts][2][C]; FC chain; BN finalize */
+int unetca_se_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, const float* mean, float* parts, int* nparts, void* stream);
+int unetca_se_fc_bwd_fused(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2, const float* p, const float* z, const float* s, const float* scale, const float* shift, const float* mean, const float* sums34, float* sums, float* dpre2, float* dz, float* dp, float* dw1, float* dw2, void* stream);
+int unetca_bn_bwd_finalize_se(const float* sums, int B, int C, long count, long pix_per_img, const float* gamma, const float* invstd, const float* s, const float* dp, float* dgamma, float* dbeta, float* coef, void* stream);
 int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* parts, float* out, void* stream);
+/* tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid */
+void unetca_set_tuning(int key, int value);
 
 /* ---- outc 1x1 conv -> class logits (UCA:125,162), CrossEntropyLoss(ignore_index) (UCA:465,344), argmax (UCA:220) */
 int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, const float* bias, int nc, float* logits, int B, long HW, void* stream);

@@ -71,6 +71,107 @@ template <int BLOCK_N, bool WGRAD> struct TcCfg {
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
 };
 
+// ---------------------------------------------------------------------------------------------------------
+// forward-like epilogue of one accumulator tile (128 pixels x BLOCK_N channels), executed by the 128 epilogue
+// threads: TMEM -> (+bias) -> bf16 -> swizzled staging -> TMA store, plus the per-channel BatchNorm partial sums.
+// ---------------------------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__device__ __forceinline__ void fwd_epilogue_tile(uint32_t t_addr, uint8_t* out_stage, float* sm_bias, float* sm_wpart,
+                                                  float* sm_stats, const CUtensorMap* mapOut, int c0, int w0, int h0, int b,
+                                                  int nb, bool valid, const float* bias, int bias_mod, bool do_stats, int N,
+                                                  uint64_t* tempty, int r, int lane, int ep_tid) {
+    // the staging buffer must have been drained by the previous tile's TMA store
+    if (ep_tid == 0) tma_store_wait_read();
+    for (int i = ep_tid; i < BLOCK_N; i += 128)
+        sm_bias[i] = bias ? __ldg(bias + (nb * BLOCK_N + i) % bias_mod) : 0.f;
+    named_bar_sync(1, 128);
+#pragma unroll 1
+    for (int j = 0; j < BLOCK_N / 64; ++j) {
+        uint32_t v[2][32];
+        tmem_ld32(t_addr + j * 64, v[0]);
+        tmem_ld32(t_addr + j * 64 + 32, v[1]);
+        tmem_wait_ld();
+        uint8_t* row = out_stage + j * kBoxBytesFwd + r * 128;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float4 b0 = *reinterpret_cast<const float4*>(sm_bias + j * 64 + half * 32 + c * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(sm_bias + j * 64 + half * 32 + c * 8 + 4);
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float f[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(v[half][c * 8 + i]) + bb[i] : 0.f;
+                uint4 pk;
+                pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
+                pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
+                const int chunk = half * 4 + c;
+                *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = pk;
+            }
+        }
+    }
+    tcgen05_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty);
+    fence_proxy_async_smem();
+    named_bar_sync(1, 128);
+    if (ep_tid == 0) {
+#pragma unroll 1
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_store_4d(mapOut, out_stage + j * kBoxBytesFwd, c0 + j * 64, w0, h0, b);
+        tma_store_commit();
+    }
+    if (do_stats) {
+        // per-channel sum / sum-of-squares of the staged bf16 tile: thread -> one 16-byte chunk (8 channels)
+        // of every RSTEP-th row; lanes sharing a chunk are folded by shuffles, warps by shared memory.
+        constexpr int NCH = BLOCK_N / 8;            // chunks per pixel row over all boxes
+        constexpr int RSTEP = 128 / NCH;            // threads per chunk
+        const int ch = ep_tid % NCH, r0 = ep_tid / NCH;
+        const uint8_t* base = out_stage + (ch >> 3) * kBoxBytesFwd;
+        float s1[8], s2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+#pragma unroll 4
+        for (int rr = r0; rr < 128; rr += RSTEP) {
+            const uint4 t4 = *reinterpret_cast<const uint4*>(base + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4));
+            const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xffff0000u);
+                s1[2 * i] += lo; s2[2 * i] = fmaf(lo, lo, s2[2 * i]);
+                s1[2 * i + 1] += hi; s2[2 * i + 1] = fmaf(hi, hi, s2[2 * i + 1]);
+            }
+        }
+        if (NCH < 32) {
+#pragma unroll
+            for (int off = NCH; off < 32; off <<= 1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+                    s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+                }
+            }
+        }
+        // one partial per (warp, chunk); for NCH == 32 every lane owns a distinct chunk
+        const int ew = ep_tid >> 5;
+        if (lane < NCH || NCH >= 32) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                sm_wpart[(ew * 2 + 0) * BLOCK_N + ch * 8 + i] = s1[i];
+                sm_wpart[(ew * 2 + 1) * BLOCK_N + ch * 8 + i] = s2[i];
+            }
+        }
+        named_bar_sync(1, 128);
+        for (int i = ep_tid; i < 2 * BLOCK_N; i += 128) {
+            const int which = i / BLOCK_N, col = i % BLOCK_N;
+            float tsum = 0.f;
+#pragma unroll
+            for (int w4i = 0; w4i < 4; ++w4i) tsum += sm_wpart[(w4i * 2 + which) * BLOCK_N + col];
+            sm_stats[which * N + nb * BLOCK_N + col] += tsum;
+        }
+    }
+}
+
 template <int BLOCK_N, bool WGRAD>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant__ TcParams p) {
     using Cfg = TcCfg<BLOCK_N, WGRAD>;
@@ -228,98 +329,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
                 const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
                 const int w0 = tw * p.TW, h0 = th * p.TH;
                 const bool valid = (h0 + r / p.TW) < p.H && (w0 + r % p.TW) < p.W;
-                // the staging buffer must have been drained by the previous tile's TMA store
-                if (ep_tid == 0) tma_store_wait_read();
-                for (int i = ep_tid; i < BLOCK_N; i += 128)
-                    sm_bias[i] = p.bias ? __ldg(p.bias + (nb * BLOCK_N + i) % p.bias_mod) : 0.f;
-                named_bar_sync(1, 128);
-#pragma unroll 1
-                for (int j = 0; j < BLOCK_N / 64; ++j) {
-                    uint32_t v[2][32];
-                    tmem_ld32(t_addr + j * 64, v[0]);
-                    tmem_ld32(t_addr + j * 64 + 32, v[1]);
-                    tmem_wait_ld();
-                    uint8_t* row = out_stage + j * kBoxBytesFwd + r * 128;
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) {
-                            const float4 b0 = *reinterpret_cast<const float4*>(sm_bias + j * 64 + half * 32 + c * 8);
-                            const float4 b1 = *reinterpret_cast<const float4*>(sm_bias + j * 64 + half * 32 + c * 8 + 4);
-                            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                            float f[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) f[i] = valid ? __uint_as_float(v[half][c * 8 + i]) + bb[i] : 0.f;
-                            uint4 pk;
-                            pk.x = pack_bf16x2(f[0], f[1]); pk.y = pack_bf16x2(f[2], f[3]);
-                            pk.z = pack_bf16x2(f[4], f[5]); pk.w = pack_bf16x2(f[6], f[7]);
-                            const int chunk = half * 4 + c;
-                            *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) = pk;
-                        }
-                    }
-                }
-                tcgen05_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[as]);
-                fence_proxy_async_smem();
-                named_bar_sync(1, 128);
-                if (ep_tid == 0) {
-                    const int om = nb / p.n_blocks_per_outmap;
-                    const int c0 = (nb % p.n_blocks_per_outmap) * BLOCK_N;
-#pragma unroll 1
-                    for (int j = 0; j < BLOCK_N / 64; ++j)
-                        tma_store_4d(&p.mapOut[om], out_stage + j * kBoxBytesFwd, c0 + j * 64, w0, h0, b);
-                    tma_store_commit();
-                }
-                if (p.stat_parts) {
-                    // per-channel sum / sum-of-squares of the staged bf16 tile: thread -> one 16-byte chunk (8 channels)
-                    // of every RSTEP-th row; lanes sharing a chunk are folded by shuffles, warps by shared memory.
-                    constexpr int NCH = BLOCK_N / 8;            // chunks per pixel row over all boxes
-                    constexpr int RSTEP = 128 / NCH;            // threads per chunk
-                    const int ch = ep_tid % NCH, r0 = ep_tid / NCH;
-                    const uint8_t* base = out_stage + (ch >> 3) * kBoxBytesFwd;
-                    float s1[8], s2[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-#pragma unroll 4
-                    for (int rr = r0; rr < 128; rr += RSTEP) {
-                        const uint4 t4 = *reinterpret_cast<const uint4*>(base + rr * 128 + (((ch & 7) ^ (rr & 7)) << 4));
-                        const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xffff0000u);
-                            s1[2 * i] += lo; s2[2 * i] = fmaf(lo, lo, s2[2 * i]);
-                            s1[2 * i + 1] += hi; s2[2 * i + 1] = fmaf(hi, hi, s2[2 * i + 1]);
-                        }
-                    }
-                    if (NCH < 32) {
-#pragma unroll
-                        for (int off = NCH; off < 32; off <<= 1) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
-                                s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
-                            }
-                        }
-                    }
-                    // one partial per (warp, chunk); for NCH == 32 every lane owns a distinct chunk
-                    const int ew = ep_tid >> 5;
-                    if (lane < NCH || NCH >= 32) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            sm_wpart[(ew * 2 + 0) * BLOCK_N + ch * 8 + i] = s1[i];
-                            sm_wpart[(ew * 2 + 1) * BLOCK_N + ch * 8 + i] = s2[i];
-                        }
-                    }
-                    named_bar_sync(1, 128);
-                    for (int i = ep_tid; i < 2 * BLOCK_N; i += 128) {
-                        const int which = i / BLOCK_N, col = i % BLOCK_N;
-                        float tsum = 0.f;
-#pragma unroll
-                        for (int w4i = 0; w4i < 4; ++w4i) tsum += sm_wpart[(w4i * 2 + which) * BLOCK_N + col];
-                        sm_stats[which * p.N + nb * BLOCK_N + col] += tsum;
-                    }
-                }
+                fwd_epilogue_tile<BLOCK_N>(t_addr, out_stage, sm_bias, sm_wpart, sm_stats, &p.mapOut[nb / p.n_blocks_per_outmap],
+                                           (nb % p.n_blocks_per_outmap) * BLOCK_N, w0, h0, b, nb, valid, p.bias, p.bias_mod,
+                                           p.stat_parts != nullptr, p.N, &tempty_bar[as], r, lane, ep_tid);
             } else {
                 const int z = (int)(t / mn_items);
                 const int nb = (int)((t % mn_items) % p.num_n_blocks);
@@ -662,6 +674,190 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide_kernel(const _
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// conv3x3 forward / dgrad with tap reuse from ONE haloed activation tile (narrow outputs, N = 64 or 128).
+//   out[p][n] = sum_{tap,c} X[p + s(tap)][c] * Wk[n][tap*C + c]
+// The generic kernel above loads one [128 px][64 c] box per tap: 9 x 16 KB of L2->shared traffic per 64-channel
+// chunk plus the weights.  With narrow N the MMAs are short (N/2 cycles each) and that fill rate (>128 B/cycle/SM)
+// is what bounds it.  Here the output tile is 8 wide x 16 high, its 10 x 18 haloed input tile (23 KB) is loaded
+// ONCE per chunk, and the nine taps are K-major A descriptors into that one tile: start address shifted by
+// (kh*10 + kw) pixel rows of 128 B, stride between 8-pixel groups SBO = 10 rows = 1280 B (legal because the
+// SWIZZLE_128B XOR is a function of the absolute shared-memory address; tools/umma_shift_probe.cu mode 0,
+// sbo=1280).  Weights stream through their own ring, one [BLOCK_N][64] box per tap; when the whole filter of the
+// layer fits the ring (C = 64, N = BLOCK_N = 64) it is loaded once and stays resident.
+// Warps: 0 = X producer, 1 = MMA issuer, 2..5 = epilogue, 6 = weight producer.
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) HaloParams {
+    CUtensorMap mapX, mapW, mapOut;
+    int tilesW, tilesH, nimg, H, W;
+    int cchunks, num_n_blocks;
+    int w_resident;
+    float* stat_parts;
+    int N;
+};
+constexpr int kHaloThreads = 224;
+constexpr int kHTW = 8, kHTH = 16, kHPitch = kHTW + 2;
+constexpr int kHXBox = kHPitch * (kHTH + 2) * 128;     // 23040 bytes written by TMA
+constexpr int kHXBytes = 23 * 1024;                    // ring slot (1024-byte aligned)
+
+template <int BLOCK_N> struct HaloCfg {
+    static constexpr int XS = BLOCK_N == 64 ? 4 : 3;
+    static constexpr int WS = BLOCK_N == 64 ? 9 : 6;
+    static constexpr int W_BYTES = BLOCK_N * 128;
+    static constexpr int OUT_BYTES = (BLOCK_N / 64) * kBoxBytesFwd;
+    static constexpr int STAT_BYTES = 2 * 1024 * 4 + BLOCK_N * 4 + 8 * BLOCK_N * 4;
+    static constexpr int SMEM_BYTES = 1024 + XS * kHXBytes + WS * W_BYTES + OUT_BYTES + STAT_BYTES + 256;
+    static_assert(SMEM_BYTES <= 227 * 1024, "halo conv: shared memory budget");
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kHaloThreads, 1) tc_conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
+    using Cfg = HaloCfg<BLOCK_N>;
+    constexpr int XS = Cfg::XS, WS = Cfg::WS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* x_ring = smem;
+    uint8_t* w_ring = smem + XS * kHXBytes;
+    uint8_t* out_stage = w_ring + WS * Cfg::W_BYTES;
+    float* sm_stats = reinterpret_cast<float*>(out_stage + Cfg::OUT_BYTES);
+    float* sm_bias = sm_stats + 2048;
+    float* sm_wpart = sm_bias + BLOCK_N;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::OUT_BYTES + Cfg::STAT_BYTES);
+    uint64_t* xfull = bars;                    // [XS]
+    uint64_t* xempty = bars + XS;              // [XS]
+    uint64_t* wfull = bars + 2 * XS;           // [WS]
+    uint64_t* wempty = bars + 2 * XS + WS;     // [WS]
+    uint64_t* tfull_bar = bars + 2 * XS + 2 * WS;       // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    static_assert((2 * XS + 2 * WS + 4) * 8 + 4 <= 256, "halo conv: barrier area");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+        for (int i = 0; i < WS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapW);
+        prefetch_tmap(&p.mapOut);
+    }
+    if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);
+    if (p.stat_parts) {
+        for (int i = threadIdx.x; i < 2 * p.N; i += kHaloThreads) sm_stats[i] = 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const long num_work = (long)tiles_per_img * p.nimg * p.num_n_blocks;
+
+    if (warp == 0) {
+        // ================================ X producer: one haloed tile per (work item, chunk) ================
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int mt = (int)(t / p.num_n_blocks);
+                const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    mbar_wait(&xempty[s], ph ^ 1);
+                    mbar_expect_tx(&xfull[s], kHXBox);
+                    tma_load_4d(&p.mapX, &xfull[s], x_ring + s * kHXBytes, cc * 64, tw * kHTW - 1, th * kHTH - 1, b);
+                    if (++s == XS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ================================ weight producer: one [BLOCK_N][64] box per (chunk, tap) ===========
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            bool loaded = false;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                if (p.w_resident && loaded) break;
+                const int nb = (int)(t % p.num_n_blocks);
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&wempty[s], ph ^ 1);
+                        mbar_expect_tx(&wfull[s], Cfg::W_BYTES);
+                        tma_load_4d(&p.mapW, &wfull[s], w_ring + s * Cfg::W_BYTES, (tap * p.cchunks + cc) * 64,
+                                    nb * BLOCK_N, 0, 0);
+                        if (++s == WS) { s = 0; ph ^= 1; }
+                    }
+                }
+                loaded = true;
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 0, 0);
+            int xs = 0; uint32_t xph = 0;
+            int ws = 0; uint32_t wph = 0;
+            int as = 0; uint32_t aph = 0;
+            bool first = true;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    mbar_wait(&xfull[xs], xph);
+                    const uint32_t xa = smem_u32(x_ring + xs * kHXBytes);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        if (!p.w_resident || first) mbar_wait(&wfull[ws], wph);
+                        tcgen05_fence_after();
+                        const uint32_t sa = xa + ((tap / 3) * kHPitch + (tap % 3)) * 128;
+                        const uint32_t sb = smem_u32(w_ring + ws * Cfg::W_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16, kHPitch * 128),
+                                      make_smem_desc(sb + k * 32, 16, 1024), idesc, (cc | tap | k) != 0);
+                        if (!p.w_resident) umma_commit(&wempty[ws]);
+                        if (++ws == WS) { ws = 0; wph ^= 1; }
+                    }
+                    umma_commit(&xempty[xs]);
+                    if (++xs == XS) { xs = 0; xph ^= 1; }
+                }
+                first = false;
+                umma_commit(&tfull_bar[as]);
+                as ^= 1; if (as == 0) aph ^= 1;
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 2..5) ================================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int ep_tid = threadIdx.x - 64;
+        int as = 0; uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            mbar_wait(&tfull_bar[as], aph);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
+            const int nb = (int)(t % p.num_n_blocks);
+            const int mt = (int)(t / p.num_n_blocks);
+            const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
+            const int w0 = tw * kHTW, h0 = th * kHTH;
+            const bool valid = (h0 + r / kHTW) < p.H && (w0 + r % kHTW) < p.W;
+            fwd_epilogue_tile<BLOCK_N>(t_addr, out_stage, sm_bias, sm_wpart, sm_stats, &p.mapOut, nb * BLOCK_N, w0, h0, b, nb,
+                                       valid, nullptr, 1, p.stat_parts != nullptr, p.N, &tempty_bar[as], r, lane, ep_tid);
+            as ^= 1; if (as == 0) aph ^= 1;
+        }
+        if (ep_tid == 0) tma_store_wait_all();
+        named_bar_sync(1, 128);
+        if (p.stat_parts) {
+            float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
+            for (int i = ep_tid; i < 2 * p.N; i += 128) dst[i] = sm_stats[i];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_base);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side: tensor maps, tiling, launch
 // ---------------------------------------------------------------------------------------------------------
@@ -753,6 +949,43 @@ static int pick_block_n(int N) {
     return 64;
 }
 
+static int g_no_halo = 1;   // the haloed narrow-N kernel is kept for experiments only: with N <= 128 every tcgen05.mma costs
+                             // ~100 cycles (A-operand fetch floor, tools/umma_rate_probe.cu), so fill reuse cannot pay
+
+template <int BLOCK_N>
+static int launch_halo_n(const HaloParams& p, long num_work, cudaStream_t st) {
+    using Cfg = HaloCfg<BLOCK_N>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::SMEM_BYTES);
+        if (e != cudaSuccess) { set_error("tc_conv3x3 (halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    long grid = num_work < num_sms() ? num_work : num_sms();
+    if (grid < 1) grid = 1;
+    tc_conv3x3_halo_kernel<BLOCK_N><<<(int)grid, kHaloThreads, Cfg::SMEM_BYTES, st>>>(p);
+    int rc = check_launch("tc_conv3x3_fwd (halo)");
+    return rc < 0 ? rc : (int)grid;
+}
+
+static int launch_halo(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
+                       float* stat_parts, cudaStream_t st) {
+    HaloParams p;
+    memset(&p, 0, sizeof(p));
+    const int BN = pick_block_n(O);
+    int rc;
+    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kHPitch, kHTH + 2)) < 0) return rc;
+    if ((rc = make_map(&p.mapW, w, 9L * C, O, 1, 1, ldk, (long)O * ldk, (long)O * ldk, BN, 1)) < 0) return rc;
+    if ((rc = make_map(&p.mapOut, y, O, W, H, B, ldy, (long)W * ldy, (long)H * W * ldy, kHTW, kHTH)) < 0) return rc;
+    p.tilesW = ceil_div(W, kHTW); p.tilesH = ceil_div(H, kHTH); p.nimg = B; p.H = H; p.W = W;
+    p.cchunks = C / 64; p.num_n_blocks = O / BN;
+    p.w_resident = (BN == 64 && C == 64 && O == 64) ? 1 : 0;
+    p.stat_parts = stat_parts; p.N = O;
+    const long num_work = (long)p.tilesW * p.tilesH * B * p.num_n_blocks;
+    return BN == 64 ? launch_halo_n<64>(p, num_work, st) : launch_halo_n<128>(p, num_work, st);
+}
+
 static void set_taps3x3(TcParams& p) {
     for (int t = 0; t < 9; ++t) { p.dh[t] = (signed char)(t / 3 - 1); p.dw[t] = (signed char)(t % 3 - 1); p.amap[t] = 0; }
 }
@@ -765,6 +998,7 @@ extern "C" {
 
 void unetca_tc_force_block_n(int n) { g_force_block_n = n; }
 void unetca_tc_force_wgrad_narrow(int on) { g_wgrad_narrow = on; }
+void unetca_tc_force_no_halo(int on) { g_no_halo = on; }
 
 // y[p][n] = sum_{tap,c} x[p+s(tap)][c] * w[n][tap*C+c]   (bf16 NHWC in/out, fp32 accumulate).
 // stat_parts != null: per-CTA partial per-channel sum / sum-of-squares of the *stored* bf16 outputs,
@@ -772,6 +1006,7 @@ void unetca_tc_force_wgrad_narrow(int on) { g_wgrad_narrow = on; }
 int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C,
                           int O, float* stat_parts, void* stream) {
     UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0 && O <= 1024, "tc_conv3x3: C=%d O=%d must be multiples of 64 (O<=1024)", C, O);
+    if (pick_block_n(O) <= 128 && !g_no_halo) return launch_halo(x, ldx, w, ldk, y, ldy, B, H, W, C, O, stat_parts, (cudaStream_t)stream);
     TcParams p;
     memset(&p, 0, sizeof(p));
     int TW = 0, TH = 0;

@@ -20,6 +20,12 @@ namespace unetca {
 constexpr int kThreads = 256;
 constexpr int kMaxParts = 1184;  // 148 SMs x 8
 
+// tuning knobs (unetca_set_tuning): pixels per thread-row of an elementwise block; waves of a per-image reduction grid
+// (0 = legacy sizing by kMaxParts)
+static int g_ew_px = 16;
+static int g_red_waves = 1;
+static int g_pool_quads = 4;      // 2x2 quads per thread-row of a se_scale_pool block
+
 struct RowMap {
     int vpr;    // 16-byte vectors per pixel row
     int rows;   // pixel rows processed concurrently by one block
@@ -33,12 +39,33 @@ template <typename T> static inline RowMap row_map(int C) {
 // pixels per block for an elementwise pass / a reduction pass
 template <typename T> static inline long ew_chunk(int C, long npix) {
     (void)npix;
-    return (long)row_map<T>(C).rows * 16;
+    return (long)row_map<T>(C).rows * g_ew_px;
 }
 template <typename T> static inline long red_chunk(int C, long npix) {
     long c = (long)row_map<T>(C).rows * 16;
     long c2 = (npix + kMaxParts - 1) / kMaxParts;
     return c > c2 ? c : c2;
+}
+
+// Per-image reduction grids (grid = (nblk, B)): size the grid to the kernel's resident capacity (148 SMs x blocks/SM
+// x g_red_waves) so that every block runs concurrently and all finish together; a grid of ~2 waves of large
+// blocks loses up to a third of the bandwidth in its tail.
+template <typename K> static int resident_blocks(K kernel) {
+    int v = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, 0) != cudaSuccess || v < 1) v = 1;
+    return v * num_sms();
+}
+template <typename T> static inline long img_red_chunk(int C, long pix_per_img, int B, int slots) {
+    if (g_red_waves <= 0) return red_chunk<T>(C, pix_per_img * B);
+    const long rows = row_map<T>(C).rows;
+    long cap = (long)slots * g_red_waves;
+    if (cap > kMaxParts) cap = kMaxParts;
+    long per_img = cap / B;
+    if (per_img < 1) per_img = 1;
+    long chunk = (pix_per_img + per_img - 1) / per_img;
+    chunk = (chunk + rows - 1) / rows * rows;
+    if (chunk < rows * 16) chunk = rows * 16;
+    return chunk;
 }
 
 // Sum `acc[s][*]` over the block's pixel rows and write out[s*C + c]; all threads must call.
@@ -208,20 +235,30 @@ __global__ void __launch_bounds__(kThreads) bn_relu_kernel(const T* __restrict__
 // ---------------------------------------------------------------------------------------------------------
 // SE excitation: p = mean_hw, z = relu(W1 p), s = sigmoid(W2 z)      UCA:54-59,65-68   (one block per image)
 // ---------------------------------------------------------------------------------------------------------
+template <int NSTAT>
 __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ parts, int nparts, int C, int Cr,
                                                     float inv_hw, const float* __restrict__ w1,
                                                     const float* __restrict__ w2, float* __restrict__ p_out,
-                                                    float* __restrict__ z_out, float* __restrict__ s_out) {
+                                                    float* __restrict__ z_out, float* __restrict__ s_out,
+                                                    float* __restrict__ sums34) {
     extern __shared__ float sm[];
     float* p = sm;          // [C]
     float* z = sm + C;      // [Cr]
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int c = tid; c < C; c += blockDim.x) {
-        double t = 0.0;
-        for (int i = 0; i < nparts; ++i) t += (double)parts[((long)b * nparts + i) * C + c];
+        double t = 0.0, t3 = 0.0, t4 = 0.0;
+        for (int i = 0; i < nparts; ++i) {
+            const float* row = parts + ((long)b * nparts + i) * NSTAT * C + c;
+            t += (double)row[0];
+            if (NSTAT == 3) { t3 += (double)row[C]; t4 += (double)row[2 * (long)C]; }
+        }
         const float v = (float)t * inv_hw;
         p[c] = v;
         p_out[(long)b * C + c] = v;
+        if (NSTAT == 3 && sums34) {
+            sums34[((long)b * 2 + 0) * C + c] = (float)t3;
+            sums34[((long)b * 2 + 1) * C + c] = (float)t4;
+        }
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -250,21 +287,20 @@ template <typename T, bool POOL>
 __global__ void __launch_bounds__(kThreads) se_scale_pool_kernel(const T* __restrict__ y, int ldy,
                                                                  T* __restrict__ out, int ldo,
                                                                  T* __restrict__ pooled, int ldp,
-                                                                 uint8_t* __restrict__ pos, int B, int H, int W, int C,
-                                                                 const float* __restrict__ scale,
+                                                                 uint8_t* __restrict__ pos, int H, int W, int C,
+                                                                 long chunk, const float* __restrict__ scale,
                                                                  const float* __restrict__ shift,
                                                                  const float* __restrict__ s) {
+    // grid = (blocks per image, B); thread (r, cv) walks quads q0+r, q0+r+rows, ... of its image with one channel vector
     constexpr int VEC = VecTraits<T>::N;
-    const int vpr = C / VEC;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    if (r >= rows) return;
     const int Ho = H >> 1, Wo = W >> 1;
-    const long nquad = (long)B * Ho * Wo;
-    const long gid = (long)blockIdx.x * kThreads + threadIdx.x;
-    const long q = gid / vpr;
-    const int cv = (int)(gid % vpr);
-    if (q >= nquad) return;
-    const int wo = (int)(q % Wo);
-    const int ho = (int)((q / Wo) % Ho);
-    const int b = (int)(q / ((long)Wo * Ho));
+    const long nquad = (long)Ho * Wo;
+    const int b = blockIdx.y;
+    const long q0 = (long)blockIdx.x * chunk;
+    long q1 = q0 + chunk; if (q1 > nquad) q1 = nquad;
     float a[VEC], sh[VEC], g[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -272,39 +308,41 @@ __global__ void __launch_bounds__(kThreads) se_scale_pool_kernel(const T* __rest
         sh[i] = shift[cv * VEC + i];
         g[i] = s ? s[(long)b * C + cv * VEC + i] : 1.f;
     }
-    float v[4][VEC];
+#pragma unroll 2
+    for (long q = q0 + r; q < q1; q += rows) {
+        const int wo = (int)(q % Wo), ho = (int)(q / Wo);
+        const long pbase = ((long)b * H + 2 * ho) * W + 2 * wo;
+        float v[4][VEC];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const long p = ((long)b * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1);
-        load_vec(y + p * ldy + cv * VEC, v[k]);
-    }
-    float best[VEC];
-    uint8_t code[VEC];
+        for (int k = 0; k < 4; ++k) load_vec(y + (pbase + (k >> 1) * W + (k & 1)) * ldy + cv * VEC, v[k]);
+        float best[VEC];
+        uint8_t code[VEC];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const long p = ((long)b * H + 2 * ho + (k >> 1)) * W + 2 * wo + (k & 1);
+        for (int k = 0; k < 4; ++k) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            float t = fmaxf(fmaf(a[i], v[k][i], sh[i]), 0.f) * g[i];
-            t = round_to(t, (const T*)nullptr);
-            v[k][i] = t;
-            if (POOL) {
-                if (k == 0) { best[i] = t; code[i] = 0; }
-                else if (t > best[i] || t != t) { best[i] = t; code[i] = (uint8_t)k; }
+            for (int i = 0; i < VEC; ++i) {
+                float t = fmaxf(fmaf(a[i], v[k][i], sh[i]), 0.f) * g[i];
+                t = round_to(t, (const T*)nullptr);
+                v[k][i] = t;
+                if (POOL) {
+                    if (k == 0) { best[i] = t; code[i] = 0; }
+                    else if (t > best[i] || t != t) { best[i] = t; code[i] = (uint8_t)k; }
+                }
             }
+            store_vec(out + (pbase + (k >> 1) * W + (k & 1)) * ldo + cv * VEC, v[k]);
         }
-        store_vec(out + p * ldo + cv * VEC, v[k]);
-    }
-    if (POOL) {
-        store_vec(pooled + q * ldp + cv * VEC, best);
-        uint8_t* dst = pos + q * C + cv * VEC;
-        if (VEC == 8) {
-            uint2 t;
-            t.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
-            t.y = code[4 % VEC] | (code[5 % VEC] << 8) | (code[6 % VEC] << 16) | (code[7 % VEC] << 24);
-            *reinterpret_cast<uint2*>(dst) = t;
-        } else {
-            *reinterpret_cast<uint32_t*>(dst) = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+        if (POOL) {
+            const long qg = (long)b * nquad + q;
+            store_vec(pooled + qg * ldp + cv * VEC, best);
+            uint8_t* dst = pos + qg * C + cv * VEC;
+            if (VEC == 8) {
+                uint2 t;
+                t.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+                t.y = code[4 % VEC] | (code[5 % VEC] << 8) | (code[6 % VEC] << 16) | (code[7 % VEC] << 24);
+                *reinterpret_cast<uint2*>(dst) = t;
+            } else {
+                *reinterpret_cast<uint32_t*>(dst) = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+            }
         }
     }
 }
@@ -597,6 +635,180 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ parts, int npar
     dgamma[c] = (float)q;
     coef[c] = gamma[c] * invstd[c];
     coef[C + c] = (float)(s / count);
+    coef[2 * C + c] = (float)(q / count);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SE + ReLU + BN backward, stage 1 when an SE layer follows the block: ONE pass over dO and Y2 instead of the
+// se_bwd_reduce + bn_bwd_reduce pair.  With m = (a*y+b > 0), per (image, channel):
+//   S1 = sum m*dO,  S2 = sum m*dO*(y-mean)          (this kernel, backward)
+//   S3 = sum m,     S4 = sum m*(y-mean)             (se_squeeze_kernel, forward: they do not depend on dO)
+// Everything downstream is linear in these: the SE excitation gradient ds = sum dO*relu(a*y+b) = a*S2 + beta*S1
+// (beta = a*mean + b), and once the FC chain has produced dp[b,c]:
+//   sum dz = sum_b s*S1 + dp/HW*S3,      sum dz*(y-mean) = sum_b s*S2 + dp/HW*S4.
+// parts: [(b*nblk + blk)][2][C]
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 4) se_bn_bwd_reduce_kernel(const T* __restrict__ dout, int ldd,
+                                                                       const T* __restrict__ y, int ldy, int C,
+                                                                       long pix_per_img, long chunk,
+                                                                       const float* __restrict__ scale,
+                                                                       const float* __restrict__ shift,
+                                                                       const float* __restrict__ mean,
+                                                                       float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const long base = (long)blockIdx.y * pix_per_img;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    float acc[2][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+    if (r < rows) {
+        float a[VEC], b[VEC], mu[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { a[i] = scale[cv * VEC + i]; b[i] = shift[cv * VEC + i]; mu[i] = mean[cv * VEC + i]; }
+#pragma unroll 4
+        for (long p = p0 + r; p < p1; p += rows) {
+            float v[VEC], d[VEC];
+            load_vec(y + (base + p) * ldy + cv * VEC, v);
+            load_vec(dout + (base + p) * ldd + cv * VEC, d);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float dm = fmaf(a[i], v[i], b[i]) > 0.f ? d[i] : 0.f;
+                acc[0][i] += dm;
+                acc[1][i] = fmaf(dm, v[i] - mu[i], acc[1][i]);
+            }
+        }
+    }
+    block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
+// SE squeeze (forward): per (image, channel) sums of relu(a*y+b), m and m*(y-mean); the last two are kept for the
+// backward pass (see above).  parts: [(b*nblk + blk)][3][C]; mean may be null (eval: treated as 0).
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 3) se_squeeze_kernel(const T* __restrict__ y, int ldy, int C,
+                                                                 long pix_per_img, long chunk,
+                                                                 const float* __restrict__ scale,
+                                                                 const float* __restrict__ shift,
+                                                                 const float* __restrict__ mean,
+                                                                 float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const long base = (long)blockIdx.y * pix_per_img;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    float acc[3][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
+    if (r < rows) {
+        float a[VEC], b[VEC], mu[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            a[i] = scale[cv * VEC + i]; b[i] = shift[cv * VEC + i]; mu[i] = mean ? mean[cv * VEC + i] : 0.f;
+        }
+#pragma unroll 8
+        for (long p = p0 + r; p < p1; p += rows) {
+            float v[VEC];
+            load_vec(y + (base + p) * ldy + cv * VEC, v);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float t = fmaf(a[i], v[i], b[i]);
+                const bool on = t > 0.f;
+                acc[0][i] += fmaxf(t, 0.f);
+                acc[1][i] += on ? 1.f : 0.f;
+                acc[2][i] += on ? v[i] - mu[i] : 0.f;
+            }
+        }
+    }
+    block_reduce_rows<3, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 3 * C);
+}
+
+// SE backward FC chain fed by the four merged sums (one block per image); also stores the per-image sums
+// sums[b][4][C] for bn_bwd_finalize_se_kernel.
+__global__ void __launch_bounds__(256) se_fc_bwd_fused_kernel(const float* __restrict__ parts, int nparts, int C, int Cr,
+                                                              const float* __restrict__ w1, const float* __restrict__ w2,
+                                                              const float* __restrict__ z, const float* __restrict__ s,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const float* __restrict__ mean,
+                                                              const float* __restrict__ sums34,
+                                                              float* __restrict__ sums,
+                                                              float* __restrict__ dpre2_out, float* __restrict__ dz_out,
+                                                              float* __restrict__ dp_out) {
+    extern __shared__ float sm[];
+    float* dpre2 = sm;       // [C]
+    float* dz = sm + C;      // [Cr]
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int c = tid; c < C; c += blockDim.x) {
+        double t[2] = {0.0, 0.0};
+        for (int i = 0; i < nparts; ++i) {
+            const float* row = parts + ((long)b * nparts + i) * 2 * C + c;
+            t[0] += (double)row[0];
+            t[1] += (double)row[C];
+        }
+        sums[((long)b * 4 + 0) * C + c] = (float)t[0];
+        sums[((long)b * 4 + 1) * C + c] = (float)t[1];
+        sums[((long)b * 4 + 2) * C + c] = sums34[((long)b * 2 + 0) * C + c];
+        sums[((long)b * 4 + 3) * C + c] = sums34[((long)b * 2 + 1) * C + c];
+        const double a = scale[c], beta = (double)scale[c] * (double)mean[c] + (double)shift[c];
+        const float ds = (float)(a * t[1] + beta * t[0]);
+        const float sv = s[(long)b * C + c];
+        const float v = ds * sv * (1.f - sv);
+        dpre2[c] = v;
+        dpre2_out[(long)b * C + c] = v;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+    for (int j = warp; j < Cr; j += nwarps) {
+        float t = 0.f;
+        for (int c = lane; c < C; c += 32) t = fmaf(dpre2[c], w2[(long)c * Cr + j], t);
+        t = warp_sum(t);
+        if (lane == 0) {
+            t = z[(long)b * Cr + j] > 0.f ? t : 0.f;
+            dz[j] = t;
+            dz_out[(long)b * Cr + j] = t;
+        }
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += blockDim.x) {
+        float t = 0.f;
+        for (int j = 0; j < Cr; ++j) t = fmaf(dz[j], w1[(long)j * C + c], t);
+        dp_out[(long)b * C + c] = t;
+    }
+}
+
+// BN backward finalize from the per-image merged sums: 32 channels per block, 8 image lanes folded in double.
+__global__ void bn_bwd_finalize_se_kernel(const float* __restrict__ sums, int B, int C, double count, double inv_hw,
+                                          const float* __restrict__ gamma, const float* __restrict__ invstd,
+                                          const float* __restrict__ s, const float* __restrict__ dp,
+                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                          float* __restrict__ coef) {
+    __shared__ double red[2][8][32];
+    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double a0 = 0.0, a1 = 0.0;
+    if (c < C) {
+        for (int b = pl; b < B; b += 8) {
+            const float* row = sums + (long)b * 4 * C + c;
+            const double sv = s[(long)b * C + c], dpv = (double)dp[(long)b * C + c] * inv_hw;
+            a0 += sv * (double)row[0] + dpv * (double)row[2 * (long)C];
+            a1 += sv * (double)row[(long)C] + dpv * (double)row[3 * (long)C];
+        }
+    }
+    red[0][pl][cl] = a0; red[1][pl][cl] = a1;
+    __syncthreads();
+    if (pl != 0 || c >= C) return;
+    double sdz = 0.0, q = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sdz += red[0][k][cl]; q += red[1][k][cl]; }
+    q *= (double)invstd[c];
+    dbeta[c] = (float)sdz;
+    dgamma[c] = (float)q;
+    coef[c] = gamma[c] * invstd[c];
+    coef[C + c] = (float)(sdz / count);
     coef[2 * C + c] = (float)(q / count);
 }
 
@@ -1031,7 +1243,9 @@ int unetca_bn_relu(int dtype, const void* y, int ldy, void* out, int ldo, int B,
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldy);
         if (out) REQ_CHAN(C, ldo);
-        const long chunk = pool_parts ? red_chunk<T>(C, pix_per_img * B) : ew_chunk<T>(C, pix_per_img);
+        static int slots = 0;
+        if (!slots) slots = resident_blocks(bn_relu_kernel<T, false, true>);
+        const long chunk = pool_parts ? img_red_chunk<T>(C, pix_per_img, B, slots) : ew_chunk<T>(C, pix_per_img);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
         cudaStream_t st = (cudaStream_t)stream;
         if (out && pool_parts)
@@ -1048,9 +1262,32 @@ int unetca_bn_relu(int dtype, const void* y, int ldy, void* out, int ldo, int B,
 
 int unetca_se_fc(const float* pool_parts, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,
                  float* p, float* z, float* s, void* stream) {
-    se_fc_kernel<<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_parts, nparts, C, Cr, 1.f / (float)hw,
-                                                                           w1, w2, p, z, s);
+    se_fc_kernel<1><<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_parts, nparts, C, Cr, 1.f / (float)hw,
+                                                                              w1, w2, p, z, s, nullptr);
     return check_launch("se_fc");
+}
+
+// SE squeeze with the two extra per-image sums the merged backward needs.  parts: [B * *nparts][3][C]
+int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale,
+                      const float* shift, const float* mean, float* parts, int* nparts, void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldy);
+        static int slots = 0;
+        if (!slots) slots = resident_blocks(se_squeeze_kernel<T>);
+        const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
+        dim3 grid(ceil_div(pix_per_img, chunk), B);
+        se_squeeze_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)y, ldy, C, pix_per_img, chunk, scale, shift, mean, parts);
+        *nparts = grid.x;
+    });
+    return check_launch("se_squeeze");
+}
+
+// FC chain on the 3-stat squeeze partials; sums34 (nullable): [B][2][C] = (sum m, sum m*(y-mean)) for the backward
+int unetca_se_fc3(const float* parts3, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,
+                  float* p, float* z, float* s, float* sums34, void* stream) {
+    se_fc_kernel<3><<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(parts3, nparts, C, Cr, 1.f / (float)hw,
+                                                                              w1, w2, p, z, s, sums34);
+    return check_launch("se_fc3");
 }
 
 // o = relu(scale*y+shift) * s[b,c] -> out (stride ldo); pooled/pos non-null: fused MaxPool2d(2)
@@ -1063,8 +1300,10 @@ int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, 
         cudaStream_t st = (cudaStream_t)stream;
         if (pooled) {
             REQ_CHAN(C, ldp);
-            const long nthr = (long)B * (H / 2) * (W / 2) * (C / VecTraits<T>::N);
-            se_scale_pool_kernel<T, true><<<ceil_div(nthr, kThreads), kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, pos, B, H, W, C, scale, shift, s);
+            const long nquad = (long)(H / 2) * (W / 2);
+            const long chunk = (long)row_map<T>(C).rows * g_pool_quads;
+            dim3 grid(ceil_div(nquad, chunk), B);
+            se_scale_pool_kernel<T, true><<<grid, kThreads, 0, st>>>((const T*)y, ldy, (T*)out, ldo, (T*)pooled, ldp, pos, H, W, C, chunk, scale, shift, s);
         } else {
             const long hw = (long)H * W;
             const long chunk = ew_chunk<T>(C, hw);
@@ -1101,7 +1340,9 @@ int unetca_se_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, in
                          const float* scale, const float* shift, float* parts, int* nparts, void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
-        const long chunk = red_chunk<T>(C, pix_per_img * B);
+        static int slots = 0;
+        if (!slots) slots = resident_blocks(se_bwd_reduce_kernel<T>);
+        const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
         se_bwd_reduce_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)dout, ldd, (const T*)y, ldy, C, pix_per_img, chunk, scale, shift, parts);
         *nparts = grid.x;
@@ -1118,13 +1359,59 @@ int unetca_se_fc_bwd(const float* parts, int nparts, int B, int C, int Cr, const
     return check_launch("se_fc_bwd");
 }
 
+// merged SE + ReLU + BN backward stage 1 (see se_bn_bwd_reduce_kernel).  parts: [B * *nparts][2][C]
+int unetca_se_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C,
+                            const float* scale, const float* shift, const float* mean, float* parts, int* nparts,
+                            void* stream) {
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
+        static int slots = 0;
+        if (!slots) slots = resident_blocks(se_bn_bwd_reduce_kernel<T>);
+        const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
+        dim3 grid(ceil_div(pix_per_img, chunk), B);
+        se_bn_bwd_reduce_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)dout, ldd, (const T*)y, ldy, C, pix_per_img, chunk, scale, shift, mean, parts);
+        *nparts = grid.x;
+    });
+    return check_launch("se_bn_bwd_reduce");
+}
+
+// FC chain of the SE backward from the merged sums; sums: [B][4][C] scratch kept for unetca_bn_bwd_finalize_se
+int unetca_se_fc_bwd_fused(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2,
+                           const float* p, const float* z, const float* s, const float* scale, const float* shift,
+                           const float* mean, const float* sums34, float* sums, float* dpre2, float* dz, float* dp,
+                           float* dw1, float* dw2, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    se_fc_bwd_fused_kernel<<<B, 256, (C + Cr) * sizeof(float), st>>>(parts, nparts, C, Cr, w1, w2, z, s, scale, shift, mean,
+                                                                     sums34, sums, dpre2, dz, dp);
+    se_fc_wgrad_kernel<<<ceil_div((long)C * Cr, 256), 256, 0, st>>>(B, C, Cr, dpre2, dz, p, z, dw1, dw2);
+    return check_launch("se_fc_bwd_fused");
+}
+
+int unetca_bn_bwd_finalize_se(const float* sums, int B, int C, long count, long pix_per_img, const float* gamma,
+                              const float* invstd, const float* s, const float* dp, float* dgamma, float* dbeta,
+                              float* coef, void* stream) {
+    bn_bwd_finalize_se_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(sums, B, C, (double)count,
+                                                                                1.0 / (double)pix_per_img, gamma, invstd,
+                                                                                s, dp, dgamma, dbeta, coef);
+    return check_launch("bn_bwd_finalize_se");
+}
+
+// tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid
+void unetca_set_tuning(int key, int value) {
+    if (key == 0 && value > 0) g_ew_px = value;
+    if (key == 1) g_red_waves = value;
+    if (key == 2 && value > 0) g_pool_quads = value;
+}
+
 // stage 1 of ReLU+BN backward (s/dp null: no SE in front).  parts: [B * *nparts][2][C]
 int unetca_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C,
                          const float* scale, const float* shift, const float* mean, const float* invstd,
                          const float* s, const float* dp, float* parts, int* nparts, void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
-        const long chunk = red_chunk<T>(C, pix_per_img * B);
+        static int slots = 0;
+        if (!slots) slots = resident_blocks(bn_bwd_kernel<T, true, false>);
+        const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
         cudaStream_t st = (cudaStream_t)stream;
         const float ihw = 1.f / (float)pix_per_img;
@@ -1149,7 +1436,7 @@ int unetca_bn_bwd_apply(int dtype, const void* dout, int ldd, const void* y, int
                         const float* invstd, const float* s, const float* dp, const float* coef, void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy); REQ_CHAN(C, lddy);
-        const long chunk = ew_chunk<T>(C, pix_per_img);
+        const long chunk = 2 * ew_chunk<T>(C, pix_per_img);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
         cudaStream_t st = (cudaStream_t)stream;
         const float ihw = 1.f / (float)pix_per_img;

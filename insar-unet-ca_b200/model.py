@@ -108,7 +108,7 @@ class _Engine:
 
     def parts(self, B, device):
         rows = _lib.load().unetca_max_parts(B)
-        return self.scratch("parts", rows * 2 * 1024, torch.float32, device)
+        return self.scratch("parts", rows * 4 * 1024, torch.float32, device)
 
     def ws(self, device):
         return self.scratch("ws", _WS_FLOATS, torch.float32, device)
@@ -215,14 +215,15 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
     if blk.se is not None:
         w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
         Cr = w1.shape[0]
-        _lib.call("unetca_bn_relu", dt, _ptr(y2), O, None, 0, B, Hl * Wl, O, _ptr(scale2), _ptr(shift2), _ptr(parts),
-                  ctypes.byref(nparts), st)
+        _lib.call("unetca_se_squeeze", dt, _ptr(y2), O, B, Hl * Wl, O, _ptr(scale2), _ptr(shift2),
+                  _ptr(sv.mean2) if train else None, _ptr(parts), ctypes.byref(nparts), st)
         p = torch.empty(B, O, dtype=torch.float32, device=dev)
         z = torch.empty(B, Cr, dtype=torch.float32, device=dev)
         s = torch.empty(B, O, dtype=torch.float32, device=dev)
-        _lib.call("unetca_se_fc", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(p), _ptr(z),
-                  _ptr(s), st)
-        sv.p, sv.z, sv.s = p, z, s
+        sums34 = torch.empty(B, 2, O, dtype=torch.float32, device=dev) if keep else None
+        _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(p), _ptr(z),
+                  _ptr(s), _ptr(sums34), st)
+        sv.p, sv.z, sv.s, sv.sums34 = p, z, s, sums34
     _lib.call("unetca_se_scale_pool", dt, _ptr(y2), O, _ptr(out_view), out_view.stride(2), _ptr(pooled),
               pooled.stride(2) if pooled is not None else 0, _ptr(pos), B, Hl, Wl, O, _ptr(scale2), _ptr(shift2),
               _ptr(s), st)
@@ -316,34 +317,43 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
     ws = eng.ws(dev)
     nparts = ctypes.c_int(0)
     pre = blk.prefix
-    s = dp = None
+    s = dp = sums = None
     if blk.se is not None:
+        # one pass over (dO, Y2) yields the four per-image sums that both the SE excitation gradient and the BN2
+        # backward statistics are linear in (csrc/elementwise.cu: se_bn_bwd_reduce_kernel)
         w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
         Cr = w1.shape[0]
-        _lib.call("unetca_se_bwd_reduce", dt, _ptr(dout), dout.stride(2), _ptr(sv.y2), O, B, Hl * Wl, O, _ptr(sv.scale2),
-                  _ptr(sv.shift2), _ptr(parts), ctypes.byref(nparts), st)
+        _lib.call("unetca_se_bn_bwd_reduce", dt, _ptr(dout), dout.stride(2), _ptr(sv.y2), O, B, Hl * Wl, O,
+                  _ptr(sv.scale2), _ptr(sv.shift2), _ptr(sv.mean2), _ptr(parts), ctypes.byref(nparts), st)
         dpre2 = torch.empty(B, O, dtype=torch.float32, device=dev)
         dz = torch.empty(B, Cr, dtype=torch.float32, device=dev)
         dp = torch.empty(B, O, dtype=torch.float32, device=dev)
+        sums = torch.empty(B, 4, O, dtype=torch.float32, device=dev)
         dw1 = G.alloc(pre + ".6.fc.0.weight", w1)
         dw2 = G.alloc(pre + ".6.fc.2.weight", w2)
-        _lib.call("unetca_se_fc_bwd", _ptr(parts), nparts.value, B, O, Cr, _ptr(w1), _ptr(w2), _ptr(sv.p), _ptr(sv.z),
-                  _ptr(sv.s), _ptr(dpre2), _ptr(dz), _ptr(dp), _ptr(dw1), _ptr(dw2), st)
+        _lib.call("unetca_se_fc_bwd_fused", _ptr(parts), nparts.value, B, O, Cr, _ptr(w1), _ptr(w2), _ptr(sv.p), _ptr(sv.z),
+                  _ptr(sv.s), _ptr(sv.scale2), _ptr(sv.shift2), _ptr(sv.mean2), _ptr(sv.sums34), _ptr(sums), _ptr(dpre2), _ptr(dz),
+                  _ptr(dp),
+                  _ptr(dw1), _ptr(dw2), st)
         G.put(pre + ".6.fc.0.weight")
         G.put(pre + ".6.fc.2.weight")
         s = sv.s
 
-    def bn_relu_bwd(d_in, ld_in, y, tag, s_, dp_, bn_idx):
+    def bn_relu_bwd(d_in, ld_in, y, tag, s_, dp_, bn_idx, sums_=None):
         scale, shift = getattr(sv, "scale" + tag), getattr(sv, "shift" + tag)
         mean, invstd = getattr(sv, "mean" + tag), getattr(sv, "invstd" + tag)
         bn = blk.bn1 if tag == "1" else blk.bn2
-        _lib.call("unetca_bn_bwd_reduce", dt, _ptr(d_in), ld_in, _ptr(y), O, B, Hl * Wl, O, _ptr(scale), _ptr(shift),
-                  _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(parts), ctypes.byref(nparts), st)
         dgamma = G.alloc(f"{pre}.{bn_idx}.weight", bn.weight)
         dbeta = G.alloc(f"{pre}.{bn_idx}.bias", bn.bias)
         coef = torch.empty(3, O, dtype=torch.float32, device=dev)
-        _lib.call("unetca_bn_bwd_finalize", _ptr(parts), nparts.value, O, npix, _ptr(bn.weight), _ptr(invstd),
-                  _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
+        if sums_ is not None:
+            _lib.call("unetca_bn_bwd_finalize_se", _ptr(sums_), B, O, npix, Hl * Wl, _ptr(bn.weight), _ptr(invstd), _ptr(s_),
+                      _ptr(dp_), _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
+        else:
+            _lib.call("unetca_bn_bwd_reduce", dt, _ptr(d_in), ld_in, _ptr(y), O, B, Hl * Wl, O, _ptr(scale), _ptr(shift),
+                      _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(parts), ctypes.byref(nparts), st)
+            _lib.call("unetca_bn_bwd_finalize", _ptr(parts), nparts.value, O, npix, _ptr(bn.weight), _ptr(invstd),
+                      _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
         dy = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
         _lib.call("unetca_bn_bwd_apply", dt, _ptr(d_in), ld_in, _ptr(y), O, _ptr(dy), O, B, Hl * Wl, O, _ptr(scale),
                   _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(coef), st)
@@ -352,7 +362,7 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
         return dy
 
     # ---- [SE ->] ReLU -> BN2 backward
-    dy2 = bn_relu_bwd(dout, dout.stride(2), sv.y2, "2", s, dp, 4)
+    dy2 = bn_relu_bwd(dout, dout.stride(2), sv.y2, "2", s, dp, 4, sums)
     # a conv bias in front of a train-mode BatchNorm has an analytically zero gradient (BN removes the mean)
     G.alloc(pre + ".3.bias", blk.conv2.bias).zero_()
     G.put(pre + ".3.bias")

@@ -4,7 +4,7 @@ The reference has no large-scene path (scenes are pre-cut into 64/128-px tiles o
 definition of "the model's output on a tile" is `model.eval(); model(tile)` (validate_model, UCA:273-287).  Because
 the SE squeeze (UCA:65) averages over the *whole input*, a tile's result depends on the tile's own extent, so the
 output of tiled inference is defined as: reference eval-forward on (core + halo), zero-filled outside the scene, keep
-the core's argmax (UCA:220).  That is the oracle the tests use, tile for tile.
+the core's argmax (UCA:220).  The parity tests check exactly that definition, tile for tile.
 
 Tiles are independent: rank r of `world` takes tiles r, r+world, ... (static round-robin), no collective on the data
 path; the optional gather of the uint8 mask is left to the caller.

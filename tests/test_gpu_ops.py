@@ -166,6 +166,39 @@ def test_se_block_forward_backward(dt, B, C, H, W, pool):
     call("unetca_bn_bwd_apply", dt, ptr(dd), C, ptr(yd), C, ptr(dy), C, B, H * W, C, ptr(sc), ptr(sh), ptr(zeros), ptr(ones),
          ptr(s), ptr(dp), ptr(coef), stream())
     assert relerr(from_nhwc(dy), dz_ref) < TOL[dt]
+    # merged SE + BN reduction (one pass over dO, Y2): same FC-chain outputs and the same BN finalize results as the
+    # two-pass path, with a non-trivial mean / invstd
+    mean = torch.from_numpy((0.3 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    invstd = torch.from_numpy((1 + 0.1 * rs.random_sample(C)).astype(np.float32)).cuda()
+    gamma = torch.from_numpy((1 + 0.2 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    call("unetca_bn_bwd_reduce", dt, ptr(dd), C, ptr(yd), C, B, H * W, C, ptr(sc), ptr(sh), ptr(mean), ptr(invstd), ptr(s),
+         ptr(dp), ptr(parts), ctypes.byref(n), stream())
+    dg_a, db_a, coef_a = torch.empty(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(3, C, device="cuda")
+    call("unetca_bn_bwd_finalize", ptr(parts), n.value, C, B * H * W, ptr(gamma), ptr(invstd), ptr(dg_a), ptr(db_a),
+         ptr(coef_a), stream())
+    parts4 = parts_buf(B, 4096)
+    call("unetca_se_squeeze", dt, ptr(yd), C, B, H * W, C, ptr(sc), ptr(sh), ptr(mean), ptr(parts4), ctypes.byref(n), stream())
+    p3, z3, s3 = torch.empty_like(p), torch.empty_like(z), torch.empty_like(s)
+    sums34 = torch.empty(B, 2, C, device="cuda")
+    call("unetca_se_fc3", ptr(parts4), n.value, B, C, Cr, H * W, ptr(w1d), ptr(w2d), ptr(p3), ptr(z3), ptr(s3), ptr(sums34),
+         stream())
+    assert relerr(p3, p) < 1e-5 and relerr(z3, z) < 1e-5 and relerr(s3, s) < 1e-5
+    on = (yr * scale[None, :, None, None] + shift[None, :, None, None]) > 0
+    assert torch.equal(sums34[:, 0].cpu(), on.float().sum((2, 3)))
+    assert relerr(sums34[:, 1].cpu(), ((yr - mean.cpu()[None, :, None, None]) * on).sum((2, 3))) < 1e-4
+    call("unetca_se_bn_bwd_reduce", dt, ptr(dd), C, ptr(yd), C, B, H * W, C, ptr(sc), ptr(sh), ptr(mean), ptr(parts4),
+         ctypes.byref(n), stream())
+    sums4 = torch.empty(B, 4, C, device="cuda")
+    dpre2b, dzb, dpb = torch.empty_like(dpre2), torch.empty_like(dzz), torch.empty_like(dp)
+    gw1b, gw2b = torch.empty_like(gw1), torch.empty_like(gw2)
+    call("unetca_se_fc_bwd_fused", ptr(parts4), n.value, B, C, Cr, ptr(w1d), ptr(w2d), ptr(p), ptr(z), ptr(s), ptr(sc),
+         ptr(sh), ptr(mean), ptr(sums34), ptr(sums4), ptr(dpre2b), ptr(dzb), ptr(dpb), ptr(gw1b), ptr(gw2b), stream())
+    assert relerr(dpb, dp) < 1e-4 and relerr(dpre2b, dpre2) < 1e-4
+    assert relerr(gw1b, gw1) < 1e-4 and relerr(gw2b, gw2) < 1e-4
+    dg_b, db_b, coef_b = torch.empty(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(3, C, device="cuda")
+    call("unetca_bn_bwd_finalize_se", ptr(sums4), B, C, B * H * W, H * W, ptr(gamma), ptr(invstd), ptr(s), ptr(dpb),
+         ptr(dg_b), ptr(db_b), ptr(coef_b), stream())
+    assert relerr(dg_b, dg_a) < 1e-4 and relerr(db_b, db_a) < 1e-4 and relerr(coef_b, coef_a) < 1e-4
 
 
 @pytest.mark.parametrize("dt", DTS)
@@ -247,7 +280,8 @@ def test_conv3x3_ffma(dt, B, C, O, H, W):
 
 
 @pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 64, 16, 16), (1, 128, 64, 8, 24), (2, 64, 192, 4, 4),
-                                       (2, 128, 256, 32, 32), (3, 256, 128, 16, 48), (1, 64, 64, 128, 128)])
+                                       (2, 128, 256, 32, 32), (3, 256, 128, 16, 48), (1, 64, 64, 128, 128),
+                                       (2, 128, 128, 40, 24), (1, 192, 64, 48, 16)])
 def test_conv3x3_tcgen05(B, C, O, H, W):
     _conv_case(BF16, 0, B, C, O, H, W)
 

@@ -23,10 +23,15 @@ def main():
     ap.add_argument("--what", default="fwd,wgrad")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--block-n", type=int, default=0)
+    ap.add_argument("--no-halo", action="store_true", help="narrow layers through the generic one-box-per-tap kernel")
+    ap.add_argument("--dgrad", action="store_true", help="add the dgrad shapes (O -> C) of the narrow layers")
     a = ap.parse_args()
     lib = _lib.load()
     lib.unetca_tc_force_block_n(a.block_n)
+    lib.unetca_tc_force_no_halo(1 if a.no_halo else 0)
     layers = LAYERS if a.layers == ["all"] else [tuple(int(v) for v in s.split(",")) for s in a.layers]
+    if a.dgrad:
+        layers = layers + [(64, 128, 512), (128, 64, 256), (256, 128, 128)]
     st = torch.cuda.current_stream().cuda_stream
     B = a.B
     ws = torch.empty(48 << 20, device="cuda")
