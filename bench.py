@@ -103,6 +103,12 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 def _work(name, a, e, cin):
     """(class, algorithmic flops, algorithmic bytes) of one call; e = bytes per activation element."""
+    if name == "unetca_conv3x3_fwd_paired":
+        B, H, W, C, O = a[6:11]
+        return "tensor", 2.0 * B * H * W * 9 * C * O, 0
+    if name == "unetca_se_squeeze":
+        B, hw, C = a[3:6]
+        return "hbm", 0, B * hw * C * e
     if name == "unetca_conv3x3_fwd":
         B, H, W, C, O = a[7:12]
         return "tensor", 2.0 * B * H * W * 9 * C * O, 0

@@ -42,6 +42,7 @@ int unetca_get_conv_impl(void);
 void unetca_tc_force_block_n(int n);
 void unetca_tc_force_wgrad_narrow(int on);
 void unetca_tc_force_no_halo(int on);
+void unetca_tc_force_no_pixn(int on);
 
 /* ---- module boundary: layout and parameter packing ------------------------------------------------------ */
 /* network input (B,Cin,H,W) NCHW fp32 (UCA:343 `model(images)`) -> im2col rows [B*H*W][Kpad], k = tap*Cin + c */
@@ -57,6 +58,10 @@ int unetca_pack_convT_weight(int dtype, const float* w, void* wf, void* wd, int 
 /* nn.Conv2d(k=3,pad=1) forward without bias, UCA:81,84; also its dgrad (pass dy, wd and swap C/O).
  * stat_parts (optional) receives partial per-channel sum / sum-of-squares of y: [*nparts][2][O]. */
 int unetca_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream);
+/* the same convolution for narrow outputs (O % 64 == 0, H even) through the row-pair layout of the tcgen05 path
+ * (csrc/conv_tc.cu, tc_conv3x3_pixn_kernel); w_pair [2*O][12*C] = unetca_pack_conv3x3_pair(w [O][ld]).  bf16 only. */
+int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream);
+int unetca_pack_conv3x3_pair(int dtype, const void* w, int ld, void* w_pair, int rows, int C, void* stream);
 /* first conv (K = 9*Cin): out[m][n] = sum_k A[m][k] * Bw[n][k] over im2col rows */
 int unetca_gemm_nt(int dtype, const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K, float* stat_parts, int* nparts, void* stream);
 /* weight gradient of conv3x3 -> dw (O,C,3,3) fp32; ws: split-K scratch (ws_floats floats) */
@@ -111,6 +116,8 @@ int unetca_cross_entropy(const float* logits, const long long* target, int nc, i
 
 /* ---- implementation-specific contraction entry points (exported for the cross-check tests) ----------------- */
 int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, void* stream);
+int unetca_tc_conv3x3_fwd_paired(const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, void* stream);
+int unetca_tc_pack_pair(const void* w, int ld, void* w_pair, int rows, int C, void* stream);
 int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K, float* stat_parts, void* stream);
 int unetca_tc_convT_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h, int wd, int Cin, int Cout, void* stream);
 int unetca_tc_convT_dgrad(const void* dout, int ldd, const void* wdg, void* dx, int ldx, int B, int h, int wd, int Cin, int Cout, void* stream);

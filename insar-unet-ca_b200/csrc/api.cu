@@ -8,6 +8,8 @@
 
 extern "C" {
 int unetca_tc_conv3x3_fwd(const void*, int, const void*, int, void*, int, int, int, int, int, int, float*, void*);
+int unetca_tc_conv3x3_fwd_paired(const void*, int, const void*, void*, int, int, int, int, int, int, float*, void*);
+int unetca_tc_pack_pair(const void*, int, void*, int, int, void*);
 int unetca_tc_gemm_nt(const void*, int, const void*, int, void*, int, long, int, int, float*, void*);
 int unetca_tc_convT_fwd(const void*, int, const void*, const float*, void*, int, int, int, int, int, int, void*);
 int unetca_tc_convT_dgrad(const void*, int, const void*, void*, int, int, int, int, int, int, void*);
@@ -49,6 +51,23 @@ int unetca_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk
     if (rc < 0) return rc;
     if (stat_parts) return unetca_chan_stats(dtype, y, ldy, O, (long)B * H * W, stat_parts, nparts, stream);
     return 0;
+}
+
+// The same convolution for narrow outputs (O a multiple of 64, H even) through the row-pair layout of the tcgen05
+// path: w_pair [2*O][12*C] comes from unetca_pack_conv3x3_pair.  bf16 / tensor-core implementation only.
+int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W,
+                              int C, int O, float* stat_parts, int* nparts, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("conv3x3_fwd_paired: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int rc = unetca_tc_conv3x3_fwd_paired(x, ldx, w_pair, y, ldy, B, H, W, C, O, stat_parts, stream);
+    if (rc < 0) return rc;
+    if (nparts) *nparts = rc;
+    return 0;
+}
+
+// w [rows][ld] (K-major packed filter, k = tap*C + c, bf16) -> w_pair [2*rows][12*C]
+int unetca_pack_conv3x3_pair(int dtype, const void* w, int ld, void* w_pair, int rows, int C, void* stream) {
+    if (dtype != UNETCA_DTYPE_BF16) { unetca::set_error("pack_conv3x3_pair: bf16 only"); return UNETCA_ERR_UNSUPPORTED; }
+    return unetca_tc_pack_pair(w, ld, w_pair, rows, C, stream);
 }
 
 // out[m][n] = sum_k A[m][k] * Bw[n][k]  (first conv on im2col rows, K = Kpad)

@@ -858,6 +858,235 @@ __global__ void __launch_bounds__(kHaloThreads, 1) tc_conv3x3_halo_kernel(const 
     if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_base);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// conv3x3 forward / dgrad for NARROW outputs (64 or 128 channels), pixels on the N side of the MMA.
+// Measured on B200 (tools/umma_rate_probe.cu): one tcgen05.mma M=128,K=16 with operands in shared memory never
+// takes less than ~100 cycles (A-operand fetch), whatever N is; it only reaches the tensor peak for N >= 192.
+// With pixels on M and N = O = 64 / 128 the generic kernel is therefore pinned at 32 % / 64 % of peak.  Here
+// the roles are swapped:     D[row][n] = sum_{tap,c} Wm[row][tap*C+c] * X[pix(n) + s(tap)][c]
+//   A (M = 128 rows)  = weight tile [128][64 c] per (tap, chunk), K-major, TMA box of the packed weight matrix
+//   B (N = 256 rows)  = 256 pixels x 64 channels, one TMA box per (tap, chunk) at tap-shifted coordinates
+// so every MMA is 128x256x16 (128 cycles, full rate).  Two row layouts:
+//   P = 1  (O % 128 == 0):  row = output channel o (128 per m-block), 9 taps, weights = the ordinary packed filter.
+//   P = 2  (O % 64 == 0):   row = (j, o), j = 0/1 selects output row 2i+j of a row pair, 64 channels per m-block.
+//          Both halves read the SAME pixel tile, so the filter is re-expressed over 4 x 3 "virtual taps"
+//          (input row 2i + vr - 1, vr = 0..3): rows j use W[kh = vr - j][kw] or zero ("pair-packed" weights,
+//          unetca_pack_conv3x3_pair).  9 of the 12 MMA row blocks are useful -> 75 % of peak instead of 32 %.
+//          The pixel tile is a lattice of even rows: a 5-D tensor map (C, W, parity, H/2, B).
+// The accumulator comes out transposed (TMEM lane = channel, column = pixel): the epilogue writes it through a
+// [pixel][64 ch] staging tile (2-byte stores, 64 contiguous bytes per warp: conflict free) and TMA-stores it; the
+// BatchNorm partial sums are thread-local (one lane = one channel).
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) PixNParams {
+    CUtensorMap mapX, mapW, mapOut;
+    int tilesW, tilesI, nimg;
+    int TW, TI, twShift, HP, W, P;      // HP = H / P rows of the (parity) lattice
+    int ntaps, cchunks, num_m_blocks;
+    signed char dw[12], par[12], off[12];
+    float* stat_parts;
+    int N;
+};
+constexpr int kPnStages = 3;
+constexpr int kPnABytes = 128 * 128, kPnBBytes = 256 * 128, kPnStageBytes = kPnABytes + kPnBBytes;
+constexpr int kPnOutBytes = 2 * 256 * 128;
+constexpr int kPnStatBytes = 2 * 1024 * 4 + 256 * 4;
+constexpr int kPnSmemBytes = 1024 + kPnStages * kPnStageBytes + kPnOutBytes + kPnStatBytes + 256;
+static_assert(kPnSmemBytes <= 227 * 1024, "pixn conv: shared memory budget");
+
+// epilogue of the pixels-on-N kernel for one thread (= one accumulator row = one channel): 256 fp32 columns (pixels)
+// -> bf16 -> staging[pixel][channel] (2-byte stores; a warp covers 64 contiguous bytes per pixel), plus the
+// thread-local sum / sum of squares of the stored values.  PARTIAL masks pixels outside the image.
+template <bool PARTIAL>
+__device__ __forceinline__ void pixn_drain(uint32_t t_addr, uint32_t my_s, float& s1, float& s2, int x0, int i0,
+                                           int twMask, int twShift, int W, int HP) {
+    float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll 1
+    for (int cb = 0; cb < 8; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + cb * 32, v);
+        tmem_wait_ld();
+        const uint32_t base = my_s + cb * 32 * 128;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            float f0 = __uint_as_float(v[i]), f1 = __uint_as_float(v[i + 1]);
+            if (PARTIAL) {
+                const int n = cb * 32 + i;
+                if (!((x0 + (n & twMask)) < W && (i0 + (n >> twShift)) < HP)) f0 = 0.f;
+                if (!((x0 + ((n + 1) & twMask)) < W && (i0 + ((n + 1) >> twShift)) < HP)) f1 = 0.f;
+            }
+            const uint32_t pk = pack_bf16x2(f0, f1);
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + i * 128), "h"((uint16_t)(pk & 0xffffu)) : "memory");
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (i + 1) * 128), "h"((uint16_t)(pk >> 16)) : "memory");
+            const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+            a1 += r0; a2 = fmaf(r0, r0, a2);
+            b1 += r1; b2 = fmaf(r1, r1, b2);
+        }
+    }
+    s1 = a1 + b1; s2 = a2 + b2;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __grid_constant__ PixNParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* out_stage = smem + kPnStages * kPnStageBytes;
+    float* sm_stats = reinterpret_cast<float*>(out_stage + kPnOutBytes);
+    float* sm_wpart = sm_stats + 2048;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kPnOutBytes + kPnStatBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kPnStages;
+    uint64_t* tfull_bar = bars + 2 * kPnStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kPnStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapW);
+        prefetch_tmap(&p.mapOut);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (p.stat_parts) {
+        for (int i = threadIdx.x; i < 2 * p.N; i += kTcThreads) sm_stats[i] = 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesI;
+    const long num_work = (long)tiles_per_img * p.nimg * p.num_m_blocks;
+    const int nk = p.ntaps * p.cchunks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int mb = (int)(t % p.num_m_blocks);
+                const int mt = (int)(t / p.num_m_blocks);
+                const int tw = mt % p.tilesW, ti = (mt / p.tilesW) % p.tilesI, b = mt / tiles_per_img;
+                const int x0 = tw * p.TW, i0 = ti * p.TI;
+                for (int tap = 0; tap < p.ntaps; ++tap) {
+                    for (int cc = 0; cc < p.cchunks; ++cc) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        uint8_t* sa = smem + s * kPnStageBytes;
+                        mbar_expect_tx(&full_bar[s], kPnStageBytes);
+                        tma_load_4d(&p.mapW, &full_bar[s], sa, (tap * p.cchunks + cc) * 64, mb * 128, 0, 0);
+                        tma_load_5d(&p.mapX, &full_bar[s], sa + kPnABytes, cc * 64, x0 + p.dw[tap], p.par[tap],
+                                    i0 + p.off[tap], b);
+                        if (++s == kPnStages) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * kPnStageBytes);
+                    const uint32_t sb = sa + kPnABytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc,
+                                  (kb | k) != 0);
+                    umma_commit(&empty_bar[s]);
+                    if (++s == kPnStages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+                as ^= 1; if (as == 0) aph ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;             // accumulator row = TMEM lane
+        const int ep_tid = threadIdx.x - 64;
+        const int box = r >> 6, oc = r & 63;
+        uint8_t* my = out_stage + box * (256 * 128) + oc * 2;
+        int as = 0; uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int mb = (int)(t % p.num_m_blocks);
+            const int mt = (int)(t / p.num_m_blocks);
+            const int tw = mt % p.tilesW, ti = (mt / p.tilesW) % p.tilesI, b = mt / tiles_per_img;
+            const int x0 = tw * p.TW, i0 = ti * p.TI;
+            const bool full = (x0 + p.TW <= p.W) && (i0 + p.TI <= p.HP);
+            mbar_wait(&tfull_bar[as], aph);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            if (ep_tid == 0) tma_store_wait_read();          // staging drained by the previous tile's store
+            named_bar_sync(1, 128);
+            float s1 = 0.f, s2 = 0.f;
+            const uint32_t my_s = smem_u32(my);
+            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0);
+            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, i0, p.TW - 1, p.twShift, p.W, p.HP);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (ep_tid == 0) {
+                if (p.P == 1) {
+                    tma_store_5d(&p.mapOut, out_stage, mb * 128, x0, 0, i0, b);
+                    tma_store_5d(&p.mapOut, out_stage + 256 * 128, mb * 128 + 64, x0, 0, i0, b);
+                } else {
+                    tma_store_5d(&p.mapOut, out_stage, mb * 64, x0, 0, i0, b);
+                    tma_store_5d(&p.mapOut, out_stage + 256 * 128, mb * 64, x0, 1, i0, b);
+                }
+                tma_store_commit();
+            }
+            if (p.stat_parts) {
+                if (p.P == 1) {
+                    sm_stats[mb * 128 + r] += s1;
+                    sm_stats[p.N + mb * 128 + r] += s2;
+                } else {
+                    sm_wpart[r] = s1; sm_wpart[128 + r] = s2;
+                    named_bar_sync(1, 128);
+                    if (r < 64) {
+                        sm_stats[mb * 64 + r] += sm_wpart[r] + sm_wpart[r + 64];
+                        sm_stats[p.N + mb * 64 + r] += sm_wpart[128 + r] + sm_wpart[192 + r];
+                    }
+                }
+            }
+            as ^= 1; if (as == 0) aph ^= 1;
+        }
+        if (ep_tid == 0) tma_store_wait_all();
+        named_bar_sync(1, 128);
+        if (p.stat_parts) {
+            float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
+            for (int i = ep_tid; i < 2 * p.N; i += 128) dst[i] = sm_stats[i];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// pair-packed weights for the P = 2 layout: dst[(g*128 + j*64 + o)][(vr*3+kw)*C + c] = src[(g*64+o)][((vr-j)*3+kw)*C + c]
+// when 0 <= vr-j <= 2, else 0.  src: K-major packed filter [rows][ld] (k = tap*C + c), rows a multiple of 64.
+__global__ void pack_pair_kernel(const bf16* __restrict__ src, int ld, bf16* __restrict__ dst, int rows, int C) {
+    const long total = (long)2 * rows * 12 * C;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int k = (int)(i % (12 * C));
+    const int row = (int)(i / (12 * C));
+    const int g = row / 128, j = (row / 64) & 1, o = row & 63;
+    const int v = k / C, c = k % C;
+    const int vr = v / 3, kw = v % 3;
+    const int kh = vr - j;
+    dst[i] = (kh >= 0 && kh <= 2) ? src[(long)(g * 64 + o) * ld + (kh * 3 + kw) * C + c] : __float2bfloat16_rn(0.f);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side: tensor maps, tiling, launch
 // ---------------------------------------------------------------------------------------------------------
@@ -986,6 +1215,69 @@ static int launch_halo(const void* x, int ldx, const void* w, int ldk, void* y, 
     return BN == 64 ? launch_halo_n<64>(p, num_work, st) : launch_halo_n<128>(p, num_work, st);
 }
 
+// 5-D bf16 map over an NHWC activation seen as (C, W, P, H/P, B): P = 2 splits the rows into an even and an odd
+// lattice (row = 2*i + parity).  box (64, bw, 1, bi, 1).
+static int make_map5(CUtensorMap* m, const void* base, long C, long W, long H, long B, long ld, int P, int bw, int bi,
+                     bool swizzle) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return UNETCA_ERR_CUDA; }
+    cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)P, (cuuint64_t)(H / P), (cuuint64_t)B};
+    cuuint64_t strides[4] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)P * W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)bw, 1, (cuuint32_t)bi, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (((uintptr_t)base & 15) || (strides[0] & 15)) { set_error("tensor map: base/strides must be 16-byte aligned"); return UNETCA_ERR_ARG; }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (5-D) failed (%d): dims %ld %ld %d %ld %ld box %d %d", (int)r, C, W, P, H / P, B, bw, bi);
+        return UNETCA_ERR_CUDA;
+    }
+    return 0;
+}
+
+static int g_no_pixn = 0;
+
+// w: P == 1: packed filter [O][9*C];  P == 2: pair-packed filter [2*O][12*C] (unetca_pack_conv3x3_pair)
+static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
+                       int P, float* stat_parts, cudaStream_t st) {
+    PixNParams p;
+    memset(&p, 0, sizeof(p));
+    const int HP = H / P;
+    int TW = 0, TI = 0;
+    pick_tile(HP, W, 256, &TW, &TI);
+    int rc;
+    if ((rc = make_map5(&p.mapX, x, C, W, H, B, ldx, P, TW, TI, true)) < 0) return rc;
+    const int ntaps = P == 1 ? 9 : 12;
+    const long rows = P == 1 ? O : 2L * O;
+    if ((rc = make_map(&p.mapW, w, (long)ntaps * C, rows, 1, 1, ldk, rows * ldk, rows * ldk, 128, 1)) < 0) return rc;
+    if ((rc = make_map5(&p.mapOut, y, O, W, H, B, ldy, P, TW, TI, false)) < 0) return rc;
+    p.tilesW = ceil_div(W, TW); p.tilesI = ceil_div(HP, TI); p.nimg = B;
+    p.TW = TW; p.TI = TI; p.HP = HP; p.W = W; p.P = P;
+    p.twShift = 0; while ((1 << p.twShift) < TW) ++p.twShift;
+    p.ntaps = ntaps; p.cchunks = C / 64;
+    p.num_m_blocks = P == 1 ? O / 128 : O / 64;
+    for (int t = 0; t < ntaps; ++t) {
+        const int d = t / 3 - 1;                  // input row offset: -1..1 (P=1) or -1..2 relative to the even row (P=2)
+        p.dw[t] = (signed char)(t % 3 - 1);
+        if (P == 1) { p.par[t] = 0; p.off[t] = (signed char)d; }
+        else { p.par[t] = (signed char)(d & 1); p.off[t] = (signed char)(d < 0 ? -1 : d / 2); }
+    }
+    p.stat_parts = stat_parts; p.N = O;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
+        if (e != cudaSuccess) { set_error("tc_conv3x3 (pixn): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    const long num_work = (long)p.tilesW * p.tilesI * B * p.num_m_blocks;
+    long grid = num_work < num_sms() ? num_work : num_sms();
+    if (grid < 1) grid = 1;
+    tc_conv3x3_pixn_kernel<<<(int)grid, kTcThreads, kPnSmemBytes, st>>>(p);
+    rc = check_launch("tc_conv3x3_fwd (pixn)");
+    return rc < 0 ? rc : (int)grid;
+}
+
 static void set_taps3x3(TcParams& p) {
     for (int t = 0; t < 9; ++t) { p.dh[t] = (signed char)(t / 3 - 1); p.dw[t] = (signed char)(t % 3 - 1); p.amap[t] = 0; }
 }
@@ -999,6 +1291,23 @@ extern "C" {
 void unetca_tc_force_block_n(int n) { g_force_block_n = n; }
 void unetca_tc_force_wgrad_narrow(int on) { g_wgrad_narrow = on; }
 void unetca_tc_force_no_halo(int on) { g_no_halo = on; }
+void unetca_tc_force_no_pixn(int on) { g_no_pixn = on; }
+
+// conv3x3 forward / dgrad through the row-pair layout (O a multiple of 64, H even); w_pair from unetca_tc_pack_pair
+int unetca_tc_conv3x3_fwd_paired(const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C,
+                                 int O, float* stat_parts, void* stream) {
+    UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0 && O <= 1024 && H % 2 == 0,
+                   "tc_conv3x3_paired: C=%d O=%d must be multiples of 64 and H=%d even", C, O, H);
+    return launch_pixn(x, ldx, w_pair, 12 * C, y, ldy, B, H, W, C, O, 2, stat_parts, (cudaStream_t)stream);
+}
+
+// w_pair [2*rows][12*C] from the K-major packed filter w [rows][ld] (k = tap*C + c)
+int unetca_tc_pack_pair(const void* w, int ld, void* w_pair, int rows, int C, void* stream) {
+    UNETCA_REQUIRE(rows % 64 == 0 && C > 0 && ld >= 9 * C, "tc_pack_pair: rows=%d C=%d ld=%d", rows, C, ld);
+    const long total = 2L * rows * 12 * C;
+    pack_pair_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)w, ld, (bf16*)w_pair, rows, C);
+    return check_launch("tc_pack_pair");
+}
 
 // y[p][n] = sum_{tap,c} x[p+s(tap)][c] * w[n][tap*C+c]   (bf16 NHWC in/out, fp32 accumulate).
 // stat_parts != null: per-CTA partial per-channel sum / sum-of-squares of the *stored* bf16 outputs,
@@ -1006,6 +1315,8 @@ void unetca_tc_force_no_halo(int on) { g_no_halo = on; }
 int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C,
                           int O, float* stat_parts, void* stream) {
     UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0 && O <= 1024, "tc_conv3x3: C=%d O=%d must be multiples of 64 (O<=1024)", C, O);
+    if (O % 128 == 0 && O % 256 != 0 && !g_no_pixn && !g_force_block_n)
+        return launch_pixn(x, ldx, w, ldk, y, ldy, B, H, W, C, O, 1, stat_parts, (cudaStream_t)stream);
     if (pick_block_n(O) <= 128 && !g_no_halo) return launch_halo(x, ldx, w, ldk, y, ldy, B, H, W, C, O, stat_parts, (cudaStream_t)stream);
     TcParams p;
     memset(&p, 0, sizeof(p));

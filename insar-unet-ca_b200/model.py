@@ -131,7 +131,17 @@ class _Engine:
             wf = torch.empty(O, ldk, dtype=tdt, device=w.device)
             wd = None if first else torch.empty(C, 9 * O, dtype=tdt, device=w.device)
             _lib.call("unetca_pack_conv3x3_weight", dt, _ptr(w), _ptr(wf), ldk, _ptr(wd), O, C, _stream())
-            return wf, wd, ldk
+            # narrow outputs (a multiple of 64 but not of 128 channels) run through the row-pair layout of the
+            # tcgen05 path, which wants the filter re-expressed over 4x3 virtual taps
+            wfp = wdp = None
+            if dt == _lib.BF16 and not first:
+                if O % 128:
+                    wfp = torch.empty(2 * O, 12 * C, dtype=tdt, device=w.device)
+                    _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wf), ldk, _ptr(wfp), O, C, _stream())
+                if C % 128:
+                    wdp = torch.empty(2 * C, 12 * O, dtype=tdt, device=w.device)
+                    _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wd), 9 * O, _ptr(wdp), C, O, _stream())
+            return wf, wd, ldk, wfp, wdp
         return self._cached(("c", id(conv)), w, tdt, build)
 
     def convT_w(self, up: nn.ConvTranspose2d, dt, tdt):
@@ -144,6 +154,14 @@ class _Engine:
             _lib.call("unetca_pack_convT_weight", dt, _ptr(w), _ptr(wf), _ptr(wd), Cin, Cout, _stream())
             return wf, wd
         return self._cached(("t", id(up)), w, tdt, build)
+
+
+def _conv3x3(dt, x, ldx, w, ldk, w_pair, y, ldy, B, H, W, C, O, sp, nparts, st):
+    """conv3x3 forward (or dgrad with the dgrad-packed filter): row-pair tcgen05 layout when a pair-packed filter exists."""
+    if w_pair is not None and H % 2 == 0 and _lib.load().unetca_get_conv_impl() == 0:
+        _lib.call("unetca_conv3x3_fwd_paired", dt, _ptr(x), ldx, _ptr(w_pair), _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
+    else:
+        _lib.call("unetca_conv3x3_fwd", dt, _ptr(x), ldx, _ptr(w), ldk, _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
 
 
 def _check_input(model, x):
@@ -194,22 +212,20 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
 
     sp = _ptr(parts) if train else None
     # ---- conv1 -> BN -> ReLU
-    wf1, _, ldk1 = eng.conv_w(blk.conv1, dt, tdt, blk.first)
+    wf1, _, ldk1, wfp1, _ = eng.conv_w(blk.conv1, dt, tdt, blk.first)
     y1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
     if blk.first:
         _lib.call("unetca_gemm_nt", dt, _ptr(col), col.shape[1], _ptr(wf1), ldk1, _ptr(y1), O, npix, O, col.shape[1],
                   sp, ctypes.byref(nparts), st)
     else:
-        _lib.call("unetca_conv3x3_fwd", dt, _ptr(xin), xin.stride(2), _ptr(wf1), ldk1, _ptr(y1), O, B, Hl, Wl, C, O,
-                  sp, ctypes.byref(nparts), st)
+        _conv3x3(dt, xin, xin.stride(2), wf1, ldk1, wfp1, y1, O, B, Hl, Wl, C, O, sp, ctypes.byref(nparts), st)
     scale1, shift1 = bn_params(blk.bn1, blk.conv1, "1")
     a1 = torch.empty_like(y1)
     _lib.call("unetca_bn_relu", dt, _ptr(y1), O, _ptr(a1), O, B, Hl * Wl, O, _ptr(scale1), _ptr(shift1), None, None, st)
     # ---- conv2 -> BN -> ReLU [-> SE] [-> MaxPool]
-    wf2, _, ldk2 = eng.conv_w(blk.conv2, dt, tdt, False)
+    wf2, _, ldk2, wfp2, _ = eng.conv_w(blk.conv2, dt, tdt, False)
     y2 = torch.empty_like(y1)
-    _lib.call("unetca_conv3x3_fwd", dt, _ptr(a1), O, _ptr(wf2), ldk2, _ptr(y2), O, B, Hl, Wl, O, O, sp,
-              ctypes.byref(nparts), st)
+    _conv3x3(dt, a1, O, wf2, ldk2, wfp2, y2, O, B, Hl, Wl, O, O, sp, ctypes.byref(nparts), st)
     scale2, shift2 = bn_params(blk.bn2, blk.conv2, "2")
     s = None
     if blk.se is not None:
@@ -372,9 +388,9 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
     dw = G.alloc(pre + ".3.weight", blk.conv2.weight)
     _lib.call("unetca_conv3x3_wgrad", dt, _ptr(dy2), O, _ptr(sv.a1), O, _ptr(ws), ws.numel(), B, Hl, Wl, O, O, _ptr(dw), st)
     G.put(pre + ".3.weight")
-    _, wd2, _ = eng.conv_w(blk.conv2, dt, tdt, False)
+    _, wd2, _, _, wdp2 = eng.conv_w(blk.conv2, dt, tdt, False)
     da1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
-    _lib.call("unetca_conv3x3_fwd", dt, _ptr(dy2), O, _ptr(wd2), 9 * O, _ptr(da1), O, B, Hl, Wl, O, O, None, None, st)
+    _conv3x3(dt, dy2, O, wd2, 9 * O, wdp2, da1, O, B, Hl, Wl, O, O, None, None, st)
     del dy2
     # ---- ReLU -> BN1 backward
     dy1 = bn_relu_bwd(da1, O, sv.y1, "1", None, None, 1)
@@ -390,9 +406,9 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
     G.put(pre + ".0.weight")
     if not need_dx or blk.first:
         return None
-    _, wd1, _ = eng.conv_w(blk.conv1, dt, tdt, False)
+    _, wd1, _, _, wdp1 = eng.conv_w(blk.conv1, dt, tdt, False)
     dx = torch.empty(B, Hl, Wl, C, dtype=tdt, device=dev)
-    _lib.call("unetca_conv3x3_fwd", dt, _ptr(dy1), O, _ptr(wd1), 9 * O, _ptr(dx), C, B, Hl, Wl, O, C, None, None, st)
+    _conv3x3(dt, dy1, O, wd1, 9 * O, wdp1, dx, C, B, Hl, Wl, O, C, None, None, st)
     return dx
 
 

@@ -271,6 +271,22 @@ def _conv_case(dt, impl, B, C, O, H, W, seed=4):
     dw = torch.empty(O, C, 3, 3, device="cuda")
     call("unetca_conv3x3_wgrad", dt, ptr(dyd), O, ptr(xd), C, ptr(ws), ws.numel(), B, H, W, C, O, ptr(dw), stream())
     assert relerr(dw.cpu(), wr.grad) < 2e-3, "wgrad"
+    if impl == 0 and dt == BF16 and H % 2 == 0:
+        # row-pair layout of the tcgen05 path (pixels on the MMA's N side, pair-packed filter): forward + stats + dgrad
+        wfp = torch.empty(2 * O, 12 * C, dtype=TDT[dt], device="cuda")
+        call("unetca_pack_conv3x3_pair", dt, ptr(wf), 9 * C, ptr(wfp), O, C, stream())
+        y2 = torch.full((B, H, W, O), float("nan"), dtype=TDT[dt], device="cuda")
+        call("unetca_conv3x3_fwd_paired", dt, ptr(xd), C, ptr(wfp), ptr(y2), O, B, H, W, C, O, ptr(parts), ctypes.byref(n),
+             stream())
+        got2 = from_nhwc(y2)
+        assert relerr(got2, ref.detach()) < tol, "fwd (paired)"
+        st = parts[: n.value * 2 * O].view(n.value, 2, O).sum(0).cpu()
+        assert relerr(st[0], got2.sum((0, 2, 3))) < 1e-3 and relerr(st[1], (got2 * got2).sum((0, 2, 3))) < 1e-3, "stats (paired)"
+        wdp = torch.empty(2 * C, 12 * O, dtype=TDT[dt], device="cuda")
+        call("unetca_pack_conv3x3_pair", dt, ptr(wdg), 9 * O, ptr(wdp), C, O, stream())
+        dx2 = torch.full((B, H, W, C), float("nan"), dtype=TDT[dt], device="cuda")
+        call("unetca_conv3x3_fwd_paired", dt, ptr(dyd), O, ptr(wdp), ptr(dx2), C, B, H, W, O, C, None, None, stream())
+        assert relerr(from_nhwc(dx2), xr.grad) < tol, "dgrad (paired)"
 
 
 @pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 64, 16, 16), (1, 128, 64, 8, 24), (2, 64, 192, 4, 4)])
@@ -281,7 +297,8 @@ def test_conv3x3_ffma(dt, B, C, O, H, W):
 
 @pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 64, 16, 16), (1, 128, 64, 8, 24), (2, 64, 192, 4, 4),
                                        (2, 128, 256, 32, 32), (3, 256, 128, 16, 48), (1, 64, 64, 128, 128),
-                                       (2, 128, 128, 40, 24), (1, 192, 64, 48, 16)])
+                                       (2, 128, 128, 40, 24), (1, 192, 64, 48, 16), (2, 64, 128, 64, 64), (1, 64, 64, 34, 20),
+                                       (1, 128, 384, 16, 16)])
 def test_conv3x3_tcgen05(B, C, O, H, W):
     _conv_case(BF16, 0, B, C, O, H, W)
 

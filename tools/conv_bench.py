@@ -24,11 +24,12 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-halo", action="store_true", help="narrow layers through the generic one-box-per-tap kernel")
+    ap.add_argument("--no-pixn", action="store_true", help="narrow layers through the pixels-on-M generic kernel")
     ap.add_argument("--dgrad", action="store_true", help="add the dgrad shapes (O -> C) of the narrow layers")
     a = ap.parse_args()
     lib = _lib.load()
     lib.unetca_tc_force_block_n(a.block_n)
-    lib.unetca_tc_force_no_halo(1 if a.no_halo else 0)
+    lib.unetca_tc_force_no_pixn(1 if a.no_pixn else 0)
     layers = LAYERS if a.layers == ["all"] else [tuple(int(v) for v in s.split(",")) for s in a.layers]
     if a.dgrad:
         layers = layers + [(64, 128, 512), (128, 64, 256), (256, 128, 128)]
@@ -44,9 +45,16 @@ def main():
         wf = (torch.randn(O, 9 * C, device="cuda") / (9 * C) ** 0.5).bfloat16()
         dw = torch.empty(O, C, 3, 3, device="cuda")
         fl = 2.0 * B * S * S * 9 * C * O
+        wfp = None
+        if O % 128 and not a.no_pixn:
+            wfp = torch.empty(2 * O, 12 * C, device="cuda", dtype=torch.bfloat16)
+            _lib.call("unetca_pack_conv3x3_pair", 1, wf.data_ptr(), 9 * C, wfp.data_ptr(), O, C, st)
         res = []
         for what in a.what.split(","):
-            if what == "fwd":
+            if what == "fwd" and wfp is not None:
+                fn = lambda: _lib.call("unetca_conv3x3_fwd_paired", 1, x.data_ptr(), C, wfp.data_ptr(), y.data_ptr(), O, B, S, S,
+                                       C, O, parts.data_ptr(), ctypes.byref(n), st)  # noqa: E731
+            elif what == "fwd":
                 fn = lambda: _lib.call("unetca_conv3x3_fwd", 1, x.data_ptr(), C, wf.data_ptr(), 9 * C, y.data_ptr(), O, B, S, S,
                                        C, O, parts.data_ptr(), ctypes.byref(n), st)  # noqa: E731
             else:
