@@ -94,6 +94,10 @@ int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, 
 /* standalone pool; idx64 (optional) = torch's (B,C,H/2,W/2) int64 flat indices h*W+w */
 int unetca_maxpool2x2(int dtype, const void* x, int ldx, void* pooled, int ldp, uint8_t* pos, long long* idx64, int B, int H, int W, int C, void* stream);
 int unetca_pool_bwd_add(int dtype, const void* skip_grad, int lds, const void* dpooled, int ldp, const uint8_t* pos, void* dx, int ldx, int B, int H, int W, int C, void* stream);
+/* bilinear resize guard of the decoder (UCA:138-157: F_T.resize(x, skip.shape, BILINEAR) when H or W is not in 16*N):
+ * (B,h,w,C) -> (B,H,W,C), align_corners=False, and its adjoint */
+int unetca_resize_bilinear_fwd(int dtype, const void* x, int ldx, int h, int w, void* out, int ldo, int H, int W, int B, int C, void* stream);
+int unetca_resize_bilinear_bwd(int dtype, const void* dout, int ldd, int H, int W, void* dx, int ldx, int h, int w, int B, int C, void* stream);
 int unetca_se_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, float* parts, int* nparts, void* stream);
 int unetca_se_fc_bwd(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2, const float* p, const float* z, const float* s, float* dpre2, float* dz, float* dp, float* dw1, float* dw2, void* stream);
 /* SE squeeze with the extra per-image sums (sum m, sum m*(y-mean)) the merged backward needs: parts [B * *nparts][3][C] */

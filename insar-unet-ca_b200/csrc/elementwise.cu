@@ -812,6 +812,116 @@ __global__ void bn_bwd_finalize_se_kernel(const float* __restrict__ sums, int B,
     coef[2 * C + c] = (float)(q / count);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Bilinear resize guard of the decoder (UCA:138-157): torchvision F_T.resize(tensor, size, BILINEAR) ==
+// interpolate(mode='bilinear', align_corners=False, antialias=True).  It only ever up-samples here
+// (2*floor(h/2) -> h), where the antialias triangle filter reduces to the ordinary two taps with index clamping
+// (the two-tap form is pinned against torch.nn.functional.interpolate(antialias=True) by the CPU tests).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bilinear_tap(int o, int n_in, float scale, int& i0, int& i1, float& lam) {
+    const float src = fmaxf(((float)o + 0.5f) * scale - 0.5f, 0.f);
+    i0 = min((int)src, n_in - 1);
+    i1 = min(i0 + 1, n_in - 1);
+    lam = src - (float)i0;
+}
+
+// one thread = one output pixel x one channel vector
+template <typename T>
+__global__ void __launch_bounds__(kThreads) resize_bilinear_fwd_kernel(const T* __restrict__ x, int ldx, int h, int w,
+                                                                       T* __restrict__ out, int ldo, int H, int W, int B,
+                                                                       int C, float sh, float sw) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC;
+    const long gid = (long)blockIdx.x * kThreads + threadIdx.x;
+    const long pix = gid / vpr;
+    const int cv = (int)(gid % vpr);
+    if (pix >= (long)B * H * W) return;
+    const int ow = (int)(pix % W), oh = (int)((pix / W) % H);
+    const long b = pix / ((long)W * H);
+    int h0, h1, w0, w1; float lh, lw;
+    bilinear_tap(oh, h, sh, h0, h1, lh);
+    bilinear_tap(ow, w, sw, w0, w1, lw);
+    float v00[VEC], v01[VEC], v10[VEC], v11[VEC];
+    const T* xb = x + b * h * w * (long)ldx + cv * VEC;
+    load_vec(xb + ((long)h0 * w + w0) * ldx, v00);
+    load_vec(xb + ((long)h0 * w + w1) * ldx, v01);
+    load_vec(xb + ((long)h1 * w + w0) * ldx, v10);
+    load_vec(xb + ((long)h1 * w + w1) * ldx, v11);
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const float top = v00[i] * (1.f - lw) + v01[i] * lw;
+        const float bot = v10[i] * (1.f - lw) + v11[i] * lw;
+        v00[i] = top * (1.f - lh) + bot * lh;
+    }
+    store_vec(out + pix * ldo + cv * VEC, v00);
+}
+
+// adjoint, as a gather: one thread = one INPUT pixel x one channel vector; it visits the few output pixels whose
+// taps can reference it (deterministic, no atomics).
+template <typename T>
+__global__ void __launch_bounds__(kThreads) resize_bilinear_bwd_kernel(const T* __restrict__ dout, int ldd, int H, int W,
+                                                                       T* __restrict__ dx, int ldx, int h, int w, int B,
+                                                                       int C, float sh, float sw) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC;
+    const long gid = (long)blockIdx.x * kThreads + threadIdx.x;
+    const long pix = gid / vpr;
+    const int cv = (int)(gid % vpr);
+    if (pix >= (long)B * h * w) return;
+    const int iw = (int)(pix % w), ih = (int)((pix / w) % h);
+    const long b = pix / ((long)w * h);
+    // output rows / columns whose source coordinate can fall in (i-1, i+1)
+    const int oh_lo = max(0, (int)floorf(((float)ih - 0.5f) / sh - 0.5f) - 1);
+    const int oh_hi = min(H - 1, (int)ceilf(((float)ih + 1.5f) / sh - 0.5f) + 1);
+    const int ow_lo = max(0, (int)floorf(((float)iw - 0.5f) / sw - 0.5f) - 1);
+    const int ow_hi = min(W - 1, (int)ceilf(((float)iw + 1.5f) / sw - 0.5f) + 1);
+    float acc[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+    const T* db = dout + b * H * W * (long)ldd + cv * VEC;
+    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+        int h0, h1; float lh;
+        bilinear_tap(oh, h, sh, h0, h1, lh);
+        const float wh = (h0 == ih ? 1.f - lh : 0.f) + (h1 == ih ? lh : 0.f);
+        if (wh == 0.f) continue;
+        for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+            int w0, w1; float lw;
+            bilinear_tap(ow, w, sw, w0, w1, lw);
+            const float ww = (w0 == iw ? 1.f - lw : 0.f) + (w1 == iw ? lw : 0.f);
+            if (ww == 0.f) continue;
+            float d[VEC];
+            load_vec(db + ((long)oh * W + ow) * ldd, d);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) acc[i] = fmaf(wh * ww, d[i], acc[i]);
+        }
+    }
+    store_vec(dx + pix * ldx + cv * VEC, acc);
+}
+
+// last row / column of an odd-sized map: MaxPool2d(2) floors, so those pixels only carry the skip gradient
+template <typename T>
+__global__ void __launch_bounds__(kThreads) pool_bwd_border_kernel(const T* __restrict__ skip_grad, int lds,
+                                                                   T* __restrict__ dx, int ldx, int B, int H, int W, int C) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC;
+    const int nrow = (H & 1) ? W : 0, ncol = (W & 1) ? (H - (H & 1)) : 0;
+    const long gid = (long)blockIdx.x * kThreads + threadIdx.x;
+    const long k = gid / vpr;
+    const int cv = (int)(gid % vpr);
+    if (k >= (long)B * (nrow + ncol)) return;
+    const int j = (int)(k % (nrow + ncol));
+    const long b = k / (nrow + ncol);
+    const int hh = j < nrow ? H - 1 : j - nrow, ww = j < nrow ? j : W - 1;
+    const long p = (b * H + hh) * W + ww;
+    float v[VEC];
+    if (skip_grad) load_vec(skip_grad + p * lds + cv * VEC, v);
+    else {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) v[i] = 0.f;
+    }
+    store_vec(dx + p * ldx + cv * VEC, v);
+}
+
 // per-channel sum over pixels (ConvTranspose2d bias gradient)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) chan_sum_kernel(const T* __restrict__ x, int ld, int C, long npix,
@@ -1331,9 +1441,38 @@ int unetca_pool_bwd_add(int dtype, const void* skip_grad, int lds, const void* d
         REQ_CHAN(C, ldp); REQ_CHAN(C, ldx);
         if (skip_grad) REQ_CHAN(C, lds);
         const long nthr = (long)B * (H / 2) * (W / 2) * (C / VecTraits<T>::N);
-        pool_bwd_add_kernel<T><<<ceil_div(nthr, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const T*)skip_grad, lds, (const T*)dpooled, ldp, pos, (T*)dx, ldx, B, H, W, C);
+        if (nthr > 0)
+            pool_bwd_add_kernel<T><<<ceil_div(nthr, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const T*)skip_grad, lds, (const T*)dpooled, ldp, pos, (T*)dx, ldx, B, H, W, C);
+        if ((H & 1) || (W & 1)) {
+            const long nb = (long)B * (((H & 1) ? W : 0) + ((W & 1) ? (H - (H & 1)) : 0)) * (C / VecTraits<T>::N);
+            pool_bwd_border_kernel<T><<<ceil_div(nb, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const T*)skip_grad, lds, (T*)dx, ldx, B, H, W, C);
+        }
     });
     return check_launch("pool_bwd_add");
+}
+
+// resize guard of the decoder (UCA:138-157): (B,h,w,C) -> (B,H,W,C), bilinear, align_corners=False
+int unetca_resize_bilinear_fwd(int dtype, const void* x, int ldx, int h, int w, void* out, int ldo, int H, int W, int B,
+                               int C, void* stream) {
+    UNETCA_REQUIRE(h > 0 && w > 0 && H >= h && W >= w, "resize_bilinear: %dx%d -> %dx%d (the guard only up-samples)", h, w, H, W);
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldx); REQ_CHAN(C, ldo);
+        const long nthr = (long)B * H * W * (C / VecTraits<T>::N);
+        resize_bilinear_fwd_kernel<T><<<ceil_div(nthr, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const T*)x, ldx, h, w, (T*)out, ldo, H, W, B, C, (float)h / (float)H, (float)w / (float)W);
+    });
+    return check_launch("resize_bilinear_fwd");
+}
+
+// adjoint: dout (B,H,W,C) -> dx (B,h,w,C)
+int unetca_resize_bilinear_bwd(int dtype, const void* dout, int ldd, int H, int W, void* dx, int ldx, int h, int w, int B,
+                               int C, void* stream) {
+    UNETCA_REQUIRE(h > 0 && w > 0 && H >= h && W >= w, "resize_bilinear: %dx%d -> %dx%d (the guard only up-samples)", h, w, H, W);
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, ldd); REQ_CHAN(C, ldx);
+        const long nthr = (long)B * h * w * (C / VecTraits<T>::N);
+        resize_bilinear_bwd_kernel<T><<<ceil_div(nthr, kThreads), kThreads, 0, (cudaStream_t)stream>>>((const T*)dout, ldd, H, W, (T*)dx, ldx, h, w, B, C, (float)h / (float)H, (float)w / (float)W);
+    });
+    return check_launch("resize_bilinear_bwd");
 }
 
 int unetca_se_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C,

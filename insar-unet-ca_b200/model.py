@@ -172,10 +172,10 @@ def _check_input(model, x):
     if x.shape[1] != model.in_channels:
         raise RuntimeError(f"expected input with {model.in_channels} channels, got {x.shape[1]}")
     H, W = x.shape[2], x.shape[3]
-    if H % 16 or W % 16:
-        raise NotImplementedError(
-            f"input {H}x{W}: H and W must be multiples of 16; the reference's bilinear resize guard "
-            "(Unet-ChannalAttention.py:138-157) is not implemented on the CUDA path")
+    if H < 16 or W < 16:
+        # four MaxPool2d(2) need at least 16 pixels per side; torch raises from max_pool2d in the reference
+        raise RuntimeError(f"input {H}x{W} is too small: four 2x2 max-pools need H, W >= 16 "
+                           "(Unet-ChannalAttention.py:106-109)")
     if x.requires_grad:
         raise NotImplementedError("gradient w.r.t. the input image is not implemented (the reference never needs it)")
 
@@ -240,9 +240,16 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
         _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(p), _ptr(z),
                   _ptr(s), _ptr(sums34), st)
         sv.p, sv.z, sv.s, sv.sums34 = p, z, s, sums34
-    _lib.call("unetca_se_scale_pool", dt, _ptr(y2), O, _ptr(out_view), out_view.stride(2), _ptr(pooled),
-              pooled.stride(2) if pooled is not None else 0, _ptr(pos), B, Hl, Wl, O, _ptr(scale2), _ptr(shift2),
-              _ptr(s), st)
+    if pooled is not None and (Hl % 2 or Wl % 2):
+        # odd extent: MaxPool2d(2) floors (UCA:106-109) -> scale pass, then the standalone pool over the stored values
+        _lib.call("unetca_se_scale_pool", dt, _ptr(y2), O, _ptr(out_view), out_view.stride(2), None, 0, None, B, Hl, Wl,
+                  O, _ptr(scale2), _ptr(shift2), _ptr(s), st)
+        _lib.call("unetca_maxpool2x2", dt, _ptr(out_view), out_view.stride(2), _ptr(pooled), pooled.stride(2), _ptr(pos),
+                  None, B, Hl, Wl, O, st)
+    else:
+        _lib.call("unetca_se_scale_pool", dt, _ptr(y2), O, _ptr(out_view), out_view.stride(2), _ptr(pooled),
+                  pooled.stride(2) if pooled is not None else 0, _ptr(pos), B, Hl, Wl, O, _ptr(scale2), _ptr(shift2),
+                  _ptr(s), st)
     if keep:
         sv.y1, sv.a1, sv.y2 = y1, a1, y2
     return sv
@@ -257,6 +264,8 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
     dev = x.device
     st = _stream()
     B, Cin, H, W = x.shape
+    Hs = [H >> l for l in range(5)]                  # MaxPool2d(2) floors: repeated halving == shift
+    Ws = [W >> l for l in range(5)]
     if train and B * (H // 16) * (W // 16) <= 1:
         raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                          f"{[B, 1024, H // 16, W // 16]}")
@@ -267,12 +276,12 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
     col = torch.empty(B * H * W, Kpad, dtype=tdt, device=dev)
     _lib.call("unetca_im2col3x3_nchw", dt, _ptr(xf), _ptr(col), B, Cin, H, W, Kpad, st)
 
-    sv = SimpleNamespace(enc=[], dec=[], up_in=[], cat=[], pos=[], B=B, H=H, W=W)
-    cat = [torch.empty(B, H >> l, W >> l, 2 * _WIDTHS[l], dtype=tdt, device=dev) for l in range(4)]
+    sv = SimpleNamespace(enc=[], dec=[], up_in=[], cat=[], pos=[], B=B, H=H, W=W, Hs=Hs, Ws=Ws)
+    cat = [torch.empty(B, Hs[l], Ws[l], 2 * _WIDTHS[l], dtype=tdt, device=dev) for l in range(4)]
     # ---- encoder
     xin = None
     for l, blk in enumerate(model._enc_blocks):
-        Hl, Wl, Cl = H >> l, W >> l, _WIDTHS[l]
+        Hl, Wl, Cl = Hs[l], Ws[l], _WIDTHS[l]
         if l < 4:
             out_view = cat[l][..., :Cl]
             pooled = torch.empty(B, Hl // 2, Wl // 2, Cl, dtype=tdt, device=dev)
@@ -289,10 +298,19 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
     h = xin
     for i, (up, blk) in enumerate(zip(model._ups, model._dec_blocks)):
         l = 3 - i
-        Hl, Wl, Cl = H >> l, W >> l, _WIDTHS[l]
+        Hl, Wl, Cl = Hs[l], Ws[l], _WIDTHS[l]
+        hi, wi = Hs[l + 1], Ws[l + 1]
         wf, _ = eng.convT_w(up, dt, tdt)
-        _lib.call("unetca_convT2x2_fwd", dt, _ptr(h), h.stride(2), _ptr(wf), _ptr(up.bias), _ptr(cat[l][..., Cl:]),
-                  2 * Cl, B, Hl // 2, Wl // 2, 2 * Cl, Cl, st)
+        if (2 * hi, 2 * wi) == (Hl, Wl):
+            _lib.call("unetca_convT2x2_fwd", dt, _ptr(h), h.stride(2), _ptr(wf), _ptr(up.bias), _ptr(cat[l][..., Cl:]),
+                      2 * Cl, B, hi, wi, 2 * Cl, Cl, st)
+        else:
+            # resize guard (UCA:138-157): the transposed conv gives 2*floor(H/2) rows / columns, the skip has H
+            u = torch.empty(B, 2 * hi, 2 * wi, Cl, dtype=tdt, device=dev)
+            _lib.call("unetca_convT2x2_fwd", dt, _ptr(h), h.stride(2), _ptr(wf), _ptr(up.bias), _ptr(u), Cl, B, hi, wi,
+                      2 * Cl, Cl, st)
+            _lib.call("unetca_resize_bilinear_fwd", dt, _ptr(u), Cl, 2 * hi, 2 * wi, _ptr(cat[l][..., Cl:]), 2 * Cl, Hl, Wl,
+                      B, Cl, st)
         sv.up_in.append(h if keep else None)
         out = torch.empty(B, Hl, Wl, Cl, dtype=tdt, device=dev)
         s = _double_conv_fwd(eng, blk, cat[l], None, B, Hl, Wl, out, None, None, train, dt, tdt, keep)
@@ -468,28 +486,32 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
     for l in range(4):
         i = 3 - l
         up, name = model._ups[i], model._up_names[i]
-        Hl, Wl, Cl = H >> l, W >> l, _WIDTHS[l]
+        Hl, Wl, Cl = sv.Hs[l], sv.Ws[l], _WIDTHS[l]
+        hi, wi = sv.Hs[l + 1], sv.Ws[l + 1]
         dcat = _double_conv_bwd(eng, sv.dec[i], dcur, G, dt, tdt, True)          # (B,Hl,Wl,2Cl)
-        du = dcat[..., Cl:]
+        du, ldu = dcat[..., Cl:], 2 * Cl
         skip_grads[l] = dcat[..., :Cl]
+        if (2 * hi, 2 * wi) != (Hl, Wl):                                         # adjoint of the resize guard
+            du_s = torch.empty(B, 2 * hi, 2 * wi, Cl, dtype=tdt, device=dev)
+            _lib.call("unetca_resize_bilinear_bwd", dt, _ptr(du), ldu, Hl, Wl, _ptr(du_s), Cl, 2 * hi, 2 * wi, B, Cl, st)
+            du, ldu = du_s, Cl
         dbias = G.alloc(name + ".bias", up.bias)
-        _lib.call("unetca_chan_sum", dt, _ptr(du), 2 * Cl, Cl, B * Hl * Wl, _ptr(parts), _ptr(dbias), st)
+        _lib.call("unetca_chan_sum", dt, _ptr(du), ldu, Cl, B * 4 * hi * wi, _ptr(parts), _ptr(dbias), st)
         G.put(name + ".bias")
         up_in = sv.up_in[i]
         dwu = G.alloc(name + ".weight", up.weight)
-        _lib.call("unetca_convT2x2_wgrad", dt, _ptr(up_in), up_in.stride(2), _ptr(du), 2 * Cl, _ptr(ws), ws.numel(), B,
-                  Hl // 2, Wl // 2, 2 * Cl, Cl, _ptr(dwu), st)
+        _lib.call("unetca_convT2x2_wgrad", dt, _ptr(up_in), up_in.stride(2), _ptr(du), ldu, _ptr(ws), ws.numel(), B,
+                  hi, wi, 2 * Cl, Cl, _ptr(dwu), st)
         G.put(name + ".weight")
         _, wd = eng.convT_w(up, dt, tdt)
-        dcur = torch.empty(B, Hl // 2, Wl // 2, 2 * Cl, dtype=tdt, device=dev)
-        _lib.call("unetca_convT2x2_dgrad", dt, _ptr(du), 2 * Cl, _ptr(wd), _ptr(dcur), 2 * Cl, B, Hl // 2, Wl // 2, 2 * Cl,
-                  Cl, st)
+        dcur = torch.empty(B, hi, wi, 2 * Cl, dtype=tdt, device=dev)
+        _lib.call("unetca_convT2x2_dgrad", dt, _ptr(du), ldu, _ptr(wd), _ptr(dcur), 2 * Cl, B, hi, wi, 2 * Cl, Cl, st)
     # ---- encoder, deep to shallow
     for l in range(4, -1, -1):
         dpooled = _double_conv_bwd(eng, sv.enc[l], dcur, G, dt, tdt, l > 0)
         if l == 0:
             break
-        Hp, Wp, Cp = H >> (l - 1), W >> (l - 1), _WIDTHS[l - 1]
+        Hp, Wp, Cp = sv.Hs[l - 1], sv.Ws[l - 1], _WIDTHS[l - 1]
         dcur = torch.empty(B, Hp, Wp, Cp, dtype=tdt, device=dev)
         sg = skip_grads[l - 1]
         _lib.call("unetca_pool_bwd_add", dt, _ptr(sg), sg.stride(2), _ptr(dpooled), Cp, _ptr(sv.pos[l - 1]), _ptr(dcur),

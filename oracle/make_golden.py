@@ -90,6 +90,8 @@ def main():
     run_case(ref, "unetca_se_b2_32", seed=0, B=2, H=32, W=32, use_se=True, full=True)
     run_case(ref, "unet_plain_b2_32", seed=1, B=2, H=32, W=48, use_se=False, full=True)
     run_case(ref, "unetca_se_b4_256", seed=0, B=4, H=256, W=256, use_se=True, full=False)   # BASELINE configs[0]
+    # H, W not multiples of 16: floor max-pools (5 -> 2, 13 -> 6) and the bilinear resize guard of UCA:138-157
+    run_case(ref, "unetca_se_b2_40x52", seed=3, B=2, H=40, W=52, use_se=True, full=True)
 
 
 if __name__ == "__main__":

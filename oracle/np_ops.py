@@ -204,6 +204,39 @@ def convT2x2_bwd(x, w, dy):
 # CrossEntropyLoss(ignore_index=255), reduction='mean'                         UCA:465, 344
 # ----------------------------------------------------------------------------------------------
 
+def bilinear_taps(n_in, n_out):
+    """(i0, i1, lam) per output index of a 1-D bilinear resize, align_corners=False (the resize guard, UCA:138-157).
+    torchvision's F_T.resize(antialias=True) only up-samples here (2*floor(h/2) -> h), where the antialias filter
+    reduces to these two taps (weights renormalised at the borders == index clamping)."""
+    scale = n_in / n_out
+    src = np.maximum((np.arange(n_out) + 0.5) * scale - 0.5, 0.0)
+    i0 = np.minimum(np.floor(src).astype(np.int64), n_in - 1)
+    i1 = np.minimum(i0 + 1, n_in - 1)
+    return i0, i1, src - i0
+
+
+def resize_bilinear_fwd(x, size):
+    """(B,C,h,w) -> (B,C,H,W)"""
+    h0, h1, lh = bilinear_taps(x.shape[2], size[0])
+    w0, w1, lw = bilinear_taps(x.shape[3], size[1])
+    rows = x[:, :, h0, :] * (1 - lh)[None, None, :, None] + x[:, :, h1, :] * lh[None, None, :, None]
+    return rows[:, :, :, w0] * (1 - lw) + rows[:, :, :, w1] * lw
+
+
+def resize_bilinear_bwd(dy, in_size):
+    """adjoint of resize_bilinear_fwd: (B,C,H,W) -> (B,C,h,w)"""
+    B, C, H, W = dy.shape
+    h0, h1, lh = bilinear_taps(in_size[0], H)
+    w0, w1, lw = bilinear_taps(in_size[1], W)
+    tmp = np.zeros((B, C, H, in_size[1]), dtype=dy.dtype)
+    np.add.at(tmp, (slice(None), slice(None), slice(None), w0), dy * (1 - lw))
+    np.add.at(tmp, (slice(None), slice(None), slice(None), w1), dy * lw)
+    dx = np.zeros((B, C, in_size[0], in_size[1]), dtype=dy.dtype)
+    np.add.at(dx, (slice(None), slice(None), h0, slice(None)), tmp * (1 - lh)[None, None, :, None])
+    np.add.at(dx, (slice(None), slice(None), h1, slice(None)), tmp * lh[None, None, :, None])
+    return dx
+
+
 def cross_entropy_fwd(logits, target, ignore_index=255):
     """-mean_{t != ignore} log_softmax(logits)[t].  All-ignored -> NaN (0/0), like torch."""
     m = logits.max(1, keepdims=True)

@@ -140,8 +140,6 @@ def unet_forward(x, p, bufs=None, use_se=True, train=True, return_aux=False):
     and is updated in place in train mode, exactly like the modules' buffers."""
     if bufs is None:
         bufs = p
-    if x.shape[2] % 16 or x.shape[3] % 16:
-        raise ValueError("port restates the fast path only: H, W must be multiples of 16 (UCA:138-157 not taken)")
     skips, pool_idx = [], []
     h = x
     for li, (name, pre) in enumerate(ENC):
@@ -152,7 +150,12 @@ def unet_forward(x, p, bufs=None, use_se=True, train=True, return_aux=False):
         skips.append(h)
     for di, (up, conv) in enumerate(DEC):
         u = F.conv_transpose2d(h, p[f'{up}.weight'], p[f'{up}.bias'], stride=2)              # UCA:136..155
-        h = torch.cat([skips[3 - di], u], dim=1)                                             # UCA:140..158
+        skip = skips[3 - di]
+        if u.shape[2:] != skip.shape[2:]:
+            # resize guard (UCA:138-139 ...): torchvision F_T.resize(tensor, size, BILINEAR) is
+            # interpolate(mode='bilinear', align_corners=False, antialias=True); only taken when H or W is not in 16*N
+            u = F.interpolate(u, size=skip.shape[2:], mode='bilinear', align_corners=False, antialias=True)
+        h = torch.cat([skip, u], dim=1)                                                      # UCA:140..158
         h = _double_conv(h, p, f'{conv}.double_conv', use_se, train, bufs)
     logits = F.conv2d(h, p['outc.weight'], p['outc.bias'])                                   # UCA:162
     if return_aux:

@@ -41,6 +41,7 @@ def _rel(a, b):
 @pytest.mark.parametrize("name,seed,B,H,W,use_se", [
     ("unetca_se_b2_32", 0, 2, 32, 32, True),
     ("unet_plain_b2_32", 1, 2, 32, 48, False),
+    ("unetca_se_b2_40x52", 3, 2, 40, 52, True),          # floor max-pools (5 -> 2, 13 -> 6) + bilinear resize guard
 ])
 def test_train_step_matches_reference_golden(golden_dir, prec, ltol, gtol, name, seed, B, H, W, use_se):
     g = np.load(os.path.join(golden_dir, name + ".npz"))
@@ -64,16 +65,19 @@ def test_train_step_matches_reference_golden(golden_dir, prec, ltol, gtol, name,
     big = ref_norms > 1e-6 * ref_total          # the 18 pre-BN conv biases have analytically zero gradients
     # per-parameter norms: 1e-2 in fp32 mode; in bf16 the small tensors (BN affine, SE FC) are sums with heavy
     # cancellation of gradients that crossed ~20 bf16-rounded layers and an 8-sample BatchNorm -> only a sanity bound
-    tol_each = 1e-2 if prec == "fp32" else 0.75
+    # The SE FC weight gradients are ill-conditioned (a K = batch sum of terms that are themselves cancelling pixel
+    # sums): on the 40x52 fixture the fp32 reference itself is 0.97 % away from its own fp64 evaluation for
+    # inc...fc.0.weight (oracle port, dtype=float64), so those get 3e-2 in fp32 mode.
+    tol_each = np.array([(3e-2 if ".fc." in n else 1e-2) if prec == "fp32" else 0.75 for n in np.array(names)[big]])
     assert np.all(np.abs(norms[big] - ref_norms[big]) / ref_norms[big] < tol_each), \
-        [(n, a, b) for n, a, b in zip(np.array(names)[big], norms[big], ref_norms[big]) if abs(a - b) / b >= tol_each]
+        [(n, a, b) for n, a, b, t in zip(np.array(names)[big], norms[big], ref_norms[big], tol_each) if abs(a - b) / b >= t]
     assert np.all(norms[~big] < 1e-5 * ref_total)
     for k in g.files:
         if k.startswith("grad:"):
             ref = torch.from_numpy(g[k])
             if ref.abs().max() < 1e-6:
                 continue
-            assert _rel(params[k[5:]].grad.cpu(), ref) < (1e-2 if prec == "fp32" else 0.75), k
+            assert _rel(params[k[5:]].grad.cpu(), ref) < ((3e-2 if ".fc." in k else 1e-2) if prec == "fp32" else 0.75), k
         if k.startswith("buf:"):
             assert _rel(dict(m.named_buffers())[k[4:]].cpu(), torch.from_numpy(g[k])) < (1e-4 if prec == "fp32" else 2e-2), k
     assert int(m.inc.double_conv[1].num_batches_tracked) == 1
@@ -187,8 +191,9 @@ def test_adam_trajectory_100_steps(prec):
 def test_error_behaviour():
     import unetca_b200
     m = unetca_b200.UNet(3, 2, True).cuda()
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(1, 3, 40, 40, device="cuda"))                  # resize guard path (UCA:138-157) not on CUDA path
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(2, 3, 12, 40, device="cuda"))                  # four 2x2 max-pools need H, W >= 16 (UCA:106-109)
+    assert m(torch.zeros(2, 3, 40, 24, device="cuda")).shape == (2, 2, 40, 24)   # resize guard path (UCA:138-157)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 1, 32, 32, device="cuda"))                  # wrong channel count
     with pytest.raises(ValueError):

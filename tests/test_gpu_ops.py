@@ -27,7 +27,7 @@ def _need_gpu(built_lib):
 
 # ------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", DTS)
-@pytest.mark.parametrize("B,C,H,W", [(2, 64, 8, 16), (1, 192, 6, 4), (3, 1024, 2, 2)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 8, 16), (1, 192, 6, 4), (3, 1024, 2, 2), (2, 64, 5, 13), (1, 128, 7, 6)])
 def test_maxpool_bit_exact(dt, B, C, H, W):
     rs = np.random.RandomState(0)
     x = torch.from_numpy(rs.randint(0, 3, (B, C, H, W)).astype(np.float32))      # many exact ties
@@ -51,6 +51,28 @@ def test_maxpool_bit_exact(dt, B, C, H, W):
     call("unetca_pool_bwd_add", dt, ptr(skd), C, ptr(dpd), C, ptr(pos), ptr(dx), C, B, H, W, C, stream())
     ref = rounded(skip, dt) + F.max_unpool2d(rounded(dpool, dt), ridx, 2, output_size=(H, W))
     assert relerr(from_nhwc(dx), ref) < TOL[dt]
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("B,C,h,w,H,W", [(2, 64, 4, 6, 5, 6), (1, 128, 10, 12, 10, 13), (2, 64, 24, 12, 25, 13)])
+def test_resize_guard_bilinear(dt, B, C, h, w, H, W):
+    """Decoder resize guard (UCA:138-157): F_T.resize(tensor, BILINEAR) == interpolate(antialias=True), and its adjoint."""
+    rs = np.random.RandomState(9)
+    x = torch.from_numpy(rs.standard_normal((B, C, h, w)).astype(np.float32))
+    xr = rounded(x, dt).requires_grad_(True)
+    ref = F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=False, antialias=True)
+    dy = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    ref.backward(rounded(dy, dt))
+    xd = to_nhwc(x, dt)
+    cat = torch.zeros(B, H, W, 2 * C, dtype=TDT[dt], device="cuda")             # written into the upper channel half
+    call("unetca_resize_bilinear_fwd", dt, ptr(xd), C, h, w, ptr(cat[..., C:]), 2 * C, H, W, B, C, stream())
+    assert relerr(from_nhwc(cat[..., C:]), ref.detach()) < TOL[dt]
+    assert cat[..., :C].abs().max().item() == 0
+    dcat = torch.zeros(B, H, W, 2 * C, dtype=TDT[dt], device="cuda")
+    dcat[..., C:] = to_nhwc(dy, dt)
+    dx = torch.empty(B, h, w, C, dtype=TDT[dt], device="cuda")
+    call("unetca_resize_bilinear_bwd", dt, ptr(dcat[..., C:]), 2 * C, H, W, ptr(dx), C, h, w, B, C, stream())
+    assert relerr(from_nhwc(dx), xr.grad) < TOL[dt]
 
 
 @pytest.mark.parametrize("dt", DTS)

@@ -17,6 +17,7 @@ def _load(golden_dir, name):
 @pytest.mark.parametrize("name,seed,B,H,W,use_se", [
     ("unetca_se_b2_32", 0, 2, 32, 32, True),
     ("unet_plain_b2_32", 1, 2, 32, 48, False),
+    ("unetca_se_b2_40x52", 3, 2, 40, 52, True),                     # floor max-pools + bilinear resize guard (UCA:138-157)
 ])
 def test_port_matches_reference_golden(golden_dir, name, seed, B, H, W, use_se):
     g = _load(golden_dir, name)
@@ -59,6 +60,21 @@ def test_port_matches_reference_configs0(golden_dir):
     assert abs(loss.item() - float(g["loss"])) < 1e-6
     mask = torch.max(logits, 1)[1].numpy().astype(np.uint8)
     assert np.array_equal(np.packbits(mask), g["argmax_packed"])
+
+
+@pytest.mark.parametrize("n_in,n_out", [(4, 5), (12, 13), (24, 25), (6, 6), (2, 3)])
+def test_resize_guard_restatement(n_in, n_out):
+    """The numpy restatement of the resize guard (two-tap bilinear, align_corners=False) == what torchvision's
+    F_T.resize(tensor, BILINEAR) computes at UCA:138-157 (interpolate(..., antialias=True)), forward and adjoint."""
+    rs = np.random.RandomState(n_in)
+    x = rs.standard_normal((2, 3, n_in, 2 * n_in)).astype(np.float64)
+    size = (n_out, 2 * n_in + 1)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    ref = torch.nn.functional.interpolate(xt, size=size, mode="bilinear", align_corners=False, antialias=True)
+    np.testing.assert_allclose(np_ops.resize_bilinear_fwd(x, size), ref.detach().numpy(), rtol=1e-12, atol=1e-12)
+    dy = rs.standard_normal(ref.shape)
+    ref.backward(torch.from_numpy(dy))
+    np.testing.assert_allclose(np_ops.resize_bilinear_bwd(dy, x.shape[2:]), xt.grad.numpy(), rtol=1e-12, atol=1e-12)
 
 
 def test_numpy_restatement_matches_port():

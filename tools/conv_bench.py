@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-halo", action="store_true", help="narrow layers through the generic one-box-per-tap kernel")
+    ap.add_argument("--convT", action="store_true", help="benchmark the four ConvTranspose2d(k2,s2) layers instead")
     ap.add_argument("--no-pixn", action="store_true", help="narrow layers through the pixels-on-M generic kernel")
     ap.add_argument("--dgrad", action="store_true", help="add the dgrad shapes (O -> C) of the narrow layers")
     a = ap.parse_args()
@@ -38,6 +39,43 @@ def main():
     ws = torch.empty(48 << 20, device="cuda")
     parts = torch.empty(lib.unetca_max_parts(B) * 2048, device="cuda")
     n = ctypes.c_int(0)
+    if a.convT:
+        for Cin, h in ((1024, 32), (512, 64), (256, 128), (128, 256)):
+            Cout = Cin // 2
+            x = torch.randn(B, h, h, Cin, device="cuda").bfloat16()
+            cat = torch.empty(B, 2 * h, 2 * h, 2 * Cout, device="cuda", dtype=torch.bfloat16)
+            dcat = torch.randn(B, 2 * h, 2 * h, 2 * Cout, device="cuda").bfloat16()
+            wf = (torch.randn(4 * Cout, Cin, device="cuda") / Cin ** 0.5).bfloat16()
+            wd = (torch.randn(Cin, 4 * Cout, device="cuda") / Cin ** 0.5).bfloat16()
+            bias = torch.randn(Cout, device="cuda")
+            dx = torch.empty_like(x)
+            dw = torch.empty(Cin, Cout, 2, 2, device="cuda")
+            fl = 2.0 * B * h * h * Cin * 4 * Cout
+            up, dup = cat[..., Cout:], dcat[..., Cout:]
+            fns = {
+                "fwd": lambda: _lib.call("unetca_convT2x2_fwd", 1, x.data_ptr(), Cin, wf.data_ptr(), bias.data_ptr(), up.data_ptr(),
+                                         2 * Cout, B, h, h, Cin, Cout, st),
+                "dgrad": lambda: _lib.call("unetca_convT2x2_dgrad", 1, dup.data_ptr(), 2 * Cout, wd.data_ptr(), dx.data_ptr(), Cin, B,
+                                           h, h, Cin, Cout, st),
+                "wgrad": lambda: _lib.call("unetca_convT2x2_wgrad", 1, x.data_ptr(), Cin, dup.data_ptr(), 2 * Cout, ws.data_ptr(),
+                                           ws.numel(), B, h, h, Cin, Cout, dw.data_ptr(), st),
+            }
+            res = []
+            for what, fn in fns.items():
+                for _ in range(3):
+                    fn()
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                s.record()
+                for _ in range(a.iters):
+                    fn()
+                e.record()
+                torch.cuda.synchronize()
+                ms = s.elapsed_time(e) / a.iters
+                res.append(f"{what} {ms:7.3f} ms {fl / ms / 1e9:7.1f} TFLOP/s")
+            print(f"convT {Cin:4d}->{Cout:4d} @{h:3d}->{2 * h:3d} B={B}: " + " | ".join(res), flush=True)
+            del x, cat, dcat
+        return
     for C, O, S in layers:
         x = torch.randn(B, S, S, C, device="cuda").bfloat16()
         dy = torch.randn(B, S, S, O, device="cuda").bfloat16()
