@@ -23,8 +23,9 @@ class TileSpec:
     halo: int = 128           # context on each side; the conv stack's receptive field is 200 px -> halo >= 100
 
     def __post_init__(self):
-        if self.core <= 0 or self.halo < 0 or (self.core + 2 * self.halo) % 16:
-            raise ValueError("core + 2*halo must be a positive multiple of 16 (four 2x2 poolings)")
+        if self.core <= 0 or self.halo < 0 or self.core + 2 * self.halo < 16:
+            raise ValueError("core + 2*halo must be at least 16 (four 2x2 poolings); multiples of 16 avoid the "
+                             "decoder's resize guard (UCA:138-157) and are the fast path")
 
     @property
     def size(self) -> int:

@@ -40,4 +40,7 @@ def test_extract_zero_fills_outside():
 def test_tilespec_validation():
     from unetca_b200 import tiling
     with pytest.raises(ValueError):
-        tiling.TileSpec(core=30, halo=8)
+        tiling.TileSpec(core=8, halo=2)                       # 12 < 16: four 2x2 poolings impossible
+    with pytest.raises(ValueError):
+        tiling.TileSpec(core=0, halo=8)
+    assert tiling.TileSpec(core=30, halo=8).size == 46        # not a multiple of 16: allowed (resize guard path)
