@@ -368,6 +368,11 @@ def main():
     # ---- rooflines -------------------------------------------------------------------------------------------
     pk = peaks()
     table = acct.summary()
+    # DRAM traffic per launch (dram__bytes_read + dram__bytes_write) from the committed ncu capture of this command
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp) and B == 64 and S == 512 and args.precision == "bf16":
+        traffic = json.load(open(tp))
     tms = sum(d["ms"] for d in table.values() if d["class"] == "tensor")
     tfl = sum(d["flops"] for d in table.values() if d["class"] == "tensor")
     hms = sum(d["ms"] for d in table.values() if d["class"] == "hbm")
@@ -377,12 +382,15 @@ def main():
     ach_t = tfl / (tms * 1e-3) / 1e12 if tms else 0.0
     ach_h = hby / (hms * 1e-3) / 1e9 if hms else 0.0
     roof = {"bound": "tensor", "achieved": ach_t, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-            "frac": ach_t / pk["tflops_sustained"], "traffic": None,
+            "frac": ach_t / pk["tflops_sustained"], "traffic": traffic.get("tensor", {}).get("dram_bytes_per_launch"),
+            "algorithmic_bytes_note": "tensor-bound: compulsory activation I/O only; see profiles/r1h_ncu_step_kernels.txt",
             "kernel": "tc_kernel<BLOCK_N,WGRAD> (tcgen05 implicit-GEMM conv3x3 fwd/dgrad/wgrad, ConvTranspose2d)",
             "launches": ncalls_t, "avg_launch_ms": tms / max(ncalls_t, 1), "share_of_step": tms / ms,
             "flops_per_launch_avg": tfl / max(ncalls_t, 1), "peak_source": pk["source"] + " bf16_tflops_sustained"}
     roof_h = {"bound": "hbm", "achieved": ach_h, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_h / pk["hbm_gbs"],
-              "traffic": None, "kernel": "BN/ReLU/SE/max-pool/outc/CE elementwise and reduction kernels (aggregate)",
+              "traffic": traffic.get("hbm", {}).get("dram_bytes_per_launch"),
+              "algorithmic_bytes_per_launch": hby / max(ncalls_h, 1),
+              "kernel": "BN/ReLU/SE/max-pool/outc/CE elementwise and reduction kernels (aggregate)",
               "launches": ncalls_h, "share_of_step": hms / ms, "peak_source": pk["source"] + " hbm_gbs"}
     if args.kernel_table and rank == 0:
         with open(args.kernel_table, "w") as f:
