@@ -43,6 +43,7 @@ void unetca_tc_force_block_n(int n);
 void unetca_tc_force_wgrad_narrow(int on);
 void unetca_tc_force_no_halo(int on);
 void unetca_tc_force_no_pixn(int on);
+void unetca_tc_set_pixn_cluster(int n);
 
 /* ---- module boundary: layout and parameter packing ------------------------------------------------------ */
 /* network input (B,Cin,H,W) NCHW fp32 (UCA:343 `model(images)`) -> im2col rows [B*H*W][Kpad], k = tap*Cin + c */

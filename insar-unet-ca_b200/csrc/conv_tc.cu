@@ -676,190 +676,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide_kernel(const _
 
 
 // ---------------------------------------------------------------------------------------------------------
-// conv3x3 forward / dgrad with tap reuse from ONE haloed activation tile (narrow outputs, N = 64 or 128).
-//   out[p][n] = sum_{tap,c} X[p + s(tap)][c] * Wk[n][tap*C + c]
-// The generic kernel above loads one [128 px][64 c] box per tap: 9 x 16 KB of L2->shared traffic per 64-channel
-// chunk plus the weights.  With narrow N the MMAs are short (N/2 cycles each) and that fill rate (>128 B/cycle/SM)
-// is what bounds it.  Here the output tile is 8 wide x 16 high, its 10 x 18 haloed input tile (23 KB) is loaded
-// ONCE per chunk, and the nine taps are K-major A descriptors into that one tile: start address shifted by
-// (kh*10 + kw) pixel rows of 128 B, stride between 8-pixel groups SBO = 10 rows = 1280 B (legal because the
-// SWIZZLE_128B XOR is a function of the absolute shared-memory address; tools/umma_shift_probe.cu mode 0,
-// sbo=1280).  Weights stream through their own ring, one [BLOCK_N][64] box per tap; when the whole filter of the
-// layer fits the ring (C = 64, N = BLOCK_N = 64) it is loaded once and stays resident.
-// Warps: 0 = X producer, 1 = MMA issuer, 2..5 = epilogue, 6 = weight producer.
-// ---------------------------------------------------------------------------------------------------------
-struct alignas(64) HaloParams {
-    CUtensorMap mapX, mapW, mapOut;
-    int tilesW, tilesH, nimg, H, W;
-    int cchunks, num_n_blocks;
-    int w_resident;
-    float* stat_parts;
-    int N;
-};
-constexpr int kHaloThreads = 224;
-constexpr int kHTW = 8, kHTH = 16, kHPitch = kHTW + 2;
-constexpr int kHXBox = kHPitch * (kHTH + 2) * 128;     // 23040 bytes written by TMA
-constexpr int kHXBytes = 23 * 1024;                    // ring slot (1024-byte aligned)
-
-template <int BLOCK_N> struct HaloCfg {
-    static constexpr int XS = BLOCK_N == 64 ? 4 : 3;
-    static constexpr int WS = BLOCK_N == 64 ? 9 : 6;
-    static constexpr int W_BYTES = BLOCK_N * 128;
-    static constexpr int OUT_BYTES = (BLOCK_N / 64) * kBoxBytesFwd;
-    static constexpr int STAT_BYTES = 2 * 1024 * 4 + BLOCK_N * 4 + 8 * BLOCK_N * 4;
-    static constexpr int SMEM_BYTES = 1024 + XS * kHXBytes + WS * W_BYTES + OUT_BYTES + STAT_BYTES + 256;
-    static_assert(SMEM_BYTES <= 227 * 1024, "halo conv: shared memory budget");
-};
-
-template <int BLOCK_N>
-__global__ void __launch_bounds__(kHaloThreads, 1) tc_conv3x3_halo_kernel(const __grid_constant__ HaloParams p) {
-    using Cfg = HaloCfg<BLOCK_N>;
-    constexpr int XS = Cfg::XS, WS = Cfg::WS;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* x_ring = smem;
-    uint8_t* w_ring = smem + XS * kHXBytes;
-    uint8_t* out_stage = w_ring + WS * Cfg::W_BYTES;
-    float* sm_stats = reinterpret_cast<float*>(out_stage + Cfg::OUT_BYTES);
-    float* sm_bias = sm_stats + 2048;
-    float* sm_wpart = sm_bias + BLOCK_N;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + Cfg::OUT_BYTES + Cfg::STAT_BYTES);
-    uint64_t* xfull = bars;                    // [XS]
-    uint64_t* xempty = bars + XS;              // [XS]
-    uint64_t* wfull = bars + 2 * XS;           // [WS]
-    uint64_t* wempty = bars + 2 * XS + WS;     // [WS]
-    uint64_t* tfull_bar = bars + 2 * XS + 2 * WS;       // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;               // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    static_assert((2 * XS + 2 * WS + 4) * 8 + 4 <= 256, "halo conv: barrier area");
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
-        for (int i = 0; i < WS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
-        fence_barrier_init();
-        prefetch_tmap(&p.mapX);
-        prefetch_tmap(&p.mapW);
-        prefetch_tmap(&p.mapOut);
-    }
-    if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_slot);
-    if (p.stat_parts) {
-        for (int i = threadIdx.x; i < 2 * p.N; i += kHaloThreads) sm_stats[i] = 0.f;
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int tiles_per_img = p.tilesW * p.tilesH;
-    const long num_work = (long)tiles_per_img * p.nimg * p.num_n_blocks;
-
-    if (warp == 0) {
-        // ================================ X producer: one haloed tile per (work item, chunk) ================
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
-                const int mt = (int)(t / p.num_n_blocks);
-                const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
-                for (int cc = 0; cc < p.cchunks; ++cc) {
-                    mbar_wait(&xempty[s], ph ^ 1);
-                    mbar_expect_tx(&xfull[s], kHXBox);
-                    tma_load_4d(&p.mapX, &xfull[s], x_ring + s * kHXBytes, cc * 64, tw * kHTW - 1, th * kHTH - 1, b);
-                    if (++s == XS) { s = 0; ph ^= 1; }
-                }
-            }
-        }
-    } else if (warp == 6) {
-        // ================================ weight producer: one [BLOCK_N][64] box per (chunk, tap) ===========
-        if (lane == 0) {
-            int s = 0; uint32_t ph = 0;
-            bool loaded = false;
-            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
-                if (p.w_resident && loaded) break;
-                const int nb = (int)(t % p.num_n_blocks);
-                for (int cc = 0; cc < p.cchunks; ++cc) {
-                    for (int tap = 0; tap < 9; ++tap) {
-                        mbar_wait(&wempty[s], ph ^ 1);
-                        mbar_expect_tx(&wfull[s], Cfg::W_BYTES);
-                        tma_load_4d(&p.mapW, &wfull[s], w_ring + s * Cfg::W_BYTES, (tap * p.cchunks + cc) * 64,
-                                    nb * BLOCK_N, 0, 0);
-                        if (++s == WS) { s = 0; ph ^= 1; }
-                    }
-                }
-                loaded = true;
-            }
-        }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 0, 0);
-            int xs = 0; uint32_t xph = 0;
-            int ws = 0; uint32_t wph = 0;
-            int as = 0; uint32_t aph = 0;
-            bool first = true;
-            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
-                mbar_wait(&tempty_bar[as], aph ^ 1);
-                tcgen05_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-                for (int cc = 0; cc < p.cchunks; ++cc) {
-                    mbar_wait(&xfull[xs], xph);
-                    const uint32_t xa = smem_u32(x_ring + xs * kHXBytes);
-#pragma unroll 1
-                    for (int tap = 0; tap < 9; ++tap) {
-                        if (!p.w_resident || first) mbar_wait(&wfull[ws], wph);
-                        tcgen05_fence_after();
-                        const uint32_t sa = xa + ((tap / 3) * kHPitch + (tap % 3)) * 128;
-                        const uint32_t sb = smem_u32(w_ring + ws * Cfg::W_BYTES);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16, kHPitch * 128),
-                                      make_smem_desc(sb + k * 32, 16, 1024), idesc, (cc | tap | k) != 0);
-                        if (!p.w_resident) umma_commit(&wempty[ws]);
-                        if (++ws == WS) { ws = 0; wph ^= 1; }
-                    }
-                    umma_commit(&xempty[xs]);
-                    if (++xs == XS) { xs = 0; xph ^= 1; }
-                }
-                first = false;
-                umma_commit(&tfull_bar[as]);
-                as ^= 1; if (as == 0) aph ^= 1;
-            }
-        }
-    } else {
-        // ================================ epilogue (warps 2..5) ================================
-        const int q = warp & 3;
-        const int r = q * 32 + lane;
-        const int ep_tid = threadIdx.x - 64;
-        int as = 0; uint32_t aph = 0;
-        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
-            mbar_wait(&tfull_bar[as], aph);
-            tcgen05_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BLOCK_N;
-            const int nb = (int)(t % p.num_n_blocks);
-            const int mt = (int)(t / p.num_n_blocks);
-            const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
-            const int w0 = tw * kHTW, h0 = th * kHTH;
-            const bool valid = (h0 + r / kHTW) < p.H && (w0 + r % kHTW) < p.W;
-            fwd_epilogue_tile<BLOCK_N>(t_addr, out_stage, sm_bias, sm_wpart, sm_stats, &p.mapOut, nb * BLOCK_N, w0, h0, b, nb,
-                                       valid, nullptr, 1, p.stat_parts != nullptr, p.N, &tempty_bar[as], r, lane, ep_tid);
-            as ^= 1; if (as == 0) aph ^= 1;
-        }
-        if (ep_tid == 0) tma_store_wait_all();
-        named_bar_sync(1, 128);
-        if (p.stat_parts) {
-            float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
-            for (int i = ep_tid; i < 2 * p.N; i += 128) dst[i] = sm_stats[i];
-        }
-    }
-    tcgen05_fence_before();
-    __syncthreads();
-    tcgen05_fence_after();
-    if (warp == 1) tmem_dealloc<2 * BLOCK_N>(tmem_base);
-}
-
-
-// ---------------------------------------------------------------------------------------------------------
 // conv3x3 forward / dgrad for NARROW outputs (64 or 128 channels), pixels on the N side of the MMA.
 // Measured on B200 (tools/umma_rate_probe.cu): one tcgen05.mma M=128,K=16 with operands in shared memory never
 // takes less than ~100 cycles (A-operand fetch), whatever N is; it only reaches the tensor peak for N >= 192.
@@ -926,6 +742,11 @@ __device__ __forceinline__ void pixn_drain(uint32_t t_addr, uint32_t my_s, float
     s1 = a1 + b1; s2 = a2 + b2;
 }
 
+// CL = 2: launched as clusters of two CTAs that walk the same (m-block, tap, chunk) sequence on neighbouring pixel
+// tiles; each CTA fetches HALF of every weight tile and TMA-multicasts it into both shared memories, so the L2->SM
+// traffic of the weight operand halves (this kernel is fill-bound: 48 KB per 512 MMA cycles without it).  A stage may
+// only be refilled when BOTH CTAs' MMAs have drained it: the MMA commits are multicast to both empty barriers.
+template <int CL>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __grid_constant__ PixNParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -941,7 +762,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kPnStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < kPnStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
         fence_barrier_init();
         prefetch_tmap(&p.mapX);
@@ -954,27 +775,38 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
     }
     tcgen05_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();              // the peer's barriers are initialised before anything is multicast
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // work: item u = (m-block, group of CL neighbouring pixel tiles); this CTA takes tile CL*group + rank.  A tile index
+    // past the end is a phantom: its loads are zero-filled (batch coordinate out of range), its stores clipped.
     const int tiles_per_img = p.tilesW * p.tilesI;
-    const long num_work = (long)tiles_per_img * p.nimg * p.num_m_blocks;
+    const long num_tiles = (long)tiles_per_img * p.nimg;
+    const long num_work = ((num_tiles + CL - 1) / CL) * p.num_m_blocks;
     const int nk = p.ntaps * p.cchunks;
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const long first = blockIdx.x / CL, stride = gridDim.x / CL;
+    constexpr uint16_t kAll = (uint16_t)((1u << CL) - 1);
 
     if (warp == 0) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            for (long t = first; t < num_work; t += stride) {
                 const int mb = (int)(t % p.num_m_blocks);
-                const int mt = (int)(t / p.num_m_blocks);
-                const int tw = mt % p.tilesW, ti = (mt / p.tilesW) % p.tilesI, b = mt / tiles_per_img;
+                const long mt = (t / p.num_m_blocks) * CL + crank;
+                const int tw = (int)(mt % p.tilesW), ti = (int)((mt / p.tilesW) % p.tilesI), b = (int)(mt / tiles_per_img);
                 const int x0 = tw * p.TW, i0 = ti * p.TI;
                 for (int tap = 0; tap < p.ntaps; ++tap) {
                     for (int cc = 0; cc < p.cchunks; ++cc) {
                         mbar_wait(&empty_bar[s], ph ^ 1);
                         uint8_t* sa = smem + s * kPnStageBytes;
                         mbar_expect_tx(&full_bar[s], kPnStageBytes);
-                        tma_load_4d(&p.mapW, &full_bar[s], sa, (tap * p.cchunks + cc) * 64, mb * 128, 0, 0);
+                        if (CL == 1)
+                            tma_load_4d(&p.mapW, &full_bar[s], sa, (tap * p.cchunks + cc) * 64, mb * 128, 0, 0);
+                        else
+                            tma_load_4d_mc(&p.mapW, &full_bar[s], sa + crank * (kPnABytes / CL), (tap * p.cchunks + cc) * 64,
+                                           mb * 128 + crank * (128 / CL), 0, 0, kAll);
                         tma_load_5d(&p.mapX, &full_bar[s], sa + kPnABytes, cc * 64, x0 + p.dw[tap], p.par[tap],
                                     i0 + p.off[tap], b);
                         if (++s == kPnStages) { s = 0; ph ^= 1; }
@@ -987,7 +819,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
             constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
             int s = 0; uint32_t ph = 0;
             int as = 0; uint32_t aph = 0;
-            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            for (long t = first; t < num_work; t += stride) {
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tcgen05_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 256;
@@ -1000,7 +832,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc,
                                   (kb | k) != 0);
-                    umma_commit(&empty_bar[s]);
+                    if (CL == 1) umma_commit(&empty_bar[s]);
+                    else umma_commit_mc(&empty_bar[s], kAll);
                     if (++s == kPnStages) { s = 0; ph ^= 1; }
                 }
                 umma_commit(&tfull_bar[as]);
@@ -1014,10 +847,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
         const int box = r >> 6, oc = r & 63;
         uint8_t* my = out_stage + box * (256 * 128) + oc * 2;
         int as = 0; uint32_t aph = 0;
-        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+        for (long t = first; t < num_work; t += stride) {
             const int mb = (int)(t % p.num_m_blocks);
-            const int mt = (int)(t / p.num_m_blocks);
-            const int tw = mt % p.tilesW, ti = (mt / p.tilesW) % p.tilesI, b = mt / tiles_per_img;
+            const long mt = (t / p.num_m_blocks) * CL + crank;
+            const int tw = (int)(mt % p.tilesW), ti = (int)((mt / p.tilesW) % p.tilesI), b = (int)(mt / tiles_per_img);
             const int x0 = tw * p.TW, i0 = ti * p.TI;
             const bool full = (x0 + p.TW <= p.W) && (i0 + p.TI <= p.HP);
             mbar_wait(&tfull_bar[as], aph);
@@ -1056,6 +889,188 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
                         sm_stats[p.N + mb * 64 + r] += sm_wpart[128 + r] + sm_wpart[192 + r];
                     }
                 }
+            }
+            as ^= 1; if (as == 0) aph ^= 1;
+        }
+        if (ep_tid == 0) tma_store_wait_all();
+        named_bar_sync(1, 128);
+        if (p.stat_parts) {
+            float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
+            for (int i = ep_tid; i < 2 * p.N; i += 128) dst[i] = sm_stats[i];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (CL > 1) cluster_sync_all();              // the peer may still multicast into / arrive on this CTA's shared memory
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv3x3 forward / dgrad, pixels on N (as above, 128 output channels per m-block) WITH tap reuse from one haloed
+// activation tile.  Why: a 128x256x16 MMA reads 12 KB of operands from shared memory in 128 cycles (96 B/cycle);
+// the one-box-per-tap kernels additionally WRITE 48 KB per 512 cycles of TMA fill into the same shared memory
+// (94 B/cycle), and the two together exceed what the SM's shared memory sustains — every such kernel here, and
+// cuBLAS's single-CTA tiles, level off near 70 % of the MMA rate.  Here the pixel tile is 8 wide x 32 high, its
+// 10 x 34 haloed input tile (43.5 KB per 64-channel chunk) is loaded ONCE, and the nine taps are K-major B
+// descriptors into it (start shifted by (kh*10 + kw) pixel rows, SBO = 10 rows = 1280 B; the swizzle is a function
+// of the absolute address, tools/umma_shift_probe.cu).  Fill drops from 432 KB to 188 KB per chunk (41 B/cycle).
+// Warps: 0 = activation producer, 1 = MMA issuer, 2..5 = epilogue (shared with the kernel above), 6 = weight producer.
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) HpixParams {
+    CUtensorMap mapX, mapW, mapOut;
+    int tilesW, tilesH, nimg, H, W;
+    int cchunks, num_m_blocks;
+    float* stat_parts;
+    int N;
+};
+constexpr int kHpThreads = 224;
+constexpr int kHpTW = 8, kHpTH = 32, kHpPitch = kHpTW + 2;
+constexpr int kHpXBox = kHpPitch * (kHpTH + 2) * 128;      // 43520 bytes written by TMA
+constexpr int kHpXBytes = 44 * 1024;                       // ring slot
+constexpr int kHpXS = 2, kHpWS = 4;
+constexpr int kHpWBytes = 128 * 128;
+constexpr int kHpSmemBytes = 1024 + kHpXS * kHpXBytes + kHpWS * kHpWBytes + kPnOutBytes + kPnStatBytes + 256;
+static_assert(kHpSmemBytes <= 227 * 1024, "hpix conv: shared memory budget");
+
+__global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __grid_constant__ HpixParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* x_ring = smem;
+    uint8_t* w_ring = smem + kHpXS * kHpXBytes;
+    uint8_t* out_stage = w_ring + kHpWS * kHpWBytes;
+    float* sm_stats = reinterpret_cast<float*>(out_stage + kPnOutBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kPnOutBytes + kPnStatBytes);
+    uint64_t* xfull = bars;
+    uint64_t* xempty = bars + kHpXS;
+    uint64_t* wfull = bars + 2 * kHpXS;
+    uint64_t* wempty = wfull + kHpWS;
+    uint64_t* tfull_bar = wempty + kHpWS;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kHpXS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+        for (int i = 0; i < kHpWS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapW);
+        prefetch_tmap(&p.mapOut);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (p.stat_parts) {
+        for (int i = threadIdx.x; i < 2 * p.N; i += kHpThreads) sm_stats[i] = 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const long num_work = (long)tiles_per_img * p.nimg * p.num_m_blocks;
+
+    if (warp == 0) {
+        // ================================ activation producer: one haloed tile per (item, chunk) ==============
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int mt = (int)(t / p.num_m_blocks);
+                const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    mbar_wait(&xempty[s], ph ^ 1);
+                    mbar_expect_tx(&xfull[s], kHpXBox);
+                    tma_load_4d(&p.mapX, &xfull[s], x_ring + s * kHpXBytes, cc * 64, tw * kHpTW - 1, th * kHpTH - 1, b);
+                    if (++s == kHpXS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 6) {
+        // ================================ weight producer: one [128 rows][64] box per (chunk, tap) ============
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int mb = (int)(t % p.num_m_blocks);
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&wempty[s], ph ^ 1);
+                        mbar_expect_tx(&wfull[s], kHpWBytes);
+                        tma_load_4d(&p.mapW, &wfull[s], w_ring + s * kHpWBytes, (tap * p.cchunks + cc) * 64, mb * 128, 0, 0);
+                        if (++s == kHpWS) { s = 0; ph ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+            int xs = 0; uint32_t xph = 0;
+            int ws = 0; uint32_t wph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    mbar_wait(&xfull[xs], xph);
+                    const uint32_t xa = smem_u32(x_ring + xs * kHpXBytes);
+#pragma unroll 1
+                    for (int tap = 0; tap < 9; ++tap) {
+                        mbar_wait(&wfull[ws], wph);
+                        tcgen05_fence_after();
+                        const uint32_t sa = smem_u32(w_ring + ws * kHpWBytes);
+                        const uint32_t sb = xa + ((tap / 3) * kHpPitch + (tap % 3)) * 128;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16, 1024),
+                                      make_smem_desc(sb + k * 32, 16, kHpPitch * 128), idesc, (cc | tap | k) != 0);
+                        umma_commit(&wempty[ws]);
+                        if (++ws == kHpWS) { ws = 0; wph ^= 1; }
+                    }
+                    umma_commit(&xempty[xs]);
+                    if (++xs == kHpXS) { xs = 0; xph ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+                as ^= 1; if (as == 0) aph ^= 1;
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 2..5): lane = channel, column = pixel ================
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int ep_tid = threadIdx.x - 64;
+        const int box = r >> 6, oc = r & 63;
+        const uint32_t my_s = smem_u32(out_stage + box * (256 * 128) + oc * 2);
+        int as = 0; uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int mb = (int)(t % p.num_m_blocks);
+            const int mt = (int)(t / p.num_m_blocks);
+            const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
+            const int x0 = tw * kHpTW, h0 = th * kHpTH;
+            const bool full = (x0 + kHpTW <= p.W) && (h0 + kHpTH <= p.H);
+            mbar_wait(&tfull_bar[as], aph);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            if (ep_tid == 0) tma_store_wait_read();
+            named_bar_sync(1, 128);
+            float s1 = 0.f, s2 = 0.f;
+            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0);
+            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, h0, kHpTW - 1, 3, p.W, p.H);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (ep_tid == 0) {
+                tma_store_4d(&p.mapOut, out_stage, mb * 128, x0, h0, b);
+                tma_store_4d(&p.mapOut, out_stage + 256 * 128, mb * 128 + 64, x0, h0, b);
+                tma_store_commit();
+            }
+            if (p.stat_parts) {
+                sm_stats[mb * 128 + r] += s1;
+                sm_stats[p.N + mb * 128 + r] += s2;
             }
             as ^= 1; if (as == 0) aph ^= 1;
         }
@@ -1178,41 +1193,49 @@ static int pick_block_n(int N) {
     return 64;
 }
 
-static int g_no_halo = 1;   // the haloed narrow-N kernel is kept for experiments only: with N <= 128 every tcgen05.mma costs
-                             // ~100 cycles (A-operand fetch floor, tools/umma_rate_probe.cu), so fill reuse cannot pay
+static int g_no_halo = 0;
 
-template <int BLOCK_N>
-static int launch_halo_n(const HaloParams& p, long num_work, cudaStream_t st) {
-    using Cfg = HaloCfg<BLOCK_N>;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_halo_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES);
-        if (e != cudaSuccess) { set_error("tc_conv3x3 (halo): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
-        attr_done = true;
-    }
-    long grid = num_work < num_sms() ? num_work : num_sms();
-    if (grid < 1) grid = 1;
-    tc_conv3x3_halo_kernel<BLOCK_N><<<(int)grid, kHaloThreads, Cfg::SMEM_BYTES, st>>>(p);
-    int rc = check_launch("tc_conv3x3_fwd (halo)");
-    return rc < 0 ? rc : (int)grid;
+// make_map variant without swizzle (linear [pixel][64 ch] staging tiles of the pixels-on-N epilogue)
+static int make_map_linear(CUtensorMap* m, const void* base, long C, long W, long H, long B, long sw, long sh, long sb,
+                           int bw, int bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return UNETCA_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)sw * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (((uintptr_t)base & 15) || (strides[0] & 15)) { set_error("tensor map: base/strides must be 16-byte aligned"); return UNETCA_ERR_ARG; }
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (linear) failed (%d)", (int)r); return UNETCA_ERR_CUDA; }
+    return 0;
 }
 
-static int launch_halo(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
+// conv3x3 forward / dgrad for O % 128 == 0 through the haloed pixels-on-N kernel; w = packed filter [O][9*C]
+static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
                        float* stat_parts, cudaStream_t st) {
-    HaloParams p;
+    HpixParams p;
     memset(&p, 0, sizeof(p));
-    const int BN = pick_block_n(O);
     int rc;
-    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kHPitch, kHTH + 2)) < 0) return rc;
-    if ((rc = make_map(&p.mapW, w, 9L * C, O, 1, 1, ldk, (long)O * ldk, (long)O * ldk, BN, 1)) < 0) return rc;
-    if ((rc = make_map(&p.mapOut, y, O, W, H, B, ldy, (long)W * ldy, (long)H * W * ldy, kHTW, kHTH)) < 0) return rc;
-    p.tilesW = ceil_div(W, kHTW); p.tilesH = ceil_div(H, kHTH); p.nimg = B; p.H = H; p.W = W;
-    p.cchunks = C / 64; p.num_n_blocks = O / BN;
-    p.w_resident = (BN == 64 && C == 64 && O == 64) ? 1 : 0;
+    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kHpPitch, kHpTH + 2)) < 0) return rc;
+    if ((rc = make_map(&p.mapW, w, 9L * C, O, 1, 1, ldk, (long)O * ldk, (long)O * ldk, 128, 1)) < 0) return rc;
+    if ((rc = make_map_linear(&p.mapOut, y, O, W, H, B, ldy, (long)W * ldy, (long)H * W * ldy, kHpTW, kHpTH)) < 0) return rc;
+    p.tilesW = ceil_div(W, kHpTW); p.tilesH = ceil_div(H, kHpTH); p.nimg = B; p.H = H; p.W = W;
+    p.cchunks = C / 64; p.num_m_blocks = O / 128;
     p.stat_parts = stat_parts; p.N = O;
-    const long num_work = (long)p.tilesW * p.tilesH * B * p.num_n_blocks;
-    return BN == 64 ? launch_halo_n<64>(p, num_work, st) : launch_halo_n<128>(p, num_work, st);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_hpix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHpSmemBytes);
+        if (e != cudaSuccess) { set_error("tc_conv3x3 (hpix): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    const long num_work = (long)p.tilesW * p.tilesH * B * p.num_m_blocks;
+    long grid = num_work < num_sms() ? num_work : num_sms();
+    if (grid < 1) grid = 1;
+    tc_conv3x3_hpix_kernel<<<(int)grid, kHpThreads, kHpSmemBytes, st>>>(p);
+    rc = check_launch("tc_conv3x3_fwd (hpix)");
+    return rc < 0 ? rc : (int)grid;
 }
 
 // 5-D bf16 map over an NHWC activation seen as (C, W, P, H/P, B): P = 2 splits the rows into an even and an odd
@@ -1237,6 +1260,7 @@ static int make_map5(CUtensorMap* m, const void* base, long C, long W, long H, l
 }
 
 static int g_no_pixn = 0;
+static int g_pixn_cluster = 2;     // CTAs per cluster sharing the weight operand by TMA multicast (1 or 2)
 
 // w: P == 1: packed filter [O][9*C];  P == 2: pair-packed filter [2*O][12*C] (unetca_pack_conv3x3_pair)
 static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
@@ -1250,7 +1274,8 @@ static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, 
     if ((rc = make_map5(&p.mapX, x, C, W, H, B, ldx, P, TW, TI, true)) < 0) return rc;
     const int ntaps = P == 1 ? 9 : 12;
     const long rows = P == 1 ? O : 2L * O;
-    if ((rc = make_map(&p.mapW, w, (long)ntaps * C, rows, 1, 1, ldk, rows * ldk, rows * ldk, 128, 1)) < 0) return rc;
+    const int CL = g_pixn_cluster;
+    if ((rc = make_map(&p.mapW, w, (long)ntaps * C, rows, 1, 1, ldk, rows * ldk, rows * ldk, 128 / CL, 1)) < 0) return rc;
     if ((rc = make_map5(&p.mapOut, y, O, W, H, B, ldy, P, TW, TI, false)) < 0) return rc;
     p.tilesW = ceil_div(W, TW); p.tilesI = ceil_div(HP, TI); p.nimg = B;
     p.TW = TW; p.TI = TI; p.HP = HP; p.W = W; p.P = P;
@@ -1266,14 +1291,28 @@ static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, 
     p.stat_parts = stat_parts; p.N = O;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
         if (e != cudaSuccess) { set_error("tc_conv3x3 (pixn): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
         attr_done = true;
     }
-    const long num_work = (long)p.tilesW * p.tilesI * B * p.num_m_blocks;
-    long grid = num_work < num_sms() ? num_work : num_sms();
-    if (grid < 1) grid = 1;
-    tc_conv3x3_pixn_kernel<<<(int)grid, kTcThreads, kPnSmemBytes, st>>>(p);
+    const long num_tiles = (long)p.tilesW * p.tilesI * B;
+    const long num_work = ((num_tiles + CL - 1) / CL) * p.num_m_blocks;          // items per cluster-walk
+    long grid = num_work * CL < num_sms() ? num_work * CL : (num_sms() / CL) * CL;
+    if (grid < CL) grid = CL;
+    if (CL == 1) {
+        tc_conv3x3_pixn_kernel<1><<<(int)grid, kTcThreads, kPnSmemBytes, st>>>(p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kPnSmemBytes; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv3x3_pixn_kernel<2>, p);
+        if (e != cudaSuccess) { set_error("tc_conv3x3 (pixn): cluster launch: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+    }
     rc = check_launch("tc_conv3x3_fwd (pixn)");
     return rc < 0 ? rc : (int)grid;
 }
@@ -1292,6 +1331,7 @@ void unetca_tc_force_block_n(int n) { g_force_block_n = n; }
 void unetca_tc_force_wgrad_narrow(int on) { g_wgrad_narrow = on; }
 void unetca_tc_force_no_halo(int on) { g_no_halo = on; }
 void unetca_tc_force_no_pixn(int on) { g_no_pixn = on; }
+void unetca_tc_set_pixn_cluster(int n) { g_pixn_cluster = n == 1 ? 1 : 2; }
 
 // conv3x3 forward / dgrad through the row-pair layout (O a multiple of 64, H even); w_pair from unetca_tc_pack_pair
 int unetca_tc_conv3x3_fwd_paired(const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C,
@@ -1315,9 +1355,10 @@ int unetca_tc_pack_pair(const void* w, int ld, void* w_pair, int rows, int C, vo
 int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C,
                           int O, float* stat_parts, void* stream) {
     UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0 && O <= 1024, "tc_conv3x3: C=%d O=%d must be multiples of 64 (O<=1024)", C, O);
+    if (O % 128 == 0 && !g_no_halo && !g_force_block_n)
+        return launch_hpix(x, ldx, w, ldk, y, ldy, B, H, W, C, O, stat_parts, (cudaStream_t)stream);
     if (O % 128 == 0 && O % 256 != 0 && !g_no_pixn && !g_force_block_n)
         return launch_pixn(x, ldx, w, ldk, y, ldy, B, H, W, C, O, 1, stat_parts, (cudaStream_t)stream);
-    if (pick_block_n(O) <= 128 && !g_no_halo) return launch_halo(x, ldx, w, ldk, y, ldy, B, H, W, C, O, stat_parts, (cudaStream_t)stream);
     TcParams p;
     memset(&p, 0, sizeof(p));
     int TW = 0, TH = 0;
