@@ -101,15 +101,17 @@ int unetca_resize_bilinear_fwd(int dtype, const void* x, int ldx, int h, int w, 
 int unetca_resize_bilinear_bwd(int dtype, const void* dout, int ldd, int H, int W, void* dx, int ldx, int h, int w, int B, int C, void* stream);
 int unetca_se_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, float* parts, int* nparts, void* stream);
 int unetca_se_fc_bwd(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2, const float* p, const float* z, const float* s, float* dpre2, float* dz, float* dp, float* dw1, float* dw2, void* stream);
-/* SE squeeze with the extra per-image sums (sum m, sum m*(y-mean)) the merged backward needs: parts [B * *nparts][3][C] */
-int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, const float* mean, float* parts, int* nparts, void* stream);
-int unetca_se_fc3(const float* parts3, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2, float* p, float* z, float* s, float* sums34, void* stream);
+/* SE squeeze as two per-image partial sums (count of active pixels, masked sum of y): parts [B * *nparts][2][C];
+ * se_fc3 derives p = mean_hw relu(a*y+b) from them, runs the FC chain, and keeps (sum m, sum m*(y-mean)) for the backward */
+int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, float* parts, int* nparts, void* stream);
+int unetca_se_fc3(const float* parts2, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2, const float* scale, const float* shift, const float* mean, float* p, float* z, float* s, float* sums34, void* stream);
 /* merged SE + ReLU + BN backward reduction (one pass over dO, Y2): parts [B * *nparts][2][C]; FC chain; BN finalize */
 int unetca_se_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, const float* mean, float* parts, int* nparts, void* stream);
 int unetca_se_fc_bwd_fused(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2, const float* p, const float* z, const float* s, const float* scale, const float* shift, const float* mean, const float* sums34, float* sums, float* dpre2, float* dz, float* dp, float* dw1, float* dw2, void* stream);
 int unetca_bn_bwd_finalize_se(const float* sums, int B, int C, long count, long pix_per_img, const float* gamma, const float* invstd, const float* s, const float* dp, float* dgamma, float* dbeta, float* coef, void* stream);
 int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* parts, float* out, void* stream);
-/* tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid */
+/* tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid,
+ * 2 = quads per thread-row of se_scale_pool */
 void unetca_set_tuning(int key, int value);
 
 /* ---- outc 1x1 conv -> class logits (UCA:125,162), CrossEntropyLoss(ignore_index) (UCA:465,344), argmax (UCA:220) */

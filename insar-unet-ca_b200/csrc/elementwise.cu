@@ -240,24 +240,29 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ pa
                                                     float inv_hw, const float* __restrict__ w1,
                                                     const float* __restrict__ w2, float* __restrict__ p_out,
                                                     float* __restrict__ z_out, float* __restrict__ s_out,
-                                                    float* __restrict__ sums34) {
+                                                    float* __restrict__ sums34, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, const float* __restrict__ mean) {
     extern __shared__ float sm[];
     float* p = sm;          // [C]
     float* z = sm + C;      // [Cr]
     const int b = blockIdx.x, tid = threadIdx.x;
     for (int c = tid; c < C; c += blockDim.x) {
-        double t = 0.0, t3 = 0.0, t4 = 0.0;
+        double t = 0.0, t3 = 0.0, ty = 0.0;
         for (int i = 0; i < nparts; ++i) {
-            const float* row = parts + ((long)b * nparts + i) * NSTAT * C + c;
-            t += (double)row[0];
-            if (NSTAT == 3) { t3 += (double)row[C]; t4 += (double)row[2 * (long)C]; }
+            if (NSTAT == 1) t += (double)parts[((long)b * nparts + i) * C + c];
+            else {
+                const float* row = parts + ((long)b * nparts + i) * 2 * C + c;
+                t3 += (double)row[0];
+                ty += (double)row[C];
+            }
         }
-        const float v = (float)t * inv_hw;
+        if (NSTAT == 3) t = (double)scale[c] * ty + (double)shift[c] * t3;       // sum relu(a*y+b) = a*Sy + b*S3
+        const float v = (float)(t * (double)inv_hw);
         p[c] = v;
         p_out[(long)b * C + c] = v;
         if (NSTAT == 3 && sums34) {
             sums34[((long)b * 2 + 0) * C + c] = (float)t3;
-            sums34[((long)b * 2 + 1) * C + c] = (float)t4;
+            sums34[((long)b * 2 + 1) * C + c] = (float)(ty - (mean ? (double)mean[c] : 0.0) * t3);
         }
     }
     __syncthreads();
@@ -685,14 +690,15 @@ __global__ void __launch_bounds__(kThreads, 4) se_bn_bwd_reduce_kernel(const T* 
     block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
-// SE squeeze (forward): per (image, channel) sums of relu(a*y+b), m and m*(y-mean); the last two are kept for the
-// backward pass (see above).  parts: [(b*nblk + blk)][3][C]; mean may be null (eval: treated as 0).
+// SE squeeze (forward): per (image, channel) S3 = sum m and Sy = sum m*y with m = (a*y+b > 0).  The squeeze itself
+// follows from them, sum relu(a*y+b) = a*Sy + b*S3, and so does the centred sum the backward pass needs,
+// S4 = Sy - mean*S3 (both formed in double by se_fc_kernel<3>).  Two predicated adds per element keep this read-only
+// pass memory-bound.  parts: [(b*nblk + blk)][2][C]
 template <typename T>
-__global__ void __launch_bounds__(kThreads, 3) se_squeeze_kernel(const T* __restrict__ y, int ldy, int C,
+__global__ void __launch_bounds__(kThreads, 4) se_squeeze_kernel(const T* __restrict__ y, int ldy, int C,
                                                                  long pix_per_img, long chunk,
                                                                  const float* __restrict__ scale,
                                                                  const float* __restrict__ shift,
-                                                                 const float* __restrict__ mean,
                                                                  float* __restrict__ parts) {
     constexpr int VEC = VecTraits<T>::N;
     const int vpr = C / VEC, rows = kThreads / vpr;
@@ -700,30 +706,24 @@ __global__ void __launch_bounds__(kThreads, 3) se_squeeze_kernel(const T* __rest
     const long base = (long)blockIdx.y * pix_per_img;
     const long p0 = (long)blockIdx.x * chunk;
     long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
-    float acc[3][VEC];
+    float acc[2][VEC];
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
+    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
     if (r < rows) {
-        float a[VEC], b[VEC], mu[VEC];
+        float a[VEC], b[VEC];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-            a[i] = scale[cv * VEC + i]; b[i] = shift[cv * VEC + i]; mu[i] = mean ? mean[cv * VEC + i] : 0.f;
-        }
+        for (int i = 0; i < VEC; ++i) { a[i] = scale[cv * VEC + i]; b[i] = shift[cv * VEC + i]; }
 #pragma unroll 8
         for (long p = p0 + r; p < p1; p += rows) {
             float v[VEC];
             load_vec(y + (base + p) * ldy + cv * VEC, v);
 #pragma unroll
             for (int i = 0; i < VEC; ++i) {
-                const float t = fmaf(a[i], v[i], b[i]);
-                const bool on = t > 0.f;
-                acc[0][i] += fmaxf(t, 0.f);
-                acc[1][i] += on ? 1.f : 0.f;
-                acc[2][i] += on ? v[i] - mu[i] : 0.f;
+                if (fmaf(a[i], v[i], b[i]) > 0.f) { acc[0][i] += 1.f; acc[1][i] += v[i]; }
             }
         }
     }
-    block_reduce_rows<3, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 3 * C);
+    block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
 // SE backward FC chain fed by the four merged sums (one block per image); also stores the per-image sums
@@ -1373,30 +1373,33 @@ int unetca_bn_relu(int dtype, const void* y, int ldy, void* out, int ldo, int B,
 int unetca_se_fc(const float* pool_parts, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,
                  float* p, float* z, float* s, void* stream) {
     se_fc_kernel<1><<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_parts, nparts, C, Cr, 1.f / (float)hw,
-                                                                              w1, w2, p, z, s, nullptr);
+                                                                              w1, w2, p, z, s, nullptr, nullptr, nullptr,
+                                                                              nullptr);
     return check_launch("se_fc");
 }
 
-// SE squeeze with the two extra per-image sums the merged backward needs.  parts: [B * *nparts][3][C]
+// SE squeeze partial sums (count of active pixels, masked sum of y) per image.  parts: [B * *nparts][2][C]
 int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale,
-                      const float* shift, const float* mean, float* parts, int* nparts, void* stream) {
+                      const float* shift, float* parts, int* nparts, void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldy);
         static int slots = 0;
         if (!slots) slots = resident_blocks(se_squeeze_kernel<T>);
         const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
-        se_squeeze_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)y, ldy, C, pix_per_img, chunk, scale, shift, mean, parts);
+        se_squeeze_kernel<T><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)y, ldy, C, pix_per_img, chunk, scale, shift, parts);
         *nparts = grid.x;
     });
     return check_launch("se_squeeze");
 }
 
-// FC chain on the 3-stat squeeze partials; sums34 (nullable): [B][2][C] = (sum m, sum m*(y-mean)) for the backward
-int unetca_se_fc3(const float* parts3, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,
-                  float* p, float* z, float* s, float* sums34, void* stream) {
-    se_fc_kernel<3><<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(parts3, nparts, C, Cr, 1.f / (float)hw,
-                                                                              w1, w2, p, z, s, sums34);
+// FC chain on the squeeze partials of unetca_se_squeeze; mean (nullable, eval) = BN batch mean; sums34 (nullable):
+// [B][2][C] = (sum m, sum m*(y-mean)) kept for the merged backward reduction
+int unetca_se_fc3(const float* parts2, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,
+                  const float* scale, const float* shift, const float* mean, float* p, float* z, float* s, float* sums34,
+                  void* stream) {
+    se_fc_kernel<3><<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(parts2, nparts, C, Cr, 1.f / (float)hw,
+                                                                              w1, w2, p, z, s, sums34, scale, shift, mean);
     return check_launch("se_fc3");
 }
 

@@ -231,14 +231,14 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
     if blk.se is not None:
         w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
         Cr = w1.shape[0]
-        _lib.call("unetca_se_squeeze", dt, _ptr(y2), O, B, Hl * Wl, O, _ptr(scale2), _ptr(shift2),
-                  _ptr(sv.mean2) if train else None, _ptr(parts), ctypes.byref(nparts), st)
+        _lib.call("unetca_se_squeeze", dt, _ptr(y2), O, B, Hl * Wl, O, _ptr(scale2), _ptr(shift2), _ptr(parts),
+                  ctypes.byref(nparts), st)
         p = torch.empty(B, O, dtype=torch.float32, device=dev)
         z = torch.empty(B, Cr, dtype=torch.float32, device=dev)
         s = torch.empty(B, O, dtype=torch.float32, device=dev)
         sums34 = torch.empty(B, 2, O, dtype=torch.float32, device=dev) if keep else None
-        _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(p), _ptr(z),
-                  _ptr(s), _ptr(sums34), st)
+        _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(scale2),
+                  _ptr(shift2), _ptr(sv.mean2) if train else None, _ptr(p), _ptr(z), _ptr(s), _ptr(sums34), st)
         sv.p, sv.z, sv.s, sv.sums34 = p, z, s, sums34
     if pooled is not None and (Hl % 2 or Wl % 2):
         # odd extent: MaxPool2d(2) floors (UCA:106-109) -> scale pass, then the standalone pool over the stored values

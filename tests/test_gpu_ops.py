@@ -199,12 +199,12 @@ def test_se_block_forward_backward(dt, B, C, H, W, pool):
     call("unetca_bn_bwd_finalize", ptr(parts), n.value, C, B * H * W, ptr(gamma), ptr(invstd), ptr(dg_a), ptr(db_a),
          ptr(coef_a), stream())
     parts4 = parts_buf(B, 4096)
-    call("unetca_se_squeeze", dt, ptr(yd), C, B, H * W, C, ptr(sc), ptr(sh), ptr(mean), ptr(parts4), ctypes.byref(n), stream())
+    call("unetca_se_squeeze", dt, ptr(yd), C, B, H * W, C, ptr(sc), ptr(sh), ptr(parts4), ctypes.byref(n), stream())
     p3, z3, s3 = torch.empty_like(p), torch.empty_like(z), torch.empty_like(s)
     sums34 = torch.empty(B, 2, C, device="cuda")
-    call("unetca_se_fc3", ptr(parts4), n.value, B, C, Cr, H * W, ptr(w1d), ptr(w2d), ptr(p3), ptr(z3), ptr(s3), ptr(sums34),
-         stream())
-    assert relerr(p3, p) < 1e-5 and relerr(z3, z) < 1e-5 and relerr(s3, s) < 1e-5
+    call("unetca_se_fc3", ptr(parts4), n.value, B, C, Cr, H * W, ptr(w1d), ptr(w2d), ptr(sc), ptr(sh), ptr(mean), ptr(p3),
+         ptr(z3), ptr(s3), ptr(sums34), stream())
+    assert relerr(p3, p) < 1e-5 and relerr(z3, z) < 1e-4 and relerr(s3, s) < 1e-5
     on = (yr * scale[None, :, None, None] + shift[None, :, None, None]) > 0
     assert torch.equal(sums34[:, 0].cpu(), on.float().sum((2, 3)))
     assert relerr(sums34[:, 1].cpu(), ((yr - mean.cpu()[None, :, None, None]) * on).sum((2, 3))) < 1e-4

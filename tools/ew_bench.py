@@ -60,7 +60,7 @@ def main():
         kernels = {
             "bn_relu(write)     2N": (2 * N * 2, "ew", lambda: _lib.call("unetca_bn_relu", 1, P(y), C, P(dy), C, B, S * S, C, P(sc), P(sh), None, None, st)),
             "bn_relu(squeeze)   1N": (N * 2, "red", lambda: _lib.call("unetca_bn_relu", 1, P(y), C, None, 0, B, S * S, C, P(sc), P(sh), P(parts), ctypes.byref(n), st)),
-            "se_squeeze(3 sums) 1N": (N * 2, "red", lambda: _lib.call("unetca_se_squeeze", 1, P(y), C, B, S * S, C, P(sc), P(sh), P(mean), P(parts), ctypes.byref(n), st)),
+            "se_squeeze(2 sums) 1N": (N * 2, "red", lambda: _lib.call("unetca_se_squeeze", 1, P(y), C, B, S * S, C, P(sc), P(sh), P(parts), ctypes.byref(n), st)),
             "se_scale_pool   2.25N": (2 * N * 2 + (N // 4) * 3, "fix", lambda: _lib.call("unetca_se_scale_pool", 1, P(y), C, P(out), 2 * C, P(pooled), C, P(pos), B, S, S, C, P(sc), P(sh), P(s), st)),
             "se_bn_bwd_reduce   2N": (2 * N * 2, "red", lambda: _lib.call("unetca_se_bn_bwd_reduce", 1, P(d), C, P(y), C, B, S * S, C, P(sc), P(sh), P(mean), P(parts), ctypes.byref(n), st)),
             "bn_bwd_reduce      2N": (2 * N * 2, "red", lambda: _lib.call("unetca_bn_bwd_reduce", 1, P(d), C, P(y), C, B, S * S, C, P(sc), P(sh), P(mean), P(invstd), None, None, P(parts), ctypes.byref(n), st)),
