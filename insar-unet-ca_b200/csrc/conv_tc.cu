@@ -6,20 +6,18 @@
 //   first conv (K=9*Cin)   UCA:81 (via im2col rows) out[p][n]  = sum_k col[p][k] * Wk[n][k]
 //   conv3x3 / convT / first-conv wgrad              dW[m][n]   = sum_p A[p][m] * B[p][n]       (K = pixels)
 //
-// Design (one persistent CTA per SM, 192 threads, warp-specialised):
-//   warp 0   TMA producer: every operand tile is ONE cp.async.bulk.tensor box of [pixels][64 channels] bf16
-//            (128-byte rows, SWIZZLE_128B) out of a 4-D (C,W,H,B) tensor map over the NHWC activation.  A 3x3
-//            tap is the same box at coordinates shifted by (dh,dw); TMA's out-of-bounds zero fill *is* the
-//            conv padding, and the stride-2 pixel lattice of the transposed conv is just a tensor map with
-//            doubled pixel strides.  No im2col buffer exists for C >= 64.
-//   warp 1   MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16) on
-//            shared-memory descriptors; fp32 accumulators live in TMEM, double-buffered (2 x BLOCK_N columns) so
-//            the epilogue of tile i overlaps the MMAs of tile i+1.  K-major descriptors for the forward-like
-//            problems, MN-major descriptors (same smem boxes, a_major=b_major=1) for the weight gradients.
-//   warps 2-5 epilogue: tcgen05.ld (32x32b) -> registers -> bf16 -> swizzled smem staging -> TMA store; the
-//            per-channel sum / sum-of-squares that BatchNorm needs are taken from the staged tile and kept in
-//            shared memory across the CTA's tiles, then written once per CTA (deterministic, no atomics).
-//            Weight-gradient tiles are written as fp32 split-K partials.
+// Kernels (all persistent, one CTA per SM, warp-specialised: TMA producer warp(s), one MMA-issuing thread, four
+// epilogue warps; fp32 accumulators double-buffered in TMEM; every operand tile is a cp.async.bulk.tensor box of
+// [pixels][64 channels] bf16 with SWIZZLE_128B; TMA out-of-bounds zero fill is the conv padding):
+//   tc_conv3x3_hpix_kernel   conv3x3 fwd/dgrad, O % 128 == 0: 128 channels x 256 pixels per MMA, nine taps from ONE
+//                            haloed activation tile (shifted K-major B descriptors)
+//   tc_conv3x3_pixn_kernel   conv3x3 fwd/dgrad, O = 64: (2 output rows x 64 channels) x 256 pixel pairs over 4x3
+//                            virtual taps (pair-packed filter, 5-D row-lattice tensor map); also the per-tap P=1 form
+//   tc_kernel<N,false>       pixels on M, one box per tap: first conv GEMM, ConvTranspose fwd/dgrad, fallback
+//   tc_wgrad3x3_wide_kernel / tc_wgrad3x3_kernel / tc_kernel<N,true>   weight gradients (MN-major descriptors)
+// Why the layouts look like this (measured, tools/umma_rate_probe.cu): an SS-mode tcgen05.mma M=128,K=16 costs
+// >= ~100 cycles whatever N is, so only N = 256 reaches the tensor rate; and TMA fill writes share the shared-memory
+// bandwidth with the MMA's operand reads, so re-using one haloed tile for all taps is what lifts the ~70 % ceiling.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <cuda.h>
