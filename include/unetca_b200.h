@@ -120,6 +120,10 @@ int unetca_outc_bwd(int dtype, const float* g, const float* gscale, const void* 
 /* loss_out[0] = mean CE over valid pixels (NaN when none), loss_out[1] = #valid; g = un-normalised dlogits;
  * gscale_out[0] = upstream/#valid; mask = argmax class map (first maximum wins); target/g/mask optional */
 int unetca_cross_entropy(const float* logits, const long long* target, int nc, int B, long HW, long long ignore_index, const float* upstream, float* g, long long* mask, float* parts, float* loss_out, float* gscale_out, void* stream);
+/* compute_metrics (UCA:214-269) on the device: counts[(nc+1)][nc] int64, row = label (row nc = label values outside
+ * [0,nc) other than ignore_index), column = argmax class of the logits (first maximum wins, UCA:220); pixels with
+ * label == ignore_index are dropped (UCA:223).  parts: unetca_max_parts(B) * (nc+1)*nc 8-byte words of scratch */
+int unetca_confusion_counts(const float* logits, const long long* target, int nc, int B, long HW, long long ignore_index, void* parts, long long* counts, void* stream);
 
 /* ---- implementation-specific contraction entry points (exported for the cross-check tests) ----------------- */
 int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, void* stream);

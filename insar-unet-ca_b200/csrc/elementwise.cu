@@ -1158,6 +1158,48 @@ __global__ void ce_finalize_kernel(const float* __restrict__ parts, int nparts, 
 // ---------------------------------------------------------------------------------------------------------
 // layout conversion at the module boundary and weight packing
 // ---------------------------------------------------------------------------------------------------------
+// compute_metrics (UCA:214-269) on the device: argmax of the class logits (first maximum wins, like
+// torch.max(outputs, 1) at UCA:220) against the label map, pixels with label == ignore_index dropped (UCA:223),
+// counted into a (nc+1) x nc table: row = label (row nc = any other label value), column = predicted class.
+// TP / FP / FN of the reference are sums over that table, so only (nc+1)*nc integers travel to the host instead of
+// the two masks (UCA:229-230).  Two-stage and deterministic: per-block tables, then one summing block.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxMetricClasses = 8;
+__global__ void __launch_bounds__(kThreads) confusion_kernel(const float* __restrict__ logits,
+                                                             const long long* __restrict__ target, int nc, long npix,
+                                                             long HW, long long ignore_index,
+                                                             unsigned long long* __restrict__ parts) {
+    __shared__ unsigned int cnt[(kMaxMetricClasses + 1) * kMaxMetricClasses];
+    const int ncell = (nc + 1) * nc;
+    for (int i = threadIdx.x; i < ncell; i += kThreads) cnt[i] = 0u;
+    __syncthreads();
+    for (long p = (long)blockIdx.x * kThreads + threadIdx.x; p < npix; p += (long)gridDim.x * kThreads) {
+        const long long t = target[p];
+        if (t == ignore_index) continue;
+        const long b = p / HW, hw = p % HW;
+        const float* lp = logits + b * nc * HW + hw;
+        float m = lp[0];
+        int am = 0;
+        for (int o = 1; o < nc; ++o) {
+            const float v = lp[o * HW];
+            if (v > m || (v != v && m == m)) { m = v; am = o; }
+        }
+        const int row = (t >= 0 && t < nc) ? (int)t : nc;
+        atomicAdd(&cnt[row * nc + am], 1u);             // shared-memory integer counter: order-independent
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ncell; i += kThreads) parts[(long)blockIdx.x * ncell + i] = cnt[i];
+}
+__global__ void confusion_finalize_kernel(const unsigned long long* __restrict__ parts, int nparts, int ncell,
+                                          long long* __restrict__ counts) {
+    const int i = threadIdx.x;
+    if (i >= ncell) return;
+    unsigned long long t = 0;
+    for (int k = 0; k < nparts; ++k) t += parts[(long)k * ncell + i];
+    counts[i] = (long long)t;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // im2col of the (B,Cin,H,W) NCHW fp32 network input for the first 3x3 conv: col[p][tap*Cin + c], zero padded to
 // Kpad columns (K = 9*Cin is not a multiple of the MMA K; the padding exists only in this staging buffer).
 template <typename T, int CIN>
@@ -1601,6 +1643,21 @@ int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* p
         sum_parts_kernel<<<ceil_div(C, 32), 256, 0, st>>>(parts, nblk, C, nullptr, out);
     });
     return check_launch("chan_sum");
+}
+
+// counts[(nc+1)][nc] (int64): row = label (row nc: labels outside [0,nc) other than ignore_index), column = argmax
+// class.  parts: scratch of unetca_max_parts(B) * (nc+1)*nc 8-byte words.
+int unetca_confusion_counts(const float* logits, const long long* target, int nc, int B, long HW, long long ignore_index,
+                            void* parts, long long* counts, void* stream) {
+    UNETCA_REQUIRE(nc >= 1 && nc <= kMaxMetricClasses, "confusion_counts: num_classes %d unsupported (1..%d)", nc, kMaxMetricClasses);
+    const long npix = (long)B * HW;
+    int nblk = ceil_div(npix, kThreads * 8);
+    if (nblk > kMaxParts) nblk = kMaxParts;
+    if (nblk < 1) nblk = 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    confusion_kernel<<<nblk, kThreads, 0, st>>>(logits, target, nc, npix, HW, ignore_index, (unsigned long long*)parts);
+    confusion_finalize_kernel<<<1, 128, 0, st>>>((const unsigned long long*)parts, nblk, (nc + 1) * nc, counts);
+    return check_launch("confusion_counts");
 }
 
 static int nc_pad(int nc) { return nc <= 2 ? 2 : nc <= 4 ? 4 : 8; }

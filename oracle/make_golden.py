@@ -84,9 +84,21 @@ def run_case(ref, name, seed, B, H, W, use_se, full):
     print(name, "loss", loss.item(), "->", path, os.path.getsize(path) // 1024, "KiB")
 
 
+def run_metrics(ref):
+    """compute_metrics (UCA:214-269) of the unmodified reference on the seeded cases of oracle/metrics_port.py."""
+    from oracle import metrics_port
+    out = {}
+    for name, logits, masks, nc in metrics_port.metric_cases():
+        m = ref.compute_metrics(logits, masks, nc)
+        out[name] = np.array([m["acc"], m["miou"], m["mpa"], m["mf1"]], dtype=np.float64)
+        print("metrics", name, out[name])
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
+    run_metrics(ref)
     run_case(ref, "unetca_se_b2_32", seed=0, B=2, H=32, W=32, use_se=True, full=True)
     run_case(ref, "unet_plain_b2_32", seed=1, B=2, H=32, W=48, use_se=False, full=True)
     run_case(ref, "unetca_se_b4_256", seed=0, B=4, H=256, W=256, use_se=True, full=False)   # BASELINE configs[0]

@@ -398,3 +398,31 @@ def test_first_conv_im2col(dt, impl):
     dw = torch.empty(O, Cin, 3, 3, device="cuda")
     call("unetca_im2col_wgrad", dt, ptr(dyd), O, ptr(col), Kpad, ptr(ws), ws.numel(), B * H * W, Cin, O, ptr(dw), stream())
     assert relerr(dw.cpu(), wr.grad) < 2e-3
+
+
+def test_metrics_on_device_match_reference(golden_dir):
+    """f-1: compute_metrics (UCA:214-269) from the on-device label-by-prediction table == the reference's numbers."""
+    import os
+    from oracle import metrics_port
+    from unetca_b200 import metrics
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    for name, logits, masks, nc in metrics_port.metric_cases():
+        counts = metrics.confusion_counts(logits.cuda(), masks.cuda(), nc).cpu().numpy()
+        preds = torch.max(logits, 1)[1]
+        valid = masks != 255
+        for r in range(nc + 1):
+            for c in range(nc):
+                lab = (masks == r) if r < nc else ((masks < 0) | (masks >= nc))
+                assert counts[r, c] == int((lab & valid & (preds == c)).sum()), (name, r, c)      # exact integers
+        m = metrics.compute_metrics(logits.cuda(), masks.cuda(), nc)
+        np.testing.assert_allclose([m["acc"], m["miou"], m["mpa"], m["mf1"]], g[name], rtol=0, atol=1e-15, err_msg=name)
+    # a full-size batch (configs[1] shape): counts add up and agree with torch on the device
+    lo = torch.randn(8, 2, 512, 512, device="cuda")
+    ma = torch.randint(0, 2, (8, 512, 512), device="cuda")
+    ma[torch.rand(8, 512, 512, device="cuda") < 0.01] = 255
+    counts = metrics.confusion_counts(lo, ma, 2)
+    pr = torch.max(lo, 1)[1]
+    for r in range(2):
+        for c in range(2):
+            assert counts[r, c].item() == ((ma == r) & (pr == c)).sum().item()
+    assert counts.sum().item() == (ma != 255).sum().item()

@@ -126,3 +126,12 @@ def test_cross_entropy_ignore_and_all_ignored():
 def test_bn_train_needs_more_than_one_value():
     with pytest.raises(ValueError):
         np_ops.bn_train_fwd(np.zeros((1, 4, 1, 1)), np.ones(4), np.zeros(4), np.zeros(4), np.ones(4))
+
+
+def test_metrics_port_matches_reference_golden(golden_dir):
+    """oracle/metrics_port.compute_metrics == the reference's compute_metrics (UCA:214-269) on the seeded cases."""
+    from oracle import metrics_port
+    g = _load(golden_dir, "metrics")
+    for name, logits, masks, nc in metrics_port.metric_cases():
+        m = metrics_port.compute_metrics(logits, masks, nc)
+        np.testing.assert_allclose([m["acc"], m["miou"], m["mpa"], m["mf1"]], g[name], rtol=0, atol=1e-15, err_msg=name)
