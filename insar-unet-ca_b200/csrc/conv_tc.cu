@@ -674,6 +674,308 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide_kernel(const _
 
 
 // ---------------------------------------------------------------------------------------------------------
+// conv3x3 weight gradient for O % 256 == 0 (and C % 128 == 0): one work item = (128 c, 256 o, tap pair).
+// The wide kernel above sits at the MN-major A-fetch floor (91 cycles per 128x128x16 MMA, 70 % of the tensor rate).
+// TMEM's 512 columns hold exactly TWO 256-column accumulators, so here the nine taps are walked as the pairs
+// (0,1) (2,3) (4,5) (6,7) and the single 8: every MMA is 128x256x16 (full rate).  Both taps of a pair come from one
+// 18 x 9 haloed X tile per 64-channel chunk (a pair spans at most two filter rows) by row/column-shifted descriptors.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWg3XRows = kWgTH + 1;
+constexpr int kWg3XBox = kWgPitch * kWg3XRows * 128;        // 20736 bytes written by TMA per chunk
+constexpr int kWg3XBytes = 21 * 1024;                       // slot
+constexpr int kWg3StageBytes = 2 * kWg3XBytes + 4 * kWgYBytes;
+constexpr int kWg3Stages = 2;
+constexpr int kWg3SmemBytes = 1024 + kWg3Stages * kWg3StageBytes + 256;
+static_assert(kWg3SmemBytes <= 227 * 1024, "wide256 wgrad: shared memory budget");
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide256_kernel(const __grid_constant__ Wg3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWg3Stages * kWg3StageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWg3Stages;
+    uint64_t* tfull_bar = bars + 2 * kWg3Stages;
+    uint64_t* tempty_bar = bars + 2 * kWg3Stages + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWg3Stages + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWg3Stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapDY);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const int cpairs = p.cchunks / 2, oquads = p.oblocks / 4;
+    const long items = (long)cpairs * oquads * 5;
+    const long num_work = items * p.nsplit;
+    const int kt_per_split = (p.ktiles_total + p.nsplit - 1) / p.nsplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / items), item = (int)(t % items);
+                const int tp = item % 5, oq = (item / 5) % oquads, cp = item / (5 * oquads);
+                const int kh0 = (2 * tp) / 3;
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    const int tw = kt % p.tilesW, th = (kt / p.tilesW) % p.tilesH, b = kt / tiles_per_img;
+                    const int w0 = tw * kWgTW, h0 = th * kWgTH;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* xs = smem + s * kWg3StageBytes;
+                    mbar_expect_tx(&full_bar[s], 2 * kWg3XBox + 4 * kWgYBytes);
+                    tma_load_4d(&p.mapX, &full_bar[s], xs, cp * 128, w0 - 1, h0 - 1 + kh0, b);
+                    tma_load_4d(&p.mapX, &full_bar[s], xs + kWg3XBytes, cp * 128 + 64, w0 - 1, h0 - 1 + kh0, b);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        tma_load_4d(&p.mapDY, &full_bar[s], xs + 2 * kWg3XBytes + j * kWgYBytes, oq * 256 + j * 64, w0, h0, b);
+                    if (++s == kWg3Stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 256, 1, 1);
+            int s = 0; uint32_t ph = 0, aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / items), item = (int)(t % items);
+                const int tp = item % 5;
+                const int t0 = 2 * tp, ntap = tp < 4 ? 2 : 1;
+                const int kh0 = t0 / 3;
+                // shift of each tap inside the haloed tile (rows relative to kh0)
+                const uint32_t off0 = (uint32_t)((t0 % 3) * 128);
+                const uint32_t off1 = (uint32_t)((((t0 + 1) / 3 - kh0) * kWgPitch + (t0 + 1) % 3) * 128);
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                mbar_wait(tempty_bar, aph ^ 1);
+                tcgen05_fence_after();
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t xs = smem_u32(smem + s * kWg3StageBytes);
+                    const uint32_t ys = xs + 2 * kWg3XBytes;
+#pragma unroll 1
+                    for (int hh = 0; hh < kWgTH; ++hh) {
+                        const uint64_t db = make_smem_desc(ys + hh * (kWgTW * 128), kWgYBytes, 1024);
+                        const uint32_t xrow = xs + hh * (kWgPitch * 128);
+                        const uint32_t acc = (kt > kt0 || hh > 0) ? 1u : 0u;
+                        umma_bf16(tmem_base, make_smem_desc(xrow + off0, kWg3XBytes, 1024), db, idesc, acc);
+                        if (ntap == 2)
+                            umma_bf16(tmem_base + 256, make_smem_desc(xrow + off1, kWg3XBytes, 1024), db, idesc, acc);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == kWg3Stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull_bar);
+                aph ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int z = (int)(t / items), item = (int)(t % items);
+            const int tp = item % 5, oq = (item / 5) % oquads, cp = item / (5 * oquads);
+            const int ntap = tp < 4 ? 2 : 1;
+            int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+            if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+            const bool have = kt1 > kt0;
+            mbar_wait(tfull_bar, aph);
+            tcgen05_fence_after();
+            float* wsz = p.ws + (long long)z * p.split_stride + (long long)(oq * 256) * p.ldn + cp * 128 + r;
+#pragma unroll 1
+            for (int j = 0; j < ntap; ++j) {
+                float* dst = wsz + (2 * tp + j) * p.C;
+#pragma unroll 1
+                for (int c32 = 0; c32 < 8; ++c32) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + j * 256 + c32 * 32, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        dst[(long long)(c32 * 32 + i) * p.ldn] = have ? __uint_as_float(v[i]) : 0.f;
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
+            aph ^= 1;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv3x3 weight gradient when C or O is only a multiple of 64 (the 512^2 / 256^2 layers): row-pair layout.
+// The kernel above (M = two taps x 64 c, N = 64 o) sits at the MN-major A-fetch floor: 91 cycles for a 32-cycle MMA.
+// Here one MMA is  D[(j, o)][(kw, c)]  with M = 128 = 2 dY row-shifts x 64 o and N = 192 = 3 kw taps x 64 c:
+//   A block j = the dY tile row hh + j (MN-major, LBO = one 16-pixel tile row), K = the 16 pixels of tile row hh;
+//   B block kw = the X view shifted by kw pixels (LBO = 128 B) at X row hh + v, v = 0..3 the "view" (row shift).
+// Block j = 0 accumulates tap kh = v, block j = 1 accumulates tap kh = v - 1 (dY row hh+1 against the same X row), so
+// walking only the EVEN tile rows hh covers every dY row exactly once: even rows through the j = 0 halves, odd rows
+// through the j = 1 halves.  6 of the 8 (view, j) halves are real taps (75 % useful work at N = 192, 96 cycles per MMA,
+// instead of 35 %).  The two halves of a tap land in different accumulators, so they are written as two split-K
+// slices (2z + j) and summed by the existing reduction.  One work item = (64 c, 64 o, view pair); 384 TMEM columns.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWg4XRows = kWgTH + 1;
+constexpr int kWg4XBox = kWgPitch * kWg4XRows * 128;        // 20736
+constexpr int kWg4XBytes = 21 * 1024;
+constexpr int kWg4StageBytes = kWg4XBytes + kWgYBytes;      // 37 KB
+constexpr int kWg4Stages = 5;
+constexpr int kWg4SmemBytes = 1024 + kWg4Stages * kWg4StageBytes + 256;
+static_assert(kWg4SmemBytes <= 227 * 1024, "row-pair wgrad: shared memory budget");
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_rowpair_kernel(const __grid_constant__ Wg3Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWg4Stages * kWg4StageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kWg4Stages;
+    uint64_t* tfull_bar = bars + 2 * kWg4Stages;
+    uint64_t* tempty_bar = bars + 2 * kWg4Stages + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWg4Stages + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWg4Stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1);
+        mbar_init(tempty_bar, 4);
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapDY);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const long items = (long)p.cchunks * p.oblocks * 2;
+    const long num_work = items * p.nsplit;
+    const int kt_per_split = (p.ktiles_total + p.nsplit - 1) / p.nsplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / items), item = (int)(t % items);
+                const int vp = item & 1, ob = (item >> 1) % p.oblocks, cc = (item >> 1) / p.oblocks;
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    const int tw = kt % p.tilesW, th = (kt / p.tilesW) % p.tilesH, b = kt / tiles_per_img;
+                    const int w0 = tw * kWgTW, h0 = th * kWgTH;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* xs = smem + s * kWg4StageBytes;
+                    mbar_expect_tx(&full_bar[s], kWg4XBox + kWgYBytes);
+                    // X rows h0 - 1 + 2*vp ... (+9): both views of the pair
+                    tma_load_4d(&p.mapX, &full_bar[s], xs, cc * 64, w0 - 1, h0 - 1 + 2 * vp, b);
+                    tma_load_4d(&p.mapDY, &full_bar[s], xs + kWg4XBytes, ob * 64, w0, h0, b);
+                    if (++s == kWg4Stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 192, 1, 1);
+            int s = 0; uint32_t ph = 0, aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / items);
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                mbar_wait(tempty_bar, aph ^ 1);
+                tcgen05_fence_after();
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t xs = smem_u32(smem + s * kWg4StageBytes);
+                    const uint32_t ys = xs + kWg4XBytes;
+#pragma unroll 1
+                    for (int hh = 0; hh < kWgTH; hh += 2) {
+                        // A: dY rows hh (j=0) and hh+1 (j=1): LBO = one tile row
+                        const uint64_t da = make_smem_desc(ys + hh * (kWgTW * 128), kWgTW * 128, 1024);
+                        const uint32_t acc = (kt > kt0 || hh > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int v = 0; v < 2; ++v) {
+                            // B: X local row hh + v, the three kw views 128 B apart
+                            const uint64_t db = make_smem_desc(xs + (hh + v) * (kWgPitch * 128), 128, 1024);
+                            umma_bf16(tmem_base + v * 192, da, db, idesc, acc);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == kWg4Stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull_bar);
+                aph ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int j = r >> 6, o = r & 63;
+        uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int z = (int)(t / items), item = (int)(t % items);
+            const int vp = item & 1, ob = (item >> 1) % p.oblocks, cc = (item >> 1) / p.oblocks;
+            int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+            if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+            const bool have = kt1 > kt0;
+            mbar_wait(tfull_bar, aph);
+            tcgen05_fence_after();
+            // split-K slice 2z + j; row o of the (O, 9C) gradient
+            float* row = p.ws + (long long)(2 * z + j) * p.split_stride + (long long)(ob * 64 + o) * p.ldn + cc * 64;
+#pragma unroll 1
+            for (int v = 0; v < 2; ++v) {
+                const int kh = 2 * vp + v - j;            // real filter row of this (view, j) half
+#pragma unroll 1
+                for (int kw = 0; kw < 3; ++kw) {
+                    uint32_t a[32], b2[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + v * 192 + kw * 64, a);
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + v * 192 + kw * 64 + 32, b2);
+                    tmem_wait_ld();
+                    if (kh >= 0 && kh <= 2) {
+                        float4* dst = reinterpret_cast<float4*>(row + (kh * 3 + kw) * p.C);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            dst[i] = have ? make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]),
+                                                        __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            dst[8 + i] = have ? make_float4(__uint_as_float(b2[4 * i]), __uint_as_float(b2[4 * i + 1]),
+                                                            __uint_as_float(b2[4 * i + 2]), __uint_as_float(b2[4 * i + 3]))
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
+            aph ^= 1;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // conv3x3 forward / dgrad for NARROW outputs (64 or 128 channels), pixels on the N side of the MMA.
 // Measured on B200 (tools/umma_rate_probe.cu): one tcgen05.mma M=128,K=16 with operands in shared memory never
 // takes less than ~100 cycles (A-operand fetch), whatever N is; it only reaches the tensor peak for N >= 192.
@@ -1472,18 +1774,23 @@ int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, fl
     Wg3Params p;
     memset(&p, 0, sizeof(p));
     int rc;
-    const bool wide = (C % 128 == 0) && (O % 128 == 0) && !g_wgrad_narrow;
-    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kWgPitch, wide ? kWgTH : kWgTH + 2)) < 0) return rc;
+    const bool wide = (C % 128 == 0) && (O % 128 == 0) && g_wgrad_narrow != 1;
+    const bool wide256 = wide && (O % 256 == 0) && g_wgrad_narrow != 2;
+    const bool rowpair = !wide && g_wgrad_narrow == 0;
+    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kWgPitch,
+                       wide256 ? kWg3XRows : wide ? kWgTH : rowpair ? kWg4XRows : kWgTH + 2)) < 0) return rc;
     if ((rc = make_map(&p.mapDY, dy, O, W, H, B, lddy, (long)W * lddy, (long)H * W * lddy, kWgTW, kWgTH)) < 0) return rc;
     p.cchunks = C / 64; p.oblocks = O / 64;
     p.tilesW = ceil_div(W, kWgTW); p.tilesH = ceil_div(H, kWgTH); p.nimg = B;
     p.ktiles_total = p.tilesW * p.tilesH * B;
     p.split_stride = (long long)O * 9 * C;
-    const long items = wide ? (long)(C / 128) * (O / 128) * 3 : (long)p.cchunks * p.oblocks;
+    const long items = wide256 ? (long)(C / 128) * (O / 256) * 5 : wide ? (long)(C / 128) * (O / 128) * 3
+                       : rowpair ? (long)p.cchunks * p.oblocks * 2 : (long)p.cchunks * p.oblocks;
+    const int slices_per_split = rowpair ? 2 : 1;        // the row-pair kernel writes the j = 0 / j = 1 halves separately
     long ns = (6L * num_sms() + items - 1) / items;
     if (ns > p.ktiles_total / 16) ns = p.ktiles_total / 16;
     if (ns < 1) ns = 1;
-    if (ns * p.split_stride > ws_floats) ns = ws_floats / p.split_stride;
+    if (ns * slices_per_split * p.split_stride > ws_floats) ns = ws_floats / (p.split_stride * slices_per_split);
     if (ns < 1) { set_error("tc_conv3x3_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
     p.nsplit = (int)ns;
     p.ws = ws; p.ldn = 9 * C; p.C = C;
@@ -1492,14 +1799,20 @@ int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, fl
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(tc_wgrad3x3_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWg2SmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc_wgrad3x3_wide256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWg3SmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc_wgrad3x3_rowpair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWg4SmemBytes);
         if (e != cudaSuccess) { set_error("tc_conv3x3_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
         attr_done = true;
     }
     long grid = items * ns < num_sms() ? items * ns : num_sms();
-    if (wide) tc_wgrad3x3_wide_kernel<<<(int)grid, kTcThreads, kWg2SmemBytes, (cudaStream_t)stream>>>(p);
+    if (wide256) tc_wgrad3x3_wide256_kernel<<<(int)grid, kTcThreads, kWg3SmemBytes, (cudaStream_t)stream>>>(p);
+    else if (wide) tc_wgrad3x3_wide_kernel<<<(int)grid, kTcThreads, kWg2SmemBytes, (cudaStream_t)stream>>>(p);
+    else if (rowpair) tc_wgrad3x3_rowpair_kernel<<<(int)grid, kTcThreads, kWg4SmemBytes, (cudaStream_t)stream>>>(p);
     else tc_wgrad3x3_kernel<<<(int)grid, kTcThreads, kWgSmemBytes, (cudaStream_t)stream>>>(p);
     rc = check_launch("tc_conv3x3_wgrad");
-    return rc < 0 ? rc : p.nsplit;
+    return rc < 0 ? rc : p.nsplit * slices_per_split;
 }
 
 // the generic (one box per tap) kernel, kept for cross-checks

@@ -26,12 +26,14 @@ def main():
     ap.add_argument("--no-halo", action="store_true", help="narrow layers through the generic one-box-per-tap kernel")
     ap.add_argument("--convT", action="store_true", help="benchmark the four ConvTranspose2d(k2,s2) layers instead")
     ap.add_argument("--pixn-cluster", type=int, default=2, help="CTAs per cluster sharing weights by TMA multicast (1|2)")
+    ap.add_argument("--wgrad-mode", type=int, default=0, help="0 auto, 1 narrow kernel everywhere, 2 no 256-wide tap-pair kernel")
     ap.add_argument("--no-pixn", action="store_true", help="narrow layers through the pixels-on-M generic kernel")
     ap.add_argument("--dgrad", action="store_true", help="add the dgrad shapes (O -> C) of the narrow layers")
     a = ap.parse_args()
     lib = _lib.load()
     lib.unetca_tc_force_block_n(a.block_n)
     lib.unetca_tc_force_no_pixn(1 if a.no_pixn else 0)
+    lib.unetca_tc_force_wgrad_narrow(a.wgrad_mode)
     lib.unetca_tc_force_no_halo(1 if a.no_halo else 0)
     lib.unetca_tc_set_pixn_cluster(a.pixn_cluster)
     layers = LAYERS if a.layers == ["all"] else [tuple(int(v) for v in s.split(",")) for s in a.layers]
