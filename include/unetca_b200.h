@@ -50,6 +50,9 @@ void unetca_tc_set_pixn_cluster(int n);
 int unetca_im2col3x3_nchw(int dtype, const float* x, void* col, int B, int Cin, int H, int W, int Kpad, void* stream);
 int unetca_nchw_to_nhwc(int dtype, const float* x, void* y, int ld, int B, int C, int H, int W, void* stream);
 int unetca_nhwc_to_nchw(int dtype, const void* x, int ld, float* y, int B, int C, int H, int W, void* stream);
+/* device side of the reference's input preprocessing (UCA:200-210, 428-433): uint8 tile -> ToTensor (/255) ->
+ * Normalize(mean, std) fp32; uint8 mask -> ToTensor().long() int64 (255 -> 1, everything else -> 0) */
+int unetca_prep_u8(const uint8_t* img, const uint8_t* mask, float* out, long long* lab, long n, float mean, float stdv, void* stream);
 /* nn.Conv2d weight (O,C,3,3) -> wf [O][ldk] (k = tap*C + c, zero padded) and optional dgrad operand wd [C][9*O] */
 int unetca_pack_conv3x3_weight(int dtype, const float* w, void* wf, int ldk, void* wd, int O, int C, void* stream);
 /* nn.ConvTranspose2d weight (Cin,Cout,2,2) -> wf [4*Cout][Cin] and wd [Cin][4*Cout] */

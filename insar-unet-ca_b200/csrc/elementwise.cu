@@ -1200,6 +1200,34 @@ __global__ void confusion_finalize_kernel(const unsigned long long* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Device side of the reference's input preprocessing (UCA:200-210, 428-433): uint8 tile -> T.ToTensor() (/255) ->
+// T.Normalize([mean],[std]); uint8 mask -> T.ToTensor()(mask).long(), i.e. 255 -> 1 and everything else -> 0.
+// Same IEEE operations in the same order as torchvision, so the tensors are bit-identical; 16 pixels per thread.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) prep_u8_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask,
+                                                           float* __restrict__ out, long long* __restrict__ lab, long n,
+                                                           float mean, float stdv) {
+    const long i0 = ((long)blockIdx.x * kThreads + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    if (i0 + 16 <= n && ((reinterpret_cast<uintptr_t>(img + i0) | reinterpret_cast<uintptr_t>(mask + i0)) & 15) == 0) {
+        const uint4 a = *reinterpret_cast<const uint4*>(img + i0);
+        const uint4 m = *reinterpret_cast<const uint4*>(mask + i0);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, mw[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float v = (float)((aw[k >> 2] >> (8 * (k & 3))) & 0xff) / 255.f;
+            out[i0 + k] = (v - mean) / stdv;
+            lab[i0 + k] = (long long)((float)((mw[k >> 2] >> (8 * (k & 3))) & 0xff) / 255.f);
+        }
+    } else {
+        for (long i = i0; i < n && i < i0 + 16; ++i) {
+            out[i] = ((float)img[i] / 255.f - mean) / stdv;
+            lab[i] = (long long)((float)mask[i] / 255.f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // im2col of the (B,Cin,H,W) NCHW fp32 network input for the first 3x3 conv: col[p][tap*Cin + c], zero padded to
 // Kpad columns (K = 9*Cin is not a multiple of the MMA K; the padding exists only in this staging buffer).
 template <typename T, int CIN>
@@ -1658,6 +1686,15 @@ int unetca_confusion_counts(const float* logits, const long long* target, int nc
     confusion_kernel<<<nblk, kThreads, 0, st>>>(logits, target, nc, npix, HW, ignore_index, (unsigned long long*)parts);
     confusion_finalize_kernel<<<1, 128, 0, st>>>((const unsigned long long*)parts, nblk, (nc + 1) * nc, counts);
     return check_launch("confusion_counts");
+}
+
+// images/masks: n uint8 pixels each; out: n fp32 = ((x/255) - mean) / std; lab: n int64 = (long)(mask/255)
+int unetca_prep_u8(const uint8_t* img, const uint8_t* mask, float* out, long long* lab, long n, float mean, float stdv,
+                   void* stream) {
+    UNETCA_REQUIRE(n >= 0 && stdv != 0.f, "prep_u8: n=%ld std=%f", n, (double)stdv);
+    if (n == 0) return 0;
+    prep_u8_kernel<<<ceil_div(n, (long)kThreads * 16), kThreads, 0, (cudaStream_t)stream>>>(img, mask, out, lab, n, mean, stdv);
+    return check_launch("prep_u8");
 }
 
 static int nc_pad(int nc) { return nc <= 2 ? 2 : nc <= 4 ? 4 : 8; }

@@ -95,10 +95,45 @@ def run_metrics(ref):
     np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
 
 
+def run_dataset(ref):
+    """A miniature VOC tree (tests/golden/voc_mini) and what the reference's VOCSegDataset + transforms
+    (UCA:166-212, 428-433) return for it."""
+    import torchvision.transforms as T
+    from PIL import Image
+    root = os.path.join(OUT, "voc_mini")
+    for d in ("JPEGImages", "SegmentationClass", os.path.join("ImageSets", "Segmentation")):
+        os.makedirs(os.path.join(root, d), exist_ok=True)
+    rs = np.random.RandomState(5)
+    ids = {"train": ["t0", "t1", "t2", "t3"], "val": ["v0", "v1"]}
+    for split, names in ids.items():
+        with open(os.path.join(root, "ImageSets", "Segmentation", f"{split}.txt"), "w") as f:
+            f.write("\n".join(names) + "\n")
+        for n in names:
+            h, w = (24, 20) if n != "t3" else (32, 32)                   # t3 already has the target size
+            yy, xx = np.mgrid[0:h, 0:w]
+            img = (127 + 90 * np.sin(xx / 3.0 + rs.rand() * 6) * np.cos(yy / 4.0) + rs.randint(-20, 20, (h, w))).clip(0, 255)
+            Image.fromarray(img.astype(np.uint8), "L").save(os.path.join(root, "JPEGImages", f"{n}.jpg"), quality=92)
+            m = np.where(rs.rand(h, w) < 0.45, 255, 0).astype(np.uint8)
+            m[rs.rand(h, w) < 0.05] = 128                                # a grey value: .long() truncates it to 0
+            Image.fromarray(m, "L").save(os.path.join(root, "SegmentationClass", f"{n}.png"))
+    S = 32
+    tf = T.Compose([T.Resize((S, S)), T.ToTensor(), T.Normalize(mean=[0.5], std=[0.5])])
+    out = {}
+    for split in ids:
+        ds = ref.VOCSegDataset(voc_root=root, image_size=S, image_set=split, transforms=tf)
+        for i, n in enumerate(ds.ids):
+            img, mask = ds[i]
+            out[f"img:{n}"] = img.numpy()
+            out[f"mask:{n}"] = mask.numpy()
+    np.savez_compressed(os.path.join(OUT, "voc_mini_expected.npz"), **out)
+    print("dataset fixture:", root, len(out) // 2, "items")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
     run_metrics(ref)
+    run_dataset(ref)
     run_case(ref, "unetca_se_b2_32", seed=0, B=2, H=32, W=32, use_se=True, full=True)
     run_case(ref, "unet_plain_b2_32", seed=1, B=2, H=32, W=48, use_se=False, full=True)
     run_case(ref, "unetca_se_b4_256", seed=0, B=4, H=256, W=256, use_se=True, full=False)   # BASELINE configs[0]

@@ -426,3 +426,30 @@ def test_metrics_on_device_match_reference(golden_dir):
         for c in range(2):
             assert counts[r, c].item() == ((ma == r) & (pr == c)).sum().item()
     assert counts.sum().item() == (ma != 255).sum().item()
+
+
+def test_device_input_pipeline_matches_reference(golden_dir):
+    """f-3: uint8 batches -> pinned H2D on a side stream -> unetca_prep_u8 == the reference's ToTensor/Normalize and
+    mask ToTensor().long() tensors, bit for bit (tests/golden/voc_mini_expected.npz from the reference's dataset)."""
+    import os
+    from torch.utils.data import DataLoader
+    from unetca_b200 import data
+    root = os.path.join(golden_dir, "voc_mini")
+    g = np.load(os.path.join(golden_dir, "voc_mini_expected.npz"))
+    ds = data.VOCSegDataset(root, 32, image_set="train", raw=True)
+    loader = DataLoader(ds, batch_size=2, shuffle=False, num_workers=0)
+    seen = 0
+    for bi, (x, y) in enumerate(data.DevicePrefetcher(loader, torch.device("cuda"))):
+        assert x.is_cuda and x.dtype == torch.float32 and x.shape == (2, 1, 32, 32)
+        assert y.is_cuda and y.dtype == torch.int64 and y.shape == (2, 32, 32)
+        for k in range(2):
+            name = ds.ids[bi * 2 + k]
+            assert np.array_equal(x[k].cpu().numpy(), g[f"img:{name}"]), name
+            assert np.array_equal(y[k].cpu().numpy(), g[f"mask:{name}"]), name
+            seen += 1
+    assert seen == 4
+    # odd sizes / unaligned tails and every byte value
+    u = torch.arange(256, dtype=torch.uint8).repeat(5)[:1237].reshape(1, 1, 1237).cuda()
+    xi, yi = data.prep_u8(u, u)
+    ref = ((u.cpu().float() / 255.0) - 0.5) / 0.5
+    assert torch.equal(xi.cpu()[:, 0], ref) and torch.equal(yi.cpu(), (u.cpu().float() / 255.0).long())
