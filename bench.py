@@ -115,6 +115,15 @@ def _work(name, a, e, cin):
     if name == "unetca_conv3x3_wgrad":
         B, H, W, C, O = a[7:12]
         return "tensor", 2.0 * B * H * W * 9 * C * O, 0
+    if name == "unetca_first_pairs_fwd":
+        B, H, W, O = a[5:9]
+        return "tensor", 2.0 * B * H * W * O * 9 * cin, 0
+    if name == "unetca_first_pairs_wgrad":
+        B, H, W, Cin, O = a[6:11]
+        return "tensor", 2.0 * B * H * W * 9 * Cin * O, 0
+    if name == "unetca_im2col_pairs":
+        B, Cin, H, W = a[3:7]
+        return "hbm", 0, B * H * W * Cin * 4 + B * (H // 2) * W * 64 * e
     if name == "unetca_gemm_nt":
         M, N = a[7], a[8]
         return "tensor", 2.0 * M * N * 9 * cin, 0

@@ -66,6 +66,14 @@ int unetca_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk
  * (csrc/conv_tc.cu, tc_conv3x3_pixn_kernel); w_pair [2*O][12*C] = unetca_pack_conv3x3_pair(w [O][ld]).  bf16 only. */
 int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream);
 int unetca_pack_conv3x3_pair(int dtype, const void* w, int ld, void* w_pair, int rows, int C, void* stream);
+/* first conv (Cin <= 5, H even) in the row-pair layout of the tcgen05 path (bf16): one im2col row per pixel PAIR
+ * (rows 2i, 2i+1 of a column) holding their shared 4x3 patch, colp [B*(H/2)*W][64]; pair-packed filter wp [2*O][64];
+ * forward = one GEMM with 128x256x16 MMAs (+ BatchNorm partial sums), weight gradient from the same colp */
+int unetca_im2col_pairs(int dtype, const float* x, void* colp, int B, int Cin, int H, int W, void* stream);
+int unetca_pack_first_pairs(int dtype, const float* w, void* wp, int O, int Cin, void* stream);
+int unetca_first_pairs_fwd(int dtype, const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O, float* stat_parts, int* nparts, void* stream);
+int unetca_first_pairs_wgrad(int dtype, const void* dy, int lddy, const void* colp, float* ws, long ws_floats, int B, int H, int W, int Cin, int O, float* dw, void* stream);
+int unetca_first_pairs_fold(const float* ws, int nsplit, int O, int Cin, float* dw, void* stream);
 /* first conv (K = 9*Cin): out[m][n] = sum_k A[m][k] * Bw[n][k] over im2col rows */
 int unetca_gemm_nt(int dtype, const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K, float* stat_parts, int* nparts, void* stream);
 /* weight gradient of conv3x3 -> dw (O,C,3,3) fp32; ws: split-K scratch (ws_floats floats) */
@@ -132,6 +140,8 @@ int unetca_confusion_counts(const float* logits, const long long* target, int nc
 int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, void* stream);
 int unetca_tc_conv3x3_fwd_paired(const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, void* stream);
 int unetca_tc_pack_pair(const void* w, int ld, void* w_pair, int rows, int C, void* stream);
+int unetca_tc_first_pairs_fwd(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O, float* stat_parts, void* stream);
+int unetca_tc_first_pairs_wgrad(const void* dy, int lddy, const void* colp, float* ws, long ws_floats, int B, int H, int W, int O, void* stream);
 int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K, float* stat_parts, void* stream);
 int unetca_tc_convT_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h, int wd, int Cin, int Cout, void* stream);
 int unetca_tc_convT_dgrad(const void* dout, int ldd, const void* wdg, void* dx, int ldx, int B, int h, int wd, int Cin, int Cout, void* stream);

@@ -78,7 +78,7 @@ def last_error() -> str:
 # kernels launched per entry point (default 1) — used for the launch count bench.py reports
 _LAUNCHES = {
     "unetca_conv3x3_wgrad": 2, "unetca_im2col_wgrad": 2, "unetca_convT2x2_wgrad": 2, "unetca_chan_sum": 2,
-    "unetca_se_fc_bwd": 2, "unetca_se_fc_bwd_fused": 2, "unetca_outc_bwd": 2, "unetca_cross_entropy": 2,
+    "unetca_se_fc_bwd": 2, "unetca_se_fc_bwd_fused": 2, "unetca_first_pairs_wgrad": 2, "unetca_outc_bwd": 2, "unetca_cross_entropy": 2,
 }
 launch_count = 0
 _hook = None

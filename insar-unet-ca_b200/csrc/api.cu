@@ -10,6 +10,9 @@ extern "C" {
 int unetca_tc_conv3x3_fwd(const void*, int, const void*, int, void*, int, int, int, int, int, int, float*, void*);
 int unetca_tc_conv3x3_fwd_paired(const void*, int, const void*, void*, int, int, int, int, int, int, float*, void*);
 int unetca_tc_pack_pair(const void*, int, void*, int, int, void*);
+int unetca_tc_first_pairs_fwd(const void*, const void*, void*, int, int, int, int, int, float*, void*);
+int unetca_tc_first_pairs_wgrad(const void*, int, const void*, float*, long, int, int, int, int, void*);
+int unetca_first_pairs_fold(const float*, int, int, int, float*, void*);
 int unetca_tc_gemm_nt(const void*, int, const void*, int, void*, int, long, int, int, float*, void*);
 int unetca_tc_convT_fwd(const void*, int, const void*, const float*, void*, int, int, int, int, int, int, void*);
 int unetca_tc_convT_dgrad(const void*, int, const void*, void*, int, int, int, int, int, int, void*);
@@ -68,6 +71,23 @@ int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_p
 int unetca_pack_conv3x3_pair(int dtype, const void* w, int ld, void* w_pair, int rows, int C, void* stream) {
     if (dtype != UNETCA_DTYPE_BF16) { unetca::set_error("pack_conv3x3_pair: bf16 only"); return UNETCA_ERR_UNSUPPORTED; }
     return unetca_tc_pack_pair(w, ld, w_pair, rows, C, stream);
+}
+
+// First conv through the pixel-pair layout (bf16 tensor-core path only; see unetca_im2col_pairs).
+int unetca_first_pairs_fwd(int dtype, const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O,
+                           float* stat_parts, int* nparts, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("first_pairs_fwd: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int rc = unetca_tc_first_pairs_fwd(colp, wp, y, ldy, B, H, W, O, stat_parts, stream);
+    if (rc < 0) return rc;
+    if (nparts) *nparts = rc;
+    return 0;
+}
+int unetca_first_pairs_wgrad(int dtype, const void* dy, int lddy, const void* colp, float* ws, long ws_floats, int B, int H,
+                             int W, int Cin, int O, float* dw, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("first_pairs_wgrad: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int ns = unetca_tc_first_pairs_wgrad(dy, lddy, colp, ws, ws_floats, B, H, W, O, stream);
+    if (ns < 0) return ns;
+    return unetca_first_pairs_fold(ws, ns, O, Cin, dw, stream);
 }
 
 // out[m][n] = sum_k A[m][k] * Bw[n][k]  (first conv on im2col rows, K = Kpad)

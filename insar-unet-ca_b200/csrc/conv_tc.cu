@@ -1562,6 +1562,27 @@ static int make_map5(CUtensorMap* m, const void* base, long C, long W, long H, l
 static int g_no_pixn = 0;
 static int g_pixn_cluster = 2;     // CTAs per cluster sharing the weight operand by TMA multicast (1 or 2)
 
+static int launch_pixn_kernel(const PixNParams& p, int CL, cudaStream_t st, const char* what) {
+    const long num_tiles = (long)p.tilesW * p.tilesI * p.nimg;
+    const long num_work = ((num_tiles + CL - 1) / CL) * p.num_m_blocks;          // items per cluster-walk
+    long grid = num_work * CL < num_sms() ? num_work * CL : (num_sms() / CL) * CL;
+    if (grid < CL) grid = CL;
+    if (CL == 1) {
+        tc_conv3x3_pixn_kernel<1><<<(int)grid, kTcThreads, kPnSmemBytes, st>>>(p);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kPnSmemBytes; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv3x3_pixn_kernel<2>, p);
+        if (e != cudaSuccess) { set_error("%s: cluster launch: %s", what, cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+    }
+    int rc = check_launch(what);
+    return rc < 0 ? rc : (int)grid;
+}
+
 // w: P == 1: packed filter [O][9*C];  P == 2: pair-packed filter [2*O][12*C] (unetca_pack_conv3x3_pair)
 static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
                        int P, float* stat_parts, cudaStream_t st) {
@@ -1597,24 +1618,38 @@ static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, 
         if (e != cudaSuccess) { set_error("tc_conv3x3 (pixn): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
         attr_done = true;
     }
-    const long num_tiles = (long)p.tilesW * p.tilesI * B;
-    const long num_work = ((num_tiles + CL - 1) / CL) * p.num_m_blocks;          // items per cluster-walk
-    long grid = num_work * CL < num_sms() ? num_work * CL : (num_sms() / CL) * CL;
-    if (grid < CL) grid = CL;
-    if (CL == 1) {
-        tc_conv3x3_pixn_kernel<1><<<(int)grid, kTcThreads, kPnSmemBytes, st>>>(p);
-    } else {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kPnSmemBytes; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv3x3_pixn_kernel<2>, p);
-        if (e != cudaSuccess) { set_error("tc_conv3x3 (pixn): cluster launch: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+    return launch_pixn_kernel(p, CL, st, "tc_conv3x3_fwd (pixn)");
+}
+
+// First conv in the row-pair layout (see elementwise.cu: im2col_pairs_kernel): one GEMM over the pixel-pair rows
+// colp [B*(H/2)*W][64] with the pair-packed filter wp [2*O][64] through the pixels-on-N kernel (one "tap", one chunk).
+static int launch_first_pairs(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O,
+                              float* stat_parts, cudaStream_t st) {
+    PixNParams p;
+    memset(&p, 0, sizeof(p));
+    const int HP = H / 2;
+    int TW = 0, TI = 0;
+    pick_tile(HP, W, 256, &TW, &TI);
+    int rc;
+    if ((rc = make_map5(&p.mapX, colp, 64, W, HP, B, 64, 1, TW, TI, true)) < 0) return rc;       // pair rows as an "image"
+    const int CL = g_pixn_cluster;
+    if ((rc = make_map(&p.mapW, wp, 64, 2L * O, 1, 1, 64, 2L * O * 64, 2L * O * 64, 128 / CL, 1)) < 0) return rc;
+    if ((rc = make_map5(&p.mapOut, y, O, W, H, B, ldy, 2, TW, TI, false)) < 0) return rc;        // rows 2i+j of the output
+    p.tilesW = ceil_div(W, TW); p.tilesI = ceil_div(HP, TI); p.nimg = B;
+    p.TW = TW; p.TI = TI; p.HP = HP; p.W = W; p.P = 2;
+    p.twShift = 0; while ((1 << p.twShift) < TW) ++p.twShift;
+    p.ntaps = 1; p.cchunks = 1;
+    p.num_m_blocks = O / 64;
+    p.stat_parts = stat_parts; p.N = O;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
+        if (e != cudaSuccess) { set_error("first_pairs: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
     }
-    rc = check_launch("tc_conv3x3_fwd (pixn)");
-    return rc < 0 ? rc : (int)grid;
+    return launch_pixn_kernel(p, CL, st, "tc_first_pairs_fwd");
 }
 
 static void set_taps3x3(TcParams& p) {
@@ -1866,6 +1901,43 @@ int unetca_tc_gemm_tn(const void* A, int lda, const void* Bm, int ldb, float* ws
     if (p.nsplit < 1) { set_error("tc_gemm_tn: workspace too small"); return UNETCA_ERR_WORKSPACE; }
     p.ws = ws; p.ldn = N; p.store_transposed = 1; p.m_valid = N;
     int r2 = launch_tc_n<true>(BN, p, (long)p.num_m_blocks * p.num_n_blocks * p.nsplit, (cudaStream_t)stream, "tc_gemm_tn");
+    return r2 < 0 ? r2 : p.nsplit;
+}
+
+// first conv forward through the row-pair layout: colp from unetca_im2col_pairs, wp from unetca_pack_first_pairs
+int unetca_tc_first_pairs_fwd(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O,
+                              float* stat_parts, void* stream) {
+    UNETCA_REQUIRE(O % 64 == 0 && O <= 1024 && H % 2 == 0, "tc_first_pairs_fwd: O=%d H=%d", O, H);
+    return launch_first_pairs(colp, wp, y, ldy, B, H, W, O, stat_parts, (cudaStream_t)stream);
+}
+
+// ws[z][k (64 rows)][(j, o)] = sum over pixel pairs of colp[pair][k] * dy[(2i+j, x)][o]; returns nsplit
+int unetca_tc_first_pairs_wgrad(const void* dy, int lddy, const void* colp, float* ws, long ws_floats, int B, int H, int W,
+                                int O, void* stream) {
+    UNETCA_REQUIRE(O % 64 == 0 && H % 2 == 0, "tc_first_pairs_wgrad: O=%d H=%d", O, H);
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    const int HP = H / 2;
+    int TW = 0, TH = 0;
+    pick_tile(HP, W, 64, &TW, &TH);
+    int rc;
+    if ((rc = make_map(&p.mapA[0], colp, 64, W, HP, B, 64, (long)W * 64, (long)HP * W * 64, TW, TH)) < 0) return rc;
+    for (int j = 0; j < 2; ++j) {
+        const bf16* base = (const bf16*)dy + (long)j * W * lddy;
+        if ((rc = make_map(&p.mapB[j], base, O, W, HP, B, lddy, 2L * W * lddy, (long)H * W * lddy, TW, TH)) < 0) return rc;
+    }
+    const int BN = pick_block_n(2 * O);
+    p.tilesW = ceil_div(W, TW); p.tilesH = ceil_div(HP, TH); p.nimg = B;
+    p.TW = TW; p.TH = TH; p.H = HP; p.W = W;
+    p.a_chunks = 1; p.a_cchunks = 1; p.b_chunks_per_map = O / 64;
+    p.num_m_blocks = 1;
+    p.num_n_blocks = 2 * O / BN;
+    p.ktiles_total = p.tilesW * p.tilesH * B;
+    p.split_stride = 64LL * 2 * O;
+    p.nsplit = pick_nsplit((long)p.num_n_blocks, p.ktiles_total, p.split_stride, ws_floats);
+    if (p.nsplit < 1) { set_error("tc_first_pairs_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+    p.ws = ws; p.ldn = 2 * O; p.store_transposed = 0; p.m_valid = 64;
+    int r2 = launch_tc_n<true>(BN, p, (long)p.num_n_blocks * p.nsplit, (cudaStream_t)stream, "tc_first_pairs_wgrad");
     return r2 < 0 ? r2 : p.nsplit;
 }
 

@@ -1262,6 +1262,76 @@ __global__ void __launch_bounds__(256) im2col3x3_small_kernel(const float* __res
     for (int e = 0; e < VEC; ++e) z[e] = 0.f;
     for (int j = (K + VEC - 1) / VEC; j < Kpad / VEC; ++j) store_vec(dst + j * VEC, z);
 }
+// ---------------------------------------------------------------------------------------------------------
+// First conv (Cin <= 5) in the row-pair layout of the tcgen05 path: instead of one im2col row of 9*Cin values per
+// pixel, one row per PIXEL PAIR (rows 2i, 2i+1 of column x) holding the 4 x 3 patch they share:
+//   colp[(b,i,x)][(vr*3 + kw)*Cin + c] = x[b, c, 2i + vr - 1, x + kw - 1]     (zero outside the image / beyond 12*Cin)
+// With the pair-packed filter  wp[(j,o)][(vr*3+kw)*Cin + c] = W[o][c][vr - j][kw]  (zero when vr - j is not 0..2) the
+// layer is ONE GEMM  out[(2i+j, x)][o] = sum_k wp[(j,o)][k] * colp[(b,i,x)][k]  with M = 128, N = 256 pixel pairs:
+// half the staging traffic of the per-pixel im2col and full-rate 128x256x16 MMAs.                      UCA:81
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, int CIN>
+__global__ void __launch_bounds__(256) im2col_pairs_kernel(const float* __restrict__ x, T* __restrict__ colp, int B, int H,
+                                                           int W) {
+    constexpr int VEC = VecTraits<T>::N;
+    constexpr int K = 12 * CIN;
+    const int HP = H >> 1;
+    const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= (long)B * HP * W) return;
+    const int xw = (int)(n % W), i = (int)((n / W) % HP);
+    const long b = n / ((long)W * HP);
+    float v[K];
+#pragma unroll
+    for (int vr = 0; vr < 4; ++vr) {
+        const int hh = 2 * i + vr - 1;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int ww = xw + kw - 1;
+            const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+                v[(vr * 3 + kw) * CIN + c] = in ? __ldg(x + ((b * CIN + c) * H + hh) * W + ww) : 0.f;
+        }
+    }
+    T* dst = colp + n * 64;
+#pragma unroll
+    for (int j = 0; j < 64 / VEC; ++j) {
+        float o[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) o[e] = (j * VEC + e) < K ? v[(j * VEC + e) < K ? (j * VEC + e) : 0] : 0.f;
+        store_vec(dst + j * VEC, o);
+    }
+}
+
+// wp[(g*128 + j*64 + o)][k], k = (vr*3+kw)*Cin + c < 12*Cin (zero padded to 64), from the OIHW fp32 filter
+template <typename T>
+__global__ void pack_first_pairs_kernel(const float* __restrict__ w, T* __restrict__ wp, int O, int Cin) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2L * O * 64) return;
+    const int k = (int)(i % 64), row = (int)(i / 64);
+    const int g = row / 128, j = (row / 64) & 1, o = g * 64 + (row & 63);
+    float val = 0.f;
+    if (k < 12 * Cin) {
+        const int c = k % Cin, v = k / Cin, vr = v / 3, kw = v % 3, kh = vr - j;
+        if (kh >= 0 && kh <= 2) val = w[((long)(o * Cin + c) * 3 + kh) * 3 + kw];
+    }
+    wp[i] = from_float<T>(val);
+}
+
+// dW[o][c][kh][kw] = sum_z sum_j ws[z][((kh+j)*3 + kw)*Cin + c][j*O + o]      (ws rows = k (64), columns = (j, o))
+__global__ void first_pairs_fold_kernel(const float* __restrict__ ws, int nsplit, int O, int Cin, float* __restrict__ dw) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= O * Cin * 9) return;
+    const int kw = i % 3, kh = (i / 3) % 3, c = (i / 9) % Cin, o = i / (9 * Cin);
+    float t = 0.f;
+    for (int z = 0; z < nsplit; ++z) {
+        const float* wz = ws + (long)z * 64 * 2 * O;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) t += wz[(long)(((kh + j) * 3 + kw) * Cin + c) * 2 * O + j * O + o];
+    }
+    dw[i] = t;
+}
+
 template <typename T>
 __global__ void im2col3x3_nchw_kernel(const float* __restrict__ x, T* __restrict__ col, int B, int Cin, int H, int W,
                                       int Kpad) {
@@ -1695,6 +1765,37 @@ int unetca_prep_u8(const uint8_t* img, const uint8_t* mask, float* out, long lon
     if (n == 0) return 0;
     prep_u8_kernel<<<ceil_div(n, (long)kThreads * 16), kThreads, 0, (cudaStream_t)stream>>>(img, mask, out, lab, n, mean, stdv);
     return check_launch("prep_u8");
+}
+
+// pixel-pair im2col of the NCHW fp32 network input (Cin <= 5, H even): colp [B*(H/2)*W][64]
+int unetca_im2col_pairs(int dtype, const float* x, void* colp, int B, int Cin, int H, int W, void* stream) {
+    UNETCA_REQUIRE(Cin >= 1 && Cin <= 5 && H % 2 == 0, "im2col_pairs: Cin=%d (1..5), H=%d (even)", Cin, H);
+    DISPATCH_T(dtype, {
+        const long n = (long)B * (H / 2) * W;
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (Cin) {
+            case 1: im2col_pairs_kernel<T, 1><<<ceil_div(n, 256), 256, 0, st>>>(x, (T*)colp, B, H, W); break;
+            case 2: im2col_pairs_kernel<T, 2><<<ceil_div(n, 256), 256, 0, st>>>(x, (T*)colp, B, H, W); break;
+            case 3: im2col_pairs_kernel<T, 3><<<ceil_div(n, 256), 256, 0, st>>>(x, (T*)colp, B, H, W); break;
+            case 4: im2col_pairs_kernel<T, 4><<<ceil_div(n, 256), 256, 0, st>>>(x, (T*)colp, B, H, W); break;
+            default: im2col_pairs_kernel<T, 5><<<ceil_div(n, 256), 256, 0, st>>>(x, (T*)colp, B, H, W); break;
+        }
+    });
+    return check_launch("im2col_pairs");
+}
+
+// pair-packed first-conv filter wp [2*O][64] from the nn.Conv2d weight (O, Cin, 3, 3)
+int unetca_pack_first_pairs(int dtype, const float* w, void* wp, int O, int Cin, void* stream) {
+    UNETCA_REQUIRE(O % 64 == 0 && Cin >= 1 && Cin <= 5, "pack_first_pairs: O=%d Cin=%d", O, Cin);
+    DISPATCH_T(dtype, {
+        pack_first_pairs_kernel<T><<<ceil_div(2L * O * 64, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wp, O, Cin);
+    });
+    return check_launch("pack_first_pairs");
+}
+
+int unetca_first_pairs_fold(const float* ws, int nsplit, int O, int Cin, float* dw, void* stream) {
+    first_pairs_fold_kernel<<<ceil_div((long)O * Cin * 9, 256), 256, 0, (cudaStream_t)stream>>>(ws, nsplit, O, Cin, dw);
+    return check_launch("first_pairs_fold");
 }
 
 static int nc_pad(int nc) { return nc <= 2 ? 2 : nc <= 4 ? 4 : 8; }

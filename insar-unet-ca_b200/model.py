@@ -134,6 +134,10 @@ class _Engine:
             # narrow outputs (a multiple of 64 but not of 128 channels) run through the row-pair layout of the
             # tcgen05 path, which wants the filter re-expressed over 4x3 virtual taps
             wfp = wdp = None
+            if dt == _lib.BF16 and first and C <= 5:
+                # first conv: pixel-pair layout (unetca_im2col_pairs), filter over the 4x3 patch a row pair shares
+                wfp = torch.empty(2 * O, 64, dtype=tdt, device=w.device)
+                _lib.call("unetca_pack_first_pairs", dt, _ptr(w), _ptr(wfp), O, C, _stream())
             if dt == _lib.BF16 and not first:
                 if O % 128:
                     wfp = torch.empty(2 * O, 12 * C, dtype=tdt, device=w.device)
@@ -162,6 +166,11 @@ def _conv3x3(dt, x, ldx, w, ldk, w_pair, y, ldy, B, H, W, C, O, sp, nparts, st):
         _lib.call("unetca_conv3x3_fwd_paired", dt, _ptr(x), ldx, _ptr(w_pair), _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
     else:
         _lib.call("unetca_conv3x3_fwd", dt, _ptr(x), ldx, _ptr(w), ldk, _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
+
+
+def sv_pairs(col, B, H, W):
+    """True when `col` is the pixel-pair im2col buffer (one row per pair of rows) rather than the per-pixel one."""
+    return col is not None and col.shape[0] == B * (H // 2) * W and H % 2 == 0
 
 
 def _check_input(model, x):
@@ -214,7 +223,9 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
     # ---- conv1 -> BN -> ReLU
     wf1, _, ldk1, wfp1, _ = eng.conv_w(blk.conv1, dt, tdt, blk.first)
     y1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
-    if blk.first:
+    if blk.first and sv_pairs(col, B, Hl, Wl):
+        _lib.call("unetca_first_pairs_fwd", dt, _ptr(col), _ptr(wfp1), _ptr(y1), O, B, Hl, Wl, O, sp, ctypes.byref(nparts), st)
+    elif blk.first:
         _lib.call("unetca_gemm_nt", dt, _ptr(col), col.shape[1], _ptr(wf1), ldk1, _ptr(y1), O, npix, O, col.shape[1],
                   sp, ctypes.byref(nparts), st)
     else:
@@ -272,9 +283,13 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
     xf = x.detach()
     if xf.dtype != torch.float32 or not xf.is_contiguous():
         xf = xf.float().contiguous()
-    Kpad = ((9 * Cin + 63) // 64) * 64
-    col = torch.empty(B * H * W, Kpad, dtype=tdt, device=dev)
-    _lib.call("unetca_im2col3x3_nchw", dt, _ptr(xf), _ptr(col), B, Cin, H, W, Kpad, st)
+    if dt == _lib.BF16 and Cin <= 5 and H % 2 == 0 and _lib.load().unetca_get_conv_impl() == 0:
+        col = torch.empty(B * (H // 2) * W, 64, dtype=tdt, device=dev)           # one row per pixel pair (rows 2i, 2i+1)
+        _lib.call("unetca_im2col_pairs", dt, _ptr(xf), _ptr(col), B, Cin, H, W, st)
+    else:
+        Kpad = ((9 * Cin + 63) // 64) * 64
+        col = torch.empty(B * H * W, Kpad, dtype=tdt, device=dev)
+        _lib.call("unetca_im2col3x3_nchw", dt, _ptr(xf), _ptr(col), B, Cin, H, W, Kpad, st)
 
     sv = SimpleNamespace(enc=[], dec=[], up_in=[], cat=[], pos=[], B=B, H=H, W=W, Hs=Hs, Ws=Ws)
     cat = [torch.empty(B, Hs[l], Ws[l], 2 * _WIDTHS[l], dtype=tdt, device=dev) for l in range(4)]
@@ -415,7 +430,10 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
     del da1
     # ---- conv1 wgrad (+ dgrad)
     dw = G.alloc(pre + ".0.weight", blk.conv1.weight)
-    if blk.first:
+    if blk.first and sv_pairs(sv.col, B, Hl, Wl):
+        _lib.call("unetca_first_pairs_wgrad", dt, _ptr(dy1), O, _ptr(sv.col), _ptr(ws), ws.numel(), B, Hl, Wl, C, O,
+                  _ptr(dw), st)
+    elif blk.first:
         _lib.call("unetca_im2col_wgrad", dt, _ptr(dy1), O, _ptr(sv.col), sv.col.shape[1], _ptr(ws), ws.numel(), npix, C, O,
                   _ptr(dw), st)
     else:

@@ -400,6 +400,38 @@ def test_first_conv_im2col(dt, impl):
     assert relerr(dw.cpu(), wr.grad) < 2e-3
 
 
+@pytest.mark.parametrize("B,Cin,H,W", [(2, 3, 16, 24), (1, 1, 34, 20), (3, 3, 64, 64)])
+def test_first_conv_pixel_pairs(B, Cin, H, W):
+    """First conv through the row-pair layout: pixel-pair im2col + pair-packed filter + one pixels-on-N GEMM (forward,
+    BatchNorm partial sums) and the weight gradient from the same pair rows, vs conv2d on the bf16-rounded operands."""
+    rs = np.random.RandomState(16)
+    call("unetca_set_conv_impl", 0)
+    dt, O = BF16, 64
+    x = torch.from_numpy(rs.standard_normal((B, Cin, H, W)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((O, Cin, 3, 3)) / np.sqrt(9 * Cin)).astype(np.float32))
+    dy = torch.from_numpy(rs.standard_normal((B, O, H, W)).astype(np.float32))
+    xr, wr, dyr = rounded(x, dt), rounded(w, dt).requires_grad_(True), rounded(dy, dt)
+    ref = F.conv2d(xr, wr, None, padding=1)
+    ref.backward(dyr)
+    colp = torch.empty(B * (H // 2) * W, 64, dtype=TDT[dt], device="cuda")
+    call("unetca_im2col_pairs", dt, ptr(x.cuda()), ptr(colp), B, Cin, H, W, stream())
+    wp = torch.empty(2 * O, 64, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_first_pairs", dt, ptr(w.cuda()), ptr(wp), O, Cin, stream())
+    y = torch.full((B, H, W, O), float("nan"), dtype=TDT[dt], device="cuda")
+    parts = parts_buf(B)
+    n = cint()
+    call("unetca_first_pairs_fwd", dt, ptr(colp), ptr(wp), ptr(y), O, B, H, W, O, ptr(parts), ctypes.byref(n), stream())
+    got = from_nhwc(y)
+    assert relerr(got, ref.detach()) < TOL[dt]
+    st = parts[: n.value * 2 * O].view(n.value, 2, O).sum(0).cpu()
+    assert relerr(st[0], got.sum((0, 2, 3))) < 1e-3 and relerr(st[1], (got * got).sum((0, 2, 3))) < 1e-3
+    dyd = to_nhwc(dy, dt)
+    ws = torch.empty(4 * 1024 * 1024, device="cuda")
+    dw = torch.empty(O, Cin, 3, 3, device="cuda")
+    call("unetca_first_pairs_wgrad", dt, ptr(dyd), O, ptr(colp), ptr(ws), ws.numel(), B, H, W, Cin, O, ptr(dw), stream())
+    assert relerr(dw.cpu(), wr.grad) < 2e-3
+
+
 def test_metrics_on_device_match_reference(golden_dir):
     """f-1: compute_metrics (UCA:214-269) from the on-device label-by-prediction table == the reference's numbers."""
     import os
