@@ -231,3 +231,27 @@ def test_tiled_inference_matches_per_tile_reference():
     nbad = int((ref != full).sum())
     assert nbad == 0, f"{nbad} of {H * W} mask pixels differ from the per-tile reference"
     assert m.training is False
+
+
+@pytest.mark.parametrize("prec,ltol", [("fp32", 1e-3), ("bf16", 4e-2)])
+def test_reference_main_configuration_one_channel_three_classes(prec, ltol):
+    """The reference's own construction is UNet(in_channels=1, ...) (UCA:464); also a 3-class head.  Against the pinned
+    oracle port on seeded inputs: logits, loss, global gradient norm, bit-exact argmax mask in fp32 mode."""
+    import unetca_b200
+    sd = port.make_state_dict(seed=11, in_channels=1, num_classes=3)
+    x, y = port.make_batch(11, 2, 48, 64, in_channels=1, num_classes=3)
+    ref_logits, ref_loss, ref_grads, _, _ = port.train_step_grads(sd, x, y)
+    m = unetca_b200.UNet(1, 3, use_se=True).cuda().set_precision(prec)
+    m.load_state_dict(sd)
+    m.train()
+    logits = m(x.cuda())
+    loss = torch.nn.CrossEntropyLoss(ignore_index=255)(logits, y.cuda())
+    loss.backward()
+    assert logits.shape == (2, 3, 48, 64)
+    assert _rel(logits.detach().cpu(), ref_logits) < ltol
+    assert abs(loss.item() - ref_loss.item()) / ref_loss.item() < 1e-2
+    gn = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in m.parameters())).item()
+    rgn = torch.sqrt(sum((g ** 2).sum() for g in ref_grads.values())).item()
+    assert abs(gn - rgn) / rgn < 1e-2
+    if prec == "fp32":
+        assert torch.equal(torch.max(logits.detach(), 1)[1].cpu(), torch.max(ref_logits, 1)[1])
