@@ -36,9 +36,11 @@ def main():
     peak = peak_gbs()
     rows = []
     for dt, tdt, e in ((_lib.BF16, torch.bfloat16, 2), (_lib.F32, torch.float32, 4)):
-        for C in (64, 128, 256, 512, 1024):
-            for S in (32, 64, 128, 256, 512):
-                B = max(1, -(-(256 << 20) // (C * S * S * e)))
+        grid = [(C, S, max(1, -(-(256 << 20) // (C * S * S * e)))) for C in (64, 128, 256, 512, 1024)
+                for S in (32, 64, 128, 256, 512)]
+        grid += [(C, S, 64) for C, S in ((64, 512), (128, 256), (256, 128), (512, 64), (1024, 32))]   # the model's own layers
+        for C, S, B in grid:
+            if True:
                 if B * C * S * S * e > (6 << 30):
                     continue
                 N = B * C * S * S
@@ -49,15 +51,16 @@ def main():
                 scale, shift = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
                 w1 = torch.randn(C // 16, C, device="cuda") / C ** 0.5
                 w2 = torch.randn(C, C // 16, device="cuda") / (C // 16) ** 0.5
-                parts = torch.empty(_lib.load().unetca_max_parts(B) * 2048, device="cuda")
+                parts = torch.empty(_lib.load().unetca_max_parts(B) * 4096, device="cuda")
                 p_, z_, s_ = torch.empty(B, C, device="cuda"), torch.empty(B, C // 16, device="cuda"), torch.empty(B, C, device="cuda")
                 n = ctypes.c_int(0)
 
                 def se(pool):
-                    _lib.call("unetca_bn_relu", dt, y.data_ptr(), C, None, 0, B, S * S, C, scale.data_ptr(), shift.data_ptr(),
+                    # the production sequence of model._double_conv_fwd: squeeze partial sums -> FC chain -> scale (+ pool)
+                    _lib.call("unetca_se_squeeze", dt, y.data_ptr(), C, B, S * S, C, scale.data_ptr(), shift.data_ptr(),
                               parts.data_ptr(), ctypes.byref(n), st())
-                    _lib.call("unetca_se_fc", parts.data_ptr(), n.value, B, C, C // 16, S * S, w1.data_ptr(), w2.data_ptr(),
-                              p_.data_ptr(), z_.data_ptr(), s_.data_ptr(), st())
+                    _lib.call("unetca_se_fc3", parts.data_ptr(), n.value, B, C, C // 16, S * S, w1.data_ptr(), w2.data_ptr(),
+                              scale.data_ptr(), shift.data_ptr(), None, p_.data_ptr(), z_.data_ptr(), s_.data_ptr(), None, st())
                     _lib.call("unetca_se_scale_pool", dt, y.data_ptr(), C, out.data_ptr(), C, pooled.data_ptr() if pool else None,
                               C if pool else 0, pos.data_ptr() if pool else None, B, S, S, C, scale.data_ptr(), shift.data_ptr(),
                               s_.data_ptr(), st())
