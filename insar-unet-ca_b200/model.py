@@ -96,6 +96,8 @@ class _Engine:
     def __init__(self, model: "UNet"):
         self.model = model
         self._packed = {}
+        self.epoch = 0            # bumped by every forward that may see stepped parameters (see _cached)
+        self.last_train = False
         self._scratch = {}
 
     # ---- scratch -------------------------------------------------------------------------------------
@@ -115,8 +117,13 @@ class _Engine:
 
     # ---- packed weights ------------------------------------------------------------------------------
     def _cached(self, key, param, tdt, build):
+        """Packed operand copy of `param`.  The copies are rebuilt by every train-mode forward and by the first eval
+        forward after one (`self.epoch`; the matching backward reuses them): fused optimizers such as
+        torch.optim.Adam(fused=True) update parameters WITHOUT bumping `Tensor._version`, so the version alone cannot
+        be trusted to see a step.  Between consecutive eval-mode forwards (inference: weights only change through
+        load_state_dict / copy_, which do bump it) the version and data pointer key the cache."""
         ent = self._packed.get(key)
-        ver = (param._version, param.data_ptr(), tdt)
+        ver = (param._version, param.data_ptr(), tdt, self.epoch)
         if ent is None or ent[0] != ver:
             ent = (ver, build())
             self._packed[key] = ent
@@ -272,6 +279,9 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
     eng = model._engine()
     dt, tdt = model._dt()
     train = model.training
+    if train or eng.last_train:
+        eng.epoch += 1            # the parameters may have been stepped since the last train-mode forward: repack them
+    eng.last_train = train
     dev = x.device
     st = _stream()
     B, Cin, H, W = x.shape

@@ -157,14 +157,15 @@ def test_configs0_bf16(golden_dir):
     assert np.all(rel < tol), (np.array(names)[big][worst], rel[worst])
 
 
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_adam_trajectory_100_steps(prec):
+@pytest.mark.parametrize("prec,fused", [("fp32", False), ("bf16", False), ("bf16", True)])
+def test_adam_trajectory_100_steps(prec, fused):
     """100 Adam(lr=1e-4) steps on the same seeded batches: loss and global grad norm within 1e-2 rel of the oracle
     at every step (UCA:342-346, 466)."""
     B, H, W, steps = 2, 32, 32, 100
     sd = port.make_state_dict(seed=7)
     m = _model(sd, prec)
-    opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+    # fused=True updates the parameters without bumping Tensor._version: the packed operand copies must still follow
+    opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=fused)
     # oracle: the torch port driven by the same optimizer on CPU
     p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
          for k, v in sd.items()}
@@ -186,6 +187,14 @@ def test_adam_trajectory_100_steps(prec):
         worst_g = max(worst_g, abs(gn - rg) / rg)
     assert worst_l < 1e-2, worst_l
     assert worst_g < (1e-2 if prec == "fp32" else 3e-2), worst_g
+    # eval right after the last optimizer step must see the stepped weights (validate_model, UCA:273-287): identical
+    # to a fresh model built from the state_dict (a stale packed-operand cache would differ)
+    m.eval()
+    x, _ = port.make_batch(200, B, H, W)
+    with torch.no_grad():
+        ev = m(x.cuda())
+        m2 = _model({k: v.clone() for k, v in m.state_dict().items()}, prec, train=False)
+        assert torch.equal(m2(x.cuda()), ev)
 
 
 def test_error_behaviour():
