@@ -1397,6 +1397,29 @@ __global__ void pack_conv3x3_kernel(const float* __restrict__ w, T* __restrict__
     }
     wf[i] = from_float<T>(v);
 }
+// The same packing for C, O multiples of 32 through a shared-memory tile (32 o x 32 c x 9 taps): the OIHW reads, the
+// [O][tap*C+c] rows and the [C][tap'*O+o] rows are all written as 64..1152-byte runs instead of 2-byte scatters.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_conv3x3_tiled_kernel(const float* __restrict__ w, T* __restrict__ wf, int ldk,
+                                                                 T* __restrict__ wd, int O, int C) {
+    __shared__ float sm[32][289];                     // [o][c*9 + tap], row padded against bank conflicts
+    const int o0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int idx = threadIdx.x; idx < 32 * 288; idx += 256) {
+        const int ol = idx / 288, r = idx % 288;
+        sm[ol][r] = w[((long)(o0 + ol) * C + c0) * 9 + r];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 32 * 288; idx += 256) {
+        const int cl = idx & 31, tap = (idx >> 5) % 9, ol = idx / 288;
+        wf[(long)(o0 + ol) * ldk + tap * C + c0 + cl] = from_float<T>(sm[ol][cl * 9 + tap]);
+    }
+    if (wd) {
+        for (int idx = threadIdx.x; idx < 32 * 288; idx += 256) {
+            const int ol = idx & 31, tap = (idx >> 5) % 9, cl = idx / 288;
+            wd[(long)(c0 + cl) * 9 * O + (long)(8 - tap) * O + o0 + ol] = from_float<T>(sm[ol][cl * 9 + tap]);
+        }
+    }
+}
 // ConvTranspose2d weight (Cin,Cout,2,2) fp32 -> forward operand [4*Cout][Cin] (n = (d*2+e)*Cout + o, k = cin) and
 // dgrad operand [Cin][4*Cout] (k = (d*2+e)*Cout + o).
 template <typename T>
@@ -1882,7 +1905,10 @@ int unetca_pack_conv3x3_weight(int dtype, const float* w, void* wf, int ldk, voi
     UNETCA_REQUIRE(ldk >= 9 * C, "pack_conv3x3: ldk %d < 9*C", ldk);
     DISPATCH_T(dtype, {
         const long total = (long)O * ldk;
-        pack_conv3x3_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, ldk, (T*)wd, O, C);
+        if (O % 32 == 0 && C % 32 == 0 && ldk == 9 * C)
+            pack_conv3x3_tiled_kernel<T><<<dim3(O / 32, C / 32), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, ldk, (T*)wd, O, C);
+        else
+            pack_conv3x3_kernel<T><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(w, (T*)wf, ldk, (T*)wd, O, C);
     });
     return check_launch("pack_conv3x3_weight");
 }
