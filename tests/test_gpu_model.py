@@ -264,3 +264,26 @@ def test_reference_main_configuration_one_channel_three_classes(prec, ltol):
     assert abs(gn - rgn) / rgn < 1e-2
     if prec == "fp32":
         assert torch.equal(torch.max(logits.detach(), 1)[1].cpu(), torch.max(ref_logits, 1)[1])
+
+
+@pytest.mark.parametrize("prec,ltol,gtol", [("fp32", 1e-3, 1e-2), ("bf16", 4e-2, 3e-2)])
+def test_odd_sizes_take_every_fallback(prec, ltol, gtol):
+    """37 x 45 input: odd extents at every level (37 -> 18 -> 9 -> 4 -> 2, 45 -> 22 -> 11 -> 5 -> 2), so the floor
+    max-pools, the bilinear resize guard in both dimensions (UCA:138-157), the per-pixel im2col first conv and the
+    pixels-on-M conv fallback for 64 output channels all run; checked against the pinned oracle port."""
+    import unetca_b200
+    sd = port.make_state_dict(seed=21)
+    x, y = port.make_batch(21, 3, 37, 45)
+    ref_logits, ref_loss, ref_grads, _, _ = port.train_step_grads(sd, x, y)
+    m = unetca_b200.UNet(3, 2, use_se=True).cuda().set_precision(prec)
+    m.load_state_dict(sd)
+    m.train()
+    loss = m.loss(x.cuda(), y.cuda())
+    loss.backward()
+    assert _rel(m.last_logits.cpu(), ref_logits) < ltol
+    assert abs(loss.item() - ref_loss.item()) / ref_loss.item() < 1e-2
+    gn = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in m.parameters())).item()
+    rgn = torch.sqrt(sum((g ** 2).sum() for g in ref_grads.values())).item()
+    assert abs(gn - rgn) / rgn < gtol
+    if prec == "fp32":
+        assert torch.equal(torch.max(m.last_logits, 1)[1].cpu(), torch.max(ref_logits, 1)[1])
