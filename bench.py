@@ -103,6 +103,9 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 def _work(name, a, e, cin):
     """(class, algorithmic flops, algorithmic bytes) of one call; e = bytes per activation element."""
+    if name == "unetca_conv3x3_fwd_kw":
+        B, H, W, C = a[6:10]
+        return "tensor", 2.0 * B * H * W * 9 * C * 64, 0
     if name == "unetca_conv3x3_fwd_paired":
         B, H, W, C, O = a[6:11]
         return "tensor", 2.0 * B * H * W * 9 * C * O, 0

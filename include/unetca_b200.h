@@ -44,6 +44,7 @@ void unetca_tc_force_wgrad_narrow(int on);
 void unetca_tc_force_no_halo(int on);
 void unetca_tc_force_no_pixn(int on);
 void unetca_tc_set_pixn_cluster(int n);
+void unetca_tc_force_no_kw(int on);
 
 /* ---- module boundary: layout and parameter packing ------------------------------------------------------ */
 /* network input (B,Cin,H,W) NCHW fp32 (UCA:343 `model(images)`) -> im2col rows [B*H*W][Kpad], k = tap*Cin + c */
@@ -66,6 +67,11 @@ int unetca_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk
  * (csrc/conv_tc.cu, tc_conv3x3_pixn_kernel); w_pair [2*O][12*C] = unetca_pack_conv3x3_pair(w [O][ld]).  bf16 only. */
 int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream);
 int unetca_pack_conv3x3_pair(int dtype, const void* w, int ld, void* w_pair, int rows, int C, void* stream);
+/* the same convolution for exactly 64 output channels and C = 64 or 128 through the kw-stacked layout of the tcgen05 path
+ * (csrc/conv_tc.cu, tc_conv3x3_kw_kernel: N = 3 kw taps x 64 channels, horizontal shift-add in the epilogue, filter
+ * resident in shared memory); w_kw [9*C][64] = unetca_pack_conv3x3_kw(w [64][ld]).  bf16 only, any H, W. */
+int unetca_conv3x3_fwd_kw(int dtype, const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C, float* stat_parts, int* nparts, void* stream);
+int unetca_pack_conv3x3_kw(int dtype, const void* w, int ld, void* w_kw, int C, void* stream);
 /* first conv (Cin <= 5, H even) in the row-pair layout of the tcgen05 path (bf16): one im2col row per pixel PAIR
  * (rows 2i, 2i+1 of a column) holding their shared 4x3 patch, colp [B*(H/2)*W][64]; pair-packed filter wp [2*O][64];
  * forward = one GEMM with 128x256x16 MMAs (+ BatchNorm partial sums), weight gradient from the same colp */
@@ -140,6 +146,8 @@ int unetca_confusion_counts(const float* logits, const long long* target, int nc
 int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, void* stream);
 int unetca_tc_conv3x3_fwd_paired(const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, void* stream);
 int unetca_tc_pack_pair(const void* w, int ld, void* w_pair, int rows, int C, void* stream);
+int unetca_tc_conv3x3_fwd_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C, float* stat_parts, void* stream);
+int unetca_tc_pack_kw(const void* w, int ld, void* w_kw, int C, void* stream);
 int unetca_tc_first_pairs_fwd(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O, float* stat_parts, void* stream);
 int unetca_tc_first_pairs_wgrad(const void* dy, int lddy, const void* colp, float* ws, long ws_floats, int B, int H, int W, int O, void* stream);
 int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out, int ldo, long M, int N, int K, float* stat_parts, void* stream);

@@ -10,6 +10,8 @@ extern "C" {
 int unetca_tc_conv3x3_fwd(const void*, int, const void*, int, void*, int, int, int, int, int, int, float*, void*);
 int unetca_tc_conv3x3_fwd_paired(const void*, int, const void*, void*, int, int, int, int, int, int, float*, void*);
 int unetca_tc_pack_pair(const void*, int, void*, int, int, void*);
+int unetca_tc_conv3x3_fwd_kw(const void*, int, const void*, void*, int, int, int, int, int, float*, void*);
+int unetca_tc_pack_kw(const void*, int, void*, int, void*);
 int unetca_tc_first_pairs_fwd(const void*, const void*, void*, int, int, int, int, int, float*, void*);
 int unetca_tc_first_pairs_wgrad(const void*, int, const void*, float*, long, int, int, int, int, void*);
 int unetca_first_pairs_fold(const float*, int, int, int, float*, void*);
@@ -65,6 +67,20 @@ int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_p
     if (rc < 0) return rc;
     if (nparts) *nparts = rc;
     return 0;
+}
+
+// 64 output channels, C = 64 / 128: kw-stacked layout (see conv_tc.cu).  bf16 / tensor-core implementation only.
+int unetca_conv3x3_fwd_kw(int dtype, const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C,
+                          float* stat_parts, int* nparts, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("conv3x3_fwd_kw: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int rc = unetca_tc_conv3x3_fwd_kw(x, ldx, w_kw, y, ldy, B, H, W, C, stat_parts, stream);
+    if (rc < 0) return rc;
+    if (nparts) *nparts = rc;
+    return 0;
+}
+int unetca_pack_conv3x3_kw(int dtype, const void* w, int ld, void* w_kw, int C, void* stream) {
+    if (dtype != UNETCA_DTYPE_BF16) { unetca::set_error("pack_conv3x3_kw: bf16 only"); return UNETCA_ERR_UNSUPPORTED; }
+    return unetca_tc_pack_kw(w, ld, w_kw, C, stream);
 }
 
 // w [rows][ld] (K-major packed filter, k = tap*C + c, bf16) -> w_pair [2*rows][12*C]

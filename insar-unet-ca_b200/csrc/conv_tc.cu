@@ -1387,6 +1387,238 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// conv3x3 forward / dgrad for 64 output channels, the three kw taps on the MMA's N side ("kw-stacked").
+// Pixels stay on M (128 = 4 rows x 32 columns of the image), N = 192 = 3 kw taps x 64 output channels:
+//   D[p][(kw, o)] = sum_{kh, c} X[p + (kh-1) rows][c] * W[o][kh][kw][c]          (only VERTICAL shifts of the A view)
+//   out[(y, x)][o] = D[(y, x-1)][(0,o)] + D[(y, x)][(1,o)] + D[(y, x+1)][(2,o)]   (horizontal shift-add in the epilogue)
+// One tcgen05.mma 128x192x16 costs its ~100-cycle A-fetch floor for 96 cycles of work (N = 64 alone: 32), there are no
+// wasted rows (the row-pair layout spends 25 % of its MMAs on zeros) and the A operand needs no horizontal halo: the
+// kh views are the same dense [6 rows][32 px] tile at row offsets.  The whole filter of the layer (3 x C/64 boxes of
+// [192][64], 72 / 144 KB) stays resident in shared memory, so the only fill traffic is 24 KB of activations per
+// 12 MMAs.  The neighbour terms come from warp shuffles (a warp = one 32-pixel image row of the tile); the two edge
+// columns of a tile are halo, so a tile yields 30 x 4 outputs.
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) KwParams {
+    CUtensorMap mapX, mapW, mapOut;
+    int tilesX, tilesY, nimg, H, W;
+    int cchunks;
+    float* stat_parts;
+};
+constexpr int kKwTW = 32, kKwTH = 4, kKwOutW = kKwTW - 2;
+constexpr int kKwXBytes = kKwTW * (kKwTH + 2) * 128;      // 24 KB: [6 rows][32 px][64 ch]
+constexpr int kKwWBox = 192 * 128;                        // 24 KB: [(kw,o)][64 c]
+constexpr int kKwOutTile = kKwTH * (kKwTW - 2) * 128;     // staging tile: [4 x 30 px][64 ch] = 15 KB
+constexpr int kKwOutBytes = 2 * kKwOutTile;               // double-buffered: the TMA store of tile i drains under tile i+1
+constexpr int kKwStatBytes = 2 * 64 * 4 + 8 * 64 * 4;
+static int kw_smem_bytes(int cchunks, int xs) { return 1024 + 3 * cchunks * kKwWBox + xs * kKwXBytes + kKwOutBytes + kKwStatBytes + 256; }
+
+template <int XS>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __grid_constant__ KwParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* w_res = smem;                                         // resident filter: [kh][cc] boxes
+    uint8_t* x_ring = w_res + 3 * p.cchunks * kKwWBox;
+    uint8_t* out_stage = x_ring + XS * kKwXBytes;
+    float* sm_stats = reinterpret_cast<float*>(out_stage + kKwOutBytes);      // [2][64]
+    float* sm_wpart = sm_stats + 128;                                         // [4 warps][2][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kKwOutBytes + kKwStatBytes);
+    uint64_t* xfull = bars;
+    uint64_t* xempty = bars + XS;
+    uint64_t* wfull = bars + 2 * XS;
+    uint64_t* tfull_bar = wfull + 1;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+        mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapW);
+        prefetch_tmap(&p.mapOut);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    if (p.stat_parts) {
+        for (int i = threadIdx.x; i < 128; i += kTcThreads) sm_stats[i] = 0.f;
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesX * p.tilesY;
+    const long num_work = (long)tiles_per_img * p.nimg;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // the whole filter once
+            mbar_expect_tx(wfull, 3 * p.cchunks * kKwWBox);
+            for (int i = 0; i < 3 * p.cchunks; ++i) tma_load_4d(&p.mapW, wfull, w_res + i * kKwWBox, 0, i * 192, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int tx = (int)(t % p.tilesX), ty = (int)((t / p.tilesX) % p.tilesY), b = (int)(t / tiles_per_img);
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    mbar_wait(&xempty[s], ph ^ 1);
+                    mbar_expect_tx(&xfull[s], kKwXBytes);
+                    tma_load_4d(&p.mapX, &xfull[s], x_ring + s * kKwXBytes, cc * 64, tx * kKwOutW - 1, ty * kKwTH - 1, b);
+                    if (++s == XS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 192, 0, 0);
+            mbar_wait(wfull, 0);
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            const uint32_t wb = smem_u32(w_res);
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    mbar_wait(&xfull[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t xa = smem_u32(x_ring + s * kKwXBytes);
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const uint32_t sa = xa + kh * (kKwTW * 128);
+                        const uint32_t sb = wb + (kh * p.cchunks + cc) * kKwWBox;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc,
+                                      (cc | kh | k) != 0);
+                    }
+                    umma_commit(&xempty[s]);
+                    if (++s == XS) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+                as ^= 1; if (as == 0) aph ^= 1;
+            }
+        }
+    } else {
+        // ================================ epilogue: lane = pixel column of the tile, warp = tile row ==========
+        const int q = warp & 3;                   // TMEM lane quarter == tile row
+        const int ep_tid = threadIdx.x - 64;
+        int as = 0; uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            uint8_t* stage = out_stage + as * kKwOutTile;    // staging buffer of this tile (alternates like the accumulator)
+            const int tx = (int)(t % p.tilesX), ty = (int)((t / p.tilesX) % p.tilesY), b = (int)(t / tiles_per_img);
+            const int x0 = tx * kKwOutW, y0 = ty * kKwTH;
+            const int xo = x0 + lane - 1, yo = y0 + q;       // the output pixel this thread assembles (lanes 1..30)
+            const bool inner = lane >= 1 && lane <= kKwOutW;
+            const bool valid = inner && xo < p.W && yo < p.H;
+            mbar_wait(&tfull_bar[as], aph);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            if (ep_tid == 0) tma_store_wait_read1();         // the store issued two tiles ago has drained this buffer
+            named_bar_sync(1, 128);
+            const int nrow = q * kKwOutW + lane - 1;         // staging row of this thread's pixel
+            uint8_t* row = stage + nrow * 128;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                uint32_t a[32], c1[32], c2[32];
+                tmem_ld32(t_addr + 0 * 64 + half * 32, a);
+                tmem_ld32(t_addr + 1 * 64 + half * 32, c1);
+                tmem_ld32(t_addr + 2 * 64 + half * 32, c2);
+                tmem_wait_ld();
+                float f[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(a[i]), 1);      // kw = 0 from column x-1
+                    const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(c2[i]), 1);  // kw = 2 from column x+1
+                    f[i] = valid ? (left + __uint_as_float(c1[i])) + right : 0.f;
+                }
+                if (inner) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 pk;
+                        pk.x = pack_bf16x2(f[c * 8 + 0], f[c * 8 + 1]); pk.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
+                        pk.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]); pk.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
+                        const int chunk = half * 4 + c;
+                        *reinterpret_cast<uint4*>(row + ((chunk ^ (nrow & 7)) << 4)) = pk;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (ep_tid == 0) {
+                tma_store_4d(&p.mapOut, stage, 0, x0, y0, b);
+                tma_store_commit();
+            }
+            if (p.stat_parts) {
+                // per-channel sum / sum of squares of the staged bf16 tile (120 rows x 8 chunks of 8 channels)
+                const int ch = ep_tid & 7, r0 = ep_tid >> 3;
+                float s1[8], s2[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+                for (int rr = r0; rr < kKwTH * kKwOutW; rr += 16) {
+                    const uint4 t4 = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
+                    const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float lo = __uint_as_float(w4[i] << 16), hi = __uint_as_float(w4[i] & 0xffff0000u);
+                        s1[2 * i] += lo; s2[2 * i] = fmaf(lo, lo, s2[2 * i]);
+                        s1[2 * i + 1] += hi; s2[2 * i + 1] = fmaf(hi, hi, s2[2 * i + 1]);
+                    }
+                }
+#pragma unroll
+                for (int off = 8; off < 32; off <<= 1) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        s1[i] += __shfl_xor_sync(0xffffffffu, s1[i], off);
+                        s2[i] += __shfl_xor_sync(0xffffffffu, s2[i], off);
+                    }
+                }
+                const int ew = ep_tid >> 5;
+                if (lane < 8) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        sm_wpart[(ew * 2 + 0) * 64 + ch * 8 + i] = s1[i];
+                        sm_wpart[(ew * 2 + 1) * 64 + ch * 8 + i] = s2[i];
+                    }
+                }
+                named_bar_sync(1, 128);
+                {
+                    const int which = ep_tid >> 6, col = ep_tid & 63;
+                    float tsum = 0.f;
+#pragma unroll
+                    for (int w4i = 0; w4i < 4; ++w4i) tsum += sm_wpart[(w4i * 2 + which) * 64 + col];
+                    sm_stats[which * 64 + col] += tsum;
+                }
+            }
+            as ^= 1; if (as == 0) aph ^= 1;
+        }
+        if (ep_tid == 0) tma_store_wait_all();
+        named_bar_sync(1, 128);
+        if (p.stat_parts) {
+            float* dst = p.stat_parts + (long)blockIdx.x * 128;
+            for (int i = ep_tid; i < 128; i += 128) dst[i] = sm_stats[i];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// kw-stacked filter: dst[((kh*cch + cc)*3 + kw)*64 + o][c_l] = src[o][(kh*3 + kw)*C + cc*64 + c_l]   (64 output rows)
+__global__ void pack_kw_kernel(const bf16* __restrict__ src, int ld, bf16* __restrict__ dst, int C) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cch = C / 64;
+    if (i >= 9L * cch * 64 * 64) return;
+    const int cl = (int)(i & 63), o = (int)((i >> 6) & 63);
+    const int blk = (int)(i >> 12);                       // (kh*cch + cc)*3 + kw
+    const int kw = blk % 3, cc = (blk / 3) % cch, kh = blk / (3 * cch);
+    dst[i] = src[(long)o * ld + (kh * 3 + kw) * C + cc * 64 + cl];
+}
+
 // pair-packed weights for the P = 2 layout: dst[(g*128 + j*64 + o)][(vr*3+kw)*C + c] = src[(g*64+o)][((vr-j)*3+kw)*C + c]
 // when 0 <= vr-j <= 2, else 0.  src: K-major packed filter [rows][ld] (k = tap*C + c), rows a multiple of 64.
 __global__ void pack_pair_kernel(const bf16* __restrict__ src, int ld, bf16* __restrict__ dst, int rows, int C) {
@@ -1538,6 +1770,41 @@ static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, 
     return rc < 0 ? rc : (int)grid;
 }
 
+static int g_no_kw = 0;
+
+// conv3x3 forward / dgrad for exactly 64 output channels and C in {64, 128}: kw-stacked kernel; w_kw from unetca_tc_pack_kw
+static int launch_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C,
+                     float* stat_parts, cudaStream_t st) {
+    KwParams p;
+    memset(&p, 0, sizeof(p));
+    const int cch = C / 64;
+    int rc;
+    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kKwTW, kKwTH + 2)) < 0) return rc;
+    const long rows = 9L * cch * 64;
+    if ((rc = make_map(&p.mapW, w_kw, 64, rows, 1, 1, 64, rows * 64, rows * 64, 192, 1)) < 0) return rc;
+    if ((rc = make_map(&p.mapOut, y, 64, W, H, B, ldy, (long)W * ldy, (long)H * W * ldy, kKwOutW, kKwTH)) < 0) return rc;
+    p.tilesX = ceil_div(W, kKwOutW); p.tilesY = ceil_div(H, kKwTH); p.nimg = B; p.H = H; p.W = W;
+    p.cchunks = cch;
+    p.stat_parts = stat_parts;
+    const int xs = cch == 1 ? 4 : 2;
+    const int smem = kw_smem_bytes(cch, xs);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_kw_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kw_smem_bytes(1, 4));
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(tc_conv3x3_kw_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kw_smem_bytes(2, 2));
+        if (e != cudaSuccess) { set_error("tc_conv3x3 (kw): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    const long num_work = (long)p.tilesX * p.tilesY * B;
+    long grid = num_work < num_sms() ? num_work : num_sms();
+    if (grid < 1) grid = 1;
+    if (cch == 1) tc_conv3x3_kw_kernel<4><<<(int)grid, kTcThreads, smem, st>>>(p);
+    else tc_conv3x3_kw_kernel<2><<<(int)grid, kTcThreads, smem, st>>>(p);
+    rc = check_launch("tc_conv3x3_fwd (kw)");
+    return rc < 0 ? rc : (int)grid;
+}
+
 // 5-D bf16 map over an NHWC activation seen as (C, W, P, H/P, B): P = 2 splits the rows into an even and an odd
 // lattice (row = 2*i + parity).  box (64, bw, 1, bi, 1).
 static int make_map5(CUtensorMap* m, const void* base, long C, long W, long H, long B, long ld, int P, int bw, int bi,
@@ -1675,6 +1942,22 @@ int unetca_tc_conv3x3_fwd_paired(const void* x, int ldx, const void* w_pair, voi
                    "tc_conv3x3_paired: C=%d O=%d must be multiples of 64 and H=%d even", C, O, H);
     return launch_pixn(x, ldx, w_pair, 12 * C, y, ldy, B, H, W, C, O, 2, stat_parts, (cudaStream_t)stream);
 }
+
+// conv3x3 forward / dgrad for 64 output channels (C = 64 or 128) through the kw-stacked kernel
+int unetca_tc_conv3x3_fwd_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C,
+                             float* stat_parts, void* stream) {
+    UNETCA_REQUIRE(C == 64 || C == 128, "tc_conv3x3_kw: C=%d must be 64 or 128 (the filter stays resident in shared memory)", C);
+    return launch_kw(x, ldx, w_kw, y, ldy, B, H, W, C, stat_parts, (cudaStream_t)stream);
+}
+
+// w_kw [9*(C/64)*64][64] from the K-major packed filter w [64][ld] (k = tap*C + c)
+int unetca_tc_pack_kw(const void* w, int ld, void* w_kw, int C, void* stream) {
+    UNETCA_REQUIRE(C % 64 == 0 && ld >= 9 * C, "tc_pack_kw: C=%d ld=%d", C, ld);
+    const long total = 9L * (C / 64) * 64 * 64;
+    pack_kw_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)w, ld, (bf16*)w_kw, C);
+    return check_launch("tc_pack_kw");
+}
+void unetca_tc_force_no_kw(int on) { g_no_kw = on; }
 
 // w_pair [2*rows][12*C] from the K-major packed filter w [rows][ld] (k = tap*C + c)
 int unetca_tc_pack_pair(const void* w, int ld, void* w_pair, int rows, int C, void* stream) {

@@ -143,15 +143,26 @@ class _Engine:
             wfp = wdp = None
             if dt == _lib.BF16 and first and C <= 5:
                 # first conv: pixel-pair layout (unetca_im2col_pairs), filter over the 4x3 patch a row pair shares
-                wfp = torch.empty(2 * O, 64, dtype=tdt, device=w.device)
+                wfp = torch.empty(2 * O, 64, dtype=tdt, device=w.device)              # (a plain tensor: first conv only)
                 _lib.call("unetca_pack_first_pairs", dt, _ptr(w), _ptr(wfp), O, C, _stream())
             if dt == _lib.BF16 and not first:
+                # 64 output channels: the row-pair layout ("pair"), except from 128 input channels where the kw-stacked
+                # layout ("kw", filter resident in shared memory) wins: its epilogue reads three accumulator columns per
+                # output from TMEM (64 B/cycle/SM) and only hides behind a mainloop of >= 2 channel chunks
                 if O % 128:
-                    wfp = torch.empty(2 * O, 12 * C, dtype=tdt, device=w.device)
-                    _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wf), ldk, _ptr(wfp), O, C, _stream())
+                    if O == 64 and C == 128:
+                        wfp = ("kw", torch.empty(9 * C, 64, dtype=tdt, device=w.device))
+                        _lib.call("unetca_pack_conv3x3_kw", dt, _ptr(wf), ldk, _ptr(wfp[1]), C, _stream())
+                    else:
+                        wfp = ("pair", torch.empty(2 * O, 12 * C, dtype=tdt, device=w.device))
+                        _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wf), ldk, _ptr(wfp[1]), O, C, _stream())
                 if C % 128:
-                    wdp = torch.empty(2 * C, 12 * O, dtype=tdt, device=w.device)
-                    _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wd), 9 * O, _ptr(wdp), C, O, _stream())
+                    if C == 64 and O == 128:
+                        wdp = ("kw", torch.empty(9 * O, 64, dtype=tdt, device=w.device))
+                        _lib.call("unetca_pack_conv3x3_kw", dt, _ptr(wd), 9 * O, _ptr(wdp[1]), O, _stream())
+                    else:
+                        wdp = ("pair", torch.empty(2 * C, 12 * O, dtype=tdt, device=w.device))
+                        _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wd), 9 * O, _ptr(wdp[1]), C, O, _stream())
             return wf, wd, ldk, wfp, wdp
         return self._cached(("c", id(conv)), w, tdt, build)
 
@@ -169,8 +180,11 @@ class _Engine:
 
 def _conv3x3(dt, x, ldx, w, ldk, w_pair, y, ldy, B, H, W, C, O, sp, nparts, st):
     """conv3x3 forward (or dgrad with the dgrad-packed filter): row-pair tcgen05 layout when a pair-packed filter exists."""
-    if w_pair is not None and H % 2 == 0 and _lib.load().unetca_get_conv_impl() == 0:
-        _lib.call("unetca_conv3x3_fwd_paired", dt, _ptr(x), ldx, _ptr(w_pair), _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
+    tc = _lib.load().unetca_get_conv_impl() == 0
+    if isinstance(w_pair, tuple) and w_pair[0] == "kw" and tc:
+        _lib.call("unetca_conv3x3_fwd_kw", dt, _ptr(x), ldx, _ptr(w_pair[1]), _ptr(y), ldy, B, H, W, C, sp, nparts, st)
+    elif isinstance(w_pair, tuple) and w_pair[0] == "pair" and H % 2 == 0 and tc:
+        _lib.call("unetca_conv3x3_fwd_paired", dt, _ptr(x), ldx, _ptr(w_pair[1]), _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
     else:
         _lib.call("unetca_conv3x3_fwd", dt, _ptr(x), ldx, _ptr(w), ldk, _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
 

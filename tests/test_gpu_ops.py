@@ -309,6 +309,23 @@ def _conv_case(dt, impl, B, C, O, H, W, seed=4):
         dx2 = torch.full((B, H, W, C), float("nan"), dtype=TDT[dt], device="cuda")
         call("unetca_conv3x3_fwd_paired", dt, ptr(dyd), O, ptr(wdp), ptr(dx2), C, B, H, W, O, C, None, None, stream())
         assert relerr(from_nhwc(dx2), xr.grad) < tol, "dgrad (paired)"
+    if impl == 0 and dt == BF16 and O == 64 and C in (64, 128):
+        # kw-stacked layout (N = 3 kw taps x 64 channels, shift-add epilogue, resident filter): forward + stats
+        wkw = torch.empty(9 * C, 64, dtype=TDT[dt], device="cuda")
+        call("unetca_pack_conv3x3_kw", dt, ptr(wf), 9 * C, ptr(wkw), C, stream())
+        y3 = torch.full((B, H, W, O), float("nan"), dtype=TDT[dt], device="cuda")
+        call("unetca_conv3x3_fwd_kw", dt, ptr(xd), C, ptr(wkw), ptr(y3), O, B, H, W, C, ptr(parts), ctypes.byref(n), stream())
+        got3 = from_nhwc(y3)
+        assert relerr(got3, ref.detach()) < tol, "fwd (kw)"
+        st = parts[: n.value * 2 * O].view(n.value, 2, O).sum(0).cpu()
+        assert relerr(st[0], got3.sum((0, 2, 3))) < 1e-3 and relerr(st[1], (got3 * got3).sum((0, 2, 3))) < 1e-3, "stats (kw)"
+    if impl == 0 and dt == BF16 and C == 64 and O in (64, 128):
+        # ... and as the dgrad of a layer with 64 input channels
+        wkd = torch.empty(9 * O, 64, dtype=TDT[dt], device="cuda")
+        call("unetca_pack_conv3x3_kw", dt, ptr(wdg), 9 * O, ptr(wkd), O, stream())
+        dx3 = torch.full((B, H, W, C), float("nan"), dtype=TDT[dt], device="cuda")
+        call("unetca_conv3x3_fwd_kw", dt, ptr(dyd), O, ptr(wkd), ptr(dx3), C, B, H, W, O, None, None, stream())
+        assert relerr(from_nhwc(dx3), xr.grad) < tol, "dgrad (kw)"
 
 
 @pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 64, 16, 16), (1, 128, 64, 8, 24), (2, 64, 192, 4, 4)])
@@ -320,7 +337,7 @@ def test_conv3x3_ffma(dt, B, C, O, H, W):
 @pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 64, 16, 16), (1, 128, 64, 8, 24), (2, 64, 192, 4, 4),
                                        (2, 128, 256, 32, 32), (3, 256, 128, 16, 48), (1, 64, 64, 128, 128),
                                        (2, 128, 128, 40, 24), (1, 192, 64, 48, 16), (2, 64, 128, 64, 64), (1, 64, 64, 34, 20),
-                                       (1, 128, 384, 16, 16)])
+                                       (1, 128, 384, 16, 16), (2, 64, 128, 36, 70), (1, 128, 64, 61, 33)])
 def test_conv3x3_tcgen05(B, C, O, H, W):
     _conv_case(BF16, 0, B, C, O, H, W)
 

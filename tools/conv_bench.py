@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--convT", action="store_true", help="benchmark the four ConvTranspose2d(k2,s2) layers instead")
     ap.add_argument("--pixn-cluster", type=int, default=2, help="CTAs per cluster sharing weights by TMA multicast (1|2)")
     ap.add_argument("--wgrad-mode", type=int, default=0, help="0 auto, 1 narrow kernel everywhere, 2 no 256-wide tap-pair kernel")
+    ap.add_argument("--no-kw", action="store_true", help="64-output layers through the row-pair kernel instead of the kw-stacked one")
     ap.add_argument("--no-pixn", action="store_true", help="narrow layers through the pixels-on-M generic kernel")
     ap.add_argument("--dgrad", action="store_true", help="add the dgrad shapes (O -> C) of the narrow layers")
     a = ap.parse_args()
@@ -88,13 +89,19 @@ def main():
         wf = (torch.randn(O, 9 * C, device="cuda") / (9 * C) ** 0.5).bfloat16()
         dw = torch.empty(O, C, 3, 3, device="cuda")
         fl = 2.0 * B * S * S * 9 * C * O
-        wfp = None
-        if O % 128 and not a.no_pixn:
+        wfp = wkw = None
+        if O == 64 and C == 128 and not a.no_kw:
+            wkw = torch.empty(9 * C, 64, device="cuda", dtype=torch.bfloat16)
+            _lib.call("unetca_pack_conv3x3_kw", 1, wf.data_ptr(), 9 * C, wkw.data_ptr(), C, st)
+        elif O % 128 and not a.no_pixn:
             wfp = torch.empty(2 * O, 12 * C, device="cuda", dtype=torch.bfloat16)
             _lib.call("unetca_pack_conv3x3_pair", 1, wf.data_ptr(), 9 * C, wfp.data_ptr(), O, C, st)
         res = []
         for what in a.what.split(","):
-            if what == "fwd" and wfp is not None:
+            if what == "fwd" and wkw is not None:
+                fn = lambda: _lib.call("unetca_conv3x3_fwd_kw", 1, x.data_ptr(), C, wkw.data_ptr(), y.data_ptr(), O, B, S, S, C,
+                                       parts.data_ptr(), ctypes.byref(n), st)  # noqa: E731
+            elif what == "fwd" and wfp is not None:
                 fn = lambda: _lib.call("unetca_conv3x3_fwd_paired", 1, x.data_ptr(), C, wfp.data_ptr(), y.data_ptr(), O, B, S, S,
                                        C, O, parts.data_ptr(), ctypes.byref(n), st)  # noqa: E731
             elif what == "fwd":
