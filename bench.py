@@ -257,6 +257,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the whole train step as one CUDA graph (unetca_b200.graph; single GPU; no per-kernel "
+                         "accounting, so the roofline objects are omitted) — what matters at small batch / tile sizes")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel table (JSON) to this path")
     args = ap.parse_args()
 
@@ -306,6 +309,31 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if args.graph:
+        if world > 1:
+            raise SystemExit("bench.py --graph: single GPU only")
+        from unetca_b200 import graph as ugraph
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+        gstep = ugraph.GraphedTrainStep(model, opt, x, y, warmup=args.warmup)
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local)
+        clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loss = gstep(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        clk = clocks.stop()
+        ms = e0.elapsed_time(e1)
+        print(json.dumps({"metric": METRIC, "value": B * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                          "config": {"workload": f"U-Net-CA (use_se=True) train step fwd+CE+bwd+Adam(capturable) replayed as ONE CUDA "
+                                                 f"graph, batch {B}, 3x{S}x{S}, {args.precision} mode"},
+                          "clocks": clk, "final_loss": loss.item()}), flush=True)
+        return
 
     acct = KernelAccount(2 if args.precision == "bf16" else 4, 3)
     _lib.set_hook(acct)

@@ -1,0 +1,53 @@
+"""Whole-train-step CUDA graph (forward + loss + backward + optimizer step as one replayable launch).
+
+At the reference's own configuration (batch 8, 1x128x128 tiles, UCA:21-24) a step is ~0.3 ms of GPU work behind ~280
+kernel launches issued from Python: the host, not the GPU, sets the step time.  Every launch of this path goes to
+PyTorch's current stream through the C ABI with caller-owned memory and no host synchronisation, so the step can be
+captured once with `torch.cuda.graph` and replayed: the tensor maps (passed by value as kernel parameters), the scratch
+buffers and the gradients all live at fixed addresses inside the graph's private memory pool.
+
+    step = GraphedTrainStep(model, optimizer, images, masks)     # optimizer must be capturable (Adam(capturable=True))
+    for images, masks in loader:
+        loss = step(images, masks)                                # copies into the static inputs, replays the graph
+
+Same kernels in the same order as the eager step, hence bit-identical results (tests/test_gpu_model.py).  Single GPU
+only: the data-parallel bucket all-reduce is not captured.
+"""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    def __init__(self, model, optimizer, images: torch.Tensor, masks: torch.Tensor, ignore_index: int = 255, warmup: int = 3):
+        if not images.is_cuda:
+            raise RuntimeError("GraphedTrainStep needs CUDA tensors; there is no CPU fallback")
+        if model._grad_sink_factory is not None:
+            raise NotImplementedError("GraphedTrainStep does not capture the data-parallel gradient all-reduce")
+        self.model, self.optimizer, self.ignore_index = model, optimizer, ignore_index
+        self.images, self.masks = images.clone(), masks.clone()
+        model.train()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up off the default stream, as torch.cuda.graph requires
+            for _ in range(warmup):
+                self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(self.graph):
+            self.loss = self._eager(zero=False)
+
+    def _eager(self, zero=True):
+        if zero:
+            self.optimizer.zero_grad(set_to_none=True)
+        loss = self.model.loss(self.images, self.masks, self.ignore_index)
+        loss.backward()
+        self.optimizer.step()
+        return loss
+
+    def __call__(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        self.images.copy_(images, non_blocking=True)
+        self.masks.copy_(masks, non_blocking=True)
+        self.graph.replay()
+        return self.loss

@@ -287,3 +287,40 @@ def test_odd_sizes_take_every_fallback(prec, ltol, gtol):
     assert abs(gn - rgn) / rgn < gtol
     if prec == "fp32":
         assert torch.equal(torch.max(m.last_logits, 1)[1].cpu(), torch.max(ref_logits, 1)[1])
+
+
+def test_graphed_train_step_is_bit_identical_to_eager():
+    """The whole train step captured as one CUDA graph replays to exactly the eager step's losses and parameters."""
+    import unetca_b200
+    from unetca_b200 import graph
+    sd = port.make_state_dict(seed=31, in_channels=1)
+    batches = [port.make_batch(300 + i, 4, 64, 64, in_channels=1) for i in range(4)]
+
+    def run(graphed):
+        m = unetca_b200.UNet(1, 2, use_se=True).cuda().set_precision("bf16")
+        m.load_state_dict(sd)
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
+        losses = []
+        if graphed:
+            # capture on the first batch: construction runs 3 warm-up steps + the capture on it, then replay per batch
+            step = graph.GraphedTrainStep(m, opt, batches[0][0].cuda(), batches[0][1].cuda(), warmup=3)
+            for x, y in batches:
+                losses.append(step(x.cuda(), y.cuda()).item())
+        else:
+            for _ in range(3):                                   # the same 3 warm-up steps on batch 0
+                opt.zero_grad(set_to_none=True)
+                m.loss(batches[0][0].cuda(), batches[0][1].cuda()).backward()
+                opt.step()
+            for x, y in batches:
+                opt.zero_grad(set_to_none=True)
+                l = m.loss(x.cuda(), y.cuda())
+                l.backward()
+                opt.step()
+                losses.append(l.item())
+        return losses, [p.detach().clone() for p in m.parameters()]
+
+    le, pe = run(False)
+    lg, pg = run(True)
+    assert le == lg, (le, lg)
+    assert all(torch.equal(a, b) for a, b in zip(pe, pg))
