@@ -502,3 +502,59 @@ def test_device_input_pipeline_matches_reference(golden_dir):
     xi, yi = data.prep_u8(u, u)
     ref = ((u.cpu().float() / 255.0) - 0.5) / 0.5
     assert torch.equal(xi.cpu()[:, 0], ref) and torch.equal(yi.cpu(), (u.cpu().float() / 255.0).long())
+
+
+def _guarded(shape, dtype, pad=4096):
+    """A tensor view of `shape` carved out of the middle of a sentinel-filled buffer, plus a checker that the guard
+    bands on both sides are untouched (compute-sanitizer is not available on the GPU pool)."""
+    n = int(np.prod(shape))
+    buf = torch.full((n + 2 * pad,), 123.0 if dtype.is_floating_point else 77, dtype=dtype, device="cuda")
+    view = buf[pad:pad + n].view(*shape)
+
+    def intact():
+        ref = 123.0 if dtype.is_floating_point else 77
+        return bool((buf[:pad] == ref).all().item() and (buf[pad + n:] == ref).all().item())
+    return view, intact
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 7, 13), (1, 192, 5, 6), (3, 128, 9, 4)])
+def test_no_out_of_bounds_writes_on_odd_shapes(B, C, H, W):
+    """Guard-band check of the HBM-bound kernels on odd extents: nothing is written outside the output tensors."""
+    dt = BF16
+    rs = np.random.RandomState(3)
+    tdt = TDT[dt]
+    y = torch.from_numpy(rs.standard_normal((B, H, W, C)).astype(np.float32)).to(tdt).cuda()
+    d = torch.from_numpy(rs.standard_normal((B, H, W, C)).astype(np.float32)).to(tdt).cuda()
+    sc, sh = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.1
+    mean, invstd = torch.randn(C, device="cuda") * 0.1, torch.rand(C, device="cuda") + 0.5
+    s, dp = torch.rand(B, C, device="cuda"), torch.randn(B, C, device="cuda")
+    coef = torch.rand(3, C, device="cuda")
+    checks = []
+    out, ok = _guarded((B, H, W, C), tdt); checks.append(ok)
+    call("unetca_bn_relu", dt, ptr(y), C, ptr(out), C, B, H * W, C, ptr(sc), ptr(sh), None, None, stream())
+    out2, ok = _guarded((B, H, W, C), tdt); checks.append(ok)
+    call("unetca_se_scale_pool", dt, ptr(y), C, ptr(out2), C, None, 0, None, B, H, W, C, ptr(sc), ptr(sh), ptr(s), stream())
+    pooled, ok = _guarded((B, H // 2, W // 2, C), tdt); checks.append(ok)
+    pos, ok = _guarded((B, H // 2, W // 2, C), torch.uint8); checks.append(ok)
+    call("unetca_maxpool2x2", dt, ptr(y), C, ptr(pooled), C, ptr(pos), None, B, H, W, C, stream())
+    dx, ok = _guarded((B, H, W, C), tdt); checks.append(ok)
+    call("unetca_pool_bwd_add", dt, ptr(d), C, ptr(pooled), C, ptr(pos), ptr(dx), C, B, H, W, C, stream())
+    dy, ok = _guarded((B, H, W, C), tdt); checks.append(ok)
+    call("unetca_bn_bwd_apply", dt, ptr(d), C, ptr(y), C, ptr(dy), C, B, H * W, C, ptr(sc), ptr(sh), ptr(mean), ptr(invstd),
+         ptr(s), ptr(dp), ptr(coef), stream())
+    up, ok = _guarded((B, H + 1, W + 1, C), tdt); checks.append(ok)
+    call("unetca_resize_bilinear_fwd", dt, ptr(y), C, H, W, ptr(up), C, H + 1, W + 1, B, C, stream())
+    dn, ok = _guarded((B, H, W, C), tdt); checks.append(ok)
+    call("unetca_resize_bilinear_bwd", dt, ptr(up), C, H + 1, W + 1, ptr(dn), C, H, W, B, C, stream())
+    parts, ok = _guarded((_lib_max_parts(B) * 2 * C,), torch.float32); checks.append(ok)
+    n = cint()
+    call("unetca_se_bn_bwd_reduce", dt, ptr(d), C, ptr(y), C, B, H * W, C, ptr(sc), ptr(sh), ptr(mean), ptr(parts),
+         ctypes.byref(n), stream())
+    assert n.value * B <= _lib_max_parts(B)
+    torch.cuda.synchronize()
+    assert all(ok() for ok in checks)
+
+
+def _lib_max_parts(B):
+    from unetca_b200 import _lib
+    return _lib.load().unetca_max_parts(B)
