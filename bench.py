@@ -151,6 +151,14 @@ def _work(name, a, e, cin):
     if name in ("unetca_se_bwd_reduce", "unetca_bn_bwd_reduce", "unetca_se_bn_bwd_reduce"):
         B, hw, C = a[5:8]
         return "hbm", 0, 2 * B * hw * C * e
+    if name == "unetca_se_bn_bwd_reduce_pool":
+        B, H, W, C = a[8:12]
+        n = B * H * W * C
+        return "hbm", 0, 2 * n * e + (n // 4) * (e + 1)
+    if name == "unetca_bn_bwd_apply_pool":
+        B, H, W, C = a[10:14]
+        n = B * H * W * C
+        return "hbm", 0, 3 * n * e + (n // 4) * (e + 1)
     if name == "unetca_bn_bwd_apply":
         B, hw, C = a[7:10]
         return "hbm", 0, 3 * B * hw * C * e

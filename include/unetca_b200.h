@@ -126,6 +126,10 @@ int unetca_se_fc3(const float* parts2, int nparts, int B, int C, int Cr, long hw
 int unetca_se_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, int ldy, int B, long pix_per_img, int C, const float* scale, const float* shift, const float* mean, float* parts, int* nparts, void* stream);
 int unetca_se_fc_bwd_fused(const float* parts, int nparts, int B, int C, int Cr, const float* w1, const float* w2, const float* p, const float* z, const float* s, const float* scale, const float* shift, const float* mean, const float* sums34, float* sums, float* dpre2, float* dz, float* dp, float* dw1, float* dw2, void* stream);
 int unetca_bn_bwd_finalize_se(const float* sums, int B, int C, long count, long pix_per_img, const float* gamma, const float* invstd, const float* s, const float* dp, float* dgamma, float* dbeta, float* coef, void* stream);
+/* the same two passes for an ENCODER block, with the gradient of the block output rebuilt on the fly from the skip
+ * gradient sg (full resolution) and the pooled gradient routed through the max-pool positions (no pool_bwd_add pass) */
+int unetca_se_bn_bwd_reduce_pool(int dtype, const void* sg, int lds, const void* dpooled, int ldp, const uint8_t* pos, const void* y, int ldy, int B, int H, int W, int C, const float* scale, const float* shift, const float* mean, float* parts, int* nparts, void* stream);
+int unetca_bn_bwd_apply_pool(int dtype, const void* sg, int lds, const void* dpooled, int ldp, const uint8_t* pos, const void* y, int ldy, void* dy, int lddy, int B, int H, int W, int C, const float* scale, const float* shift, const float* mean, const float* invstd, const float* s, const float* dp, const float* coef, void* stream);
 int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* parts, float* out, void* stream);
 /* tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid,
  * 2 = quads per thread-row of se_scale_pool */

@@ -690,6 +690,99 @@ __global__ void __launch_bounds__(kThreads, 4) se_bn_bwd_reduce_kernel(const T* 
     block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The SE + ReLU + BN backward of an ENCODER block, with the gradient of its output formed on the fly.  That output
+// feeds the decoder (skip gradient sg, full resolution) and the next level's MaxPool2d(2) (gradient dpooled routed to
+// the window position `pos`): dO[p] = sg[p] + (pos[quad(p)] == k(p) ? dpooled[quad(p)] : 0).  Materialising dO first
+// (pool_bwd_add) costs a 2.25*N pass; here both passes that consume it (reduction and apply) rebuild it per 2x2 quad
+// from one dpooled vector and one 8-byte position word.  One thread = a run of quads x one channel vector;
+// grid = (blocks per image, B).  APPLY = false: parts[(b*nblk+blk)][2][C] = (sum m*dO, sum m*dO*(y-mean));
+// APPLY = true: dY as in bn_bwd_kernel<T, true, true>.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T, bool APPLY>
+__global__ void __launch_bounds__(kThreads, 2) se_bn_bwd_pool_kernel(const T* __restrict__ sg, int lds,
+                                                                     const T* __restrict__ dpooled, int ldp,
+                                                                     const uint8_t* __restrict__ pos,
+                                                                     const T* __restrict__ y, int ldy, T* __restrict__ dy,
+                                                                     int lddy, int H, int W, int C, long chunk, float inv_hw,
+                                                                     const float* __restrict__ scale,
+                                                                     const float* __restrict__ shift,
+                                                                     const float* __restrict__ mean,
+                                                                     const float* __restrict__ invstd,
+                                                                     const float* __restrict__ s, const float* __restrict__ dp,
+                                                                     const float* __restrict__ coef,
+                                                                     float* __restrict__ parts) {
+    constexpr int VEC = VecTraits<T>::N;
+    const int vpr = C / VEC, rows = kThreads / vpr;
+    const int r = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const long nquad = (long)Ho * Wo;
+    const int b = blockIdx.y;
+    const long q0 = (long)blockIdx.x * chunk;
+    long q1 = q0 + chunk; if (q1 > nquad) q1 = nquad;
+    float acc[2][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+    if (r < rows) {
+        float a[VEC], bb[VEC], m0[VEC], m1[VEC], k2[VEC], k0[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+            const int c = cv * VEC + i;
+            a[i] = scale[c]; bb[i] = shift[c];
+            if (APPLY) {
+                const float g = coef[c], c1 = coef[C + c], c2 = coef[2 * C + c];
+                k2[i] = g * c2 * invstd[c];
+                k0[i] = mean[c] * k2[i] - g * c1;
+                m0[i] = g * s[(long)b * C + c]; m1[i] = g * dp[(long)b * C + c] * inv_hw;
+            } else {
+                k2[i] = mean[c]; k0[i] = 0.f; m0[i] = 0.f; m1[i] = 0.f;
+            }
+        }
+#pragma unroll 2
+        for (long q = q0 + r; q < q1; q += rows) {
+            const int wo = (int)(q % Wo), ho = (int)(q / Wo);
+            const long qg = (long)b * nquad + q;
+            float g[VEC];
+            load_vec(dpooled + qg * ldp + cv * VEC, g);
+            uint8_t code[VEC];
+            const uint8_t* src = pos + qg * C + cv * VEC;
+            if (VEC == 8) {
+                const uint2 t = *reinterpret_cast<const uint2*>(src);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { code[i] = (t.x >> (8 * i)) & 0xff; code[(4 + i) % VEC] = (t.y >> (8 * i)) & 0xff; }
+            } else {
+                const uint32_t t = *reinterpret_cast<const uint32_t*>(src);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) code[i] = (t >> (8 * i)) & 0xff;
+            }
+            const long pbase = ((long)b * H + 2 * ho) * W + 2 * wo;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long p = pbase + (k >> 1) * W + (k & 1);
+                float v[VEC], d[VEC];
+                load_vec(y + p * ldy + cv * VEC, v);
+                load_vec(sg + p * lds + cv * VEC, d);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float dO = code[i] == k ? d[i] + g[i] : d[i];
+                    const bool on = fmaf(a[i], v[i], bb[i]) > 0.f;
+                    if (APPLY) {
+                        const float dz = on ? fmaf(dO, m0[i], m1[i]) : 0.f;
+                        d[i] = fmaf(-v[i], k2[i], dz) + k0[i];
+                    } else {
+                        const float dm = on ? dO : 0.f;
+                        acc[0][i] += dm;
+                        acc[1][i] = fmaf(dm, v[i] - k2[i], acc[1][i]);
+                    }
+                }
+                if (APPLY) store_vec(dy + p * lddy + cv * VEC, d);
+            }
+        }
+    }
+    if (!APPLY)
+        block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
 // SE squeeze (forward): per (image, channel) S3 = sum m and Sy = sum m*y with m = (a*y+b > 0).  The squeeze itself
 // follows from them, sum relu(a*y+b) = a*Sy + b*S3, and so does the centred sum the backward pass needs,
 // S4 = Sy - mean*S3 (both formed in double by se_fc_kernel<3>).  Two predicated adds per element keep this read-only
@@ -1662,6 +1755,41 @@ int unetca_se_fc_bwd(const float* parts, int nparts, int B, int C, int Cr, const
     se_fc_bwd_kernel<<<B, 256, (C + Cr) * sizeof(float), st>>>(parts, nparts, C, Cr, w1, w2, z, s, dpre2, dz, dp);
     se_fc_wgrad_kernel<<<ceil_div((long)C * Cr, 256), 256, 0, st>>>(B, C, Cr, dpre2, dz, p, z, dw1, dw2);
     return check_launch("se_fc_bwd");
+}
+
+// se_bn_bwd_reduce with the block-output gradient rebuilt per quad from the skip gradient and the pooled gradient
+// (H, W even).  parts: [B * *nparts][2][C]
+int unetca_se_bn_bwd_reduce_pool(int dtype, const void* sg, int lds, const void* dpooled, int ldp, const uint8_t* pos,
+                                 const void* y, int ldy, int B, int H, int W, int C, const float* scale, const float* shift,
+                                 const float* mean, float* parts, int* nparts, void* stream) {
+    UNETCA_REQUIRE(H % 2 == 0 && W % 2 == 0, "se_bn_bwd_reduce_pool: H, W must be even (got %d x %d)", H, W);
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, lds); REQ_CHAN(C, ldp); REQ_CHAN(C, ldy);
+        static int slots = 0;
+        if (!slots) slots = resident_blocks(se_bn_bwd_pool_kernel<T, false>);
+        const long nquad = (long)(H / 2) * (W / 2);
+        const long chunk = img_red_chunk<T>(C, nquad, B, slots);
+        dim3 grid(ceil_div(nquad, chunk), B);
+        se_bn_bwd_pool_kernel<T, false><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)sg, lds, (const T*)dpooled, ldp, pos, (const T*)y, ldy, nullptr, 0, H, W, C, chunk, 0.f, scale, shift, mean, nullptr, nullptr, nullptr, nullptr, parts);
+        *nparts = grid.x;
+    });
+    return check_launch("se_bn_bwd_reduce_pool");
+}
+
+// bn_bwd_apply (SE form) with the same on-the-fly block-output gradient
+int unetca_bn_bwd_apply_pool(int dtype, const void* sg, int lds, const void* dpooled, int ldp, const uint8_t* pos,
+                             const void* y, int ldy, void* dy, int lddy, int B, int H, int W, int C, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, const float* s, const float* dp,
+                             const float* coef, void* stream) {
+    UNETCA_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_bwd_apply_pool: H, W must be even (got %d x %d)", H, W);
+    DISPATCH_T(dtype, {
+        REQ_CHAN(C, lds); REQ_CHAN(C, ldp); REQ_CHAN(C, ldy); REQ_CHAN(C, lddy);
+        const long nquad = (long)(H / 2) * (W / 2);
+        const long chunk = (long)row_map<T>(C).rows * g_pool_quads * 2;
+        dim3 grid(ceil_div(nquad, chunk), B);
+        se_bn_bwd_pool_kernel<T, true><<<grid, kThreads, 0, (cudaStream_t)stream>>>((const T*)sg, lds, (const T*)dpooled, ldp, pos, (const T*)y, ldy, (T*)dy, lddy, H, W, C, chunk, 1.f / (float)((long)H * W), scale, shift, mean, invstd, s, dp, coef, nullptr);
+    });
+    return check_launch("bn_bwd_apply_pool");
 }
 
 // merged SE + ReLU + BN backward stage 1 (see se_bn_bwd_reduce_kernel).  parts: [B * *nparts][2][C]

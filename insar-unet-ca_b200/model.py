@@ -377,13 +377,15 @@ def _block_grad_order(pre, use_se):
                   pre + ".1.weight", pre + ".1.bias", pre + ".0.weight"]
 
 
-def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
+def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None):
     """Gradient of one DoubleConv block; dout is d(loss)/d(block output) (NHWC view).  Returns d/d(block input).
-    G: gradient sink with alloc(name, like) -> tensor to write into and put(name) once it is complete."""
+    G: gradient sink with alloc(name, like) -> tensor to write into and put(name) once it is complete.
+    lazy = (skip_grad, dpooled, pos) instead of dout: the output gradient of an encoder block, skip gradient plus the
+    max-pool routing of the pooled gradient, is rebuilt inside the two kernels that consume it (SE blocks, even H, W)."""
     blk = sv.blk
     B, Hl, Wl = sv.B, sv.H, sv.W
     C, O = blk.cin, blk.cout
-    dev = dout.device
+    dev = (dout if dout is not None else lazy[0]).device
     st = _stream()
     npix = B * Hl * Wl
     parts = eng.parts(B, dev)
@@ -396,8 +398,14 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
         # backward statistics are linear in (csrc/elementwise.cu: se_bn_bwd_reduce_kernel)
         w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
         Cr = w1.shape[0]
-        _lib.call("unetca_se_bn_bwd_reduce", dt, _ptr(dout), dout.stride(2), _ptr(sv.y2), O, B, Hl * Wl, O,
-                  _ptr(sv.scale2), _ptr(sv.shift2), _ptr(sv.mean2), _ptr(parts), ctypes.byref(nparts), st)
+        if lazy is not None:
+            sg, dpl, pos = lazy
+            _lib.call("unetca_se_bn_bwd_reduce_pool", dt, _ptr(sg), sg.stride(2), _ptr(dpl), dpl.stride(2), _ptr(pos),
+                      _ptr(sv.y2), O, B, Hl, Wl, O, _ptr(sv.scale2), _ptr(sv.shift2), _ptr(sv.mean2), _ptr(parts),
+                      ctypes.byref(nparts), st)
+        else:
+            _lib.call("unetca_se_bn_bwd_reduce", dt, _ptr(dout), dout.stride(2), _ptr(sv.y2), O, B, Hl * Wl, O,
+                      _ptr(sv.scale2), _ptr(sv.shift2), _ptr(sv.mean2), _ptr(parts), ctypes.byref(nparts), st)
         dpre2 = torch.empty(B, O, dtype=torch.float32, device=dev)
         dz = torch.empty(B, Cr, dtype=torch.float32, device=dev)
         dp = torch.empty(B, O, dtype=torch.float32, device=dev)
@@ -428,14 +436,20 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx):
             _lib.call("unetca_bn_bwd_finalize", _ptr(parts), nparts.value, O, npix, _ptr(bn.weight), _ptr(invstd),
                       _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
         dy = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
-        _lib.call("unetca_bn_bwd_apply", dt, _ptr(d_in), ld_in, _ptr(y), O, _ptr(dy), O, B, Hl * Wl, O, _ptr(scale),
-                  _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(coef), st)
+        if sums_ is not None and lazy is not None:
+            sg, dpl, pos = lazy
+            _lib.call("unetca_bn_bwd_apply_pool", dt, _ptr(sg), sg.stride(2), _ptr(dpl), dpl.stride(2), _ptr(pos), _ptr(y), O,
+                      _ptr(dy), O, B, Hl, Wl, O, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_),
+                      _ptr(coef), st)
+        else:
+            _lib.call("unetca_bn_bwd_apply", dt, _ptr(d_in), ld_in, _ptr(y), O, _ptr(dy), O, B, Hl * Wl, O, _ptr(scale),
+                      _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(coef), st)
         G.put(f"{pre}.{bn_idx}.weight")
         G.put(f"{pre}.{bn_idx}.bias")
         return dy
 
     # ---- [SE ->] ReLU -> BN2 backward
-    dy2 = bn_relu_bwd(dout, dout.stride(2), sv.y2, "2", s, dp, 4, sums)
+    dy2 = bn_relu_bwd(dout, dout.stride(2) if dout is not None else 0, sv.y2, "2", s, dp, 4, sums)
     # a conv bias in front of a train-mode BatchNorm has an analytically zero gradient (BN removes the mean)
     G.alloc(pre + ".3.bias", blk.conv2.bias).zero_()
     G.put(pre + ".3.bias")
@@ -549,13 +563,19 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
         dcur = torch.empty(B, hi, wi, 2 * Cl, dtype=tdt, device=dev)
         _lib.call("unetca_convT2x2_dgrad", dt, _ptr(du), ldu, _ptr(wd), _ptr(dcur), 2 * Cl, B, hi, wi, 2 * Cl, Cl, st)
     # ---- encoder, deep to shallow
+    lazy = None
     for l in range(4, -1, -1):
-        dpooled = _double_conv_bwd(eng, sv.enc[l], dcur, G, dt, tdt, l > 0)
+        dpooled = _double_conv_bwd(eng, sv.enc[l], dcur, G, dt, tdt, l > 0, lazy)
         if l == 0:
             break
         Hp, Wp, Cp = sv.Hs[l - 1], sv.Ws[l - 1], _WIDTHS[l - 1]
-        dcur = torch.empty(B, Hp, Wp, Cp, dtype=tdt, device=dev)
         sg = skip_grads[l - 1]
+        if model.use_se and Hp % 2 == 0 and Wp % 2 == 0:
+            # the next block rebuilds dO = skip gradient + unpool(dpooled) inside its own reduction / apply kernels
+            lazy, dcur = (sg, dpooled, sv.pos[l - 1]), None
+            continue
+        lazy = None
+        dcur = torch.empty(B, Hp, Wp, Cp, dtype=tdt, device=dev)
         _lib.call("unetca_pool_bwd_add", dt, _ptr(sg), sg.stride(2), _ptr(dpooled), Cp, _ptr(sv.pos[l - 1]), _ptr(dcur),
                   Cp, B, Hp, Wp, Cp, st)
     return G.finish()

@@ -558,3 +558,39 @@ def test_no_out_of_bounds_writes_on_odd_shapes(B, C, H, W):
 def _lib_max_parts(B):
     from unetca_b200 import _lib
     return _lib.load().unetca_max_parts(B)
+
+
+@pytest.mark.parametrize("dt", DTS)
+def test_encoder_backward_with_on_the_fly_unpool(dt):
+    """se_bn_bwd_reduce_pool / bn_bwd_apply_pool (dO rebuilt per quad from skip gradient + max-pool routing) against the
+    two-step path pool_bwd_add -> se_bn_bwd_reduce / bn_bwd_apply; the fused kernels keep dO in fp32, the two-step path
+    rounds it to the storage type in between, hence the tolerance in bf16."""
+    rs = np.random.RandomState(12)
+    B, C, H, W = 2, 128, 12, 16
+    tdt = TDT[dt]
+    y = torch.from_numpy(rs.standard_normal((B, H, W, C)).astype(np.float32)).to(tdt).cuda()
+    sg = torch.from_numpy(rs.standard_normal((B, H, W, 2 * C)).astype(np.float32)).to(tdt).cuda()[..., :C]   # strided view
+    dpl = torch.from_numpy(rs.standard_normal((B, H // 2, W // 2, C)).astype(np.float32)).to(tdt).cuda()
+    pos = torch.from_numpy(rs.randint(0, 4, (B, H // 2, W // 2, C)).astype(np.uint8)).cuda()
+    sc, sh = torch.rand(C, device="cuda") + 0.5, torch.randn(C, device="cuda") * 0.2
+    mean, invstd = torch.randn(C, device="cuda") * 0.2, torch.rand(C, device="cuda") + 0.5
+    s, dp = torch.rand(B, C, device="cuda"), torch.randn(B, C, device="cuda")
+    coef = torch.rand(3, C, device="cuda")
+    dcur = torch.empty(B, H, W, C, dtype=tdt, device="cuda")
+    call("unetca_pool_bwd_add", dt, ptr(sg), 2 * C, ptr(dpl), C, ptr(pos), ptr(dcur), C, B, H, W, C, stream())
+    pa, pb = parts_buf(B, 4096), parts_buf(B, 4096)
+    na, nb = cint(), cint()
+    call("unetca_se_bn_bwd_reduce", dt, ptr(dcur), C, ptr(y), C, B, H * W, C, ptr(sc), ptr(sh), ptr(mean), ptr(pa),
+         ctypes.byref(na), stream())
+    call("unetca_se_bn_bwd_reduce_pool", dt, ptr(sg), 2 * C, ptr(dpl), C, ptr(pos), ptr(y), C, B, H, W, C, ptr(sc), ptr(sh),
+         ptr(mean), ptr(pb), ctypes.byref(nb), stream())
+    ra = pa[: B * na.value * 2 * C].view(B, na.value, 2, C).sum(1)
+    rb = pb[: B * nb.value * 2 * C].view(B, nb.value, 2, C).sum(1)
+    assert relerr(rb, ra) < (1e-5 if dt == F32 else 1e-2)
+    dya = torch.empty(B, H, W, C, dtype=tdt, device="cuda")
+    dyb = torch.empty(B, H, W, C, dtype=tdt, device="cuda")
+    call("unetca_bn_bwd_apply", dt, ptr(dcur), C, ptr(y), C, ptr(dya), C, B, H * W, C, ptr(sc), ptr(sh), ptr(mean), ptr(invstd),
+         ptr(s), ptr(dp), ptr(coef), stream())
+    call("unetca_bn_bwd_apply_pool", dt, ptr(sg), 2 * C, ptr(dpl), C, ptr(pos), ptr(y), C, ptr(dyb), C, B, H, W, C, ptr(sc),
+         ptr(sh), ptr(mean), ptr(invstd), ptr(s), ptr(dp), ptr(coef), stream())
+    assert relerr(dyb.float(), dya.float()) < (1e-5 if dt == F32 else 1.5e-2)
