@@ -1060,7 +1060,16 @@ __global__ void __launch_bounds__(kThreads) outc_fwd_kernel(const T* __restrict_
     for (int i = threadIdx.x; i < NC * C; i += kThreads) wsm[i] = (i / C) < nc ? w[i] : 0.f;
     __syncthreads();
     const int lane = threadIdx.x & 31, sub = lane & 7, grp = lane >> 3;
-    const long warp_pix0 = ((long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32;
+    const long warp_stride = (long)gridDim.x * (kThreads / 32) * 32;
+    const bool one_pass = C == 8 * VEC;        // every lane group covers the pixel in one load: keep its weights in registers
+    float wr[NC][VEC];
+#pragma unroll
+    for (int o = 0; o < NC; ++o)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) wr[o][i] = one_pass ? wsm[o * C + sub * VEC + i] : 0.f;
+    // each warp walks 32-pixel groups with a grid stride: the weight prologue is paid once per block, not per 256 pixels
+    for (long warp_pix0 = ((long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) * 32; warp_pix0 < npix;
+         warp_pix0 += warp_stride) {
     float keep[NC];
 #pragma unroll
     for (int o = 0; o < NC; ++o) keep[o] = 0.f;
@@ -1070,7 +1079,14 @@ __global__ void __launch_bounds__(kThreads) outc_fwd_kernel(const T* __restrict_
         float acc[NC];
 #pragma unroll
         for (int o = 0; o < NC; ++o) acc[o] = 0.f;
-        if (p < npix) {
+        if (p < npix && one_pass) {
+            float v[VEC];
+            load_vec(x + p * ldx + sub * VEC, v);
+#pragma unroll
+            for (int o = 0; o < NC; ++o)
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) acc[o] = fmaf(v[i], wr[o][i], acc[o]);
+        } else if (p < npix) {
             for (int c0 = sub * VEC; c0 < C; c0 += 8 * VEC) {
                 float v[VEC];
                 load_vec(x + p * ldx + c0, v);
@@ -1098,6 +1114,7 @@ __global__ void __launch_bounds__(kThreads) outc_fwd_kernel(const T* __restrict_
         for (int o = 0; o < NC; ++o)
             if (o < nc) logits[(b * nc + o) * HW + hw] = keep[o] + bias[o];
     }
+    }
 }
 
 // outc backward: g (B,NC,H,W) fp32 = un-normalised dlogits, *gscale = 1/N_valid * upstream grad.
@@ -1124,12 +1141,15 @@ __global__ void __launch_bounds__(kThreads) outc_bwd_kernel(const float* __restr
         for (int i = 0; i < VEC; ++i) { acc[o][i] = 0.f; wv[o][i] = (o < nc && r < rows) ? w[o * C + cv * VEC + i] : 0.f; }
     }
     if (r < rows) {
+        // (image, pixel-in-image) of p, advanced incrementally: a 64-bit divide per pixel costs more than the FMAs
+        long b = (p0 + r) / HW, hw = (p0 + r) % HW;
 #pragma unroll 2
         for (long p = p0 + r; p < p1; p += rows) {
-            const long b = p / HW, hw = p % HW;
             float gv[NC];
 #pragma unroll
             for (int o = 0; o < NC; ++o) gv[o] = o < nc ? g[(b * nc + o) * HW + hw] : 0.f;
+            hw += rows;
+            while (hw >= HW) { hw -= HW; ++b; }
             float v[VEC], d[VEC];
             load_vec(x + p * ldx + cv * VEC, v);
 #pragma unroll
@@ -1957,7 +1977,8 @@ int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, co
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldx);
         const long npix = (long)B * HW;
-        const int nblk = ceil_div(npix, kThreads);
+        int nblk = ceil_div(npix, kThreads);
+        if (nblk > 8 * num_sms()) nblk = 8 * num_sms();
         cudaStream_t st = (cudaStream_t)stream;
         const int ncp = nc_pad(nc);
         const size_t sm = (size_t)ncp * C * sizeof(float);

@@ -40,7 +40,7 @@ def main():
     ap.add_argument("--scene", type=int, default=16384)
     ap.add_argument("--core", type=int, default=1024)
     ap.add_argument("--halo", type=int, default=128)
-    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--repeat", type=int, default=2, help="passes over this rank's tiles (the first is the warm-up)")
     a = ap.parse_args()
