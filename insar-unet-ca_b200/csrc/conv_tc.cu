@@ -1002,6 +1002,8 @@ struct alignas(64) PixNParams {
     signed char dw[12], par[12], off[12];
     float* stat_parts;
     int N;
+    const float* ep_scale;       // optional per-channel affine + ReLU applied in the epilogue (eval-mode BatchNorm)
+    const float* ep_shift;
 };
 constexpr int kPnStages = 3;
 constexpr int kPnABytes = 128 * 128, kPnBBytes = 256 * 128, kPnStageBytes = kPnABytes + kPnBBytes;
@@ -1015,7 +1017,8 @@ static_assert(kPnSmemBytes <= 227 * 1024, "pixn conv: shared memory budget");
 // thread-local sum / sum of squares of the stored values.  PARTIAL masks pixels outside the image.
 template <bool PARTIAL>
 __device__ __forceinline__ void pixn_drain(uint32_t t_addr, uint32_t my_s, float& s1, float& s2, int x0, int i0,
-                                           int twMask, int twShift, int W, int HP) {
+                                           int twMask, int twShift, int W, int HP, bool act = false, float ea = 1.f,
+                                           float eb = 0.f) {
     float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll 1
     for (int cb = 0; cb < 8; ++cb) {
@@ -1026,6 +1029,10 @@ __device__ __forceinline__ void pixn_drain(uint32_t t_addr, uint32_t my_s, float
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
             float f0 = __uint_as_float(v[i]), f1 = __uint_as_float(v[i + 1]);
+            if (act) {           // inference: BatchNorm (running statistics folded into ea, eb) + ReLU in the epilogue
+                f0 = fmaxf(fmaf(ea, f0, eb), 0.f);
+                f1 = fmaxf(fmaf(ea, f1, eb), 0.f);
+            }
             if (PARTIAL) {
                 const int n = cb * 32 + i;
                 if (!((x0 + (n & twMask)) < W && (i0 + (n >> twShift)) < HP)) f0 = 0.f;
@@ -1160,8 +1167,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
             named_bar_sync(1, 128);
             float s1 = 0.f, s2 = 0.f;
             const uint32_t my_s = smem_u32(my);
-            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0);
-            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, i0, p.TW - 1, p.twShift, p.W, p.HP);
+            const bool act = p.ep_scale != nullptr;
+            const int ech = p.P == 1 ? mb * 128 + r : mb * 64 + (r & 63);
+            const float ea = act ? __ldg(p.ep_scale + ech) : 1.f, eb = act ? __ldg(p.ep_shift + ech) : 0.f;
+            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, act, ea, eb);
+            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, i0, p.TW - 1, p.twShift, p.W, p.HP, act, ea, eb);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -1223,6 +1233,8 @@ struct alignas(64) HpixParams {
     int cchunks, num_m_blocks;
     float* stat_parts;
     int N;
+    const float* ep_scale;
+    const float* ep_shift;
 };
 constexpr int kHpThreads = 224;
 constexpr int kHpTW = 8, kHpTH = 32, kHpPitch = kHpTW + 2;
@@ -1356,8 +1368,10 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
             if (ep_tid == 0) tma_store_wait_read();
             named_bar_sync(1, 128);
             float s1 = 0.f, s2 = 0.f;
-            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0);
-            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, h0, kHpTW - 1, 3, p.W, p.H);
+            const bool act = p.ep_scale != nullptr;
+            const float ea = act ? __ldg(p.ep_scale + mb * 128 + r) : 1.f, eb = act ? __ldg(p.ep_shift + mb * 128 + r) : 0.f;
+            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, act, ea, eb);
+            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, h0, kHpTW - 1, 3, p.W, p.H, act, ea, eb);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -1404,6 +1418,8 @@ struct alignas(64) KwParams {
     int tilesX, tilesY, nimg, H, W;
     int cchunks;
     float* stat_parts;
+    const float* ep_scale;
+    const float* ep_shift;
 };
 constexpr int kKwTW = 32, kKwTH = 4, kKwOutW = kKwTW - 2;
 constexpr int kKwXBytes = kKwTW * (kKwTH + 2) * 128;      // 24 KB: [6 rows][32 px][64 ch]
@@ -1530,7 +1546,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __gr
                 for (int i = 0; i < 32; ++i) {
                     const float left = __shfl_up_sync(0xffffffffu, __uint_as_float(a[i]), 1);      // kw = 0 from column x-1
                     const float right = __shfl_down_sync(0xffffffffu, __uint_as_float(c2[i]), 1);  // kw = 2 from column x+1
-                    f[i] = valid ? (left + __uint_as_float(c1[i])) + right : 0.f;
+                    float t = (left + __uint_as_float(c1[i])) + right;
+                    if (p.ep_scale) t = fmaxf(fmaf(__ldg(p.ep_scale + half * 32 + i), t, __ldg(p.ep_shift + half * 32 + i)), 0.f);
+                    f[i] = valid ? t : 0.f;
                 }
                 if (inner) {
 #pragma unroll
@@ -1746,7 +1764,7 @@ static int make_map_linear(CUtensorMap* m, const void* base, long C, long W, lon
 
 // conv3x3 forward / dgrad for O % 128 == 0 through the haloed pixels-on-N kernel; w = packed filter [O][9*C]
 static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
-                       float* stat_parts, cudaStream_t st) {
+                       float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr) {
     HpixParams p;
     memset(&p, 0, sizeof(p));
     int rc;
@@ -1756,6 +1774,7 @@ static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, 
     p.tilesW = ceil_div(W, kHpTW); p.tilesH = ceil_div(H, kHpTH); p.nimg = B; p.H = H; p.W = W;
     p.cchunks = C / 64; p.num_m_blocks = O / 128;
     p.stat_parts = stat_parts; p.N = O;
+    p.ep_scale = ep_scale; p.ep_shift = ep_shift;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_hpix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHpSmemBytes);
@@ -1774,7 +1793,7 @@ static int g_no_kw = 0;
 
 // conv3x3 forward / dgrad for exactly 64 output channels and C in {64, 128}: kw-stacked kernel; w_kw from unetca_tc_pack_kw
 static int launch_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C,
-                     float* stat_parts, cudaStream_t st) {
+                     float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr) {
     KwParams p;
     memset(&p, 0, sizeof(p));
     const int cch = C / 64;
@@ -1786,6 +1805,7 @@ static int launch_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy,
     p.tilesX = ceil_div(W, kKwOutW); p.tilesY = ceil_div(H, kKwTH); p.nimg = B; p.H = H; p.W = W;
     p.cchunks = cch;
     p.stat_parts = stat_parts;
+    p.ep_scale = ep_scale; p.ep_shift = ep_shift;
     const int xs = cch == 1 ? 4 : 2;
     const int smem = kw_smem_bytes(cch, xs);
     static bool attr_done = false;
@@ -1852,7 +1872,8 @@ static int launch_pixn_kernel(const PixNParams& p, int CL, cudaStream_t st, cons
 
 // w: P == 1: packed filter [O][9*C];  P == 2: pair-packed filter [2*O][12*C] (unetca_pack_conv3x3_pair)
 static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
-                       int P, float* stat_parts, cudaStream_t st) {
+                       int P, float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr,
+                       const float* ep_shift = nullptr) {
     PixNParams p;
     memset(&p, 0, sizeof(p));
     const int HP = H / P;
@@ -1877,6 +1898,7 @@ static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, 
         else { p.par[t] = (signed char)(d & 1); p.off[t] = (signed char)(d < 0 ? -1 : d / 2); }
     }
     p.stat_parts = stat_parts; p.N = O;
+    p.ep_scale = ep_scale; p.ep_shift = ep_shift;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
@@ -1891,7 +1913,8 @@ static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, 
 // First conv in the row-pair layout (see elementwise.cu: im2col_pairs_kernel): one GEMM over the pixel-pair rows
 // colp [B*(H/2)*W][64] with the pair-packed filter wp [2*O][64] through the pixels-on-N kernel (one "tap", one chunk).
 static int launch_first_pairs(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O,
-                              float* stat_parts, cudaStream_t st) {
+                              float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr,
+                              const float* ep_shift = nullptr) {
     PixNParams p;
     memset(&p, 0, sizeof(p));
     const int HP = H / 2;
@@ -1908,6 +1931,7 @@ static int launch_first_pairs(const void* colp, const void* wp, void* y, int ldy
     p.ntaps = 1; p.cchunks = 1;
     p.num_m_blocks = O / 64;
     p.stat_parts = stat_parts; p.N = O;
+    p.ep_scale = ep_scale; p.ep_shift = ep_shift;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
@@ -1958,6 +1982,33 @@ int unetca_tc_pack_kw(const void* w, int ld, void* w_kw, int C, void* stream) {
     return check_launch("tc_pack_kw");
 }
 void unetca_tc_force_no_kw(int on) { g_no_kw = on; }
+
+// Inference forms: conv3x3 + eval-mode BatchNorm (scale, shift = running statistics folded, unetca_bn_fold_eval) + ReLU
+// in the epilogue of the tcgen05 kernels, so the pre-activation tensor is never written.  layout: 0 = packed filter
+// [O][9*C] (needs O % 128 == 0), 1 = pair-packed filter (O % 64 == 0, H even), 2 = kw-stacked filter (O = 64, C = 128).
+int unetca_tc_conv3x3_bnrelu_fwd(const void* x, int ldx, const void* w, int layout, void* y, int ldy, int B, int H, int W,
+                                 int C, int O, const float* scale, const float* shift, void* stream) {
+    UNETCA_REQUIRE(scale && shift && C % 64 == 0 && O % 64 == 0 && O <= 1024, "tc_conv3x3_bnrelu: C=%d O=%d", C, O);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (layout == 0) {
+        UNETCA_REQUIRE(O % 128 == 0, "tc_conv3x3_bnrelu: layout 0 needs O %% 128 == 0 (O=%d)", O);
+        rc = launch_hpix(x, ldx, w, 9 * C, y, ldy, B, H, W, C, O, nullptr, st, scale, shift);
+    } else if (layout == 1) {
+        UNETCA_REQUIRE(H % 2 == 0, "tc_conv3x3_bnrelu: layout 1 needs an even H (H=%d)", H);
+        rc = launch_pixn(x, ldx, w, 12 * C, y, ldy, B, H, W, C, O, 2, nullptr, st, scale, shift);
+    } else {
+        UNETCA_REQUIRE(O == 64 && C == 128, "tc_conv3x3_bnrelu: layout 2 needs O = 64, C = 128 (O=%d C=%d)", O, C);
+        rc = launch_kw(x, ldx, w, y, ldy, B, H, W, C, nullptr, st, scale, shift);
+    }
+    return rc < 0 ? rc : 0;
+}
+int unetca_tc_first_pairs_bnrelu_fwd(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O,
+                                     const float* scale, const float* shift, void* stream) {
+    UNETCA_REQUIRE(scale && shift && O % 64 == 0 && O <= 1024 && H % 2 == 0, "tc_first_pairs_bnrelu: O=%d H=%d", O, H);
+    int rc = launch_first_pairs(colp, wp, y, ldy, B, H, W, O, nullptr, (cudaStream_t)stream, scale, shift);
+    return rc < 0 ? rc : 0;
+}
 
 // w_pair [2*rows][12*C] from the K-major packed filter w [rows][ld] (k = tap*C + c)
 int unetca_tc_pack_pair(const void* w, int ld, void* w_pair, int rows, int C, void* stream) {

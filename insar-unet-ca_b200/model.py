@@ -115,6 +115,15 @@ class _Engine:
     def ws(self, device):
         return self.scratch("ws", _WS_FLOATS, torch.float32, device)
 
+    def identity_affine(self, C, device):
+        """(ones, zeros) of length C: the BatchNorm arguments of the SE kernels when they run on an activation"""
+        key = ("ident", C)
+        t = self._scratch.get(key)
+        if t is None or t[0].device != device:
+            t = (torch.ones(C, dtype=torch.float32, device=device), torch.zeros(C, dtype=torch.float32, device=device))
+            self._scratch[key] = t
+        return t
+
     # ---- packed weights ------------------------------------------------------------------------------
     def _cached(self, key, param, tdt, build):
         """Packed operand copy of `param`.  The copies are rebuilt by every train-mode forward and by the first eval
@@ -194,6 +203,24 @@ def sv_pairs(col, B, H, W):
     return col is not None and col.shape[0] == B * (H // 2) * W and H % 2 == 0
 
 
+def _conv3x3_bnrelu(dt, x, ldx, w, w_pair, y, ldy, B, H, W, C, O, scale, shift, st):
+    """Inference: conv3x3 + folded eval-mode BatchNorm + ReLU in one tcgen05 kernel (UCA:81-86 under model.eval()).
+    Returns False when this shape has no fused kernel (the caller then runs conv and bn_relu separately)."""
+    if dt != _lib.BF16 or _lib.load().unetca_get_conv_impl() != 0:
+        return False
+    if isinstance(w_pair, tuple) and w_pair[0] == "kw":
+        layout, wt = 2, w_pair[1]
+    elif isinstance(w_pair, tuple) and w_pair[0] == "pair" and H % 2 == 0:
+        layout, wt = 1, w_pair[1]
+    elif O % 128 == 0:
+        layout, wt = 0, w
+    else:
+        return False
+    _lib.call("unetca_conv3x3_bnrelu_fwd", dt, _ptr(x), ldx, _ptr(wt), layout, _ptr(y), ldy, B, H, W, C, O, _ptr(scale),
+              _ptr(shift), st)
+    return True
+
+
 def _check_input(model, x):
     if not isinstance(x, torch.Tensor) or x.dim() != 4:
         raise ValueError("UNet expects a 4-D (B, C, H, W) tensor")
@@ -241,6 +268,10 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
         return scale, shift
 
     sp = _ptr(parts) if train else None
+    if not train and not keep and dt == _lib.BF16:
+        done = _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, dt, tdt, bn_params, parts, nparts)
+        if done:
+            return sv
     # ---- conv1 -> BN -> ReLU
     wf1, _, ldk1, wfp1, _ = eng.conv_w(blk.conv1, dt, tdt, blk.first)
     y1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
@@ -285,6 +316,64 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
     if keep:
         sv.y1, sv.a1, sv.y2 = y1, a1, y2
     return sv
+
+
+def _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, dt, tdt, bn_params, parts, nparts):
+    """Inference form of one DoubleConv: BatchNorm uses running statistics, so both conv + BN + ReLU pairs run as single
+    tcgen05 kernels (the activation is what gets written; the pre-BN tensors never exist), followed by the SE squeeze /
+    scale (+ max-pool) passes on the activation with an identity affine.  Returns False if a conv of this block has
+    no fused kernel for its shape."""
+    dev = out_view.device
+    st = _stream()
+    C, O = blk.cin, blk.cout
+    wf1, _, ldk1, wfp1, _ = eng.conv_w(blk.conv1, dt, tdt, blk.first)
+    wf2, _, ldk2, wfp2, _ = eng.conv_w(blk.conv2, dt, tdt, False)
+    # can both convolutions be fused?  (decide before launching anything)
+    tc = _lib.load().unetca_get_conv_impl() == 0
+
+    def fusable(w_pair, Cin, first):
+        if not tc:
+            return False
+        if first:
+            return sv_pairs(col, B, Hl, Wl)
+        if isinstance(w_pair, tuple) and (w_pair[0] == "kw" or Hl % 2 == 0):
+            return True
+        return O % 128 == 0
+    if not (fusable(wfp1, C, blk.first) and fusable(wfp2, O, False)):
+        return False
+    scale1, shift1 = bn_params(blk.bn1, blk.conv1, "1")
+    a1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
+    if blk.first:
+        _lib.call("unetca_first_pairs_bnrelu_fwd", dt, _ptr(col), _ptr(wfp1), _ptr(a1), O, B, Hl, Wl, O, _ptr(scale1),
+                  _ptr(shift1), st)
+    else:
+        ok = _conv3x3_bnrelu(dt, xin, xin.stride(2), wf1, wfp1, a1, O, B, Hl, Wl, C, O, scale1, shift1, st)
+        assert ok
+    scale2, shift2 = bn_params(blk.bn2, blk.conv2, "2")
+    a2 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
+    ok = _conv3x3_bnrelu(dt, a1, O, wf2, wfp2, a2, O, B, Hl, Wl, O, O, scale2, shift2, st)
+    assert ok
+    one, zero = eng.identity_affine(O, dev)
+    s = None
+    if blk.se is not None:
+        w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
+        Cr = w1.shape[0]
+        _lib.call("unetca_se_squeeze", dt, _ptr(a2), O, B, Hl * Wl, O, _ptr(one), _ptr(zero), _ptr(parts),
+                  ctypes.byref(nparts), st)
+        p = torch.empty(B, O, dtype=torch.float32, device=dev)
+        z = torch.empty(B, Cr, dtype=torch.float32, device=dev)
+        s = torch.empty(B, O, dtype=torch.float32, device=dev)
+        _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(one), _ptr(zero),
+                  None, _ptr(p), _ptr(z), _ptr(s), None, st)
+    if pooled is not None and (Hl % 2 or Wl % 2):
+        _lib.call("unetca_se_scale_pool", dt, _ptr(a2), O, _ptr(out_view), out_view.stride(2), None, 0, None, B, Hl, Wl,
+                  O, _ptr(one), _ptr(zero), _ptr(s), st)
+        _lib.call("unetca_maxpool2x2", dt, _ptr(out_view), out_view.stride(2), _ptr(pooled), pooled.stride(2), _ptr(pos),
+                  None, B, Hl, Wl, O, st)
+    else:
+        _lib.call("unetca_se_scale_pool", dt, _ptr(a2), O, _ptr(out_view), out_view.stride(2), _ptr(pooled),
+                  pooled.stride(2) if pooled is not None else 0, _ptr(pos), B, Hl, Wl, O, _ptr(one), _ptr(zero), _ptr(s), st)
+    return True
 
 
 def _forward(model: "UNet", x: torch.Tensor, keep: bool):
