@@ -231,6 +231,48 @@ def cpu_reference_step_time(steps, warmup, size, sample_b=2):
     return times, sample_b
 
 
+def run_reference_gpu(args):
+    """EXTRA, not one of the contract's arms: the reference's own module stack (oracle port = the same ATen ops) on the
+    B200 through cuDNN, channels_last + autocast(bf16) — the honest GPU competitor named in SURVEY.md 8(d)."""
+    from oracle import unet_ca_port as port        # baseline leg only
+    dev = torch.device("cuda", 0)
+    B, S = args.batch, args.size
+    sd = port.make_state_dict(seed=0)
+    p = {k: (v.to(dev).requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.to(dev))
+         for k, v in sd.items()}
+    opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4, fused=True)
+    g = torch.Generator(device=dev).manual_seed(1234)
+    x = torch.randn(B, 3, S, S, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 2, (B, S, S), device=dev, generator=g)
+    torch.backends.cudnn.benchmark = True
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits = port.unet_forward(x, p, train=True)
+        loss = port.loss_fn(logits.float(), y)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({"impl": "reference-gpu (extra)", "metric": METRIC, "value": B * args.steps / (ms / 1e3), "unit": UNIT,
+                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+                      "higher_is_better": True, "dtype": "bf16 autocast", "data": "synthetic",
+                      "config": {"workload": f"the reference's module stack (ATen ops via oracle/unet_ca_port.py) on one B200: cuDNN, "
+                                             f"channels_last, autocast(bf16), fused Adam; batch {B}, 3x{S}x{S}"},
+                      "final_loss": loss.item()}), flush=True)
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -259,7 +301,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"],
+                    help="reference = the reference's CPU path (contract arm); reference-gpu = EXTRA: the same ATen ops on the "
+                         "GPU through cuDNN (channels_last + autocast bf16)")
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
@@ -277,6 +321,10 @@ def main():
 
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.impl == "reference-gpu":
+        if rank == 0:
+            run_reference_gpu(args)
         return
 
     import torch.distributed as dist
@@ -480,9 +528,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         times, sb = cpu_reference_step_time(2, 1, S)
         v = sb * len(times) / sum(times)
+        # BASELINE.json configs[0] exactly: batch 4, 3x256x256, fp32, best of 3 after 1 warm-up
+        t0, _ = cpu_reference_step_time(3, 1, 256, sample_b=4)
         cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": f"{sb} images of 3x{S}x{S} per step (of the {B}-image batch), fp32 fwd+CE+bwd+Adam, 2 timed steps "
-                         f"after 1 warm-up, ATen CPU kernels via oracle/unet_ca_port.py"}
+                         f"after 1 warm-up, ATen CPU kernels via oracle/unet_ca_port.py",
+               "configs0": {"value": 4 / min(t0), "unit": UNIT,
+                            "sample": "BASELINE configs[0]: batch 4, 3x256x256, fp32 fwd+CE+bwd+Adam, best of 3 after 1 warm-up"}}
 
     if rank == 0:
         gflop_img = TRAIN_GFLOP_PER_IMG_512 * (S * S) / (512 * 512)
