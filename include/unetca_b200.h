@@ -74,8 +74,10 @@ int unetca_conv3x3_fwd_kw(int dtype, const void* x, int ldx, const void* w_kw, v
 int unetca_pack_conv3x3_kw(int dtype, const void* w, int ld, void* w_kw, int C, void* stream);
 /* inference forms (bf16 tcgen05 path): conv3x3 + eval-mode BatchNorm folded to (scale, shift) by unetca_bn_fold_eval + ReLU
  * applied in the conv epilogue — UCA:81-86 under model.eval() (UCA:276) without writing the pre-activation tensor.
- * layout 0: w = packed filter [O][9*C], O % 128 == 0; 1: w = pair-packed filter, H even; 2: w = kw-stacked filter */
-int unetca_conv3x3_bnrelu_fwd(int dtype, const void* x, int ldx, const void* w, int layout, void* y, int ldy, int B, int H, int W, int C, int O, const float* scale, const float* shift, void* stream);
+ * layout 0: w = packed filter [O][9*C], O % 128 == 0; 1: w = pair-packed filter, H even; 2: w = kw-stacked filter.
+ * sq_parts (optional, layouts 0/1; zero-filled by the caller: B * unetca_num_sms() * O floats) receives the SE squeeze as
+ * per-image partial channel sums [B][*nparts][O] of the stored activation, ready for unetca_se_fc */
+int unetca_conv3x3_bnrelu_fwd(int dtype, const void* x, int ldx, const void* w, int layout, void* y, int ldy, int B, int H, int W, int C, int O, const float* scale, const float* shift, float* sq_parts, int* nparts, void* stream);
 int unetca_first_pairs_bnrelu_fwd(int dtype, const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O, const float* scale, const float* shift, void* stream);
 /* first conv (Cin <= 5, H even) in the row-pair layout of the tcgen05 path (bf16): one im2col row per pixel PAIR
  * (rows 2i, 2i+1 of a column) holding their shared 4x3 patch, colp [B*(H/2)*W][64]; pair-packed filter wp [2*O][64];
@@ -157,7 +159,7 @@ int unetca_tc_conv3x3_fwd_paired(const void* x, int ldx, const void* w_pair, voi
 int unetca_tc_pack_pair(const void* w, int ld, void* w_pair, int rows, int C, void* stream);
 int unetca_tc_conv3x3_fwd_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C, float* stat_parts, void* stream);
 int unetca_tc_pack_kw(const void* w, int ld, void* w_kw, int C, void* stream);
-int unetca_tc_conv3x3_bnrelu_fwd(const void* x, int ldx, const void* w, int layout, void* y, int ldy, int B, int H, int W, int C, int O, const float* scale, const float* shift, void* stream);
+int unetca_tc_conv3x3_bnrelu_fwd(const void* x, int ldx, const void* w, int layout, void* y, int ldy, int B, int H, int W, int C, int O, const float* scale, const float* shift, float* sq_parts, void* stream);
 int unetca_tc_first_pairs_bnrelu_fwd(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O, const float* scale, const float* shift, void* stream);
 int unetca_tc_first_pairs_fwd(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O, float* stat_parts, void* stream);
 int unetca_tc_first_pairs_wgrad(const void* dy, int lddy, const void* colp, float* ws, long ws_floats, int B, int H, int W, int O, void* stream);

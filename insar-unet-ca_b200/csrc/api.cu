@@ -12,7 +12,7 @@ int unetca_tc_conv3x3_fwd_paired(const void*, int, const void*, void*, int, int,
 int unetca_tc_pack_pair(const void*, int, void*, int, int, void*);
 int unetca_tc_conv3x3_fwd_kw(const void*, int, const void*, void*, int, int, int, int, int, float*, void*);
 int unetca_tc_pack_kw(const void*, int, void*, int, void*);
-int unetca_tc_conv3x3_bnrelu_fwd(const void*, int, const void*, int, void*, int, int, int, int, int, int, const float*, const float*, void*);
+int unetca_tc_conv3x3_bnrelu_fwd(const void*, int, const void*, int, void*, int, int, int, int, int, int, const float*, const float*, float*, void*);
 int unetca_tc_first_pairs_bnrelu_fwd(const void*, const void*, void*, int, int, int, int, int, const float*, const float*, void*);
 int unetca_tc_first_pairs_fwd(const void*, const void*, void*, int, int, int, int, int, float*, void*);
 int unetca_tc_first_pairs_wgrad(const void*, int, const void*, float*, long, int, int, int, int, void*);
@@ -73,9 +73,13 @@ int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_p
 
 // Inference: conv3x3 + folded eval-mode BatchNorm + ReLU in one tcgen05 kernel (bf16 tensor-core path only).
 int unetca_conv3x3_bnrelu_fwd(int dtype, const void* x, int ldx, const void* w, int layout, void* y, int ldy, int B, int H,
-                              int W, int C, int O, const float* scale, const float* shift, void* stream) {
+                              int W, int C, int O, const float* scale, const float* shift, float* sq_parts, int* nparts,
+                              void* stream) {
     if (!use_tc(dtype)) { unetca::set_error("conv3x3_bnrelu_fwd: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
-    return unetca_tc_conv3x3_bnrelu_fwd(x, ldx, w, layout, y, ldy, B, H, W, C, O, scale, shift, stream);
+    int rc = unetca_tc_conv3x3_bnrelu_fwd(x, ldx, w, layout, y, ldy, B, H, W, C, O, scale, shift, sq_parts, stream);
+    if (rc < 0) return rc;
+    if (nparts) *nparts = rc;
+    return 0;
 }
 int unetca_first_pairs_bnrelu_fwd(int dtype, const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O,
                                   const float* scale, const float* shift, void* stream) {

@@ -1004,6 +1004,7 @@ struct alignas(64) PixNParams {
     int N;
     const float* ep_scale;       // optional per-channel affine + ReLU applied in the epilogue (eval-mode BatchNorm)
     const float* ep_shift;
+    float* sq_parts;             // optional [nimg][gridDim.x][N]: per-image channel sums of the stored activations (SE squeeze)
 };
 constexpr int kPnStages = 3;
 constexpr int kPnABytes = 128 * 128, kPnBBytes = 256 * 128, kPnStageBytes = kPnABytes + kPnBBytes;
@@ -1011,6 +1012,17 @@ constexpr int kPnOutBytes = 2 * 256 * 128;
 constexpr int kPnStatBytes = 2 * 1024 * 4 + 256 * 4;
 constexpr int kPnSmemBytes = 1024 + kPnStages * kPnStageBytes + kPnOutBytes + kPnStatBytes + 256;
 static_assert(kPnSmemBytes <= 227 * 1024, "pixn conv: shared memory budget");
+
+// write this CTA's per-image channel sums (the entries of sm_sq owned by epilogue thread r) to
+// sq_parts[image][blockIdx.x][N] and clear them; P = 1: thread r owns channels mb*128 + r, P = 2: threads r < 64 own mb*64 + r
+__device__ __forceinline__ void pixn_flush_sq(float* sq_parts, float* sm_sq, int image, int N, int P, int num_m_blocks, int r) {
+    float* dst = sq_parts + ((long)image * gridDim.x + blockIdx.x) * N;
+    if (P == 1) {
+        for (int mb = 0; mb < num_m_blocks; ++mb) { dst[mb * 128 + r] = sm_sq[mb * 128 + r]; sm_sq[mb * 128 + r] = 0.f; }
+    } else if (r < 64) {
+        for (int mb = 0; mb < num_m_blocks; ++mb) { dst[mb * 64 + r] = sm_sq[mb * 64 + r]; sm_sq[mb * 64 + r] = 0.f; }
+    }
+}
 
 // epilogue of the pixels-on-N kernel for one thread (= one accumulator row = one channel): 256 fp32 columns (pixels)
 // -> bf16 -> staging[pixel][channel] (2-byte stores; a warp covers 64 contiguous bytes per pixel), plus the
@@ -1077,7 +1089,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
         prefetch_tmap(&p.mapOut);
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
-    if (p.stat_parts) {
+    if (p.stat_parts || p.sq_parts) {
         for (int i = threadIdx.x; i < 2 * p.N; i += kTcThreads) sm_stats[i] = 0.f;
     }
     tcgen05_fence_before();
@@ -1154,6 +1166,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
         const int box = r >> 6, oc = r & 63;
         uint8_t* my = out_stage + box * (256 * 128) + oc * 2;
         int as = 0; uint32_t aph = 0;
+        int cur_b = -1;
         for (long t = first; t < num_work; t += stride) {
             const int mb = (int)(t % p.num_m_blocks);
             const long mt = (t / p.num_m_blocks) * CL + crank;
@@ -1200,8 +1213,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
                     }
                 }
             }
+            if (p.sq_parts && b < p.nimg) {
+                // SE squeeze of the stored activation: per-image channel sums, flushed when this CTA moves to the next image
+                if (b != cur_b) {
+                    if (cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, p.P, p.num_m_blocks, r);
+                    cur_b = b;
+                }
+                if (p.P == 1) sm_stats[mb * 128 + r] += s1;
+                else {
+                    sm_wpart[r] = s1;
+                    named_bar_sync(1, 128);
+                    if (r < 64) sm_stats[mb * 64 + r] += sm_wpart[r] + sm_wpart[r + 64];
+                    named_bar_sync(1, 128);
+                }
+            }
             as ^= 1; if (as == 0) aph ^= 1;
         }
+        if (p.sq_parts && cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, p.P, p.num_m_blocks, r);
         if (ep_tid == 0) tma_store_wait_all();
         named_bar_sync(1, 128);
         if (p.stat_parts) {
@@ -1235,6 +1263,7 @@ struct alignas(64) HpixParams {
     int N;
     const float* ep_scale;
     const float* ep_shift;
+    float* sq_parts;             // optional [nimg][gridDim.x][N] per-image channel sums (SE squeeze of the activation)
 };
 constexpr int kHpThreads = 224;
 constexpr int kHpTW = 8, kHpTH = 32, kHpPitch = kHpTW + 2;
@@ -1272,7 +1301,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
         prefetch_tmap(&p.mapOut);
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
-    if (p.stat_parts) {
+    if (p.stat_parts || p.sq_parts) {
         for (int i = threadIdx.x; i < 2 * p.N; i += kHpThreads) sm_stats[i] = 0.f;
     }
     tcgen05_fence_before();
@@ -1356,6 +1385,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
         const int box = r >> 6, oc = r & 63;
         const uint32_t my_s = smem_u32(out_stage + box * (256 * 128) + oc * 2);
         int as = 0; uint32_t aph = 0;
+        int cur_b = -1;
         for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
             const int mb = (int)(t % p.num_m_blocks);
             const int mt = (int)(t / p.num_m_blocks);
@@ -1386,8 +1416,16 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
                 sm_stats[mb * 128 + r] += s1;
                 sm_stats[p.N + mb * 128 + r] += s2;
             }
+            if (p.sq_parts) {
+                if (b != cur_b) {
+                    if (cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
+                    cur_b = b;
+                }
+                sm_stats[mb * 128 + r] += s1;
+            }
             as ^= 1; if (as == 0) aph ^= 1;
         }
+        if (p.sq_parts && cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
         if (ep_tid == 0) tma_store_wait_all();
         named_bar_sync(1, 128);
         if (p.stat_parts) {
@@ -1764,7 +1802,8 @@ static int make_map_linear(CUtensorMap* m, const void* base, long C, long W, lon
 
 // conv3x3 forward / dgrad for O % 128 == 0 through the haloed pixels-on-N kernel; w = packed filter [O][9*C]
 static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
-                       float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr) {
+                       float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr,
+                       float* sq_parts = nullptr) {
     HpixParams p;
     memset(&p, 0, sizeof(p));
     int rc;
@@ -1774,7 +1813,7 @@ static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, 
     p.tilesW = ceil_div(W, kHpTW); p.tilesH = ceil_div(H, kHpTH); p.nimg = B; p.H = H; p.W = W;
     p.cchunks = C / 64; p.num_m_blocks = O / 128;
     p.stat_parts = stat_parts; p.N = O;
-    p.ep_scale = ep_scale; p.ep_shift = ep_shift;
+    p.ep_scale = ep_scale; p.ep_shift = ep_shift; p.sq_parts = sq_parts;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_hpix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHpSmemBytes);
@@ -1873,7 +1912,7 @@ static int launch_pixn_kernel(const PixNParams& p, int CL, cudaStream_t st, cons
 // w: P == 1: packed filter [O][9*C];  P == 2: pair-packed filter [2*O][12*C] (unetca_pack_conv3x3_pair)
 static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
                        int P, float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr,
-                       const float* ep_shift = nullptr) {
+                       const float* ep_shift = nullptr, float* sq_parts = nullptr) {
     PixNParams p;
     memset(&p, 0, sizeof(p));
     const int HP = H / P;
@@ -1898,7 +1937,7 @@ static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, 
         else { p.par[t] = (signed char)(d & 1); p.off[t] = (signed char)(d < 0 ? -1 : d / 2); }
     }
     p.stat_parts = stat_parts; p.N = O;
-    p.ep_scale = ep_scale; p.ep_shift = ep_shift;
+    p.ep_scale = ep_scale; p.ep_shift = ep_shift; p.sq_parts = sq_parts;
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
@@ -1986,22 +2025,25 @@ void unetca_tc_force_no_kw(int on) { g_no_kw = on; }
 // Inference forms: conv3x3 + eval-mode BatchNorm (scale, shift = running statistics folded, unetca_bn_fold_eval) + ReLU
 // in the epilogue of the tcgen05 kernels, so the pre-activation tensor is never written.  layout: 0 = packed filter
 // [O][9*C] (needs O % 128 == 0), 1 = pair-packed filter (O % 64 == 0, H even), 2 = kw-stacked filter (O = 64, C = 128).
+// sq_parts (optional, layouts 0 and 1): [B][ret][O] per-image channel sums of the stored activations — the SE squeeze
+// (UCA:65) taken in the epilogue; the caller zero-fills B * unetca_num_sms() * O floats first.  Returns the number of
+// partial rows per image (> 0) or < 0 on error.
 int unetca_tc_conv3x3_bnrelu_fwd(const void* x, int ldx, const void* w, int layout, void* y, int ldy, int B, int H, int W,
-                                 int C, int O, const float* scale, const float* shift, void* stream) {
+                                 int C, int O, const float* scale, const float* shift, float* sq_parts, void* stream) {
     UNETCA_REQUIRE(scale && shift && C % 64 == 0 && O % 64 == 0 && O <= 1024, "tc_conv3x3_bnrelu: C=%d O=%d", C, O);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (layout == 0) {
         UNETCA_REQUIRE(O % 128 == 0, "tc_conv3x3_bnrelu: layout 0 needs O %% 128 == 0 (O=%d)", O);
-        rc = launch_hpix(x, ldx, w, 9 * C, y, ldy, B, H, W, C, O, nullptr, st, scale, shift);
+        rc = launch_hpix(x, ldx, w, 9 * C, y, ldy, B, H, W, C, O, nullptr, st, scale, shift, sq_parts);
     } else if (layout == 1) {
         UNETCA_REQUIRE(H % 2 == 0, "tc_conv3x3_bnrelu: layout 1 needs an even H (H=%d)", H);
-        rc = launch_pixn(x, ldx, w, 12 * C, y, ldy, B, H, W, C, O, 2, nullptr, st, scale, shift);
+        rc = launch_pixn(x, ldx, w, 12 * C, y, ldy, B, H, W, C, O, 2, nullptr, st, scale, shift, sq_parts);
     } else {
-        UNETCA_REQUIRE(O == 64 && C == 128, "tc_conv3x3_bnrelu: layout 2 needs O = 64, C = 128 (O=%d C=%d)", O, C);
+        UNETCA_REQUIRE(O == 64 && C == 128 && !sq_parts, "tc_conv3x3_bnrelu: layout 2 needs O = 64, C = 128, no squeeze sums (O=%d C=%d)", O, C);
         rc = launch_kw(x, ldx, w, y, ldy, B, H, W, C, nullptr, st, scale, shift);
     }
-    return rc < 0 ? rc : 0;
+    return rc;
 }
 int unetca_tc_first_pairs_bnrelu_fwd(const void* colp, const void* wp, void* y, int ldy, int B, int H, int W, int O,
                                      const float* scale, const float* shift, void* stream) {

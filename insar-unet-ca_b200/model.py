@@ -203,7 +203,10 @@ def sv_pairs(col, B, H, W):
     return col is not None and col.shape[0] == B * (H // 2) * W and H % 2 == 0
 
 
-def _conv3x3_bnrelu(dt, x, ldx, w, w_pair, y, ldy, B, H, W, C, O, scale, shift, st):
+FUSE_SQUEEZE = True      # inference: take the SE squeeze in the second conv's epilogue (False: separate read-only pass)
+
+
+def _conv3x3_bnrelu(dt, x, ldx, w, w_pair, y, ldy, B, H, W, C, O, scale, shift, st, sq_parts=None, nparts=None):
     """Inference: conv3x3 + folded eval-mode BatchNorm + ReLU in one tcgen05 kernel (UCA:81-86 under model.eval()).
     Returns False when this shape has no fused kernel (the caller then runs conv and bn_relu separately)."""
     if dt != _lib.BF16 or _lib.load().unetca_get_conv_impl() != 0:
@@ -216,8 +219,10 @@ def _conv3x3_bnrelu(dt, x, ldx, w, w_pair, y, ldy, B, H, W, C, O, scale, shift, 
         layout, wt = 0, w
     else:
         return False
+    if layout == 2:
+        sq_parts = None                     # the kw-stacked kernel has no squeeze sums (it never is a block's second conv)
     _lib.call("unetca_conv3x3_bnrelu_fwd", dt, _ptr(x), ldx, _ptr(wt), layout, _ptr(y), ldy, B, H, W, C, O, _ptr(scale),
-              _ptr(shift), st)
+              _ptr(shift), _ptr(sq_parts), nparts, st)
     return True
 
 
@@ -351,20 +356,34 @@ def _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos
         assert ok
     scale2, shift2 = bn_params(blk.bn2, blk.conv2, "2")
     a2 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
-    ok = _conv3x3_bnrelu(dt, a1, O, wf2, wfp2, a2, O, B, Hl, Wl, O, O, scale2, shift2, st)
-    assert ok
     one, zero = eng.identity_affine(O, dev)
     s = None
     if blk.se is not None:
         w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
         Cr = w1.shape[0]
-        _lib.call("unetca_se_squeeze", dt, _ptr(a2), O, B, Hl * Wl, O, _ptr(one), _ptr(zero), _ptr(parts),
-                  ctypes.byref(nparts), st)
         p = torch.empty(B, O, dtype=torch.float32, device=dev)
         z = torch.empty(B, Cr, dtype=torch.float32, device=dev)
         s = torch.empty(B, O, dtype=torch.float32, device=dev)
-        _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(one), _ptr(zero),
-                  None, _ptr(p), _ptr(z), _ptr(s), None, st)
+        kw2 = isinstance(wfp2, tuple) and wfp2[0] == "kw"
+        if FUSE_SQUEEZE and not kw2:
+            # the second conv's epilogue also leaves the SE squeeze: per-image partial channel sums of the activation
+            nsq = B * _lib.load().unetca_num_sms() * O
+            sq = eng.scratch("sq_parts", nsq, torch.float32, dev)
+            sq[:nsq].zero_()
+            ok = _conv3x3_bnrelu(dt, a1, O, wf2, wfp2, a2, O, B, Hl, Wl, O, O, scale2, shift2, st, sq, ctypes.byref(nparts))
+            assert ok
+            _lib.call("unetca_se_fc", _ptr(sq), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(p), _ptr(z),
+                      _ptr(s), st)
+        else:
+            ok = _conv3x3_bnrelu(dt, a1, O, wf2, wfp2, a2, O, B, Hl, Wl, O, O, scale2, shift2, st)
+            assert ok
+            _lib.call("unetca_se_squeeze", dt, _ptr(a2), O, B, Hl * Wl, O, _ptr(one), _ptr(zero), _ptr(parts),
+                      ctypes.byref(nparts), st)
+            _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(one),
+                      _ptr(zero), None, _ptr(p), _ptr(z), _ptr(s), None, st)
+    else:
+        ok = _conv3x3_bnrelu(dt, a1, O, wf2, wfp2, a2, O, B, Hl, Wl, O, O, scale2, shift2, st)
+        assert ok
     if pooled is not None and (Hl % 2 or Wl % 2):
         _lib.call("unetca_se_scale_pool", dt, _ptr(a2), O, _ptr(out_view), out_view.stride(2), None, 0, None, B, Hl, Wl,
                   O, _ptr(one), _ptr(zero), _ptr(s), st)

@@ -342,6 +342,57 @@ def test_conv3x3_tcgen05(B, C, O, H, W):
     _conv_case(BF16, 0, B, C, O, H, W)
 
 
+@pytest.mark.parametrize("B,C,O,H,W,layout", [(3, 128, 128, 40, 72, 0), (2, 64, 256, 16, 48, 0), (5, 128, 128, 8, 8, 0),
+                                              (3, 64, 64, 40, 72, 1), (2, 64, 64, 128, 160, 1), (70, 64, 64, 16, 16, 1),
+                                              (1, 128, 64, 24, 40, 2)])
+def test_conv3x3_bnrelu_squeeze_epilogue(B, C, O, H, W, layout):
+    """Inference form of a block's convolution: eval-mode BatchNorm + ReLU in the epilogue (UCA:83-90 with running
+    statistics) and, for a block's second convolution, the SE squeeze (UCA:65) as per-image partial channel sums."""
+    dt = BF16
+    rs = np.random.RandomState(17)
+    call("unetca_set_conv_impl", 0)
+    x = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((O, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32))
+    scale = torch.from_numpy((0.5 + rs.rand(O)).astype(np.float32))
+    shift = torch.from_numpy((0.3 * rs.standard_normal(O)).astype(np.float32))
+    ref = F.relu(F.conv2d(rounded(x, dt), rounded(w, dt), None, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    xd, wdev = to_nhwc(x, dt), w.cuda()
+    wf = torch.empty(O, 9 * C, dtype=TDT[dt], device="cuda")
+    wdg = torch.empty(C, 9 * O, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_conv3x3_weight", dt, ptr(wdev), ptr(wf), 9 * C, ptr(wdg), O, C, stream())
+    wt = wf
+    if layout == 1:
+        wt = torch.empty(2 * O, 12 * C, dtype=TDT[dt], device="cuda")
+        call("unetca_pack_conv3x3_pair", dt, ptr(wf), 9 * C, ptr(wt), O, C, stream())
+    elif layout == 2:
+        wt = torch.empty(9 * C, 64, dtype=TDT[dt], device="cuda")
+        call("unetca_pack_conv3x3_kw", dt, ptr(wf), 9 * C, ptr(wt), C, stream())
+    y = torch.full((B, H, W, O), float("nan"), dtype=TDT[dt], device="cuda")
+    sq = None
+    if layout != 2:
+        sq = torch.zeros(B * unetca_b200._lib.load().unetca_num_sms() * O, device="cuda")
+    n = cint()
+    scale_d, shift_d = scale.cuda(), shift.cuda()
+    call("unetca_conv3x3_bnrelu_fwd", dt, ptr(xd), C, ptr(wt), layout, ptr(y), O, B, H, W, C, O, ptr(scale_d),
+         ptr(shift_d), ptr(sq), ctypes.byref(n), stream())
+    got = from_nhwc(y)
+    assert relerr(got, ref) < TOL[dt]
+    if sq is not None:
+        assert 0 < n.value <= unetca_b200._lib.load().unetca_num_sms()
+        sums = sq[: B * n.value * O].view(B, n.value, O).sum(1).cpu()
+        want = got.sum((2, 3))                                   # of the stored (bf16) activations
+        assert relerr(sums, want) < 1e-4
+        # ... and they feed unetca_se_fc unchanged: its pooled output is the per-image channel mean
+        Cr = O // 16
+        w1 = torch.from_numpy((rs.standard_normal((Cr, O)) / np.sqrt(O)).astype(np.float32)).cuda()
+        w2 = torch.from_numpy((rs.standard_normal((O, Cr)) / np.sqrt(Cr)).astype(np.float32)).cuda()
+        pl, z, sg = torch.empty(B, O, device="cuda"), torch.empty(B, Cr, device="cuda"), torch.empty(B, O, device="cuda")
+        call("unetca_se_fc", ptr(sq), n.value, B, O, Cr, H * W, ptr(w1), ptr(w2), ptr(pl), ptr(z), ptr(sg), stream())
+        mean = want / (H * W)
+        assert relerr(pl.cpu(), mean) < 1e-4
+        assert relerr(sg.cpu(), torch.sigmoid(F.relu(mean @ w1.cpu().t()) @ w2.cpu().t())) < 1e-4
+
+
 def _convT_case(dt, impl, B, Cin, Cout, h, w_, seed=5):
     rs = np.random.RandomState(seed)
     call("unetca_set_conv_impl", impl)

@@ -43,7 +43,11 @@ def main():
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--repeat", type=int, default=2, help="passes over this rank's tiles (the first is the warm-up)")
+    ap.add_argument("--no-squeeze-fuse", action="store_true", help="SE squeeze as a separate pass (A/B of the epilogue fusion)")
     a = ap.parse_args()
+    if a.no_squeeze_fuse:
+        from unetca_b200 import model as _m
+        _m.FUSE_SQUEEZE = False
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
