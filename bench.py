@@ -309,6 +309,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--torch-adam", action="store_true",
+                    help="step with torch.optim.Adam(fused=True) instead of unetca_b200.optim.Adam (A/B)")
     ap.add_argument("--graph", action="store_true",
                     help="replay the whole train step as one CUDA graph (unetca_b200.graph; single GPU; no per-kernel "
                          "accounting, so the roofline objects are omitted) — what matters at small batch / tile sizes")
@@ -330,6 +332,7 @@ def main():
     import torch.distributed as dist
     import unetca_b200
     from unetca_b200 import _lib, parallel
+    from unetca_b200 import optim as uoptim
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
@@ -349,7 +352,11 @@ def main():
     model.train()
     if world > 1:
         parallel.GradBuckets(model)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    if args.torch_adam:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+    else:
+        # this repo's multi-tensor Adam: same arithmetic, emits the packed conv filters for the next forward
+        opt = uoptim.Adam(model.parameters(), lr=1e-4, model=model)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x = torch.randn(B, 3, S, S, device=dev, generator=g)
     y = torch.randint(0, 2, (B, S, S), device=dev, generator=g)
@@ -370,7 +377,8 @@ def main():
         if world > 1:
             raise SystemExit("bench.py --graph: single GPU only")
         from unetca_b200 import graph as ugraph
-        opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
+        if args.torch_adam:
+            opt = torch.optim.Adam(model.parameters(), lr=1e-4, capturable=True)
         gstep = ugraph.GraphedTrainStep(model, opt, x, y, warmup=args.warmup)
         torch.cuda.synchronize()
         clocks = ClockSampler(local)

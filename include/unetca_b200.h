@@ -179,6 +179,18 @@ int unetca_simt_convT_dgrad(int dtype, const void* dout, int ldd, const void* w,
 int unetca_simt_convT_wgrad(int dtype, const void* x, int ldx, const void* dout, int ldd, float* ws, long ws_floats, int B, int h, int wd, int Cin, int Cout, void* stream);
 int unetca_wgrad_reduce(const float* ws, int nsplit, long split_stride, int mode, int D0, int D1, int ldn, float* dw, void* stream);
 
+/* ---- optimizer step: optim.Adam(model.parameters(), lr) UCA:466, optimizer.step() UCA:346 ----
+ * Multi-tensor Adam on the fp32 master weights (torch.optim.Adam arithmetic, no amsgrad / maximize).
+ * hyper: 8 floats on the device, zero-initialised by the caller; hyper[0] is the step count.  unetca_adam_tick
+ * advances it and derives the bias corrections on the device, so a captured train step replays correctly.
+ * unetca_adam_step: table = host array of ntensors rows {p, g, m, v, numel} (64-bit each; fp32 device pointers).
+ * unetca_adam_step_conv3x3: table = host array of nlayers rows {p, g, m, v, wf, wd, O, C}: (O,C,3,3) filters with O, C
+ * multiples of 32; the stepped weights are also emitted as the packed operand copies of unetca_pack_conv3x3_weight
+ * (wf [O][9*C] forward, wd [C][9*O] dgrad, storage type dtype; either may be 0).  Both return the launch count. */
+int unetca_adam_tick(float* hyper, double lr, double beta1, double beta2, double eps, double weight_decay, void* stream);
+int unetca_adam_step(const long long* table, int ntensors, const float* hyper, void* stream);
+int unetca_adam_step_conv3x3(int dtype, const long long* table, int nlayers, const float* hyper, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

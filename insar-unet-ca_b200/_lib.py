@@ -39,6 +39,8 @@ def parse_header(path: str = HEADER):
                     argtypes.append(ctypes.c_long)
                 elif a.startswith("float"):
                     argtypes.append(ctypes.c_float)
+                elif a.startswith("double"):
+                    argtypes.append(ctypes.c_double)
                 elif a.startswith("int"):
                     argtypes.append(ctypes.c_int)
                 else:

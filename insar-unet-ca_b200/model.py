@@ -138,6 +138,37 @@ class _Engine:
             self._packed[key] = ent
         return ent[1]
 
+    def _derive(self, w, dt, tdt, first, wf, wd, ldk, wfp=None, wdp=None):
+        """The layouts derived from the base packed filters wf / wd (allocated on first use, then rewritten in place):
+        narrow outputs (a multiple of 64 but not of 128 channels) run through the row-pair layout of the tcgen05 path,
+        which wants the filter re-expressed over 4x3 virtual taps."""
+        O, C = w.shape[0], w.shape[1]
+        st = _stream()
+        if dt == _lib.BF16 and first and C <= 5:
+            # first conv: pixel-pair layout (unetca_im2col_pairs), filter over the 4x3 patch a row pair shares
+            if wfp is None:
+                wfp = torch.empty(2 * O, 64, dtype=tdt, device=w.device)              # (a plain tensor: first conv only)
+            _lib.call("unetca_pack_first_pairs", dt, _ptr(w), _ptr(wfp), O, C, st)
+        if dt == _lib.BF16 and not first:
+            # 64 output channels: the row-pair layout ("pair"), except from 128 input channels where the kw-stacked
+            # layout ("kw", filter resident in shared memory) wins: its epilogue reads three accumulator columns per
+            # output from TMEM (64 B/cycle/SM) and only hides behind a mainloop of >= 2 channel chunks
+            if O % 128:
+                if O == 64 and C == 128:
+                    wfp = wfp or ("kw", torch.empty(9 * C, 64, dtype=tdt, device=w.device))
+                    _lib.call("unetca_pack_conv3x3_kw", dt, _ptr(wf), ldk, _ptr(wfp[1]), C, st)
+                else:
+                    wfp = wfp or ("pair", torch.empty(2 * O, 12 * C, dtype=tdt, device=w.device))
+                    _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wf), ldk, _ptr(wfp[1]), O, C, st)
+            if C % 128:
+                if C == 64 and O == 128:
+                    wdp = wdp or ("kw", torch.empty(9 * O, 64, dtype=tdt, device=w.device))
+                    _lib.call("unetca_pack_conv3x3_kw", dt, _ptr(wd), 9 * O, _ptr(wdp[1]), O, st)
+                else:
+                    wdp = wdp or ("pair", torch.empty(2 * C, 12 * O, dtype=tdt, device=w.device))
+                    _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wd), 9 * O, _ptr(wdp[1]), C, O, st)
+        return wfp, wdp
+
     def conv_w(self, conv: nn.Conv2d, dt, tdt, first):
         w = conv.weight
         O, C = w.shape[0], w.shape[1]
@@ -147,33 +178,19 @@ class _Engine:
             wf = torch.empty(O, ldk, dtype=tdt, device=w.device)
             wd = None if first else torch.empty(C, 9 * O, dtype=tdt, device=w.device)
             _lib.call("unetca_pack_conv3x3_weight", dt, _ptr(w), _ptr(wf), ldk, _ptr(wd), O, C, _stream())
-            # narrow outputs (a multiple of 64 but not of 128 channels) run through the row-pair layout of the
-            # tcgen05 path, which wants the filter re-expressed over 4x3 virtual taps
-            wfp = wdp = None
-            if dt == _lib.BF16 and first and C <= 5:
-                # first conv: pixel-pair layout (unetca_im2col_pairs), filter over the 4x3 patch a row pair shares
-                wfp = torch.empty(2 * O, 64, dtype=tdt, device=w.device)              # (a plain tensor: first conv only)
-                _lib.call("unetca_pack_first_pairs", dt, _ptr(w), _ptr(wfp), O, C, _stream())
-            if dt == _lib.BF16 and not first:
-                # 64 output channels: the row-pair layout ("pair"), except from 128 input channels where the kw-stacked
-                # layout ("kw", filter resident in shared memory) wins: its epilogue reads three accumulator columns per
-                # output from TMEM (64 B/cycle/SM) and only hides behind a mainloop of >= 2 channel chunks
-                if O % 128:
-                    if O == 64 and C == 128:
-                        wfp = ("kw", torch.empty(9 * C, 64, dtype=tdt, device=w.device))
-                        _lib.call("unetca_pack_conv3x3_kw", dt, _ptr(wf), ldk, _ptr(wfp[1]), C, _stream())
-                    else:
-                        wfp = ("pair", torch.empty(2 * O, 12 * C, dtype=tdt, device=w.device))
-                        _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wf), ldk, _ptr(wfp[1]), O, C, _stream())
-                if C % 128:
-                    if C == 64 and O == 128:
-                        wdp = ("kw", torch.empty(9 * O, 64, dtype=tdt, device=w.device))
-                        _lib.call("unetca_pack_conv3x3_kw", dt, _ptr(wd), 9 * O, _ptr(wdp[1]), O, _stream())
-                    else:
-                        wdp = ("pair", torch.empty(2 * C, 12 * O, dtype=tdt, device=w.device))
-                        _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wd), 9 * O, _ptr(wdp[1]), C, O, _stream())
+            wfp, wdp = self._derive(w, dt, tdt, first, wf, wd, ldk)
             return wf, wd, ldk, wfp, wdp
         return self._cached(("c", id(conv)), w, tdt, build)
+
+    def conv_w_adopt(self, conv: nn.Conv2d, dt, tdt):
+        """For an optimizer that has just written the stepped weights into this layer's base packed filters
+        (optim.Adam -> unetca_adam_step_conv3x3): refresh the derived layouts in place and mark the entry as the one the
+        next forward (which bumps `epoch`) will accept, so that forward repacks nothing."""
+        w = conv.weight
+        key = ("c", id(conv))
+        _, (wf, wd, ldk, wfp, wdp) = self._packed[key]
+        wfp, wdp = self._derive(w, dt, tdt, False, wf, wd, ldk, wfp, wdp)
+        self._packed[key] = ((w._version, w.data_ptr(), tdt, self.epoch + 1), (wf, wd, ldk, wfp, wdp))
 
     def convT_w(self, up: nn.ConvTranspose2d, dt, tdt):
         w = up.weight

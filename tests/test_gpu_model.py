@@ -157,7 +157,7 @@ def test_configs0_bf16(golden_dir):
     assert np.all(rel < tol), (np.array(names)[big][worst], rel[worst])
 
 
-@pytest.mark.parametrize("prec,fused", [("fp32", False), ("bf16", False), ("bf16", True)])
+@pytest.mark.parametrize("prec,fused", [("fp32", False), ("bf16", False), ("bf16", True), ("bf16", "own"), ("fp32", "own")])
 def test_adam_trajectory_100_steps(prec, fused):
     """100 Adam(lr=1e-4) steps on the same seeded batches: loss and global grad norm within 1e-2 rel of the oracle
     at every step (UCA:342-346, 466)."""
@@ -165,7 +165,12 @@ def test_adam_trajectory_100_steps(prec, fused):
     sd = port.make_state_dict(seed=7)
     m = _model(sd, prec)
     # fused=True updates the parameters without bumping Tensor._version: the packed operand copies must still follow
-    opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=fused)
+    if fused == "own":
+        # the multi-tensor Adam of this repo, which writes the packed filters itself (the forward repacks nothing)
+        from unetca_b200 import optim as uoptim
+        opt = uoptim.Adam(m.parameters(), lr=1e-4, model=m)
+    else:
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=fused)
     # oracle: the torch port driven by the same optimizer on CPU
     p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
          for k, v in sd.items()}
@@ -289,8 +294,10 @@ def test_odd_sizes_take_every_fallback(prec, ltol, gtol):
         assert torch.equal(torch.max(m.last_logits, 1)[1].cpu(), torch.max(ref_logits, 1)[1])
 
 
-def test_graphed_train_step_is_bit_identical_to_eager():
-    """The whole train step captured as one CUDA graph replays to exactly the eager step's losses and parameters."""
+@pytest.mark.parametrize("own", [False, True])
+def test_graphed_train_step_is_bit_identical_to_eager(own):
+    """The whole train step captured as one CUDA graph replays to exactly the eager step's losses and parameters
+    (own: with this repo's Adam, whose step count lives on the device and which writes the packed filters)."""
     import unetca_b200
     from unetca_b200 import graph
     sd = port.make_state_dict(seed=31, in_channels=1)
@@ -300,7 +307,11 @@ def test_graphed_train_step_is_bit_identical_to_eager():
         m = unetca_b200.UNet(1, 2, use_se=True).cuda().set_precision("bf16")
         m.load_state_dict(sd)
         m.train()
-        opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
+        if own:
+            from unetca_b200 import optim as uoptim
+            opt = uoptim.Adam(m.parameters(), lr=1e-4, model=m)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=1e-4, capturable=True)
         losses = []
         if graphed:
             # capture on the first batch: construction runs 3 warm-up steps + the capture on it, then replay per batch

@@ -645,3 +645,81 @@ def test_encoder_backward_with_on_the_fly_unpool(dt):
     call("unetca_bn_bwd_apply_pool", dt, ptr(sg), 2 * C, ptr(dpl), C, ptr(pos), ptr(y), C, ptr(dyb), C, B, H, W, C, ptr(sc),
          ptr(sh), ptr(mean), ptr(invstd), ptr(s), ptr(dp), ptr(coef), stream())
     assert relerr(dyb.float(), dya.float()) < (1e-5 if dt == F32 else 1.5e-2)
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_adam_multi_tensor_matches_torch(wd):
+    """optimizer.step() (UCA:346) with optim.Adam (UCA:466): 6 steps on tensors of awkward sizes against torch.optim.Adam
+    on the CPU; fp32 both sides, differences are rounding only (fused multiply-adds): 2e-6 of the largest value."""
+    from unetca_b200 import optim as uoptim
+    rs = np.random.RandomState(3)
+    shapes = [(1,), (7,), (64,), (2, 64, 1, 1), (4096,), (4097,), (3, 4096), (64, 3, 3, 3), (33, 5, 7), (100000,)] + [(64,)] * 70
+    ref = [torch.nn.Parameter(torch.from_numpy(rs.standard_normal(sh).astype(np.float32))) for sh in shapes]
+    own = [torch.nn.Parameter(r.detach().clone().cuda()) for r in ref]
+    ropt = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    opt = uoptim.Adam(own, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    for step in range(6):
+        for r, o in zip(ref, own):
+            g = torch.from_numpy(rs.standard_normal(tuple(r.shape)).astype(np.float32)) * (10.0 ** (step - 3))
+            r.grad = g
+            o.grad = g.cuda() if not (step == 2 and r.numel() == 7) else None      # one skipped tensor in one step
+            if o.grad is None:
+                r.grad = None
+        ropt.step()
+        opt.step()
+    for r, o in zip(ref, own):
+        if r.numel() == 7:
+            continue          # skipped once: torch keeps a per-tensor step count, this optimizer one per group (documented)
+        assert relerr(o.detach().cpu(), r.detach()) < 2e-6
+        assert relerr(opt.state[o]["exp_avg"].cpu(), ropt.state[r]["exp_avg"]) < 2e-6
+        assert relerr(opt.state[o]["exp_avg_sq"].cpu(), ropt.state[r]["exp_avg_sq"]) < 2e-6
+    # state_dict round trip into torch.optim.Adam and back
+    sd = opt.state_dict()
+    assert float(sd["state"][0]["step"]) == 6.0
+    topt = torch.optim.Adam([torch.nn.Parameter(o.detach().clone()) for o in own], lr=1e-2, betas=(0.9, 0.99), weight_decay=wd)
+    import copy
+    topt.load_state_dict(copy.deepcopy(sd))          # (torch's load_state_dict aliases same-device state tensors)
+    opt2 = uoptim.Adam([torch.nn.Parameter(o.detach().clone()) for o in own], lr=1e-2, betas=(0.9, 0.99), weight_decay=wd)
+    opt2.load_state_dict(topt.state_dict())
+    for a, b, c in zip(own, topt.param_groups[0]["params"], opt2.param_groups[0]["params"]):
+        if a.numel() == 7:
+            continue
+        g = torch.ones_like(a)
+        a.grad, b.grad, c.grad = g, g.clone(), g.clone()
+    opt.step(); topt.step(); opt2.step()
+    for a, b, c in zip(own, topt.param_groups[0]["params"], opt2.param_groups[0]["params"]):
+        if a.numel() == 7:
+            continue
+        assert torch.equal(a, c)
+        assert relerr(a, b) < 2e-6
+    with pytest.raises(RuntimeError):
+        cpu_p = torch.nn.Parameter(torch.zeros(4)); cpu_p.grad = torch.ones(4)
+        uoptim.Adam([cpu_p]).step()
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("O,C", [(64, 96), (128, 64), (32, 32)])
+def test_adam_conv3x3_emits_packed_filters(dt, O, C):
+    """The conv-filter Adam kernel: same step as the multi-tensor kernel, and the packed operand copies it writes are
+    bit-identical to unetca_pack_conv3x3_weight of the stepped weights."""
+    rs = np.random.RandomState(5)
+    mk = lambda sc=1.0: torch.from_numpy((sc * rs.standard_normal((O, C, 3, 3))).astype(np.float32)).cuda()
+    p, g, m, v = mk(), mk(0.1), mk(0.05), mk(0.02).abs()
+    p2, m2, v2 = p.clone(), m.clone(), v.clone()
+    hyper = torch.zeros(8, device="cuda")
+    hyper[0] = 4
+    call("unetca_adam_tick", ptr(hyper), 1e-3, 0.9, 0.999, 1e-8, 0.0, stream())
+    assert hyper[0].item() == 5.0
+    assert abs(hyper[1].item() - 1e-3 / (1 - 0.9 ** 5)) < 1e-9 and abs(hyper[2].item() - (1 - 0.999 ** 5) ** 0.5) < 1e-8
+    wf = torch.full((O, 9 * C), float("nan"), dtype=TDT[dt], device="cuda")
+    wd = torch.full((C, 9 * O), float("nan"), dtype=TDT[dt], device="cuda")
+    tab = np.asarray([(ptr(p), ptr(g), ptr(m), ptr(v), ptr(wf), ptr(wd), O, C)], dtype=np.int64)
+    assert call("unetca_adam_step_conv3x3", dt, tab.ctypes.data_as(ctypes.c_void_p), 1, ptr(hyper), stream()) == 1
+    tab2 = np.asarray([(ptr(p2), ptr(g), ptr(m2), ptr(v2), p2.numel())], dtype=np.int64)
+    assert call("unetca_adam_step", tab2.ctypes.data_as(ctypes.c_void_p), 1, ptr(hyper), stream()) == 1
+    assert torch.equal(p, p2) and torch.equal(m, m2) and torch.equal(v, v2)
+    wf_ref = torch.empty_like(wf)
+    wd_ref = torch.empty_like(wd)
+    call("unetca_pack_conv3x3_weight", dt, ptr(p), ptr(wf_ref), 9 * C, ptr(wd_ref), O, C, stream())
+    assert torch.equal(wf.view(torch.int16 if dt == BF16 else torch.int32), wf_ref.view(torch.int16 if dt == BF16 else torch.int32))
+    assert torch.equal(wd.view(torch.int16 if dt == BF16 else torch.int32), wd_ref.view(torch.int16 if dt == BF16 else torch.int32))
