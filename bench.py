@@ -346,6 +346,8 @@ def main():
 
     if os.environ.get("UNETCA_BLOCK_N"):                 # tuning knob: force the tcgen05 tile width where it divides N
         _lib.load().unetca_tc_force_block_n(int(os.environ["UNETCA_BLOCK_N"]))
+    if os.environ.get("UNETCA_EW_STREAM"):               # tuning knob: 0 = register kernels for the BN-backward / squeeze passes
+        _lib.load().unetca_set_tuning(3, int(os.environ["UNETCA_EW_STREAM"]))
     B, S = args.batch, args.size
     torch.manual_seed(0)
     model = unetca_b200.UNet(3, 2, use_se=True).to(dev).set_precision(args.precision)

@@ -42,6 +42,7 @@ int unetca_get_conv_impl(void);
 void unetca_tc_force_block_n(int n);
 void unetca_tc_force_wgrad_narrow(int on);
 void unetca_tc_force_no_halo(int on);
+void unetca_tc_set_convT_wide(int on);
 void unetca_tc_force_no_pixn(int on);
 void unetca_tc_set_pixn_cluster(int n);
 void unetca_tc_force_no_kw(int on);

@@ -38,7 +38,7 @@ struct alignas(64) TcParams {
     // forward-like
     int ntaps, cchunks;
     signed char dh[12], dw[12], amap[12];
-    int n_blocks_per_outmap;
+    int out_chunks_per_map;      // 64-channel chunks per output map (ConvTranspose: one map per (d,e) sub-pixel)
     const float* bias;
     int bias_mod;
     float* stat_parts;
@@ -75,7 +75,7 @@ template <int BLOCK_N, bool WGRAD> struct TcCfg {
 // ---------------------------------------------------------------------------------------------------------
 template <int BLOCK_N>
 __device__ __forceinline__ void fwd_epilogue_tile(uint32_t t_addr, uint8_t* out_stage, float* sm_bias, float* sm_wpart,
-                                                  float* sm_stats, const CUtensorMap* mapOut, int c0, int w0, int h0, int b,
+                                                  float* sm_stats, const CUtensorMap* mapOut, int chunks_per_map, int w0, int h0, int b,
                                                   int nb, bool valid, const float* bias, int bias_mod, bool do_stats, int N,
                                                   uint64_t* tempty, int r, int lane, int ep_tid) {
     // the staging buffer must have been drained by the previous tile's TMA store
@@ -115,8 +115,10 @@ __device__ __forceinline__ void fwd_epilogue_tile(uint32_t t_addr, uint8_t* out_
     named_bar_sync(1, 128);
     if (ep_tid == 0) {
 #pragma unroll 1
-        for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_store_4d(mapOut, out_stage + j * kBoxBytesFwd, c0 + j * 64, w0, h0, b);
+        for (int j = 0; j < BLOCK_N / 64; ++j) {
+            const int q = nb * (BLOCK_N / 64) + j;          // global 64-channel chunk -> (output map, channel offset)
+            tma_store_4d(mapOut + q / chunks_per_map, out_stage + j * kBoxBytesFwd, (q % chunks_per_map) * 64, w0, h0, b);
+        }
         tma_store_commit();
     }
     if (do_stats) {
@@ -327,8 +329,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
                 const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
                 const int w0 = tw * p.TW, h0 = th * p.TH;
                 const bool valid = (h0 + r / p.TW) < p.H && (w0 + r % p.TW) < p.W;
-                fwd_epilogue_tile<BLOCK_N>(t_addr, out_stage, sm_bias, sm_wpart, sm_stats, &p.mapOut[nb / p.n_blocks_per_outmap],
-                                           (nb % p.n_blocks_per_outmap) * BLOCK_N, w0, h0, b, nb, valid, p.bias, p.bias_mod,
+                fwd_epilogue_tile<BLOCK_N>(t_addr, out_stage, sm_bias, sm_wpart, sm_stats, p.mapOut,
+                                           p.out_chunks_per_map, w0, h0, b, nb, valid, p.bias, p.bias_mod,
                                            p.stat_parts != nullptr, p.N, &tempty_bar[as], r, lane, ep_tid);
             } else {
                 const int z = (int)(t / mn_items);
@@ -1782,6 +1784,7 @@ static int pick_block_n(int N) {
 }
 
 static int g_no_halo = 0;
+static int g_convT_wide = 1;       // ConvTranspose forward / wgrad: N blocks of 256 across the four sub-pixel maps
 
 // make_map variant without swizzle (linear [pixel][64 ch] staging tiles of the pixels-on-N epilogue)
 static int make_map_linear(CUtensorMap* m, const void* base, long C, long W, long H, long B, long sw, long sh, long sb,
@@ -1995,6 +1998,7 @@ extern "C" {
 void unetca_tc_force_block_n(int n) { g_force_block_n = n; }
 void unetca_tc_force_wgrad_narrow(int on) { g_wgrad_narrow = on; }
 void unetca_tc_force_no_halo(int on) { g_no_halo = on; }
+void unetca_tc_set_convT_wide(int on) { g_convT_wide = on; }
 void unetca_tc_force_no_pixn(int on) { g_no_pixn = on; }
 void unetca_tc_set_pixn_cluster(int n) { g_pixn_cluster = n == 1 ? 1 : 2; }
 
@@ -2086,7 +2090,7 @@ int unetca_tc_conv3x3_fwd(const void* x, int ldx, const void* w, int ldk, void* 
     p.num_n_blocks = O / BN;
     p.ntaps = 9; p.cchunks = C / 64;
     set_taps3x3(p);
-    p.n_blocks_per_outmap = p.num_n_blocks;
+    p.out_chunks_per_map = O / 64;
     p.stat_parts = stat_parts; p.N = O;
     return launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_conv3x3_fwd");
 }
@@ -2109,7 +2113,7 @@ int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out
     p.num_m_blocks = p.tilesW;
     p.num_n_blocks = N / BN;
     p.ntaps = 1; p.cchunks = K / 64;
-    p.n_blocks_per_outmap = p.num_n_blocks;
+    p.out_chunks_per_map = N / 64;
     p.stat_parts = stat_parts; p.N = N;
     return launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_gemm_nt");
 }
@@ -2124,7 +2128,9 @@ int unetca_tc_convT_fwd(const void* x, int ldx, const void* w, const float* bias
     pick_tile(h, wd, 128, &TW, &TH);
     int rc;
     if ((rc = make_map(&p.mapA[0], x, Cin, wd, h, B, ldx, (long)wd * ldx, (long)h * wd * ldx, TW, TH)) < 0) return rc;
-    const int BN = pick_block_n(Cout);
+    // one N block may span several (d,e) sub-pixel maps: 4*Cout is always a multiple of 256, the width at which an
+    // SS-mode MMA reaches full rate, and the activation tile is then read once instead of once per sub-pixel
+    const int BN = g_convT_wide ? pick_block_n(4 * Cout) : pick_block_n(Cout);
     if ((rc = make_map(&p.mapB[0], w, Cin, 4L * Cout, 1, 1, Cin, 4L * Cout * Cin, 4L * Cout * Cin, BN, 1)) < 0) return rc;
     for (int de = 0; de < 4; ++de) {
         const bf16* base = (const bf16*)out + ((long)(de >> 1) * 2 * wd + (de & 1)) * ldo;
@@ -2135,7 +2141,7 @@ int unetca_tc_convT_fwd(const void* x, int ldx, const void* w, const float* bias
     p.num_m_blocks = p.tilesW * p.tilesH * B;
     p.num_n_blocks = 4 * Cout / BN;
     p.ntaps = 1; p.cchunks = Cin / 64;
-    p.n_blocks_per_outmap = Cout / BN;
+    p.out_chunks_per_map = Cout / 64;
     p.bias = bias; p.bias_mod = Cout;
     p.N = 4 * Cout;
     int r2 = launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_convT_fwd");
@@ -2164,7 +2170,7 @@ int unetca_tc_convT_dgrad(const void* dout, int ldd, const void* wdg, void* dx, 
     p.num_m_blocks = p.tilesW * p.tilesH * B;
     p.num_n_blocks = Cin / BN;
     p.ntaps = 4; p.cchunks = Cout / 64;
-    p.n_blocks_per_outmap = p.num_n_blocks;
+    p.out_chunks_per_map = Cin / 64;
     p.N = Cin;
     int r2 = launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_convT_dgrad");
     return r2 < 0 ? r2 : 0;
@@ -2331,7 +2337,7 @@ int unetca_tc_convT_wgrad(const void* x, int ldx, const void* dout, int ldd, flo
         const bf16* base = (const bf16*)dout + ((long)(de >> 1) * 2 * wd + (de & 1)) * ldd;
         if ((rc = make_map(&p.mapB[de], base, Cout, wd, h, B, 2L * ldd, 4L * wd * ldd, 4L * h * wd * ldd, TW, TH)) < 0) return rc;
     }
-    const int BN = pick_block_n(Cout);
+    const int BN = g_convT_wide ? pick_block_n(4 * Cout) : pick_block_n(Cout);     // N blocks may span the (d,e) maps
     p.tilesW = ceil_div(wd, TW); p.tilesH = ceil_div(h, TH); p.nimg = B;
     p.TW = TW; p.TH = TH; p.H = h; p.W = wd;
     p.a_chunks = Cin / 64; p.a_cchunks = Cin / 64; p.b_chunks_per_map = Cout / 64;

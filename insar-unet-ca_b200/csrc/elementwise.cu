@@ -13,6 +13,7 @@
 // whole 128-byte pixel rows (fully coalesced).  Reductions are two-stage and deterministic: per-block
 // partials in a caller-provided fp32 scratch, then a tiny finalize kernel that sums them in double.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <math.h>
 
 namespace unetca {
@@ -23,6 +24,7 @@ constexpr int kMaxParts = 1184;  // 148 SMs x 8
 // tuning knobs (unetca_set_tuning): pixels per thread-row of an elementwise block; waves of a per-image reduction grid
 // (0 = legacy sizing by kMaxParts)
 static int g_ew_px = 16;
+static int g_apply_stream = 8;      // > 0: BN-backward / squeeze passes as shared-memory streams; bn_bwd_apply: this many 8 KB tiles per block
 static int g_red_waves = 1;
 static int g_pool_quads = 4;      // 2x2 quads per thread-row of a se_scale_pool block
 
@@ -626,6 +628,205 @@ __global__ void __launch_bounds__(kThreads, APPLY ? 3 : 4) bn_bwd_kernel(const T
     }
     if (!APPLY)
         block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The APPLY pass as a shared-memory stream (dense bf16 tensors, C/8 a power of two <= 256): one elected thread moves
+// 8 KB tiles of Y and dO with cp.async.bulk into a ring of stages, all threads transform a tile in place in shared
+// memory, and the result leaves by a bulk store.  The register-based kernel above keeps only 2-4 16-byte loads per
+// thread in flight (48 per-channel constants crowd the register file at 3 blocks/SM): ~25-50 KB per SM, at the edge of
+// what HBM latency x bandwidth needs (~35 KB).  Here (kStStages - 1) x 16 KB per block are in flight whatever the
+// register budget.  Same arithmetic in the same order: bit-identical results.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kStTile = 8192;        // bytes per operand per stage
+constexpr int kStStages = 4;
+constexpr int kStSmemBytes = kStStages * 2 * kStTile;
+
+__device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_store_1d(void* dst, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+
+template <bool SE>
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_apply_stream_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y,
+                                                                          bf16* __restrict__ dy, int C, long pix_per_img, long chunk,
+                                                                          float inv_hw, const float* __restrict__ scale,
+                                                                          const float* __restrict__ shift,
+                                                                          const float* __restrict__ mean,
+                                                                          const float* __restrict__ invstd,
+                                                                          const float* __restrict__ s, const float* __restrict__ dp,
+                                                                          const float* __restrict__ coef) {
+    extern __shared__ __align__(128) uint8_t st_smem[];        // [stage][y tile | dO tile]
+    __shared__ __align__(8) uint64_t full_bar[kStStages];
+    constexpr int VEC = 8;
+    const int vpr = C / VEC;
+    const int cv = threadIdx.x & (vpr - 1);
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    const long off0 = ((long)blockIdx.y * pix_per_img + p0) * C * 2;        // byte offset of this block's range
+    const long nbytes = (p1 - p0) * C * 2;
+    const int ntiles = (int)((nbytes + kStTile - 1) / kStTile);
+    const uint8_t* yb = reinterpret_cast<const uint8_t*>(y) + off0;
+    const uint8_t* db = reinterpret_cast<const uint8_t*>(dout) + off0;
+    uint8_t* ob = reinterpret_cast<uint8_t*>(dy) + off0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int stg = t % kStStages;
+        const long o = (long)t * kStTile;
+        const uint32_t bytes = (uint32_t)(nbytes - o < kStTile ? nbytes - o : kStTile);
+        mbar_expect_tx(&full_bar[stg], 2 * bytes);
+        bulk_load_1d(st_smem + stg * 2 * kStTile, yb + o, bytes, &full_bar[stg]);
+        bulk_load_1d(st_smem + stg * 2 * kStTile + kStTile, db + o, bytes, &full_bar[stg]);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < kStStages - 1 && t < ntiles; ++t) issue(t);
+    float a[VEC], b[VEC], m0[VEC], m1[VEC], k2[VEC], k0[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = cv * VEC + i;
+        a[i] = scale[c]; b[i] = shift[c];
+        float sv = 1.f, dpv = 0.f;
+        if (SE) { sv = s[(long)blockIdx.y * C + c]; dpv = dp[(long)blockIdx.y * C + c] * inv_hw; }
+        const float g = coef[c], c1 = coef[C + c], c2 = coef[2 * C + c];
+        k2[i] = g * c2 * invstd[c];
+        k0[i] = mean[c] * k2[i] - g * c1;
+        m0[i] = g * sv; m1[i] = g * dpv;
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        const int stg = t % kStStages;
+        const long o = (long)t * kStTile;
+        const int bytes = (int)(nbytes - o < kStTile ? nbytes - o : kStTile);
+        mbar_wait(&full_bar[stg], (uint32_t)((t / kStStages) & 1));
+        bf16* ys = reinterpret_cast<bf16*>(st_smem + stg * 2 * kStTile);
+        bf16* ds = reinterpret_cast<bf16*>(st_smem + stg * 2 * kStTile + kStTile);
+        for (int i = threadIdx.x; i < bytes / 16; i += kThreads) {
+            float v[VEC], d[VEC];
+            load_vec(ys + i * VEC, v);
+            load_vec(ds + i * VEC, d);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const float da = SE ? fmaf(d[j], m0[j], m1[j]) : d[j] * m0[j];
+                const float dz = fmaf(a[j], v[j], b[j]) > 0.f ? da : 0.f;
+                d[j] = fmaf(-v[j], k2[j], dz) + k0[j];
+            }
+            store_vec(ds + i * VEC, d);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store_1d(ob + o, ds, (uint32_t)bytes);
+            tma_store_commit();
+            // the stage tile t-1 lived in is free once its store has read it: refill it with tile t-1+kStStages
+            if (t >= 1) {
+                tma_store_wait_read1();
+                if (t - 1 + kStStages < ntiles) issue(t - 1 + kStStages);
+            } else if (kStStages - 1 < ntiles) {
+                issue(kStStages - 1);          // the one stage the prologue left empty
+            }
+        }
+    }
+    if (threadIdx.x == 0) tma_store_wait_all();
+}
+
+// The read-only reduction passes as the same shared-memory stream (no store: a stage is refilled as soon as every
+// thread has consumed it, so all kRdStages tiles are in flight).
+//   MODE 0: (sum m*dO, sum m*dO*(y-mean)) from dO and Y — bn_bwd_reduce without SE in front, and se_bn_bwd_reduce
+//   MODE 1: (sum m, sum m*y) from Y alone — se_squeeze                                  m = (a*y+b > 0)
+// parts: [(b*gridDim.x + blk)][2][C], as the register kernels write them.
+constexpr int kRdSmemBytes = 3 * 2 * kStTile;          // 3 stages of 2 x 8 KB (two operands) or 1 x 16 KB (one)
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads, 3) reduce_stream_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ y,
+                                                                    int C, long pix_per_img, long chunk,
+                                                                    const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift,
+                                                                    const float* __restrict__ mean, float* __restrict__ parts) {
+    constexpr int VEC = 8;
+    constexpr int NOP = MODE == 0 ? 2 : 1;
+    constexpr int TILE = NOP == 1 ? 2 * kStTile : kStTile;      // one operand: twice the tile, same bytes per stage
+    constexpr int kRdStages = kRdSmemBytes / (NOP * TILE);
+    extern __shared__ __align__(128) uint8_t st_smem[];        // [stage][y tile | dO tile]
+    __shared__ __align__(8) uint64_t full_bar[kRdStages];
+    const int vpr = C / VEC;
+    const int cv = threadIdx.x & (vpr - 1);
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    const long off0 = ((long)blockIdx.y * pix_per_img + p0) * C * 2;
+    const long nbytes = p1 > p0 ? (p1 - p0) * C * 2 : 0;
+    const int ntiles = (int)((nbytes + TILE - 1) / TILE);
+    const uint8_t* yb = reinterpret_cast<const uint8_t*>(y) + off0;
+    const uint8_t* db = MODE == 0 ? reinterpret_cast<const uint8_t*>(dout) + off0 : nullptr;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kRdStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int stg = t % kRdStages;
+        const long o = (long)t * TILE;
+        const uint32_t bytes = (uint32_t)(nbytes - o < TILE ? nbytes - o : TILE);
+        mbar_expect_tx(&full_bar[stg], NOP * bytes);
+        bulk_load_1d(st_smem + stg * NOP * TILE, yb + o, bytes, &full_bar[stg]);
+        if (MODE == 0) bulk_load_1d(st_smem + stg * NOP * TILE + TILE, db + o, bytes, &full_bar[stg]);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < kRdStages && t < ntiles; ++t) issue(t);
+    float a[VEC], b[VEC], mu[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        a[i] = scale[cv * VEC + i]; b[i] = shift[cv * VEC + i];
+        mu[i] = MODE == 0 ? mean[cv * VEC + i] : 0.f;
+    }
+    float acc[2][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+        const int stg = t % kRdStages;
+        const long o = (long)t * TILE;
+        const int bytes = (int)(nbytes - o < TILE ? nbytes - o : TILE);
+        mbar_wait(&full_bar[stg], (uint32_t)((t / kRdStages) & 1));
+        const bf16* ys = reinterpret_cast<const bf16*>(st_smem + stg * NOP * TILE);
+        const bf16* ds = reinterpret_cast<const bf16*>(st_smem + stg * NOP * TILE + TILE);
+        for (int i = threadIdx.x; i < bytes / 16; i += kThreads) {
+            float v[VEC], d[VEC];
+            load_vec(ys + i * VEC, v);
+            if (MODE == 0) load_vec(ds + i * VEC, d);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) {
+                const bool m = fmaf(a[j], v[j], b[j]) > 0.f;
+                if (MODE == 0) {
+                    const float dm = m ? d[j] : 0.f;
+                    acc[0][j] += dm;
+                    acc[1][j] = fmaf(dm, v[j] - mu[j], acc[1][j]);
+                } else if (m) {
+                    acc[0][j] += 1.f; acc[1][j] += v[j];
+                }
+            }
+        }
+        __syncthreads();                                   // every thread is done with this stage
+        if (threadIdx.x == 0 && t + kRdStages < ntiles) issue(t + kRdStages);
+    }
+    block_reduce_rows<2, VEC>(acc, C, vpr, kThreads / vpr, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+template <typename K> static int resident_blocks_smem(K kernel, int smem) {
+    int v = 0;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kernel, kThreads, smem) != cudaSuccess || v < 1) return 0;
+    return v * num_sms();
+}
+// dense bf16 tensors whose channel-vector count is a power of two dividing the block: the shapes the streams take
+template <typename T> static inline bool stream_ok(int C, int ld0, int ld1) {
+    const int vpr8 = C / 8;
+    return g_apply_stream > 0 && sizeof(T) == 2 && ld0 == C && ld1 == C && C % 8 == 0 && vpr8 >= 1 && vpr8 <= kThreads &&
+           (vpr8 & (vpr8 - 1)) == 0;
 }
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ parts, int nparts, int C, double count,
@@ -1659,6 +1860,17 @@ int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img
                       const float* shift, float* parts, int* nparts, void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldy);
+        if (stream_ok<T>(C, ldy, ldy)) {
+            static int sslots = 0;
+            if (!sslots) sslots = resident_blocks_smem(reduce_stream_kernel<1>, kRdSmemBytes);
+            if (sslots > 0) {
+                const long chunk = img_red_chunk<T>(C, pix_per_img, B, sslots);
+                dim3 grid(ceil_div(pix_per_img, chunk), B);
+                reduce_stream_kernel<1><<<grid, kThreads, kRdSmemBytes, (cudaStream_t)stream>>>(nullptr, (const bf16*)y, C, pix_per_img, chunk, scale, shift, nullptr, parts);
+                *nparts = grid.x;
+                return check_launch("se_squeeze (stream)");
+            }
+        }
         static int slots = 0;
         if (!slots) slots = resident_blocks(se_squeeze_kernel<T>);
         const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
@@ -1818,6 +2030,17 @@ int unetca_se_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y,
                             void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
+        if (stream_ok<T>(C, ldd, ldy)) {
+            static int sslots = 0;
+            if (!sslots) sslots = resident_blocks_smem(reduce_stream_kernel<0>, kRdSmemBytes);
+            if (sslots > 0) {
+                const long chunk = img_red_chunk<T>(C, pix_per_img, B, sslots);
+                dim3 grid(ceil_div(pix_per_img, chunk), B);
+                reduce_stream_kernel<0><<<grid, kThreads, kRdSmemBytes, (cudaStream_t)stream>>>((const bf16*)dout, (const bf16*)y, C, pix_per_img, chunk, scale, shift, mean, parts);
+                *nparts = grid.x;
+                return check_launch("se_bn_bwd_reduce (stream)");
+            }
+        }
         static int slots = 0;
         if (!slots) slots = resident_blocks(se_bn_bwd_reduce_kernel<T>);
         const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
@@ -1849,11 +2072,13 @@ int unetca_bn_bwd_finalize_se(const float* sums, int B, int C, long count, long 
     return check_launch("bn_bwd_finalize_se");
 }
 
-// tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid
+// tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid,
+// 2 = pool quads per thread, 3 = 8 KB tiles per block of the streamed bn_bwd_apply (0: register kernel)
 void unetca_set_tuning(int key, int value) {
     if (key == 0 && value > 0) g_ew_px = value;
     if (key == 1) g_red_waves = value;
     if (key == 2 && value > 0) g_pool_quads = value;
+    if (key == 3) g_apply_stream = value;
 }
 
 // stage 1 of ReLU+BN backward (s/dp null: no SE in front).  parts: [B * *nparts][2][C]
@@ -1862,6 +2087,17 @@ int unetca_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, in
                          const float* s, const float* dp, float* parts, int* nparts, void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
+        if (!s && stream_ok<T>(C, ldd, ldy)) {
+            static int sslots = 0;
+            if (!sslots) sslots = resident_blocks_smem(reduce_stream_kernel<0>, kRdSmemBytes);
+            if (sslots > 0) {
+                const long chunk = img_red_chunk<T>(C, pix_per_img, B, sslots);
+                dim3 grid(ceil_div(pix_per_img, chunk), B);
+                reduce_stream_kernel<0><<<grid, kThreads, kRdSmemBytes, (cudaStream_t)stream>>>((const bf16*)dout, (const bf16*)y, C, pix_per_img, chunk, scale, shift, mean, parts);
+                *nparts = grid.x * B;
+                return check_launch("bn_bwd_reduce (stream)");
+            }
+        }
         static int slots = 0;
         if (!slots) slots = resident_blocks(bn_bwd_kernel<T, true, false>);
         const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
@@ -1889,10 +2125,29 @@ int unetca_bn_bwd_apply(int dtype, const void* dout, int ldd, const void* y, int
                         const float* invstd, const float* s, const float* dp, const float* coef, void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy); REQ_CHAN(C, lddy);
-        const long chunk = 2 * ew_chunk<T>(C, pix_per_img);
-        dim3 grid(ceil_div(pix_per_img, chunk), B);
         cudaStream_t st = (cudaStream_t)stream;
         const float ihw = 1.f / (float)pix_per_img;
+        if (stream_ok<T>(C, ldd, ldy) && lddy == C) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                cudaError_t e = cudaFuncSetAttribute(bn_bwd_apply_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmemBytes);
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(bn_bwd_apply_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmemBytes);
+                if (e != cudaSuccess) { set_error("bn_bwd_apply: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+                attr_done = true;
+            }
+            // g_apply_stream tiles of 8 KB per block (whole pixels: 8 KB is a multiple of the pixel size for C <= 4096)
+            long chunk = (long)g_apply_stream * kStTile / (C * 2);
+            if (chunk < 1) chunk = 1;
+            dim3 grid(ceil_div(pix_per_img, chunk), B);
+            if (s)
+                bn_bwd_apply_stream_kernel<true><<<grid, kThreads, kStSmemBytes, st>>>((const bf16*)dout, (const bf16*)y, (bf16*)dy, C, pix_per_img, chunk, ihw, scale, shift, mean, invstd, s, dp, coef);
+            else
+                bn_bwd_apply_stream_kernel<false><<<grid, kThreads, kStSmemBytes, st>>>((const bf16*)dout, (const bf16*)y, (bf16*)dy, C, pix_per_img, chunk, ihw, scale, shift, mean, invstd, nullptr, nullptr, coef);
+            return check_launch("bn_bwd_apply (stream)");
+        }
+        const long chunk = 2 * ew_chunk<T>(C, pix_per_img);
+        dim3 grid(ceil_div(pix_per_img, chunk), B);
         if (s)
             bn_bwd_kernel<T, true, true><<<grid, kThreads, 0, st>>>((const T*)dout, ldd, (const T*)y, ldy, (T*)dy, lddy, C, pix_per_img, chunk, ihw, scale, shift, mean, invstd, s, dp, coef, nullptr);
         else

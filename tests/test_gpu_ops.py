@@ -12,6 +12,8 @@ pytestmark = pytest.mark.gpu
 
 from gpu_util import *  # noqa: E402,F401,F403
 
+DEFAULT_APPLY_STREAM = 8      # library default of tuning key 3 (restored after the A/B test)
+
 DTS = [F32, BF16]
 TOL = {F32: 2e-4, BF16: 1.2e-2}
 
@@ -723,3 +725,34 @@ def test_adam_conv3x3_emits_packed_filters(dt, O, C):
     call("unetca_pack_conv3x3_weight", dt, ptr(p), ptr(wf_ref), 9 * C, ptr(wd_ref), O, C, stream())
     assert torch.equal(wf.view(torch.int16 if dt == BF16 else torch.int32), wf_ref.view(torch.int16 if dt == BF16 else torch.int32))
     assert torch.equal(wd.view(torch.int16 if dt == BF16 else torch.int32), wd_ref.view(torch.int16 if dt == BF16 else torch.int32))
+
+
+@pytest.mark.parametrize("B,C,HW,se", [(2, 64, 16 * 16, False), (3, 128, 37 * 45, True), (2, 1024, 2 * 2, True), (1, 64, 1, False),
+                                       (2, 256, 640, True), (5, 512, 4 * 5, False)])
+def test_bn_bwd_apply_stream_equals_register_kernel(B, C, HW, se):
+    """The shared-memory-streamed form of the ReLU+BN(+SE) backward apply pass (cp.async.bulk ring) must give the very
+    bits of the register kernel — whole tiles, ragged tails, ranges shorter than one tile."""
+    rs = np.random.RandomState(9)
+    mk = lambda *sh: torch.from_numpy(rs.standard_normal(sh).astype(np.float32)).cuda()
+    y, d = mk(B, HW, C).bfloat16(), mk(B, HW, C).bfloat16()
+    scale, shift, mean, invstd = mk(C), mk(C), mk(C), mk(C).abs() + 0.5
+    coef = mk(3, C)
+    s_, dp = (torch.sigmoid(mk(B, C)), mk(B, C)) if se else (None, None)
+    outs = []
+    try:
+        for tiles in (0, 1, 3, 16):
+            unetca_b200._lib.load().unetca_set_tuning(3, tiles)
+            dy = torch.full((B, HW, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+            guard = torch.full((B * HW * C + 4096,), 7.0, dtype=torch.bfloat16, device="cuda")     # guard band behind a second output
+            dy2 = guard[: B * HW * C].view(B, HW, C)
+            for o in (dy, dy2):
+                call("unetca_bn_bwd_apply", BF16, ptr(d), C, ptr(y), C, ptr(o), C, B, HW, C, ptr(scale), ptr(shift), ptr(mean),
+                     ptr(invstd), ptr(s_), ptr(dp), ptr(coef), stream())
+            assert torch.equal(dy.view(torch.int16), dy2.view(torch.int16))
+            assert torch.all(guard[B * HW * C:] == 7.0)
+            assert not torch.isnan(dy.float()).any()
+            outs.append(dy)
+    finally:
+        unetca_b200._lib.load().unetca_set_tuning(3, DEFAULT_APPLY_STREAM)
+    for o in outs[1:]:
+        assert torch.equal(o.view(torch.int16), outs[0].view(torch.int16))

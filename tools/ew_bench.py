@@ -35,8 +35,12 @@ def main():
     ap.add_argument("--red-waves", type=int, nargs="*", default=[1])
     ap.add_argument("--pool-quads", type=int, nargs="*", default=[4])
     ap.add_argument("--shapes", nargs="*", default=None)
+    ap.add_argument("--only", default=None, help="substring filter on the kernel label")
+    ap.add_argument("--apply-stream", type=int, default=None, help="tuning key 3: 8 KB tiles per block of the streamed bn_bwd_apply (0 = register kernel)")
     a = ap.parse_args()
     lib = _lib.load()
+    if a.apply_stream is not None:
+        lib.unetca_set_tuning(3, a.apply_stream)
     st = torch.cuda.current_stream().cuda_stream
     B = a.B
     shapes = SHAPES if not a.shapes else [tuple(int(v) for v in s.split(",")) for s in a.shapes]
@@ -69,6 +73,8 @@ def main():
             "pool_bwd_add    2.25N": (2 * N * 2 + (N // 4) * 3, "fix", lambda: _lib.call("unetca_pool_bwd_add", 1, P(d), C, P(pooled), C, P(pos), P(dy), C, B, S, S, C, st)),
         }
         for name, (nbytes, kind, fn) in kernels.items():
+            if a.only and a.only not in name:
+                continue
             res = []
             settings = [(px, 1) for px in a.ew_px] if kind == "ew" else [(16, w) for w in a.red_waves] if kind == "red" else [(q, 1) for q in a.pool_quads]
             for px, w in settings:
