@@ -1803,6 +1803,26 @@ static int make_map_linear(CUtensorMap* m, const void* base, long C, long W, lon
     return 0;
 }
 
+// Plain (unswizzled) 4-D NHWC map for the streamed elementwise kernels: dims (C, W, H, B), pixel stride ld elements,
+// box (C, bw, bh, 1); elem_bytes 2 (bf16) or 1 (uint8).  Out-of-bounds loads are zero-filled, stores clipped.
+// (external linkage: used by elementwise.cu)
+int make_tmap_nhwc(CUtensorMap* m, const void* base, int elem_bytes, long C, long W, long H, long B, long ld, int bw, int bh) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) { set_error("cuTensorMapEncodeTiled not available"); return UNETCA_ERR_CUDA; }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)W * ld * elem_bytes, (cuuint64_t)H * W * ld * elem_bytes};
+    cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (((uintptr_t)base & 15) || (strides[0] & 15) || C > 256 || bw > 256 || bh > 256 || ((C * elem_bytes) & 15)) {
+        set_error("tensor map (nhwc): base/strides must be 16-byte aligned, box dims <= 256"); return UNETCA_ERR_ARG;
+    }
+    CUresult r = enc(m, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 4,
+                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (nhwc) failed (%d)", (int)r); return UNETCA_ERR_CUDA; }
+    return 0;
+}
+
 // conv3x3 forward / dgrad for O % 128 == 0 through the haloed pixels-on-N kernel; w = packed filter [O][9*C]
 static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
                        float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr,

@@ -17,6 +17,10 @@
 #include <math.h>
 
 namespace unetca {
+int make_tmap_nhwc(CUtensorMap* m, const void* base, int elem_bytes, long C, long W, long H, long B, long ld, int bw, int bh);
+}
+
+namespace unetca {
 
 constexpr int kThreads = 256;
 constexpr int kMaxParts = 1184;  // 148 SMs x 8
@@ -982,6 +986,142 @@ __global__ void __launch_bounds__(kThreads, 2) se_bn_bwd_pool_kernel(const T* __
     }
     if (!APPLY)
         block_reduce_rows<2, VEC>(acc, C, vpr, rows, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
+// The same two passes as a shared-memory stream (bf16, C = 64 / 128 / 256): a tile is one quad-row segment of
+// QW = 2048/C quads — sg and Y as [2 rows][2*QW px][C] boxes, dpooled and pos as [QW][C] — fetched by four TMA tensor
+// copies (so sg may be a channel slice of the decoder's concat gradient), one quad x 8 channels per thread.  APPLY
+// writes dY in place over the sg tile and stores it with one TMA copy.  Same arithmetic as above.
+constexpr int kQpStages = 2;
+constexpr int kQpTileSg = 16384, kQpTileDp = 4096, kQpTilePos = 2048;
+constexpr int kQpStageBytes = 2 * kQpTileSg + kQpTileDp + kQpTilePos;
+constexpr int kQpSmemBytes = kQpStages * kQpStageBytes + 1024;
+struct QpMaps { CUtensorMap sg, y, dp, pos, dy; };
+
+template <bool APPLY>
+__global__ void __launch_bounds__(kThreads, 2) se_bn_bwd_pool_stream_kernel(const __grid_constant__ QpMaps maps, int H, int W, int C,
+                                                                            int tiles_per_block, float inv_hw,
+                                                                            const float* __restrict__ scale,
+                                                                            const float* __restrict__ shift,
+                                                                            const float* __restrict__ mean,
+                                                                            const float* __restrict__ invstd,
+                                                                            const float* __restrict__ s, const float* __restrict__ dp,
+                                                                            const float* __restrict__ coef, float* __restrict__ parts) {
+    extern __shared__ uint8_t qp_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qp_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kQpStages];
+    constexpr int VEC = 8;
+    const int vpr = C / VEC, QW = kThreads / vpr;
+    const int ql = threadIdx.x / vpr, cv = threadIdx.x % vpr;          // quad within the tile, channel vector
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int nseg = (Wo + QW - 1) / QW;
+    const int ntile_img = Ho * nseg;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * tiles_per_block;
+    int t1 = t0 + tiles_per_block; if (t1 > ntile_img) t1 = ntile_img;
+    const int ntiles = t1 > t0 ? t1 - t0 : 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kQpStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        uint8_t* st = smem + (t % kQpStages) * kQpStageBytes;
+        const int tt = t0 + t, ho = tt / nseg, w0 = (tt % nseg) * QW;
+        mbar_expect_tx(&full_bar[t % kQpStages], kQpStageBytes);
+        tma_load_4d(&maps.sg, &full_bar[t % kQpStages], st, 0, 2 * w0, 2 * ho, b);
+        tma_load_4d(&maps.y, &full_bar[t % kQpStages], st + kQpTileSg, 0, 2 * w0, 2 * ho, b);
+        tma_load_4d(&maps.dp, &full_bar[t % kQpStages], st + 2 * kQpTileSg, 0, w0, ho, b);
+        tma_load_4d(&maps.pos, &full_bar[t % kQpStages], st + 2 * kQpTileSg + kQpTileDp, 0, w0, ho, b);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < (APPLY ? kQpStages - 1 : kQpStages) && t < ntiles; ++t) issue(t);
+    float a[VEC], bb[VEC], m0[VEC], m1[VEC], k2[VEC], k0[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = cv * VEC + i;
+        a[i] = scale[c]; bb[i] = shift[c];
+        if (APPLY) {
+            const float g = coef[c], c1 = coef[C + c], c2 = coef[2 * C + c];
+            k2[i] = g * c2 * invstd[c];
+            k0[i] = mean[c] * k2[i] - g * c1;
+            m0[i] = g * s[(long)b * C + c]; m1[i] = g * dp[(long)b * C + c] * inv_hw;
+        } else {
+            k2[i] = mean[c]; k0[i] = 0.f; m0[i] = 0.f; m1[i] = 0.f;
+        }
+    }
+    float acc[2][VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[0][i] = acc[1][i] = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+        uint8_t* st = smem + (t % kQpStages) * kQpStageBytes;
+        mbar_wait(&full_bar[t % kQpStages], (uint32_t)((t / kQpStages) & 1));
+        bf16* sgs = reinterpret_cast<bf16*>(st);
+        const bf16* ys = reinterpret_cast<const bf16*>(st + kQpTileSg);
+        float g[VEC];
+        load_vec(reinterpret_cast<const bf16*>(st + 2 * kQpTileSg) + ((long)ql * C + cv * VEC), g);
+        const uint2 tp = *reinterpret_cast<const uint2*>(st + 2 * kQpTileSg + kQpTileDp + ql * C + cv * VEC);
+        uint8_t code[VEC];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { code[i] = (tp.x >> (8 * i)) & 0xff; code[4 + i] = (tp.y >> (8 * i)) & 0xff; }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long e = ((long)((k >> 1) * 2 * QW + 2 * ql + (k & 1))) * C + cv * VEC;      // [row][px][C]
+            float v[VEC], d[VEC];
+            load_vec(ys + e, v);
+            load_vec(sgs + e, d);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                const float dO = code[i] == k ? d[i] + g[i] : d[i];
+                const bool on = fmaf(a[i], v[i], bb[i]) > 0.f;
+                if (APPLY) {
+                    const float dz = on ? fmaf(dO, m0[i], m1[i]) : 0.f;
+                    d[i] = fmaf(-v[i], k2[i], dz) + k0[i];
+                } else {
+                    const float dm = on ? dO : 0.f;
+                    acc[0][i] += dm;
+                    acc[1][i] = fmaf(dm, v[i] - k2[i], acc[1][i]);
+                }
+            }
+            if (APPLY) store_vec(sgs + e, d);
+        }
+        if (APPLY) fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (APPLY) {
+                const int tt = t0 + t, ho = tt / nseg, w0 = (tt % nseg) * QW;
+                tma_store_4d(&maps.dy, st, 0, 2 * w0, 2 * ho, b);
+                tma_store_commit();
+                if (t >= 1) {
+                    tma_store_wait_read1();
+                    if (t - 1 + kQpStages < ntiles) issue(t - 1 + kQpStages);
+                } else if (kQpStages - 1 < ntiles) {
+                    issue(kQpStages - 1);
+                }
+            } else if (t + kQpStages < ntiles) {
+                issue(t + kQpStages);
+            }
+        }
+    }
+    if (APPLY) { if (threadIdx.x == 0) tma_store_wait_all(); }
+    else block_reduce_rows<2, VEC>(acc, C, vpr, kThreads / vpr, parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C);
+}
+
+// tensor maps + launch geometry of se_bn_bwd_pool_stream_kernel; returns 0 when the shape is not streamable
+static int qp_setup(QpMaps* m, const void* sg, int lds, const void* dpooled, int ldp, const uint8_t* pos, const void* y, int ldy,
+                    void* dy, int lddy, int B, int H, int W, int C) {
+    const int QW = kThreads / (C / 8);
+    int rc;
+    if ((rc = make_tmap_nhwc(&m->sg, sg, 2, C, W, H, B, lds, 2 * QW, 2)) < 0) return rc;
+    if ((rc = make_tmap_nhwc(&m->y, y, 2, C, W, H, B, ldy, 2 * QW, 2)) < 0) return rc;
+    if ((rc = make_tmap_nhwc(&m->dp, dpooled, 2, C, W / 2, H / 2, B, ldp, QW, 1)) < 0) return rc;
+    if ((rc = make_tmap_nhwc(&m->pos, pos, 1, C, W / 2, H / 2, B, C, QW, 1)) < 0) return rc;
+    if (dy && (rc = make_tmap_nhwc(&m->dy, dy, 2, C, W, H, B, lddy, 2 * QW, 2)) < 0) return rc;
+    return 1;
+}
+template <typename T> static inline bool qp_ok(int C, int lds, int ldp, int ldy, int lddy) {
+    return g_apply_stream > 0 && sizeof(T) == 2 && (C == 64 || C == 128 || C == 256) && lds % 8 == 0 && ldp % 8 == 0 &&
+           ldy % 8 == 0 && lddy % 8 == 0;
 }
 
 // SE squeeze (forward): per (image, channel) S3 = sum m and Sy = sum m*y with m = (a*y+b > 0).  The squeeze itself
@@ -1997,6 +2137,24 @@ int unetca_se_bn_bwd_reduce_pool(int dtype, const void* sg, int lds, const void*
     UNETCA_REQUIRE(H % 2 == 0 && W % 2 == 0, "se_bn_bwd_reduce_pool: H, W must be even (got %d x %d)", H, W);
     DISPATCH_T(dtype, {
         REQ_CHAN(C, lds); REQ_CHAN(C, ldp); REQ_CHAN(C, ldy);
+        if (qp_ok<T>(C, lds, ldp, ldy, 8)) {
+            static int sslots = 0;
+            if (!sslots) sslots = resident_blocks_smem(se_bn_bwd_pool_stream_kernel<false>, kQpSmemBytes);
+            QpMaps maps;
+            int rc = sslots > 0 ? qp_setup(&maps, sg, lds, dpooled, ldp, pos, y, ldy, nullptr, 0, B, H, W, C) : 0;
+            if (rc < 0) return rc;
+            if (rc > 0) {
+                const int QW = kThreads / (C / 8);
+                const int ntile_img = (H / 2) * ceil_div(W / 2, QW);
+                int nblk = sslots / B; if (nblk < 1) nblk = 1; if (nblk > ntile_img) nblk = ntile_img;
+                if ((long)nblk * B > kMaxParts) nblk = kMaxParts / B > 0 ? kMaxParts / B : 1;
+                const int tpb = ceil_div(ntile_img, nblk);
+                dim3 grid(ceil_div(ntile_img, tpb), B);
+                se_bn_bwd_pool_stream_kernel<false><<<grid, kThreads, kQpSmemBytes, (cudaStream_t)stream>>>(maps, H, W, C, tpb, 0.f, scale, shift, mean, nullptr, nullptr, nullptr, nullptr, parts);
+                *nparts = grid.x;
+                return check_launch("se_bn_bwd_reduce_pool (stream)");
+            }
+        }
         static int slots = 0;
         if (!slots) slots = resident_blocks(se_bn_bwd_pool_kernel<T, false>);
         const long nquad = (long)(H / 2) * (W / 2);
@@ -2016,6 +2174,21 @@ int unetca_bn_bwd_apply_pool(int dtype, const void* sg, int lds, const void* dpo
     UNETCA_REQUIRE(H % 2 == 0 && W % 2 == 0, "bn_bwd_apply_pool: H, W must be even (got %d x %d)", H, W);
     DISPATCH_T(dtype, {
         REQ_CHAN(C, lds); REQ_CHAN(C, ldp); REQ_CHAN(C, ldy); REQ_CHAN(C, lddy);
+        if (qp_ok<T>(C, lds, ldp, ldy, lddy)) {
+            static int sslots = 0;
+            if (!sslots) sslots = resident_blocks_smem(se_bn_bwd_pool_stream_kernel<true>, kQpSmemBytes);
+            QpMaps maps;
+            int rc = sslots > 0 ? qp_setup(&maps, sg, lds, dpooled, ldp, pos, y, ldy, dy, lddy, B, H, W, C) : 0;
+            if (rc < 0) return rc;
+            if (rc > 0) {
+                const int QW = kThreads / (C / 8);
+                const int ntile_img = (H / 2) * ceil_div(W / 2, QW);
+                const int tpb = 16;
+                dim3 grid(ceil_div(ntile_img, tpb), B);
+                se_bn_bwd_pool_stream_kernel<true><<<grid, kThreads, kQpSmemBytes, (cudaStream_t)stream>>>(maps, H, W, C, tpb, 1.f / (float)((long)H * W), scale, shift, mean, invstd, s, dp, coef, nullptr);
+                return check_launch("bn_bwd_apply_pool (stream)");
+            }
+        }
         const long nquad = (long)(H / 2) * (W / 2);
         const long chunk = (long)row_map<T>(C).rows * g_pool_quads * 2;
         dim3 grid(ceil_div(nquad, chunk), B);

@@ -756,3 +756,39 @@ def test_bn_bwd_apply_stream_equals_register_kernel(B, C, HW, se):
         unetca_b200._lib.load().unetca_set_tuning(3, DEFAULT_APPLY_STREAM)
     for o in outs[1:]:
         assert torch.equal(o.view(torch.int16), outs[0].view(torch.int16))
+
+
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 8, 128), (3, 64, 6, 70), (2, 128, 12, 16), (1, 256, 4, 34), (2, 256, 18, 16), (1, 64, 2, 2)])
+def test_pool_backward_stream_equals_register_kernels(B, C, H, W):
+    """The quad-row shared-memory stream of se_bn_bwd_reduce_pool / bn_bwd_apply_pool (TMA tensor copies, sg a channel
+    slice of a wider buffer) against the register kernels: apply bit-identical, sums equal up to fp32 summation order."""
+    rs = np.random.RandomState(21)
+    mk = lambda *sh: torch.from_numpy(rs.standard_normal(sh).astype(np.float32)).cuda()
+    y = mk(B, H, W, C).bfloat16()
+    sg = mk(B, H, W, 2 * C).bfloat16()[..., C:]                       # strided view (the skip half of a concat gradient)
+    dpl = mk(B, H // 2, W // 2, C).bfloat16()
+    pos = torch.from_numpy(rs.randint(0, 4, (B, H // 2, W // 2, C)).astype(np.uint8)).cuda()
+    sc, sh = torch.rand(C, device="cuda") + 0.5, mk(C) * 0.2
+    mean, invstd = mk(C) * 0.2, torch.rand(C, device="cuda") + 0.5
+    s_, dp = torch.rand(B, C, device="cuda"), mk(B, C)
+    coef = torch.rand(3, C, device="cuda")
+    res = {}
+    try:
+        for mode in (0, 8):
+            unetca_b200._lib.load().unetca_set_tuning(3, mode)
+            parts = parts_buf(B, 4096)
+            n = cint()
+            call("unetca_se_bn_bwd_reduce_pool", BF16, ptr(sg), 2 * C, ptr(dpl), C, ptr(pos), ptr(y), C, B, H, W, C, ptr(sc), ptr(sh),
+                 ptr(mean), ptr(parts), ctypes.byref(n), stream())
+            sums = parts[: B * n.value * 2 * C].view(B, n.value, 2, C).double().sum(1)
+            guard = torch.full((B * H * W * C + 8192,), 3.0, dtype=torch.bfloat16, device="cuda")
+            dy = guard[: B * H * W * C].view(B, H, W, C)
+            dy.fill_(float("nan"))
+            call("unetca_bn_bwd_apply_pool", BF16, ptr(sg), 2 * C, ptr(dpl), C, ptr(pos), ptr(y), C, ptr(dy), C, B, H, W, C, ptr(sc),
+                 ptr(sh), ptr(mean), ptr(invstd), ptr(s_), ptr(dp), ptr(coef), stream())
+            assert torch.all(guard[B * H * W * C:] == 3.0) and not torch.isnan(dy.float()).any()
+            res[mode] = (sums, dy.clone())
+    finally:
+        unetca_b200._lib.load().unetca_set_tuning(3, DEFAULT_APPLY_STREAM)
+    assert torch.equal(res[0][1].view(torch.int16), res[8][1].view(torch.int16))
+    assert relerr(res[8][0], res[0][0]) < 1e-5
