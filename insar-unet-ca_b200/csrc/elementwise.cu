@@ -991,11 +991,13 @@ __global__ void __launch_bounds__(kThreads, 2) se_bn_bwd_pool_kernel(const T* __
 // The same two passes as a shared-memory stream (bf16, C = 64 / 128 / 256): a tile is one quad-row segment of
 // QW = 2048/C quads — sg and Y as [2 rows][2*QW px][C] boxes, dpooled and pos as [QW][C] — fetched by four TMA tensor
 // copies (so sg may be a channel slice of the decoder's concat gradient), one quad x 8 channels per thread.  APPLY
-// writes dY in place over the sg tile and stores it with one TMA copy.  Same arithmetic as above.
+// writes dY into one of two staging tiles and stores it with one TMA copy, so the input stages refill at once.
+// Same arithmetic as above.
 constexpr int kQpStages = 2;
 constexpr int kQpTileSg = 16384, kQpTileDp = 4096, kQpTilePos = 2048;
 constexpr int kQpStageBytes = 2 * kQpTileSg + kQpTileDp + kQpTilePos;
 constexpr int kQpSmemBytes = kQpStages * kQpStageBytes + 1024;
+constexpr int kQpSmemBytesApply = kQpSmemBytes + 2 * kQpTileSg;       // + two dY staging tiles
 struct QpMaps { CUtensorMap sg, y, dp, pos, dy; };
 
 template <bool APPLY>
@@ -1035,7 +1037,8 @@ __global__ void __launch_bounds__(kThreads, 2) se_bn_bwd_pool_stream_kernel(cons
         tma_load_4d(&maps.pos, &full_bar[t % kQpStages], st + 2 * kQpTileSg + kQpTileDp, 0, w0, ho, b);
     };
     if (threadIdx.x == 0)
-        for (int t = 0; t < (APPLY ? kQpStages - 1 : kQpStages) && t < ntiles; ++t) issue(t);
+        for (int t = 0; t < kQpStages && t < ntiles; ++t) issue(t);
+    uint8_t* out_tiles = smem + kQpStages * kQpStageBytes;             // APPLY: dY staging, double-buffered
     float a[VEC], bb[VEC], m0[VEC], m1[VEC], k2[VEC], k0[VEC];
 #pragma unroll
     for (int i = 0; i < VEC; ++i) {
@@ -1056,8 +1059,9 @@ __global__ void __launch_bounds__(kThreads, 2) se_bn_bwd_pool_stream_kernel(cons
     for (int t = 0; t < ntiles; ++t) {
         uint8_t* st = smem + (t % kQpStages) * kQpStageBytes;
         mbar_wait(&full_bar[t % kQpStages], (uint32_t)((t / kQpStages) & 1));
-        bf16* sgs = reinterpret_cast<bf16*>(st);
+        const bf16* sgs = reinterpret_cast<const bf16*>(st);
         const bf16* ys = reinterpret_cast<const bf16*>(st + kQpTileSg);
+        bf16* outs = reinterpret_cast<bf16*>(out_tiles + (t & 1) * kQpTileSg);
         float g[VEC];
         load_vec(reinterpret_cast<const bf16*>(st + 2 * kQpTileSg) + ((long)ql * C + cv * VEC), g);
         const uint2 tp = *reinterpret_cast<const uint2*>(st + 2 * kQpTileSg + kQpTileDp + ql * C + cv * VEC);
@@ -1083,24 +1087,21 @@ __global__ void __launch_bounds__(kThreads, 2) se_bn_bwd_pool_stream_kernel(cons
                     acc[1][i] = fmaf(dm, v[i] - k2[i], acc[1][i]);
                 }
             }
-            if (APPLY) store_vec(sgs + e, d);
+            if (APPLY) store_vec(outs + e, d);
         }
-        if (APPLY) fence_proxy_async_smem();
+        if (APPLY) {
+            // the other staging tile (written next iteration) must have been read by its store, issued one tile ago
+            if (threadIdx.x == 0) tma_store_wait_read();
+            fence_proxy_async_smem();
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
             if (APPLY) {
                 const int tt = t0 + t, ho = tt / nseg, w0 = (tt % nseg) * QW;
-                tma_store_4d(&maps.dy, st, 0, 2 * w0, 2 * ho, b);
+                tma_store_4d(&maps.dy, outs, 0, 2 * w0, 2 * ho, b);
                 tma_store_commit();
-                if (t >= 1) {
-                    tma_store_wait_read1();
-                    if (t - 1 + kQpStages < ntiles) issue(t - 1 + kQpStages);
-                } else if (kQpStages - 1 < ntiles) {
-                    issue(kQpStages - 1);
-                }
-            } else if (t + kQpStages < ntiles) {
-                issue(t + kQpStages);
             }
+            if (t + kQpStages < ntiles) issue(t + kQpStages);      // the input stage is free as soon as everyone has read it
         }
     }
     if (APPLY) { if (threadIdx.x == 0) tma_store_wait_all(); }
@@ -1122,6 +1123,165 @@ static int qp_setup(QpMaps* m, const void* sg, int lds, const void* dpooled, int
 template <typename T> static inline bool qp_ok(int C, int lds, int ldp, int ldy, int lddy) {
     return g_apply_stream > 0 && sizeof(T) == 2 && (C == 64 || C == 128 || C == 256) && lds % 8 == 0 && ldp % 8 == 0 &&
            ldy % 8 == 0 && lddy % 8 == 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Block output o = relu(a*y+b) * s[b,c] (+ fused MaxPool2d(2)) as shared-memory streams (bf16).
+//   se_scale_pool_stream_kernel: quad-row tiles as above — Y in by one TMA tensor copy; o (possibly a channel slice of
+//     the decoder's concat buffer), pooled and pos out by three, from double-buffered staging (C = 64 / 128 / 256)
+//   se_scale_stream_kernel: dense 1-D tiles, transformed in place (any power-of-two channel-vector count)
+// Same arithmetic, rounding and tie-break as se_scale_pool_kernel / se_scale_kernel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSpStages = 3;
+constexpr int kSpOutBytes = kQpTileSg + kQpTileDp + kQpTilePos;                      // o | pooled | pos
+constexpr int kSpSmemBytes = kSpStages * kQpTileSg + 2 * kSpOutBytes + 1024;
+struct SpMaps { CUtensorMap y, out, pooled, pos; };
+
+__global__ void __launch_bounds__(kThreads, 2) se_scale_pool_stream_kernel(const __grid_constant__ SpMaps maps, int H, int W, int C,
+                                                                           int tiles_per_block, const float* __restrict__ scale,
+                                                                           const float* __restrict__ shift,
+                                                                           const float* __restrict__ s) {
+    extern __shared__ uint8_t qp_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(qp_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t full_bar[kSpStages];
+    constexpr int VEC = 8;
+    const int vpr = C / VEC, QW = kThreads / vpr;
+    const int ql = threadIdx.x / vpr, cv = threadIdx.x % vpr;
+    const int Ho = H >> 1, Wo = W >> 1;
+    const int nseg = (Wo + QW - 1) / QW;
+    const int ntile_img = Ho * nseg;
+    const int b = blockIdx.y;
+    const int t0 = blockIdx.x * tiles_per_block;
+    int t1 = t0 + tiles_per_block; if (t1 > ntile_img) t1 = ntile_img;
+    const int ntiles = t1 > t0 ? t1 - t0 : 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSpStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const int tt = t0 + t, ho = tt / nseg, w0 = (tt % nseg) * QW;
+        mbar_expect_tx(&full_bar[t % kSpStages], kQpTileSg);
+        tma_load_4d(&maps.y, &full_bar[t % kSpStages], smem + (t % kSpStages) * kQpTileSg, 0, 2 * w0, 2 * ho, b);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < kSpStages && t < ntiles; ++t) issue(t);
+    uint8_t* out_tiles = smem + kSpStages * kQpTileSg;
+    float a[VEC], sh[VEC], g[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        a[i] = scale[cv * VEC + i];
+        sh[i] = shift[cv * VEC + i];
+        g[i] = s ? s[(long)b * C + cv * VEC + i] : 1.f;
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        mbar_wait(&full_bar[t % kSpStages], (uint32_t)((t / kSpStages) & 1));
+        const bf16* ys = reinterpret_cast<const bf16*>(smem + (t % kSpStages) * kQpTileSg);
+        uint8_t* ob = out_tiles + (t & 1) * kSpOutBytes;
+        bf16* os = reinterpret_cast<bf16*>(ob);
+        float best[VEC];
+        uint8_t code[VEC];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long e = ((long)((k >> 1) * 2 * QW + 2 * ql + (k & 1))) * C + cv * VEC;
+            float v[VEC];
+            load_vec(ys + e, v);
+#pragma unroll
+            for (int i = 0; i < VEC; ++i) {
+                float tv = fmaxf(fmaf(a[i], v[i], sh[i]), 0.f) * g[i];
+                tv = round_to(tv, (const bf16*)nullptr);
+                v[i] = tv;
+                if (k == 0) { best[i] = tv; code[i] = 0; }
+                else if (tv > best[i] || tv != tv) { best[i] = tv; code[i] = (uint8_t)k; }
+            }
+            store_vec(os + e, v);
+        }
+        store_vec(reinterpret_cast<bf16*>(ob + kQpTileSg) + ((long)ql * C + cv * VEC), best);
+        uint2 tp;
+        tp.x = code[0] | (code[1] << 8) | (code[2] << 16) | (code[3] << 24);
+        tp.y = code[4] | (code[5] << 8) | (code[6] << 16) | (code[7] << 24);
+        *reinterpret_cast<uint2*>(ob + kQpTileSg + kQpTileDp + ql * C + cv * VEC) = tp;
+        if (threadIdx.x == 0) tma_store_wait_read();        // the other staging buffer's stores (one tile ago) have read it
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int tt = t0 + t, ho = tt / nseg, w0 = (tt % nseg) * QW;
+            tma_store_4d(&maps.out, ob, 0, 2 * w0, 2 * ho, b);
+            tma_store_4d(&maps.pooled, ob + kQpTileSg, 0, w0, ho, b);
+            tma_store_4d(&maps.pos, ob + kQpTileSg + kQpTileDp, 0, w0, ho, b);
+            tma_store_commit();
+            if (t + kSpStages < ntiles) issue(t + kSpStages);
+        }
+    }
+    if (threadIdx.x == 0) tma_store_wait_all();
+}
+
+constexpr int kScTile = 16384;
+constexpr int kScStages = 4;
+constexpr int kScSmemBytes = kScStages * kScTile;
+__global__ void __launch_bounds__(kThreads, 3) se_scale_stream_kernel(const bf16* __restrict__ y, bf16* __restrict__ out, int C,
+                                                                      long pix_per_img, long chunk,
+                                                                      const float* __restrict__ scale,
+                                                                      const float* __restrict__ shift,
+                                                                      const float* __restrict__ s) {
+    extern __shared__ __align__(128) uint8_t st_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kScStages];
+    constexpr int VEC = 8;
+    const int vpr = C / VEC;
+    const int cv = threadIdx.x & (vpr - 1);
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > pix_per_img) p1 = pix_per_img;
+    const long off0 = ((long)blockIdx.y * pix_per_img + p0) * C * 2;
+    const long nbytes = (p1 - p0) * C * 2;
+    const int ntiles = (int)((nbytes + kScTile - 1) / kScTile);
+    const uint8_t* yb = reinterpret_cast<const uint8_t*>(y) + off0;
+    uint8_t* ob = reinterpret_cast<uint8_t*>(out) + off0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kScStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const long o = (long)t * kScTile;
+        const uint32_t bytes = (uint32_t)(nbytes - o < kScTile ? nbytes - o : kScTile);
+        mbar_expect_tx(&full_bar[t % kScStages], bytes);
+        bulk_load_1d(st_smem + (t % kScStages) * kScTile, yb + o, bytes, &full_bar[t % kScStages]);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < kScStages - 1 && t < ntiles; ++t) issue(t);
+    float a[VEC], sh[VEC], g[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        a[i] = scale[cv * VEC + i];
+        sh[i] = shift[cv * VEC + i];
+        g[i] = s ? s[(long)blockIdx.y * C + cv * VEC + i] : 1.f;
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        const long o = (long)t * kScTile;
+        const int bytes = (int)(nbytes - o < kScTile ? nbytes - o : kScTile);
+        mbar_wait(&full_bar[t % kScStages], (uint32_t)((t / kScStages) & 1));
+        bf16* ys = reinterpret_cast<bf16*>(st_smem + (t % kScStages) * kScTile);
+        for (int i = threadIdx.x; i < bytes / 16; i += kThreads) {
+            float v[VEC];
+            load_vec(ys + i * VEC, v);
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) v[j] = fmaxf(fmaf(a[j], v[j], sh[j]), 0.f) * g[j];
+            store_vec(ys + i * VEC, v);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store_1d(ob + o, ys, (uint32_t)bytes);
+            tma_store_commit();
+            if (t >= 1) {
+                tma_store_wait_read1();
+                if (t - 1 + kScStages < ntiles) issue(t - 1 + kScStages);
+            } else if (kScStages - 1 < ntiles) {
+                issue(kScStages - 1);
+            }
+        }
+    }
+    if (threadIdx.x == 0) tma_store_wait_all();
 }
 
 // SE squeeze (forward): per (image, channel) S3 = sum m and Sy = sum m*y with m = (a*y+b > 0).  The squeeze itself
@@ -2039,6 +2199,39 @@ int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, 
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldy); REQ_CHAN(C, ldo);
         cudaStream_t st = (cudaStream_t)stream;
+        if (pooled && qp_ok<T>(C, ldy, ldo, ldp, 8)) {
+            static int sslots = 0;
+            if (!sslots) sslots = resident_blocks_smem(se_scale_pool_stream_kernel, kSpSmemBytes);
+            if (sslots > 0) {
+                const int QW = kThreads / (C / 8);
+                SpMaps maps;
+                int rc;
+                if ((rc = make_tmap_nhwc(&maps.y, y, 2, C, W, H, B, ldy, 2 * QW, 2)) < 0) return rc;
+                if ((rc = make_tmap_nhwc(&maps.out, out, 2, C, W, H, B, ldo, 2 * QW, 2)) < 0) return rc;
+                if ((rc = make_tmap_nhwc(&maps.pooled, pooled, 2, C, W / 2, H / 2, B, ldp, QW, 1)) < 0) return rc;
+                if ((rc = make_tmap_nhwc(&maps.pos, pos, 1, C, W / 2, H / 2, B, C, QW, 1)) < 0) return rc;
+                const int ntile_img = (H / 2) * ceil_div(W / 2, QW);
+                const int tpb = 16;
+                dim3 grid(ceil_div(ntile_img, tpb), B);
+                se_scale_pool_stream_kernel<<<grid, kThreads, kSpSmemBytes, st>>>(maps, H, W, C, tpb, scale, shift, s);
+                return check_launch("se_scale_pool (stream)");
+            }
+        }
+        if (!pooled && stream_ok<T>(C, ldy, ldo)) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                if (cudaFuncSetAttribute(se_scale_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScSmemBytes) != cudaSuccess) {
+                    set_error("se_scale: cudaFuncSetAttribute failed"); return UNETCA_ERR_CUDA;
+                }
+                attr_done = true;
+            }
+            const long hw = (long)H * W;
+            long chunk = (long)g_apply_stream * kScTile / (C * 2);
+            if (chunk < 1) chunk = 1;
+            dim3 grid(ceil_div(hw, chunk), B);
+            se_scale_stream_kernel<<<grid, kThreads, kScSmemBytes, st>>>((const bf16*)y, (bf16*)out, C, hw, chunk, scale, shift, s);
+            return check_launch("se_scale (stream)");
+        }
         if (pooled) {
             REQ_CHAN(C, ldp);
             const long nquad = (long)(H / 2) * (W / 2);
@@ -2176,7 +2369,7 @@ int unetca_bn_bwd_apply_pool(int dtype, const void* sg, int lds, const void* dpo
         REQ_CHAN(C, lds); REQ_CHAN(C, ldp); REQ_CHAN(C, ldy); REQ_CHAN(C, lddy);
         if (qp_ok<T>(C, lds, ldp, ldy, lddy)) {
             static int sslots = 0;
-            if (!sslots) sslots = resident_blocks_smem(se_bn_bwd_pool_stream_kernel<true>, kQpSmemBytes);
+            if (!sslots) sslots = resident_blocks_smem(se_bn_bwd_pool_stream_kernel<true>, kQpSmemBytesApply);
             QpMaps maps;
             int rc = sslots > 0 ? qp_setup(&maps, sg, lds, dpooled, ldp, pos, y, ldy, dy, lddy, B, H, W, C) : 0;
             if (rc < 0) return rc;
@@ -2185,7 +2378,7 @@ int unetca_bn_bwd_apply_pool(int dtype, const void* sg, int lds, const void* dpo
                 const int ntile_img = (H / 2) * ceil_div(W / 2, QW);
                 const int tpb = 16;
                 dim3 grid(ceil_div(ntile_img, tpb), B);
-                se_bn_bwd_pool_stream_kernel<true><<<grid, kThreads, kQpSmemBytes, (cudaStream_t)stream>>>(maps, H, W, C, tpb, 1.f / (float)((long)H * W), scale, shift, mean, invstd, s, dp, coef, nullptr);
+                se_bn_bwd_pool_stream_kernel<true><<<grid, kThreads, kQpSmemBytesApply, (cudaStream_t)stream>>>(maps, H, W, C, tpb, 1.f / (float)((long)H * W), scale, shift, mean, invstd, s, dp, coef, nullptr);
                 return check_launch("bn_bwd_apply_pool (stream)");
             }
         }

@@ -792,3 +792,35 @@ def test_pool_backward_stream_equals_register_kernels(B, C, H, W):
         unetca_b200._lib.load().unetca_set_tuning(3, DEFAULT_APPLY_STREAM)
     assert torch.equal(res[0][1].view(torch.int16), res[8][1].view(torch.int16))
     assert relerr(res[8][0], res[0][0]) < 1e-5
+
+
+@pytest.mark.parametrize("B,C,H,W,pool", [(2, 64, 8, 128, True), (3, 64, 6, 70, True), (2, 128, 12, 16, True), (1, 256, 4, 34, True),
+                                          (1, 64, 2, 2, True), (2, 64, 9, 37, False), (2, 1024, 2, 2, False), (3, 128, 40, 24, False)])
+def test_se_scale_pool_stream_equals_register_kernel(B, C, H, W, pool):
+    """Block output relu(bn(y)) * s (+ MaxPool2d(2) value and window position, UCA:72, 106-109) through the shared-memory
+    streams: bit-identical to the register kernels, also when the output is a channel slice of a wider buffer."""
+    rs = np.random.RandomState(23)
+    mk = lambda *sh: torch.from_numpy(rs.standard_normal(sh).astype(np.float32)).cuda()
+    y = mk(B, H, W, C).bfloat16()
+    y[0, 0, 0, :8] = float("nan")                                     # NaN propagates through max-pool like torch
+    sc, sh = torch.rand(C, device="cuda") + 0.5, mk(C) * 0.2
+    s_ = torch.rand(B, C, device="cuda")
+    res = {}
+    try:
+        for mode in (0, 8):
+            unetca_b200._lib.load().unetca_set_tuning(3, mode)
+            wide = torch.full((B, H, W, 2 * C if pool else C), 5.0, dtype=torch.bfloat16, device="cuda")
+            out = wide[..., :C]
+            pooled = torch.full((B, H // 2, W // 2, C), 5.0, dtype=torch.bfloat16, device="cuda") if pool else None
+            pos = torch.full((B, H // 2, W // 2, C), 9, dtype=torch.uint8, device="cuda") if pool else None
+            call("unetca_se_scale_pool", BF16, ptr(y), C, ptr(out), wide.shape[-1], ptr(pooled), C, ptr(pos), B, H, W, C, ptr(sc), ptr(sh),
+                 ptr(s_), stream())
+            if pool:
+                assert torch.all(wide[..., C:] == 5.0)                 # the other half of the concat buffer is untouched
+            res[mode] = (wide.clone(), pooled, pos)
+    finally:
+        unetca_b200._lib.load().unetca_set_tuning(3, DEFAULT_APPLY_STREAM)
+    assert torch.equal(res[0][0].view(torch.int16), res[8][0].view(torch.int16))
+    if pool:
+        assert torch.equal(res[0][1].view(torch.int16), res[8][1].view(torch.int16))
+        assert torch.equal(res[0][2], res[8][2])
