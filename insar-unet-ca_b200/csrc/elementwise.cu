@@ -1685,6 +1685,182 @@ __global__ void __launch_bounds__(kThreads) outc_bwd_kernel(const float* __restr
         }
     }
 }
+// outc forward / backward as shared-memory streams (bf16, dense, C = 64, at most 2 classes, H*W a multiple of 128):
+// 128-pixel tiles of x by cp.async.bulk; 8 threads share a pixel (16 B each) as in the kernels above.  Forward stages
+// the 2 x 128 logits of a tile and writes them as two 512-byte runs; backward also fetches the tile's dlogits rows by
+// bulk copy, overwrites the x tile with dx and stores it in bulk.  Same arithmetic as the register kernels.
+constexpr int kOcTile = 16384, kOcPix = 128;
+constexpr int kOcFwdStages = 4;
+constexpr int kOcFwdSmem = kOcFwdStages * kOcTile;
+__global__ void __launch_bounds__(kThreads, 3) outc_fwd_stream_kernel(const bf16* __restrict__ x, const float* __restrict__ w,
+                                                                      const float* __restrict__ bias, int nc,
+                                                                      float* __restrict__ logits, long HW, long chunk) {
+    extern __shared__ __align__(128) uint8_t st_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kOcFwdStages];
+    __shared__ float res[2][kOcPix];
+    constexpr int C = 64, VEC = 8;
+    const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > HW) p1 = HW;
+    const int b = blockIdx.y;
+    const long nbytes = (p1 - p0) * C * 2;
+    const int ntiles = (int)((nbytes + kOcTile - 1) / kOcTile);
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + ((long)b * HW + p0) * C * 2;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kOcFwdStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const long o = (long)t * kOcTile;
+        const uint32_t bytes = (uint32_t)(nbytes - o < kOcTile ? nbytes - o : kOcTile);
+        mbar_expect_tx(&full_bar[t % kOcFwdStages], bytes);
+        bulk_load_1d(st_smem + (t % kOcFwdStages) * kOcTile, xb + o, bytes, &full_bar[t % kOcFwdStages]);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < kOcFwdStages && t < ntiles; ++t) issue(t);
+    float wr[2][VEC];
+#pragma unroll
+    for (int o = 0; o < 2; ++o)
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) wr[o][i] = o < nc ? w[o * C + sub * VEC + i] : 0.f;
+    const float bo = (threadIdx.x >> 7) < nc ? bias[threadIdx.x >> 7] : 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+        const long o = (long)t * kOcTile;
+        const int npx = (int)((nbytes - o < kOcTile ? nbytes - o : kOcTile) / (C * 2));
+        mbar_wait(&full_bar[t % kOcFwdStages], (uint32_t)((t / kOcFwdStages) & 1));
+        const bf16* xs = reinterpret_cast<const bf16*>(st_smem + (t % kOcFwdStages) * kOcTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int px = pl + 32 * k;
+            float acc0 = 0.f, acc1 = 0.f;
+            if (px < npx) {
+                float v[VEC];
+                load_vec(xs + px * C + sub * VEC, v);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) { acc0 = fmaf(v[i], wr[0][i], acc0); acc1 = fmaf(v[i], wr[1][i], acc1); }
+            }
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
+            if (sub == 0) { res[0][px] = acc0; res[1][px] = acc1; }
+        }
+        __syncthreads();                                       // tile consumed, results staged
+        if (threadIdx.x == 0 && t + kOcFwdStages < ntiles) issue(t + kOcFwdStages);
+        {
+            const int o2 = threadIdx.x >> 7, px = threadIdx.x & 127;
+            if (o2 < nc && px < npx) logits[((long)b * nc + o2) * HW + p0 + (long)t * kOcPix + px] = res[o2][px] + bo;
+        }
+        __syncthreads();                                       // res may be overwritten
+    }
+}
+
+constexpr int kOcBwdStages = 4;
+constexpr int kOcBwdStage = kOcTile + 2 * kOcPix * 4;          // x tile | two dlogits rows
+constexpr int kOcBwdSmem = kOcBwdStages * kOcBwdStage;
+__global__ void __launch_bounds__(kThreads, 3) outc_bwd_stream_kernel(const float* __restrict__ g, const float* __restrict__ gscale,
+                                                                      const bf16* __restrict__ x, bf16* __restrict__ dx,
+                                                                      const float* __restrict__ w, int nc, long HW, long chunk,
+                                                                      float* __restrict__ parts) {
+    extern __shared__ __align__(128) uint8_t st_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kOcBwdStages];
+    constexpr int C = 64, VEC = 8, NC = 2;
+    const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > HW) p1 = HW;
+    const int b = blockIdx.y;
+    const long nbytes = (p1 - p0) * C * 2;
+    const int ntiles = (int)((nbytes + kOcTile - 1) / kOcTile);
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(x) + ((long)b * HW + p0) * C * 2;
+    uint8_t* ob = reinterpret_cast<uint8_t*>(dx) + ((long)b * HW + p0) * C * 2;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kOcBwdStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const long o = (long)t * kOcTile;
+        const uint32_t bytes = (uint32_t)(nbytes - o < kOcTile ? nbytes - o : kOcTile);
+        const uint32_t gb = bytes / (C * 2) * 4;                         // dlogits bytes per class (a multiple of 16)
+        uint8_t* st = st_smem + (t % kOcBwdStages) * kOcBwdStage;
+        mbar_expect_tx(&full_bar[t % kOcBwdStages], bytes + nc * gb);
+        bulk_load_1d(st, xb + o, bytes, &full_bar[t % kOcBwdStages]);
+        for (int o2 = 0; o2 < nc; ++o2)
+            bulk_load_1d(st + kOcTile + o2 * kOcPix * 4, g + ((long)b * nc + o2) * HW + p0 + (long)t * kOcPix, gb,
+                         &full_bar[t % kOcBwdStages]);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < kOcBwdStages - 1 && t < ntiles; ++t) issue(t);
+    const float gs = *gscale;
+    float acc[NC][VEC], accb[NC], wv[NC][VEC];
+#pragma unroll
+    for (int o = 0; o < NC; ++o) {
+        accb[o] = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) { acc[o][i] = 0.f; wv[o][i] = o < nc ? w[o * C + sub * VEC + i] : 0.f; }
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        const long o = (long)t * kOcTile;
+        const int bytes = (int)(nbytes - o < kOcTile ? nbytes - o : kOcTile);
+        const int npx = bytes / (C * 2);
+        uint8_t* st = st_smem + (t % kOcBwdStages) * kOcBwdStage;
+        mbar_wait(&full_bar[t % kOcBwdStages], (uint32_t)((t / kOcBwdStages) & 1));
+        bf16* xs = reinterpret_cast<bf16*>(st);
+        const float* gsm = reinterpret_cast<const float*>(st + kOcTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int px = pl + 32 * k;
+            if (px < npx) {
+                float gv[NC];
+#pragma unroll
+                for (int o2 = 0; o2 < NC; ++o2) gv[o2] = o2 < nc ? gsm[o2 * kOcPix + px] : 0.f;
+                float v[VEC], d[VEC];
+                load_vec(xs + px * C + sub * VEC, v);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) d[i] = 0.f;
+#pragma unroll
+                for (int o2 = 0; o2 < NC; ++o2) {
+                    if (sub == 0) accb[o2] += gv[o2];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        d[i] = fmaf(gv[o2], wv[o2][i], d[i]);
+                        acc[o2][i] = fmaf(gv[o2], v[i], acc[o2][i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) d[i] *= gs;
+                store_vec(xs + px * C + sub * VEC, d);
+            }
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_store_1d(ob + o, xs, (uint32_t)bytes);
+            tma_store_commit();
+            if (t >= 1) {
+                tma_store_wait_read1();
+                if (t - 1 + kOcBwdStages < ntiles) issue(t - 1 + kOcBwdStages);
+            } else if (kOcBwdStages - 1 < ntiles) {
+                issue(kOcBwdStages - 1);
+            }
+        }
+    }
+    if (threadIdx.x == 0) tma_store_wait_all();
+    float* out = parts + ((long)blockIdx.y * gridDim.x + blockIdx.x) * (NC * C + NC);
+    block_reduce_rows<NC, VEC>(acc, C, 8, kThreads / 8, out);
+    __shared__ float bred[kThreads];
+#pragma unroll
+    for (int o2 = 0; o2 < NC; ++o2) {
+        __syncthreads();
+        bred[threadIdx.x] = sub == 0 ? accb[o2] : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tsum = 0.f;
+            for (int i = 0; i < kThreads; ++i) tsum += bred[i];
+            out[NC * C + o2] = tsum;
+        }
+    }
+}
 // finalize: dW[o][c] (nc x C) and db[o] from parts laid out with the padded NC
 __global__ void outc_bwd_finalize_kernel(const float* __restrict__ parts, int nparts, int NCpad, int nc, int C,
                                          const float* __restrict__ gscale, float* __restrict__ dw,
@@ -2598,9 +2774,22 @@ int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, co
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldx);
         const long npix = (long)B * HW;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (stream_ok<T>(C, ldx, ldx) && C == 64 && nc <= 2 && HW % kOcPix == 0) {
+            static bool attr_done = false;
+            if (!attr_done) {
+                if (cudaFuncSetAttribute(outc_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOcFwdSmem) != cudaSuccess) {
+                    set_error("outc_fwd: cudaFuncSetAttribute failed"); return UNETCA_ERR_CUDA;
+                }
+                attr_done = true;
+            }
+            const long chunk = (long)g_apply_stream * 2 * kOcPix;            // 16 tiles per block by default
+            dim3 grid(ceil_div(HW, chunk), B);
+            outc_fwd_stream_kernel<<<grid, kThreads, kOcFwdSmem, st>>>((const bf16*)x, w, bias, nc, logits, HW, chunk);
+            return check_launch("outc_fwd (stream)");
+        }
         int nblk = ceil_div(npix, kThreads);
         if (nblk > 8 * num_sms()) nblk = 8 * num_sms();
-        cudaStream_t st = (cudaStream_t)stream;
         const int ncp = nc_pad(nc);
         const size_t sm = (size_t)ncp * C * sizeof(float);
         if (ncp == 2) outc_fwd_kernel<T, 2><<<nblk, kThreads, sm, st>>>((const T*)x, ldx, C, w, bias, nc, logits, npix, HW);
@@ -2617,9 +2806,24 @@ int unetca_outc_bwd(int dtype, const float* g, const float* gscale, const void* 
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldx); REQ_CHAN(C, lddx);
         const long npix = (long)B * HW;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (stream_ok<T>(C, ldx, lddx) && C == 64 && nc <= 2 && HW % kOcPix == 0) {
+            static int sslots = 0;
+            if (!sslots) sslots = resident_blocks_smem(outc_bwd_stream_kernel, kOcBwdSmem);
+            if (sslots > 0) {
+                // one wave of resident blocks, whole 128-pixel tiles per block, blocks never straddle an image
+                long per_img = sslots / B; if (per_img < 1) per_img = 1;
+                long chunk = ceil_div(ceil_div(HW, per_img), (long)kOcPix) * kOcPix;
+                dim3 grid(ceil_div(HW, chunk), B);
+                if ((long)grid.x * B <= kMaxParts) {
+                    outc_bwd_stream_kernel<<<grid, kThreads, kOcBwdSmem, st>>>(g, gscale, (const bf16*)x, (bf16*)dx, w, nc, HW, chunk, parts);
+                    outc_bwd_finalize_kernel<<<ceil_div((long)(nc * C + nc) * 32, 128), 128, 0, st>>>(parts, grid.x * B, 2, nc, C, gscale, dw, db);
+                    return check_launch("outc_bwd (stream)");
+                }
+            }
+        }
         const long chunk = red_chunk<T>(C, npix);
         const int nblk = ceil_div(npix, chunk);
-        cudaStream_t st = (cudaStream_t)stream;
         const int ncp = nc_pad(nc);
         if (ncp == 2) outc_bwd_kernel<T, 2><<<nblk, kThreads, 0, st>>>(g, gscale, (const T*)x, ldx, (T*)dx, lddx, C, w, nc, npix, HW, chunk, parts);
         else if (ncp == 4) outc_bwd_kernel<T, 4><<<nblk, kThreads, 0, st>>>(g, gscale, (const T*)x, ldx, (T*)dx, lddx, C, w, nc, npix, HW, chunk, parts);

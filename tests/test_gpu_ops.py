@@ -824,3 +824,35 @@ def test_se_scale_pool_stream_equals_register_kernel(B, C, H, W, pool):
     if pool:
         assert torch.equal(res[0][1].view(torch.int16), res[8][1].view(torch.int16))
         assert torch.equal(res[0][2], res[8][2])
+
+
+@pytest.mark.parametrize("B,HW,nc", [(2, 128, 2), (3, 128 * 37, 2), (2, 512 * 512, 2), (2, 1024, 1)])
+def test_outc_stream_equals_register_kernels(B, HW, nc):
+    """outc (UCA:125, 162) forward and backward through the shared-memory streams against the register kernels:
+    logits and dx bit-identical, dW / db equal up to fp32 summation order."""
+    C = 64
+    rs = np.random.RandomState(27)
+    mk = lambda *sh: torch.from_numpy(rs.standard_normal(sh).astype(np.float32)).cuda()
+    x = mk(B, HW, C).bfloat16()
+    w, bias = mk(nc, C) * 0.2, mk(nc)
+    g = mk(B, nc, HW)
+    gscale = torch.tensor([0.37], device="cuda")
+    res = {}
+    try:
+        for mode in (0, 8):
+            unetca_b200._lib.load().unetca_set_tuning(3, mode)
+            logits = torch.full((B, nc, HW), float("nan"), device="cuda")
+            call("unetca_outc_fwd", BF16, ptr(x), C, C, ptr(w), ptr(bias), nc, ptr(logits), B, HW, stream())
+            dx = torch.full((B, HW, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+            parts = torch.empty(unetca_b200._lib.load().unetca_max_parts(B) * (8 * C + 8), device="cuda")
+            dw, db = torch.empty(nc, C, device="cuda"), torch.empty(nc, device="cuda")
+            call("unetca_outc_bwd", BF16, ptr(g), ptr(gscale), ptr(x), C, ptr(dx), C, C, ptr(w), nc, B, HW, ptr(parts), ptr(dw), ptr(db),
+                 stream())
+            res[mode] = (logits, dx, dw, db)
+    finally:
+        unetca_b200._lib.load().unetca_set_tuning(3, DEFAULT_APPLY_STREAM)
+    assert torch.equal(res[0][0], res[8][0]) and not torch.isnan(res[8][0]).any()
+    assert torch.equal(res[0][1].view(torch.int16), res[8][1].view(torch.int16))
+    assert relerr(res[8][2], res[0][2]) < 1e-5 and relerr(res[8][3], res[0][3]) < 1e-5
+    ref = torch.einsum("bpc,oc->bop", x.float(), w) + bias.view(1, nc, 1)
+    assert relerr(res[8][0], ref) < 1e-5
