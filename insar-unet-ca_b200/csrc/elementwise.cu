@@ -2265,6 +2265,23 @@ template <typename T> static bool chan_ok(int C, int ld) {
 #define REQ_CHAN(C, ld) UNETCA_REQUIRE(chan_ok<T>(C, ld), "%s: C=%d ld=%d unsupported (C must be a multiple of %d, <= %d)", \
                                        __func__, C, ld, VecTraits<T>::N, kThreads * VecTraits<T>::N)
 
+// out = relu(a*y+b) [* s[b,c]] over dense bf16 tensors through se_scale_stream_kernel
+static int launch_se_scale_stream(const void* y, void* out, int B, long hw, int C, const float* scale, const float* shift,
+                                  const float* s, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(se_scale_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScSmemBytes) != cudaSuccess) {
+            set_error("se_scale: cudaFuncSetAttribute failed"); return UNETCA_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    long chunk = (long)g_apply_stream * kScTile / (C * 2);
+    if (chunk < 1) chunk = 1;
+    dim3 grid(ceil_div(hw, chunk), B);
+    se_scale_stream_kernel<<<grid, kThreads, kScSmemBytes, st>>>((const bf16*)y, (bf16*)out, C, hw, chunk, scale, shift, s);
+    return check_launch("se_scale (stream)");
+}
+
 extern "C" {
 
 // capacity (in partial rows) every `parts` scratch argument must provide for a batch of B images
@@ -2306,6 +2323,10 @@ int unetca_bn_relu(int dtype, const void* y, int ldy, void* out, int ldo, int B,
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldy);
         if (out) REQ_CHAN(C, ldo);
+        if (out && !pool_parts && stream_ok<T>(C, ldy, ldo)) {
+            if (nparts) *nparts = 0;
+            return launch_se_scale_stream(y, out, B, pix_per_img, C, scale, shift, nullptr, (cudaStream_t)stream);
+        }
         static int slots = 0;
         if (!slots) slots = resident_blocks(bn_relu_kernel<T, false, true>);
         const long chunk = pool_parts ? img_red_chunk<T>(C, pix_per_img, B, slots) : ew_chunk<T>(C, pix_per_img);
@@ -2393,21 +2414,7 @@ int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, 
                 return check_launch("se_scale_pool (stream)");
             }
         }
-        if (!pooled && stream_ok<T>(C, ldy, ldo)) {
-            static bool attr_done = false;
-            if (!attr_done) {
-                if (cudaFuncSetAttribute(se_scale_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScSmemBytes) != cudaSuccess) {
-                    set_error("se_scale: cudaFuncSetAttribute failed"); return UNETCA_ERR_CUDA;
-                }
-                attr_done = true;
-            }
-            const long hw = (long)H * W;
-            long chunk = (long)g_apply_stream * kScTile / (C * 2);
-            if (chunk < 1) chunk = 1;
-            dim3 grid(ceil_div(hw, chunk), B);
-            se_scale_stream_kernel<<<grid, kThreads, kScSmemBytes, st>>>((const bf16*)y, (bf16*)out, C, hw, chunk, scale, shift, s);
-            return check_launch("se_scale (stream)");
-        }
+        if (!pooled && stream_ok<T>(C, ldy, ldo)) return launch_se_scale_stream(y, out, B, (long)H * W, C, scale, shift, s, st);
         if (pooled) {
             REQ_CHAN(C, ldp);
             const long nquad = (long)(H / 2) * (W / 2);
