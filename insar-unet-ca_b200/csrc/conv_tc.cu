@@ -1466,18 +1466,22 @@ constexpr int kKwXBytes = kKwTW * (kKwTH + 2) * 128;      // 24 KB: [6 rows][32 
 constexpr int kKwWBox = 192 * 128;                        // 24 KB: [(kw,o)][64 c]
 constexpr int kKwOutTile = kKwTH * (kKwTW - 2) * 128;     // staging tile: [4 x 30 px][64 ch] = 15 KB
 constexpr int kKwOutBytes = 2 * kKwOutTile;               // double-buffered: the TMA store of tile i drains under tile i+1
-constexpr int kKwStatBytes = 2 * 64 * 4 + 8 * 64 * 4;
-static int kw_smem_bytes(int cchunks, int xs) { return 1024 + 3 * cchunks * kKwWBox + xs * kKwXBytes + kKwOutBytes + kKwStatBytes + 256; }
+constexpr int kKwStatBytes = 2 * 64 * 4 + 16 * 64 * 4;
+constexpr int kKwThreads = 320;                          // producer, MMA issuer, eight epilogue warps
+static int kw_smem_bytes(int cchunks, int xs) { return 3 * cchunks * kKwWBox + xs * kKwXBytes + kKwOutBytes + kKwStatBytes + 256; }
 
 template <int XS>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __grid_constant__ KwParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+__global__ void __launch_bounds__(kKwThreads, 1) tc_conv3x3_kw_kernel(const __grid_constant__ KwParams p) {
+    // the budget has no room for an alignment pad (resident filter + ring + staging fill the 227 KB): the array is
+    // declared 1024-byte aligned and the kernel traps if the driver ever places it otherwise
+    extern __shared__ __align__(1024) uint8_t kw_smem[];
+    uint8_t* smem = kw_smem;
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint8_t* w_res = smem;                                         // resident filter: [kh][cc] boxes
     uint8_t* x_ring = w_res + 3 * p.cchunks * kKwWBox;
     uint8_t* out_stage = x_ring + XS * kKwXBytes;
     float* sm_stats = reinterpret_cast<float*>(out_stage + kKwOutBytes);      // [2][64]
-    float* sm_wpart = sm_stats + 128;                                         // [4 warps][2][64]
+    float* sm_wpart = sm_stats + 128;                                         // [8 warps][2][64]
     uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kKwOutBytes + kKwStatBytes);
     uint64_t* xfull = bars;
     uint64_t* xempty = bars + XS;
@@ -1490,7 +1494,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __gr
     if (threadIdx.x == 0) {
         for (int i = 0; i < XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
         mbar_init(wfull, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
         fence_barrier_init();
         prefetch_tmap(&p.mapX);
         prefetch_tmap(&p.mapW);
@@ -1498,7 +1502,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __gr
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     if (p.stat_parts) {
-        for (int i = threadIdx.x; i < 128; i += kTcThreads) sm_stats[i] = 0.f;
+        for (int i = threadIdx.x; i < 128; i += kKwThreads) sm_stats[i] = 0.f;
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -1556,8 +1560,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __gr
             }
         }
     } else {
-        // ================================ epilogue: lane = pixel column of the tile, warp = tile row ==========
+        // ================================ epilogue: lane = pixel column of the tile, warp pair = tile row =====
+        // Eight warps: one warp per scheduler issues ~0.35 instructions per cycle through this dependent shuffle / add /
+        // pack chain and the 24 MMAs of a tile finished in half the time the drain took (tensor pipe 47 % active);
+        // warps w and w + 4 share a TMEM lane quarter and take 32 of the 64 output channels each.
         const int q = warp & 3;                   // TMEM lane quarter == tile row
+        const int half = (warp - 2) >> 2;         // which 32 output channels
         const int ep_tid = threadIdx.x - 64;
         int as = 0; uint32_t aph = 0;
         for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
@@ -1571,11 +1579,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __gr
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
             if (ep_tid == 0) tma_store_wait_read1();         // the store issued two tiles ago has drained this buffer
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             const int nrow = q * kKwOutW + lane - 1;         // staging row of this thread's pixel
             uint8_t* row = stage + nrow * 128;
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
+            {
                 uint32_t a[32], c1[32], c2[32];
                 tmem_ld32(t_addr + 0 * 64 + half * 32, a);
                 tmem_ld32(t_addr + 1 * 64 + half * 32, c1);
@@ -1605,7 +1612,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __gr
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             if (ep_tid == 0) {
                 tma_store_4d(&p.mapOut, stage, 0, x0, y0, b);
                 tma_store_commit();
@@ -1616,7 +1623,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __gr
                 float s1[8], s2[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-                for (int rr = r0; rr < kKwTH * kKwOutW; rr += 16) {
+                for (int rr = r0; rr < kKwTH * kKwOutW; rr += 32) {
                     const uint4 t4 = *reinterpret_cast<const uint4*>(stage + rr * 128 + ((ch ^ (rr & 7)) << 4));
                     const uint32_t w4[4] = {t4.x, t4.y, t4.z, t4.w};
 #pragma unroll
@@ -1642,22 +1649,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_kw_kernel(const __gr
                         sm_wpart[(ew * 2 + 1) * 64 + ch * 8 + i] = s2[i];
                     }
                 }
-                named_bar_sync(1, 128);
-                {
+                named_bar_sync(1, 256);
+                if (ep_tid < 128) {
                     const int which = ep_tid >> 6, col = ep_tid & 63;
                     float tsum = 0.f;
 #pragma unroll
-                    for (int w4i = 0; w4i < 4; ++w4i) tsum += sm_wpart[(w4i * 2 + which) * 64 + col];
+                    for (int w8i = 0; w8i < 8; ++w8i) tsum += sm_wpart[(w8i * 2 + which) * 64 + col];
                     sm_stats[which * 64 + col] += tsum;
                 }
             }
             as ^= 1; if (as == 0) aph ^= 1;
         }
         if (ep_tid == 0) tma_store_wait_all();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (p.stat_parts) {
             float* dst = p.stat_parts + (long)blockIdx.x * 128;
-            for (int i = ep_tid; i < 128; i += 128) dst[i] = sm_stats[i];
+            for (int i = ep_tid; i < 128; i += 256) dst[i] = sm_stats[i];
         }
     }
     tcgen05_fence_before();
@@ -1881,8 +1888,8 @@ static int launch_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy,
     const long num_work = (long)p.tilesX * p.tilesY * B;
     long grid = num_work < num_sms() ? num_work : num_sms();
     if (grid < 1) grid = 1;
-    if (cch == 1) tc_conv3x3_kw_kernel<4><<<(int)grid, kTcThreads, smem, st>>>(p);
-    else tc_conv3x3_kw_kernel<2><<<(int)grid, kTcThreads, smem, st>>>(p);
+    if (cch == 1) tc_conv3x3_kw_kernel<4><<<(int)grid, kKwThreads, smem, st>>>(p);
+    else tc_conv3x3_kw_kernel<2><<<(int)grid, kKwThreads, smem, st>>>(p);
     rc = check_launch("tc_conv3x3_fwd (kw)");
     return rc < 0 ? rc : (int)grid;
 }
