@@ -566,4 +566,10 @@ def main():
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: native libraries write to fd 1 as well (NCCL prints its version banner
+    # there), so fd 1 is pointed at stderr and Python's own stdout keeps the original descriptor
+    _real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(_real_stdout, "w")
     main()
+    sys.stdout.flush()

@@ -2,7 +2,8 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dp_check.py
 Every rank runs its shard of a global batch through the CUDA path with the bucketed, overlapped NCCL all-reduce
 (unetca_b200.parallel.GradBuckets) and compares the resulting parameter gradients with the mean of the per-shard
-gradients of the CPU oracle — fp32 mode 1e-2 on every gradient norm, bf16 1e-2 on the global norm."""
+gradients of the CPU oracle — fp32 mode 1e-2 on every gradient norm, bf16 1e-2 on the global norm —
+and, to 1e-5, with the mean of the per-shard gradients of the same CUDA path run without data parallelism."""
 import os
 import sys
 
@@ -43,18 +44,36 @@ def main():
         params = dict(m.named_parameters())
         tot = torch.sqrt(sum((p.grad.float().cpu() ** 2).sum() for p in params.values())).item()
         rtot = torch.sqrt(sum((v ** 2).sum() for v in ref.values())).item()
-        worst = 0.0
+        worst, worst_name = 0.0, ""
         for k, v in ref.items():
             if v.norm() > 1e-6 * rtot:
-                worst = max(worst, abs(params[k].grad.float().cpu().norm().item() - v.norm().item()) / v.norm().item())
-        good = abs(tot - rtot) / rtot < 1e-2 and (worst < 1e-2 if prec == "fp32" else worst < 0.75)
+                e = abs(params[k].grad.float().cpu().norm().item() - v.norm().item()) / v.norm().item()
+                if e > worst:
+                    worst, worst_name = e, k
+        # the data-parallel machinery itself, free of precision effects: the all-reduced gradient must equal the mean of
+        # the per-shard gradients of the SAME CUDA path run shard by shard on this GPU without GradBuckets
+        own = None
+        for r in range(world):
+            m2 = unetca_b200.UNet(3, 2, True).cuda().set_precision(prec)
+            m2.load_state_dict(sd)
+            m2.train()
+            m2.loss(x[r * per:(r + 1) * per].cuda(), y[r * per:(r + 1) * per].cuda()).backward()
+            g2 = {k: q.grad.double() for k, q in m2.named_parameters()}
+            own = g2 if own is None else {k: own[k] + g2[k] for k in g2}
+        dp_err = max(((params[k].grad.double() - own[k] / world).norm() / (own[k] / world).norm().clamp_min(1e-30)).item()
+                     for k in own)
+        # against the fp32 CPU oracle: every gradient norm in fp32 mode; in bf16 mode the global norm (the per-parameter
+        # figure is reported: the tiny SE fc gradients of 2-image shards are dominated by bf16 rounding, identically so
+        # with and without data parallelism)
+        good = dp_err < 1e-5 and abs(tot - rtot) / rtot < 1e-2 and (worst < 1e-2 or prec != "fp32")
         # every rank must hold identical averaged gradients
         probe = torch.stack([p.grad.flatten()[0] for p in params.values()])
         gathered = [torch.zeros_like(probe) for _ in range(world)]
         dist.all_gather(gathered, probe)
         same = all(torch.equal(gathered[0], t) for t in gathered)
-        print(f"[rank {rank}] {prec}: global grad norm {tot:.6f} vs oracle mean-of-shards {rtot:.6f}, worst per-param "
-              f"norm rel err {worst:.3e}, identical across ranks: {same} -> {'OK' if good and same else 'FAIL'}", flush=True)
+        print(f"[rank {rank}] {prec}: DP vs own mean-of-shards {dp_err:.2e}; global grad norm {tot:.6f} vs oracle mean-of-shards "
+              f"{rtot:.6f}, worst per-param norm rel err {worst:.3e} ({worst_name}), identical across ranks: {same} -> "
+              f"{'OK' if good and same else 'FAIL'}", flush=True)
         ok = ok and good and same
     dist.barrier()
     dist.destroy_process_group()
