@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--block-n", type=int, default=0)
     ap.add_argument("--no-halo", action="store_true", help="narrow layers through the generic one-box-per-tap kernel")
+    ap.add_argument("--kw64", action="store_true", help="64->64 layers through the kw-stacked kernel instead of the row-pair one")
     ap.add_argument("--convT", action="store_true", help="benchmark the four ConvTranspose2d(k2,s2) layers instead")
     ap.add_argument("--convT-narrow", action="store_true", help="ConvTranspose N blocks confined to one sub-pixel map (A/B)")
     ap.add_argument("--pixn-cluster", type=int, default=2, help="CTAs per cluster sharing weights by TMA multicast (1|2)")
@@ -92,7 +93,7 @@ def main():
         dw = torch.empty(O, C, 3, 3, device="cuda")
         fl = 2.0 * B * S * S * 9 * C * O
         wfp = wkw = None
-        if O == 64 and C == 128 and not a.no_kw:
+        if O == 64 and (C == 128 or (C == 64 and a.kw64)) and not a.no_kw:
             wkw = torch.empty(9 * C, 64, device="cuda", dtype=torch.bfloat16)
             _lib.call("unetca_pack_conv3x3_kw", 1, wf.data_ptr(), 9 * C, wkw.data_ptr(), C, st)
         elif O % 128 and not a.no_pixn:
