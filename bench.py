@@ -525,7 +525,7 @@ def main():
               "launches": ncalls_h, "share_of_step": hms / ms, "peak_source": pk["source"] + " hbm_gbs"}
     if domh:
         ach = domh["bytes"] / (domh["ms"] * 1e-3) / 1e9
-        roof_h["dominant"] = {"kernel": "bn_bwd_kernel<bf16,*,APPLY> (entry unetca_bn_bwd_apply: ReLU+BN backward, 3*N*e bytes)",
+        roof_h["dominant"] = {"kernel": "bn_bwd_apply_stream_kernel (entry unetca_bn_bwd_apply: ReLU+BN backward as a cp.async.bulk shared-memory stream, 3*N*e bytes)",
                               "achieved": ach, "frac": ach / pk["hbm_gbs"], "launches": domh["calls"],
                               "avg_launch_ms": domh["ms"] / domh["calls"], "share_of_step": domh["ms"] / ms,
                               "algorithmic_bytes_per_launch": domh["bytes"] / domh["calls"],

@@ -107,8 +107,8 @@ def main():
                          f"--clock-control none {a.command}, last step)",
                "tensor": cls("tensor"), "hbm": cls("hbm"),
                "dominant": one(lambda n: n.startswith("tc_conv3x3_hpix_kernel"), "tc_conv3x3_hpix_kernel"),
-               "dominant_hbm": one(lambda n: re.match(r"bn_bwd_kernel<.*,\s*1>$", n) is not None,
-                                   "bn_bwd_kernel<bf16,*,APPLY> (unetca_bn_bwd_apply)")}
+               "dominant_hbm": one(lambda n: n.startswith("bn_bwd_apply_stream_kernel") or re.match(r"bn_bwd_kernel<.*,\s*1>$", n) is not None,
+                                   "bn_bwd_apply_stream_kernel / bn_bwd_kernel<bf16,*,APPLY> (unetca_bn_bwd_apply)")}
         json.dump(out, open(a.traffic, "w"), indent=1)
     print(open(a.out_prefix + ".txt").read())
 
