@@ -11,7 +11,9 @@ buffers and the gradients all live at fixed addresses inside the graph's private
         loss = step(images, masks)                                # copies into the static inputs, replays the graph
 
 Same kernels in the same order as the eager step, hence bit-identical results (tests/test_gpu_model.py).  Single GPU
-only: the data-parallel bucket all-reduce is not captured.
+only: the data-parallel bucket all-reduce is not captured.  If eager steps ran before, drop every reference to their
+losses / outputs first (`loss = None`): autograd keeps the parameters' AccumulateGrad nodes bound to the stream they
+were created on while an old graph is alive, and a capture that touches them is invalidated.
 """
 from __future__ import annotations
 
