@@ -139,6 +139,9 @@ int unetca_bn_bwd_finalize_se(const float* sums, int B, int C, long count, long 
 int unetca_se_bn_bwd_reduce_pool(int dtype, const void* sg, int lds, const void* dpooled, int ldp, const uint8_t* pos, const void* y, int ldy, int B, int H, int W, int C, const float* scale, const float* shift, const float* mean, float* parts, int* nparts, void* stream);
 int unetca_bn_bwd_apply_pool(int dtype, const void* sg, int lds, const void* dpooled, int ldp, const uint8_t* pos, const void* y, int ldy, void* dy, int lddy, int B, int H, int W, int C, const float* scale, const float* shift, const float* mean, const float* invstd, const float* s, const float* dp, const float* coef, void* stream);
 int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* parts, float* out, void* stream);
+/* out[i] = sum over nrows rows of parts[row*row_stride + i] (i < n): second stage for per-CTA channel sums, e.g. the
+ * ConvTranspose2d bias gradient (UCA:114) taken from the statistics epilogue of the convolution that writes dcat */
+int unetca_sum_rows(const float* parts, int nrows, long row_stride, int n, float* out, void* stream);
 /* tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid,
  * 2 = quads per thread-row of se_scale_pool */
 void unetca_set_tuning(int key, int value);

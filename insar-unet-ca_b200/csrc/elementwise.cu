@@ -1548,6 +1548,15 @@ __global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, in
     out[i] = (float)(tot[0] * (scale_ptr ? (double)*scale_ptr : 1.0));
 }
 
+// out[i] = sum over rows of parts[row * row_stride + i], i < n   (double accumulation, fixed order)
+__global__ void sum_rows_kernel(const float* __restrict__ parts, int nrows, long row_stride, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double t = 0.0;
+    for (int r = 0; r < nrows; ++r) t += (double)parts[(long)r * row_stride + i];
+    out[i] = (float)t;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // outc: 1x1 conv C -> NC class logits, NHWC T in, NCHW fp32 out.                       UCA:125,162
 // 8 lanes share one pixel (16 B each), shuffle-reduce, then the warp's 32 pixels are written coalesced.
@@ -2716,6 +2725,14 @@ int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* p
         sum_parts_kernel<<<ceil_div(C, 32), 256, 0, st>>>(parts, nblk, C, nullptr, out);
     });
     return check_launch("chan_sum");
+}
+
+// out[i] = sum_r parts[r*row_stride + i]: e.g. the ConvTranspose bias gradient (UCA:114) from the per-CTA channel sums
+// that the dgrad convolution producing the concat gradient leaves in its statistics epilogue (parts + Cl, stride 2*O)
+int unetca_sum_rows(const float* parts, int nrows, long row_stride, int n, float* out, void* stream) {
+    UNETCA_REQUIRE(parts && out && nrows >= 1 && n >= 1 && row_stride >= n, "sum_rows: bad arguments");
+    sum_rows_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(parts, nrows, row_stride, n, out);
+    return check_launch("sum_rows");
 }
 
 // counts[(nc+1)][nc] (int64): row = label (row nc: labels outside [0,nc) other than ignore_index), column = argmax

@@ -502,11 +502,13 @@ def _block_grad_order(pre, use_se):
                   pre + ".1.weight", pre + ".1.bias", pre + ".0.weight"]
 
 
-def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None):
+def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=None):
     """Gradient of one DoubleConv block; dout is d(loss)/d(block output) (NHWC view).  Returns d/d(block input).
     G: gradient sink with alloc(name, like) -> tensor to write into and put(name) once it is complete.
     lazy = (skip_grad, dpooled, pos) instead of dout: the output gradient of an encoder block, skip gradient plus the
-    max-pool routing of the pooled gradient, is rebuilt inside the two kernels that consume it (SE blocks, even H, W)."""
+    max-pool routing of the pooled gradient, is rebuilt inside the two kernels that consume it (SE blocks, even H, W).
+    dx_stats = (parts, nparts): have the dgrad convolution that writes the returned gradient leave its per-CTA channel
+    sums there ([n][2][C], the BatchNorm-statistics epilogue) — the decoder takes the ConvTranspose bias gradient from them."""
     blk = sv.blk
     B, Hl, Wl = sv.B, sv.H, sv.W
     C, O = blk.cin, blk.cout
@@ -607,7 +609,8 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None):
         return None
     _, wd1, _, _, wdp1 = eng.conv_w(blk.conv1, dt, tdt, False)
     dx = torch.empty(B, Hl, Wl, C, dtype=tdt, device=dev)
-    _conv3x3(dt, dy1, O, wd1, 9 * O, wdp1, dx, C, B, Hl, Wl, O, C, None, None, st)
+    sp, npp = (dx_stats[0], ctypes.byref(dx_stats[1])) if dx_stats is not None else (None, None)
+    _conv3x3(dt, dy1, O, wd1, 9 * O, wdp1, dx, C, B, Hl, Wl, O, C, _ptr(sp) if sp is not None else None, npp, st)
     return dx
 
 
@@ -669,7 +672,12 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
         up, name = model._ups[i], model._up_names[i]
         Hl, Wl, Cl = sv.Hs[l], sv.Ws[l], _WIDTHS[l]
         hi, wi = sv.Hs[l + 1], sv.Ws[l + 1]
-        dcat = _double_conv_bwd(eng, sv.dec[i], dcur, G, dt, tdt, True)          # (B,Hl,Wl,2Cl)
+        # bf16 tensor-core path, no resize guard: the dgrad conv that writes dcat also leaves its per-CTA channel sums,
+        # whose upper half is the ConvTranspose bias gradient (one less pass over dcat)
+        fused_db = (dt == _lib.BF16 and _lib.load().unetca_get_conv_impl() == 0 and (2 * hi, 2 * wi) == (Hl, Wl))
+        nst = ctypes.c_int(0)
+        dcat = _double_conv_bwd(eng, sv.dec[i], dcur, G, dt, tdt, True,
+                                dx_stats=(parts, nst) if fused_db else None)        # (B,Hl,Wl,2Cl)
         du, ldu = dcat[..., Cl:], 2 * Cl
         skip_grads[l] = dcat[..., :Cl]
         if (2 * hi, 2 * wi) != (Hl, Wl):                                         # adjoint of the resize guard
@@ -677,7 +685,10 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
             _lib.call("unetca_resize_bilinear_bwd", dt, _ptr(du), ldu, Hl, Wl, _ptr(du_s), Cl, 2 * hi, 2 * wi, B, Cl, st)
             du, ldu = du_s, Cl
         dbias = G.alloc(name + ".bias", up.bias)
-        _lib.call("unetca_chan_sum", dt, _ptr(du), ldu, Cl, B * 4 * hi * wi, _ptr(parts), _ptr(dbias), st)
+        if fused_db and nst.value > 0:
+            _lib.call("unetca_sum_rows", parts.data_ptr() + 4 * Cl, nst.value, 4 * Cl, Cl, _ptr(dbias), st)
+        else:
+            _lib.call("unetca_chan_sum", dt, _ptr(du), ldu, Cl, B * 4 * hi * wi, _ptr(parts), _ptr(dbias), st)
         G.put(name + ".bias")
         up_in = sv.up_in[i]
         dwu = G.alloc(name + ".weight", up.weight)
