@@ -8,21 +8,27 @@ the drop-in `unetca_b200.UNet` (C ABI -> sm_100a kernels), the bucketed gradient
 torch.optim.Adam(lr=1e-4) — the reference's train step (Unet-ChannalAttention.py:338-346).  Workload at every N
 (weak scaling): BASELINE.json configs[1], U-Net-CA (use_se=True), bf16 mode, batch 64 per GPU, 3x512x512, 2 classes.
 
-One JSON line on stdout (rank 0).  `value` = images/s with the batch resident in HBM; `e2e` = the same step fed
-from pinned host memory (H2D copy of images+masks every step, prefetched on a side stream, and the loss read back
-every step); `roofline` = the tcgen05 contraction kernels' algorithmic FLOP/s, timed with CUDA events around their
-launches inside the timed region, against the measured bf16 peak; `roofline_hbm` = the same for the memory-bound
-kernels against the measured copy bandwidth; `cpu_baseline` = the oracle port of the reference (ATen CPU kernels)
-timed on this box's host cores on a bounded sample.
+One JSON line on stdout (rank 0).  `value` = images/s with the batch resident in HBM, timed with NO per-kernel
+instrumentation; `e2e` = the same step fed from pinned host memory (H2D copy of images+masks every step, prefetched
+on a side stream, and the loss read back every step); `roofline` = the dominant tcgen05 contraction kernel's
+algorithmic FLOP/s against the measured bf16 peak and `roofline_hbm` = the same for the memory-bound kernels against
+the measured copy bandwidth, both from a SEPARATE pass of the same run in which every C-ABI call is bracketed by CUDA
+events (the bracketing costs ~1 % and therefore stays out of `value`); `cpu_baseline` = the unmodified reference
+classes timed on this box's host cores on a bounded sample.  `extra` carries the other BASELINE configs on the same
+build: configs[2] (global batch 512 as 64-image micro-steps), the data-parallel gradient parity at N > 1, configs[3]
+(tiled scene inference), configs[4] (SE + max-pool sweep, plain U-Net ablation) and the cuDNN arm.
 
---impl reference: the reference's CPU implementation of the same step (oracle/unet_ca_port.py — /root/reference does
-not exist on the GPU box; the port calls the same ATen CPU kernels as the reference's modules) on all host threads,
-on a bounded sample of the workload (2 images of 3x512x512 per step).
+--impl reference: the reference's own CPU implementation of the same step — `UNet` / `nn.CrossEntropyLoss` of the
+UNMODIFIED Unet-ChannalAttention.py, which `__graft_entry__.build()` copies into the git-ignored oracle/_ref/ so that it
+travels to the GPU box (kind "reference"; the oracle port stands in only if that copy is absent, kind "port") — on all
+host threads, each step a bounded sample of the workload (2 images of 3x512x512).
 """
 from __future__ import annotations
 
 import argparse
 import contextlib
+import hashlib
+import importlib.util
 import json
 import os
 import statistics
@@ -208,91 +214,299 @@ class KernelAccount:
 
 
 # ------------------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port of the reference on host cores, bounded sample
+# CPU baseline / reference arm: the UNMODIFIED reference classes on host cores, bounded sample
 # ------------------------------------------------------------------------------------------------------------
+REF_COPY = os.path.join(ROOT, "oracle", "_ref", "Unet-ChannalAttention.py")     # placed by __graft_entry__.build()
+
+
+def load_reference_module():
+    """The reference's own module (a byte-identical copy under the git-ignored oracle/_ref/), or None."""
+    if not os.path.exists(REF_COPY):
+        return None
+    spec = importlib.util.spec_from_file_location("unet_ca_reference", REF_COPY)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)          # no import-time side effects: everything runs under main() (UCA:489)
+    return mod
+
+
 def cpu_reference_step_time(steps, warmup, size, sample_b=2):
-    from oracle import unet_ca_port as port        # test infrastructure; bench.py's baseline legs only
+    """Time the reference train step (UCA:338-346: zero_grad, model(images), criterion, backward, Adam.step, loss.item())
+    on the host.  -> (per-step seconds, images per step, kind)."""
+    from oracle import unet_ca_port as port        # fixtures (+ fallback implementation); bench.py's baseline legs only
     torch.set_num_threads(os.cpu_count() or 1)
     sd = port.make_state_dict(seed=0)
-    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
-         for k, v in sd.items()}
-    opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4)
     x, y = port.make_batch(0, sample_b, size, size)
+    ref = load_reference_module()
+    if ref is not None:
+        kind = "reference"
+        model = ref.UNet(in_channels=3, num_classes=2, use_se=True)
+        model.load_state_dict(sd)
+        model.train()
+        crit = torch.nn.CrossEntropyLoss(ignore_index=255)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+
+        def fwd():
+            return crit(model(x), y)
+    else:
+        kind = "port"
+        p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+             for k, v in sd.items()}
+        opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4)
+
+        def fwd():
+            return port.loss_fn(port.unet_forward(x, p, train=True), y)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         opt.zero_grad()
-        loss = port.loss_fn(port.unet_forward(x, p, train=True), y)
+        loss = fwd()
         loss.backward()
         opt.step()
         _ = loss.item()
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return times, sample_b
+    return times, sample_b, kind
 
 
-def run_reference_gpu(args):
-    """EXTRA, not one of the contract's arms: the reference's own module stack (oracle port = the same ATen ops) on the
-    B200 through cuDNN, channels_last + autocast(bf16) — the honest GPU competitor named in SURVEY.md 8(d)."""
+KIND_NOTE = {"reference": "unmodified UNet + nn.CrossEntropyLoss of Unet-ChannalAttention.py (oracle/_ref copy made by build())",
+             "port": "oracle/unet_ca_port.py (same ATen CPU kernels; oracle/_ref copy of the reference absent)"}
+
+
+def run_reference_gpu(batch, size, steps, warmup):
+    """EXTRA, not one of the contract's arms: the reference's own module stack on the B200 through cuDNN,
+    channels_last + autocast(bf16) + fused Adam — the honest GPU competitor named in SURVEY.md 8(d)."""
     from oracle import unet_ca_port as port        # baseline leg only
-    dev = torch.device("cuda", 0)
-    B, S = args.batch, args.size
+    dev = torch.device("cuda", torch.cuda.current_device())
+    B, S = batch, size
     sd = port.make_state_dict(seed=0)
-    p = {k: (v.to(dev).requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.to(dev))
-         for k, v in sd.items()}
-    opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4, fused=True)
+    ref = load_reference_module()
     g = torch.Generator(device=dev).manual_seed(1234)
     x = torch.randn(B, 3, S, S, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 2, (B, S, S), device=dev, generator=g)
     torch.backends.cudnn.benchmark = True
+    if ref is not None:
+        kind = "reference"
+        model = ref.UNet(in_channels=3, num_classes=2, use_se=True)
+        model.load_state_dict(sd)
+        model = model.to(dev).to(memory_format=torch.channels_last).train()
+        crit = torch.nn.CrossEntropyLoss(ignore_index=255)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+
+        def fwd():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = model(x)
+            return crit(logits.float(), y)
+    else:
+        kind = "port"
+        p = {k: (v.to(dev).requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.to(dev))
+             for k, v in sd.items()}
+        opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4, fused=True)
+
+        def fwd():
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                logits = port.unet_forward(x, p, train=True)
+            return port.loss_fn(logits.float(), y)
 
     def step():
         opt.zero_grad(set_to_none=True)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            logits = port.unet_forward(x, p, train=True)
-        loss = port.loss_fn(logits.float(), y)
+        loss = fwd()
         loss.backward()
         opt.step()
         return loss
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print(json.dumps({"impl": "reference-gpu (extra)", "metric": METRIC, "value": B * args.steps / (ms / 1e3), "unit": UNIT,
-                      "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
-                      "higher_is_better": True, "dtype": "bf16 autocast", "data": "synthetic",
-                      "config": {"workload": f"the reference's module stack (ATen ops via oracle/unet_ca_port.py) on one B200: cuDNN, "
-                                             f"channels_last, autocast(bf16), fused Adam; batch {B}, 3x{S}x{S}"},
-                      "final_loss": loss.item()}), flush=True)
+    return {"impl": "reference-gpu (extra)", "metric": METRIC, "value": B * steps / (ms / 1e3), "unit": UNIT,
+            "n_gpus": 1, "steps": steps, "warmup": max(warmup, 3), "ms_per_step": ms / steps,
+            "higher_is_better": True, "dtype": "bf16 autocast", "data": "synthetic", "kind": kind,
+            "config": {"workload": f"the reference's module stack ({KIND_NOTE[kind]}) on one B200: cuDNN, channels_last, "
+                                   f"autocast(bf16), fused Adam; batch {B}, 3x{S}x{S}"},
+            "final_loss": loss.item()}
+
+
+def config_dict(B, S, precision, world):
+    """`config` of the JSON line — the same object on both arms (the reference arm runs a bounded sample of it)."""
+    return {"workload": f"BASELINE configs[1]: U-Net-CA (use_se=True) train step fwd+CE+bwd+Adam(lr=1e-4), batch {B}/GPU, "
+                        f"3x{S}x{S}, 2 classes, {precision} mode",
+            "global_batch": B * world, "parallelism": f"dp{world}",
+            "l2": "working set (~50 GB of activations per step) >> 126 MB L2; no explicit flush"}
 
 
 def run_reference(args, rank):
+    """Contract arm: the reference's CPU implementation on this box's host cores, on OUR arm's metric / unit / config;
+    every step is a bounded sample (2 images) of that workload."""
     if rank != 0:
         return
-    times, sb = cpu_reference_step_time(args.steps, args.warmup, args.size)
+    times, sb, kind = cpu_reference_step_time(args.steps, args.warmup, args.size)
     total = sum(times)
     v = sb * len(times) / total
     cores = torch.get_num_threads()
+    sample = (f"{sb} images of 3x{args.size}x{args.size} per step (a bounded sample of the {args.batch}-image batch), fp32 "
+              f"fwd+CE+bwd+Adam, {len(times)} timed steps after {args.warmup} warm-up; {KIND_NOTE[kind]}")
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"U-Net-CA (use_se) train step fwd+CE+bwd+Adam, 3x{args.size}x{args.size}, 2 classes; "
-                               f"reference CPU path on a bounded sample of {sb} images per step"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sb} images of 3x{args.size}x{args.size} per step, fp32, {len(times)} timed steps "
-                                   f"after {args.warmup} warm-up, ATen CPU kernels via oracle/unet_ca_port.py"},
+        "config": config_dict(args.batch, args.size, args.precision, args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def csrc_hash():
+    """Identity of the kernel sources a profile was captured on (tools/ncu_step_summary.py records it)."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "insar-unet-ca_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# extras: the other BASELINE configs on the same build (each guarded: a failure is recorded, never fatal)
+# ------------------------------------------------------------------------------------------------------------
+def guarded(fn):
+    try:
+        return fn()
+    except Exception as e:                                       # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
+def extra_dp_parity(dev, rank, world):
+    """N > 1: one untimed tiny fp32 train step.  The all-reduced gradients that GradBuckets leaves in .grad against the
+    all-gathered mean of the per-rank gradients of the SAME model run without data parallelism, and whether every
+    rank ends up with bit-identical gradients."""
+    import torch.distributed as dist
+    import unetca_b200
+    from unetca_b200 import parallel
+    torch.manual_seed(4321)                                      # same init everywhere
+    m = unetca_b200.UNet(3, 2, use_se=True).to(dev).set_precision("fp32")
+    m.train()
+    g = torch.Generator(device=dev).manual_seed(99 + rank)       # a different shard per rank
+    x = torch.randn(2, 3, 64, 64, device=dev, generator=g)
+    y = torch.randint(0, 2, (2, 64, 64), device=dev, generator=g)
+    m.loss(x, y).backward()
+    local = torch.cat([p.grad.flatten() for p in m.parameters()])
+    for p in m.parameters():
+        p.grad = None
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    want = torch.stack(gathered).double().mean(0)
+    gb = parallel.GradBuckets(m)
+    # BatchNorm running statistics moved in the first forward; the forward itself (batch statistics) does not read them
+    m.loss(x, y).backward()
+    got = torch.cat([p.grad.flatten() for p in m.parameters()]).double()
+    gb.detach()
+    err = ((got - want).norm() / want.norm()).item()
+    worst = ((got - want).abs().max() / want.abs().max()).item()
+    mine = got.float()
+    all_g = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(all_g, mine)
+    same = all(torch.equal(all_g[0], t) for t in all_g)
+    return {"rel_l2_err_vs_mean_of_rank_grads": err, "max_abs_err_over_max": worst, "identical_across_ranks": bool(same),
+            "params": int(got.numel()), "what": "fp32 mode, 2 images of 3x64x64 per rank, bucketed overlapped all-reduce vs "
+                                               "all-gathered mean of the same model's per-rank gradients"}
+
+
+def extra_global_batch(model, opt, buckets, x, y, world, rank, dev, global_batch=512, steps=3):
+    """BASELINE configs[2]: global batch 512 at every N as k = 512 / (64 N) micro-steps of 64 images per GPU (the
+    BatchNorm batch stays 64), gradients accumulated locally and all-reduced on the k-th backward only."""
+    import torch.distributed as dist
+    B = x.shape[0]
+    k = max(1, global_batch // (B * world))
+    if buckets is not None:
+        buckets.set_accumulation(k)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        for _ in range(k):
+            (model.loss(x, y) / k).backward()
+        opt.step()
+
+    step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    if buckets is not None:
+        buckets.set_accumulation(1)
+    return {"value": k * B * world * steps / (ms / 1e3), "unit": UNIT, "global_batch": k * B * world, "micro_steps": k,
+            "images_per_gpu_per_micro_step": B, "optimizer_steps_timed": steps, "ms_per_optimizer_step": ms / steps,
+            "scaling": "strong", "all_reduces_per_optimizer_step": 1 if world > 1 else 0}
+
+
+def extra_ablation(dev, B, S, precision, steps=3):
+    """configs[4]'s ablation baseline: the plain U-Net (use_se=False, /root/reference/Unet.py) through the same path."""
+    import unetca_b200
+    from unetca_b200 import optim as uoptim
+    torch.manual_seed(0)
+    m = unetca_b200.UNet(3, 2, use_se=False).to(dev).set_precision(precision)
+    m.train()
+    opt = uoptim.Adam(m.parameters(), lr=1e-4, model=m)
+    g = torch.Generator(device=dev).manual_seed(77)
+    x = torch.randn(B, 3, S, S, device=dev, generator=g)
+    y = torch.randint(0, 2, (B, S, S), device=dev, generator=g)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        m.loss(x, y).backward()
+        opt.step()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "workload": f"plain U-Net (use_se=False), batch {B}, 3x{S}x{S}"}
+
+
+def extra_scene(dev, scene=4096):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import scene_bench
+    ms, ones, my_tiles, ntiles, size = scene_bench.run_scene(scene, 1024, 128, 4, "bf16", 2, dev)
+    return {"value": scene * scene / 1e6 / (ms / 1e3), "unit": "Mpx/s", "ms": ms, "tiles": ntiles, "tiles_per_sec": ntiles / (ms / 1e3),
+            "workload": f"BASELINE configs[3] on one GPU at reduced extent: {scene}x{scene} hashed scene, core 1024 + halo 128 -> "
+                        f"{size}^2 windows, 4 per forward, eval mode, bf16, second pass timed", "class1_pixels": ones}
+
+
+def extra_se_sweep():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import se_pool_sweep
+    peak, rows = se_pool_sweep.run_sweep(dtypes=("bf16",), iters=5, verbose=False)
+    out = se_pool_sweep.summarize(rows)
+    out["hbm_peak_gbs"] = peak
+    out["workload"] = ("BASELINE configs[4], bf16: C in {64..1024} x HW in {32..512}, B sized for >= 256 MB tensors; fraction of the "
+                       "measured HBM copy bandwidth at 3*N*e (+ pool) algorithmic bytes; full table: tools/se_pool_sweep.py")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -302,13 +516,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"],
-                    help="reference = the reference's CPU path (contract arm); reference-gpu = EXTRA: the same ATen ops on the "
+                    help="reference = the reference's CPU path (contract arm); reference-gpu = EXTRA: the same modules on the "
                          "GPU through cuDNN (channels_last + autocast bf16)")
     ap.add_argument("--batch", type=int, default=64, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `extra` object (configs[2..4], DP parity, cuDNN arm)")
+    ap.add_argument("--no-kernel-pass", action="store_true", help="skip the instrumented pass (no roofline objects)")
+    ap.add_argument("--kernel-steps", type=int, default=5, help="steps of the instrumented pass (CUDA events around every call)")
     ap.add_argument("--torch-adam", action="store_true",
                     help="step with torch.optim.Adam(fused=True) instead of unetca_b200.optim.Adam (A/B)")
     ap.add_argument("--graph", action="store_true",
@@ -326,7 +543,8 @@ def main():
         return
     if args.impl == "reference-gpu":
         if rank == 0:
-            run_reference_gpu(args)
+            torch.cuda.set_device(0)
+            print(json.dumps(run_reference_gpu(args.batch, args.size, args.steps, args.warmup)), flush=True)
         return
 
     import torch.distributed as dist
@@ -352,8 +570,7 @@ def main():
     torch.manual_seed(0)
     model = unetca_b200.UNet(3, 2, use_se=True).to(dev).set_precision(args.precision)
     model.train()
-    if world > 1:
-        parallel.GradBuckets(model)
+    buckets = parallel.GradBuckets(model) if world > 1 else None
     if args.torch_adam:
         opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
     else:
@@ -401,16 +618,13 @@ def main():
                           "clocks": clk, "final_loss": loss.item()}), flush=True)
         return
 
-    acct = KernelAccount(2 if args.precision == "bf16" else 4, 3)
-    _lib.set_hook(acct)
     for _ in range(args.warmup):
         step(x, y)
-    # ---- timed region 1: batch resident in HBM ------------------------------------------------------------
+    # ---- timed region 1: batch resident in HBM; NO per-kernel instrumentation ---------------------------------
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
         clocks.start()
-    acct.enabled = True
     n0 = _lib.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -418,7 +632,6 @@ def main():
         loss = step(x, y)
     e1.record()
     barrier()
-    acct.enabled = False
     launches = _lib.launch_count - n0
     clk = clocks.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
@@ -427,6 +640,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     value = world * B * args.steps / (ms / 1e3)
+    ms_step = ms / args.steps
     final_loss = loss.item()
 
     # ---- timed region 2: end to end from pinned host memory ------------------------------------------------
@@ -469,80 +683,124 @@ def main():
             dt_e2e = t.item()
         e2e = {"value": world * B * args.steps / dt_e2e, "unit": UNIT,
                "h2d_bytes_per_step": int(hx[0].numel() * 4 + hy[0].numel() * 8), "d2h_bytes_per_step": 4}
+        del hx, hy, dx, dy
 
-    _lib.set_hook(None)
-    # ---- rooflines -------------------------------------------------------------------------------------------
+    # ---- instrumented pass (same run, same tensors): CUDA events around every C-ABI call -----------------------
+    roof = roof_all = roof_h = None
     pk = peaks()
-    table = acct.summary()
-    # DRAM traffic per launch (dram__bytes_read + dram__bytes_write) from the committed ncu capture of this command
-    traffic = {}
-    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp) and B == 64 and S == 512 and args.precision == "bf16":
-        traffic = json.load(open(tp))
-    tms = sum(d["ms"] for d in table.values() if d["class"] == "tensor")
-    tfl = sum(d["flops"] for d in table.values() if d["class"] == "tensor")
-    hms = sum(d["ms"] for d in table.values() if d["class"] == "hbm")
-    hby = sum(d["bytes"] for d in table.values() if d["class"] == "hbm")
-    ncalls_t = sum(d["calls"] for d in table.values() if d["class"] == "tensor")
-    ncalls_h = sum(d["calls"] for d in table.values() if d["class"] == "hbm")
-    ach_t = tfl / (tms * 1e-3) / 1e12 if tms else 0.0
-    ach_h = hby / (hms * 1e-3) / 1e9 if hms else 0.0
-    def one(name):
-        d = table.get(name)
-        if not d or not d["ms"]:
-            return None
-        return d
+    if not args.no_kernel_pass:
+        acct = KernelAccount(2 if args.precision == "bf16" else 4, 3)
+        _lib.set_hook(acct)
+        acct.enabled = True
+        barrier()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(args.kernel_steps):
+            step(x, y)
+        k1.record()
+        barrier()
+        acct.enabled = False
+        _lib.set_hook(None)
+        ms_kstep = k0.elapsed_time(k1) / args.kernel_steps
+        table = acct.summary()
+        nk = args.kernel_steps
+        # DRAM traffic per launch (dram__bytes_read + dram__bytes_write) from the committed ncu capture of this command —
+        # only if it was taken on the kernel sources that are running now
+        traffic, traffic_note = {}, None
+        tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tp) and B == 64 and S == 512 and args.precision == "bf16":
+            tj = json.load(open(tp))
+            if tj.get("csrc_sha") == csrc_hash():
+                traffic = tj
+                traffic_note = tj.get("source")
+            else:
+                traffic_note = (f"profiles/ncu_traffic.json was captured on kernel sources {tj.get('csrc_sha')}, this build is "
+                                f"{csrc_hash()}: traffic withheld (re-run the ncu pass of tools/ncu_step_summary.py)")
+        tms = sum(d["ms"] for d in table.values() if d["class"] == "tensor")
+        tfl = sum(d["flops"] for d in table.values() if d["class"] == "tensor")
+        hms = sum(d["ms"] for d in table.values() if d["class"] == "hbm")
+        hby = sum(d["bytes"] for d in table.values() if d["class"] == "hbm")
+        ncalls_t = sum(d["calls"] for d in table.values() if d["class"] == "tensor")
+        ncalls_h = sum(d["calls"] for d in table.values() if d["class"] == "hbm")
+        ach_t = tfl / (tms * 1e-3) / 1e12 if tms else 0.0
+        ach_h = hby / (hms * 1e-3) / 1e9 if hms else 0.0
 
-    # dominant kernel of the step: the haloed pixels-on-N conv kernel behind unetca_conv3x3_fwd (forward + dgrad of every
-    # layer with O % 128 == 0); the aggregate over all contraction kernels is kept beside it
-    dom = one("unetca_conv3x3_fwd")
-    if dom:
-        ach_d = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach_d, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach_d / pk["tflops_sustained"], "frac_of_burst_peak": ach_d / pk["tflops_burst"],
-                "traffic": traffic.get("dominant", {}).get("dram_bytes_per_launch"),
-                "kernel": "tc_conv3x3_hpix_kernel (tcgen05 haloed pixels-on-N conv3x3 forward/dgrad, entry unetca_conv3x3_fwd)",
-                "launches": dom["calls"], "avg_launch_ms": dom["ms"] / dom["calls"], "share_of_step": dom["ms"] / ms,
-                "flops_per_launch_avg": dom["flops"] / dom["calls"], "peak_source": pk["source"] + " bf16_tflops_sustained",
-                "algorithmic_note": "2*B*H*W*9*C*O per launch (true shapes); `peak` is the measured SUSTAINED cuBLAS bf16 rate "
-                                    "of MEASURED_PEAKS.json (a frac near or above 1 means this kernel holds what cuBLAS holds "
-                                    "under the same power cap; frac_of_burst_peak uses the burst figure); ncu --set full: "
-                                    "profiles/r1l_ncu_full_hpix_512to512_at64.txt (tensor pipe 87 % active)"}
-    else:
-        roof = None
-    roof_all = {"bound": "tensor", "achieved": ach_t, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
-                "frac": ach_t / pk["tflops_sustained"], "traffic": traffic.get("tensor", {}).get("dram_bytes_per_launch"),
-                "kernel": "all tcgen05 contraction kernels (conv3x3 fwd/dgrad/wgrad, ConvTranspose, first conv), aggregate",
-                "launches": ncalls_t, "avg_launch_ms": tms / max(ncalls_t, 1), "share_of_step": tms / ms,
-                "flops_per_launch_avg": tfl / max(ncalls_t, 1), "peak_source": pk["source"] + " bf16_tflops_sustained"}
-    if roof is None:
-        roof = roof_all
-    domh = one("unetca_bn_bwd_apply")
-    roof_h = {"bound": "hbm", "achieved": ach_h, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_h / pk["hbm_gbs"],
-              "traffic": traffic.get("hbm", {}).get("dram_bytes_per_launch"),
-              "algorithmic_bytes_per_launch": hby / max(ncalls_h, 1),
-              "kernel": "BN/ReLU/SE/max-pool/outc/CE elementwise and reduction kernels (aggregate)",
-              "launches": ncalls_h, "share_of_step": hms / ms, "peak_source": pk["source"] + " hbm_gbs"}
-    if domh:
-        ach = domh["bytes"] / (domh["ms"] * 1e-3) / 1e9
-        roof_h["dominant"] = {"kernel": "bn_bwd_apply_stream_kernel (entry unetca_bn_bwd_apply: ReLU+BN backward as a cp.async.bulk shared-memory stream, 3*N*e bytes)",
-                              "achieved": ach, "frac": ach / pk["hbm_gbs"], "launches": domh["calls"],
-                              "avg_launch_ms": domh["ms"] / domh["calls"], "share_of_step": domh["ms"] / ms,
-                              "algorithmic_bytes_per_launch": domh["bytes"] / domh["calls"],
-                              "traffic": traffic.get("dominant_hbm", {}).get("dram_bytes_per_launch")}
-    if args.kernel_table and rank == 0:
-        with open(args.kernel_table, "w") as f:
-            json.dump({k: {**v, "ms_per_step": v["ms"] / args.steps} for k, v in table.items()}, f, indent=1)
+        def one(name):
+            d = table.get(name)
+            return d if d and d["ms"] else None
+
+        how = (f"separate instrumented pass of the same run: {nk} steps with CUDA events around every C-ABI call "
+               f"({ms_kstep:.2f} ms/step instrumented vs {ms_step:.2f} in the headline region)")
+        # dominant kernel of the step: the haloed pixels-on-N conv kernel behind unetca_conv3x3_fwd (forward + dgrad of every
+        # layer with O % 128 == 0); the aggregate over all contraction kernels is kept beside it
+        dom = one("unetca_conv3x3_fwd")
+        roof_all = {"bound": "tensor", "achieved": ach_t, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach_t / pk["tflops_sustained"], "traffic": traffic.get("tensor", {}).get("dram_bytes_per_launch"),
+                    "kernel": "all tcgen05 contraction kernels (conv3x3 fwd/dgrad/wgrad, ConvTranspose, first conv), aggregate",
+                    "launches": ncalls_t, "avg_launch_ms": tms / max(ncalls_t, 1), "share_of_step": tms / nk / ms_kstep,
+                    "flops_per_launch_avg": tfl / max(ncalls_t, 1), "peak_source": pk["source"] + " bf16_tflops_sustained"}
+        if dom:
+            ach_d = dom["flops"] / (dom["ms"] * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach_d, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach_d / pk["tflops_sustained"], "frac_of_burst_peak": ach_d / pk["tflops_burst"],
+                    "traffic": traffic.get("dominant", {}).get("dram_bytes_per_launch"), "traffic_source": traffic_note,
+                    "kernel": "tc_conv3x3_hpix_kernel (tcgen05 haloed pixels-on-N conv3x3 forward/dgrad, entry unetca_conv3x3_fwd)",
+                    "launches": dom["calls"], "avg_launch_ms": dom["ms"] / dom["calls"], "share_of_step": dom["ms"] / nk / ms_kstep,
+                    "flops_per_launch_avg": dom["flops"] / dom["calls"], "peak_source": pk["source"] + " bf16_tflops_sustained",
+                    "measured": how,
+                    "algorithmic_note": "2*B*H*W*9*C*O per launch (true shapes); `peak` is the measured SUSTAINED cuBLAS bf16 rate "
+                                        "of MEASURED_PEAKS.json (a frac near or above 1 means this kernel holds what cuBLAS holds "
+                                        "under the same power cap; frac_of_burst_peak uses the burst figure)"}
+        else:
+            roof = roof_all
+        domh = one("unetca_bn_bwd_apply")
+        roof_h = {"bound": "hbm", "achieved": ach_h, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_h / pk["hbm_gbs"],
+                  "traffic": traffic.get("hbm", {}).get("dram_bytes_per_launch"),
+                  "algorithmic_bytes_per_launch": hby / max(ncalls_h, 1),
+                  "kernel": "BN/ReLU/SE/max-pool/outc/CE elementwise and reduction kernels (aggregate)",
+                  "launches": ncalls_h, "share_of_step": hms / nk / ms_kstep, "peak_source": pk["source"] + " hbm_gbs"}
+        if domh:
+            ach = domh["bytes"] / (domh["ms"] * 1e-3) / 1e9
+            roof_h["dominant"] = {"kernel": "bn_bwd_apply_stream_kernel (entry unetca_bn_bwd_apply: ReLU+BN backward as a cp.async.bulk shared-memory stream, 3*N*e bytes)",
+                                  "achieved": ach, "frac": ach / pk["hbm_gbs"], "launches": domh["calls"],
+                                  "avg_launch_ms": domh["ms"] / domh["calls"], "share_of_step": domh["ms"] / nk / ms_kstep,
+                                  "algorithmic_bytes_per_launch": domh["bytes"] / domh["calls"],
+                                  "traffic": traffic.get("dominant_hbm", {}).get("dram_bytes_per_launch")}
+        if args.kernel_table and rank == 0:
+            with open(args.kernel_table, "w") as f:
+                json.dump({k: {**v, "ms_per_step": v["ms"] / nk} for k, v in table.items()}, f, indent=1)
+
+    # ---- extras: the other BASELINE configs on this build ------------------------------------------------------
+    extra = None
+    if not args.no_extras:
+        extra = {}
+        extra["global_batch_512"] = guarded(lambda: extra_global_batch(model, opt, buckets, x, y, world, rank, dev))
+        if world > 1:
+            if buckets is not None:
+                buckets.detach()
+            extra["dp_parity"] = guarded(lambda: extra_dp_parity(dev, rank, world))
+    del model, opt, buckets
+    torch.cuda.empty_cache()
+    if extra is not None and world == 1:
+        extra["ablation_plain_unet"] = guarded(lambda: extra_ablation(dev, B, S, args.precision))
+        torch.cuda.empty_cache()
+        extra["scene_inference"] = guarded(lambda: extra_scene(dev))
+        torch.cuda.empty_cache()
+        extra["se_pool_sweep"] = guarded(extra_se_sweep)
+        torch.cuda.empty_cache()
+        del x, y
+        extra["cudnn_arm"] = guarded(lambda: run_reference_gpu(B, S, 5, 3))
+        torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        times, sb = cpu_reference_step_time(2, 1, S)
+        times, sb, kind = cpu_reference_step_time(5, 2, S)
         v = sb * len(times) / sum(times)
         # BASELINE.json configs[0] exactly: batch 4, 3x256x256, fp32, best of 3 after 1 warm-up
-        t0, _ = cpu_reference_step_time(3, 1, 256, sample_b=4)
-        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"{sb} images of 3x{S}x{S} per step (of the {B}-image batch), fp32 fwd+CE+bwd+Adam, 2 timed steps "
-                         f"after 1 warm-up, ATen CPU kernels via oracle/unet_ca_port.py",
+        t0, _, _ = cpu_reference_step_time(3, 1, 256, sample_b=4)
+        cpu = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+               "sample": f"{sb} images of 3x{S}x{S} per step (of the {B}-image batch), fp32 fwd+CE+bwd+Adam, {len(times)} timed "
+                         f"steps after 2 warm-up; {KIND_NOTE[kind]}",
                "configs0": {"value": 4 / min(t0), "unit": UNIT,
                             "sample": "BASELINE configs[0]: batch 4, 3x256x256, fp32 fwd+CE+bwd+Adam, best of 3 after 1 warm-up"}}
 
@@ -550,15 +808,12 @@ def main():
         gflop_img = TRAIN_GFLOP_PER_IMG_512 * (S * S) / (512 * 512)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.precision, "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]: U-Net-CA (use_se=True) train step fwd+CE+bwd+Adam(lr=1e-4), "
-                                   f"batch {B}/GPU, 3x{S}x{S}, 2 classes, {args.precision} mode",
-                       "global_batch": B * world, "parallelism": f"dp{world}",
-                       "l2": "working set (~50 GB of activations per step) >> 126 MB L2; no explicit flush"},
+            "config": config_dict(B, S, args.precision, world),
             "tensor_util_step": value / world * gflop_img * 1e9 / (pk["tflops_sustained"] * 1e12),
-            "roofline": roof, "roofline_tensor_all": roof_all, "roofline_hbm": roof_h, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
-            "clocks": clk, "final_loss": final_loss,
+            "roofline": roof, "roofline_tensor_all": roof_all, "roofline_hbm": roof_h, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches, "clocks": clk, "final_loss": final_loss, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -6,8 +6,10 @@
  *
  * Rules for every function:
  *   - plain pointers and sizes only; every pointer is a CUDA *device* pointer unless stated otherwise;
- *   - the caller owns all memory (tensors, scratch); the library allocates nothing and keeps no state
- *     besides the implementation switch below;
+ *   - the caller owns all memory (tensors, scratch); the library allocates nothing.  Its only state is
+ *     process-global and read-only on the data path: cached device properties (SM count, kernel attributes), the
+ *     implementation switch below, and the development knobs of unetca_b200_tuning.h (A/B sweeps and cross-checks
+ *     only — not part of the drop-in ABI, not re-entrant; the product path never calls them);
  *   - stream-ordered on `stream` (a cudaStream_t), no host synchronisation, no exceptions;
  *   - returns 0 (or a documented non-negative count) on success, <0 on error; unetca_last_error() returns the
  *     thread-local message.  There is no CPU fallback: without a CUDA device every op fails.
@@ -39,13 +41,6 @@ int unetca_max_parts(int B);
 /* 0 (default): bf16 -> tcgen05 kernels, fp32 -> FFMA kernels; 1: FFMA kernels for both (cross-check only) */
 void unetca_set_conv_impl(int impl);
 int unetca_get_conv_impl(void);
-void unetca_tc_force_block_n(int n);
-void unetca_tc_force_wgrad_narrow(int on);
-void unetca_tc_force_no_halo(int on);
-void unetca_tc_set_convT_wide(int on);
-void unetca_tc_force_no_pixn(int on);
-void unetca_tc_set_pixn_cluster(int n);
-void unetca_tc_force_no_kw(int on);
 
 /* ---- module boundary: layout and parameter packing ------------------------------------------------------ */
 /* network input (B,Cin,H,W) NCHW fp32 (UCA:343 `model(images)`) -> im2col rows [B*H*W][Kpad], k = tap*Cin + c */
@@ -114,6 +109,12 @@ int unetca_bn_bwd_apply(int dtype, const void* dout, int ldd, const void* y, int
 /* ---- SELayer, UCA:45-72, and MaxPool2d(2), UCA:106-109 ----------------------------------------------------- */
 /* p = mean_hw, z = relu(W1 p), s = sigmoid(W2 z) from the squeeze partial sums */
 int unetca_se_fc(const float* pool_parts, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2, float* p, float* z, float* s, void* stream);
+/* SELayer.forward called on its own (UCA:61-72; NCHW fp32, any sign): plane-wise passes around unetca_se_fc /
+ * unetca_se_fc_bwd.  plane_dot: out[plane] = sum a * (b ? b : 1) over the hw contiguous floats of each (b,c) plane (the
+ * squeeze, and ds = sum dy * x); plane_scale_add: out = x * s[plane] + (t ? t[plane] * tscale : 0) (y = x * s, and
+ * dx = dy * s + dp / HW) */
+int unetca_plane_dot(const float* a, const float* b, long nplanes, long hw, float* out, void* stream);
+int unetca_plane_scale_add(const float* x, const float* s, const float* t, float tscale, long nplanes, long hw, float* out, void* stream);
 /* out = relu(scale*y+shift) * s[b,c] (s null: no SE); pooled/pos non-null: fused 2x2 max-pool of out with
  * torch's first-max / NaN rule, pos = 1-byte window position dh*2+dw */
 int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, void* pooled, int ldp, uint8_t* pos, int B, int H, int W, int C, const float* scale, const float* shift, const float* s, void* stream);
@@ -142,9 +143,6 @@ int unetca_chan_sum(int dtype, const void* x, int ld, int C, long npix, float* p
 /* out[i] = sum over nrows rows of parts[row*row_stride + i] (i < n): second stage for per-CTA channel sums, e.g. the
  * ConvTranspose2d bias gradient (UCA:114) taken from the statistics epilogue of the convolution that writes dcat */
 int unetca_sum_rows(const float* parts, int nrows, long row_stride, int n, float* out, void* stream);
-/* tuning knobs for sweeps: key 0 = pixels per thread-row of an elementwise block, 1 = waves of a reduction grid,
- * 2 = quads per thread-row of se_scale_pool */
-void unetca_set_tuning(int key, int value);
 
 /* ---- outc 1x1 conv -> class logits (UCA:125,162), CrossEntropyLoss(ignore_index) (UCA:465,344), argmax (UCA:220) */
 int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, const float* bias, int nc, float* logits, int B, long HW, void* stream);

@@ -13,6 +13,7 @@ import re
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 HEADER = os.path.join(ROOT, "include", "unetca_b200.h")
+TUNING_HEADER = os.path.join(ROOT, "include", "unetca_b200_tuning.h")      # development knobs, not the drop-in ABI
 LIB_PATH = os.path.join(_HERE, "libunetca_b200.so")
 
 F32, BF16 = 0, 1
@@ -62,7 +63,9 @@ def load():
             f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()'). "
             "unetca_b200 has no CPU or PyTorch fallback.")
     lib = ctypes.CDLL(LIB_PATH)
-    for name, (restype, argtypes) in parse_header().items():
+    decls = parse_header()
+    decls.update(parse_header(TUNING_HEADER))
+    for name, (restype, argtypes) in decls.items():
         try:
             fn = getattr(lib, name)
         except AttributeError as e:

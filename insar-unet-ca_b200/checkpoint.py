@@ -38,10 +38,19 @@ def save_resume(path: str, model: torch.nn.Module, optimizer: torch.optim.Optimi
 
 
 def load_resume(path: str, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer] = None,
-                map_location=None) -> Tuple[int, float, List[Dict[str, Any]]]:
+                map_location=None, trust_pickle: bool = False) -> Tuple[int, float, List[Dict[str, Any]]]:
     """Restore a `save_resume` file (or a bare reference state_dict: model only).  Returns (completed epochs,
-    best mIoU so far, history) — resume the loop at `range(epoch, num_epochs)` with `best_m_iou` as in UCA:326."""
-    obj = torch.load(path, map_location=map_location, weights_only=False)
+    best mIoU so far, history) — resume the loop at `range(epoch, num_epochs)` with `best_m_iou` as in UCA:326.
+
+    Files are read with torch's safe unpickler (`weights_only=True`): everything `save_resume` writes is tensors and
+    plain Python types.  Only `trust_pickle=True` falls back to full pickle (arbitrary code execution — for files whose
+    history holds custom objects and whose origin is trusted)."""
+    try:
+        obj = torch.load(path, map_location=map_location, weights_only=True)
+    except Exception:
+        if not trust_pickle:
+            raise
+        obj = torch.load(path, map_location=map_location, weights_only=False)
     if isinstance(obj, dict) and obj.get("format") == FORMAT:
         model.load_state_dict(obj["model"])
         if optimizer is not None:

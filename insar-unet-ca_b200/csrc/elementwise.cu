@@ -2253,6 +2253,36 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int nsplit, lo
     dw[i] = t;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Standalone SELayer (UCA:61-72 called on its own, NCHW fp32, inputs of any sign): the two plane-wise passes around
+// unetca_se_fc / unetca_se_fc_bwd.  One block per (b, c) plane of hw contiguous floats.
+//   plane_dot:        out[plane] = sum_i a[i] * (b ? b[i] : 1)          squeeze (b null) and ds = sum dy * x
+//   plane_scale_add:  out[i] = x[i] * s[plane] + (t ? t[plane] * tscale : 0)     y = x * s;  dx = dy * s + dp / HW
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) plane_dot_kernel(const float* __restrict__ a, const float* __restrict__ b, long hw,
+                                                        float* __restrict__ out) {
+    const float* pa = a + (long)blockIdx.x * hw;
+    const float* pb = b ? b + (long)blockIdx.x * hw : nullptr;
+    float acc = 0.f;
+    for (long i = threadIdx.x; i < hw; i += 256) acc = pb ? fmaf(pa[i], pb[i], acc) : acc + pa[i];
+    __shared__ float red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        out[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(256) plane_scale_add_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                                              const float* __restrict__ t, float tscale, long hw,
+                                                              float* __restrict__ out) {
+    const long base = (long)blockIdx.x * hw;
+    const float sv = s[blockIdx.x], tv = t ? t[blockIdx.x] * tscale : 0.f;
+    for (long i = threadIdx.x; i < hw; i += 256) out[base + i] = fmaf(x[base + i], sv, tv);
+}
+
 }  // namespace unetca
 
 // =========================================================================================================
@@ -2351,6 +2381,18 @@ int unetca_bn_relu(int dtype, const void* y, int ldy, void* out, int ldo, int B,
         if (nparts) *nparts = grid.x;
     });
     return check_launch("bn_relu");
+}
+
+int unetca_plane_dot(const float* a, const float* b, long nplanes, long hw, float* out, void* stream) {
+    UNETCA_REQUIRE(a && out && nplanes > 0 && hw > 0, "plane_dot: bad arguments");
+    plane_dot_kernel<<<(unsigned)nplanes, 256, 0, (cudaStream_t)stream>>>(a, b, hw, out);
+    return check_launch("plane_dot");
+}
+int unetca_plane_scale_add(const float* x, const float* s, const float* t, float tscale, long nplanes, long hw, float* out,
+                           void* stream) {
+    UNETCA_REQUIRE(x && s && out && nplanes > 0 && hw > 0, "plane_scale_add: bad arguments");
+    plane_scale_add_kernel<<<(unsigned)nplanes, 256, 0, (cudaStream_t)stream>>>(x, s, t, tscale, hw, out);
+    return check_launch("plane_scale_add");
 }
 
 int unetca_se_fc(const float* pool_parts, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,

@@ -10,7 +10,8 @@ buffers and the gradients all live at fixed addresses inside the graph's private
     for images, masks in loader:
         loss = step(images, masks)                                # copies into the static inputs, replays the graph
 
-Same kernels in the same order as the eager step, hence bit-identical results (tests/test_gpu_model.py).  Single GPU
+Same kernels in the same order as the eager step, hence bit-identical results (tests/test_gpu_model.py), also when
+eval-mode forwards (validation) are interleaved with replays.  Single GPU
 only: the data-parallel bucket all-reduce is not captured.  If eager steps ran before, drop every reference to their
 losses / outputs first (`loss = None`): autograd keeps the parameters' AccumulateGrad nodes bound to the stream they
 were created on while an old graph is alive, and a capture that touches them is invalidated.
@@ -39,6 +40,11 @@ class GraphedTrainStep:
         optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(self.graph):
             self.loss = self._eager(zero=False)
+        # The captured kernels read and write the model's packed operand copies and scratch buffers by address.  The engine
+        # rewrites those buffers in place (it never reallocates them while the parameters stay where they are); holding
+        # them here as well keeps the memory alive even if the engine's caches are dropped.
+        eng = model._engine()
+        self._pinned = [list(eng._packed.values()), list(eng._scratch.values())]
 
     def _eager(self, zero=True):
         if zero:
@@ -52,4 +58,9 @@ class GraphedTrainStep:
         self.images.copy_(images, non_blocking=True)
         self.masks.copy_(masks, non_blocking=True)
         self.graph.replay()
+        # A replay steps the parameters without running any Python: neither Tensor._version nor the engine's own step
+        # marker moves.  Tell the engine a train step happened, so the next eval-mode forward (the reference's per-epoch
+        # validate_model, UCA:273-287) re-derives the packed filters from the stepped parameters instead of reusing the
+        # ones of the previous validation.
+        self.model._engine().last_train = True
         return self.loss

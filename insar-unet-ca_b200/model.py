@@ -8,6 +8,10 @@ the C ABI in include/unetca_b200.h (NHWC activations; tcgen05 implicit-GEMM conv
 parity mode), driven by one `torch.autograd.Function`.  PyTorch only owns memory and the stream.
 
 There is no CPU path and no ATen fallback: CPU tensors, a missing shared library or an unsupported shape raise.
+`DoubleConv` and `SELayer` are also usable on their own, like the reference's (UCA:61-72, 96-97): their `forward`
+runs the same kernels behind a small autograd Function each.  The whole autograd surface of the reference is kept:
+gradients w.r.t. the parameters and, when `images.requires_grad`, w.r.t. the input; backward also works under
+`model.eval()` (running-statistics BatchNorm).
 
 Extra, beyond the reference API:
   * `model.precision` / `model.set_precision('bf16' | 'fp32')` — storage type of activations and contraction
@@ -44,8 +48,18 @@ class SELayer(nn.Module):
         )
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        raise RuntimeError("unetca_b200.SELayer is a parameter container of UNet; its arithmetic runs fused inside "
-                           "UNet.forward (kernels unetca_bn_relu / unetca_se_fc / unetca_se_scale_pool)")
+        """x * sigmoid(W2 relu(W1 mean_hw(x))) for an NCHW tensor of any sign (UCA:61-72).  Inside UNet the layer runs
+        fused with its neighbours instead (unetca_se_squeeze / unetca_se_fc3 / unetca_se_scale_pool)."""
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise ValueError("SELayer expects a 4-D (B, C, H, W) tensor")
+        if not x.is_cuda:
+            raise RuntimeError("unetca_b200.SELayer runs only on CUDA tensors (sm_100a); there is no CPU fallback")
+        w1, w2 = self.fc[0].weight, self.fc[2].weight
+        if x.shape[1] != w1.shape[1]:
+            raise RuntimeError(f"expected input with {w1.shape[1]} channels, got {x.shape[1]}")
+        with torch.cuda.device(x.device):
+            out = _SELayerFn.apply(x, w1, w2)
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
 
 
 class DoubleConv(nn.Module):
@@ -65,9 +79,43 @@ class DoubleConv(nn.Module):
             layers.append(SELayer(out_channels))
         self.double_conv = nn.Sequential(*layers)
 
+        object.__setattr__(self, "precision", "bf16")
+        object.__setattr__(self, "_eng", None)
+        object.__setattr__(self, "_blk", None)
+
+    def set_precision(self, precision: str) -> "DoubleConv":
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        object.__setattr__(self, "precision", precision)
+        return self
+
+    def _dt(self):
+        return (_lib.BF16, torch.bfloat16) if self.precision == "bf16" else (_lib.F32, torch.float32)
+
+    def _engine(self):
+        if self._eng is None:
+            object.__setattr__(self, "_eng", _Engine(self))
+            conv1 = self.double_conv[0]
+            object.__setattr__(self, "_blk", _Block("double_conv", self, conv1.in_channels, conv1.out_channels, 0,
+                                                    first=conv1.in_channels <= 5))
+        return self._eng
+
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        raise RuntimeError("unetca_b200.DoubleConv is a parameter container of UNet; its arithmetic runs inside "
-                           "UNet.forward")
+        """The block on its own (UCA:96-97): NCHW in, NCHW out, train()/eval() BatchNorm semantics, differentiable
+        w.r.t. the parameters and the input.  In bf16 mode the input channels must be <= 5 or a multiple of 64 (the
+        shapes UNet uses); 'fp32' mode (FFMA) takes any channel count that is <= 5 or a multiple of 4."""
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise ValueError("DoubleConv expects a 4-D (B, C, H, W) tensor")
+        if not x.is_cuda:
+            raise RuntimeError("unetca_b200.DoubleConv runs only on CUDA tensors (sm_100a); there is no CPU fallback")
+        conv1 = self.double_conv[0]
+        if x.shape[1] != conv1.in_channels:
+            raise RuntimeError(f"expected input with {conv1.in_channels} channels, got {x.shape[1]}")
+        self._engine()
+        keep = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+        with torch.cuda.device(x.device):
+            out = _DoubleConvFn.apply(self, x, keep, *[p for _, p in self.named_parameters()])
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
 
 
 def _ptr(t):
@@ -134,9 +182,17 @@ class _Engine:
         ent = self._packed.get(key)
         ver = (param._version, param.data_ptr(), tdt, self.epoch)
         if ent is None or ent[0] != ver:
-            ent = (ver, build())
+            # same storage type as before: rebuild INTO the existing buffers, so their addresses never change (a CUDA
+            # graph of the train step and an optimizer that writes the packed filters keep pointing at live memory)
+            old = ent[1] if ent is not None and ent[0][2] == tdt and ent[0][1] == param.data_ptr() else None
+            ent = (ver, build(old))
             self._packed[key] = ent
         return ent[1]
+
+    def invalidate(self):
+        """Forget that the packed operand copies are current (the next forward rebuilds them in place).  For writes
+        that bypass the version counter: `p.data.copy_()`, raw-pointer optimizers, dist.broadcast(t.data)."""
+        self.epoch += 1
 
     def _derive(self, w, dt, tdt, first, wf, wd, ldk, wfp=None, wdp=None):
         """The layouts derived from the base packed filters wf / wd (allocated on first use, then rewritten in place):
@@ -173,14 +229,31 @@ class _Engine:
         w = conv.weight
         O, C = w.shape[0], w.shape[1]
 
-        def build():
+        def build(old):
             ldk = ((9 * C + 63) // 64) * 64 if first else 9 * C
-            wf = torch.empty(O, ldk, dtype=tdt, device=w.device)
-            wd = None if first else torch.empty(C, 9 * O, dtype=tdt, device=w.device)
+            if old is not None:
+                wf, wd, _, wfp, wdp = old
+            else:
+                wf = torch.empty(O, ldk, dtype=tdt, device=w.device)
+                wd = None if first else torch.empty(C, 9 * O, dtype=tdt, device=w.device)
+                wfp = wdp = None
             _lib.call("unetca_pack_conv3x3_weight", dt, _ptr(w), _ptr(wf), ldk, _ptr(wd), O, C, _stream())
-            wfp, wdp = self._derive(w, dt, tdt, first, wf, wd, ldk)
+            wfp, wdp = self._derive(w, dt, tdt, first, wf, wd, ldk, wfp, wdp)
             return wf, wd, ldk, wfp, wdp
         return self._cached(("c", id(conv)), w, tdt, build)
+
+    def conv_w_first_dgrad(self, conv: nn.Conv2d, dt, tdt):
+        """dgrad operand [Cin][9*O] of the first conv — only needed for the gradient w.r.t. the input image."""
+        w = conv.weight
+        O, C = w.shape[0], w.shape[1]
+
+        def build(old):
+            ldk = ((9 * C + 63) // 64) * 64
+            wf, wd = old if old is not None else (torch.empty(O, ldk, dtype=tdt, device=w.device),
+                                                  torch.empty(C, 9 * O, dtype=tdt, device=w.device))
+            _lib.call("unetca_pack_conv3x3_weight", dt, _ptr(w), _ptr(wf), ldk, _ptr(wd), O, C, _stream())
+            return wf, wd
+        return self._cached(("cd", id(conv)), w, tdt, build)[1]
 
     def conv_w_adopt(self, conv: nn.Conv2d, dt, tdt):
         """For an optimizer that has just written the stepped weights into this layer's base packed filters
@@ -196,9 +269,9 @@ class _Engine:
         w = up.weight
         Cin, Cout = w.shape[0], w.shape[1]
 
-        def build():
-            wf = torch.empty(4 * Cout, Cin, dtype=tdt, device=w.device)
-            wd = torch.empty(Cin, 4 * Cout, dtype=tdt, device=w.device)
+        def build(old):
+            wf, wd = old if old is not None else (torch.empty(4 * Cout, Cin, dtype=tdt, device=w.device),
+                                                  torch.empty(Cin, 4 * Cout, dtype=tdt, device=w.device))
             _lib.call("unetca_pack_convT_weight", dt, _ptr(w), _ptr(wf), _ptr(wd), Cin, Cout, _stream())
             return wf, wd
         return self._cached(("t", id(up)), w, tdt, build)
@@ -255,8 +328,6 @@ def _check_input(model, x):
         # four MaxPool2d(2) need at least 16 pixels per side; torch raises from max_pool2d in the reference
         raise RuntimeError(f"input {H}x{W} is too small: four 2x2 max-pools need H, W >= 16 "
                            "(Unet-ChannalAttention.py:106-109)")
-    if x.requires_grad:
-        raise NotImplementedError("gradient w.r.t. the input image is not implemented (the reference never needs it)")
 
 
 # =======================================================================================================
@@ -270,21 +341,31 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
     npix = B * Hl * Wl
     parts = eng.parts(B, dev)
     nparts = ctypes.c_int(0)
-    sv = SimpleNamespace(blk=blk, xin=xin if keep else None, col=col if keep else None, B=B, H=Hl, W=Wl)
+    sv = SimpleNamespace(blk=blk, xin=xin if keep else None, col=col if keep else None, B=B, H=Hl, W=Wl, train=train)
 
     def bn_params(bn, conv, tag):
         mean = torch.empty(O, dtype=torch.float32, device=dev)
         invstd = torch.empty_like(mean)
         scale = torch.empty_like(mean)
         shift = torch.empty_like(mean)
+        if bn.running_mean is None or bn.running_var is None:
+            raise NotImplementedError("BatchNorm2d(track_running_stats=False) is not supported by the CUDA path "
+                                      "(the reference uses the default, UCA:82,85)")
         if train:
+            # momentum=None is torch's cumulative moving average: factor 1 / (batches seen so far, this one included)
+            mom = float(bn.momentum) if bn.momentum is not None else 1.0 / (int(bn.num_batches_tracked) + 1)
             _lib.call("unetca_bn_finalize_train", _ptr(parts), nparts.value, O, npix, _ptr(conv.bias), _ptr(bn.weight),
-                      _ptr(bn.bias), _ptr(bn.running_mean), _ptr(bn.running_var), float(bn.momentum), float(bn.eps),
+                      _ptr(bn.bias), _ptr(bn.running_mean), _ptr(bn.running_var), mom, float(bn.eps),
                       _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), st)
             bn.num_batches_tracked += 1
         else:
             _lib.call("unetca_bn_fold_eval", O, _ptr(conv.bias), _ptr(bn.weight), _ptr(bn.bias), _ptr(bn.running_mean),
                       _ptr(bn.running_var), float(bn.eps), _ptr(scale), _ptr(shift), st)
+            if keep:
+                # backward under eval(): BatchNorm is the fixed affine of its running statistics.  The stored conv
+                # output carries no bias, so "mean" is running_mean - bias (two O-element host-side formulas)
+                torch.rsqrt(bn.running_var.detach().float() + float(bn.eps), out=invstd)
+                torch.sub(bn.running_mean.detach().float(), conv.bias.detach().float(), out=mean)
         setattr(sv, "mean" + tag, mean); setattr(sv, "invstd" + tag, invstd)
         setattr(sv, "scale" + tag, scale); setattr(sv, "shift" + tag, shift)
         return scale, shift
@@ -323,7 +404,7 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
         s = torch.empty(B, O, dtype=torch.float32, device=dev)
         sums34 = torch.empty(B, 2, O, dtype=torch.float32, device=dev) if keep else None
         _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(scale2),
-                  _ptr(shift2), _ptr(sv.mean2) if train else None, _ptr(p), _ptr(z), _ptr(s), _ptr(sums34), st)
+                  _ptr(shift2), _ptr(sv.mean2) if (train or keep) else None, _ptr(p), _ptr(z), _ptr(s), _ptr(sums34), st)
         sv.p, sv.z, sv.s, sv.sums34 = p, z, s, sums34
     if pooled is not None and (Hl % 2 or Wl % 2):
         # odd extent: MaxPool2d(2) floors (UCA:106-109) -> scale pass, then the standalone pool over the stored values
@@ -412,6 +493,20 @@ def _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos
     return True
 
 
+def _first_conv_rows(dt, tdt, xf, B, Cin, H, W):
+    """im2col rows of the network input for the first convolution (K = 9*Cin): one row per pixel pair on the bf16
+    tensor-core path with an even H (unetca_im2col_pairs), one per pixel otherwise."""
+    dev, st = xf.device, _stream()
+    if dt == _lib.BF16 and Cin <= 5 and H % 2 == 0 and _lib.load().unetca_get_conv_impl() == 0:
+        col = torch.empty(B * (H // 2) * W, 64, dtype=tdt, device=dev)           # one row per pixel pair (rows 2i, 2i+1)
+        _lib.call("unetca_im2col_pairs", dt, _ptr(xf), _ptr(col), B, Cin, H, W, st)
+    else:
+        Kpad = ((9 * Cin + 63) // 64) * 64
+        col = torch.empty(B * H * W, Kpad, dtype=tdt, device=dev)
+        _lib.call("unetca_im2col3x3_nchw", dt, _ptr(xf), _ptr(col), B, Cin, H, W, Kpad, st)
+    return col
+
+
 def _forward(model: "UNet", x: torch.Tensor, keep: bool):
     """UNet.forward (UCA:127-163).  Returns (logits NCHW fp32, saved-state or None)."""
     _check_input(model, x)
@@ -432,13 +527,7 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
     xf = x.detach()
     if xf.dtype != torch.float32 or not xf.is_contiguous():
         xf = xf.float().contiguous()
-    if dt == _lib.BF16 and Cin <= 5 and H % 2 == 0 and _lib.load().unetca_get_conv_impl() == 0:
-        col = torch.empty(B * (H // 2) * W, 64, dtype=tdt, device=dev)           # one row per pixel pair (rows 2i, 2i+1)
-        _lib.call("unetca_im2col_pairs", dt, _ptr(xf), _ptr(col), B, Cin, H, W, st)
-    else:
-        Kpad = ((9 * Cin + 63) // 64) * 64
-        col = torch.empty(B * H * W, Kpad, dtype=tdt, device=dev)
-        _lib.call("unetca_im2col3x3_nchw", dt, _ptr(xf), _ptr(col), B, Cin, H, W, Kpad, st)
+    col = _first_conv_rows(dt, tdt, xf, B, Cin, H, W)
 
     sv = SimpleNamespace(enc=[], dec=[], up_in=[], cat=[], pos=[], B=B, H=H, W=W, Hs=Hs, Ws=Ws)
     cat = [torch.empty(B, Hs[l], Ws[l], 2 * _WIDTHS[l], dtype=tdt, device=dev) for l in range(4)]
@@ -498,8 +587,8 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
 def _block_grad_order(pre, use_se):
     """Order in which _double_conv_bwd completes the parameter gradients of one block (DP buckets follow it)."""
     out = [pre + ".6.fc.0.weight", pre + ".6.fc.2.weight"] if use_se else []
-    return out + [pre + ".4.weight", pre + ".4.bias", pre + ".3.bias", pre + ".0.bias", pre + ".3.weight",
-                  pre + ".1.weight", pre + ".1.bias", pre + ".0.weight"]
+    return out + [pre + ".4.weight", pre + ".4.bias", pre + ".3.bias", pre + ".3.weight",
+                  pre + ".1.weight", pre + ".1.bias", pre + ".0.bias", pre + ".0.weight"]
 
 
 def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=None):
@@ -562,6 +651,12 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
                       _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(parts), ctypes.byref(nparts), st)
             _lib.call("unetca_bn_bwd_finalize", _ptr(parts), nparts.value, O, npix, _ptr(bn.weight), _ptr(invstd),
                       _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
+        if not sv.train:
+            # eval(): no batch statistics to differentiate through -> dY = gamma*invstd_running * dz (c1 = c2 = 0), and the
+            # conv bias in front (folded into the shift) gets  sum dY = gamma*invstd * sum dz
+            coef[1:].zero_()
+            conv = blk.conv1 if tag == "1" else blk.conv2
+            torch.mul(coef[0], dbeta, out=G.alloc(f"{pre}.{bn_idx - 1}.bias", conv.bias))
         dy = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
         if sums_ is not None and lazy is not None:
             sg, dpl, pos = lazy
@@ -577,11 +672,11 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
 
     # ---- [SE ->] ReLU -> BN2 backward
     dy2 = bn_relu_bwd(dout, dout.stride(2) if dout is not None else 0, sv.y2, "2", s, dp, 4, sums)
-    # a conv bias in front of a train-mode BatchNorm has an analytically zero gradient (BN removes the mean)
-    G.alloc(pre + ".3.bias", blk.conv2.bias).zero_()
+    # a conv bias in front of a train-mode BatchNorm has an analytically zero gradient (BN removes the mean); under
+    # eval() bn_relu_bwd has just written the real one for .3.bias, and writes .0.bias below
+    if sv.train:
+        G.alloc(pre + ".3.bias", blk.conv2.bias).zero_()
     G.put(pre + ".3.bias")
-    G.alloc(pre + ".0.bias", blk.conv1.bias).zero_()
-    G.put(pre + ".0.bias")
     # ---- conv2 wgrad + dgrad
     dw = G.alloc(pre + ".3.weight", blk.conv2.weight)
     _lib.call("unetca_conv3x3_wgrad", dt, _ptr(dy2), O, _ptr(sv.a1), O, _ptr(ws), ws.numel(), B, Hl, Wl, O, O, _ptr(dw), st)
@@ -593,6 +688,9 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
     # ---- ReLU -> BN1 backward
     dy1 = bn_relu_bwd(da1, O, sv.y1, "1", None, None, 1)
     del da1
+    if sv.train:
+        G.alloc(pre + ".0.bias", blk.conv1.bias).zero_()
+    G.put(pre + ".0.bias")
     # ---- conv1 wgrad (+ dgrad)
     dw = G.alloc(pre + ".0.weight", blk.conv1.weight)
     if blk.first and sv_pairs(sv.col, B, Hl, Wl):
@@ -605,8 +703,15 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
         _lib.call("unetca_conv3x3_wgrad", dt, _ptr(dy1), O, _ptr(sv.xin), sv.xin.stride(2), _ptr(ws), ws.numel(), B, Hl,
                   Wl, C, O, _ptr(dw), st)
     G.put(pre + ".0.weight")
-    if not need_dx or blk.first:
+    if not need_dx:
         return None
+    if blk.first:
+        # gradient w.r.t. the network input (only when the caller asked for it: images.requires_grad): the dgrad of the
+        # K = 9*Cin first conv is 0.9 GFLOP/img with N = Cin <= 5 output channels — FFMA kernel, NHWC rows of Cin values
+        wd0 = eng.conv_w_first_dgrad(blk.conv1, dt, tdt)
+        dx = torch.empty(B, Hl, Wl, C, dtype=tdt, device=dev)
+        _lib.call("unetca_simt_conv3x3_fwd", dt, _ptr(dy1), O, _ptr(wd0), 9 * O, _ptr(dx), C, B, Hl, Wl, O, C, st)
+        return dx
     _, wd1, _, _, wdp1 = eng.conv_w(blk.conv1, dt, tdt, False)
     dx = torch.empty(B, Hl, Wl, C, dtype=tdt, device=dev)
     sp, npp = (dx_stats[0], ctypes.byref(dx_stats[1])) if dx_stats is not None else (None, None)
@@ -645,8 +750,9 @@ def grad_order(model: "UNet"):
     return names
 
 
-def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
-    """loss.backward() (UCA:345) for every parameter.  g: (B,nc,H,W) fp32 dlogits up to the factor *gscale."""
+def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor, need_dx: bool = False):
+    """loss.backward() (UCA:345) for every parameter.  g: (B,nc,H,W) fp32 dlogits up to the factor *gscale.
+    Returns ({name: gradient} or None when the sink owns .grad, d(loss)/d(input) NCHW fp32 or None)."""
     G = model._grad_sink_factory() if model._grad_sink_factory is not None else _GradSink()
     eng = model._engine()
     dt, tdt = model._dt()
@@ -701,7 +807,7 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
     # ---- encoder, deep to shallow
     lazy = None
     for l in range(4, -1, -1):
-        dpooled = _double_conv_bwd(eng, sv.enc[l], dcur, G, dt, tdt, l > 0, lazy)
+        dpooled = _double_conv_bwd(eng, sv.enc[l], dcur, G, dt, tdt, l > 0 or need_dx, lazy)
         if l == 0:
             break
         Hp, Wp, Cp = sv.Hs[l - 1], sv.Ws[l - 1], _WIDTHS[l - 1]
@@ -714,7 +820,19 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor):
         dcur = torch.empty(B, Hp, Wp, Cp, dtype=tdt, device=dev)
         _lib.call("unetca_pool_bwd_add", dt, _ptr(sg), sg.stride(2), _ptr(dpooled), Cp, _ptr(sv.pos[l - 1]), _ptr(dcur),
                   Cp, B, Hp, Wp, Cp, st)
-    return G.finish()
+    dx = None
+    if need_dx:
+        Cin = model.in_channels
+        dx = torch.empty(B, Cin, H, W, dtype=torch.float32, device=dev)
+        _lib.call("unetca_nhwc_to_nchw", dt, _ptr(dpooled), Cin, _ptr(dx), B, Cin, H, W, st)
+    return G.finish(), dx
+
+
+def _param_grads(model, grads):
+    """Gradients in parameter order for autograd; a sink that owns `.grad` itself (parallel.GradBuckets) hands None."""
+    if grads is None:
+        return (None,) * len(model._param_names)
+    return tuple(grads[n] for n in model._param_names)
 
 
 class _UNetFn(torch.autograd.Function):
@@ -722,7 +840,8 @@ class _UNetFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, keep, *params):
-        logits, sv = _forward(model, x, keep)
+        with torch.cuda.device(x.device):
+            logits, sv = _forward(model, x, keep)
         ctx.model, ctx.sv = model, sv
         return logits
 
@@ -733,9 +852,10 @@ class _UNetFn(torch.autograd.Function):
             raise RuntimeError("backward through a forward that ran without grad")
         g = dlogits.contiguous().float()
         one = torch.ones(1, dtype=torch.float32, device=g.device)
-        grads = _backward(model, sv, g, one)
+        with torch.cuda.device(g.device):
+            grads, dx = _backward(model, sv, g, one, ctx.needs_input_grad[1])
         ctx.sv = None
-        return (None, None, None) + tuple(grads[n] for n in model._param_names)
+        return (None, dx, None) + _param_grads(model, grads)
 
 
 class _UNetLossFn(torch.autograd.Function):
@@ -743,19 +863,21 @@ class _UNetLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, x, target, ignore_index, keep, *params):
-        logits, sv = _forward(model, x, keep)
-        B, nc, H, W = logits.shape
-        dev = logits.device
+        B, H, W = x.shape[0], x.shape[2], x.shape[3]
         if target.shape != (B, H, W) or target.dtype != torch.int64 or not target.is_cuda:
             raise ValueError(f"target must be a CUDA int64 tensor of shape {(B, H, W)}")
-        target = target.contiguous()
-        eng = model._engine()
-        parts = eng.parts(B, dev)
-        g = torch.empty_like(logits) if keep else None
-        out = torch.empty(2, dtype=torch.float32, device=dev)
-        gscale = torch.empty(1, dtype=torch.float32, device=dev)
-        _lib.call("unetca_cross_entropy", _ptr(logits), _ptr(target), nc, B, H * W, int(ignore_index), None, _ptr(g),
-                  None, _ptr(parts), _ptr(out), _ptr(gscale), _stream())
+        with torch.cuda.device(x.device):
+            logits, sv = _forward(model, x, keep)
+            nc = logits.shape[1]
+            dev = logits.device
+            target = target.contiguous()
+            eng = model._engine()
+            parts = eng.parts(B, dev)
+            g = torch.empty_like(logits) if keep else None
+            out = torch.empty(2, dtype=torch.float32, device=dev)
+            gscale = torch.empty(1, dtype=torch.float32, device=dev)
+            _lib.call("unetca_cross_entropy", _ptr(logits), _ptr(target), nc, B, H * W, int(ignore_index), None, _ptr(g),
+                      None, _ptr(parts), _ptr(out), _ptr(gscale), _stream())
         model.last_logits = logits
         ctx.model, ctx.sv, ctx.g, ctx.gscale = model, sv, g, gscale
         return out[0].clone()
@@ -766,9 +888,106 @@ class _UNetLossFn(torch.autograd.Function):
         if sv is None:
             raise RuntimeError("backward through a forward that ran without grad")
         gscale = ctx.gscale * dloss.reshape(1).float()
-        grads = _backward(model, sv, ctx.g, gscale)
+        with torch.cuda.device(gscale.device):
+            grads, dx = _backward(model, sv, ctx.g, gscale, ctx.needs_input_grad[1])
         ctx.sv = ctx.g = None
-        return (None, None, None, None, None) + tuple(grads[n] for n in model._param_names)
+        return (None, dx, None, None, None) + _param_grads(model, grads)
+
+
+class _SELayerFn(torch.autograd.Function):
+    """SELayer.forward on its own (UCA:61-72): NCHW fp32 plane passes around the SE FC kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w1, w2):
+        B, C, H, W = x.shape
+        Cr, hw, st, dev = w1.shape[0], H * W, _stream(), x.device
+        xf = x.detach().float().contiguous()
+        w1f, w2f = w1.detach().float().contiguous(), w2.detach().float().contiguous()
+        sums = torch.empty(B, C, dtype=torch.float32, device=dev)
+        _lib.call("unetca_plane_dot", _ptr(xf), None, B * C, hw, _ptr(sums), st)
+        p = torch.empty(B, C, dtype=torch.float32, device=dev)
+        z = torch.empty(B, Cr, dtype=torch.float32, device=dev)
+        s = torch.empty(B, C, dtype=torch.float32, device=dev)
+        _lib.call("unetca_se_fc", _ptr(sums), 1, B, C, Cr, hw, _ptr(w1f), _ptr(w2f), _ptr(p), _ptr(z), _ptr(s), st)
+        out = torch.empty_like(xf)
+        _lib.call("unetca_plane_scale_add", _ptr(xf), _ptr(s), None, 0.0, B * C, hw, _ptr(out), st)
+        ctx.save_for_backward(xf, w1f, w2f, p, z, s)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        xf, w1f, w2f, p, z, s = ctx.saved_tensors
+        B, C, H, W = xf.shape
+        Cr, hw, dev = w1f.shape[0], H * W, xf.device
+        with torch.cuda.device(dev):
+            st = _stream()
+            dyf = dy.float().contiguous()
+            ds = torch.empty(B, C, dtype=torch.float32, device=dev)
+            _lib.call("unetca_plane_dot", _ptr(dyf), _ptr(xf), B * C, hw, _ptr(ds), st)
+            dpre2 = torch.empty(B, C, dtype=torch.float32, device=dev)
+            dz = torch.empty(B, Cr, dtype=torch.float32, device=dev)
+            dp = torch.empty(B, C, dtype=torch.float32, device=dev)
+            dw1, dw2 = torch.empty_like(w1f), torch.empty_like(w2f)
+            _lib.call("unetca_se_fc_bwd", _ptr(ds), 1, B, C, Cr, _ptr(w1f), _ptr(w2f), _ptr(p), _ptr(z), _ptr(s), _ptr(dpre2),
+                      _ptr(dz), _ptr(dp), _ptr(dw1), _ptr(dw2), st)
+            dx = torch.empty_like(xf)
+            _lib.call("unetca_plane_scale_add", _ptr(dyf), _ptr(s), _ptr(dp), 1.0 / hw, B * C, hw, _ptr(dx), st)
+        return dx, dw1, dw2
+
+
+class _DoubleConvFn(torch.autograd.Function):
+    """DoubleConv.forward on its own (UCA:96-97): the block kernels of UNet between two NCHW <-> NHWC boundary passes."""
+
+    @staticmethod
+    def forward(ctx, mod, x, keep, *params):
+        eng, blk = mod._engine(), mod._blk
+        dt, tdt = mod._dt()
+        train = mod.training
+        if train or eng.last_train:
+            eng.epoch += 1
+        eng.last_train = train
+        B, C, H, W = x.shape
+        O, dev = blk.cout, x.device
+        if train and B * H * W <= 1:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {[B, O, H, W]}")
+        with torch.cuda.device(dev):
+            st = _stream()
+            xf = x.detach().float().contiguous()
+            if blk.first:
+                xin, col = None, _first_conv_rows(dt, tdt, xf, B, C, H, W)
+            else:
+                xin, col = torch.empty(B, H, W, C, dtype=tdt, device=dev), None
+                _lib.call("unetca_nchw_to_nhwc", dt, _ptr(xf), _ptr(xin), C, B, C, H, W, st)
+            out = torch.empty(B, H, W, O, dtype=tdt, device=dev)
+            sv = _double_conv_fwd(eng, blk, xin, col, B, H, W, out, None, None, train, dt, tdt, keep)
+            y = torch.empty(B, O, H, W, dtype=torch.float32, device=dev)
+            _lib.call("unetca_nhwc_to_nchw", dt, _ptr(out), O, _ptr(y), B, O, H, W, st)
+        ctx.mod, ctx.sv = mod, sv if keep else None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mod, sv = ctx.mod, ctx.sv
+        if sv is None:
+            raise RuntimeError("backward through a forward that ran without grad")
+        eng, blk = mod._engine(), mod._blk
+        dt, tdt = mod._dt()
+        B, H, W, C, O, dev = sv.B, sv.H, sv.W, blk.cin, blk.cout, dy.device
+        with torch.cuda.device(dev):
+            st = _stream()
+            g = dy.float().contiguous()
+            dout = torch.empty(B, H, W, O, dtype=tdt, device=dev)
+            _lib.call("unetca_nchw_to_nhwc", dt, _ptr(g), _ptr(dout), O, B, O, H, W, st)
+            G = _GradSink()
+            need_dx = ctx.needs_input_grad[1]
+            dxn = _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx)
+            dx = None
+            if need_dx:
+                dx = torch.empty(B, C, H, W, dtype=torch.float32, device=dev)
+                _lib.call("unetca_nhwc_to_nchw", dt, _ptr(dxn), C, _ptr(dx), B, C, H, W, st)
+        ctx.sv = None
+        grads = G.finish()
+        return (None, dx, None) + tuple(grads[n] for n, _ in mod.named_parameters())
 
 
 class UNet(nn.Module):
@@ -829,13 +1048,15 @@ class UNet(nn.Module):
             object.__setattr__(self, "_eng", _Engine(self))
         return self._eng
 
-    def _keep(self) -> bool:
+    def _keep(self, x=None) -> bool:
         """Will this forward be differentiated?  (decided here: autograd.Function.forward always runs in no-grad mode)"""
-        keep = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        if keep and not self.training:
-            raise NotImplementedError("backward in eval() mode (running-stat BatchNorm) is not implemented; the "
-                                      "reference only differentiates in train() mode (UCA:333,345)")
-        return keep
+        return torch.is_grad_enabled() and (any(p.requires_grad for p in self.parameters()) or
+                                            (x is not None and x.requires_grad))
+
+    def invalidate_packed(self) -> None:
+        """Call after writing parameters behind autograd's back (`p.data.copy_()`, EMA/SWA swaps, raw-pointer optimizers):
+        the next forward re-derives the packed bf16 operand copies from the fp32 parameters."""
+        self._engine().invalidate()
 
     def _params(self):
         return [p for _, p in self.named_parameters()]
@@ -844,14 +1065,14 @@ class UNet(nn.Module):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """(B,Cin,H,W) float -> class logits (B,num_classes,H,W), like the reference's UNet.forward (UCA:127-163)."""
         _check_input(self, x)
-        out = _UNetFn.apply(self, x, self._keep(), *self._params())
+        out = _UNetFn.apply(self, x, self._keep(x), *self._params())
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
     # ---- fused extras ---------------------------------------------------------------------------------
     def loss(self, images: torch.Tensor, masks: torch.Tensor, ignore_index: int = 255) -> torch.Tensor:
         """criterion(model(images), masks) with nn.CrossEntropyLoss(ignore_index) semantics, fused."""
         _check_input(self, images)
-        return _UNetLossFn.apply(self, images, masks, ignore_index, self._keep(), *self._params())
+        return _UNetLossFn.apply(self, images, masks, ignore_index, self._keep(images), *self._params())
 
     @torch.no_grad()
     def predict_mask(self, images: torch.Tensor) -> torch.Tensor:
@@ -859,6 +1080,7 @@ class UNet(nn.Module):
         logits = self.forward(images).float().contiguous()
         B, nc, H, W = logits.shape
         mask = torch.empty(B, H, W, dtype=torch.int64, device=logits.device)
-        _lib.call("unetca_cross_entropy", _ptr(logits), None, nc, B, H * W, -1, None, None, _ptr(mask), None, None, None,
-                  _stream())
+        with torch.cuda.device(logits.device):
+            _lib.call("unetca_cross_entropy", _ptr(logits), None, nc, B, H * W, -1, None, None, _ptr(mask), None, None, None,
+                      _stream())
         return mask

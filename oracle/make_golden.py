@@ -129,16 +129,56 @@ def run_dataset(ref):
     print("dataset fixture:", root, len(out) // 2, "items")
 
 
+def run_trajectory(ref, name, seed, B, H, W, steps):
+    """100 steps of the reference's own train loop body (UCA:338-346: zero_grad, forward, criterion, backward,
+    Adam(lr=1e-4).step) with the UNMODIFIED classes on seeded batches (make_batch(1000 + s % 4)): the loss and the
+    global gradient norm of every step.  Large enough (bottleneck BatchNorm over B*(H/16)*(W/16) >= 256 values) for the
+    bf16 path to be held to the north_star's 1e-2."""
+    sd = port.make_state_dict(seed=seed)
+    model = ref.UNet(in_channels=3, num_classes=2, use_se=True)
+    model.load_state_dict(sd, strict=True)
+    model.train()
+    crit = torch.nn.CrossEntropyLoss(ignore_index=255)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    losses, gnorms = [], []
+    for s in range(steps):
+        x, y = port.make_batch(1000 + s % 4, B, H, W)
+        opt.zero_grad()
+        loss = crit(model(x), y)
+        loss.backward()
+        gnorms.append(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in model.parameters())).item())
+        losses.append(loss.item())
+        opt.step()
+    path = os.path.join(OUT, name + ".npz")
+    np.savez_compressed(path, loss=np.array(losses, dtype=np.float64), grad_norm=np.array(gnorms, dtype=np.float64),
+                        cfg=np.array([seed, B, H, W, steps]))
+    print(name, "loss", losses[0], "->", losses[-1], "gnorm", gnorms[0], "->", gnorms[-1], path)
+
+
 def main():
+    """python oracle/make_golden.py [case ...] — no arguments: regenerate everything."""
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
-    run_metrics(ref)
-    run_dataset(ref)
-    run_case(ref, "unetca_se_b2_32", seed=0, B=2, H=32, W=32, use_se=True, full=True)
-    run_case(ref, "unet_plain_b2_32", seed=1, B=2, H=32, W=48, use_se=False, full=True)
-    run_case(ref, "unetca_se_b4_256", seed=0, B=4, H=256, W=256, use_se=True, full=False)   # BASELINE configs[0]
-    # H, W not multiples of 16: floor max-pools (5 -> 2, 13 -> 6) and the bilinear resize guard of UCA:138-157
-    run_case(ref, "unetca_se_b2_40x52", seed=3, B=2, H=40, W=52, use_se=True, full=True)
+    cases = [
+        ("metrics", lambda: run_metrics(ref)),
+        ("voc_mini", lambda: run_dataset(ref)),
+        ("unetca_se_b2_32", lambda: run_case(ref, "unetca_se_b2_32", seed=0, B=2, H=32, W=32, use_se=True, full=True)),
+        ("unet_plain_b2_32", lambda: run_case(ref, "unet_plain_b2_32", seed=1, B=2, H=32, W=48, use_se=False, full=True)),
+        # BASELINE configs[0]
+        ("unetca_se_b4_256", lambda: run_case(ref, "unetca_se_b4_256", seed=0, B=4, H=256, W=256, use_se=True, full=False)),
+        # H, W not multiples of 16: floor max-pools (5 -> 2, 13 -> 6) and the bilinear resize guard of UCA:138-157
+        ("unetca_se_b2_40x52", lambda: run_case(ref, "unetca_se_b2_40x52", seed=3, B=2, H=40, W=52, use_se=True, full=True)),
+        # the benchmarked tile size (BASELINE configs[1] is 64 of these): 8 images of 3x512x512 — what host RAM and a
+        # CPU oracle run in test time; every kernel family the B=64 bench dispatches is on this path
+        ("unetca_se_b8_512", lambda: run_case(ref, "unetca_se_b8_512", seed=4, B=8, H=512, W=512, use_se=True, full=False)),
+        ("trajectory_b4_128", lambda: run_trajectory(ref, "trajectory_b4_128", seed=7, B=4, H=128, W=128, steps=100)),
+    ]
+    want = set(sys.argv[1:])
+    unknown = want - {n for n, _ in cases}
+    assert not unknown, f"unknown case(s) {sorted(unknown)}"
+    for name, fn in cases:
+        if not want or name in want:
+            fn()
 
 
 if __name__ == "__main__":

@@ -127,12 +127,22 @@ def _double_conv(x, p, pre, use_se, train, bufs):
             bufs[f'{pre}.{j}.num_batches_tracked'] += 1
         x = F.relu(x)                                                                        # UCA:83,86
     if use_se:
-        b, c = x.shape[:2]
-        y = F.adaptive_avg_pool2d(x, 1).view(b, c)                                           # UCA:65
-        y = F.relu(F.linear(y, p[f'{pre}.6.fc.0.weight']))                                   # UCA:55-56
-        y = torch.sigmoid(F.linear(y, p[f'{pre}.6.fc.2.weight']))                            # UCA:57-58
-        x = x * y.view(b, c, 1, 1)                                                           # UCA:72
+        x = se_layer(x, p[f'{pre}.6.fc.0.weight'], p[f'{pre}.6.fc.2.weight'])
     return x
+
+
+def se_layer(x, w1, w2):
+    """SELayer.forward (UCA:61-72) on its own: x * sigmoid(W2 relu(W1 mean_hw(x)))."""
+    b, c = x.shape[:2]
+    y = F.adaptive_avg_pool2d(x, 1).view(b, c)                                               # UCA:65
+    y = F.relu(F.linear(y, w1))                                                              # UCA:55-56
+    y = torch.sigmoid(F.linear(y, w2))                                                       # UCA:57-58
+    return x * y.view(b, c, 1, 1)                                                            # UCA:72
+
+
+def double_conv(x, p, pre, use_se, train):
+    """DoubleConv.forward (UCA:96-97) on its own, parameters / buffers keyed `pre.<index>.<name>` as in the state_dict."""
+    return _double_conv(x, p, pre, use_se, train, p)
 
 
 def unet_forward(x, p, bufs=None, use_se=True, train=True, return_aux=False):

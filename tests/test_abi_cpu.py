@@ -13,7 +13,11 @@ def test_library_exports_every_declared_symbol(built_lib):
     import unetca_b200
     decls = unetca_b200._lib.parse_header()
     assert len(decls) >= 45
-    for name in decls:
+    # the development knobs live in their own header: the drop-in ABI declares no process-global switch but conv_impl
+    tuning = unetca_b200._lib.parse_header(unetca_b200._lib.TUNING_HEADER)
+    assert tuning and not (set(tuning) & set(decls))
+    assert not [n for n in decls if "force" in n or "set_tuning" in n or n.startswith("unetca_tc_set")]
+    for name in list(decls) + list(tuning):
         assert hasattr(built_lib, name), name
     assert built_lib.unetca_abi_version() == 1
     assert built_lib.unetca_max_parts(4) > 4
@@ -54,6 +58,26 @@ def test_no_cpu_fallback():
         m(torch.zeros(1, 3, 32, 32))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         m.loss(torch.zeros(1, 3, 32, 32), torch.zeros(1, 32, 32, dtype=torch.int64))
+
+
+def test_standalone_modules_have_no_cpu_fallback_either():
+    import unetca_b200
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        unetca_b200.SELayer(64)(torch.zeros(1, 64, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        unetca_b200.DoubleConv(3, 64, use_se=True)(torch.zeros(1, 3, 8, 8))
+
+
+def test_reference_arm_is_the_unmodified_reference():
+    """build() stages a byte-identical copy of the reference's hot-path script in the git-ignored oracle/_ref/ whenever
+    /root/reference is present (bench.py --impl reference and cpu_baseline import UNet / CrossEntropyLoss from it)."""
+    import __graft_entry__ as g
+    if not os.path.exists(g.REFERENCE_SRC):
+        pytest.skip("no /root/reference on this box")
+    assert g.stage_reference()
+    assert open(g.REFERENCE_COPY, "rb").read() == open(g.REFERENCE_SRC, "rb").read()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert "oracle/_ref/" in open(os.path.join(root, ".gitignore")).read()
 
 
 def test_product_does_not_import_oracle():

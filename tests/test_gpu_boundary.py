@@ -1,0 +1,223 @@
+"""-m gpu: the parts of the reference's module surface beyond `UNet.forward` in train mode:
+standalone `SELayer` / `DoubleConv` (UCA:61-72, 96-97), the gradient w.r.t. the input image, backward under eval(),
+validation interleaved with CUDA-graph replays, and writes to parameters that bypass autograd's version counter.
+Checked against the pinned oracle port (same ATen CPU ops as the reference's modules)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import unet_ca_port as port  # noqa: E402
+
+
+@pytest.fixture(autouse=True)
+def _need_gpu(built_lib):
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    built_lib.unetca_set_conv_impl(0)
+    yield
+    torch.cuda.synchronize()
+
+
+def _rel(a, b):
+    return ((a.float().cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("C,H,W", [(64, 24, 40), (256, 7, 9)])
+def test_selayer_standalone_forward_backward(C, H, W):
+    """unetca_b200.SELayer called like the reference's (UCA:61-72) on an input of mixed sign."""
+    import unetca_b200
+    torch.manual_seed(C)
+    se = unetca_b200.SELayer(C).cuda()
+    x = torch.randn(3, C, H, W)
+    dy = torch.randn(3, C, H, W)
+    w1 = se.fc[0].weight.detach().cpu().clone().requires_grad_(True)
+    w2 = se.fc[2].weight.detach().cpu().clone().requires_grad_(True)
+    xr = x.clone().requires_grad_(True)
+    ref = port.se_layer(xr, w1, w2)
+    ref.backward(dy)
+    xg = x.cuda().requires_grad_(True)
+    out = se(xg)
+    out.backward(dy.cuda())
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert _rel(out.detach(), ref.detach()) < 1e-5
+    assert _rel(xg.grad, xr.grad) < 1e-4
+    assert _rel(se.fc[0].weight.grad, w1.grad) < 1e-3
+    assert _rel(se.fc[2].weight.grad, w2.grad) < 1e-3
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-3), ("bf16", 5e-2)])
+@pytest.mark.parametrize("cin,cout,use_se,train", [(3, 64, True, True), (64, 128, True, True), (128, 64, False, True),
+                                                   (64, 128, True, False)])
+def test_doubleconv_standalone_forward_backward(prec, tol, cin, cout, use_se, train):
+    """unetca_b200.DoubleConv called like the reference's (UCA:96-97): NCHW in/out, train and eval BatchNorm, gradients
+    w.r.t. the input and every parameter."""
+    import unetca_b200
+    torch.manual_seed(cin + cout)
+    dc = unetca_b200.DoubleConv(cin, cout, use_se=use_se).cuda().set_precision(prec)
+    with torch.no_grad():
+        for n, b in dc.named_buffers():
+            if n.endswith("running_mean"):
+                b.normal_(0, 0.1)
+            if n.endswith("running_var"):
+                b.uniform_(0.8, 1.3)
+    dc.train(train)
+    B, H, W = 4, 32, 48
+    x = torch.randn(B, cin, H, W)
+    dy = torch.randn(B, cout, H, W)
+    p = {"dc." + k: (v.detach().cpu().clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k
+                     else v.detach().cpu().clone()) for k, v in dc.double_conv.state_dict().items()}
+    xr = x.clone().requires_grad_(True)
+    ref = port.double_conv(xr, p, "dc", use_se, train)
+    ref.backward(dy)
+    xg = x.cuda().requires_grad_(True)
+    out = dc(xg)
+    out.backward(dy.cuda())
+    assert out.shape == ref.shape
+    assert _rel(out.detach(), ref.detach()) < tol
+    assert _rel(xg.grad, xr.grad) < tol * (2 if prec == "fp32" else 1)
+    gn = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in dc.parameters())).item()
+    rgn = torch.sqrt(sum((v.grad ** 2).sum() for v in p.values() if v.requires_grad)).item()
+    assert abs(gn - rgn) / rgn < (1e-2 if prec == "fp32" else 3e-2)
+    if prec == "fp32":
+        for k, q in dc.double_conv.named_parameters():
+            r = p["dc." + k].grad
+            if r.abs().max() > 1e-6 * rgn:
+                assert _rel(q.grad, r) < 1e-2, k
+    if train:
+        for k, b in dc.double_conv.named_buffers():
+            if "running" in k:
+                assert _rel(b, p["dc." + k]) < (1e-4 if prec == "fp32" else 2e-2), k
+
+
+@pytest.mark.parametrize("prec,tol", [("fp32", 2e-3), ("bf16", 6e-2)])
+@pytest.mark.parametrize("train", [True, False])
+def test_unet_input_gradient_and_eval_backward(prec, tol, train):
+    """`images.requires_grad` (saliency maps, adversarial probes) and backward under eval(): plain autograd in the
+    reference (UCA:127-163), a first-conv dgrad and a fixed-affine BatchNorm backward here."""
+    import unetca_b200
+    sd = port.make_state_dict(seed=13)
+    for k in sd:
+        if k.endswith("running_mean"):
+            sd[k] = 0.05 * torch.randn(sd[k].shape, generator=torch.Generator().manual_seed(len(k)))
+        if k.endswith("running_var"):
+            sd[k] = 1.0 + 0.2 * torch.rand(sd[k].shape, generator=torch.Generator().manual_seed(len(k) + 1))
+    x, y = port.make_batch(13, 3, 48, 64)
+    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    rl = port.loss_fn(port.unet_forward(xr, p, train=train), y)
+    rl.backward()
+    m = unetca_b200.UNet(3, 2, use_se=True).cuda().set_precision(prec)
+    m.load_state_dict(sd)
+    m.train(train)
+    xg = x.cuda().requires_grad_(True)
+    loss = torch.nn.CrossEntropyLoss(ignore_index=255)(m(xg), y.cuda())
+    loss.backward()
+    assert abs(loss.item() - rl.item()) / rl.item() < 1e-2
+    assert xg.grad.shape == x.shape
+    assert _rel(xg.grad, xr.grad) < tol
+    gn = torch.sqrt(sum((q.grad.float() ** 2).sum() for q in m.parameters())).item()
+    rgn = torch.sqrt(sum((v.grad ** 2).sum() for v in p.values() if v.requires_grad)).item()
+    assert abs(gn - rgn) / rgn < (1e-2 if prec == "fp32" else 3e-2)
+    if not train and prec == "fp32":
+        params = dict(m.named_parameters())
+        # under eval() the conv biases in front of BatchNorm have REAL gradients (train mode: analytically zero)
+        for k in ("inc.double_conv.0.bias", "down2.1.double_conv.3.bias", "conv3.double_conv.0.bias"):
+            assert _rel(params[k].grad, p[k].grad) < 1e-2, k
+        # fused loss path gives the same input gradient
+        xg2 = x.cuda().requires_grad_(True)
+        for q in m.parameters():
+            q.grad = None
+        m.loss(xg2, y.cuda()).backward()
+        assert _rel(xg2.grad, xr.grad) < tol
+
+
+@pytest.mark.parametrize("own", [False, True])
+def test_graph_replays_interleaved_with_validation(own):
+    """replay x N -> eval -> replay x N -> eval (the reference's per-epoch validate_model, UCA:375-376) must see the
+    stepped weights both times: eval logits identical to the eager run's (round-1 advisor finding)."""
+    import unetca_b200
+    from unetca_b200 import graph
+    sd = port.make_state_dict(seed=41, in_channels=1)
+    batches = [port.make_batch(400 + i, 4, 64, 64, in_channels=1) for i in range(3)]
+    xv = port.make_batch(450, 2, 64, 64, in_channels=1)[0].cuda()
+
+    def run(graphed):
+        m = unetca_b200.UNet(1, 2, use_se=True).cuda().set_precision("bf16")
+        m.load_state_dict(sd)
+        m.train()
+        if own:
+            from unetca_b200 import optim as uoptim
+            opt = uoptim.Adam(m.parameters(), lr=1e-3, model=m)
+        else:
+            opt = torch.optim.Adam(m.parameters(), lr=1e-3, capturable=True)
+        evals = []
+        step = graph.GraphedTrainStep(m, opt, batches[0][0].cuda(), batches[0][1].cuda(), warmup=3) if graphed else None
+        if not graphed:
+            for _ in range(4):                                  # 3 warm-up steps + the capture pass, all on batch 0
+                opt.zero_grad(set_to_none=True)
+                m.loss(batches[0][0].cuda(), batches[0][1].cuda()).backward()
+                opt.step()
+        for epoch in range(3):
+            m.train()
+            for x, y in batches:
+                if graphed:
+                    step(x.cuda(), y.cuda())
+                else:
+                    opt.zero_grad(set_to_none=True)
+                    m.loss(x.cuda(), y.cuda()).backward()
+                    opt.step()
+            m.eval()
+            with torch.no_grad():
+                evals.append(m(xv).clone())
+            torch.cuda.empty_cache()                            # the packed buffers the graph points at must survive this
+        return evals
+
+    ee, eg = run(False), run(True)
+    for a, b in zip(ee, eg):
+        assert torch.equal(a, b)
+    assert not torch.equal(eg[0], eg[1]) and not torch.equal(eg[1], eg[2])     # the weights did move between validations
+
+
+def test_invalidate_packed_after_data_write():
+    """p.data.copy_() (EMA / SWA swaps) does not bump the version counter: model.invalidate_packed() makes the next
+    eval forward re-derive the packed operands."""
+    import unetca_b200
+    sd = port.make_state_dict(seed=5)
+    m = unetca_b200.UNet(3, 2, True).cuda().set_precision("bf16")
+    m.load_state_dict(sd)
+    m.eval()
+    x = port.make_batch(5, 2, 32, 32)[0].cuda()
+    with torch.no_grad():
+        a = m(x).clone()
+        m.down2[1].double_conv[0].weight.data.mul_(1.5)
+        m.invalidate_packed()
+        b = m(x).clone()
+        m2 = unetca_b200.UNet(3, 2, True).cuda().set_precision("bf16")
+        m2.load_state_dict(m.state_dict())
+        m2.eval()
+        assert torch.equal(m2(x), b) and not torch.equal(a, b)
+
+
+def test_gradient_accumulation_single_gpu_matches_big_batch_mean():
+    """k micro-steps of (loss / k).backward() accumulate in .grad exactly like torch (no GradBuckets at N = 1)."""
+    import unetca_b200
+    sd = port.make_state_dict(seed=3)
+    m = unetca_b200.UNet(3, 2, True).cuda().set_precision("fp32")
+    m.load_state_dict(sd)
+    m.train()
+    xs = [port.make_batch(60 + i, 2, 32, 32) for i in range(2)]
+    for x, y in xs:
+        (m.loss(x.cuda(), y.cuda()) / 2).backward()
+    acc = [p.grad.clone() for p in m.parameters()]
+    want = None
+    for x, y in xs:
+        for p in m.parameters():
+            p.grad = None
+        m.loss(x.cuda(), y.cuda()).backward()
+        g = [p.grad.clone() / 2 for p in m.parameters()]
+        want = g if want is None else [a + b for a, b in zip(want, g)]
+    for a, w in zip(acc, want):
+        assert torch.allclose(a, w, rtol=1e-5, atol=1e-8)

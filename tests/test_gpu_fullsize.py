@@ -121,3 +121,120 @@ def test_model_full_size_properties():
     assert abs(out[0].item() - np.log(2.0)) < 1e-6
     assert out[1].item() == (y != 255).sum().item()
     assert g.sum(1).abs().max().item() < 1e-6 and (g[:, 0][y == 255] == 0).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# What the three-layout test above does not reach at batch 64: the kw-stacked kernel production dispatches (128 -> 64 at
+# 512^2), every weight-gradient family with its split-K over K = B*H*W up to 16.8 M, and the ConvTranspose trio at the
+# full-resolution level.  Reference: ATen's CUDA kernels in fp32 with TF32 off on the SAME bf16-rounded operands, so the
+# only difference is fp32 summation order (and, for outputs stored as bf16, one rounding).
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def fp32_exact():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _relmax(a, b):
+    return ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
+
+
+def test_conv3x3_kw_stacked_full_size_vs_aten(fp32_exact):
+    """unetca_conv3x3_fwd_kw at (128 -> 64, 512^2, B = 64) — the shape model._derive sends to the kw-stacked kernel."""
+    torch.manual_seed(7)
+    call("unetca_set_conv_impl", 0)
+    C, O, HW = 128, 64, 512
+    x = torch.randn(B, HW, HW, C, device="cuda").to(torch.bfloat16)
+    w = torch.randn(O, C, 3, 3, device="cuda") / (9 * C) ** 0.5
+    wf = torch.empty(O, 9 * C, dtype=torch.bfloat16, device="cuda")
+    call("unetca_pack_conv3x3_weight", BF16, ptr(w), ptr(wf), 9 * C, None, O, C, stream())
+    wkw = torch.empty(9 * C, 64, dtype=torch.bfloat16, device="cuda")
+    call("unetca_pack_conv3x3_kw", BF16, ptr(wf), 9 * C, ptr(wkw), C, stream())
+    y = torch.empty(B, HW, HW, O, dtype=torch.bfloat16, device="cuda")
+    parts = parts_buf(B)
+    n = cint()
+    call("unetca_conv3x3_fwd_kw", BF16, ptr(x), C, ptr(wkw), ptr(y), O, B, HW, HW, C, ptr(parts), ctypes.byref(n), stream())
+    st = parts[: n.value * 2 * O].view(n.value, 2, O).double().sum(0)
+    wq = w.to(torch.bfloat16).float().contiguous(memory_format=torch.channels_last)
+    worst = 0.0
+    for b0 in range(0, B, 8):                                    # fp32 reference in slabs of 8 images (memory)
+        ref = F.conv2d(_nhwc(x[b0:b0 + 8]).float(), wq, None, padding=1)
+        worst = max(worst, _relmax(_nhwc(y[b0:b0 + 8]), ref))
+    assert worst < 6e-3, worst                                   # one bf16 rounding of the stored output
+    yf = y.float()
+    s1, s2 = yf.sum((0, 1, 2)).double(), (yf * yf).sum((0, 1, 2)).double()
+    assert ((st[0] - s1).abs().max() / s1.abs().max()).item() < 1e-3
+    assert ((st[1] - s2).abs().max() / s2.abs().max()).item() < 1e-3
+
+
+@pytest.mark.parametrize("C,O,HW,family", [
+    (64, 64, 512, "rowpair"), (128, 64, 512, "rowpair"), (64, 128, 256, "rowpair"),
+    (128, 128, 256, "wide"), (256, 128, 256, "wide"),
+    (128, 256, 128, "wide256"), (512, 512, 64, "wide256"), (1024, 1024, 32, "wide256"),
+])
+def test_conv3x3_wgrad_full_size_vs_aten(fp32_exact, C, O, HW, family):
+    """Every conv3x3 weight-gradient family at batch 64 (split-K over K = B*H*W pixels, deterministic reduction) against
+    torch.nn.grad.conv2d_weight in fp32 on the same bf16 operands."""
+    torch.manual_seed(C * 3 + O)
+    call("unetca_set_conv_impl", 0)
+    x = torch.randn(B, HW, HW, C, device="cuda").to(torch.bfloat16)
+    dy = torch.randn(B, HW, HW, O, device="cuda").to(torch.bfloat16)
+    ws = torch.empty(48 * 1024 * 1024, device="cuda")
+    dw = torch.empty(O, C, 3, 3, device="cuda")
+    call("unetca_conv3x3_wgrad", BF16, ptr(dy), O, ptr(x), C, ptr(ws), ws.numel(), B, HW, HW, C, O, ptr(dw), stream())
+    ref = torch.zeros(O, C, 3, 3, device="cuda", dtype=torch.float64)
+    step = 8 if HW >= 256 else 32
+    for b0 in range(0, B, step):
+        ref += torch.nn.grad.conv2d_weight(_nhwc(x[b0:b0 + step]).float(), (O, C, 3, 3), _nhwc(dy[b0:b0 + step]).float(),
+                                           padding=1).double()
+    err = ((dw.double() - ref).abs().max() / ref.abs().max()).item()
+    assert err < 1e-4, (family, err)                             # fp32 accumulation of exact bf16 x bf16 products
+    dw2 = torch.empty_like(dw)
+    call("unetca_conv3x3_wgrad", BF16, ptr(dy), O, ptr(x), C, ptr(ws), ws.numel(), B, HW, HW, C, O, ptr(dw2), stream())
+    assert torch.equal(dw, dw2)                                  # no atomics: run-to-run identical
+
+
+def test_convT_full_size_level0_vs_aten(fp32_exact):
+    """ConvTranspose2d(128, 64, 2, 2) at 256^2 -> 512^2, batch 64 (up4, UCA:121): forward into the upper half of a concat
+    buffer, dgrad and weight gradient, against ATen in fp32 on the same bf16 operands."""
+    torch.manual_seed(11)
+    call("unetca_set_conv_impl", 0)
+    Cin, Cout, h = 128, 64, 256
+    x = torch.randn(B, h, h, Cin, device="cuda").to(torch.bfloat16)
+    w = torch.randn(Cin, Cout, 2, 2, device="cuda") / (Cin) ** 0.5
+    bias = torch.randn(Cout, device="cuda") * 0.1
+    wf = torch.empty(4 * Cout, Cin, dtype=torch.bfloat16, device="cuda")
+    wd = torch.empty(Cin, 4 * Cout, dtype=torch.bfloat16, device="cuda")
+    call("unetca_pack_convT_weight", BF16, ptr(w), ptr(wf), ptr(wd), Cin, Cout, stream())
+    cat = torch.zeros(B, 2 * h, 2 * h, 2 * Cout, dtype=torch.bfloat16, device="cuda")
+    up = cat[..., Cout:]
+    call("unetca_convT2x2_fwd", BF16, ptr(x), Cin, ptr(wf), ptr(bias), ptr(up), 2 * Cout, B, h, h, Cin, Cout, stream())
+    wq = w.to(torch.bfloat16).float()
+    worst = 0.0
+    for b0 in range(0, B, 8):
+        ref = F.conv_transpose2d(_nhwc(x[b0:b0 + 8]).float(), wq, bias, stride=2)
+        worst = max(worst, _relmax(_nhwc(up[b0:b0 + 8]), ref))
+    assert worst < 6e-3, worst
+    assert int((cat[..., :Cout] != 0).sum()) == 0                # the skip half of the concat buffer is untouched
+    # dgrad + wgrad from a gradient living in the same channel slice
+    dcat = torch.randn(B, 2 * h, 2 * h, 2 * Cout, device="cuda").to(torch.bfloat16)
+    du = dcat[..., Cout:]
+    dx = torch.empty(B, h, h, Cin, dtype=torch.bfloat16, device="cuda")
+    call("unetca_convT2x2_dgrad", BF16, ptr(du), 2 * Cout, ptr(wd), ptr(dx), Cin, B, h, h, Cin, Cout, stream())
+    ws = torch.empty(48 * 1024 * 1024, device="cuda")
+    dw = torch.empty(Cin, Cout, 2, 2, device="cuda")
+    call("unetca_convT2x2_wgrad", BF16, ptr(x), Cin, ptr(du), 2 * Cout, ptr(ws), ws.numel(), B, h, h, Cin, Cout, ptr(dw), stream())
+    worst = 0.0
+    refw = torch.zeros(Cin, Cout, 2, 2, device="cuda", dtype=torch.float64)
+    for b0 in range(0, B, 8):
+        xs = _nhwc(x[b0:b0 + 8]).float().requires_grad_(True)
+        wr = wq.clone().requires_grad_(True)
+        F.conv_transpose2d(xs, wr, None, stride=2).backward(_nhwc(du[b0:b0 + 8]).float())
+        worst = max(worst, _relmax(_nhwc(dx[b0:b0 + 8]), xs.grad))
+        refw += wr.grad.double()
+    assert worst < 6e-3, worst
+    err = ((dw.double() - refw).abs().max() / refw.abs().max()).item()
+    assert err < 1e-4, err

@@ -62,6 +62,39 @@ def test_port_matches_reference_configs0(golden_dir):
     assert np.array_equal(np.packbits(mask), g["argmax_packed"])
 
 
+def test_port_matches_reference_trajectory_head(golden_dir):
+    """The first 8 of the 100 reference train steps of tests/golden/trajectory_b4_128.npz (batch 4, 3x128x128,
+    Adam(lr=1e-4), UCA:338-346): the port driven by the same optimizer reproduces loss and gradient norm."""
+    g = _load(golden_dir, "trajectory_b4_128")
+    seed, B, H, W, steps = [int(v) for v in g["cfg"]]
+    assert steps == 100 and len(g["loss"]) == 100
+    sd = port.make_state_dict(seed=seed)
+    p = {k: (v.clone().requires_grad_(True) if v.dtype.is_floating_point and "running" not in k else v.clone())
+         for k, v in sd.items()}
+    opt = torch.optim.Adam([v for v in p.values() if v.requires_grad], lr=1e-4)
+    for s in range(8):
+        x, y = port.make_batch(1000 + s % 4, B, H, W)
+        opt.zero_grad()
+        loss = port.loss_fn(port.unet_forward(x, p, train=True), y)
+        loss.backward()
+        gn = torch.sqrt(sum((v.grad.double() ** 2).sum() for v in p.values() if v.requires_grad)).item()
+        opt.step()
+        assert abs(loss.item() - g["loss"][s]) < 2e-5 * abs(g["loss"][s]), (s, loss.item(), g["loss"][s])
+        assert abs(gn - g["grad_norm"][s]) < 1e-3 * g["grad_norm"][s], (s, gn, g["grad_norm"][s])
+
+
+def test_golden_b8_512_is_present_and_consistent(golden_dir):
+    """The benchmarked-tile-size fixture (8 x 3x512x512, from the unmodified reference): shape / key sanity here; the
+    port itself is re-checked against it at this size by bench-time tooling (a forward is ~10 s of CPU)."""
+    g = _load(golden_dir, "unetca_se_b8_512")
+    assert g["logits_sub"].shape == (8, 2, 64, 64) and g["eval_logits_sub"].shape == (8, 2, 64, 64)
+    assert g["argmax_packed"].size == 8 * 512 * 512 // 8
+    assert len(g["grad_norms"]) == 100 and len(g["keys"]) == 154
+    sd = port.make_state_dict(seed=4)
+    x, y = port.make_batch(4, 1, 512, 512)                 # the fixture generator is the one the golden was made with
+    assert x.shape == (1, 3, 512, 512) and list(sd.keys()) == [str(k) for k in g["keys"]]
+
+
 @pytest.mark.parametrize("n_in,n_out", [(4, 5), (12, 13), (24, 25), (6, 6), (2, 3)])
 def test_resize_guard_restatement(n_in, n_out):
     """The numpy restatement of the resize guard (two-tap bilinear, align_corners=False) == what torchvision's

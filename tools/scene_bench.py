@@ -35,6 +35,46 @@ def window(tile, spec, H, W, dev):
     return torch.where(inside, v * 1.7320508, torch.zeros((), device=dev))
 
 
+def run_scene(scene, core, halo, batch, precision, repeat, dev, rank=0, world=1):
+    """Tiled eval-mode inference of this rank's share of a hashed scene x scene image.  -> (ms of the last pass, number
+    of class-1 pixels, tiles of this rank, tiles in total, window size)."""
+    torch.manual_seed(0)
+    model = unetca_b200.UNet(3, 2, use_se=True).to(dev).set_precision(precision)
+    spec = tiling.TileSpec(core=core, halo=halo)
+    H = W = scene
+    # random-init weights: give the BatchNorm running statistics real values (a few train-mode forwards on scene
+    # windows, untimed) so that the eval-mode masks are not degenerate
+    model.train()
+    with torch.no_grad():
+        for k in range(8):
+            t0 = tiling.Tile(k, core * (k % max(1, scene // core)), core * (k % max(1, scene // core)), core, core)
+            wnd = window(t0, spec, H, W, dev)
+            model(torch.stack([wnd[:, :512, :512], wnd[:, 512:1024, 512:1024]]))
+    model.eval()
+    tiles = tiling.shard(tiling.plan(H, W, spec), rank, world)
+    out = torch.empty(len(tiles), core, core, dtype=torch.uint8, device=dev)     # this rank's cores
+
+    def one_pass():
+        k = 0
+        for t, m in tiling.predict_tiles(model, tiles, spec, lambda tl: window(tl, spec, H, W, dev), batch):
+            out[k, :t.h, :t.w] = m
+            k += 1
+
+    ms = None
+    for it in range(repeat):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        one_pass()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    ones = int((out == 1).sum().item())
+    return ms, ones, len(tiles), len(tiling.plan(H, W, spec)), spec.size
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scene", type=int, default=16384)
@@ -55,56 +95,23 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    torch.manual_seed(0)
-    model = unetca_b200.UNet(3, 2, use_se=True).to(dev).set_precision(a.precision)
-    spec = tiling.TileSpec(core=a.core, halo=a.halo)
     H = W = a.scene
-    # random-init weights: give the BatchNorm running statistics real values (a few train-mode forwards on scene
-    # windows, untimed) so that the eval-mode masks are not degenerate
-    model.train()
-    with torch.no_grad():
-        for k in range(8):
-            t0 = tiling.Tile(k, 1024 * k, 1024 * k, a.core, a.core)
-            model(torch.stack([window(t0, spec, H, W, dev)[:, :512, :512], window(t0, spec, H, W, dev)[:, 512:1024, 512:1024]]))
-    model.eval()
-    tiles = tiling.shard(tiling.plan(H, W, spec), rank, world)
-    out = torch.empty(len(tiles), a.core, a.core, dtype=torch.uint8, device=dev)     # this rank's cores
-
-    def one_pass():
-        k = 0
-        for t, m in tiling.predict_tiles(model, tiles, spec, lambda tl: window(tl, spec, H, W, dev), a.batch):
-            out[k, :t.h, :t.w] = m
-            k += 1
-
-    ms = None
-    for it in range(a.repeat):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        one_pass()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+    ms, ones, my_tiles, ntiles, size = run_scene(a.scene, a.core, a.halo, a.batch, a.precision, a.repeat, dev, rank, world)
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
-    ones = int((out == 1).sum().item())
-    if world > 1:
         t = torch.tensor([ones], device=dev, dtype=torch.int64)
         dist.all_reduce(t)
         ones = int(t.item())
     if rank == 0:
-        ntiles = len(tiling.plan(H, W, spec))
         print(json.dumps({
             "metric": "unet_ca_tiled_inference_megapixels_per_sec", "value": H * W / 1e6 / (ms / 1e3), "unit": "Mpx/s",
             "tiles_per_sec": ntiles / (ms / 1e3), "n_gpus": world, "ms": ms, "dtype": a.precision, "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[3]: {H}x{W} scene, core {a.core} + halo {a.halo} -> {spec.size}^2 windows, "
+            "config": {"workload": f"BASELINE configs[3]: {H}x{W} scene, core {a.core} + halo {a.halo} -> {size}^2 windows, "
                                    f"{ntiles} tiles round-robin over {world} GPU(s), {a.batch} tiles per forward, eval mode, "
                                    "window generation (coordinate hash) inside the timed region",
-                       "tiles_per_rank": len(tiles)},
+                       "tiles_per_rank": my_tiles},
             "class1_pixels": ones,
         }), flush=True)
     if world > 1:
