@@ -204,11 +204,15 @@ class KernelAccount:
         t.record()
         self.records.append((name, args, s, t))
 
-    def summary(self):
+    def summary(self, by_shape=False):
+        """Per entry point; by_shape: per (entry point, integer arguments) — one row per layer shape."""
         out = {}
         for name, args, s, t in self.records:
             cls, fl, by = _work(name, args, self.e, self.cin)
-            d = out.setdefault(name, {"class": cls, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "calls": 0})
+            key = name
+            if by_shape:
+                key = name + "(" + ",".join(str(a) for a in args[1:] if isinstance(a, int) and 0 < a <= 4096) + ")"
+            d = out.setdefault(key, {"class": cls, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "calls": 0})
             d["ms"] += s.elapsed_time(t); d["flops"] += fl; d["bytes"] += by; d["calls"] += 1
         return out
 
@@ -769,6 +773,8 @@ def main():
         if args.kernel_table and rank == 0:
             with open(args.kernel_table, "w") as f:
                 json.dump({k: {**v, "ms_per_step": v["ms"] / nk} for k, v in table.items()}, f, indent=1)
+            with open(args.kernel_table.replace(".json", "") + "_by_shape.json", "w") as f:
+                json.dump({k: {**v, "ms_per_step": v["ms"] / nk} for k, v in acct.summary(by_shape=True).items()}, f, indent=1)
 
     # ---- extras: the other BASELINE configs on this build ------------------------------------------------------
     extra = None

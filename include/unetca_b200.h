@@ -62,6 +62,15 @@ int unetca_conv3x3_fwd(int dtype, const void* x, int ldx, const void* w, int ldk
 /* the same convolution for narrow outputs (O % 64 == 0, H even) through the row-pair layout of the tcgen05 path
  * (csrc/conv_tc.cu, tc_conv3x3_pixn_kernel); w_pair [2*O][12*C] = unetca_pack_conv3x3_pair(w [O][ld]).  bf16 only. */
 int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_pair, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream);
+/* the 64 -> 64 channel layers (inc / conv4 second convs and their dgrads, UCA:84 at full resolution), H even: row-pair
+ * layout with the whole filter resident in shared memory and haloed lattice tiles (tc_conv3x3_rp64_kernel); w is the
+ * ordinary packed filter [64][ldk >= 576] of unetca_pack_conv3x3_weight.  bf16 only. */
+int unetca_conv3x3_fwd_rp64(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, float* stat_parts, int* nparts, void* stream);
+/* dgrad of a block's second conv (dy -> dA1, wd = dgrad-packed filter [O][ldk]) that also leaves the statistics of the
+ * ReLU + BatchNorm backward that follows (autograd of UCA:82-83): parts [*nparts][2][O] = (sum dz, sum dz*(y1 - mean)) with
+ * dz = dA1 * (scale*y1 + shift > 0), y1 the saved conv output — the input of unetca_bn_bwd_finalize, without the
+ * unetca_bn_bwd_reduce pass over dA1 and y1.  O % 128 == 0, or C = O = 64 with an even H; else UNETCA_ERR_UNSUPPORTED (-3). */
+int unetca_conv3x3_dgrad_bnstats(int dtype, const void* dy, int lddy, const void* wd, int ldk, void* da, int ldda, int B, int H, int W, int C, int O, const void* y1, int ldy1, const float* scale, const float* shift, const float* mean, float* parts, int* nparts, void* stream);
 int unetca_pack_conv3x3_pair(int dtype, const void* w, int ld, void* w_pair, int rows, int C, void* stream);
 /* the same convolution for exactly 64 output channels and C = 64 or 128 through the kw-stacked layout of the tcgen05 path
  * (csrc/conv_tc.cu, tc_conv3x3_kw_kernel: N = 3 kw taps x 64 channels, horizontal shift-add in the epilogue, filter
@@ -70,7 +79,8 @@ int unetca_conv3x3_fwd_kw(int dtype, const void* x, int ldx, const void* w_kw, v
 int unetca_pack_conv3x3_kw(int dtype, const void* w, int ld, void* w_kw, int C, void* stream);
 /* inference forms (bf16 tcgen05 path): conv3x3 + eval-mode BatchNorm folded to (scale, shift) by unetca_bn_fold_eval + ReLU
  * applied in the conv epilogue — UCA:81-86 under model.eval() (UCA:276) without writing the pre-activation tensor.
- * layout 0: w = packed filter [O][9*C], O % 128 == 0; 1: w = pair-packed filter, H even; 2: w = kw-stacked filter.
+ * layout 0: w = packed filter [O][9*C], O % 128 == 0; 1: w = pair-packed filter, H even; 2: w = kw-stacked filter;
+ * 3: w = packed filter, C = O = 64, H even (resident-filter row-pair kernel).
  * sq_parts (optional, layouts 0/1; zero-filled by the caller: B * unetca_num_sms() * O floats) receives the SE squeeze as
  * per-image partial channel sums [B][*nparts][O] of the stored activation, ready for unetca_se_fc */
 int unetca_conv3x3_bnrelu_fwd(int dtype, const void* x, int ldx, const void* w, int layout, void* y, int ldy, int B, int H, int W, int C, int O, const float* scale, const float* shift, float* sq_parts, int* nparts, void* stream);

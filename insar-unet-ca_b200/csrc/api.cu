@@ -10,6 +10,9 @@ extern "C" {
 int unetca_tc_conv3x3_fwd(const void*, int, const void*, int, void*, int, int, int, int, int, int, float*, void*);
 int unetca_tc_conv3x3_fwd_paired(const void*, int, const void*, void*, int, int, int, int, int, int, float*, void*);
 int unetca_tc_pack_pair(const void*, int, void*, int, int, void*);
+int unetca_tc_conv3x3_fwd_rp64(const void*, int, const void*, int, void*, int, int, int, int, float*, void*);
+int unetca_tc_conv3x3_dgrad_bnstats(const void*, int, const void*, int, void*, int, int, int, int, int, int, const void*, int,
+                                    const float*, const float*, const float*, float*, void*);
 int unetca_tc_conv3x3_fwd_kw(const void*, int, const void*, void*, int, int, int, int, int, float*, void*);
 int unetca_tc_pack_kw(const void*, int, void*, int, void*);
 int unetca_tc_conv3x3_bnrelu_fwd(const void*, int, const void*, int, void*, int, int, int, int, int, int, const float*, const float*, float*, void*);
@@ -66,6 +69,27 @@ int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_p
                               int C, int O, float* stat_parts, int* nparts, void* stream) {
     if (!use_tc(dtype)) { unetca::set_error("conv3x3_fwd_paired: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
     int rc = unetca_tc_conv3x3_fwd_paired(x, ldx, w_pair, y, ldy, B, H, W, C, O, stat_parts, stream);
+    if (rc < 0) return rc;
+    if (nparts) *nparts = rc;
+    return 0;
+}
+
+// 64 -> 64 channels, H even: resident-filter row-pair kernel on the ordinary packed filter [64][ldk] (bf16 tensor cores only)
+int unetca_conv3x3_fwd_rp64(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W,
+                            float* stat_parts, int* nparts, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("conv3x3_fwd_rp64: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int rc = unetca_tc_conv3x3_fwd_rp64(x, ldx, w, ldk, y, ldy, B, H, W, stat_parts, stream);
+    if (rc < 0) return rc;
+    if (nparts) *nparts = rc;
+    return 0;
+}
+
+// dgrad + ReLU/BatchNorm backward statistics of its output in one kernel (replaces the unetca_bn_bwd_reduce pass)
+int unetca_conv3x3_dgrad_bnstats(int dtype, const void* dy, int lddy, const void* wd, int ldk, void* da, int ldda, int B, int H,
+                                 int W, int C, int O, const void* y1, int ldy1, const float* scale, const float* shift,
+                                 const float* mean, float* parts, int* nparts, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("conv3x3_dgrad_bnstats: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int rc = unetca_tc_conv3x3_dgrad_bnstats(dy, lddy, wd, ldk, da, ldda, B, H, W, C, O, y1, ldy1, scale, shift, mean, parts, stream);
     if (rc < 0) return rc;
     if (nparts) *nparts = rc;
     return 0;

@@ -1029,15 +1029,29 @@ __device__ __forceinline__ void pixn_flush_sq(float* sq_parts, float* sm_sq, int
 // epilogue of the pixels-on-N kernel for one thread (= one accumulator row = one channel): 256 fp32 columns (pixels)
 // -> bf16 -> staging[pixel][channel] (2-byte stores; a warp covers 64 contiguous bytes per pixel), plus the
 // thread-local sum / sum of squares of the stored values.  PARTIAL masks pixels outside the image.
-template <bool PARTIAL>
+// BWD (haloed kernel only: 8-pixel-wide tiles): instead of sum / sum of squares, the ReLU + BatchNorm backward statistics
+// of the tensor being written, s1 = sum dz, s2 = sum dz * (y - mean) with dz = value * (ba*y + bb > 0) and y the saved
+// pre-BN conv output of the same pixel and channel (ybase -> this thread's channel at the tile's first pixel).
+template <bool PARTIAL, bool BWD = false>
 __device__ __forceinline__ void pixn_drain(uint32_t t_addr, uint32_t my_s, float& s1, float& s2, int x0, int i0,
                                            int twMask, int twShift, int W, int HP, bool act = false, float ea = 1.f,
-                                           float eb = 0.f) {
+                                           float eb = 0.f, const bf16* ybase = nullptr, long yrow = 0, int ypix = 0,
+                                           float ba = 0.f, float bb = 0.f, float bm = 0.f, int cb0 = 0, int ncb = 8) {
     float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
 #pragma unroll 1
-    for (int cb = 0; cb < 8; ++cb) {
+    for (int cb = cb0; cb < cb0 + ncb; ++cb) {
         uint32_t v[32];
         tmem_ld32(t_addr + cb * 32, v);
+        uint16_t yv[BWD ? 32 : 1];
+        if (BWD) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int n = cb * 32 + i;
+                const bool ok = !PARTIAL || ((x0 + (n & 7)) < W && (i0 + (n >> 3)) < HP);
+                yv[BWD ? i : 0] = ok ? __ldg(reinterpret_cast<const unsigned short*>(ybase + (n >> 3) * yrow + (long)(n & 7) * ypix))
+                                     : (uint16_t)0;
+            }
+        }
         tmem_wait_ld();
         const uint32_t base = my_s + cb * 32 * 128;
 #pragma unroll
@@ -1056,8 +1070,15 @@ __device__ __forceinline__ void pixn_drain(uint32_t t_addr, uint32_t my_s, float
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + i * 128), "h"((uint16_t)(pk & 0xffffu)) : "memory");
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(base + (i + 1) * 128), "h"((uint16_t)(pk >> 16)) : "memory");
             const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
-            a1 += r0; a2 = fmaf(r0, r0, a2);
-            b1 += r1; b2 = fmaf(r1, r1, b2);
+            if (BWD) {
+                const float y0 = __uint_as_float((uint32_t)yv[BWD ? i : 0] << 16), y1 = __uint_as_float((uint32_t)yv[BWD ? i + 1 : 0] << 16);
+                const float d0 = fmaf(ba, y0, bb) > 0.f ? r0 : 0.f, d1 = fmaf(ba, y1, bb) > 0.f ? r1 : 0.f;
+                a1 += d0; a2 = fmaf(d0, y0 - bm, a2);
+                b1 += d1; b2 = fmaf(d1, y1 - bm, b2);
+            } else {
+                a1 += r0; a2 = fmaf(r0, r0, a2);
+                b1 += r1; b2 = fmaf(r1, r1, b2);
+            }
         }
     }
     s1 = a1 + b1; s2 = a2 + b2;
@@ -1266,8 +1287,15 @@ struct alignas(64) HpixParams {
     const float* ep_scale;
     const float* ep_shift;
     float* sq_parts;             // optional [nimg][gridDim.x][N] per-image channel sums (SE squeeze of the activation)
+    // optional fused ReLU + BatchNorm backward statistics of the tensor being written (see pixn_drain<.., BWD>); the sums
+    // go to stat_parts in place of sum / sum of squares
+    const bf16* bwd_y;
+    int bwd_ldy;
+    const float* bwd_scale;
+    const float* bwd_shift;
+    const float* bwd_mean;
 };
-constexpr int kHpThreads = 224;
+constexpr int kHpThreads = 352;          // X producer, MMA issuer, eight epilogue warps, weight producer
 constexpr int kHpTW = 8, kHpTH = 32, kHpPitch = kHpTW + 2;
 constexpr int kHpXBox = kHpPitch * (kHpTH + 2) * 128;      // 43520 bytes written by TMA
 constexpr int kHpXBytes = 44 * 1024;                       // ring slot
@@ -1296,7 +1324,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
     if (threadIdx.x == 0) {
         for (int i = 0; i < kHpXS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
         for (int i = 0; i < kHpWS; ++i) { mbar_init(&wfull[i], 1); mbar_init(&wempty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
         fence_barrier_init();
         prefetch_tmap(&p.mapX);
         prefetch_tmap(&p.mapW);
@@ -1329,7 +1357,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
                 }
             }
         }
-    } else if (warp == 6) {
+    } else if (warp == 10) {
         // ================================ weight producer: one [128 rows][64] box per (chunk, tap) ============
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
@@ -1380,12 +1408,18 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
             }
         }
     } else {
-        // ================================ epilogue (warps 2..5): lane = channel, column = pixel ================
+        // ================================ epilogue (warps 2..9): lane = channel, column = pixel ================
+        // Eight warps: the drain is a dependent chain (TMEM load, convert, two 2-byte staging stores, statistics) that one
+        // warp per scheduler issues at ~0.35 instructions per cycle; at 128 input channels a tile's 72 MMAs do not cover
+        // it.  Warps w and w + 4 share a TMEM lane quarter and take 128 of the 256 pixel columns each; the second half hands
+        // its statistics to the first through shared memory (fixed order: run-to-run identical sums).
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;
         const int r = q * 32 + lane;
-        const int ep_tid = threadIdx.x - 64;
+        const int ep_tid = threadIdx.x - 64;      // 0..255
         const int box = r >> 6, oc = r & 63;
         const uint32_t my_s = smem_u32(out_stage + box * (256 * 128) + oc * 2);
+        float* sm_wpart = sm_stats + 2048;        // [2][128]
         int as = 0; uint32_t aph = 0;
         int cur_b = -1;
         for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
@@ -1398,41 +1432,346 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
             if (ep_tid == 0) tma_store_wait_read();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             float s1 = 0.f, s2 = 0.f;
             const bool act = p.ep_scale != nullptr;
             const float ea = act ? __ldg(p.ep_scale + mb * 128 + r) : 1.f, eb = act ? __ldg(p.ep_shift + mb * 128 + r) : 0.f;
-            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, act, ea, eb);
-            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, h0, kHpTW - 1, 3, p.W, p.H, act, ea, eb);
+            const int cb0 = chalf * 4;
+            if (p.bwd_y) {
+                const int ch = mb * 128 + r;
+                const bf16* ybase = p.bwd_y + (((long)b * p.H + h0) * p.W + x0) * p.bwd_ldy + ch;
+                const long yrow = (long)p.W * p.bwd_ldy;
+                const float ba = __ldg(p.bwd_scale + ch), bb = __ldg(p.bwd_shift + ch), bm = __ldg(p.bwd_mean + ch);
+                if (full) pixn_drain<false, true>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, false, 1.f, 0.f, ybase, yrow, p.bwd_ldy, ba, bb, bm, cb0, 4);
+                else pixn_drain<true, true>(t_addr, my_s, s1, s2, x0, h0, kHpTW - 1, 3, p.W, p.H, false, 1.f, 0.f, ybase, yrow, p.bwd_ldy, ba, bb, bm, cb0, 4);
+            } else if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, cb0, 4);
+            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, h0, kHpTW - 1, 3, p.W, p.H, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, cb0, 4);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (chalf == 1 && (p.stat_parts || p.sq_parts)) { sm_wpart[r] = s1; sm_wpart[128 + r] = s2; }
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             if (ep_tid == 0) {
                 tma_store_4d(&p.mapOut, out_stage, mb * 128, x0, h0, b);
                 tma_store_4d(&p.mapOut, out_stage + 256 * 128, mb * 128 + 64, x0, h0, b);
                 tma_store_commit();
             }
-            if (p.stat_parts) {
-                sm_stats[mb * 128 + r] += s1;
-                sm_stats[p.N + mb * 128 + r] += s2;
-            }
-            if (p.sq_parts) {
-                if (b != cur_b) {
-                    if (cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
-                    cur_b = b;
+            if (chalf == 0) {
+                if (p.stat_parts) {
+                    sm_stats[mb * 128 + r] += s1 + sm_wpart[r];
+                    sm_stats[p.N + mb * 128 + r] += s2 + sm_wpart[128 + r];
                 }
-                sm_stats[mb * 128 + r] += s1;
+                if (p.sq_parts) {
+                    if (b != cur_b) {
+                        if (cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
+                        cur_b = b;
+                    }
+                    sm_stats[mb * 128 + r] += s1 + sm_wpart[r];
+                }
             }
             as ^= 1; if (as == 0) aph ^= 1;
         }
-        if (p.sq_parts && cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
+        if (chalf == 0 && p.sq_parts && cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
         if (ep_tid == 0) tma_store_wait_all();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (p.stat_parts) {
             float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
-            for (int i = ep_tid; i < 2 * p.N; i += 128) dst[i] = sm_stats[i];
+            for (int i = ep_tid; i < 2 * p.N; i += 256) dst[i] = sm_stats[i];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv3x3 forward / dgrad for 64 -> 64 channels (the two full-resolution DoubleConv layers, 4 launches per step):
+// the row-pair layout of tc_conv3x3_pixn_kernel<P = 2> with the tap reuse of the haloed kernel and a RESIDENT filter.
+//   D[(j, o)][(i, x)] = sum_{vr, kw, c} Wv[(j, o)][vr][kw][c] * X[2(i0+i) + vr - 1][x0 + x + kw - 1][c]
+// M = 128 = 2 output rows of a row pair x 64 channels, N = 256 = 32 pair rows x 8 columns, 4 x 3 virtual taps of
+// which rows j use W[kh = vr - j] or zero (9 of 12 row blocks useful).  What bounded the per-tap kernel was shared-
+// memory fill: 12 x (16 KB weights + 32 KB pixels) per 48 MMAs = 94 B/cycle next to 96 B/cycle of operand reads.  Here:
+//   * the input rows of a tile are two haloed LATTICE tiles (even image rows 2i: vr = 1, 3; odd rows 2i+1: vr = 0, 2),
+//     each [33 lattice rows][10 px][64 ch] = 42 KB through the 5-D (C, W, parity, H/2, B) tensor map; the six taps of a
+//     lattice are K-major B descriptors into it, start shifted by (dv*10 + kw) pixel rows, SBO = 10 px = 1280 B (8 pixels
+//     of one pair row per 8-row group) — 84 KB of fill per tile instead of 384 KB;
+//   * the whole filter stays in shared memory as thirteen 8 KB blocks [64 o][64 c]:  Z b2 b1 b0 Z b2 b1 b0 Z b2 b1 b0 Z
+//     (one run per kw, b_kh = W[.][kh][kw][.], Z = zeros).  The A operand of virtual tap (vr, kw) is the 16 KB starting
+//     at block (run + 2 - vr): rows j = 0 read b_vr, rows j = 1 the next block b_(vr-1), and the out-of-range filter
+//     rows fall on a Z block — no pair-packed copy of the filter exists any more (TMA boxes of the ordinary [O][9*C]);
+//   * the epilogue writes its bf16 values straight to global memory (a warp = 32 channels of one pixel = 64 contiguous
+//     bytes, two full sectors): no staging tile, so the ~1500 wavefronts per tile of staging stores and TMA-store reads
+//     leave the shared-memory pipe to the MMA (operands 4608 + fill 660 wavefronts per 6144 MMA cycles).
+// Warps: 0 = producer, 1 = MMA issuer, 2..5 = epilogue.  ~190 KB of shared memory.
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) Rp64Params {
+    CUtensorMap mapX, mapW;
+    bf16* out;
+    int ldo;
+    int tilesW, tilesI, nimg, HP, W;
+    float* stat_parts;           // optional [gridDim.x][2][64]: sum / sum of squares of the stored values
+    const float* ep_scale;       // optional eval-mode BatchNorm + ReLU in the epilogue
+    const float* ep_shift;
+    float* sq_parts;             // optional [nimg][gridDim.x][64]: per-image channel sums of the stored activations (SE squeeze)
+    // optional fused ReLU + BatchNorm backward statistics of the tensor being written (dA1 = this dgrad's output):
+    // sum dz, sum dz * (y - mean) per channel with dz = dA1 * (a*y + b > 0), y = bwd_y (the saved pre-BN conv output)
+    const bf16* bwd_y;
+    int bwd_ldy;
+    const float* bwd_scale;
+    const float* bwd_shift;
+    const float* bwd_mean;
+};
+constexpr int kRpTW = 8, kRpTI = 32, kRpPitch = kRpTW + 2, kRpRows = kRpTI + 1;
+constexpr int kRpXBox = kRpPitch * kRpRows * 128;           // 42240 bytes written by TMA per lattice tile
+constexpr int kRpXBytes = 42 * 1024;                        // slot
+constexpr int kRpWBlock = 64 * 128;                         // [64 o][64 c] bf16
+constexpr int kRpWBytes = 13 * kRpWBlock;
+constexpr int kRpStatBytes = (2 * 64 + 2 * 256 + 64) * 4;
+constexpr int kRpSmemBytes = 1024 + kRpWBytes + 2 * kRpXBytes + kRpStatBytes + 256;
+static_assert(kRpSmemBytes <= 227 * 1024, "rp64 conv: shared memory budget");
+
+constexpr int kRpThreads = 320;          // producer, MMA issuer, eight epilogue warps
+
+// Epilogue of one thread (= one (j, channel) accumulator row) over the 128 columns [cb0*32, cb0*32 + 128): fp32 -> (BN + ReLU)
+// -> bf16 -> global memory (a warp = 32 channels of one pixel = 64 contiguous bytes), plus either sum / sum of squares of the
+// stored values or (BWD) the ReLU + BatchNorm backward statistics against the saved conv output of the same pixels.
+// Column n = (pair row i = n >> 3, x = n & 7).  FULL: the whole tile lies inside the image (no bounds checks).
+// LDO / LDY: compile-time pixel strides of the output / saved tensor (0 = take the run-time value) — with the two layouts the
+// model uses (dense 64, channel half of a 128-wide concat buffer) every store address is row pointer + immediate.
+template <bool FULL, bool BWD, int LDO, int LDY, bool ACT = false>
+__device__ __forceinline__ void rp64_drain(uint32_t t_addr, int cb0, bf16* __restrict__ obase, long row_stride, int ldo_rt, int ni,
+                                           int nx, bool act_rt, float ea, float eb, const bf16* __restrict__ ybase, long yrow_stride,
+                                           int ldy_rt, float ba, float bb, float bm, float& s1, float& s2) {
+    const int ldo = LDO ? LDO : ldo_rt, ldy = LDY ? LDY : ldy_rt;
+    const bool act = ACT || (!FULL && act_rt);          // the inference epilogue: specialised on full tiles, run-time flag on partial ones
+    float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+#pragma unroll 1
+    for (int cb = cb0; cb < cb0 + 4; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + cb * 32, v);
+        unsigned short yv[BWD ? 32 : 1];
+        if (BWD) {
+            // the saved conv output of the same 32 pixels: all loads in flight before the accumulator wait
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+                const unsigned short* yrow = reinterpret_cast<const unsigned short*>(ybase + (long)(cb * 4 + ii) * yrow_stride);
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                    const bool ok = FULL || ((cb * 4 + ii) < ni && x < nx);
+                    yv[BWD ? ii * 8 + x : 0] = ok ? __ldg(yrow + x * ldy) : (unsigned short)0;
+                }
+            }
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            unsigned short* prow = reinterpret_cast<unsigned short*>(obase + (long)(cb * 4 + ii) * row_stride);
+            const bool rok = FULL || (cb * 4 + ii) < ni;
+#pragma unroll
+            for (int x = 0; x < 8; x += 2) {
+                float f0 = __uint_as_float(v[ii * 8 + x]), f1 = __uint_as_float(v[ii * 8 + x + 1]);
+                if (act) {
+                    f0 = fmaxf(fmaf(ea, f0, eb), 0.f);
+                    f1 = fmaf(ea, f1, eb); f1 = fmaxf(f1, 0.f);
+                }
+                const bool ok0 = rok && (FULL || x < nx), ok1 = rok && (FULL || x + 1 < nx);
+                if (!FULL) { if (!ok0) f0 = 0.f; if (!ok1) f1 = 0.f; }
+                const uint32_t pk = pack_bf16x2(f0, f1);
+                if (ok0) prow[x * ldo] = (unsigned short)(pk & 0xffffu);
+                if (ok1) prow[(x + 1) * ldo] = (unsigned short)(pk >> 16);
+                const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+                if (BWD) {
+                    const float y0 = __uint_as_float((uint32_t)yv[BWD ? ii * 8 + x : 0] << 16);
+                    const float y1 = __uint_as_float((uint32_t)yv[BWD ? ii * 8 + x + 1 : 0] << 16);
+                    const float d0 = fmaf(ba, y0, bb) > 0.f ? r0 : 0.f, d1 = fmaf(ba, y1, bb) > 0.f ? r1 : 0.f;
+                    a1 += d0; a2 = fmaf(d0, y0 - bm, a2);
+                    b1 += d1; b2 = fmaf(d1, y1 - bm, b2);
+                } else {
+                    a1 += r0; a2 = fmaf(r0, r0, a2);
+                    b1 += r1; b2 = fmaf(r1, r1, b2);
+                }
+            }
+        }
+    }
+    s1 = a1 + b1; s2 = a2 + b2;
+}
+
+__global__ void __launch_bounds__(kRpThreads, 1) tc_conv3x3_rp64_kernel(const __grid_constant__ Rp64Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* w_res = smem;
+    uint8_t* x_ring = smem + kRpWBytes;
+    float* sm_stats = reinterpret_cast<float*>(x_ring + 2 * kRpXBytes);      // [2][64]
+    float* sm_wpart = sm_stats + 128;                                         // [2][256]
+    float* sm_sq = sm_wpart + 512;                                            // [64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(x_ring + 2 * kRpXBytes + kRpStatBytes);
+    uint64_t* xfull = bars;            // [2]
+    uint64_t* xempty = bars + 2;       // [2]
+    uint64_t* wfull = bars + 4;
+    uint64_t* tfull_bar = bars + 5;    // [2]
+    uint64_t* tempty_bar = bars + 7;   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
+        mbar_init(wfull, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapW);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    // the four zero blocks of the resident filter (blocks 0, 4, 8, 12) and the statistics
+    for (int i = threadIdx.x; i < 4 * (kRpWBlock / 16); i += kRpThreads) {
+        const int blk = (i / (kRpWBlock / 16)) * 4, off = (i % (kRpWBlock / 16)) * 16;
+        *reinterpret_cast<uint4*>(w_res + blk * kRpWBlock + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int i = threadIdx.x; i < kRpStatBytes / 4; i += kRpThreads) sm_stats[i] = 0.f;
+    fence_proxy_async_smem();
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesI;
+    const long num_work = (long)tiles_per_img * p.nimg;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // the filter, once: block (kh, kw) of the packed [64][9*64] matrix -> slot 1 + 4*kw + (2 - kh)
+            mbar_expect_tx(wfull, 9 * kRpWBlock);
+            for (int kh = 0; kh < 3; ++kh)
+                for (int kw = 0; kw < 3; ++kw)
+                    tma_load_4d(&p.mapW, wfull, w_res + (1 + 4 * kw + (2 - kh)) * kRpWBlock, (kh * 3 + kw) * 64, 0, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int tw = (int)(t % p.tilesW), ti = (int)((t / p.tilesW) % p.tilesI), b = (int)(t / tiles_per_img);
+                const int x0 = tw * kRpTW, i0 = ti * kRpTI;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    // half 0: even lattice rows i0 .. i0+32 (vr = 1, 3); half 1: odd lattice rows i0-1 .. i0+31 (vr = 0, 2)
+                    mbar_wait(&xempty[s], ph ^ 1);
+                    mbar_expect_tx(&xfull[s], kRpXBox);
+                    tma_load_5d(&p.mapX, &xfull[s], x_ring + s * kRpXBytes, 0, x0 - 1, half, i0 - half, b);
+                    if (++s == 2) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+            mbar_wait(wfull, 0);
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            const uint32_t wb = smem_u32(w_res);
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&xfull[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t xa = smem_u32(x_ring + s * kRpXBytes);
+#pragma unroll
+                    for (int dv = 0; dv < 2; ++dv) {
+                        const int vr = half == 0 ? 1 + 2 * dv : 2 * dv;
+#pragma unroll
+                        for (int kw = 0; kw < 3; ++kw) {
+                            const uint32_t sa = wb + (uint32_t)(1 + 4 * kw + 2 - vr) * kRpWBlock;
+                            const uint32_t sb = xa + (uint32_t)(dv * kRpPitch + kw) * 128;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16, 1024),
+                                          make_smem_desc(sb + k * 32, 16, kRpPitch * 128), idesc, (half | dv | kw | k) != 0);
+                        }
+                    }
+                    umma_commit(&xempty[s]);
+                    if (++s == 2) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+                as ^= 1; if (as == 0) aph ^= 1;
+            }
+        }
+    } else {
+        // ================================ epilogue (warps 2..9) =======================================================
+        // TMEM lane = (j, channel); warps w and w + 4 share a lane quarter and take 128 of the 256 columns (pair row, x) each
+        const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        const int ep_tid = threadIdx.x - 64;     // 0..255
+        const int j = r >> 6, oc = r & 63;
+        const bool act = p.ep_scale != nullptr;
+        const float ea = act ? __ldg(p.ep_scale + oc) : 1.f, eb = act ? __ldg(p.ep_shift + oc) : 0.f;
+        const bool bwd = p.bwd_y != nullptr;
+        const float ba = bwd ? __ldg(p.bwd_scale + oc) : 0.f, bb = bwd ? __ldg(p.bwd_shift + oc) : 0.f;
+        const float bm = bwd ? __ldg(p.bwd_mean + oc) : 0.f;
+        const long row_stride = 2L * p.W * p.ldo;                             // one pair row down
+        const long yrow_stride = 2L * p.W * p.bwd_ldy;
+        int as = 0; uint32_t aph = 0;
+        int cur_b = -1;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int tw = (int)(t % p.tilesW), ti = (int)((t / p.tilesW) % p.tilesI), b = (int)(t / tiles_per_img);
+            const int x0 = tw * kRpTW, i0 = ti * kRpTI;
+            mbar_wait(&tfull_bar[as], aph);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            // element (i, x) of this thread's channel: out[((b*H + 2*(i0+i) + j) * W + x0 + x) * ldo + oc]
+            const long pix0 = ((long)b * 2 * p.HP + 2 * i0 + j) * p.W + x0;
+            bf16* obase = p.out + pix0 * p.ldo + oc;
+            const bf16* ybase = bwd ? p.bwd_y + pix0 * p.bwd_ldy + oc : nullptr;
+            const int nx = p.W - x0 < kRpTW ? p.W - x0 : kRpTW;              // valid columns
+            const int ni = p.HP - i0 < kRpTI ? p.HP - i0 : kRpTI;            // valid pair rows
+            const bool full = nx == kRpTW && ni == kRpTI;
+            float a1, a2;
+            if (bwd) {
+                if (full && p.ldo == 64 && p.bwd_ldy == 64)
+                    rp64_drain<true, true, 64, 64>(t_addr, chalf * 4, obase, row_stride, 64, ni, nx, false, 1.f, 0.f, ybase, yrow_stride, 64, ba, bb, bm, a1, a2);
+                else if (full) rp64_drain<true, true, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, false, 1.f, 0.f, ybase, yrow_stride, p.bwd_ldy, ba, bb, bm, a1, a2);
+                else rp64_drain<false, true, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, false, 1.f, 0.f, ybase, yrow_stride, p.bwd_ldy, ba, bb, bm, a1, a2);
+            } else {
+                if (full && act) rp64_drain<true, false, 0, 0, true>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, true, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, a1, a2);
+                else if (full && p.ldo == 64) rp64_drain<true, false, 64, 0>(t_addr, chalf * 4, obase, row_stride, 64, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, a1, a2);
+                else if (full && p.ldo == 128) rp64_drain<true, false, 128, 0>(t_addr, chalf * 4, obase, row_stride, 128, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, a1, a2);
+                else if (full) rp64_drain<true, false, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, a1, a2);
+                else rp64_drain<false, false, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, a1, a2);
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (p.stat_parts) {
+                sm_wpart[chalf * 128 + r] = a1; sm_wpart[256 + chalf * 128 + r] = a2;
+                named_bar_sync(1, 256);
+                if (ep_tid < 64) {
+                    sm_stats[ep_tid] += (sm_wpart[ep_tid] + sm_wpart[ep_tid + 64]) + (sm_wpart[128 + ep_tid] + sm_wpart[192 + ep_tid]);
+                    sm_stats[64 + ep_tid] += (sm_wpart[256 + ep_tid] + sm_wpart[320 + ep_tid]) + (sm_wpart[384 + ep_tid] + sm_wpart[448 + ep_tid]);
+                }
+                named_bar_sync(1, 256);
+            }
+            if (p.sq_parts) {
+                // SE squeeze of the stored activation: per-image channel sums, flushed when this CTA moves to the next image
+                if (b != cur_b) {
+                    if (cur_b >= 0 && ep_tid < 64) {
+                        p.sq_parts[((long)cur_b * gridDim.x + blockIdx.x) * 64 + ep_tid] = sm_sq[ep_tid];
+                        sm_sq[ep_tid] = 0.f;
+                    }
+                    cur_b = b;
+                }
+                sm_wpart[chalf * 128 + r] = a1;
+                named_bar_sync(1, 256);
+                if (ep_tid < 64) sm_sq[ep_tid] += (sm_wpart[ep_tid] + sm_wpart[ep_tid + 64]) + (sm_wpart[128 + ep_tid] + sm_wpart[192 + ep_tid]);
+                named_bar_sync(1, 256);
+            }
+            as ^= 1; if (as == 0) aph ^= 1;
+        }
+        if (p.sq_parts && cur_b >= 0 && ep_tid < 64) p.sq_parts[((long)cur_b * gridDim.x + blockIdx.x) * 64 + ep_tid] = sm_sq[ep_tid];
+        named_bar_sync(1, 256);
+        if (p.stat_parts) {
+            float* dst = p.stat_parts + (long)blockIdx.x * 128;
+            if (ep_tid < 128) dst[ep_tid] = sm_stats[ep_tid];
         }
     }
     tcgen05_fence_before();
@@ -1830,10 +2169,13 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int elem_bytes, long C, lon
     return 0;
 }
 
+// fused ReLU + BatchNorm backward statistics of a dgrad's output (saved pre-BN conv output y + the BN constants)
+struct BwdStats { const void* y; int ldy; const float* scale; const float* shift; const float* mean; };
+
 // conv3x3 forward / dgrad for O % 128 == 0 through the haloed pixels-on-N kernel; w = packed filter [O][9*C]
 static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
                        float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr,
-                       float* sq_parts = nullptr) {
+                       float* sq_parts = nullptr, const BwdStats* bwd = nullptr) {
     HpixParams p;
     memset(&p, 0, sizeof(p));
     int rc;
@@ -1844,6 +2186,10 @@ static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, 
     p.cchunks = C / 64; p.num_m_blocks = O / 128;
     p.stat_parts = stat_parts; p.N = O;
     p.ep_scale = ep_scale; p.ep_shift = ep_shift; p.sq_parts = sq_parts;
+    if (bwd) {
+        p.bwd_y = (const bf16*)bwd->y; p.bwd_ldy = bwd->ldy;
+        p.bwd_scale = bwd->scale; p.bwd_shift = bwd->shift; p.bwd_mean = bwd->mean;
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_hpix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHpSmemBytes);
@@ -2012,6 +2358,38 @@ static int launch_first_pairs(const void* colp, const void* wp, void* y, int ldy
     return launch_pixn_kernel(p, CL, st, "tc_first_pairs_fwd");
 }
 
+// conv3x3 forward / dgrad, 64 -> 64 channels, H even: resident-filter row-pair kernel; w = packed filter [64][ldk >= 576]
+static int launch_rp64(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W,
+                       float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr,
+                       float* sq_parts = nullptr, const BwdStats* bwd = nullptr) {
+    Rp64Params p;
+    memset(&p, 0, sizeof(p));
+    const int HP = H / 2;
+    int rc;
+    if ((rc = make_map5(&p.mapX, x, 64, W, H, B, ldx, 2, kRpPitch, kRpRows, true)) < 0) return rc;
+    if ((rc = make_map(&p.mapW, w, 9L * 64, 64, 1, 1, ldk, 64L * ldk, 64L * ldk, 64, 1)) < 0) return rc;
+    p.out = (bf16*)y; p.ldo = ldy;
+    p.tilesW = ceil_div(W, kRpTW); p.tilesI = ceil_div(HP, kRpTI); p.nimg = B; p.HP = HP; p.W = W;
+    p.stat_parts = stat_parts;
+    p.ep_scale = ep_scale; p.ep_shift = ep_shift; p.sq_parts = sq_parts;
+    if (bwd) {
+        p.bwd_y = (const bf16*)bwd->y; p.bwd_ldy = bwd->ldy;
+        p.bwd_scale = bwd->scale; p.bwd_shift = bwd->shift; p.bwd_mean = bwd->mean;
+    }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_rp64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes);
+        if (e != cudaSuccess) { set_error("tc_conv3x3 (rp64): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    const long num_work = (long)p.tilesW * p.tilesI * B;
+    long grid = num_work < num_sms() ? num_work : num_sms();
+    if (grid < 1) grid = 1;
+    tc_conv3x3_rp64_kernel<<<(int)grid, kRpThreads, kRpSmemBytes, st>>>(p);
+    rc = check_launch("tc_conv3x3_fwd (rp64)");
+    return rc < 0 ? rc : (int)grid;
+}
+
 static void set_taps3x3(TcParams& p) {
     for (int t = 0; t < 9; ++t) { p.dh[t] = (signed char)(t / 3 - 1); p.dw[t] = (signed char)(t % 3 - 1); p.amap[t] = 0; }
 }
@@ -2035,6 +2413,29 @@ int unetca_tc_conv3x3_fwd_paired(const void* x, int ldx, const void* w_pair, voi
     UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0 && O <= 1024 && H % 2 == 0,
                    "tc_conv3x3_paired: C=%d O=%d must be multiples of 64 and H=%d even", C, O, H);
     return launch_pixn(x, ldx, w_pair, 12 * C, y, ldy, B, H, W, C, O, 2, stat_parts, (cudaStream_t)stream);
+}
+
+// conv3x3 forward / dgrad for 64 -> 64 channels (H even) through the resident-filter row-pair kernel; w = packed filter [64][ldk]
+int unetca_tc_conv3x3_fwd_rp64(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W,
+                               float* stat_parts, void* stream) {
+    UNETCA_REQUIRE(H % 2 == 0 && ldk >= 576, "tc_conv3x3_rp64: H=%d must be even, ldk=%d >= 576", H, ldk);
+    return launch_rp64(x, ldx, w, ldk, y, ldy, B, H, W, stat_parts, (cudaStream_t)stream);
+}
+
+// dgrad conv3x3 (x = dY, w = dgrad-packed filter [O][9*C], y = dA) that also leaves the ReLU + BatchNorm backward
+// statistics of dA in stat_parts [ret][2][O]: sum dz, sum dz*(y1 - mean), dz = dA * (scale*y1 + shift > 0).
+// O % 128 == 0 (haloed kernel) or C == O == 64 with an even H (row-pair kernel); otherwise UNETCA_ERR_UNSUPPORTED.
+int unetca_tc_conv3x3_dgrad_bnstats(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W,
+                                    int C, int O, const void* y1, int ldy1, const float* scale, const float* shift,
+                                    const float* mean, float* stat_parts, void* stream) {
+    UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0 && O <= 1024 && y1 && scale && shift && mean && stat_parts,
+                   "tc_conv3x3_dgrad_bnstats: C=%d O=%d", C, O);
+    BwdStats bs{y1, ldy1, scale, shift, mean};
+    if (O % 128 == 0) return launch_hpix(x, ldx, w, ldk, y, ldy, B, H, W, C, O, stat_parts, (cudaStream_t)stream, nullptr, nullptr, nullptr, &bs);
+    if (C == 64 && O == 64 && H % 2 == 0)
+        return launch_rp64(x, ldx, w, ldk, y, ldy, B, H, W, stat_parts, (cudaStream_t)stream, nullptr, nullptr, nullptr, &bs);
+    set_error("tc_conv3x3_dgrad_bnstats: no fused kernel for C=%d O=%d H=%d", C, O, H);
+    return UNETCA_ERR_UNSUPPORTED;
 }
 
 // conv3x3 forward / dgrad for 64 output channels (C = 64 or 128) through the kw-stacked kernel
@@ -2070,6 +2471,9 @@ int unetca_tc_conv3x3_bnrelu_fwd(const void* x, int ldx, const void* w, int layo
     } else if (layout == 1) {
         UNETCA_REQUIRE(H % 2 == 0, "tc_conv3x3_bnrelu: layout 1 needs an even H (H=%d)", H);
         rc = launch_pixn(x, ldx, w, 12 * C, y, ldy, B, H, W, C, O, 2, nullptr, st, scale, shift, sq_parts);
+    } else if (layout == 3) {
+        UNETCA_REQUIRE(H % 2 == 0 && C == 64 && O == 64, "tc_conv3x3_bnrelu: layout 3 needs C = O = 64 and an even H (C=%d O=%d H=%d)", C, O, H);
+        rc = launch_rp64(x, ldx, w, 9 * C, y, ldy, B, H, W, nullptr, st, scale, shift, sq_parts);
     } else {
         UNETCA_REQUIRE(O == 64 && C == 128 && !sq_parts, "tc_conv3x3_bnrelu: layout 2 needs O = 64, C = 128, no squeeze sums (O=%d C=%d)", O, C);
         rc = launch_kw(x, ldx, w, y, ldy, B, H, W, C, nullptr, st, scale, shift);

@@ -210,14 +210,18 @@ class _Engine:
             # layout ("kw", filter resident in shared memory) wins: its epilogue reads three accumulator columns per
             # output from TMEM (64 B/cycle/SM) and only hides behind a mainloop of >= 2 channel chunks
             if O % 128:
-                if O == 64 and C == 128:
+                if O == 64 and C == 64:
+                    wfp = ("rp64", None)            # resident-filter row-pair kernel: reads the ordinary packed filter
+                elif O == 64 and C == 128:
                     wfp = wfp or ("kw", torch.empty(9 * C, 64, dtype=tdt, device=w.device))
                     _lib.call("unetca_pack_conv3x3_kw", dt, _ptr(wf), ldk, _ptr(wfp[1]), C, st)
                 else:
                     wfp = wfp or ("pair", torch.empty(2 * O, 12 * C, dtype=tdt, device=w.device))
                     _lib.call("unetca_pack_conv3x3_pair", dt, _ptr(wf), ldk, _ptr(wfp[1]), O, C, st)
             if C % 128:
-                if C == 64 and O == 128:
+                if C == 64 and O == 64:
+                    wdp = ("rp64", None)
+                elif C == 64 and O == 128:
                     wdp = wdp or ("kw", torch.empty(9 * O, 64, dtype=tdt, device=w.device))
                     _lib.call("unetca_pack_conv3x3_kw", dt, _ptr(wd), 9 * O, _ptr(wdp[1]), O, st)
                 else:
@@ -280,7 +284,9 @@ class _Engine:
 def _conv3x3(dt, x, ldx, w, ldk, w_pair, y, ldy, B, H, W, C, O, sp, nparts, st):
     """conv3x3 forward (or dgrad with the dgrad-packed filter): row-pair tcgen05 layout when a pair-packed filter exists."""
     tc = _lib.load().unetca_get_conv_impl() == 0
-    if isinstance(w_pair, tuple) and w_pair[0] == "kw" and tc:
+    if isinstance(w_pair, tuple) and w_pair[0] == "rp64" and H % 2 == 0 and tc:
+        _lib.call("unetca_conv3x3_fwd_rp64", dt, _ptr(x), ldx, _ptr(w), ldk, _ptr(y), ldy, B, H, W, sp, nparts, st)
+    elif isinstance(w_pair, tuple) and w_pair[0] == "kw" and tc:
         _lib.call("unetca_conv3x3_fwd_kw", dt, _ptr(x), ldx, _ptr(w_pair[1]), _ptr(y), ldy, B, H, W, C, sp, nparts, st)
     elif isinstance(w_pair, tuple) and w_pair[0] == "pair" and H % 2 == 0 and tc:
         _lib.call("unetca_conv3x3_fwd_paired", dt, _ptr(x), ldx, _ptr(w_pair[1]), _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
@@ -294,6 +300,7 @@ def sv_pairs(col, B, H, W):
 
 
 FUSE_SQUEEZE = True      # inference: take the SE squeeze in the second conv's epilogue (False: separate read-only pass)
+FUSE_BN_BWD_STATS = True  # training: BN1-backward statistics in the epilogue of the dgrad conv that writes dA1 (False: reduce pass)
 
 
 def _conv3x3_bnrelu(dt, x, ldx, w, w_pair, y, ldy, B, H, W, C, O, scale, shift, st, sq_parts=None, nparts=None):
@@ -301,7 +308,9 @@ def _conv3x3_bnrelu(dt, x, ldx, w, w_pair, y, ldy, B, H, W, C, O, scale, shift, 
     Returns False when this shape has no fused kernel (the caller then runs conv and bn_relu separately)."""
     if dt != _lib.BF16 or _lib.load().unetca_get_conv_impl() != 0:
         return False
-    if isinstance(w_pair, tuple) and w_pair[0] == "kw":
+    if isinstance(w_pair, tuple) and w_pair[0] == "rp64" and H % 2 == 0:
+        layout, wt = 3, w
+    elif isinstance(w_pair, tuple) and w_pair[0] == "kw":
         layout, wt = 2, w_pair[1]
     elif isinstance(w_pair, tuple) and w_pair[0] == "pair" and H % 2 == 0:
         layout, wt = 1, w_pair[1]
@@ -636,7 +645,7 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
         G.put(pre + ".6.fc.2.weight")
         s = sv.s
 
-    def bn_relu_bwd(d_in, ld_in, y, tag, s_, dp_, bn_idx, sums_=None):
+    def bn_relu_bwd(d_in, ld_in, y, tag, s_, dp_, bn_idx, sums_=None, have_parts=False):
         scale, shift = getattr(sv, "scale" + tag), getattr(sv, "shift" + tag)
         mean, invstd = getattr(sv, "mean" + tag), getattr(sv, "invstd" + tag)
         bn = blk.bn1 if tag == "1" else blk.bn2
@@ -647,8 +656,9 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
             _lib.call("unetca_bn_bwd_finalize_se", _ptr(sums_), B, O, npix, Hl * Wl, _ptr(bn.weight), _ptr(invstd), _ptr(s_),
                       _ptr(dp_), _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
         else:
-            _lib.call("unetca_bn_bwd_reduce", dt, _ptr(d_in), ld_in, _ptr(y), O, B, Hl * Wl, O, _ptr(scale), _ptr(shift),
-                      _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(parts), ctypes.byref(nparts), st)
+            if not have_parts:               # (else: the dgrad conv that wrote d_in left the statistics in `parts` already)
+                _lib.call("unetca_bn_bwd_reduce", dt, _ptr(d_in), ld_in, _ptr(y), O, B, Hl * Wl, O, _ptr(scale), _ptr(shift),
+                          _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(parts), ctypes.byref(nparts), st)
             _lib.call("unetca_bn_bwd_finalize", _ptr(parts), nparts.value, O, npix, _ptr(bn.weight), _ptr(invstd),
                       _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
         if not sv.train:
@@ -683,10 +693,18 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
     G.put(pre + ".3.weight")
     _, wd2, _, _, wdp2 = eng.conv_w(blk.conv2, dt, tdt, False)
     da1 = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
-    _conv3x3(dt, dy2, O, wd2, 9 * O, wdp2, da1, O, B, Hl, Wl, O, O, None, None, st)
+    # bf16 tensor-core path: the dgrad's epilogue also takes the statistics of the ReLU + BN1 backward that follows (it holds
+    # every dA1 value it writes; the saved Y1 of the same pixels is read from L2 / HBM under the MMAs) — no reduce pass
+    fused_stats = (FUSE_BN_BWD_STATS and dt == _lib.BF16 and _lib.load().unetca_get_conv_impl() == 0 and
+                   (O % 128 == 0 or (O == 64 and Hl % 2 == 0)))
+    if fused_stats:
+        _lib.call("unetca_conv3x3_dgrad_bnstats", dt, _ptr(dy2), O, _ptr(wd2), 9 * O, _ptr(da1), O, B, Hl, Wl, O, O, _ptr(sv.y1), O,
+                  _ptr(sv.scale1), _ptr(sv.shift1), _ptr(sv.mean1), _ptr(parts), ctypes.byref(nparts), st)
+    else:
+        _conv3x3(dt, dy2, O, wd2, 9 * O, wdp2, da1, O, B, Hl, Wl, O, O, None, None, st)
     del dy2
     # ---- ReLU -> BN1 backward
-    dy1 = bn_relu_bwd(da1, O, sv.y1, "1", None, None, 1)
+    dy1 = bn_relu_bwd(da1, O, sv.y1, "1", None, None, 1, have_parts=fused_stats)
     del da1
     if sv.train:
         G.alloc(pre + ".0.bias", blk.conv1.bias).zero_()

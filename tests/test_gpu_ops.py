@@ -344,9 +344,98 @@ def test_conv3x3_tcgen05(B, C, O, H, W):
     _conv_case(BF16, 0, B, C, O, H, W)
 
 
+@pytest.mark.parametrize("B,H,W", [(2, 16, 16), (1, 64, 8), (3, 40, 72), (1, 130, 34), (2, 128, 160), (70, 16, 16)])
+def test_conv3x3_rp64_resident_filter(B, H, W):
+    """64 -> 64 channels through tc_conv3x3_rp64_kernel (row pairs, resident filter, haloed lattice tiles, direct global
+    stores): forward + BatchNorm partial sums, and as a dgrad, vs conv2d on the bf16-rounded operands; partial tiles in both
+    directions (W % 8, (H/2) % 32), untouched neighbours of a channel-slice output."""
+    dt, C, O = BF16, 64, 64
+    rs = np.random.RandomState(B * 1000 + H + W)
+    call("unetca_set_conv_impl", 0)
+    x = torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((O, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32))
+    dy = torch.from_numpy(rs.standard_normal((B, O, H, W)).astype(np.float32))
+    xr, wr, dyr = rounded(x, dt).requires_grad_(True), rounded(w, dt), rounded(dy, dt)
+    ref = F.conv2d(xr, wr, None, padding=1)
+    ref.backward(dyr)
+    xd, dyd = to_nhwc(x, dt), to_nhwc(dy, dt)
+    wf = torch.empty(O, 9 * C, dtype=TDT[dt], device="cuda")
+    wdg = torch.empty(C, 9 * O, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_conv3x3_weight", dt, ptr(w.cuda()), ptr(wf), 9 * C, ptr(wdg), O, C, stream())
+    # output = the lower channel half of a wider buffer (ld = 128): the upper half must stay untouched
+    buf = torch.full((B, H, W, 2 * O), 7.0, dtype=TDT[dt], device="cuda")
+    y = buf[..., :O]
+    parts = parts_buf(B)
+    n = cint()
+    call("unetca_conv3x3_fwd_rp64", dt, ptr(xd), C, ptr(wf), 9 * C, ptr(y), 2 * O, B, H, W, ptr(parts), ctypes.byref(n), stream())
+    got = from_nhwc(y.contiguous())
+    assert relerr(got, ref.detach()) < TOL[dt]
+    assert bool((buf[..., O:] == 7.0).all())
+    st = parts[: n.value * 2 * O].view(n.value, 2, O).sum(0).cpu()
+    assert relerr(st[0], got.sum((0, 2, 3))) < 1e-3 and relerr(st[1], (got * got).sum((0, 2, 3))) < 1e-3
+    dx = torch.full((B, H, W, C), float("nan"), dtype=TDT[dt], device="cuda")
+    call("unetca_conv3x3_fwd_rp64", dt, ptr(dyd), O, ptr(wdg), 9 * O, ptr(dx), C, B, H, W, None, None, stream())
+    assert relerr(from_nhwc(dx), xr.grad) < TOL[dt]
+    # bit-identical to the per-tap row-pair kernel it replaces? (same products, fp32 accumulation order differs) -> close
+    wp = torch.empty(2 * O, 12 * C, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_conv3x3_pair", dt, ptr(wf), 9 * C, ptr(wp), O, C, stream())
+    y2 = torch.empty(B, H, W, O, dtype=TDT[dt], device="cuda")
+    call("unetca_conv3x3_fwd_paired", dt, ptr(xd), C, ptr(wp), ptr(y2), O, B, H, W, C, O, None, None, stream())
+    assert relerr(from_nhwc(y2), got) < 1e-2
+
+
+@pytest.mark.parametrize("B,C,O,H,W", [(2, 64, 64, 16, 16), (3, 64, 64, 40, 72), (1, 64, 64, 130, 34), (2, 128, 128, 40, 24),
+                                       (1, 256, 256, 33, 17), (3, 128, 128, 8, 8), (2, 512, 512, 16, 16)])
+def test_conv3x3_dgrad_with_fused_bn_backward_statistics(B, C, O, H, W):
+    """unetca_conv3x3_dgrad_bnstats: same dA1 as the plain dgrad, and its partial sums finalize to the same dgamma / dbeta /
+    coefficients as the unetca_bn_bwd_reduce pass over (dA1, Y1) it replaces (autograd of UCA:82-84)."""
+    dt = BF16
+    rs = np.random.RandomState(C + H)
+    call("unetca_set_conv_impl", 0)
+    dy = torch.from_numpy(rs.standard_normal((B, O, H, W)).astype(np.float32))
+    w = torch.from_numpy((rs.standard_normal((O, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32))
+    y1 = to_nhwc(torch.from_numpy((0.3 + rs.standard_normal((B, C, H, W))).astype(np.float32)), dt)
+    dyd = to_nhwc(dy, dt)
+    wf = torch.empty(O, 9 * C, dtype=TDT[dt], device="cuda")
+    wdg = torch.empty(C, 9 * O, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_conv3x3_weight", dt, ptr(w.cuda()), ptr(wf), 9 * C, ptr(wdg), O, C, stream())
+    scale = torch.from_numpy((0.5 + rs.rand(C)).astype(np.float32)).cuda()
+    shift = torch.from_numpy((0.3 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    mean = torch.from_numpy((0.3 + 0.1 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    invstd = torch.from_numpy((0.8 + 0.4 * rs.rand(C)).astype(np.float32)).cuda()
+    gamma = torch.from_numpy((1 + 0.1 * rs.standard_normal(C)).astype(np.float32)).cuda()
+    # reference path: plain dgrad, then the reduce pass
+    da_ref = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    call("unetca_conv3x3_fwd", dt, ptr(dyd), O, ptr(wdg), 9 * O, ptr(da_ref), C, B, H, W, O, C, None, None, stream())
+    parts = parts_buf(B)
+    n = cint()
+    call("unetca_bn_bwd_reduce", dt, ptr(da_ref), C, ptr(y1), C, B, H * W, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), None,
+         None, ptr(parts), ctypes.byref(n), stream())
+    out_ref = [torch.empty(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(3, C, device="cuda")]
+    call("unetca_bn_bwd_finalize", ptr(parts), n.value, C, B * H * W, ptr(gamma), ptr(invstd), ptr(out_ref[0]), ptr(out_ref[1]),
+         ptr(out_ref[2]), stream())
+    # fused
+    da = torch.full((B, H, W, C), float("nan"), dtype=TDT[dt], device="cuda")
+    parts2 = parts_buf(B)
+    n2 = cint()
+    call("unetca_conv3x3_dgrad_bnstats", dt, ptr(dyd), O, ptr(wdg), 9 * O, ptr(da), C, B, H, W, O, C, ptr(y1), C, ptr(scale), ptr(shift),
+         ptr(mean), ptr(parts2), ctypes.byref(n2), stream())
+    out = [torch.empty(C, device="cuda"), torch.empty(C, device="cuda"), torch.empty(3, C, device="cuda")]
+    call("unetca_bn_bwd_finalize", ptr(parts2), n2.value, C, B * H * W, ptr(gamma), ptr(invstd), ptr(out[0]), ptr(out[1]), ptr(out[2]),
+         stream())
+    if C == 64:
+        assert relerr(da.float().cpu(), da_ref.float().cpu()) < 1e-2        # rp64 vs the kernel unetca_conv3x3_fwd picks for O = 64
+    else:
+        assert torch.equal(da, da_ref)                                      # same haloed kernel, same arithmetic
+    for a, b in zip(out, out_ref):
+        # sums of the same bf16 values in a different order (per-thread columns vs per-pixel-row blocks): fp32 round-off,
+        # measured against the mass that was summed
+        assert relerr(a.cpu(), b.cpu()) < (2e-2 if C == 64 else 1e-3)
+
+
 @pytest.mark.parametrize("B,C,O,H,W,layout", [(3, 128, 128, 40, 72, 0), (2, 64, 256, 16, 48, 0), (5, 128, 128, 8, 8, 0),
                                               (3, 64, 64, 40, 72, 1), (2, 64, 64, 128, 160, 1), (70, 64, 64, 16, 16, 1),
-                                              (1, 128, 64, 24, 40, 2)])
+                                              (1, 128, 64, 24, 40, 2), (3, 64, 64, 40, 72, 3), (70, 64, 64, 16, 16, 3)])
 def test_conv3x3_bnrelu_squeeze_epilogue(B, C, O, H, W, layout):
     """Inference form of a block's convolution: eval-mode BatchNorm + ReLU in the epilogue (UCA:83-90 with running
     statistics) and, for a block's second convolution, the SE squeeze (UCA:65) as per-image partial channel sums."""

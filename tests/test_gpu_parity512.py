@@ -53,7 +53,12 @@ def test_b8_512_train_step_vs_reference_golden(golden_dir, prec, ltol, ptol):
     loss = torch.nn.CrossEntropyLoss(ignore_index=255)(logits, y.cuda())
     loss.backward()
     lg = logits.detach().cpu()
-    assert _rel(lg[:, :, ::8, ::8], torch.from_numpy(g["logits_sub"])) < ltol
+    ref_sub = torch.from_numpy(g["logits_sub"])
+    d = (lg[:, :, ::8, ::8] - ref_sub).abs() / ref_sub.abs().max()
+    rel_l2 = ((lg[:, :, ::8, ::8] - ref_sub).norm() / ref_sub.norm()).item()
+    print(f"b8_512[{prec}]: logits max|d|/max|ref| {d.max().item():.3e}, 99.99th pct {d.flatten().kthvalue(int(0.9999 * d.numel())).values.item():.3e}, "
+          f"rel L2 {rel_l2:.3e}")
+    assert d.max().item() < ltol, d.max().item()
     assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < (1e-3 if prec == "fp32" else 1e-2)
     names = [str(n) for n in g["param_names"]]
     params = dict(m.named_parameters())
@@ -61,7 +66,11 @@ def test_b8_512_train_step_vs_reference_golden(golden_dir, prec, ltol, ptol):
     ref_norms = g["grad_norms"]
     total, ref_total = np.sqrt((norms ** 2).sum()), np.sqrt((ref_norms ** 2).sum())
     assert abs(total - ref_total) / ref_total < 1e-2, (total, ref_total)
-    big = ref_norms > 1e-6 * ref_total          # excludes the 18 pre-BN conv biases (analytically zero gradients)
+    # the 18 conv biases in front of a train-mode BatchNorm have analytically zero gradients: the reference holds rounding
+    # noise there (up to ~1e-5 of the total at this size), this path exact zeros
+    prebn = np.array([n.endswith((".double_conv.0.bias", ".double_conv.3.bias")) for n in names])
+    big = ~prebn
+    assert ref_norms[prebn].max() < 1e-4 * ref_total
     rel = np.abs(norms[big] - ref_norms[big]) / ref_norms[big]
     # per-parameter norms: 1 % in fp32 mode; bf16: 10 % (30 % for the SE FC weights, K = batch sums of pixel sums with
     # heavy cancellation — same bound as at BASELINE configs[0])

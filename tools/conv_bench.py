@@ -32,6 +32,8 @@ def main():
     ap.add_argument("--no-kw", action="store_true", help="64-output layers through the row-pair kernel instead of the kw-stacked one")
     ap.add_argument("--no-pixn", action="store_true", help="narrow layers through the pixels-on-M generic kernel")
     ap.add_argument("--dgrad", action="store_true", help="add the dgrad shapes (O -> C) of the narrow layers")
+    ap.add_argument("--rp64", action="store_true", help="64->64 layers through the resident-filter row-pair kernel")
+    ap.add_argument("--bnstats", action="store_true", help="'fwd' = dgrad with the fused BatchNorm-backward statistics epilogue (C == O)")
     a = ap.parse_args()
     lib = _lib.load()
     lib.unetca_tc_force_block_n(a.block_n)
@@ -100,8 +102,17 @@ def main():
             wfp = torch.empty(2 * O, 12 * C, device="cuda", dtype=torch.bfloat16)
             _lib.call("unetca_pack_conv3x3_pair", 1, wf.data_ptr(), 9 * C, wfp.data_ptr(), O, C, st)
         res = []
+        y1 = torch.randn(B, S, S, O, device="cuda").bfloat16() if a.bnstats else None
+        cvec = [torch.rand(O, device="cuda") + 0.5, torch.randn(O, device="cuda") * 0.3, torch.randn(O, device="cuda") * 0.1]
         for what in a.what.split(","):
-            if what == "fwd" and wkw is not None:
+            if what == "fwd" and a.bnstats and C == O:
+                fn = lambda: _lib.call("unetca_conv3x3_dgrad_bnstats", 1, x.data_ptr(), C, wf.data_ptr(), 9 * C, y.data_ptr(), O, B, S, S,
+                                       C, O, y1.data_ptr(), O, cvec[0].data_ptr(), cvec[1].data_ptr(), cvec[2].data_ptr(),
+                                       parts.data_ptr(), ctypes.byref(n), st)  # noqa: E731
+            elif what == "fwd" and a.rp64 and C == 64 and O == 64:
+                fn = lambda: _lib.call("unetca_conv3x3_fwd_rp64", 1, x.data_ptr(), C, wf.data_ptr(), 9 * C, y.data_ptr(), O, B, S, S,
+                                       parts.data_ptr(), ctypes.byref(n), st)  # noqa: E731
+            elif what == "fwd" and wkw is not None:
                 fn = lambda: _lib.call("unetca_conv3x3_fwd_kw", 1, x.data_ptr(), C, wkw.data_ptr(), y.data_ptr(), O, B, S, S, C,
                                        parts.data_ptr(), ctypes.byref(n), st)  # noqa: E731
             elif what == "fwd" and wfp is not None:
