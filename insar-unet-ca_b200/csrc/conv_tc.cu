@@ -1012,7 +1012,9 @@ constexpr int kPnStages = 3;
 constexpr int kPnABytes = 128 * 128, kPnBBytes = 256 * 128, kPnStageBytes = kPnABytes + kPnBBytes;
 constexpr int kPnOutBytes = 2 * 256 * 128;
 constexpr int kPnStatBytes = 2 * 1024 * 4 + 256 * 4;
-constexpr int kPnSmemBytes = 1024 + kPnStages * kPnStageBytes + kPnOutBytes + kPnStatBytes + 256;
+constexpr int kPnThreads = 320;          // producer, MMA issuer, eight epilogue warps
+constexpr int kPnHandBytes = 2 * 128 * 4;                   // per-tile statistics handed from the second epilogue half to the first
+constexpr int kPnSmemBytes = 1024 + kPnStages * kPnStageBytes + kPnOutBytes + kPnStatBytes + kPnHandBytes + 256;
 static_assert(kPnSmemBytes <= 227 * 1024, "pixn conv: shared memory budget");
 
 // write this CTA's per-image channel sums (the entries of sm_sq owned by epilogue thread r) to
@@ -1089,13 +1091,13 @@ __device__ __forceinline__ void pixn_drain(uint32_t t_addr, uint32_t my_s, float
 // traffic of the weight operand halves (this kernel is fill-bound: 48 KB per 512 MMA cycles without it).  A stage may
 // only be refilled when BOTH CTAs' MMAs have drained it: the MMA commits are multicast to both empty barriers.
 template <int CL>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __grid_constant__ PixNParams p) {
+__global__ void __launch_bounds__(kPnThreads, 1) tc_conv3x3_pixn_kernel(const __grid_constant__ PixNParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* out_stage = smem + kPnStages * kPnStageBytes;
     float* sm_stats = reinterpret_cast<float*>(out_stage + kPnOutBytes);
     float* sm_wpart = sm_stats + 2048;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kPnOutBytes + kPnStatBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kPnOutBytes + kPnStatBytes + kPnHandBytes);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kPnStages;
     uint64_t* tfull_bar = bars + 2 * kPnStages;
@@ -1105,7 +1107,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPnStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
         fence_barrier_init();
         prefetch_tmap(&p.mapX);
         prefetch_tmap(&p.mapW);
@@ -1113,7 +1115,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     if (p.stat_parts || p.sq_parts) {
-        for (int i = threadIdx.x; i < 2 * p.N; i += kTcThreads) sm_stats[i] = 0.f;
+        for (int i = threadIdx.x; i < 2 * p.N; i += kPnThreads) sm_stats[i] = 0.f;
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -1183,11 +1185,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
             }
         }
     } else {
+        // eight epilogue warps (2..9): warps w and w + 4 share a TMEM lane quarter and take 128 of the 256 pixel columns each
+        // (the drain is a dependent chain one warp per scheduler issues at ~0.35 instructions per cycle; with a single
+        // k-block per tile, as in the first convolution, it is the whole tile time); the second half hands its statistics
+        // to the first through shared memory in a fixed order
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;
         const int r = q * 32 + lane;             // accumulator row = TMEM lane
-        const int ep_tid = threadIdx.x - 64;
+        const int ep_tid = threadIdx.x - 64;     // 0..255
         const int box = r >> 6, oc = r & 63;
         uint8_t* my = out_stage + box * (256 * 128) + oc * 2;
+        float* sm_hand = sm_wpart + 256;         // [2][128]: statistics of the second column half
         int as = 0; uint32_t aph = 0;
         int cur_b = -1;
         for (long t = first; t < num_work; t += stride) {
@@ -1200,19 +1208,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
             if (ep_tid == 0) tma_store_wait_read();          // staging drained by the previous tile's store
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             float s1 = 0.f, s2 = 0.f;
             const uint32_t my_s = smem_u32(my);
             const bool act = p.ep_scale != nullptr;
             const int ech = p.P == 1 ? mb * 128 + r : mb * 64 + (r & 63);
             const float ea = act ? __ldg(p.ep_scale + ech) : 1.f, eb = act ? __ldg(p.ep_shift + ech) : 0.f;
-            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, act, ea, eb);
-            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, i0, p.TW - 1, p.twShift, p.W, p.HP, act, ea, eb);
+            if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, chalf * 4, 4);
+            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, i0, p.TW - 1, p.twShift, p.W, p.HP, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, chalf * 4, 4);
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (chalf == 1) { sm_hand[r] = s1; sm_hand[128 + r] = s2; }
             fence_proxy_async_smem();
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             if (ep_tid == 0) {
                 if (p.P == 1) {
                     tma_store_5d(&p.mapOut, out_stage, mb * 128, x0, 0, i0, b);
@@ -1223,41 +1232,45 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv3x3_pixn_kernel(const __
                 }
                 tma_store_commit();
             }
-            if (p.stat_parts) {
-                if (p.P == 1) {
-                    sm_stats[mb * 128 + r] += s1;
-                    sm_stats[p.N + mb * 128 + r] += s2;
-                } else {
-                    sm_wpart[r] = s1; sm_wpart[128 + r] = s2;
-                    named_bar_sync(1, 128);
-                    if (r < 64) {
-                        sm_stats[mb * 64 + r] += sm_wpart[r] + sm_wpart[r + 64];
-                        sm_stats[p.N + mb * 64 + r] += sm_wpart[128 + r] + sm_wpart[192 + r];
+            // from here on only the first column half works (128 threads, named barrier 2); its partner's sums are in sm_hand
+            if (chalf == 0) {
+                s1 += sm_hand[r]; s2 += sm_hand[128 + r];
+                if (p.stat_parts) {
+                    if (p.P == 1) {
+                        sm_stats[mb * 128 + r] += s1;
+                        sm_stats[p.N + mb * 128 + r] += s2;
+                    } else {
+                        sm_wpart[r] = s1; sm_wpart[128 + r] = s2;
+                        named_bar_sync(2, 128);
+                        if (r < 64) {
+                            sm_stats[mb * 64 + r] += sm_wpart[r] + sm_wpart[r + 64];
+                            sm_stats[p.N + mb * 64 + r] += sm_wpart[128 + r] + sm_wpart[192 + r];
+                        }
                     }
                 }
-            }
-            if (p.sq_parts && b < p.nimg) {
-                // SE squeeze of the stored activation: per-image channel sums, flushed when this CTA moves to the next image
-                if (b != cur_b) {
-                    if (cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, p.P, p.num_m_blocks, r);
-                    cur_b = b;
-                }
-                if (p.P == 1) sm_stats[mb * 128 + r] += s1;
-                else {
-                    sm_wpart[r] = s1;
-                    named_bar_sync(1, 128);
-                    if (r < 64) sm_stats[mb * 64 + r] += sm_wpart[r] + sm_wpart[r + 64];
-                    named_bar_sync(1, 128);
+                if (p.sq_parts && b < p.nimg) {
+                    // SE squeeze of the stored activation: per-image channel sums, flushed when this CTA moves to the next image
+                    if (b != cur_b) {
+                        if (cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, p.P, p.num_m_blocks, r);
+                        cur_b = b;
+                    }
+                    if (p.P == 1) sm_stats[mb * 128 + r] += s1;
+                    else {
+                        sm_wpart[r] = s1;
+                        named_bar_sync(2, 128);
+                        if (r < 64) sm_stats[mb * 64 + r] += sm_wpart[r] + sm_wpart[r + 64];
+                        named_bar_sync(2, 128);
+                    }
                 }
             }
             as ^= 1; if (as == 0) aph ^= 1;
         }
-        if (p.sq_parts && cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, p.P, p.num_m_blocks, r);
+        if (chalf == 0 && p.sq_parts && cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, p.P, p.num_m_blocks, r);
         if (ep_tid == 0) tma_store_wait_all();
-        named_bar_sync(1, 128);
+        named_bar_sync(1, 256);
         if (p.stat_parts) {
             float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
-            for (int i = ep_tid; i < 2 * p.N; i += 128) dst[i] = sm_stats[i];
+            for (int i = ep_tid; i < 2 * p.N; i += 256) dst[i] = sm_stats[i];
         }
     }
     tcgen05_fence_before();
@@ -2130,6 +2143,7 @@ static int pick_block_n(int N) {
 }
 
 static int g_no_halo = 0;
+static int g_wgrad_waves = 6;      // conv3x3 weight gradients: work items per SM that the split-K factor aims for
 static int g_convT_wide = 1;       // ConvTranspose forward / wgrad: N blocks of 256 across the four sub-pixel maps
 
 // make_map variant without swizzle (linear [pixel][64 ch] staging tiles of the pixels-on-N epilogue)
@@ -2270,10 +2284,10 @@ static int launch_pixn_kernel(const PixNParams& p, int CL, cudaStream_t st, cons
     long grid = num_work * CL < num_sms() ? num_work * CL : (num_sms() / CL) * CL;
     if (grid < CL) grid = CL;
     if (CL == 1) {
-        tc_conv3x3_pixn_kernel<1><<<(int)grid, kTcThreads, kPnSmemBytes, st>>>(p);
+        tc_conv3x3_pixn_kernel<1><<<(int)grid, kPnThreads, kPnSmemBytes, st>>>(p);
     } else {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kTcThreads); cfg.dynamicSmemBytes = kPnSmemBytes; cfg.stream = st;
+        cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kPnThreads); cfg.dynamicSmemBytes = kPnSmemBytes; cfg.stream = st;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -2607,12 +2621,33 @@ int unetca_tc_convT_dgrad(const void* dout, int ldd, const void* wdg, void* dx, 
     return r2 < 0 ? r2 : 0;
 }
 
+// Split-K factor for a persistent weight-gradient kernel: `items` equal work items per split walk the grid in rounds of
+// num_sms() CTAs, so the kernel takes ceil(items * s / num_sms()) rounds of (1 / s) of the K range each.  Around the
+// target number of waves, pick the s with the least total time = rounds / s — i.e. the one whose last round is full
+// (items = 16, 148 SMs: s = 19 -> 3 rounds of 1/19 = 0.158; s = 18 -> 2 rounds of 1/18 = 0.111 of the serial time).
+static long fit_split(long items, int waves, long smax) {
+    const long G = num_sms();
+    long target = ((long)waves * G + items - 1) / items;
+    if (target > smax) target = smax;
+    if (target < 1) target = 1;
+    long lo = target - target / 3, hi = target + target / 4;
+    if (lo < 1) lo = 1;
+    if (hi > smax) hi = smax;
+    long best = target;
+    double best_t = 1e30;
+    for (long s = lo; s <= hi; ++s) {
+        const long rounds = (items * s + G - 1) / G;
+        const double t = (double)rounds / (double)s;
+        if (t < best_t * (1.0 - 1e-9)) { best_t = t; best = s; }
+    }
+    return best;
+}
+
 static int pick_nsplit(long tiles, int ktiles, long stride_floats, long ws_floats) {
-    long s = (2L * num_sms() + tiles - 1) / tiles;
-    if (s > ktiles / 4) s = ktiles / 4;
-    if (s < 1) s = 1;
-    if (s * stride_floats > ws_floats) s = ws_floats / stride_floats;
-    return (int)s;
+    long smax = ktiles / 4;
+    if (ws_floats / stride_floats < smax) smax = ws_floats / stride_floats;
+    if (smax < 1) return (int)(ws_floats / stride_floats);        // 0 when the workspace cannot hold one slice
+    return (int)fit_split(tiles, 2, smax);
 }
 
 // ws[z][o][tap*C+c] = sum_{p in split z} dy[p][o] * x[p+s(tap)][c]; returns nsplit.  Halo-reuse kernel.
@@ -2635,11 +2670,11 @@ int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, fl
     const long items = wide256 ? (long)(C / 128) * (O / 256) * 5 : wide ? (long)(C / 128) * (O / 128) * 3
                        : rowpair ? (long)p.cchunks * p.oblocks * 2 : (long)p.cchunks * p.oblocks;
     const int slices_per_split = rowpair ? 2 : 1;        // the row-pair kernel writes the j = 0 / j = 1 halves separately
-    long ns = (6L * num_sms() + items - 1) / items;
-    if (ns > p.ktiles_total / 16) ns = p.ktiles_total / 16;
-    if (ns < 1) ns = 1;
-    if (ns * slices_per_split * p.split_stride > ws_floats) ns = ws_floats / (p.split_stride * slices_per_split);
-    if (ns < 1) { set_error("tc_conv3x3_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+    long smax = p.ktiles_total / 16;
+    if (smax < 1) smax = 1;
+    if (ws_floats / (p.split_stride * slices_per_split) < smax) smax = ws_floats / (p.split_stride * slices_per_split);
+    if (smax < 1) { set_error("tc_conv3x3_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+    const long ns = g_wgrad_waves > 0 ? fit_split(items, g_wgrad_waves, smax) : 1;
     p.nsplit = (int)ns;
     p.ws = ws; p.ldn = 9 * C; p.C = C;
     static bool attr_done = false;

@@ -1939,6 +1939,64 @@ __global__ void __launch_bounds__(kThreads) ce_kernel(const float* __restrict__ 
         parts[2 * blockIdx.x + 1] = c;
     }
 }
+// Two classes, HW % 4 == 0: the same arithmetic as ce_kernel, in the same order per pixel, on four consecutive pixels per
+// thread with 16-byte loads / stores (two float4 of logits, two longlong2 of labels in; two float4 of dlogits out).
+__global__ void __launch_bounds__(kThreads) ce2_vec_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                                           long nquad, long HW, long long ignore_index, float* __restrict__ g,
+                                                           long long* __restrict__ mask, float* __restrict__ parts) {
+    float lsum = 0.f, lcnt = 0.f;
+    for (long q = (long)blockIdx.x * kThreads + threadIdx.x; q < nquad; q += (long)gridDim.x * kThreads) {
+        const long p = q * 4;
+        const long b = p / HW, hw = p % HW;
+        const float* lp = logits + b * 2 * HW + hw;
+        const float4 l0 = *reinterpret_cast<const float4*>(lp), l1 = *reinterpret_cast<const float4*>(lp + HW);
+        const float a[4] = {l0.x, l0.y, l0.z, l0.w}, c[4] = {l1.x, l1.y, l1.z, l1.w};
+        long long t[4] = {0, 0, 0, 0};
+        if (target) {
+            const longlong2 t01 = *reinterpret_cast<const longlong2*>(target + p), t23 = *reinterpret_cast<const longlong2*>(target + p + 2);
+            t[0] = t01.x; t[1] = t01.y; t[2] = t23.x; t[3] = t23.y;
+        }
+        float g0[4], g1[4];
+        long long am[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float m = a[i];
+            am[i] = 0;
+            if (c[i] > m || (c[i] != c[i] && m == m)) { m = c[i]; am[i] = 1; }     // first max wins; NaN propagates like torch.max
+            float se = 0.f;
+            se += expf(a[i] - m);
+            se += expf(c[i] - m);
+            const float lse = m + logf(se);
+            long long ti = t[i];
+            const bool valid = ti != ignore_index;
+            if (target && valid && (ti < 0 || ti >= 2)) { lsum = nanf(""); ti = 0; }
+            if (target && valid) { lsum += lse - (ti ? c[i] : a[i]); lcnt += 1.f; }
+            g0[i] = valid ? expf(a[i] - lse) - (ti == 0 ? 1.f : 0.f) : 0.f;
+            g1[i] = valid ? expf(c[i] - lse) - (ti == 1 ? 1.f : 0.f) : 0.f;
+        }
+        if (mask) {
+            *reinterpret_cast<longlong2*>(mask + p) = make_longlong2(am[0], am[1]);
+            *reinterpret_cast<longlong2*>(mask + p + 2) = make_longlong2(am[2], am[3]);
+        }
+        if (target && g) {
+            float* gp = g + b * 2 * HW + hw;
+            *reinterpret_cast<float4*>(gp) = make_float4(g0[0], g0[1], g0[2], g0[3]);
+            *reinterpret_cast<float4*>(gp + HW) = make_float4(g1[0], g1[1], g1[2], g1[3]);
+        }
+    }
+    __shared__ float rs[kThreads / 32], rc[kThreads / 32];
+    lsum = warp_sum(lsum);
+    lcnt = warp_sum(lcnt);
+    if ((threadIdx.x & 31) == 0) { rs[threadIdx.x >> 5] = lsum; rc[threadIdx.x >> 5] = lcnt; }
+    __syncthreads();
+    if (threadIdx.x == 0 && parts) {
+        float sa = 0.f, sc = 0.f;
+        for (int i = 0; i < kThreads / 32; ++i) { sa += rs[i]; sc += rc[i]; }
+        parts[2 * blockIdx.x] = sa;
+        parts[2 * blockIdx.x + 1] = sc;
+    }
+}
+
 __global__ void ce_finalize_kernel(const float* __restrict__ parts, int nparts, const float* __restrict__ upstream,
                                    float* __restrict__ loss, float* __restrict__ gscale) {
     // one warp
@@ -2076,7 +2134,7 @@ __global__ void __launch_bounds__(256) im2col_pairs_kernel(const float* __restri
     constexpr int K = 12 * CIN;
     const int HP = H >> 1;
     const long n = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= (long)B * HP * W) return;
+    const bool live = n < (long)B * HP * W;                 // (every thread reaches the barrier below)
     const int xw = (int)(n % W), i = (int)((n / W) % HP);
     const long b = n / ((long)W * HP);
     float v[K];
@@ -2086,19 +2144,48 @@ __global__ void __launch_bounds__(256) im2col_pairs_kernel(const float* __restri
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) {
             const int ww = xw + kw - 1;
-            const bool in = hh >= 0 && hh < H && ww >= 0 && ww < W;
+            const bool in = live && hh >= 0 && hh < H && ww >= 0 && ww < W;
 #pragma unroll
             for (int c = 0; c < CIN; ++c)
                 v[(vr * 3 + kw) * CIN + c] = in ? __ldg(x + ((b * CIN + c) * H + hh) * W + ww) : 0.f;
         }
     }
-    T* dst = colp + n * 64;
+    if constexpr (sizeof(T) == 4) {
+        // fp32 rows (cross-check only): each thread writes its own 256-byte row
+        if (!live) return;
+        T* dst = colp + n * 64;
 #pragma unroll
-    for (int j = 0; j < 64 / VEC; ++j) {
+        for (int j = 0; j < 64 / VEC; ++j) {
+            float o[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) o[e] = (j * VEC + e) < K ? v[(j * VEC + e) < K ? (j * VEC + e) : 0] : 0.f;
+            store_vec(dst + j * VEC, o);
+        }
+    } else {
+    // rows are staged in shared memory and leave as contiguous 16-byte chunks (a warp writes 512 contiguous bytes): a
+    // thread writing its own row would touch 32 different 128-byte lines per store instruction
+    __shared__ __align__(16) T stage[256 * 64];
+    // chunk j of row r at slot (j ^ (r & 7)): conflict-free both for the row-wise writes and the chunk-wise reads (bf16)
+    constexpr int NCH = 64 / VEC;
+    T* srow = stage + threadIdx.x * 64;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
         float o[VEC];
 #pragma unroll
         for (int e = 0; e < VEC; ++e) o[e] = (j * VEC + e) < K ? v[(j * VEC + e) < K ? (j * VEC + e) : 0] : 0.f;
-        store_vec(dst + j * VEC, o);
+        store_vec(srow + ((j ^ (threadIdx.x & (NCH - 1))) * VEC), o);
+    }
+    __syncthreads();
+    const long row0 = (long)blockIdx.x * blockDim.x;
+    const long nrows = (long)B * HP * W;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+        const int cidx = k * 256 + threadIdx.x;              // chunk index within the block's [256][NCH] chunks
+        const int r = cidx / NCH, j = cidx % NCH;
+        if (row0 + r < nrows)
+            *reinterpret_cast<uint4*>(colp + (row0 + r) * 64 + j * VEC) =
+                *reinterpret_cast<const uint4*>(stage + r * 64 + ((j ^ (r & (NCH - 1))) * VEC));
+    }
     }
 }
 
@@ -2909,6 +2996,13 @@ int unetca_cross_entropy(const float* logits, const long long* target, int nc, i
     if (nblk > kMaxParts) nblk = kMaxParts;
     if (nblk < 1) nblk = 1;
     cudaStream_t st = (cudaStream_t)stream;
+    const bool al16 = (((uintptr_t)logits | (uintptr_t)target | (uintptr_t)g | (uintptr_t)mask) & 15) == 0;
+    if (nc == 2 && HW % 4 == 0 && al16) {
+        // the reference's case (NUM_CLASSES = 2, UCA:24): four pixels per thread, 16-byte accesses — 24 B/px at HBM speed
+        nblk = ceil_div(npix / 4, kThreads * 2);
+        if (nblk > kMaxParts) nblk = kMaxParts;
+        ce2_vec_kernel<<<nblk, kThreads, 0, st>>>(logits, target, npix / 4, HW, ignore_index, g, mask, parts);
+    } else
     ce_kernel<<<nblk, kThreads, 0, st>>>(logits, target, nc, npix, HW, ignore_index, g, mask, parts);
     if (target && loss_out) ce_finalize_kernel<<<1, 32, 0, st>>>(parts, nblk, upstream, loss_out, gscale_out);
     return check_launch("cross_entropy");
