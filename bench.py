@@ -115,6 +115,12 @@ def _work(name, a, e, cin):
     if name == "unetca_conv3x3_fwd_paired":
         B, H, W, C, O = a[6:11]
         return "tensor", 2.0 * B * H * W * 9 * C * O, 0
+    if name == "unetca_conv3x3_fwd_rp64":
+        B, H, W = a[7:10]
+        return "tensor", 2.0 * B * H * W * 9 * 64 * 64, 0
+    if name == "unetca_conv3x3_dgrad_bnstats":
+        B, H, W, C, O = a[7:12]
+        return "tensor", 2.0 * B * H * W * 9 * C * O, 0
     if name == "unetca_se_squeeze":
         B, hw, C = a[3:6]
         return "hbm", 0, B * hw * C * e
@@ -388,6 +394,58 @@ def guarded(fn):
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
+def record_timeline(step, x, y, rank, world, path):
+    """One profiled step (all ranks run it, rank 0 records): every CUDA kernel with its stream, start and duration; the
+    summary says how much NCCL time there is, how much of it runs under compute kernels, and how long the step's tail after
+    the last compute kernel is."""
+    import torch.distributed as dist
+    from torch.profiler import ProfilerActivity, profile
+    step(x, y)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if rank != 0:
+        step(x, y)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        return None
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step(x, y)
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
+    ks = sorted(((e.name, e.time_range.start, e.time_range.end, getattr(e, "device_index", 0)) for e in ev), key=lambda t: t[1])
+    if not ks:
+        return {"error": "no CUDA kernel events recorded"}
+    t0 = ks[0][1]
+    nccl = [(a - t0, b - t0) for n, a, b, _ in ks if "nccl" in n.lower()]
+    comp = [(n, a - t0, b - t0) for n, a, b, _ in ks if "nccl" not in n.lower() and "memcpy" not in n.lower() and "memset" not in n.lower()]
+
+    def overlap(iv, others):
+        tot = 0.0
+        for a, b in iv:
+            for c, d in others:
+                lo, hi = max(a, c), min(b, d)
+                if hi > lo:
+                    tot += hi - lo
+        return tot
+    comp_iv = [(a, b) for _, a, b in comp]
+    end_comp = max(b for _, _, b in comp)
+    end_all = max(b for _, _, b, _ in ks) - t0
+    # compute kernels that ran while an NCCL kernel was active, with their durations
+    under = [(n, b - a) for n, a, b in comp if overlap([(a, b)], nccl) > 0.25 * (b - a)]
+    out = {"step_us": end_all, "kernels": len(ks), "nccl_kernels": len(nccl), "nccl_us": sum(b - a for a, b in nccl),
+           "nccl_us_under_compute": overlap(nccl, comp_iv), "tail_after_last_compute_us": end_all - end_comp,
+           "compute_us": sum(b - a for a, b in comp_iv),
+           "compute_kernels_running_under_nccl": [{"name": n[:60], "us": d} for n, d in under][:40],
+           "nccl_intervals_us": [[round(a, 1), round(b, 1)] for a, b in nccl][:40]}
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    return {k: out[k] for k in ("step_us", "nccl_kernels", "nccl_us", "nccl_us_under_compute", "tail_after_last_compute_us")}
+
+
 def extra_dp_parity(dev, rank, world):
     """N > 1: one untimed tiny fp32 train step.  The all-reduced gradients that GradBuckets leaves in .grad against the
     all-gathered mean of the per-rank gradients of the SAME model run without data parallelism, and whether every
@@ -536,6 +594,11 @@ def main():
                     help="replay the whole train step as one CUDA graph (unetca_b200.graph; single GPU; no per-kernel "
                          "accounting, so the roofline objects are omitted) — what matters at small batch / tile sizes")
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel table (JSON) to this path")
+    ap.add_argument("--nccl-max-ctas", type=int, default=int(os.environ.get("UNETCA_NCCL_MAX_CTAS", "0")),
+                    help="N > 1: cap the CTAs NCCL may use for the gradient all-reduce (0 = NCCL's default)")
+    ap.add_argument("--timeline", default=None,
+                    help="N > 1: rank 0 records one extra step with torch.profiler and writes a per-stream kernel timeline "
+                         "summary (JSON) here: NCCL time, overlap with compute, exposed tail")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -562,7 +625,15 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        pg_opts = None
+        if args.nccl_max_ctas > 0:
+            # the bucket all-reduces run UNDER the persistent one-CTA-per-SM contraction kernels of backward: every SM NCCL
+            # takes delays a CTA that owns a fixed share of tiles, so the collective is capped to a few CTAs (125 MB per
+            # ~90 ms step needs < 5 GB/s of the 900 GB/s NVLink port)
+            pg_opts = dist.ProcessGroupNCCL.Options()
+            pg_opts.config.max_ctas = args.nccl_max_ctas
+            pg_opts.config.min_ctas = min(args.nccl_max_ctas, 1)
+        dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
     if args.warmup < 3:
         args.warmup = 3
 
@@ -775,6 +846,11 @@ def main():
                 json.dump({k: {**v, "ms_per_step": v["ms"] / nk} for k, v in table.items()}, f, indent=1)
             with open(args.kernel_table.replace(".json", "") + "_by_shape.json", "w") as f:
                 json.dump({k: {**v, "ms_per_step": v["ms"] / nk} for k, v in acct.summary(by_shape=True).items()}, f, indent=1)
+
+    if args.timeline:
+        tl = guarded(lambda: record_timeline(step, x, y, rank, world, args.timeline))
+        if rank == 0:
+            print("timeline:", json.dumps(tl)[:600], file=sys.stderr)
 
     # ---- extras: the other BASELINE configs on this build ------------------------------------------------------
     extra = None

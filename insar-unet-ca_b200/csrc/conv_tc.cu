@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_kernel(const __grid
     uint64_t* tfull_bar = bars + 2 * kWgStages;
     uint64_t* tempty_bar = bars + 2 * kWgStages + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWgStages + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kWgStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -561,7 +561,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide_kernel(const _
     uint64_t* tfull_bar = bars + 2 * kWg2Stages;
     uint64_t* tempty_bar = bars + 2 * kWg2Stages + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWg2Stages + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kWg2Stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide256_kernel(cons
     uint64_t* tfull_bar = bars + 2 * kWg3Stages;
     uint64_t* tempty_bar = bars + 2 * kWg3Stages + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWg3Stages + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kWg3Stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_rowpair_kernel(cons
     uint64_t* tfull_bar = bars + 2 * kWg4Stages;
     uint64_t* tempty_bar = bars + 2 * kWg4Stages + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kWg4Stages + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kWg4Stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -1103,7 +1103,7 @@ __global__ void __launch_bounds__(kPnThreads, 1) tc_conv3x3_pixn_kernel(const __
     uint64_t* tfull_bar = bars + 2 * kPnStages;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kPnStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
@@ -1280,6 +1280,144 @@ __global__ void __launch_bounds__(kPnThreads, 1) tc_conv3x3_pixn_kernel(const __
     if (warp == 1) tmem_dealloc<512>(tmem_base);
 }
 
+// DIRECT-STORE epilogue shared by the haloed and the resident-filter row-pair kernels.
+// Epilogue of one thread (= one accumulator row: a channel, or (j, channel) in the row-pair layout) over the 128 columns [cb0*32, cb0*32 + 128): fp32 -> (BN + ReLU)
+// -> bf16 -> global memory (a warp = 32 channels of one pixel = 64 contiguous bytes), plus either sum / sum of squares of the
+// stored values or (BWD) the ReLU + BatchNorm backward statistics against the saved conv output of the same pixels.
+// Column n = (pair row i = n >> 3, x = n & 7).  FULL: the whole tile lies inside the image (no bounds checks).
+// LDO / LDY: compile-time pixel strides of the output / saved tensor (0 = take the run-time value) — with the two layouts the
+// model uses (dense 64, channel half of a 128-wide concat buffer) every store address is row pointer + immediate.
+template <bool FULL, bool BWD, int LDO, int LDY, bool ACT = false>
+__device__ __forceinline__ void rp64_drain(uint32_t t_addr, int cb0, bf16* __restrict__ obase, long row_stride, int ldo_rt, int ni,
+                                           int nx, bool act_rt, float ea, float eb, const bf16* __restrict__ ybase, long yrow_stride,
+                                           int ldy_rt, float ba, float bb, float bm, float& s1, float& s2) {
+    const int ldo = LDO ? LDO : ldo_rt, ldy = LDY ? LDY : ldy_rt;
+    const bool act = ACT || (!FULL && act_rt);          // the inference epilogue: specialised on full tiles, run-time flag on partial ones
+    float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+    unsigned short* prow = reinterpret_cast<unsigned short*>(obase) + (long)cb0 * 4 * row_stride;
+    const unsigned short* yrow = reinterpret_cast<const unsigned short*>(ybase) + (BWD ? (long)cb0 * 4 * yrow_stride : 0);
+#pragma unroll 1
+    for (int cb = cb0; cb < cb0 + 4; ++cb) {
+        uint32_t v[32];
+        tmem_ld32(t_addr + cb * 32, v);
+        unsigned short yv[BWD ? 32 : 1];
+        if (BWD) {
+            // the saved conv output of the same 32 pixels: all loads in flight before the accumulator wait
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) {
+#pragma unroll
+                for (int x = 0; x < 8; ++x) {
+                    const bool ok = FULL || ((cb * 4 + ii) < ni && x < nx);
+                    yv[BWD ? ii * 8 + x : 0] = ok ? __ldg(yrow + ii * yrow_stride + x * ldy) : (unsigned short)0;
+                }
+            }
+            yrow += 4 * yrow_stride;
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const bool rok = FULL || (cb * 4 + ii) < ni;
+#pragma unroll
+            for (int x = 0; x < 8; x += 2) {
+                float f0 = __uint_as_float(v[ii * 8 + x]), f1 = __uint_as_float(v[ii * 8 + x + 1]);
+                if (act) {
+                    f0 = fmaxf(fmaf(ea, f0, eb), 0.f);
+                    f1 = fmaxf(fmaf(ea, f1, eb), 0.f);
+                }
+                const bool ok0 = rok && (FULL || x < nx), ok1 = rok && (FULL || x + 1 < nx);
+                if (!FULL) { if (!ok0) f0 = 0.f; if (!ok1) f1 = 0.f; }
+                const uint32_t pk = pack_bf16x2(f0, f1);
+                if (ok0) prow[x * ldo] = (unsigned short)(pk & 0xffffu);
+                if (ok1) prow[(x + 1) * ldo] = (unsigned short)(pk >> 16);
+                const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+                if (BWD) {
+                    // dz = value where the forward ReLU was open; (a2, b2) collect sum dz*y — the mean is taken out once at the end
+                    const float y0 = __uint_as_float((uint32_t)yv[BWD ? ii * 8 + x : 0] << 16);
+                    const float y1 = __uint_as_float((uint32_t)yv[BWD ? ii * 8 + x + 1 : 0] << 16);
+                    if (fmaf(ba, y0, bb) > 0.f) { a1 += r0; a2 = fmaf(r0, y0, a2); }
+                    if (fmaf(ba, y1, bb) > 0.f) { b1 += r1; b2 = fmaf(r1, y1, b2); }
+                } else {
+                    a1 += r0; a2 = fmaf(r0, r0, a2);
+                    b1 += r1; b2 = fmaf(r1, r1, b2);
+                }
+            }
+            prow += row_stride;
+        }
+    }
+    s1 = a1 + b1;
+    s2 = BWD ? fmaf(-bm, s1, a2 + b2) : a2 + b2;        // sum dz*(y - mean) = sum dz*y - mean * sum dz
+}
+
+// The fused BatchNorm-backward statistics need the saved conv output y of every pixel the thread writes.  Those are 2-byte
+// loads that miss L1 (each tile is read once): issued next to their use they put ~1 us of L2 / HBM latency into every
+// 32-column chunk.  So they run one chunk AHEAD: the first chunk's loads are issued before the thread waits for the tile's
+// accumulator (they do not depend on it), each further chunk's loads before the previous chunk is processed.
+// (two bf16 values per register: pixels x and x + 1 of a row)
+template <bool FULL, int LDY>
+__device__ __forceinline__ void bwd_load_y(uint32_t (&yv)[16], const unsigned short* __restrict__ yrow, long yrow_stride,
+                                           int ldy_rt, int cb, int ni, int nx) {
+    const int ldy = LDY ? LDY : ldy_rt;
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+#pragma unroll
+        for (int x = 0; x < 8; x += 2) {
+            const bool rok = FULL || (cb * 4 + ii) < ni;
+            const uint32_t lo = (rok && (FULL || x < nx)) ? (uint32_t)__ldg(yrow + ii * yrow_stride + x * ldy) : 0u;
+            const uint32_t hi = (rok && (FULL || x + 1 < nx)) ? (uint32_t)__ldg(yrow + ii * yrow_stride + (x + 1) * ldy) : 0u;
+            yv[ii * 4 + (x >> 1)] = lo | (hi << 16);
+        }
+    }
+}
+// yv: the saved conv output of all 128 pixels of this thread's column half (bwd_load_all_y), loaded by the caller BEFORE
+// it waited for the accumulator — the loads depend on nothing the MMA produces and are complete by the time the tile is
+template <bool FULL, int LDY>
+__device__ __forceinline__ void bwd_load_all_y(uint32_t (&yv)[4][16], const bf16* __restrict__ ybase, long yrow_stride,
+                                               int ldy_rt, int cb0, int ni, int nx) {
+    const unsigned short* yrow = reinterpret_cast<const unsigned short*>(ybase) + (long)cb0 * 4 * yrow_stride;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        bwd_load_y<FULL, LDY>(yv[k], yrow, yrow_stride, ldy_rt, cb0 + k, ni, nx);
+        yrow += 4 * yrow_stride;
+    }
+}
+template <bool FULL, int LDO>
+__device__ __forceinline__ void rp64_drain_bwd(uint32_t t_addr, int cb0, bf16* __restrict__ obase, long row_stride, int ldo_rt,
+                                               int ni, int nx, float ba, float bb, float bm, uint32_t (&yv)[4][16], float& s1,
+                                               float& s2) {
+    const int ldo = LDO ? LDO : ldo_rt;
+    float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+    unsigned short* prow = reinterpret_cast<unsigned short*>(obase) + (long)cb0 * 4 * row_stride;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int cb = cb0 + k;
+        uint32_t v[32];
+        tmem_ld32(t_addr + cb * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const bool rok = FULL || (cb * 4 + ii) < ni;
+#pragma unroll
+            for (int x = 0; x < 8; x += 2) {
+                float f0 = __uint_as_float(v[ii * 8 + x]), f1 = __uint_as_float(v[ii * 8 + x + 1]);
+                const bool ok0 = rok && (FULL || x < nx), ok1 = rok && (FULL || x + 1 < nx);
+                if (!FULL) { if (!ok0) f0 = 0.f; if (!ok1) f1 = 0.f; }
+                const uint32_t pk = pack_bf16x2(f0, f1);
+                if (ok0) prow[x * ldo] = (unsigned short)(pk & 0xffffu);
+                if (ok1) prow[(x + 1) * ldo] = (unsigned short)(pk >> 16);
+                const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
+                // dz = value where the forward ReLU was open; (a2, b2) collect sum dz*y — the mean is taken out once at the end
+                const uint32_t yp = yv[k][ii * 4 + (x >> 1)];
+                const float y0 = __uint_as_float(yp << 16), y1 = __uint_as_float(yp & 0xffff0000u);
+                if (fmaf(ba, y0, bb) > 0.f) { a1 += r0; a2 = fmaf(r0, y0, a2); }
+                if (fmaf(ba, y1, bb) > 0.f) { b1 += r1; b2 = fmaf(r1, y1, b2); }
+            }
+            prow += row_stride;
+        }
+    }
+    s1 = a1 + b1;
+    s2 = fmaf(-bm, s1, a2 + b2);                         // sum dz*(y - mean) = sum dz*y - mean * sum dz
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // conv3x3 forward / dgrad, pixels on N (as above, 128 output channels per m-block) WITH tap reuse from one haloed
 // activation tile.  Why: a 128x256x16 MMA reads 12 KB of operands from shared memory in 128 cycles (96 B/cycle);
@@ -1292,7 +1430,9 @@ __global__ void __launch_bounds__(kPnThreads, 1) tc_conv3x3_pixn_kernel(const __
 // Warps: 0 = activation producer, 1 = MMA issuer, 2..5 = epilogue (shared with the kernel above), 6 = weight producer.
 // ---------------------------------------------------------------------------------------------------------
 struct alignas(64) HpixParams {
-    CUtensorMap mapX, mapW, mapOut;
+    CUtensorMap mapX, mapW;
+    bf16* out;
+    int ldo;
     int tilesW, tilesH, nimg, H, W;
     int cchunks, num_m_blocks;
     float* stat_parts;
@@ -1312,9 +1452,9 @@ constexpr int kHpThreads = 352;          // X producer, MMA issuer, eight epilog
 constexpr int kHpTW = 8, kHpTH = 32, kHpPitch = kHpTW + 2;
 constexpr int kHpXBox = kHpPitch * (kHpTH + 2) * 128;      // 43520 bytes written by TMA
 constexpr int kHpXBytes = 44 * 1024;                       // ring slot
-constexpr int kHpXS = 2, kHpWS = 4;
+constexpr int kHpXS = 3, kHpWS = 5;                        // (the 64 KB output staging tile of the TMA-store epilogue is gone)
 constexpr int kHpWBytes = 128 * 128;
-constexpr int kHpSmemBytes = 1024 + kHpXS * kHpXBytes + kHpWS * kHpWBytes + kPnOutBytes + kPnStatBytes + 256;
+constexpr int kHpSmemBytes = 1024 + kHpXS * kHpXBytes + kHpWS * kHpWBytes + kPnStatBytes + 256;
 static_assert(kHpSmemBytes <= 227 * 1024, "hpix conv: shared memory budget");
 
 __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __grid_constant__ HpixParams p) {
@@ -1322,9 +1462,8 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* x_ring = smem;
     uint8_t* w_ring = smem + kHpXS * kHpXBytes;
-    uint8_t* out_stage = w_ring + kHpWS * kHpWBytes;
-    float* sm_stats = reinterpret_cast<float*>(out_stage + kPnOutBytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(out_stage + kPnOutBytes + kPnStatBytes);
+    float* sm_stats = reinterpret_cast<float*>(w_ring + kHpWS * kHpWBytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(w_ring + kHpWS * kHpWBytes + kPnStatBytes);
     uint64_t* xfull = bars;
     uint64_t* xempty = bars + kHpXS;
     uint64_t* wfull = bars + 2 * kHpXS;
@@ -1332,7 +1471,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
     uint64_t* tfull_bar = wempty + kHpWS;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kHpXS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
@@ -1341,7 +1480,6 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
         fence_barrier_init();
         prefetch_tmap(&p.mapX);
         prefetch_tmap(&p.mapW);
-        prefetch_tmap(&p.mapOut);
     }
     if (warp == 1) tmem_alloc<512>(tmem_slot);
     if (p.stat_parts || p.sq_parts) {
@@ -1422,17 +1560,20 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
         }
     } else {
         // ================================ epilogue (warps 2..9): lane = channel, column = pixel ================
-        // Eight warps: the drain is a dependent chain (TMEM load, convert, two 2-byte staging stores, statistics) that one
-        // warp per scheduler issues at ~0.35 instructions per cycle; at 128 input channels a tile's 72 MMAs do not cover
-        // it.  Warps w and w + 4 share a TMEM lane quarter and take 128 of the 256 pixel columns each; the second half hands
-        // its statistics to the first through shared memory (fixed order: run-to-run identical sums).
+        // Eight warps (w and w + 4 share a TMEM lane quarter and take 128 of the 256 pixel columns each) that write their
+        // bf16 values STRAIGHT to global memory — a warp = 32 channels of one pixel = 64 contiguous bytes, two full
+        // sectors.  The staging tile + TMA store this replaces cost ~1500 shared-memory wavefronts per tile (1024 two-byte
+        // stores + the store's reads) on the pipe that also feeds the MMA: 22 % of the pipe at 128 input channels, where
+        // operands (75 %) + fill (33 %) already exceed it; its 64 KB now hold a third activation stage and a fifth
+        // weight stage.  The second column half hands its statistics to the first through shared memory (fixed order).
         const int q = warp & 3;
         const int chalf = (warp - 2) >> 2;
         const int r = q * 32 + lane;
         const int ep_tid = threadIdx.x - 64;      // 0..255
-        const int box = r >> 6, oc = r & 63;
-        const uint32_t my_s = smem_u32(out_stage + box * (256 * 128) + oc * 2);
         float* sm_wpart = sm_stats + 2048;        // [2][128]
+        const bool act = p.ep_scale != nullptr;
+        const bool bwd = p.bwd_y != nullptr;
+        const long row_stride = (long)p.W * p.ldo, yrow_stride = (long)p.W * p.bwd_ldy;
         int as = 0; uint32_t aph = 0;
         int cur_b = -1;
         for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
@@ -1440,53 +1581,58 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
             const int mt = (int)(t / p.num_m_blocks);
             const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
             const int x0 = tw * kHpTW, h0 = th * kHpTH;
-            const bool full = (x0 + kHpTW <= p.W) && (h0 + kHpTH <= p.H);
+            const int nx = p.W - x0 < kHpTW ? p.W - x0 : kHpTW, ni = p.H - h0 < kHpTH ? p.H - h0 : kHpTH;
+            const bool full = nx == kHpTW && ni == kHpTH;
+            const int ch = mb * 128 + r;
+            const long pix0 = ((long)b * p.H + h0) * p.W + x0;
+            bf16* obase = p.out + pix0 * p.ldo + ch;
+            const bf16* ybase = bwd ? p.bwd_y + pix0 * p.bwd_ldy + ch : nullptr;
+            uint32_t yv[4][16];
+            if (bwd) {          // the saved-output loads go out before the accumulator is waited for
+                if (full) bwd_load_all_y<true, 0>(yv, ybase, yrow_stride, p.bwd_ldy, chalf * 4, ni, nx);
+                else bwd_load_all_y<false, 0>(yv, ybase, yrow_stride, p.bwd_ldy, chalf * 4, ni, nx);
+            }
             mbar_wait(&tfull_bar[as], aph);
             tcgen05_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
-            if (ep_tid == 0) tma_store_wait_read();
-            named_bar_sync(1, 256);
             float s1 = 0.f, s2 = 0.f;
-            const bool act = p.ep_scale != nullptr;
-            const float ea = act ? __ldg(p.ep_scale + mb * 128 + r) : 1.f, eb = act ? __ldg(p.ep_shift + mb * 128 + r) : 0.f;
-            const int cb0 = chalf * 4;
-            if (p.bwd_y) {
-                const int ch = mb * 128 + r;
-                const bf16* ybase = p.bwd_y + (((long)b * p.H + h0) * p.W + x0) * p.bwd_ldy + ch;
-                const long yrow = (long)p.W * p.bwd_ldy;
+            if (bwd) {
                 const float ba = __ldg(p.bwd_scale + ch), bb = __ldg(p.bwd_shift + ch), bm = __ldg(p.bwd_mean + ch);
-                if (full) pixn_drain<false, true>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, false, 1.f, 0.f, ybase, yrow, p.bwd_ldy, ba, bb, bm, cb0, 4);
-                else pixn_drain<true, true>(t_addr, my_s, s1, s2, x0, h0, kHpTW - 1, 3, p.W, p.H, false, 1.f, 0.f, ybase, yrow, p.bwd_ldy, ba, bb, bm, cb0, 4);
-            } else if (full) pixn_drain<false>(t_addr, my_s, s1, s2, 0, 0, 0, 0, 0, 0, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, cb0, 4);
-            else pixn_drain<true>(t_addr, my_s, s1, s2, x0, h0, kHpTW - 1, 3, p.W, p.H, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, cb0, 4);
+                if (full) rp64_drain_bwd<true, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, ba, bb, bm, yv, s1, s2);
+                else rp64_drain_bwd<false, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, ba, bb, bm, yv, s1, s2);
+            } else {
+                const float ea = act ? __ldg(p.ep_scale + ch) : 1.f, eb = act ? __ldg(p.ep_shift + ch) : 0.f;
+                if (full && act) rp64_drain<true, false, 0, 0, true>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, true, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else if (full && p.ldo == 128) rp64_drain<true, false, 128, 0>(t_addr, chalf * 4, obase, row_stride, 128, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else if (full && p.ldo == 256) rp64_drain<true, false, 256, 0>(t_addr, chalf * 4, obase, row_stride, 256, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else if (full && p.ldo == 512) rp64_drain<true, false, 512, 0>(t_addr, chalf * 4, obase, row_stride, 512, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else if (full) rp64_drain<true, false, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else rp64_drain<false, false, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+            }
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
-            if (chalf == 1 && (p.stat_parts || p.sq_parts)) { sm_wpart[r] = s1; sm_wpart[128 + r] = s2; }
-            fence_proxy_async_smem();
-            named_bar_sync(1, 256);
-            if (ep_tid == 0) {
-                tma_store_4d(&p.mapOut, out_stage, mb * 128, x0, h0, b);
-                tma_store_4d(&p.mapOut, out_stage + 256 * 128, mb * 128 + 64, x0, h0, b);
-                tma_store_commit();
-            }
-            if (chalf == 0) {
-                if (p.stat_parts) {
-                    sm_stats[mb * 128 + r] += s1 + sm_wpart[r];
-                    sm_stats[p.N + mb * 128 + r] += s2 + sm_wpart[128 + r];
-                }
-                if (p.sq_parts) {
-                    if (b != cur_b) {
-                        if (cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
-                        cur_b = b;
+            if (p.stat_parts || p.sq_parts) {
+                if (chalf == 1) { sm_wpart[r] = s1; sm_wpart[128 + r] = s2; }
+                named_bar_sync(1, 256);
+                if (chalf == 0) {
+                    if (p.stat_parts) {
+                        sm_stats[mb * 128 + r] += s1 + sm_wpart[r];
+                        sm_stats[p.N + mb * 128 + r] += s2 + sm_wpart[128 + r];
                     }
-                    sm_stats[mb * 128 + r] += s1 + sm_wpart[r];
+                    if (p.sq_parts) {
+                        if (b != cur_b) {
+                            if (cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
+                            cur_b = b;
+                        }
+                        sm_stats[mb * 128 + r] += s1 + sm_wpart[r];
+                    }
                 }
+                named_bar_sync(1, 256);         // sm_wpart may be rewritten
             }
             as ^= 1; if (as == 0) aph ^= 1;
         }
         if (chalf == 0 && p.sq_parts && cur_b >= 0) pixn_flush_sq(p.sq_parts, sm_stats, cur_b, p.N, 1, p.num_m_blocks, r);
-        if (ep_tid == 0) tma_store_wait_all();
         named_bar_sync(1, 256);
         if (p.stat_parts) {
             float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
@@ -1547,70 +1693,6 @@ static_assert(kRpSmemBytes <= 227 * 1024, "rp64 conv: shared memory budget");
 
 constexpr int kRpThreads = 320;          // producer, MMA issuer, eight epilogue warps
 
-// Epilogue of one thread (= one (j, channel) accumulator row) over the 128 columns [cb0*32, cb0*32 + 128): fp32 -> (BN + ReLU)
-// -> bf16 -> global memory (a warp = 32 channels of one pixel = 64 contiguous bytes), plus either sum / sum of squares of the
-// stored values or (BWD) the ReLU + BatchNorm backward statistics against the saved conv output of the same pixels.
-// Column n = (pair row i = n >> 3, x = n & 7).  FULL: the whole tile lies inside the image (no bounds checks).
-// LDO / LDY: compile-time pixel strides of the output / saved tensor (0 = take the run-time value) — with the two layouts the
-// model uses (dense 64, channel half of a 128-wide concat buffer) every store address is row pointer + immediate.
-template <bool FULL, bool BWD, int LDO, int LDY, bool ACT = false>
-__device__ __forceinline__ void rp64_drain(uint32_t t_addr, int cb0, bf16* __restrict__ obase, long row_stride, int ldo_rt, int ni,
-                                           int nx, bool act_rt, float ea, float eb, const bf16* __restrict__ ybase, long yrow_stride,
-                                           int ldy_rt, float ba, float bb, float bm, float& s1, float& s2) {
-    const int ldo = LDO ? LDO : ldo_rt, ldy = LDY ? LDY : ldy_rt;
-    const bool act = ACT || (!FULL && act_rt);          // the inference epilogue: specialised on full tiles, run-time flag on partial ones
-    float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
-#pragma unroll 1
-    for (int cb = cb0; cb < cb0 + 4; ++cb) {
-        uint32_t v[32];
-        tmem_ld32(t_addr + cb * 32, v);
-        unsigned short yv[BWD ? 32 : 1];
-        if (BWD) {
-            // the saved conv output of the same 32 pixels: all loads in flight before the accumulator wait
-#pragma unroll
-            for (int ii = 0; ii < 4; ++ii) {
-                const unsigned short* yrow = reinterpret_cast<const unsigned short*>(ybase + (long)(cb * 4 + ii) * yrow_stride);
-#pragma unroll
-                for (int x = 0; x < 8; ++x) {
-                    const bool ok = FULL || ((cb * 4 + ii) < ni && x < nx);
-                    yv[BWD ? ii * 8 + x : 0] = ok ? __ldg(yrow + x * ldy) : (unsigned short)0;
-                }
-            }
-        }
-        tmem_wait_ld();
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-            unsigned short* prow = reinterpret_cast<unsigned short*>(obase + (long)(cb * 4 + ii) * row_stride);
-            const bool rok = FULL || (cb * 4 + ii) < ni;
-#pragma unroll
-            for (int x = 0; x < 8; x += 2) {
-                float f0 = __uint_as_float(v[ii * 8 + x]), f1 = __uint_as_float(v[ii * 8 + x + 1]);
-                if (act) {
-                    f0 = fmaxf(fmaf(ea, f0, eb), 0.f);
-                    f1 = fmaf(ea, f1, eb); f1 = fmaxf(f1, 0.f);
-                }
-                const bool ok0 = rok && (FULL || x < nx), ok1 = rok && (FULL || x + 1 < nx);
-                if (!FULL) { if (!ok0) f0 = 0.f; if (!ok1) f1 = 0.f; }
-                const uint32_t pk = pack_bf16x2(f0, f1);
-                if (ok0) prow[x * ldo] = (unsigned short)(pk & 0xffffu);
-                if (ok1) prow[(x + 1) * ldo] = (unsigned short)(pk >> 16);
-                const float r0 = __uint_as_float(pk << 16), r1 = __uint_as_float(pk & 0xffff0000u);
-                if (BWD) {
-                    const float y0 = __uint_as_float((uint32_t)yv[BWD ? ii * 8 + x : 0] << 16);
-                    const float y1 = __uint_as_float((uint32_t)yv[BWD ? ii * 8 + x + 1 : 0] << 16);
-                    const float d0 = fmaf(ba, y0, bb) > 0.f ? r0 : 0.f, d1 = fmaf(ba, y1, bb) > 0.f ? r1 : 0.f;
-                    a1 += d0; a2 = fmaf(d0, y0 - bm, a2);
-                    b1 += d1; b2 = fmaf(d1, y1 - bm, b2);
-                } else {
-                    a1 += r0; a2 = fmaf(r0, r0, a2);
-                    b1 += r1; b2 = fmaf(r1, r1, b2);
-                }
-            }
-        }
-    }
-    s1 = a1 + b1; s2 = a2 + b2;
-}
-
 __global__ void __launch_bounds__(kRpThreads, 1) tc_conv3x3_rp64_kernel(const __grid_constant__ Rp64Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -1626,7 +1708,9 @@ __global__ void __launch_bounds__(kRpThreads, 1) tc_conv3x3_rp64_kernel(const __
     uint64_t* tfull_bar = bars + 5;    // [2]
     uint64_t* tempty_bar = bars + 7;   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp index through a shuffle: tells the compiler that the role branches below are warp-uniform, so the epilogue's global
+    // accesses keep their descriptors in uniform registers instead of re-deriving them per access (3 R2UR per store otherwise)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
@@ -1729,9 +1813,6 @@ __global__ void __launch_bounds__(kRpThreads, 1) tc_conv3x3_rp64_kernel(const __
         for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
             const int tw = (int)(t % p.tilesW), ti = (int)((t / p.tilesW) % p.tilesI), b = (int)(t / tiles_per_img);
             const int x0 = tw * kRpTW, i0 = ti * kRpTI;
-            mbar_wait(&tfull_bar[as], aph);
-            tcgen05_fence_after();
-            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
             // element (i, x) of this thread's channel: out[((b*H + 2*(i0+i) + j) * W + x0 + x) * ldo + oc]
             const long pix0 = ((long)b * 2 * p.HP + 2 * i0 + j) * p.W + x0;
             bf16* obase = p.out + pix0 * p.ldo + oc;
@@ -1739,12 +1820,21 @@ __global__ void __launch_bounds__(kRpThreads, 1) tc_conv3x3_rp64_kernel(const __
             const int nx = p.W - x0 < kRpTW ? p.W - x0 : kRpTW;              // valid columns
             const int ni = p.HP - i0 < kRpTI ? p.HP - i0 : kRpTI;            // valid pair rows
             const bool full = nx == kRpTW && ni == kRpTI;
+            const bool dense = p.ldo == 64 && p.bwd_ldy == 64;
+            uint32_t yv[4][16];
+            if (bwd) {          // the saved-output loads go out before the accumulator is waited for
+                if (full && dense) bwd_load_all_y<true, 64>(yv, ybase, yrow_stride, 64, chalf * 4, ni, nx);
+                else if (full) bwd_load_all_y<true, 0>(yv, ybase, yrow_stride, p.bwd_ldy, chalf * 4, ni, nx);
+                else bwd_load_all_y<false, 0>(yv, ybase, yrow_stride, p.bwd_ldy, chalf * 4, ni, nx);
+            }
+            mbar_wait(&tfull_bar[as], aph);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
             float a1, a2;
             if (bwd) {
-                if (full && p.ldo == 64 && p.bwd_ldy == 64)
-                    rp64_drain<true, true, 64, 64>(t_addr, chalf * 4, obase, row_stride, 64, ni, nx, false, 1.f, 0.f, ybase, yrow_stride, 64, ba, bb, bm, a1, a2);
-                else if (full) rp64_drain<true, true, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, false, 1.f, 0.f, ybase, yrow_stride, p.bwd_ldy, ba, bb, bm, a1, a2);
-                else rp64_drain<false, true, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, false, 1.f, 0.f, ybase, yrow_stride, p.bwd_ldy, ba, bb, bm, a1, a2);
+                if (full && dense) rp64_drain_bwd<true, 64>(t_addr, chalf * 4, obase, row_stride, 64, ni, nx, ba, bb, bm, yv, a1, a2);
+                else if (full) rp64_drain_bwd<true, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, ba, bb, bm, yv, a1, a2);
+                else rp64_drain_bwd<false, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, ba, bb, bm, yv, a1, a2);
             } else {
                 if (full && act) rp64_drain<true, false, 0, 0, true>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, true, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, a1, a2);
                 else if (full && p.ldo == 64) rp64_drain<true, false, 64, 0>(t_addr, chalf * 4, obase, row_stride, 64, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, a1, a2);
@@ -1841,7 +1931,7 @@ __global__ void __launch_bounds__(kKwThreads, 1) tc_conv3x3_kw_kernel(const __gr
     uint64_t* tfull_bar = wfull + 1;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < XS; ++i) { mbar_init(&xfull[i], 1); mbar_init(&xempty[i], 1); }
@@ -2195,7 +2285,7 @@ static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, 
     int rc;
     if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kHpPitch, kHpTH + 2)) < 0) return rc;
     if ((rc = make_map(&p.mapW, w, 9L * C, O, 1, 1, ldk, (long)O * ldk, (long)O * ldk, 128, 1)) < 0) return rc;
-    if ((rc = make_map_linear(&p.mapOut, y, O, W, H, B, ldy, (long)W * ldy, (long)H * W * ldy, kHpTW, kHpTH)) < 0) return rc;
+    p.out = (bf16*)y; p.ldo = ldy;
     p.tilesW = ceil_div(W, kHpTW); p.tilesH = ceil_div(H, kHpTH); p.nimg = B; p.H = H; p.W = W;
     p.cchunks = C / 64; p.num_m_blocks = O / 128;
     p.stat_parts = stat_parts; p.N = O;

@@ -239,10 +239,44 @@ __global__ void __launch_bounds__(kThreads) bn_relu_kernel(const T* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Per-image partial rows -> one row per image, in place (row 0 of each image).  The per-image reduction grids write
+// ~resident-capacity / B rows per image: 6 at batch 64, but 440 for a single large image, which one FC block per image
+// would then sum alone (390 us at C = 1024).  Block = 32 columns x 8 row groups, grid = (ceil(width / 32), B); fixed
+// summation order (row groups, then rows), double accumulation.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) img_parts_sum_kernel(float* __restrict__ parts, int nparts, int width) {
+    __shared__ double red[8][32];
+    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cl;
+    float* base = parts + (long)blockIdx.y * nparts * width;
+    double acc = 0.0;
+    if (col < width) {
+        int i = g;
+        for (; i + 24 < nparts; i += 32) {
+            const float a0 = base[(long)i * width + col], a1 = base[(long)(i + 8) * width + col];
+            const float a2 = base[(long)(i + 16) * width + col], a3 = base[(long)(i + 24) * width + col];
+            acc += (double)a0; acc += (double)a1; acc += (double)a2; acc += (double)a3;
+        }
+        for (; i < nparts; i += 8) acc += (double)base[(long)i * width + col];
+    }
+    red[g][cl] = acc;
+    __syncthreads();
+    if (g == 0 && col < width) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][cl];
+        base[col] = (float)t;
+    }
+}
+// rows per image beyond which the FC kernels get the pre-reduced single row (launch + ~5 us against nparts sequential loads)
+constexpr int kPartsPreReduce = 16;
+
+// ---------------------------------------------------------------------------------------------------------
 // SE excitation: p = mean_hw, z = relu(W1 p), s = sigmoid(W2 z)      UCA:54-59,65-68   (one block per image)
+// parts rows of image b start at row b * img_rows; the first nparts of them are summed.
 // ---------------------------------------------------------------------------------------------------------
 template <int NSTAT>
-__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ parts, int nparts, int C, int Cr,
+__global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ parts, int nparts, int img_rows, int C, int Cr,
                                                     float inv_hw, const float* __restrict__ w1,
                                                     const float* __restrict__ w2, float* __restrict__ p_out,
                                                     float* __restrict__ z_out, float* __restrict__ s_out,
@@ -255,9 +289,9 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ pa
     for (int c = tid; c < C; c += blockDim.x) {
         double t = 0.0, t3 = 0.0, ty = 0.0;
         for (int i = 0; i < nparts; ++i) {
-            if (NSTAT == 1) t += (double)parts[((long)b * nparts + i) * C + c];
+            if (NSTAT == 1) t += (double)parts[((long)b * img_rows + i) * C + c];
             else {
-                const float* row = parts + ((long)b * nparts + i) * 2 * C + c;
+                const float* row = parts + ((long)b * img_rows + i) * 2 * C + c;
                 t3 += (double)row[0];
                 ty += (double)row[C];
             }
@@ -282,7 +316,18 @@ __global__ void __launch_bounds__(256) se_fc_kernel(const float* __restrict__ pa
     __syncthreads();
     for (int c = tid; c < C; c += blockDim.x) {
         float t = 0.f;
-        for (int j = 0; j < Cr; ++j) t = fmaf(w2[(long)c * Cr + j], z[j], t);
+        if ((Cr & 3) == 0) {
+            // the thread's own row of W2 as 16-byte loads (Cr = C / 16 is a multiple of 4 for every layer of the model); same
+            // summation order as the scalar loop
+            const float4* wr = reinterpret_cast<const float4*>(w2 + (long)c * Cr);
+            for (int j4 = 0; j4 < Cr / 4; ++j4) {
+                const float4 w = __ldg(wr + j4);
+                t = fmaf(w.x, z[4 * j4], t); t = fmaf(w.y, z[4 * j4 + 1], t);
+                t = fmaf(w.z, z[4 * j4 + 2], t); t = fmaf(w.w, z[4 * j4 + 3], t);
+            }
+        } else {
+            for (int j = 0; j < Cr; ++j) t = fmaf(w2[(long)c * Cr + j], z[j], t);
+        }
         s_out[(long)b * C + c] = 1.f / (1.f + expf(-t));
     }
 }
@@ -1322,7 +1367,7 @@ __global__ void __launch_bounds__(kThreads, 4) se_squeeze_kernel(const T* __rest
 
 // SE backward FC chain fed by the four merged sums (one block per image); also stores the per-image sums
 // sums[b][4][C] for bn_bwd_finalize_se_kernel.
-__global__ void __launch_bounds__(256) se_fc_bwd_fused_kernel(const float* __restrict__ parts, int nparts, int C, int Cr,
+__global__ void __launch_bounds__(256) se_fc_bwd_fused_kernel(const float* __restrict__ parts, int nparts, int img_rows, int C, int Cr,
                                                               const float* __restrict__ w1, const float* __restrict__ w2,
                                                               const float* __restrict__ z, const float* __restrict__ s,
                                                               const float* __restrict__ scale,
@@ -1339,7 +1384,7 @@ __global__ void __launch_bounds__(256) se_fc_bwd_fused_kernel(const float* __res
     for (int c = tid; c < C; c += blockDim.x) {
         double t[2] = {0.0, 0.0};
         for (int i = 0; i < nparts; ++i) {
-            const float* row = parts + ((long)b * nparts + i) * 2 * C + c;
+            const float* row = parts + ((long)b * img_rows + i) * 2 * C + c;
             t[0] += (double)row[0];
             t[1] += (double)row[C];
         }
@@ -1356,15 +1401,27 @@ __global__ void __launch_bounds__(256) se_fc_bwd_fused_kernel(const float* __res
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
-    for (int j = warp; j < Cr; j += nwarps) {
-        float t = 0.f;
-        for (int c = lane; c < C; c += 32) t = fmaf(dpre2[c], w2[(long)c * Cr + j], t);
-        t = warp_sum(t);
-        if (lane == 0) {
-            t = z[(long)b * Cr + j] > 0.f ? t : 0.f;
-            dz[j] = t;
-            dz_out[(long)b * Cr + j] = t;
+    // dz[j] = (sum_c dpre2[c] * W2[c][j]) * (z[j] > 0).  W2 is (C, Cr) row-major: lanes run along j (a warp reads whole
+    // rows, coalesced) and each warp walks a contiguous slice of c; the warps' partial vectors are then added in a fixed
+    // order.  (Lanes along c read one element out of every row: 32 sectors per load, 60 us per call at C = 1024.)
+    float* wpart = sm + C + Cr;                       // [nwarps][Cr]
+    const int cper = (C + nwarps - 1) / nwarps;
+    for (int j0 = 0; j0 < Cr; j0 += 32) {
+        const int j = j0 + lane;
+        if (j < Cr) {
+            float t = 0.f;
+            const int c0 = warp * cper, c1 = c0 + cper < C ? c0 + cper : C;
+            for (int c = c0; c < c1; ++c) t = fmaf(dpre2[c], __ldg(w2 + (long)c * Cr + j), t);
+            wpart[warp * Cr + j] = t;
         }
+    }
+    __syncthreads();
+    for (int j = tid; j < Cr; j += blockDim.x) {
+        float t = 0.f;
+        for (int w = 0; w < nwarps; ++w) t += wpart[w * Cr + j];
+        t = z[(long)b * Cr + j] > 0.f ? t : 0.f;
+        dz[j] = t;
+        dz_out[(long)b * Cr + j] = t;
     }
     __syncthreads();
     for (int c = tid; c < C; c += blockDim.x) {
@@ -2484,9 +2541,14 @@ int unetca_plane_scale_add(const float* x, const float* s, const float* t, float
 
 int unetca_se_fc(const float* pool_parts, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,
                  float* p, float* z, float* s, void* stream) {
-    se_fc_kernel<1><<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(pool_parts, nparts, C, Cr, 1.f / (float)hw,
-                                                                              w1, w2, p, z, s, nullptr, nullptr, nullptr,
-                                                                              nullptr);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rows = nparts;
+    if (nparts > kPartsPreReduce) {
+        img_parts_sum_kernel<<<dim3(ceil_div(C, 32), B), 256, 0, st>>>(const_cast<float*>(pool_parts), nparts, C);
+        rows = 1;
+    }
+    se_fc_kernel<1><<<B, 256, (C + Cr) * sizeof(float), st>>>(pool_parts, rows, nparts, C, Cr, 1.f / (float)hw, w1, w2, p, z, s,
+                                                             nullptr, nullptr, nullptr, nullptr);
     return check_launch("se_fc");
 }
 
@@ -2521,8 +2583,14 @@ int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img
 int unetca_se_fc3(const float* parts2, int nparts, int B, int C, int Cr, long hw, const float* w1, const float* w2,
                   const float* scale, const float* shift, const float* mean, float* p, float* z, float* s, float* sums34,
                   void* stream) {
-    se_fc_kernel<3><<<B, 256, (C + Cr) * sizeof(float), (cudaStream_t)stream>>>(parts2, nparts, C, Cr, 1.f / (float)hw,
-                                                                              w1, w2, p, z, s, sums34, scale, shift, mean);
+    cudaStream_t st = (cudaStream_t)stream;
+    int rows = nparts;
+    if (nparts > kPartsPreReduce) {
+        img_parts_sum_kernel<<<dim3(ceil_div(2 * C, 32), B), 256, 0, st>>>(const_cast<float*>(parts2), nparts, 2 * C);
+        rows = 1;
+    }
+    se_fc_kernel<3><<<B, 256, (C + Cr) * sizeof(float), st>>>(parts2, rows, nparts, C, Cr, 1.f / (float)hw, w1, w2, p, z, s, sums34,
+                                                             scale, shift, mean);
     return check_launch("se_fc3");
 }
 
@@ -2744,8 +2812,13 @@ int unetca_se_fc_bwd_fused(const float* parts, int nparts, int B, int C, int Cr,
                            const float* mean, const float* sums34, float* sums, float* dpre2, float* dz, float* dp,
                            float* dw1, float* dw2, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    se_fc_bwd_fused_kernel<<<B, 256, (C + Cr) * sizeof(float), st>>>(parts, nparts, C, Cr, w1, w2, z, s, scale, shift, mean,
-                                                                     sums34, sums, dpre2, dz, dp);
+    int rows = nparts;
+    if (nparts > kPartsPreReduce) {
+        img_parts_sum_kernel<<<dim3(ceil_div(2 * C, 32), B), 256, 0, st>>>(const_cast<float*>(parts), nparts, 2 * C);
+        rows = 1;
+    }
+    se_fc_bwd_fused_kernel<<<B, 256, (C + Cr + 8 * Cr) * sizeof(float), st>>>(parts, rows, nparts, C, Cr, w1, w2, z, s, scale, shift,
+                                                                              mean, sums34, sums, dpre2, dz, dp);
     se_fc_wgrad_kernel<<<ceil_div((long)C * Cr, 256), 256, 0, st>>>(B, C, Cr, dpre2, dz, p, z, dw1, dw2);
     return check_launch("se_fc_bwd_fused");
 }
