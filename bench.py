@@ -436,14 +436,25 @@ def record_timeline(step, x, y, rank, world, path):
     end_all = max(b for _, _, b, _ in ks) - t0
     # compute kernels that ran while an NCCL kernel was active, with their durations
     under = [(n, b - a) for n, a, b in comp if overlap([(a, b)], nccl) > 0.25 * (b - a)]
-    out = {"step_us": end_all, "kernels": len(ks), "nccl_kernels": len(nccl), "nccl_us": sum(b - a for a, b in nccl),
+    # idle time of the compute stream: gaps between consecutive non-NCCL kernels (launch latency, host not far enough ahead)
+    gaps = []
+    cur_end = comp[0][2]
+    for (n, a, b), (pn, _, _) in zip(comp[1:], comp[:-1]):
+        if a > cur_end:
+            gaps.append((a - cur_end, pn[:50], n[:50]))
+        cur_end = max(cur_end, b)
+    gaps.sort(reverse=True)
+    out = {"idle_us_between_compute_kernels": sum(g[0] for g in gaps), "gaps_over_20us": len([g for g in gaps if g[0] > 20]),
+           "largest_gaps": [{"us": round(g[0], 1), "after": g[1], "before": g[2]} for g in gaps[:25]],
+           "step_us": end_all, "kernels": len(ks), "nccl_kernels": len(nccl), "nccl_us": sum(b - a for a, b in nccl),
            "nccl_us_under_compute": overlap(nccl, comp_iv), "tail_after_last_compute_us": end_all - end_comp,
            "compute_us": sum(b - a for a, b in comp_iv),
            "compute_kernels_running_under_nccl": [{"name": n[:60], "us": d} for n, d in under][:40],
            "nccl_intervals_us": [[round(a, 1), round(b, 1)] for a, b in nccl][:40]}
     with open(path, "w") as f:
         json.dump(out, f, indent=1)
-    return {k: out[k] for k in ("step_us", "nccl_kernels", "nccl_us", "nccl_us_under_compute", "tail_after_last_compute_us")}
+    return {k: out[k] for k in ("step_us", "kernels", "idle_us_between_compute_kernels", "gaps_over_20us", "nccl_kernels", "nccl_us",
+                                "nccl_us_under_compute", "tail_after_last_compute_us")}
 
 
 def extra_dp_parity(dev, rank, world):

@@ -156,6 +156,18 @@ int unetca_sum_rows(const float* parts, int nrows, long row_stride, int n, float
 
 /* ---- outc 1x1 conv -> class logits (UCA:125,162), CrossEntropyLoss(ignore_index) (UCA:465,344), argmax (UCA:220) */
 int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, const float* bias, int nc, float* logits, int B, long HW, void* stream);
+/* The output head fused with the last DoubleConv's elementwise passes (UCA:86-94 of conv4, then UCA:162; bf16, dense C = 64,
+ * nc <= 2, HW % 128 == 0 — otherwise UNETCA_ERR_UNSUPPORTED (-3) and the caller runs the separate passes).  The block output
+ * h = relu(scale*y2 + shift) * s[b,c] and its gradient W^T dlogits are per-pixel functions of y2 and of the 8 bytes of dlogits:
+ * neither full-resolution tensor is written or read.
+ *   se_scale_outc_fwd:   y2 -> logits (B,nc,HW) NCHW fp32
+ *   outc_bn_bwd_reduce:  (g = dlogits up to *gscale, y2) -> parts_bn rows [B * *nparts][2][C] exactly as unetca_se_bn_bwd_reduce /
+ *                        unetca_bn_bwd_reduce leave them (*nparts rows per image), and the outc gradients dw (nc,C), db (nc);
+ *                        s: the SE scale of the block (null without SE); parts_oc: scratch, parts_oc_floats floats
+ *   outc_bn_bwd_apply:   (g, y2) -> dY2, arguments as unetca_bn_bwd_apply */
+int unetca_se_scale_outc_fwd(int dtype, const void* y, int ldy, int B, long HW, int C, const float* scale, const float* shift, const float* s, const float* w, const float* bias, int nc, float* logits, void* stream);
+int unetca_outc_bn_bwd_reduce(int dtype, const float* g, const float* gscale, const float* w, int nc, const void* y, int ldy, int B, long HW, int C, const float* scale, const float* shift, const float* mean, const float* s, float* parts_bn, int* nparts, float* parts_oc, long parts_oc_floats, float* dw, float* db, void* stream);
+int unetca_outc_bn_bwd_apply(int dtype, const float* g, const float* gscale, const float* w, int nc, const void* y, int ldy, void* dy, int lddy, int B, long HW, int C, const float* scale, const float* shift, const float* mean, const float* invstd, const float* s, const float* dp, const float* coef, void* stream);
 int unetca_outc_bwd(int dtype, const float* g, const float* gscale, const void* x, int ldx, void* dx, int lddx, int C, const float* w, int nc, int B, long HW, float* parts, float* dw, float* db, void* stream);
 /* loss_out[0] = mean CE over valid pixels (NaN when none), loss_out[1] = #valid; g = un-normalised dlogits;
  * gscale_out[0] = upstream/#valid; mask = argmax class map (first maximum wins); target/g/mask optional */

@@ -1928,6 +1928,243 @@ __global__ void __launch_bounds__(kThreads, 3) outc_bwd_stream_kernel(const floa
     }
 }
 // finalize: dW[o][c] (nc x C) and db[o] from parts laid out with the padded NC
+// ---------------------------------------------------------------------------------------------------------
+// Output head fused with the last DoubleConv's elementwise passes (bf16, C = 64, nc <= 2, HW % 128 == 0).
+// The 1x1 outc conv (UCA:125,162) reads and its backward writes a [B,H,W,64] tensor at full resolution: the block output
+// h = relu(bn2(y2)) * s going in (written by se_scale, read by outc_fwd, read again by outc_bwd), and its gradient
+// dh = W^T dlogits coming back (written by outc_bwd, read by the SE+BN2 reduction and by the BN2 apply pass) — 2.1 GB
+// each at batch 64, five passes, none of which holds information: h is a per-pixel function of y2, dh of the 8 bytes of
+// dlogits per pixel.  So neither tensor exists any more:
+//   forward   se_scale_outc_fwd:      y2 -> logits                       (h formed per pixel, rounded to bf16 as before)
+//   backward  outc_bn_bwd_reduce:     (dlogits, y2) -> S1, S2 partial sums of the SE+BN2 backward, and dW_outc, db_outc
+//             outc_bn_bwd_apply:      (dlogits, y2) -> dY2
+// h and dh stay in fp32 registers (the unfused passes rounded them to bf16 on their way through memory), so the fused head
+// is slightly CLOSER to the fp32 reference than the passes it replaces.  The kernels are sized for the ALU, not only for
+// HBM: at 64 channels a pass has ~9 instructions per element before it becomes issue-bound, so per-(image, channel) factors
+// are folded into the weights / taken out of the sums (s into W_outc, gscale into W_outc^T, the mean out of sum dz*(y-mean)).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 3) se_scale_outc_fwd_stream_kernel(const bf16* __restrict__ y, const float* __restrict__ scale,
+                                                                               const float* __restrict__ shift, const float* __restrict__ s,
+                                                                               const float* __restrict__ w, const float* __restrict__ bias,
+                                                                               int nc, float* __restrict__ logits, long HW, long chunk) {
+    extern __shared__ __align__(128) uint8_t st_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kOcFwdStages];
+    __shared__ float res[2][kOcPix];
+    constexpr int C = 64, VEC = 8;
+    const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > HW) p1 = HW;
+    const int b = blockIdx.y;
+    const long nbytes = (p1 - p0) * C * 2;
+    const int ntiles = (int)((nbytes + kOcTile - 1) / kOcTile);
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(y) + ((long)b * HW + p0) * C * 2;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kOcFwdStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const long o = (long)t * kOcTile;
+        const uint32_t bytes = (uint32_t)(nbytes - o < kOcTile ? nbytes - o : kOcTile);
+        mbar_expect_tx(&full_bar[t % kOcFwdStages], bytes);
+        bulk_load_1d(st_smem + (t % kOcFwdStages) * kOcTile, xb + o, bytes, &full_bar[t % kOcFwdStages]);
+    };
+    if (threadIdx.x == 0)
+        for (int t = 0; t < kOcFwdStages && t < ntiles; ++t) issue(t);
+    float wr[2][VEC], a[VEC], sh[VEC], gg[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        a[i] = scale[sub * VEC + i]; sh[i] = shift[sub * VEC + i];
+        gg[i] = s ? s[(long)b * C + sub * VEC + i] : 1.f;
+#pragma unroll
+        for (int o = 0; o < 2; ++o) wr[o][i] = o < nc ? w[o * C + sub * VEC + i] * gg[i] : 0.f;      // W_outc * s[b, c]
+    }
+    const float bo = (threadIdx.x >> 7) < nc ? bias[threadIdx.x >> 7] : 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+        const long o = (long)t * kOcTile;
+        const int npx = (int)((nbytes - o < kOcTile ? nbytes - o : kOcTile) / (C * 2));
+        mbar_wait(&full_bar[t % kOcFwdStages], (uint32_t)((t / kOcFwdStages) & 1));
+        const bf16* xs = reinterpret_cast<const bf16*>(st_smem + (t % kOcFwdStages) * kOcTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int px = pl + 32 * k;
+            float acc0 = 0.f, acc1 = 0.f;
+            if (px < npx) {
+                float v[VEC];
+                load_vec(xs + px * C + sub * VEC, v);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) {
+                    const float h = fmaxf(fmaf(a[i], v[i], sh[i]), 0.f);
+                    acc0 = fmaf(h, wr[0][i], acc0); acc1 = fmaf(h, wr[1][i], acc1);
+                }
+            }
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 4); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 4);
+            if (sub == 0) { res[0][px] = acc0; res[1][px] = acc1; }
+        }
+        __syncthreads();                                       // tile consumed, results staged
+        if (threadIdx.x == 0 && t + kOcFwdStages < ntiles) issue(t + kOcFwdStages);
+        {
+            const int o2 = threadIdx.x >> 7, px = threadIdx.x & 127;
+            if (o2 < nc && px < npx) logits[((long)b * nc + o2) * HW + p0 + (long)t * kOcPix + px] = res[o2][px] + bo;
+        }
+        __syncthreads();                                       // res may be overwritten
+    }
+}
+
+// MODE 0: reduction (no store): parts_bn [(b*gridDim.x + blk)][2][C] = (sum m*dh, sum m*dh*(y - mean)), m = (a*y + b > 0);
+//         parts_oc [(b*gridDim.x + blk)][2*C + 2] = (sum_p g_o * h, sum_p g_o) for the outc weight / bias gradients.
+// MODE 1: apply: dY2 = g*dz - y*k2 + k0 as in bn_bwd_apply_stream_kernel, dz = m * (dh*(g*s) + g*dp/HW) (SE) or m * dh * g.
+template <int MODE, bool SE>
+__global__ void __launch_bounds__(kThreads, MODE == 0 ? 2 : 3) outc_bn_bwd_stream_kernel(const float* __restrict__ g, const float* __restrict__ gscale,
+                                                                         const float* __restrict__ w, int nc,
+                                                                         const bf16* __restrict__ y, bf16* __restrict__ dy, long HW,
+                                                                         long chunk, float inv_hw, const float* __restrict__ scale,
+                                                                         const float* __restrict__ shift, const float* __restrict__ mean,
+                                                                         const float* __restrict__ invstd, const float* __restrict__ s,
+                                                                         const float* __restrict__ dp, const float* __restrict__ coef,
+                                                                         float* __restrict__ parts_bn, float* __restrict__ parts_oc) {
+    extern __shared__ __align__(128) uint8_t st_smem[];
+    __shared__ __align__(8) uint64_t full_bar[kOcBwdStages];
+    constexpr int C = 64, VEC = 8, NC = 2;
+    const int sub = threadIdx.x & 7, pl = threadIdx.x >> 3;
+    const long p0 = (long)blockIdx.x * chunk;
+    long p1 = p0 + chunk; if (p1 > HW) p1 = HW;
+    const int b = blockIdx.y;
+    const long nbytes = p1 > p0 ? (p1 - p0) * C * 2 : 0;
+    const int ntiles = (int)((nbytes + kOcTile - 1) / kOcTile);
+    const uint8_t* xb = reinterpret_cast<const uint8_t*>(y) + ((long)b * HW + p0) * C * 2;
+    uint8_t* ob = MODE == 1 ? reinterpret_cast<uint8_t*>(dy) + ((long)b * HW + p0) * C * 2 : nullptr;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kOcBwdStages; ++i) mbar_init(&full_bar[i], 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    auto issue = [&](int t) {
+        const long o = (long)t * kOcTile;
+        const uint32_t bytes = (uint32_t)(nbytes - o < kOcTile ? nbytes - o : kOcTile);
+        const uint32_t gb = bytes / (C * 2) * 4;                         // dlogits bytes per class (a multiple of 16)
+        uint8_t* st = st_smem + (t % kOcBwdStages) * kOcBwdStage;
+        mbar_expect_tx(&full_bar[t % kOcBwdStages], bytes + nc * gb);
+        bulk_load_1d(st, xb + o, bytes, &full_bar[t % kOcBwdStages]);
+        for (int o2 = 0; o2 < nc; ++o2)
+            bulk_load_1d(st + kOcTile + o2 * kOcPix * 4, g + ((long)b * nc + o2) * HW + p0 + (long)t * kOcPix, gb,
+                         &full_bar[t % kOcBwdStages]);
+    };
+    // MODE 0 refills a stage as soon as every thread has consumed it (all stages in flight); MODE 1 after its store has read it
+    if (threadIdx.x == 0)
+        for (int t = 0; t < (MODE == 0 ? kOcBwdStages : kOcBwdStages - 1) && t < ntiles; ++t) issue(t);
+    const float gs = *gscale;
+    float wv[NC][VEC], a[VEC], sh[VEC], gg[VEC];
+    float acc[NC][VEC], accb[NC], sbn[2][VEC], mu[VEC], m0[VEC], m1[VEC], k2[VEC], k0[VEC];
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        const int c = sub * VEC + i;
+        a[i] = scale[c]; sh[i] = shift[c];
+        gg[i] = s ? s[(long)b * C + c] : 1.f;
+#pragma unroll
+        for (int o = 0; o < NC; ++o) { wv[o][i] = o < nc ? w[o * C + c] * gs : 0.f; acc[o][i] = 0.f; }      // W_outc^T * gscale
+        sbn[0][i] = sbn[1][i] = 0.f;
+        mu[i] = MODE == 0 ? mean[c] : 0.f;
+        if (MODE == 1) {
+            const float gc = coef[c], c1 = coef[C + c], c2 = coef[2 * C + c];
+            const float sv = SE ? s[(long)b * C + c] : 1.f, dpv = SE ? dp[(long)b * C + c] * inv_hw : 0.f;
+            k2[i] = gc * c2 * invstd[c];
+            k0[i] = mean[c] * k2[i] - gc * c1;
+            m0[i] = gc * sv; m1[i] = gc * dpv;
+        } else { k2[i] = k0[i] = m0[i] = m1[i] = 0.f; }
+    }
+    accb[0] = accb[1] = 0.f;
+    for (int t = 0; t < ntiles; ++t) {
+        const long o = (long)t * kOcTile;
+        const int bytes = (int)(nbytes - o < kOcTile ? nbytes - o : kOcTile);
+        const int npx = bytes / (C * 2);
+        uint8_t* st = st_smem + (t % kOcBwdStages) * kOcBwdStage;
+        mbar_wait(&full_bar[t % kOcBwdStages], (uint32_t)((t / kOcBwdStages) & 1));
+        bf16* xs = reinterpret_cast<bf16*>(st);
+        const float* gsm = reinterpret_cast<const float*>(st + kOcTile);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int px = pl + 32 * k;
+            if (px < npx) {
+                float gv[NC];
+#pragma unroll
+                for (int o2 = 0; o2 < NC; ++o2) gv[o2] = o2 < nc ? gsm[o2 * kOcPix + px] : 0.f;
+                float v[VEC], d[VEC];
+                load_vec(xs + px * C + sub * VEC, v);
+#pragma unroll
+                for (int i = 0; i < VEC; ++i) d[i] = fmaf(gv[1], wv[1][i], gv[0] * wv[0][i]);          // dh = W^T g * gscale
+                if (MODE == 0) {
+#pragma unroll
+                    for (int o2 = 0; o2 < NC; ++o2) if (sub == 0) accb[o2] += gv[o2];
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const float pre = fmaf(a[i], v[i], sh[i]);
+                        if (pre > 0.f) {
+                            // relu(pre) = pre here; the SE scale s[b,c] multiplies the finished sums (one image per block)
+                            acc[0][i] = fmaf(gv[0], pre, acc[0][i]);
+                            acc[1][i] = fmaf(gv[1], pre, acc[1][i]);
+                            sbn[0][i] += d[i];
+                            sbn[1][i] = fmaf(d[i], v[i], sbn[1][i]);                                   // the mean is taken out at the end
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        const float da = SE ? fmaf(d[i], m0[i], m1[i]) : d[i] * m0[i];
+                        const float dz = fmaf(a[i], v[i], sh[i]) > 0.f ? da : 0.f;
+                        d[i] = fmaf(-v[i], k2[i], dz) + k0[i];
+                    }
+                    store_vec(xs + px * C + sub * VEC, d);
+                }
+            }
+        }
+        if (MODE == 1) {
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_store_1d(ob + o, xs, (uint32_t)bytes);
+                tma_store_commit();
+                if (t >= 1) {
+                    tma_store_wait_read1();
+                    if (t - 1 + kOcBwdStages < ntiles) issue(t - 1 + kOcBwdStages);
+                } else if (kOcBwdStages - 1 < ntiles) {
+                    issue(kOcBwdStages - 1);
+                }
+            }
+        } else {
+            __syncthreads();                                   // every thread is done with this stage
+            if (threadIdx.x == 0 && t + kOcBwdStages < ntiles) issue(t + kOcBwdStages);
+        }
+    }
+    if (MODE == 1) {
+        if (threadIdx.x == 0) tma_store_wait_all();
+        return;
+    }
+    const long row = (long)blockIdx.y * gridDim.x + blockIdx.x;
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) {
+        sbn[1][i] = fmaf(-mu[i], sbn[0][i], sbn[1][i]);          // sum dz*(y - mean) = sum dz*y - mean * sum dz
+        acc[0][i] *= gg[i]; acc[1][i] *= gg[i];                  // h = relu(pre) * s[b,c]
+    }
+    block_reduce_rows<2, VEC>(sbn, C, 8, kThreads / 8, parts_bn + row * 2 * C);
+    float* out = parts_oc + row * (NC * C + NC);
+    block_reduce_rows<NC, VEC>(acc, C, 8, kThreads / 8, out);
+    __shared__ float bred[kThreads];
+#pragma unroll
+    for (int o2 = 0; o2 < NC; ++o2) {
+        __syncthreads();
+        bred[threadIdx.x] = sub == 0 ? accb[o2] : 0.f;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tsum = 0.f;
+            for (int i = 0; i < kThreads; ++i) tsum += bred[i];
+            out[NC * C + o2] = tsum;
+        }
+    }
+}
+
 __global__ void outc_bwd_finalize_kernel(const float* __restrict__ parts, int nparts, int NCpad, int nc, int C,
                                          const float* __restrict__ gscale, float* __restrict__ dw,
                                          float* __restrict__ db) {
@@ -3026,6 +3263,72 @@ int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, co
 }
 
 // parts scratch: unetca_max_parts() * (8*C + 8) floats
+// Fused output head (see se_scale_outc_fwd_stream_kernel): bf16, dense C = 64 tensors, nc <= 2, HW % 128 == 0; anything else
+// returns UNETCA_ERR_UNSUPPORTED and the caller runs the separate passes.
+static bool head_fusable(int dtype, int ldy, int C, int nc, long HW) {
+    return dtype == UNETCA_DTYPE_BF16 && g_apply_stream > 0 && C == 64 && ldy == 64 && nc >= 1 && nc <= 2 && HW % kOcPix == 0;
+}
+int unetca_se_scale_outc_fwd(int dtype, const void* y, int ldy, int B, long HW, int C, const float* scale, const float* shift,
+                             const float* s, const float* w, const float* bias, int nc, float* logits, void* stream) {
+    if (!head_fusable(dtype, ldy, C, nc, HW)) { set_error("se_scale_outc_fwd: unsupported shape / dtype"); return UNETCA_ERR_UNSUPPORTED; }
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(se_scale_outc_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOcFwdSmem) != cudaSuccess) {
+            set_error("se_scale_outc_fwd: cudaFuncSetAttribute failed"); return UNETCA_ERR_CUDA;
+        }
+        attr_done = true;
+    }
+    const long chunk = (long)g_apply_stream * 2 * kOcPix;
+    dim3 grid(ceil_div(HW, chunk), B);
+    se_scale_outc_fwd_stream_kernel<<<grid, kThreads, kOcFwdSmem, (cudaStream_t)stream>>>((const bf16*)y, scale, shift, s, w, bias, nc, logits, HW, chunk);
+    return check_launch("se_scale_outc_fwd");
+}
+// parts_bn: rows as unetca_se_bn_bwd_reduce writes them ([B * *nparts][2][C], *nparts rows per image); parts_oc: scratch of
+// B * *nparts * (2*C + 2) floats; dw (nc, C) and db (nc) receive the outc gradients (times *gscale).
+int unetca_outc_bn_bwd_reduce(int dtype, const float* g, const float* gscale, const float* w, int nc, const void* y, int ldy,
+                              int B, long HW, int C, const float* scale, const float* shift, const float* mean, const float* s,
+                              float* parts_bn, int* nparts, float* parts_oc, long parts_oc_floats, float* dw, float* db,
+                              void* stream) {
+    if (!head_fusable(dtype, ldy, C, nc, HW)) { set_error("outc_bn_bwd_reduce: unsupported shape / dtype"); return UNETCA_ERR_UNSUPPORTED; }
+    static int sslots = 0;
+    if (!sslots) sslots = resident_blocks_smem(outc_bn_bwd_stream_kernel<0, false>, kOcBwdSmem);
+    if (sslots <= 0) { set_error("outc_bn_bwd_reduce: kernel does not fit"); return UNETCA_ERR_CUDA; }
+    long per_img = sslots / B; if (per_img < 1) per_img = 1;
+    const long chunk = ceil_div(ceil_div(HW, per_img), (long)kOcPix) * kOcPix;
+    dim3 grid(ceil_div(HW, chunk), B);
+    UNETCA_REQUIRE((long)grid.x * B <= kMaxParts + B && (long)grid.x * B * (2 * C + 2) <= parts_oc_floats,
+                   "outc_bn_bwd_reduce: scratch too small for %d x %d partial rows", (int)grid.x, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    outc_bn_bwd_stream_kernel<0, false><<<grid, kThreads, kOcBwdSmem, st>>>(g, gscale, w, nc, (const bf16*)y, nullptr, HW, chunk, 0.f, scale,
+                                                                          shift, mean, nullptr, s, nullptr, nullptr, parts_bn, parts_oc);
+    outc_bwd_finalize_kernel<<<ceil_div((long)(nc * C + nc) * 32, 128), 128, 0, st>>>(parts_oc, grid.x * B, 2, nc, C, gscale, dw, db);
+    *nparts = grid.x;
+    return check_launch("outc_bn_bwd_reduce");
+}
+int unetca_outc_bn_bwd_apply(int dtype, const float* g, const float* gscale, const float* w, int nc, const void* y, int ldy, void* dy,
+                             int lddy, int B, long HW, int C, const float* scale, const float* shift, const float* mean,
+                             const float* invstd, const float* s, const float* dp, const float* coef, void* stream) {
+    if (!head_fusable(dtype, ldy, C, nc, HW) || lddy != C) { set_error("outc_bn_bwd_apply: unsupported shape / dtype"); return UNETCA_ERR_UNSUPPORTED; }
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(outc_bn_bwd_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOcBwdSmem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(outc_bn_bwd_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOcBwdSmem);
+        if (e != cudaSuccess) { set_error("outc_bn_bwd_apply: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    const long chunk = (long)g_apply_stream * 2 * kOcPix;            // 16 tiles of 128 pixels per block by default
+    dim3 grid(ceil_div(HW, chunk), B);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float ihw = 1.f / (float)HW;
+    if (s && dp)
+        outc_bn_bwd_stream_kernel<1, true><<<grid, kThreads, kOcBwdSmem, st>>>(g, gscale, w, nc, (const bf16*)y, (bf16*)dy, HW, chunk, ihw, scale,
+                                                                             shift, mean, invstd, s, dp, coef, nullptr, nullptr);
+    else
+        outc_bn_bwd_stream_kernel<1, false><<<grid, kThreads, kOcBwdSmem, st>>>(g, gscale, w, nc, (const bf16*)y, (bf16*)dy, HW, chunk, ihw, scale,
+                                                                              shift, mean, invstd, nullptr, nullptr, coef, nullptr, nullptr);
+    return check_launch("outc_bn_bwd_apply");
+}
+
 int unetca_outc_bwd(int dtype, const float* g, const float* gscale, const void* x, int ldx, void* dx, int lddx, int C,
                     const float* w, int nc, int B, long HW, float* parts, float* dw, float* db, void* stream) {
     UNETCA_REQUIRE(nc >= 1 && nc <= 8, "outc: num_classes %d unsupported (1..8)", nc);

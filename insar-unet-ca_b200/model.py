@@ -300,6 +300,7 @@ def sv_pairs(col, B, H, W):
 
 
 FUSE_SQUEEZE = True      # inference: take the SE squeeze in the second conv's epilogue (False: separate read-only pass)
+FUSE_HEAD = True          # outc (UCA:162) fused with the last block's SE-scale / BN2-backward passes: its input and input-gradient never exist
 FUSE_BN_BWD_STATS = True  # training: BN1-backward statistics in the epilogue of the dgrad conv that writes dA1 (False: reduce pass)
 
 
@@ -342,9 +343,16 @@ def _check_input(model, x):
 # =======================================================================================================
 # forward
 # =======================================================================================================
-def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train, dt, tdt, keep):
-    """One DoubleConv (+SE, + the following MaxPool when `pooled` is given).  Returns what backward needs."""
-    dev = out_view.device
+def _head_ok(dt, O, nc, hw):
+    """Shapes the fused output-head kernels take (unetca_se_scale_outc_fwd and friends)."""
+    return FUSE_HEAD and dt == _lib.BF16 and O == 64 and 1 <= nc <= 2 and hw % 128 == 0
+
+
+def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train, dt, tdt, keep, head=None):
+    """One DoubleConv (+SE, + the following MaxPool when `pooled` is given).  Returns what backward needs.
+    head = (outc module, logits): the last block — its SE-scale pass also applies the 1x1 outc conv and writes the logits;
+    the block output itself is never stored (out_view is None)."""
+    dev = (out_view if out_view is not None else head[1]).device
     st = _stream()
     C, O = blk.cin, blk.cout
     npix = B * Hl * Wl
@@ -381,7 +389,8 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
 
     sp = _ptr(parts) if train else None
     if not train and not keep and dt == _lib.BF16:
-        done = _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, dt, tdt, bn_params, parts, nparts)
+        done = _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, dt, tdt, bn_params, parts, nparts,
+                                       head)
         if done:
             return sv
     # ---- conv1 -> BN -> ReLU
@@ -415,7 +424,11 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
         _lib.call("unetca_se_fc3", _ptr(parts), nparts.value, B, O, Cr, Hl * Wl, _ptr(w1), _ptr(w2), _ptr(scale2),
                   _ptr(shift2), _ptr(sv.mean2) if (train or keep) else None, _ptr(p), _ptr(z), _ptr(s), _ptr(sums34), st)
         sv.p, sv.z, sv.s, sv.sums34 = p, z, s, sums34
-    if pooled is not None and (Hl % 2 or Wl % 2):
+    if head is not None:
+        outc, logits = head
+        _lib.call("unetca_se_scale_outc_fwd", dt, _ptr(y2), O, B, Hl * Wl, O, _ptr(scale2), _ptr(shift2), _ptr(s),
+                  _ptr(outc.weight), _ptr(outc.bias), outc.weight.shape[0], _ptr(logits), st)
+    elif pooled is not None and (Hl % 2 or Wl % 2):
         # odd extent: MaxPool2d(2) floors (UCA:106-109) -> scale pass, then the standalone pool over the stored values
         _lib.call("unetca_se_scale_pool", dt, _ptr(y2), O, _ptr(out_view), out_view.stride(2), None, 0, None, B, Hl, Wl,
                   O, _ptr(scale2), _ptr(shift2), _ptr(s), st)
@@ -430,12 +443,12 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
     return sv
 
 
-def _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, dt, tdt, bn_params, parts, nparts):
+def _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, dt, tdt, bn_params, parts, nparts, head=None):
     """Inference form of one DoubleConv: BatchNorm uses running statistics, so both conv + BN + ReLU pairs run as single
     tcgen05 kernels (the activation is what gets written; the pre-BN tensors never exist), followed by the SE squeeze /
     scale (+ max-pool) passes on the activation with an identity affine.  Returns False if a conv of this block has
     no fused kernel for its shape."""
-    dev = out_view.device
+    dev = (out_view if out_view is not None else head[1]).device
     st = _stream()
     C, O = blk.cin, blk.cout
     wf1, _, ldk1, wfp1, _ = eng.conv_w(blk.conv1, dt, tdt, blk.first)
@@ -491,7 +504,11 @@ def _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos
     else:
         ok = _conv3x3_bnrelu(dt, a1, O, wf2, wfp2, a2, O, B, Hl, Wl, O, O, scale2, shift2, st)
         assert ok
-    if pooled is not None and (Hl % 2 or Wl % 2):
+    if head is not None:
+        outc, logits = head
+        _lib.call("unetca_se_scale_outc_fwd", dt, _ptr(a2), O, B, Hl * Wl, O, _ptr(one), _ptr(zero), _ptr(s), _ptr(outc.weight),
+                  _ptr(outc.bias), outc.weight.shape[0], _ptr(logits), st)
+    elif pooled is not None and (Hl % 2 or Wl % 2):
         _lib.call("unetca_se_scale_pool", dt, _ptr(a2), O, _ptr(out_view), out_view.stride(2), None, 0, None, B, Hl, Wl,
                   O, _ptr(one), _ptr(zero), _ptr(s), st)
         _lib.call("unetca_maxpool2x2", dt, _ptr(out_view), out_view.stride(2), _ptr(pooled), pooled.stride(2), _ptr(pos),
@@ -574,19 +591,26 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
             _lib.call("unetca_resize_bilinear_fwd", dt, _ptr(u), Cl, 2 * hi, 2 * wi, _ptr(cat[l][..., Cl:]), 2 * Cl, Hl, Wl,
                       B, Cl, st)
         sv.up_in.append(h if keep else None)
-        out = torch.empty(B, Hl, Wl, Cl, dtype=tdt, device=dev)
-        s = _double_conv_fwd(eng, blk, cat[l], None, B, Hl, Wl, out, None, None, train, dt, tdt, keep)
+        head = None
+        if l == 0 and _head_ok(dt, Cl, model.num_classes, Hl * Wl):
+            # the last block: outc rides in its SE-scale pass, the block output is never written
+            logits = torch.empty(B, model.num_classes, H, W, dtype=torch.float32, device=dev)
+            head, out = (model.outc, logits), None
+        else:
+            out = torch.empty(B, Hl, Wl, Cl, dtype=tdt, device=dev)
+        s = _double_conv_fwd(eng, blk, cat[l], None, B, Hl, Wl, out, None, None, train, dt, tdt, keep, head)
         sv.dec.append(s)
         h = out
     # ---- outc
     nc = model.num_classes
-    logits = torch.empty(B, nc, H, W, dtype=torch.float32, device=dev)
-    _lib.call("unetca_outc_fwd", dt, _ptr(h), h.stride(2), 64, _ptr(model.outc.weight), _ptr(model.outc.bias), nc,
-              _ptr(logits), B, H * W, st)
+    if h is not None:
+        logits = torch.empty(B, nc, H, W, dtype=torch.float32, device=dev)
+        _lib.call("unetca_outc_fwd", dt, _ptr(h), h.stride(2), 64, _ptr(model.outc.weight), _ptr(model.outc.bias), nc,
+                  _ptr(logits), B, H * W, st)
     if not keep:
         return logits, None
     sv.cat = cat
-    sv.dec_out = h
+    sv.dec_out = h                       # None when the head was fused
     return logits, sv
 
 
@@ -600,17 +624,19 @@ def _block_grad_order(pre, use_se):
                   pre + ".1.weight", pre + ".1.bias", pre + ".0.bias", pre + ".0.weight"]
 
 
-def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=None):
+def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=None, head=None):
     """Gradient of one DoubleConv block; dout is d(loss)/d(block output) (NHWC view).  Returns d/d(block input).
     G: gradient sink with alloc(name, like) -> tensor to write into and put(name) once it is complete.
     lazy = (skip_grad, dpooled, pos) instead of dout: the output gradient of an encoder block, skip gradient plus the
     max-pool routing of the pooled gradient, is rebuilt inside the two kernels that consume it (SE blocks, even H, W).
     dx_stats = (parts, nparts): have the dgrad convolution that writes the returned gradient leave its per-CTA channel
-    sums there ([n][2][C], the BatchNorm-statistics epilogue) — the decoder takes the ConvTranspose bias gradient from them."""
+    sums there ([n][2][C], the BatchNorm-statistics epilogue) — the decoder takes the ConvTranspose bias gradient from them.
+    head = (g, gscale, outc, dw, db) instead of dout (last block, fused output head): dout = W_outc^T g is rebuilt per pixel inside
+    the reduction and the apply pass from the dlogits g; the outc weight / bias gradients come out of the reduction."""
     blk = sv.blk
     B, Hl, Wl = sv.B, sv.H, sv.W
     C, O = blk.cin, blk.cout
-    dev = (dout if dout is not None else lazy[0]).device
+    dev = dout.device if dout is not None else (lazy[0] if lazy is not None else head[0]).device
     st = _stream()
     npix = B * Hl * Wl
     parts = eng.parts(B, dev)
@@ -623,7 +649,14 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
         # backward statistics are linear in (csrc/elementwise.cu: se_bn_bwd_reduce_kernel)
         w1, w2 = blk.se.fc[0].weight, blk.se.fc[2].weight
         Cr = w1.shape[0]
-        if lazy is not None:
+        if head is not None:
+            hg, hgs, outc, hdw, hdb = head
+            _lib.call("unetca_outc_bn_bwd_reduce", dt, _ptr(hg), _ptr(hgs), _ptr(outc.weight), outc.weight.shape[0], _ptr(sv.y2), O, B,
+                      Hl * Wl, O, _ptr(sv.scale2), _ptr(sv.shift2), _ptr(sv.mean2), _ptr(sv.s), _ptr(parts), ctypes.byref(nparts),
+                      _ptr(ws), ws.numel(), _ptr(hdw), _ptr(hdb), st)
+            G.put("outc.weight")
+            G.put("outc.bias")
+        elif lazy is not None:
             sg, dpl, pos = lazy
             _lib.call("unetca_se_bn_bwd_reduce_pool", dt, _ptr(sg), sg.stride(2), _ptr(dpl), dpl.stride(2), _ptr(pos),
                       _ptr(sv.y2), O, B, Hl, Wl, O, _ptr(sv.scale2), _ptr(sv.shift2), _ptr(sv.mean2), _ptr(parts),
@@ -656,7 +689,15 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
             _lib.call("unetca_bn_bwd_finalize_se", _ptr(sums_), B, O, npix, Hl * Wl, _ptr(bn.weight), _ptr(invstd), _ptr(s_),
                       _ptr(dp_), _ptr(dgamma), _ptr(dbeta), _ptr(coef), st)
         else:
-            if not have_parts:               # (else: the dgrad conv that wrote d_in left the statistics in `parts` already)
+            if head is not None and tag == "2":          # plain U-Net: fused output head without SE
+                hg, hgs, outc, hdw, hdb = head
+                _lib.call("unetca_outc_bn_bwd_reduce", dt, _ptr(hg), _ptr(hgs), _ptr(outc.weight), outc.weight.shape[0], _ptr(y), O, B,
+                          Hl * Wl, O, _ptr(scale), _ptr(shift), _ptr(mean), None, _ptr(parts), ctypes.byref(nparts), _ptr(ws),
+                          ws.numel(), _ptr(hdw), _ptr(hdb), st)
+                G.put("outc.weight")
+                G.put("outc.bias")
+                nparts.value *= B
+            elif not have_parts:             # (else: the dgrad conv that wrote d_in left the statistics in `parts` already)
                 _lib.call("unetca_bn_bwd_reduce", dt, _ptr(d_in), ld_in, _ptr(y), O, B, Hl * Wl, O, _ptr(scale), _ptr(shift),
                           _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(parts), ctypes.byref(nparts), st)
             _lib.call("unetca_bn_bwd_finalize", _ptr(parts), nparts.value, O, npix, _ptr(bn.weight), _ptr(invstd),
@@ -668,7 +709,11 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
             conv = blk.conv1 if tag == "1" else blk.conv2
             torch.mul(coef[0], dbeta, out=G.alloc(f"{pre}.{bn_idx - 1}.bias", conv.bias))
         dy = torch.empty(B, Hl, Wl, O, dtype=tdt, device=dev)
-        if sums_ is not None and lazy is not None:
+        if head is not None and tag == "2":
+            hg, hgs, outc, _, _ = head
+            _lib.call("unetca_outc_bn_bwd_apply", dt, _ptr(hg), _ptr(hgs), _ptr(outc.weight), outc.weight.shape[0], _ptr(y), O, _ptr(dy),
+                      O, B, Hl * Wl, O, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_), _ptr(coef), st)
+        elif sums_ is not None and lazy is not None:
             sg, dpl, pos = lazy
             _lib.call("unetca_bn_bwd_apply_pool", dt, _ptr(sg), sg.stride(2), _ptr(dpl), dpl.stride(2), _ptr(pos), _ptr(y), O,
                       _ptr(dy), O, B, Hl, Wl, O, _ptr(scale), _ptr(shift), _ptr(mean), _ptr(invstd), _ptr(s_), _ptr(dp_),
@@ -782,13 +827,18 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor, need_dx:
     ws = eng.ws(dev)
     # ---- outc
     h = sv.dec_out
-    dcur = torch.empty(B, H, W, 64, dtype=tdt, device=dev)
     dw = G.alloc("outc.weight", model.outc.weight)
     db = G.alloc("outc.bias", model.outc.bias)
-    _lib.call("unetca_outc_bwd", dt, _ptr(g), _ptr(gscale), _ptr(h), h.stride(2), _ptr(dcur), 64, 64,
-              _ptr(model.outc.weight), nc, B, H * W, _ptr(parts), _ptr(dw), _ptr(db), st)
-    G.put("outc.weight")
-    G.put("outc.bias")
+    head = None
+    if h is None:
+        # fused output head: the last block's backward passes rebuild d(block output) from the dlogits and leave dw / db
+        head, dcur = (g, gscale, model.outc, dw, db), None
+    else:
+        dcur = torch.empty(B, H, W, 64, dtype=tdt, device=dev)
+        _lib.call("unetca_outc_bwd", dt, _ptr(g), _ptr(gscale), _ptr(h), h.stride(2), _ptr(dcur), 64, 64,
+                  _ptr(model.outc.weight), nc, B, H * W, _ptr(parts), _ptr(dw), _ptr(db), st)
+        G.put("outc.weight")
+        G.put("outc.bias")
     # ---- decoder, shallow to deep
     skip_grads = [None] * 4
     for l in range(4):
@@ -801,7 +851,8 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor, need_dx:
         fused_db = (dt == _lib.BF16 and _lib.load().unetca_get_conv_impl() == 0 and (2 * hi, 2 * wi) == (Hl, Wl))
         nst = ctypes.c_int(0)
         dcat = _double_conv_bwd(eng, sv.dec[i], dcur, G, dt, tdt, True,
-                                dx_stats=(parts, nst) if fused_db else None)        # (B,Hl,Wl,2Cl)
+                                dx_stats=(parts, nst) if fused_db else None,        # (B,Hl,Wl,2Cl)
+                                head=head if l == 0 else None)
         du, ldu = dcat[..., Cl:], 2 * Cl
         skip_grads[l] = dcat[..., :Cl]
         if (2 * hi, 2 * wi) != (Hl, Wl):                                         # adjoint of the resize guard

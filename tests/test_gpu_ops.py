@@ -945,3 +945,63 @@ def test_outc_stream_equals_register_kernels(B, HW, nc):
     assert relerr(res[8][2], res[0][2]) < 1e-5 and relerr(res[8][3], res[0][3]) < 1e-5
     ref = torch.einsum("bpc,oc->bop", x.float(), w) + bias.view(1, nc, 1)
     assert relerr(res[8][0], ref) < 1e-5
+
+
+@pytest.mark.parametrize("B,H,W,use_se", [(2, 16, 32, True), (3, 64, 64, True), (2, 16, 32, False), (5, 32, 48, True)])
+def test_fused_output_head_matches_separate_passes(B, H, W, use_se):
+    """unetca_se_scale_outc_fwd / unetca_outc_bn_bwd_reduce / unetca_outc_bn_bwd_apply against the passes they replace
+    (se_scale_pool -> outc_fwd; outc_bwd -> se_bn_bwd_reduce / bn_bwd_reduce -> bn_bwd_apply): the block output and its
+    gradient are never stored, the results are the same (UCA:86-94 of conv4, UCA:162 and their autograd)."""
+    dt, C, nc, HW = BF16, 64, 2, H * W
+    rs = np.random.RandomState(B * 7 + H)
+    call("unetca_set_conv_impl", 0)
+    y2 = to_nhwc(torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32)), dt)
+    f = lambda *shape, sc=1.0, off=0.0: torch.from_numpy((off + sc * rs.standard_normal(shape)).astype(np.float32)).cuda()
+    scale, shift, mean = f(C, sc=0.2, off=1.0), f(C, sc=0.3), f(C, sc=0.2)
+    invstd, coef = f(C, sc=0.1, off=1.0), f(3, C, sc=0.1, off=0.5)
+    s = torch.sigmoid(f(B, C)) if use_se else None
+    dp = f(B, C, sc=0.5) if use_se else None
+    w, bias = f(nc, C, sc=0.2), f(nc, sc=0.1)
+    g = f(B, nc, H, W, sc=1.0)
+    gscale = torch.tensor([1.0 / (B * HW)], device="cuda")
+    # ---- forward: separate
+    out = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    call("unetca_se_scale_pool", dt, ptr(y2), C, ptr(out), C, None, 0, None, B, H, W, C, ptr(scale), ptr(shift), ptr(s), stream())
+    lg_ref = torch.empty(B, nc, H, W, device="cuda")
+    call("unetca_outc_fwd", dt, ptr(out), C, C, ptr(w), ptr(bias), nc, ptr(lg_ref), B, HW, stream())
+    lg = torch.full((B, nc, H, W), float("nan"), device="cuda")
+    call("unetca_se_scale_outc_fwd", dt, ptr(y2), C, B, HW, C, ptr(scale), ptr(shift), ptr(s), ptr(w), ptr(bias), nc, ptr(lg), stream())
+    # (the fused head keeps the block output in fp32 registers where the separate passes stored it as bf16)
+    assert relerr(lg.cpu(), lg_ref.cpu()) < 4e-3
+    # ---- backward: separate
+    parts = parts_buf(B)
+    dh = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    dw_ref, db_ref = torch.empty(nc, C, device="cuda"), torch.empty(nc, device="cuda")
+    call("unetca_outc_bwd", dt, ptr(g), ptr(gscale), ptr(out), C, ptr(dh), C, C, ptr(w), nc, B, HW, ptr(parts), ptr(dw_ref), ptr(db_ref),
+         stream())
+    n = cint()
+    if use_se:
+        call("unetca_se_bn_bwd_reduce", dt, ptr(dh), C, ptr(y2), C, B, HW, C, ptr(scale), ptr(shift), ptr(mean), ptr(parts), ctypes.byref(n),
+             stream())
+    else:
+        call("unetca_bn_bwd_reduce", dt, ptr(dh), C, ptr(y2), C, B, HW, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), None, None,
+             ptr(parts), ctypes.byref(n), stream())
+    rows = n.value * (B if use_se else 1)
+    sums_ref = parts[: rows * 2 * C].view(rows, 2, C).double().sum(0).cpu()
+    dy_ref = torch.empty(B, H, W, C, dtype=TDT[dt], device="cuda")
+    call("unetca_bn_bwd_apply", dt, ptr(dh), C, ptr(y2), C, ptr(dy_ref), C, B, HW, C, ptr(scale), ptr(shift), ptr(mean), ptr(invstd), ptr(s),
+         ptr(dp), ptr(coef), stream())
+    # ---- backward: fused
+    parts2 = parts_buf(B)
+    ws = torch.empty(1 << 20, device="cuda")
+    dw, db = torch.empty(nc, C, device="cuda"), torch.empty(nc, device="cuda")
+    n2 = cint()
+    call("unetca_outc_bn_bwd_reduce", dt, ptr(g), ptr(gscale), ptr(w), nc, ptr(y2), C, B, HW, C, ptr(scale), ptr(shift), ptr(mean), ptr(s),
+         ptr(parts2), ctypes.byref(n2), ptr(ws), ws.numel(), ptr(dw), ptr(db), stream())
+    sums = parts2[: n2.value * B * 2 * C].view(n2.value * B, 2, C).double().sum(0).cpu()
+    assert relerr(sums, sums_ref) < 5e-3
+    assert relerr(dw.cpu(), dw_ref.cpu()) < 5e-3 and relerr(db.cpu(), db_ref.cpu()) < 1e-5
+    dy = torch.full((B, H, W, C), float("nan"), dtype=TDT[dt], device="cuda")
+    call("unetca_outc_bn_bwd_apply", dt, ptr(g), ptr(gscale), ptr(w), nc, ptr(y2), C, ptr(dy), C, B, HW, C, ptr(scale), ptr(shift), ptr(mean),
+         ptr(invstd), ptr(s), ptr(dp), ptr(coef), stream())
+    assert relerr(dy.float().cpu(), dy_ref.float().cpu()) < 1e-2          # dh unrounded vs bf16-rounded
