@@ -11,9 +11,24 @@ comparable with bench.py's live CUDA-event numbers.
 """
 import argparse
 import csv
+import hashlib
 import json
+import os
 import re
 import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def csrc_hash():
+    """Identity of the kernel sources the capture was taken on (bench.py compares it with the build it is timing)."""
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "insar-unet-ca_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
 
 
 def short(name):
@@ -26,7 +41,7 @@ def short(name):
 def klass(name):
     if name.startswith("tc_"):
         return "tensor"
-    if name.startswith(("at::", "void at::", "adam_", "pack_", "wgrad_reduce", "sum_parts", "first_pairs_fold")):
+    if name.startswith(("at::", "void at::", "adam_", "pack_", "wgrad_reduce", "sum_parts", "first_pairs_fold", "img_parts_sum")):
         return "other"
     if "finalize" in name or name.startswith(("se_fc", "confusion")):
         return "other"              # tiny per-channel kernels
@@ -103,7 +118,8 @@ def main():
             return {"kernel": label, "launches_per_step": n,
                     "dram_bytes_per_launch": sum(d["dram_read_bytes"] + d["dram_write_bytes"] for d in ds) / max(n, 1),
                     "ms_per_step_under_ncu": sum(d["ms"] for d in ds)}
-        out = {"source": f"{a.out_prefix}.json (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
+        out = {"csrc_sha": csrc_hash(),
+               "source": f"{a.out_prefix}.json (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum "
                          f"--clock-control none {a.command}, last step)",
                "tensor": cls("tensor"), "hbm": cls("hbm"),
                "dominant": one(lambda n: n.startswith("tc_conv3x3_hpix_kernel"), "tc_conv3x3_hpix_kernel"),
