@@ -87,6 +87,8 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+constexpr int kMaxDevices = 64;
+int device_slot();          // current device ordinal (index into per-device caches)
 int num_sms();
 
 }  // namespace unetca

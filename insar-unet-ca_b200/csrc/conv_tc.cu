@@ -2198,7 +2198,8 @@ static void pick_tile(int H, int W, int npx, int* TW, int* TH) {
 template <int BLOCK_N, bool WGRAD>
 static int launch_tc(const TcParams& p, long num_work, cudaStream_t st, const char* what) {
     using Cfg = TcCfg<BLOCK_N, WGRAD>;
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_kernel<BLOCK_N, WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::SMEM_BYTES);
@@ -2294,7 +2295,8 @@ static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, 
         p.bwd_y = (const bf16*)bwd->y; p.bwd_ldy = bwd->ldy;
         p.bwd_scale = bwd->scale; p.bwd_shift = bwd->shift; p.bwd_mean = bwd->mean;
     }
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_hpix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHpSmemBytes);
         if (e != cudaSuccess) { set_error("tc_conv3x3 (hpix): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
@@ -2327,7 +2329,8 @@ static int launch_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy,
     p.ep_scale = ep_scale; p.ep_shift = ep_shift;
     const int xs = cch == 1 ? 4 : 2;
     const int smem = kw_smem_bytes(cch, xs);
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_kw_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kw_smem_bytes(1, 4));
         if (e == cudaSuccess)
@@ -2418,7 +2421,8 @@ static int launch_pixn(const void* x, int ldx, const void* w, int ldk, void* y, 
     }
     p.stat_parts = stat_parts; p.N = O;
     p.ep_scale = ep_scale; p.ep_shift = ep_shift; p.sq_parts = sq_parts;
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
         if (e == cudaSuccess)
@@ -2451,7 +2455,8 @@ static int launch_first_pairs(const void* colp, const void* wp, void* y, int ldy
     p.num_m_blocks = O / 64;
     p.stat_parts = stat_parts; p.N = O;
     p.ep_scale = ep_scale; p.ep_shift = ep_shift;
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_pixn_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPnSmemBytes);
         if (e == cudaSuccess)
@@ -2480,7 +2485,8 @@ static int launch_rp64(const void* x, int ldx, const void* w, int ldk, void* y, 
         p.bwd_y = (const bf16*)bwd->y; p.bwd_ldy = bwd->ldy;
         p.bwd_scale = bwd->scale; p.bwd_shift = bwd->shift; p.bwd_mean = bwd->mean;
     }
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_conv3x3_rp64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRpSmemBytes);
         if (e != cudaSuccess) { set_error("tc_conv3x3 (rp64): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
@@ -2767,7 +2773,8 @@ int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, fl
     const long ns = g_wgrad_waves > 0 ? fit_split(items, g_wgrad_waves, smax) : 1;
     p.nsplit = (int)ns;
     p.ws = ws; p.ldn = 9 * C; p.C = C;
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(tc_wgrad3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemBytes);
         if (e == cudaSuccess)

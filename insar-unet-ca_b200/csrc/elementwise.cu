@@ -2688,7 +2688,8 @@ template <typename T> static bool chan_ok(int C, int ld) {
 // out = relu(a*y+b) [* s[b,c]] over dense bf16 tensors through se_scale_stream_kernel
 static int launch_se_scale_stream(const void* y, void* out, int B, long hw, int C, const float* scale, const float* shift,
                                   const float* s, cudaStream_t st) {
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         if (cudaFuncSetAttribute(se_scale_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kScSmemBytes) != cudaSuccess) {
             set_error("se_scale: cudaFuncSetAttribute failed"); return UNETCA_ERR_CUDA;
@@ -2747,7 +2748,8 @@ int unetca_bn_relu(int dtype, const void* y, int ldy, void* out, int ldo, int B,
             if (nparts) *nparts = 0;
             return launch_se_scale_stream(y, out, B, pix_per_img, C, scale, shift, nullptr, (cudaStream_t)stream);
         }
-        static int slots = 0;
+        static int slots_dev[kMaxDevices] = {};
+        int& slots = slots_dev[device_slot()];
         if (!slots) slots = resident_blocks(bn_relu_kernel<T, false, true>);
         const long chunk = pool_parts ? img_red_chunk<T>(C, pix_per_img, B, slots) : ew_chunk<T>(C, pix_per_img);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
@@ -2795,7 +2797,8 @@ int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldy);
         if (stream_ok<T>(C, ldy, ldy)) {
-            static int sslots = 0;
+            static int sslots_dev[kMaxDevices] = {};
+            int& sslots = sslots_dev[device_slot()];
             if (!sslots) sslots = resident_blocks_smem(reduce_stream_kernel<1>, kRdSmemBytes);
             if (sslots > 0) {
                 const long chunk = img_red_chunk<T>(C, pix_per_img, B, sslots);
@@ -2805,7 +2808,8 @@ int unetca_se_squeeze(int dtype, const void* y, int ldy, int B, long pix_per_img
                 return check_launch("se_squeeze (stream)");
             }
         }
-        static int slots = 0;
+        static int slots_dev[kMaxDevices] = {};
+        int& slots = slots_dev[device_slot()];
         if (!slots) slots = resident_blocks(se_squeeze_kernel<T>);
         const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
@@ -2840,7 +2844,8 @@ int unetca_se_scale_pool(int dtype, const void* y, int ldy, void* out, int ldo, 
         REQ_CHAN(C, ldy); REQ_CHAN(C, ldo);
         cudaStream_t st = (cudaStream_t)stream;
         if (pooled && qp_ok<T>(C, ldy, ldo, ldp, 8)) {
-            static int sslots = 0;
+            static int sslots_dev[kMaxDevices] = {};
+            int& sslots = sslots_dev[device_slot()];
             if (!sslots) sslots = resident_blocks_smem(se_scale_pool_stream_kernel, kSpSmemBytes);
             if (sslots > 0) {
                 const int QW = kThreads / (C / 8);
@@ -2929,7 +2934,8 @@ int unetca_se_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, in
                          const float* scale, const float* shift, float* parts, int* nparts, void* stream) {
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
-        static int slots = 0;
+        static int slots_dev[kMaxDevices] = {};
+        int& slots = slots_dev[device_slot()];
         if (!slots) slots = resident_blocks(se_bwd_reduce_kernel<T>);
         const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
@@ -2957,7 +2963,8 @@ int unetca_se_bn_bwd_reduce_pool(int dtype, const void* sg, int lds, const void*
     DISPATCH_T(dtype, {
         REQ_CHAN(C, lds); REQ_CHAN(C, ldp); REQ_CHAN(C, ldy);
         if (qp_ok<T>(C, lds, ldp, ldy, 8)) {
-            static int sslots = 0;
+            static int sslots_dev[kMaxDevices] = {};
+            int& sslots = sslots_dev[device_slot()];
             if (!sslots) sslots = resident_blocks_smem(se_bn_bwd_pool_stream_kernel<false>, kQpSmemBytes);
             QpMaps maps;
             int rc = sslots > 0 ? qp_setup(&maps, sg, lds, dpooled, ldp, pos, y, ldy, nullptr, 0, B, H, W, C) : 0;
@@ -2974,7 +2981,8 @@ int unetca_se_bn_bwd_reduce_pool(int dtype, const void* sg, int lds, const void*
                 return check_launch("se_bn_bwd_reduce_pool (stream)");
             }
         }
-        static int slots = 0;
+        static int slots_dev[kMaxDevices] = {};
+        int& slots = slots_dev[device_slot()];
         if (!slots) slots = resident_blocks(se_bn_bwd_pool_kernel<T, false>);
         const long nquad = (long)(H / 2) * (W / 2);
         const long chunk = img_red_chunk<T>(C, nquad, B, slots);
@@ -2994,7 +3002,8 @@ int unetca_bn_bwd_apply_pool(int dtype, const void* sg, int lds, const void* dpo
     DISPATCH_T(dtype, {
         REQ_CHAN(C, lds); REQ_CHAN(C, ldp); REQ_CHAN(C, ldy); REQ_CHAN(C, lddy);
         if (qp_ok<T>(C, lds, ldp, ldy, lddy)) {
-            static int sslots = 0;
+            static int sslots_dev[kMaxDevices] = {};
+            int& sslots = sslots_dev[device_slot()];
             if (!sslots) sslots = resident_blocks_smem(se_bn_bwd_pool_stream_kernel<true>, kQpSmemBytesApply);
             QpMaps maps;
             int rc = sslots > 0 ? qp_setup(&maps, sg, lds, dpooled, ldp, pos, y, ldy, dy, lddy, B, H, W, C) : 0;
@@ -3023,7 +3032,8 @@ int unetca_se_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y,
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
         if (stream_ok<T>(C, ldd, ldy)) {
-            static int sslots = 0;
+            static int sslots_dev[kMaxDevices] = {};
+            int& sslots = sslots_dev[device_slot()];
             if (!sslots) sslots = resident_blocks_smem(reduce_stream_kernel<0>, kRdSmemBytes);
             if (sslots > 0) {
                 const long chunk = img_red_chunk<T>(C, pix_per_img, B, sslots);
@@ -3033,7 +3043,8 @@ int unetca_se_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y,
                 return check_launch("se_bn_bwd_reduce (stream)");
             }
         }
-        static int slots = 0;
+        static int slots_dev[kMaxDevices] = {};
+        int& slots = slots_dev[device_slot()];
         if (!slots) slots = resident_blocks(se_bn_bwd_reduce_kernel<T>);
         const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
@@ -3085,7 +3096,8 @@ int unetca_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, in
     DISPATCH_T(dtype, {
         REQ_CHAN(C, ldd); REQ_CHAN(C, ldy);
         if (!s && stream_ok<T>(C, ldd, ldy)) {
-            static int sslots = 0;
+            static int sslots_dev[kMaxDevices] = {};
+            int& sslots = sslots_dev[device_slot()];
             if (!sslots) sslots = resident_blocks_smem(reduce_stream_kernel<0>, kRdSmemBytes);
             if (sslots > 0) {
                 const long chunk = img_red_chunk<T>(C, pix_per_img, B, sslots);
@@ -3095,7 +3107,8 @@ int unetca_bn_bwd_reduce(int dtype, const void* dout, int ldd, const void* y, in
                 return check_launch("bn_bwd_reduce (stream)");
             }
         }
-        static int slots = 0;
+        static int slots_dev[kMaxDevices] = {};
+        int& slots = slots_dev[device_slot()];
         if (!slots) slots = resident_blocks(bn_bwd_kernel<T, true, false>);
         const long chunk = img_red_chunk<T>(C, pix_per_img, B, slots);
         dim3 grid(ceil_div(pix_per_img, chunk), B);
@@ -3125,7 +3138,8 @@ int unetca_bn_bwd_apply(int dtype, const void* dout, int ldd, const void* y, int
         cudaStream_t st = (cudaStream_t)stream;
         const float ihw = 1.f / (float)pix_per_img;
         if (stream_ok<T>(C, ldd, ldy) && lddy == C) {
-            static bool attr_done = false;
+            static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
             if (!attr_done) {
                 cudaError_t e = cudaFuncSetAttribute(bn_bwd_apply_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kStSmemBytes);
                 if (e == cudaSuccess)
@@ -3239,7 +3253,8 @@ int unetca_outc_fwd(int dtype, const void* x, int ldx, int C, const float* w, co
         const long npix = (long)B * HW;
         cudaStream_t st = (cudaStream_t)stream;
         if (stream_ok<T>(C, ldx, ldx) && C == 64 && nc <= 2 && HW % kOcPix == 0) {
-            static bool attr_done = false;
+            static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
             if (!attr_done) {
                 if (cudaFuncSetAttribute(outc_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOcFwdSmem) != cudaSuccess) {
                     set_error("outc_fwd: cudaFuncSetAttribute failed"); return UNETCA_ERR_CUDA;
@@ -3271,7 +3286,8 @@ static bool head_fusable(int dtype, int ldy, int C, int nc, long HW) {
 int unetca_se_scale_outc_fwd(int dtype, const void* y, int ldy, int B, long HW, int C, const float* scale, const float* shift,
                              const float* s, const float* w, const float* bias, int nc, float* logits, void* stream) {
     if (!head_fusable(dtype, ldy, C, nc, HW)) { set_error("se_scale_outc_fwd: unsupported shape / dtype"); return UNETCA_ERR_UNSUPPORTED; }
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         if (cudaFuncSetAttribute(se_scale_outc_fwd_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kOcFwdSmem) != cudaSuccess) {
             set_error("se_scale_outc_fwd: cudaFuncSetAttribute failed"); return UNETCA_ERR_CUDA;
@@ -3290,7 +3306,8 @@ int unetca_outc_bn_bwd_reduce(int dtype, const float* g, const float* gscale, co
                               float* parts_bn, int* nparts, float* parts_oc, long parts_oc_floats, float* dw, float* db,
                               void* stream) {
     if (!head_fusable(dtype, ldy, C, nc, HW)) { set_error("outc_bn_bwd_reduce: unsupported shape / dtype"); return UNETCA_ERR_UNSUPPORTED; }
-    static int sslots = 0;
+    static int sslots_dev[kMaxDevices] = {};
+    int& sslots = sslots_dev[device_slot()];
     if (!sslots) sslots = resident_blocks_smem(outc_bn_bwd_stream_kernel<0, false>, kOcBwdSmem);
     if (sslots <= 0) { set_error("outc_bn_bwd_reduce: kernel does not fit"); return UNETCA_ERR_CUDA; }
     long per_img = sslots / B; if (per_img < 1) per_img = 1;
@@ -3309,7 +3326,8 @@ int unetca_outc_bn_bwd_apply(int dtype, const float* g, const float* gscale, con
                              int lddy, int B, long HW, int C, const float* scale, const float* shift, const float* mean,
                              const float* invstd, const float* s, const float* dp, const float* coef, void* stream) {
     if (!head_fusable(dtype, ldy, C, nc, HW) || lddy != C) { set_error("outc_bn_bwd_apply: unsupported shape / dtype"); return UNETCA_ERR_UNSUPPORTED; }
-    static bool attr_done = false;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];          // cudaFuncSetAttribute is per device
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(outc_bn_bwd_stream_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOcBwdSmem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(outc_bn_bwd_stream_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kOcBwdSmem);
@@ -3337,7 +3355,8 @@ int unetca_outc_bwd(int dtype, const float* g, const float* gscale, const void* 
         const long npix = (long)B * HW;
         cudaStream_t st = (cudaStream_t)stream;
         if (stream_ok<T>(C, ldx, lddx) && C == 64 && nc <= 2 && HW % kOcPix == 0) {
-            static int sslots = 0;
+            static int sslots_dev[kMaxDevices] = {};
+            int& sslots = sslots_dev[device_slot()];
             if (!sslots) sslots = resident_blocks_smem(outc_bwd_stream_kernel, kOcBwdSmem);
             if (sslots > 0) {
                 // one wave of resident blocks, whole 128-pixel tiles per block, blocks never straddle an image

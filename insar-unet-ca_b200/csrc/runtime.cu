@@ -23,15 +23,22 @@ int check_launch(const char* what) {
     return UNETCA_OK;
 }
 
+// Ordinal of the calling thread's current device, clamped to the size of the per-device caches below.  Everything the
+// library remembers (SM count, "kernel attributes set" flags) is a property of a DEVICE: a process that drives several
+// GPUs (one model on cuda:0, another on cuda:1) must not reuse what it learnt on the first one.
+int device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+    return dev < kMaxDevices ? dev : kMaxDevices - 1;
+}
+
 int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-            n = 148;
+    static int n[kMaxDevices] = {};
+    const int d = device_slot();
+    if (n[d] == 0) {
+        if (cudaDeviceGetAttribute(&n[d], cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n[d] <= 0) n[d] = 148;
     }
-    return n;
+    return n[d];
 }
 
 }  // namespace unetca
