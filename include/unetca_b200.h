@@ -65,6 +65,9 @@ int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_p
 /* the 64 -> 64 channel layers (inc / conv4 second convs and their dgrads, UCA:84 at full resolution), H even: row-pair
  * layout with the whole filter resident in shared memory and haloed lattice tiles (tc_conv3x3_rp64_kernel); w is the
  * ordinary packed filter [64][ldk >= 576] of unetca_pack_conv3x3_weight.  bf16 only. */
+/* unetca_conv3x3_fwd (O % 128 == 0) writing output channels [0, split) to y and [split, O) to y2: the dgrad of a decoder block's
+ * first conv (its input is torch.cat([skip, up]), UCA:140) leaves d(skip) and d(up) as two dense tensors.  bf16 only. */
+int unetca_conv3x3_fwd_split(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, void* y2, int ldy2, int split, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream);
 int unetca_conv3x3_fwd_rp64(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, float* stat_parts, int* nparts, void* stream);
 /* dgrad of a block's second conv (dy -> dA1, wd = dgrad-packed filter [O][ldk]) that also leaves the statistics of the
  * ReLU + BatchNorm backward that follows (autograd of UCA:82-83): parts [*nparts][2][O] = (sum dz, sum dz*(y1 - mean)) with

@@ -11,6 +11,7 @@ int unetca_tc_conv3x3_fwd(const void*, int, const void*, int, void*, int, int, i
 int unetca_tc_conv3x3_fwd_paired(const void*, int, const void*, void*, int, int, int, int, int, int, float*, void*);
 int unetca_tc_pack_pair(const void*, int, void*, int, int, void*);
 int unetca_tc_conv3x3_fwd_rp64(const void*, int, const void*, int, void*, int, int, int, int, float*, void*);
+int unetca_tc_conv3x3_fwd_split(const void*, int, const void*, int, void*, int, void*, int, int, int, int, int, int, int, float*, void*);
 int unetca_tc_conv3x3_dgrad_bnstats(const void*, int, const void*, int, void*, int, int, int, int, int, int, const void*, int,
                                     const float*, const float*, const float*, float*, void*);
 int unetca_tc_conv3x3_fwd_kw(const void*, int, const void*, void*, int, int, int, int, int, float*, void*);
@@ -79,6 +80,16 @@ int unetca_conv3x3_fwd_rp64(int dtype, const void* x, int ldx, const void* w, in
                             float* stat_parts, int* nparts, void* stream) {
     if (!use_tc(dtype)) { unetca::set_error("conv3x3_fwd_rp64: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
     int rc = unetca_tc_conv3x3_fwd_rp64(x, ldx, w, ldk, y, ldy, B, H, W, stat_parts, stream);
+    if (rc < 0) return rc;
+    if (nparts) *nparts = rc;
+    return 0;
+}
+
+// conv3x3 fwd / dgrad (O % 128 == 0) whose output channels go to TWO tensors: [0, split) -> y, [split, O) -> y2 (bf16 tensor cores)
+int unetca_conv3x3_fwd_split(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, void* y2, int ldy2,
+                             int split, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("conv3x3_fwd_split: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int rc = unetca_tc_conv3x3_fwd_split(x, ldx, w, ldk, y, ldy, y2, ldy2, split, B, H, W, C, O, stat_parts, stream);
     if (rc < 0) return rc;
     if (nparts) *nparts = rc;
     return 0;

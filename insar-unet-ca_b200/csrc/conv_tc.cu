@@ -1433,6 +1433,11 @@ struct alignas(64) HpixParams {
     CUtensorMap mapX, mapW;
     bf16* out;
     int ldo;
+    // optional second destination: output channels >= split go to out2 (pixel stride ldo2, channel - split) — the dgrad of a
+    // decoder block's first conv writes d(skip) and d(upsampled) as two dense tensors instead of one [.., 2C] buffer whose
+    // halves every consumer would then read as 128-byte rows at a 256-byte stride
+    bf16* out2;
+    int ldo2, split;
     int tilesW, tilesH, nimg, H, W;
     int cchunks, num_m_blocks;
     float* stat_parts;
@@ -1573,7 +1578,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
         float* sm_wpart = sm_stats + 2048;        // [2][128]
         const bool act = p.ep_scale != nullptr;
         const bool bwd = p.bwd_y != nullptr;
-        const long row_stride = (long)p.W * p.ldo, yrow_stride = (long)p.W * p.bwd_ldy;
+        const long yrow_stride = (long)p.W * p.bwd_ldy;
         int as = 0; uint32_t aph = 0;
         int cur_b = -1;
         for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
@@ -1585,7 +1590,10 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
             const bool full = nx == kHpTW && ni == kHpTH;
             const int ch = mb * 128 + r;
             const long pix0 = ((long)b * p.H + h0) * p.W + x0;
-            bf16* obase = p.out + pix0 * p.ldo + ch;
+            const bool second = p.out2 != nullptr && ch >= p.split;
+            const int ldo = second ? p.ldo2 : p.ldo;
+            bf16* obase = second ? p.out2 + pix0 * ldo + (ch - p.split) : p.out + pix0 * ldo + ch;
+            const long row_stride = (long)p.W * ldo;
             const bf16* ybase = bwd ? p.bwd_y + pix0 * p.bwd_ldy + ch : nullptr;
             uint32_t yv[4][16];
             if (bwd) {          // the saved-output loads go out before the accumulator is waited for
@@ -1598,16 +1606,16 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
             float s1 = 0.f, s2 = 0.f;
             if (bwd) {
                 const float ba = __ldg(p.bwd_scale + ch), bb = __ldg(p.bwd_shift + ch), bm = __ldg(p.bwd_mean + ch);
-                if (full) rp64_drain_bwd<true, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, ba, bb, bm, yv, s1, s2);
-                else rp64_drain_bwd<false, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, ba, bb, bm, yv, s1, s2);
+                if (full) rp64_drain_bwd<true, 0>(t_addr, chalf * 4, obase, row_stride, ldo, ni, nx, ba, bb, bm, yv, s1, s2);
+                else rp64_drain_bwd<false, 0>(t_addr, chalf * 4, obase, row_stride, ldo, ni, nx, ba, bb, bm, yv, s1, s2);
             } else {
                 const float ea = act ? __ldg(p.ep_scale + ch) : 1.f, eb = act ? __ldg(p.ep_shift + ch) : 0.f;
-                if (full && act) rp64_drain<true, false, 0, 0, true>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, true, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
-                else if (full && p.ldo == 128) rp64_drain<true, false, 128, 0>(t_addr, chalf * 4, obase, row_stride, 128, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
-                else if (full && p.ldo == 256) rp64_drain<true, false, 256, 0>(t_addr, chalf * 4, obase, row_stride, 256, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
-                else if (full && p.ldo == 512) rp64_drain<true, false, 512, 0>(t_addr, chalf * 4, obase, row_stride, 512, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
-                else if (full) rp64_drain<true, false, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
-                else rp64_drain<false, false, 0, 0>(t_addr, chalf * 4, obase, row_stride, p.ldo, ni, nx, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                if (full && act) rp64_drain<true, false, 0, 0, true>(t_addr, chalf * 4, obase, row_stride, ldo, ni, nx, true, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else if (full && ldo == 128) rp64_drain<true, false, 128, 0>(t_addr, chalf * 4, obase, row_stride, 128, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else if (full && ldo == 256) rp64_drain<true, false, 256, 0>(t_addr, chalf * 4, obase, row_stride, 256, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else if (full && ldo == 512) rp64_drain<true, false, 512, 0>(t_addr, chalf * 4, obase, row_stride, 512, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else if (full) rp64_drain<true, false, 0, 0>(t_addr, chalf * 4, obase, row_stride, ldo, ni, nx, false, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+                else rp64_drain<false, false, 0, 0>(t_addr, chalf * 4, obase, row_stride, ldo, ni, nx, act, ea, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
             }
             tcgen05_fence_before();
             __syncwarp();
@@ -2280,13 +2288,14 @@ struct BwdStats { const void* y; int ldy; const float* scale; const float* shift
 // conv3x3 forward / dgrad for O % 128 == 0 through the haloed pixels-on-N kernel; w = packed filter [O][9*C]
 static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
                        float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr,
-                       float* sq_parts = nullptr, const BwdStats* bwd = nullptr) {
+                       float* sq_parts = nullptr, const BwdStats* bwd = nullptr, void* y2 = nullptr, int ldy2 = 0, int split = 0) {
     HpixParams p;
     memset(&p, 0, sizeof(p));
     int rc;
     if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kHpPitch, kHpTH + 2)) < 0) return rc;
     if ((rc = make_map(&p.mapW, w, 9L * C, O, 1, 1, ldk, (long)O * ldk, (long)O * ldk, 128, 1)) < 0) return rc;
     p.out = (bf16*)y; p.ldo = ldy;
+    p.out2 = (bf16*)y2; p.ldo2 = ldy2; p.split = split;
     p.tilesW = ceil_div(W, kHpTW); p.tilesH = ceil_div(H, kHpTH); p.nimg = B; p.H = H; p.W = W;
     p.cchunks = C / 64; p.num_m_blocks = O / 128;
     p.stat_parts = stat_parts; p.N = O;
@@ -2546,6 +2555,15 @@ int unetca_tc_conv3x3_dgrad_bnstats(const void* x, int ldx, const void* w, int l
         return launch_rp64(x, ldx, w, ldk, y, ldy, B, H, W, stat_parts, (cudaStream_t)stream, nullptr, nullptr, nullptr, &bs);
     set_error("tc_conv3x3_dgrad_bnstats: no fused kernel for C=%d O=%d H=%d", C, O, H);
     return UNETCA_ERR_UNSUPPORTED;
+}
+
+// conv3x3 forward / dgrad, O % 128 == 0, output channels [0, split) -> y (pixel stride ldy), [split, O) -> y2 (pixel stride ldy2)
+int unetca_tc_conv3x3_fwd_split(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, void* y2, int ldy2, int split,
+                                int B, int H, int W, int C, int O, float* stat_parts, void* stream) {
+    UNETCA_REQUIRE(C % 64 == 0 && O % 128 == 0 && O <= 1024 && split > 0 && split < O && split % 64 == 0 && y2,
+                   "tc_conv3x3_fwd_split: C=%d O=%d split=%d", C, O, split);
+    return launch_hpix(x, ldx, w, ldk, y, ldy, B, H, W, C, O, stat_parts, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr,
+                       y2, ldy2, split);
 }
 
 // conv3x3 forward / dgrad for 64 output channels (C = 64 or 128) through the kw-stacked kernel

@@ -301,6 +301,7 @@ def sv_pairs(col, B, H, W):
 
 FUSE_SQUEEZE = True      # inference: take the SE squeeze in the second conv's epilogue (False: separate read-only pass)
 FUSE_HEAD = True          # outc (UCA:162) fused with the last block's SE-scale / BN2-backward passes: its input and input-gradient never exist
+SPLIT_DCAT = True         # decoder conv1 dgrad writes d(skip) and d(up) as two dense tensors (False: one [.., 2C] buffer)
 FUSE_BN_BWD_STATS = True  # training: BN1-backward statistics in the epilogue of the dgrad conv that writes dA1 (False: reduce pass)
 
 
@@ -624,13 +625,15 @@ def _block_grad_order(pre, use_se):
                   pre + ".1.weight", pre + ".1.bias", pre + ".0.bias", pre + ".0.weight"]
 
 
-def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=None, head=None):
+def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=None, head=None, split=0):
     """Gradient of one DoubleConv block; dout is d(loss)/d(block output) (NHWC view).  Returns d/d(block input).
     G: gradient sink with alloc(name, like) -> tensor to write into and put(name) once it is complete.
     lazy = (skip_grad, dpooled, pos) instead of dout: the output gradient of an encoder block, skip gradient plus the
     max-pool routing of the pooled gradient, is rebuilt inside the two kernels that consume it (SE blocks, even H, W).
     dx_stats = (parts, nparts): have the dgrad convolution that writes the returned gradient leave its per-CTA channel
     sums there ([n][2][C], the BatchNorm-statistics epilogue) — the decoder takes the ConvTranspose bias gradient from them.
+    split = C_skip > 0 (decoder blocks on the bf16 tensor-core path): return (d skip, d upsampled) as two dense tensors instead of
+    one [.., 2C] buffer — every consumer of either half would otherwise read 128-byte rows at a 256-byte stride.
     head = (g, gscale, outc, dw, db) instead of dout (last block, fused output head): dout = W_outc^T g is rebuilt per pixel inside
     the reduction and the apply pass from the dlogits g; the outc weight / bias gradients come out of the reduction."""
     blk = sv.blk
@@ -776,8 +779,14 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
         _lib.call("unetca_simt_conv3x3_fwd", dt, _ptr(dy1), O, _ptr(wd0), 9 * O, _ptr(dx), C, B, Hl, Wl, O, C, st)
         return dx
     _, wd1, _, _, wdp1 = eng.conv_w(blk.conv1, dt, tdt, False)
-    dx = torch.empty(B, Hl, Wl, C, dtype=tdt, device=dev)
     sp, npp = (dx_stats[0], ctypes.byref(dx_stats[1])) if dx_stats is not None else (None, None)
+    if split and C % 128 == 0 and dt == _lib.BF16 and _lib.load().unetca_get_conv_impl() == 0:
+        dskip = torch.empty(B, Hl, Wl, split, dtype=tdt, device=dev)
+        dup = torch.empty(B, Hl, Wl, C - split, dtype=tdt, device=dev)
+        _lib.call("unetca_conv3x3_fwd_split", dt, _ptr(dy1), O, _ptr(wd1), 9 * O, _ptr(dskip), split, _ptr(dup), C - split, split,
+                  B, Hl, Wl, O, C, _ptr(sp) if sp is not None else None, npp, st)
+        return dskip, dup
+    dx = torch.empty(B, Hl, Wl, C, dtype=tdt, device=dev)
     _conv3x3(dt, dy1, O, wd1, 9 * O, wdp1, dx, C, B, Hl, Wl, O, C, _ptr(sp) if sp is not None else None, npp, st)
     return dx
 
@@ -851,10 +860,14 @@ def _backward(model: "UNet", sv, g: torch.Tensor, gscale: torch.Tensor, need_dx:
         fused_db = (dt == _lib.BF16 and _lib.load().unetca_get_conv_impl() == 0 and (2 * hi, 2 * wi) == (Hl, Wl))
         nst = ctypes.c_int(0)
         dcat = _double_conv_bwd(eng, sv.dec[i], dcur, G, dt, tdt, True,
-                                dx_stats=(parts, nst) if fused_db else None,        # (B,Hl,Wl,2Cl)
-                                head=head if l == 0 else None)
-        du, ldu = dcat[..., Cl:], 2 * Cl
-        skip_grads[l] = dcat[..., :Cl]
+                                dx_stats=(parts, nst) if fused_db else None,        # (B,Hl,Wl,2Cl), or its two halves
+                                head=head if l == 0 else None, split=Cl if SPLIT_DCAT else 0)
+        if isinstance(dcat, tuple):
+            skip_grads[l], du = dcat
+            ldu = Cl
+        else:
+            du, ldu = dcat[..., Cl:], 2 * Cl
+            skip_grads[l] = dcat[..., :Cl]
         if (2 * hi, 2 * wi) != (Hl, Wl):                                         # adjoint of the resize guard
             du_s = torch.empty(B, 2 * hi, 2 * wi, Cl, dtype=tdt, device=dev)
             _lib.call("unetca_resize_bilinear_bwd", dt, _ptr(du), ldu, Hl, Wl, _ptr(du_s), Cl, 2 * hi, 2 * wi, B, Cl, st)

@@ -51,6 +51,14 @@ def test_module_mirrors_reference_state_dict(golden_dir):
     assert m3.outc.weight.shape == (2, 64, 1, 1)
 
 
+def test_package_directory_is_importable():
+    """`insar-unet-ca_b200/` is a real package (importlib: the hyphen cannot appear in an import statement); `unetca_b200` is
+    its canonical alias."""
+    import importlib
+    m = importlib.import_module("insar-unet-ca_b200")
+    assert m.UNet.__name__ == "UNet" and hasattr(m, "DoubleConv") and hasattr(m, "SELayer")
+
+
 def test_no_cpu_fallback():
     import unetca_b200
     m = unetca_b200.UNet(3, 2, True)

@@ -1005,3 +1005,27 @@ def test_fused_output_head_matches_separate_passes(B, H, W, use_se):
     call("unetca_outc_bn_bwd_apply", dt, ptr(g), ptr(gscale), ptr(w), nc, ptr(y2), C, ptr(dy), C, B, HW, C, ptr(scale), ptr(shift), ptr(mean),
          ptr(invstd), ptr(s), ptr(dp), ptr(coef), stream())
     assert relerr(dy.float().cpu(), dy_ref.float().cpu()) < 1e-2          # dh unrounded vs bf16-rounded
+
+
+@pytest.mark.parametrize("B,C,O,H,W,split", [(2, 64, 128, 40, 24, 64), (1, 128, 256, 33, 17, 128), (2, 256, 512, 16, 16, 256)])
+def test_conv3x3_two_destination_epilogue(B, C, O, H, W, split):
+    """unetca_conv3x3_fwd_split == unetca_conv3x3_fwd with the output channels delivered as two dense tensors (the dgrad of a
+    decoder block's first conv: d skip / d upsampled, autograd of torch.cat at UCA:140), statistics unchanged."""
+    dt = BF16
+    rs = np.random.RandomState(C + O)
+    call("unetca_set_conv_impl", 0)
+    x = to_nhwc(torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32)), dt)
+    w = torch.from_numpy((rs.standard_normal((O, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32)).cuda()
+    wf = torch.empty(O, 9 * C, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_conv3x3_weight", dt, ptr(w), ptr(wf), 9 * C, None, O, C, stream())
+    y = torch.empty(B, H, W, O, dtype=TDT[dt], device="cuda")
+    parts, n = parts_buf(B), cint()
+    call("unetca_conv3x3_fwd", dt, ptr(x), C, ptr(wf), 9 * C, ptr(y), O, B, H, W, C, O, ptr(parts), ctypes.byref(n), stream())
+    st_ref = parts[: n.value * 2 * O].clone()
+    y1 = torch.full((B, H, W, split), float("nan"), dtype=TDT[dt], device="cuda")
+    y2 = torch.full((B, H, W, O - split), float("nan"), dtype=TDT[dt], device="cuda")
+    parts2, n2 = parts_buf(B), cint()
+    call("unetca_conv3x3_fwd_split", dt, ptr(x), C, ptr(wf), 9 * C, ptr(y1), split, ptr(y2), O - split, split, B, H, W, C, O,
+         ptr(parts2), ctypes.byref(n2), stream())
+    assert torch.equal(y1, y[..., :split]) and torch.equal(y2, y[..., split:])
+    assert n2.value == n.value and torch.equal(parts2[: n.value * 2 * O], st_ref)

@@ -51,6 +51,11 @@ def run_scene(scene, core, halo, batch, precision, repeat, dev, rank=0, world=1)
             wnd = window(t0, spec, H, W, dev)
             model(torch.stack([wnd[:, :512, :512], wnd[:, 512:1024, 512:1024]]))
     model.eval()
+    # ... and centre the two class logits (random weights leave a constant offset, i.e. an all-zero mask): shift the class-1
+    # bias by the median logit difference of one window, the same on every rank (same seed, same window)
+    with torch.no_grad():
+        lg = model(window(tiling.Tile(0, 0, 0, core, core), spec, H, W, dev)[None, :, :512, :512])
+        model.outc.bias.data[1] += (lg[:, 0] - lg[:, 1]).median()
     tiles = tiling.shard(tiling.plan(H, W, spec), rank, world)
     out = torch.empty(len(tiles), core, core, dtype=torch.uint8, device=dev)     # this rank's cores
 
