@@ -124,6 +124,12 @@ def _work(name, a, e, cin):
     if name == "unetca_conv3x3_dgrad_bnstats":
         B, H, W, C, O = a[7:12]
         return "tensor", 2.0 * B * H * W * 9 * C * O, 0
+    if name == "unetca_conv3x3_fwd_cat":
+        B, H, W, C, O = a[9:14]
+        return "tensor", 2.0 * B * H * W * 9 * C * O, 0
+    if name == "unetca_conv3x3_wgrad_cat":
+        B, H, W, C, O = a[10:15]
+        return "tensor", 2.0 * B * H * W * 9 * C * O, 0
     if name == "unetca_se_squeeze":
         B, hw, C = a[3:6]
         return "hbm", 0, B * hw * C * e
@@ -847,7 +853,8 @@ def main():
         # (tc_conv3x3_hpix_kernel: every unetca_conv3x3_fwd call here has O % 128 == 0, plus the dgrads with the fused
         # BatchNorm-backward statistics epilogue, unetca_conv3x3_dgrad_bnstats with O % 128 == 0)
         dom = kernel_rows(lambda n, a: n in ("unetca_conv3x3_fwd", "unetca_conv3x3_fwd_split") or
-                          (n == "unetca_conv3x3_dgrad_bnstats" and a[11] % 128 == 0))
+                          (n == "unetca_conv3x3_dgrad_bnstats" and a[11] % 128 == 0) or
+                          (n == "unetca_conv3x3_fwd_cat" and a[13] % 128 == 0))
         roof_all = {"bound": "tensor", "achieved": ach_t, "peak": pk["tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach_t / pk["tflops_sustained"], "traffic": traffic.get("tensor", {}).get("dram_bytes_per_launch"),
                     "kernel": "all tcgen05 contraction kernels (conv3x3 fwd/dgrad/wgrad, ConvTranspose, first conv), aggregate",
@@ -859,7 +866,7 @@ def main():
                     "frac": ach_d / pk["tflops_sustained"], "frac_of_burst_peak": ach_d / pk["tflops_burst"],
                     "traffic": traffic.get("dominant", {}).get("dram_bytes_per_launch"), "traffic_source": traffic_note,
                     "kernel": "tc_conv3x3_hpix_kernel (tcgen05 haloed pixels-on-N conv3x3 forward/dgrad; entries unetca_conv3x3_fwd, "
-                              "unetca_conv3x3_fwd_split (two-destination epilogue) and, with the fused BN-backward statistics epilogue, "
+                              "unetca_conv3x3_fwd_split (two-destination epilogue), unetca_conv3x3_fwd_cat (two-source operand) and, with the fused BN-backward statistics epilogue, "
                               "unetca_conv3x3_dgrad_bnstats)",
                     "launches": dom["calls"], "avg_launch_ms": dom["ms"] / dom["calls"], "share_of_step": dom["ms"] / nk / ms_kstep,
                     "flops_per_launch_avg": dom["flops"] / dom["calls"], "peak_source": pk["source"] + " bf16_tflops_sustained",

@@ -65,6 +65,13 @@ int unetca_conv3x3_fwd_paired(int dtype, const void* x, int ldx, const void* w_p
 /* the 64 -> 64 channel layers (inc / conv4 second convs and their dgrads, UCA:84 at full resolution), H even: row-pair
  * layout with the whole filter resident in shared memory and haloed lattice tiles (tc_conv3x3_rp64_kernel); w is the
  * ordinary packed filter [64][ldk >= 576] of unetca_pack_conv3x3_weight.  bf16 only. */
+/* First conv of a decoder block: its input is torch.cat([skip, up], dim=1) (UCA:140,146,152,158).  The two halves stay two
+ * DENSE tensors (x: channels [0, C1) = skip, x2: [C1, C) = upsampled; C1 % 64 == 0): the concat costs nothing and nobody writes or
+ * reads half-pixels at a doubled stride.  fwd_cat: O % 128 == 0 with w = packed filter [O][9*C], or O == 64 && C == 128 with
+ * w = kw-stacked filter; scale/shift non-null: eval-mode BatchNorm + ReLU in the epilogue (as unetca_conv3x3_bnrelu_fwd), sq_parts:
+ * SE squeeze sums (O % 128 == 0 only).  wgrad_cat: as unetca_conv3x3_wgrad.  bf16 only; other shapes: UNETCA_ERR_UNSUPPORTED. */
+int unetca_conv3x3_fwd_cat(int dtype, const void* x, int ldx, const void* x2, int ldx2, int C1, const void* w, void* y, int ldy, int B, int H, int W, int C, int O, float* stat_parts, const float* scale, const float* shift, float* sq_parts, int* nparts, void* stream);
+int unetca_conv3x3_wgrad_cat(int dtype, const void* dy, int lddy, const void* x, int ldx, const void* x2, int ldx2, int C1, float* ws, long ws_floats, int B, int H, int W, int C, int O, float* dw, void* stream);
 /* unetca_conv3x3_fwd (O % 128 == 0) writing output channels [0, split) to y and [split, O) to y2: the dgrad of a decoder block's
  * first conv (its input is torch.cat([skip, up]), UCA:140) leaves d(skip) and d(up) as two dense tensors.  bf16 only. */
 int unetca_conv3x3_fwd_split(int dtype, const void* x, int ldx, const void* w, int ldk, void* y, int ldy, void* y2, int ldy2, int split, int B, int H, int W, int C, int O, float* stat_parts, int* nparts, void* stream);

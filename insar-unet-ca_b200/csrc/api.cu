@@ -12,6 +12,9 @@ int unetca_tc_conv3x3_fwd_paired(const void*, int, const void*, void*, int, int,
 int unetca_tc_pack_pair(const void*, int, void*, int, int, void*);
 int unetca_tc_conv3x3_fwd_rp64(const void*, int, const void*, int, void*, int, int, int, int, float*, void*);
 int unetca_tc_conv3x3_fwd_split(const void*, int, const void*, int, void*, int, void*, int, int, int, int, int, int, int, float*, void*);
+int unetca_tc_conv3x3_fwd_cat(const void*, int, const void*, int, int, const void*, void*, int, int, int, int, int, int, float*,
+                              const float*, const float*, float*, void*);
+int unetca_tc_conv3x3_wgrad_cat(const void*, int, const void*, int, const void*, int, int, float*, long, int, int, int, int, int, void*);
 int unetca_tc_conv3x3_dgrad_bnstats(const void*, int, const void*, int, void*, int, int, int, int, int, int, const void*, int,
                                     const float*, const float*, const float*, float*, void*);
 int unetca_tc_conv3x3_fwd_kw(const void*, int, const void*, void*, int, int, int, int, int, float*, void*);
@@ -93,6 +96,24 @@ int unetca_conv3x3_fwd_split(int dtype, const void* x, int ldx, const void* w, i
     if (rc < 0) return rc;
     if (nparts) *nparts = rc;
     return 0;
+}
+
+// conv3x3 forward of torch.cat([x, x2], 1) (UCA:140) with the two halves as dense tensors; see the header.  bf16 tensor cores only.
+int unetca_conv3x3_fwd_cat(int dtype, const void* x, int ldx, const void* x2, int ldx2, int C1, const void* w, void* y, int ldy,
+                           int B, int H, int W, int C, int O, float* stat_parts, const float* scale, const float* shift,
+                           float* sq_parts, int* nparts, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("conv3x3_fwd_cat: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int rc = unetca_tc_conv3x3_fwd_cat(x, ldx, x2, ldx2, C1, w, y, ldy, B, H, W, C, O, stat_parts, scale, shift, sq_parts, stream);
+    if (rc < 0) return rc;
+    if (nparts) *nparts = rc;
+    return 0;
+}
+int unetca_conv3x3_wgrad_cat(int dtype, const void* dy, int lddy, const void* x, int ldx, const void* x2, int ldx2, int C1,
+                             float* ws, long ws_floats, int B, int H, int W, int C, int O, float* dw, void* stream) {
+    if (!use_tc(dtype)) { unetca::set_error("conv3x3_wgrad_cat: bf16 tensor-core path only"); return UNETCA_ERR_UNSUPPORTED; }
+    int ns = unetca_tc_conv3x3_wgrad_cat(dy, lddy, x, ldx, x2, ldx2, C1, ws, ws_floats, B, H, W, C, O, stream);
+    if (ns < 0) return ns;
+    return unetca_wgrad_reduce(ws, ns, (long)O * 9 * C, 0, O, C, 9 * C, dw, stream);
 }
 
 // dgrad + ReLU/BatchNorm backward statistics of its output in one kernel (replaces the unetca_bn_bwd_reduce pass)

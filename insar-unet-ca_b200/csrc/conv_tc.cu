@@ -25,6 +25,16 @@
 
 namespace unetca {
 
+// Activation operand with TWO sources: channels [0, xsplit) come from tensor map m1, channels [xsplit, C) from m2 (at
+// c0 - xsplit).  A decoder block's first conv reads torch.cat([skip, up], 1) (UCA:140): with the two halves kept as two DENSE
+// tensors — the encoder block writes the skip, the transposed conv the upsampled one — nobody writes or reads 128-byte rows
+// at a 256-byte stride, and the concat still costs nothing.  xsplit == 0: single source (a multiple of 64 otherwise).
+__device__ __forceinline__ void tma_load_x2(const CUtensorMap* m1, const CUtensorMap* m2, int xsplit, uint64_t* bar, void* dst,
+                                            int c0, int w, int h, int b) {
+    if (xsplit > 0 && c0 >= xsplit) tma_load_4d(m2, bar, dst, c0 - xsplit, w, h, b);
+    else tma_load_4d(m1, bar, dst, c0, w, h, b);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // kernel parameters
 // ---------------------------------------------------------------------------------------------------------
@@ -399,6 +409,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_kernel(const __grid_constant
 // ---------------------------------------------------------------------------------------------------------
 struct alignas(64) Wg3Params {
     CUtensorMap mapX, mapDY;
+    CUtensorMap mapX2;           // second activation source (channels >= xsplit), see tma_load_x2
+    int xsplit;
     int cchunks, oblocks;
     int tilesW, tilesH, nimg;
     int ktiles_total, nsplit;
@@ -458,7 +470,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_kernel(const __grid
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* xs = smem + s * kWgStageBytes;
                     mbar_expect_tx(&full_bar[s], kWgXBox + kWgYBytes);
-                    tma_load_4d(&p.mapX, &full_bar[s], xs, cc * 64, w0 - 1, h0 - 1, b);
+                    tma_load_x2(&p.mapX, &p.mapX2, p.xsplit, &full_bar[s], xs, cc * 64, w0 - 1, h0 - 1, b);
                     tma_load_4d(&p.mapDY, &full_bar[s], xs + kWgXBytes, ob * 64, w0, h0, b);
                     if (++s == kWgStages) { s = 0; ph ^= 1; }
                 }
@@ -597,8 +609,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide_kernel(const _
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* xs = smem + s * kWg2StageBytes;
                     mbar_expect_tx(&full_bar[s], kWg2StageBytes);
-                    tma_load_4d(&p.mapX, &full_bar[s], xs, cp * 128, w0 - 1, h0 - 1 + kh, b);
-                    tma_load_4d(&p.mapX, &full_bar[s], xs + kWg2XBytes, cp * 128 + 64, w0 - 1, h0 - 1 + kh, b);
+                    tma_load_x2(&p.mapX, &p.mapX2, p.xsplit, &full_bar[s], xs, cp * 128, w0 - 1, h0 - 1 + kh, b);
+                    tma_load_x2(&p.mapX, &p.mapX2, p.xsplit, &full_bar[s], xs + kWg2XBytes, cp * 128 + 64, w0 - 1, h0 - 1 + kh, b);
                     tma_load_4d(&p.mapDY, &full_bar[s], xs + 2 * kWg2XBytes, op * 128, w0, h0, b);
                     tma_load_4d(&p.mapDY, &full_bar[s], xs + 2 * kWg2XBytes + kWgYBytes, op * 128 + 64, w0, h0, b);
                     if (++s == kWg2Stages) { s = 0; ph ^= 1; }
@@ -736,8 +748,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_wide256_kernel(cons
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* xs = smem + s * kWg3StageBytes;
                     mbar_expect_tx(&full_bar[s], 2 * kWg3XBox + 4 * kWgYBytes);
-                    tma_load_4d(&p.mapX, &full_bar[s], xs, cp * 128, w0 - 1, h0 - 1 + kh0, b);
-                    tma_load_4d(&p.mapX, &full_bar[s], xs + kWg3XBytes, cp * 128 + 64, w0 - 1, h0 - 1 + kh0, b);
+                    tma_load_x2(&p.mapX, &p.mapX2, p.xsplit, &full_bar[s], xs, cp * 128, w0 - 1, h0 - 1 + kh0, b);
+                    tma_load_x2(&p.mapX, &p.mapX2, p.xsplit, &full_bar[s], xs + kWg3XBytes, cp * 128 + 64, w0 - 1, h0 - 1 + kh0, b);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         tma_load_4d(&p.mapDY, &full_bar[s], xs + 2 * kWg3XBytes + j * kWgYBytes, oq * 256 + j * 64, w0, h0, b);
@@ -886,7 +898,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_wgrad3x3_rowpair_kernel(cons
                     uint8_t* xs = smem + s * kWg4StageBytes;
                     mbar_expect_tx(&full_bar[s], kWg4XBox + kWgYBytes);
                     // X rows h0 - 1 + 2*vp ... (+9): both views of the pair
-                    tma_load_4d(&p.mapX, &full_bar[s], xs, cc * 64, w0 - 1, h0 - 1 + 2 * vp, b);
+                    tma_load_x2(&p.mapX, &p.mapX2, p.xsplit, &full_bar[s], xs, cc * 64, w0 - 1, h0 - 1 + 2 * vp, b);
                     tma_load_4d(&p.mapDY, &full_bar[s], xs + kWg4XBytes, ob * 64, w0, h0, b);
                     if (++s == kWg4Stages) { s = 0; ph ^= 1; }
                 }
@@ -1431,6 +1443,8 @@ __device__ __forceinline__ void rp64_drain_bwd(uint32_t t_addr, int cb0, bf16* _
 // ---------------------------------------------------------------------------------------------------------
 struct alignas(64) HpixParams {
     CUtensorMap mapX, mapW;
+    CUtensorMap mapX2;           // second activation source (channels >= xsplit), see tma_load_x2
+    int xsplit;
     bf16* out;
     int ldo;
     // optional second destination: output channels >= split go to out2 (pixel stride ldo2, channel - split) — the dgrad of a
@@ -1508,7 +1522,7 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     mbar_wait(&xempty[s], ph ^ 1);
                     mbar_expect_tx(&xfull[s], kHpXBox);
-                    tma_load_4d(&p.mapX, &xfull[s], x_ring + s * kHpXBytes, cc * 64, tw * kHpTW - 1, th * kHpTH - 1, b);
+                    tma_load_x2(&p.mapX, &p.mapX2, p.xsplit, &xfull[s], x_ring + s * kHpXBytes, cc * 64, tw * kHpTW - 1, th * kHpTH - 1, b);
                     if (++s == kHpXS) { s = 0; ph ^= 1; }
                 }
             }
@@ -1905,6 +1919,8 @@ __global__ void __launch_bounds__(kRpThreads, 1) tc_conv3x3_rp64_kernel(const __
 // ---------------------------------------------------------------------------------------------------------
 struct alignas(64) KwParams {
     CUtensorMap mapX, mapW, mapOut;
+    CUtensorMap mapX2;           // second activation source (channels >= xsplit), see tma_load_x2
+    int xsplit;
     int tilesX, tilesY, nimg, H, W;
     int cchunks;
     float* stat_parts;
@@ -1973,7 +1989,7 @@ __global__ void __launch_bounds__(kKwThreads, 1) tc_conv3x3_kw_kernel(const __gr
                 for (int cc = 0; cc < p.cchunks; ++cc) {
                     mbar_wait(&xempty[s], ph ^ 1);
                     mbar_expect_tx(&xfull[s], kKwXBytes);
-                    tma_load_4d(&p.mapX, &xfull[s], x_ring + s * kKwXBytes, cc * 64, tx * kKwOutW - 1, ty * kKwTH - 1, b);
+                    tma_load_x2(&p.mapX, &p.mapX2, p.xsplit, &xfull[s], x_ring + s * kKwXBytes, cc * 64, tx * kKwOutW - 1, ty * kKwTH - 1, b);
                     if (++s == XS) { s = 0; ph ^= 1; }
                 }
             }
@@ -2282,17 +2298,27 @@ int make_tmap_nhwc(CUtensorMap* m, const void* base, int elem_bytes, long C, lon
     return 0;
 }
 
+// optional second activation source of a conv whose input is a channel concat kept as two dense tensors
+struct XSrc2 { const void* x2; int ldx2; int xsplit; };
+
 // fused ReLU + BatchNorm backward statistics of a dgrad's output (saved pre-BN conv output y + the BN constants)
 struct BwdStats { const void* y; int ldy; const float* scale; const float* shift; const float* mean; };
 
 // conv3x3 forward / dgrad for O % 128 == 0 through the haloed pixels-on-N kernel; w = packed filter [O][9*C]
 static int launch_hpix(const void* x, int ldx, const void* w, int ldk, void* y, int ldy, int B, int H, int W, int C, int O,
                        float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr,
-                       float* sq_parts = nullptr, const BwdStats* bwd = nullptr, void* y2 = nullptr, int ldy2 = 0, int split = 0) {
+                       float* sq_parts = nullptr, const BwdStats* bwd = nullptr, void* y2 = nullptr, int ldy2 = 0, int split = 0,
+                       const XSrc2* xs2 = nullptr) {
     HpixParams p;
     memset(&p, 0, sizeof(p));
     int rc;
-    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kHpPitch, kHpTH + 2)) < 0) return rc;
+    const int C1 = xs2 ? xs2->xsplit : C;
+    if ((rc = make_map(&p.mapX, x, C1, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kHpPitch, kHpTH + 2)) < 0) return rc;
+    if (xs2) {
+        if ((rc = make_map(&p.mapX2, xs2->x2, C - C1, W, H, B, xs2->ldx2, (long)W * xs2->ldx2, (long)H * W * xs2->ldx2, kHpPitch,
+                           kHpTH + 2)) < 0) return rc;
+        p.xsplit = C1;
+    }
     if ((rc = make_map(&p.mapW, w, 9L * C, O, 1, 1, ldk, (long)O * ldk, (long)O * ldk, 128, 1)) < 0) return rc;
     p.out = (bf16*)y; p.ldo = ldy;
     p.out2 = (bf16*)y2; p.ldo2 = ldy2; p.split = split;
@@ -2323,12 +2349,19 @@ static int g_no_kw = 0;
 
 // conv3x3 forward / dgrad for exactly 64 output channels and C in {64, 128}: kw-stacked kernel; w_kw from unetca_tc_pack_kw
 static int launch_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C,
-                     float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr) {
+                     float* stat_parts, cudaStream_t st, const float* ep_scale = nullptr, const float* ep_shift = nullptr,
+                     const XSrc2* xs2 = nullptr) {
     KwParams p;
     memset(&p, 0, sizeof(p));
     const int cch = C / 64;
     int rc;
-    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kKwTW, kKwTH + 2)) < 0) return rc;
+    const int C1 = xs2 ? xs2->xsplit : C;
+    if ((rc = make_map(&p.mapX, x, C1, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kKwTW, kKwTH + 2)) < 0) return rc;
+    if (xs2) {
+        if ((rc = make_map(&p.mapX2, xs2->x2, C - C1, W, H, B, xs2->ldx2, (long)W * xs2->ldx2, (long)H * W * xs2->ldx2, kKwTW,
+                           kKwTH + 2)) < 0) return rc;
+        p.xsplit = C1;
+    }
     const long rows = 9L * cch * 64;
     if ((rc = make_map(&p.mapW, w_kw, 64, rows, 1, 1, 64, rows * 64, rows * 64, 192, 1)) < 0) return rc;
     if ((rc = make_map(&p.mapOut, y, 64, W, H, B, ldy, (long)W * ldy, (long)H * W * ldy, kKwOutW, kKwTH)) < 0) return rc;
@@ -2566,6 +2599,23 @@ int unetca_tc_conv3x3_fwd_split(const void* x, int ldx, const void* w, int ldk, 
                        y2, ldy2, split);
 }
 
+// conv3x3 forward whose input is a channel concat kept as two dense tensors (x: channels [0, C1), x2: [C1, C)).
+// O % 128 == 0: haloed kernel with w = packed filter [O][9*C]; O == 64 && C == 128: kw-stacked kernel with w = kw-stacked filter.
+// scale / shift non-null: eval-mode BatchNorm + ReLU in the epilogue; sq_parts: SE squeeze sums (haloed kernel only).
+int unetca_tc_conv3x3_fwd_cat(const void* x, int ldx, const void* x2, int ldx2, int C1, const void* w, void* y, int ldy, int B,
+                              int H, int W, int C, int O, float* stat_parts, const float* scale, const float* shift,
+                              float* sq_parts, void* stream) {
+    UNETCA_REQUIRE(x2 && C % 64 == 0 && C1 > 0 && C1 < C && C1 % 64 == 0 && O % 64 == 0 && O <= 1024, "tc_conv3x3_fwd_cat: C1=%d C=%d O=%d", C1, C, O);
+    XSrc2 xs{x2, ldx2, C1};
+    if (O % 128 == 0)
+        return launch_hpix(x, ldx, w, 9 * C, y, ldy, B, H, W, C, O, stat_parts, (cudaStream_t)stream, scale, shift, sq_parts, nullptr,
+                           nullptr, 0, 0, &xs);
+    if (O == 64 && C == 128 && !sq_parts)
+        return launch_kw(x, ldx, w, y, ldy, B, H, W, C, stat_parts, (cudaStream_t)stream, scale, shift, &xs);
+    set_error("tc_conv3x3_fwd_cat: no kernel for C=%d O=%d", C, O);
+    return UNETCA_ERR_UNSUPPORTED;
+}
+
 // conv3x3 forward / dgrad for 64 output channels (C = 64 or 128) through the kw-stacked kernel
 int unetca_tc_conv3x3_fwd_kw(const void* x, int ldx, const void* w_kw, void* y, int ldy, int B, int H, int W, int C,
                              float* stat_parts, void* stream) {
@@ -2765,8 +2815,8 @@ static int pick_nsplit(long tiles, int ktiles, long stride_floats, long ws_float
 }
 
 // ws[z][o][tap*C+c] = sum_{p in split z} dy[p][o] * x[p+s(tap)][c]; returns nsplit.  Halo-reuse kernel.
-int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H,
-                            int W, int C, int O, void* stream) {
+static int tc_conv3x3_wgrad_impl(const void* dy, int lddy, const void* x, int ldx, const XSrc2* xs2, float* ws, long ws_floats,
+                                 int B, int H, int W, int C, int O, void* stream) {
     UNETCA_REQUIRE(C % 64 == 0 && O % 64 == 0, "tc_conv3x3_wgrad: C=%d O=%d must be multiples of 64", C, O);
     Wg3Params p;
     memset(&p, 0, sizeof(p));
@@ -2774,8 +2824,14 @@ int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, fl
     const bool wide = (C % 128 == 0) && (O % 128 == 0) && g_wgrad_narrow != 1;
     const bool wide256 = wide && (O % 256 == 0) && g_wgrad_narrow != 2;
     const bool rowpair = !wide && g_wgrad_narrow == 0;
-    if ((rc = make_map(&p.mapX, x, C, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kWgPitch,
-                       wide256 ? kWg3XRows : wide ? kWgTH : rowpair ? kWg4XRows : kWgTH + 2)) < 0) return rc;
+    const int xrows = wide256 ? kWg3XRows : wide ? kWgTH : rowpair ? kWg4XRows : kWgTH + 2;
+    const int C1 = xs2 ? xs2->xsplit : C;
+    if ((rc = make_map(&p.mapX, x, C1, W, H, B, ldx, (long)W * ldx, (long)H * W * ldx, kWgPitch, xrows)) < 0) return rc;
+    if (xs2) {
+        if ((rc = make_map(&p.mapX2, xs2->x2, C - C1, W, H, B, xs2->ldx2, (long)W * xs2->ldx2, (long)H * W * xs2->ldx2, kWgPitch,
+                           xrows)) < 0) return rc;
+        p.xsplit = C1;
+    }
     if ((rc = make_map(&p.mapDY, dy, O, W, H, B, lddy, (long)W * lddy, (long)H * W * lddy, kWgTW, kWgTH)) < 0) return rc;
     p.cchunks = C / 64; p.oblocks = O / 64;
     p.tilesW = ceil_div(W, kWgTW); p.tilesH = ceil_div(H, kWgTH); p.nimg = B;
@@ -2811,6 +2867,18 @@ int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, fl
     else tc_wgrad3x3_kernel<<<(int)grid, kTcThreads, kWgSmemBytes, (cudaStream_t)stream>>>(p);
     rc = check_launch("tc_conv3x3_wgrad");
     return rc < 0 ? rc : p.nsplit * slices_per_split;
+}
+
+int unetca_tc_conv3x3_wgrad(const void* dy, int lddy, const void* x, int ldx, float* ws, long ws_floats, int B, int H,
+                            int W, int C, int O, void* stream) {
+    return tc_conv3x3_wgrad_impl(dy, lddy, x, ldx, nullptr, ws, ws_floats, B, H, W, C, O, stream);
+}
+// the same with the activation given as two dense tensors: channels [0, C1) in x, [C1, C) in x2 (C1 a multiple of 64)
+int unetca_tc_conv3x3_wgrad_cat(const void* dy, int lddy, const void* x, int ldx, const void* x2, int ldx2, int C1, float* ws,
+                                long ws_floats, int B, int H, int W, int C, int O, void* stream) {
+    UNETCA_REQUIRE(x2 && C1 > 0 && C1 < C && C1 % 64 == 0, "tc_conv3x3_wgrad_cat: C1=%d C=%d", C1, C);
+    XSrc2 xs{x2, ldx2, C1};
+    return tc_conv3x3_wgrad_impl(dy, lddy, x, ldx, &xs, ws, ws_floats, B, H, W, C, O, stream);
 }
 
 // the generic (one box per tap) kernel, kept for cross-checks

@@ -23,6 +23,7 @@ Extra, beyond the reference API:
 from __future__ import annotations
 
 import ctypes
+import os
 from types import SimpleNamespace
 
 import torch
@@ -294,6 +295,17 @@ def _conv3x3(dt, x, ldx, w, ldk, w_pair, y, ldy, B, H, W, C, O, sp, nparts, st):
         _lib.call("unetca_conv3x3_fwd", dt, _ptr(x), ldx, _ptr(w), ldk, _ptr(y), ldy, B, H, W, C, O, sp, nparts, st)
 
 
+def _conv3x3_cat(dt, xin, wf, w_pair, y, ldy, B, H, W, C, O, sp, nparts, st, scale=None, shift=None, sq_parts=None):
+    """conv3x3 of torch.cat([skip, up], 1) (UCA:140) with the two halves as dense tensors xin = (skip, up): haloed kernel for
+    O % 128 == 0, kw-stacked kernel for 128 -> 64; optional eval-mode BatchNorm + ReLU / SE squeeze epilogue."""
+    x1, x2 = xin
+    w = w_pair[1] if (O % 128 and isinstance(w_pair, tuple) and w_pair[0] == "kw") else wf
+    if O % 128 and w is wf:
+        raise RuntimeError(f"no two-source conv kernel for {C} -> {O} channels")
+    _lib.call("unetca_conv3x3_fwd_cat", dt, _ptr(x1), x1.stride(2), _ptr(x2), x2.stride(2), x1.shape[3], _ptr(w), _ptr(y), ldy,
+              B, H, W, C, O, sp, _ptr(scale), _ptr(shift), _ptr(sq_parts), nparts, st)
+
+
 def sv_pairs(col, B, H, W):
     """True when `col` is the pixel-pair im2col buffer (one row per pair of rows) rather than the per-pixel one."""
     return col is not None and col.shape[0] == B * (H // 2) * W and H % 2 == 0
@@ -301,6 +313,7 @@ def sv_pairs(col, B, H, W):
 
 FUSE_SQUEEZE = True      # inference: take the SE squeeze in the second conv's epilogue (False: separate read-only pass)
 FUSE_HEAD = True          # outc (UCA:162) fused with the last block's SE-scale / BN2-backward passes: its input and input-gradient never exist
+PLANAR_CAT = os.environ.get("UNETCA_PLANAR_CAT", "0") == "1"   # decoder conv1 input as two dense tensors (two-source conv operand) instead of one [.., 2C] concat buffer; bit-identical, measured neutral -> off
 SPLIT_DCAT = True         # decoder conv1 dgrad writes d(skip) and d(up) as two dense tensors (False: one [.., 2C] buffer)
 FUSE_BN_BWD_STATS = True  # training: BN1-backward statistics in the epilogue of the dgrad conv that writes dA1 (False: reduce pass)
 
@@ -402,6 +415,8 @@ def _double_conv_fwd(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos, train
     elif blk.first:
         _lib.call("unetca_gemm_nt", dt, _ptr(col), col.shape[1], _ptr(wf1), ldk1, _ptr(y1), O, npix, O, col.shape[1],
                   sp, ctypes.byref(nparts), st)
+    elif isinstance(xin, tuple):
+        _conv3x3_cat(dt, xin, wf1, wfp1, y1, O, B, Hl, Wl, C, O, sp, ctypes.byref(nparts), st)
     else:
         _conv3x3(dt, xin, xin.stride(2), wf1, ldk1, wfp1, y1, O, B, Hl, Wl, C, O, sp, ctypes.byref(nparts), st)
     scale1, shift1 = bn_params(blk.bn1, blk.conv1, "1")
@@ -472,6 +487,8 @@ def _double_conv_eval_fused(eng, blk, xin, col, B, Hl, Wl, out_view, pooled, pos
     if blk.first:
         _lib.call("unetca_first_pairs_bnrelu_fwd", dt, _ptr(col), _ptr(wfp1), _ptr(a1), O, B, Hl, Wl, O, _ptr(scale1),
                   _ptr(shift1), st)
+    elif isinstance(xin, tuple):
+        _conv3x3_cat(dt, xin, wf1, wfp1, a1, O, B, Hl, Wl, C, O, None, None, st, scale1, shift1)
     else:
         ok = _conv3x3_bnrelu(dt, xin, xin.stride(2), wf1, wfp1, a1, O, B, Hl, Wl, C, O, scale1, shift1, st)
         assert ok
@@ -557,13 +574,21 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
     col = _first_conv_rows(dt, tdt, xf, B, Cin, H, W)
 
     sv = SimpleNamespace(enc=[], dec=[], up_in=[], cat=[], pos=[], B=B, H=H, W=W, Hs=Hs, Ws=Ws)
-    cat = [torch.empty(B, Hs[l], Ws[l], 2 * _WIDTHS[l], dtype=tdt, device=dev) for l in range(4)]
+    # torch.cat([skip, up], 1) (UCA:140..158) never happens: the producers write the operand of the decoder's first conv in
+    # place.  bf16 tensor-core path: two DENSE tensors per level (the conv kernels take a two-source operand), so nobody
+    # writes or reads half-pixels at a doubled stride; otherwise the two channel halves of one [B,H,W,2C] buffer.
+    planar = PLANAR_CAT and dt == _lib.BF16 and _lib.load().unetca_get_conv_impl() == 0
+    if planar:
+        cat = [(torch.empty(B, Hs[l], Ws[l], _WIDTHS[l], dtype=tdt, device=dev),
+                torch.empty(B, Hs[l], Ws[l], _WIDTHS[l], dtype=tdt, device=dev)) for l in range(4)]
+    else:
+        cat = [torch.empty(B, Hs[l], Ws[l], 2 * _WIDTHS[l], dtype=tdt, device=dev) for l in range(4)]
     # ---- encoder
     xin = None
     for l, blk in enumerate(model._enc_blocks):
         Hl, Wl, Cl = Hs[l], Ws[l], _WIDTHS[l]
         if l < 4:
-            out_view = cat[l][..., :Cl]
+            out_view = cat[l][0] if planar else cat[l][..., :Cl]
             pooled = torch.empty(B, Hl // 2, Wl // 2, Cl, dtype=tdt, device=dev)
             pos = torch.empty(B, Hl // 2, Wl // 2, Cl, dtype=torch.uint8, device=dev)
         else:
@@ -581,15 +606,16 @@ def _forward(model: "UNet", x: torch.Tensor, keep: bool):
         Hl, Wl, Cl = Hs[l], Ws[l], _WIDTHS[l]
         hi, wi = Hs[l + 1], Ws[l + 1]
         wf, _ = eng.convT_w(up, dt, tdt)
+        up_view = cat[l][1] if planar else cat[l][..., Cl:]
         if (2 * hi, 2 * wi) == (Hl, Wl):
-            _lib.call("unetca_convT2x2_fwd", dt, _ptr(h), h.stride(2), _ptr(wf), _ptr(up.bias), _ptr(cat[l][..., Cl:]),
-                      2 * Cl, B, hi, wi, 2 * Cl, Cl, st)
+            _lib.call("unetca_convT2x2_fwd", dt, _ptr(h), h.stride(2), _ptr(wf), _ptr(up.bias), _ptr(up_view),
+                      up_view.stride(2), B, hi, wi, 2 * Cl, Cl, st)
         else:
             # resize guard (UCA:138-157): the transposed conv gives 2*floor(H/2) rows / columns, the skip has H
             u = torch.empty(B, 2 * hi, 2 * wi, Cl, dtype=tdt, device=dev)
             _lib.call("unetca_convT2x2_fwd", dt, _ptr(h), h.stride(2), _ptr(wf), _ptr(up.bias), _ptr(u), Cl, B, hi, wi,
                       2 * Cl, Cl, st)
-            _lib.call("unetca_resize_bilinear_fwd", dt, _ptr(u), Cl, 2 * hi, 2 * wi, _ptr(cat[l][..., Cl:]), 2 * Cl, Hl, Wl,
+            _lib.call("unetca_resize_bilinear_fwd", dt, _ptr(u), Cl, 2 * hi, 2 * wi, _ptr(up_view), up_view.stride(2), Hl, Wl,
                       B, Cl, st)
         sv.up_in.append(h if keep else None)
         head = None
@@ -765,6 +791,10 @@ def _double_conv_bwd(eng, sv, dout, G, dt, tdt, need_dx, lazy=None, dx_stats=Non
     elif blk.first:
         _lib.call("unetca_im2col_wgrad", dt, _ptr(dy1), O, _ptr(sv.col), sv.col.shape[1], _ptr(ws), ws.numel(), npix, C, O,
                   _ptr(dw), st)
+    elif isinstance(sv.xin, tuple):
+        x1, x2 = sv.xin
+        _lib.call("unetca_conv3x3_wgrad_cat", dt, _ptr(dy1), O, _ptr(x1), x1.stride(2), _ptr(x2), x2.stride(2), x1.shape[3],
+                  _ptr(ws), ws.numel(), B, Hl, Wl, C, O, _ptr(dw), st)
     else:
         _lib.call("unetca_conv3x3_wgrad", dt, _ptr(dy1), O, _ptr(sv.xin), sv.xin.stride(2), _ptr(ws), ws.numel(), B, Hl,
                   Wl, C, O, _ptr(dw), st)

@@ -335,3 +335,30 @@ def test_graphed_train_step_is_bit_identical_to_eager(own):
     lg, pg = run(True)
     assert le == lg, (le, lg)
     assert all(torch.equal(a, b) for a, b in zip(pe, pg))
+
+
+@pytest.mark.parametrize("H,W,train", [(64, 64, True), (40, 52, True), (64, 48, False)])
+def test_two_source_concat_is_bit_identical(H, W, train, monkeypatch):
+    """model.PLANAR_CAT (opt-in): skip and upsampled halves of torch.cat (UCA:140) kept as two dense tensors that the decoder's
+    first conv and its weight gradient read through a two-source operand — logits, loss and every gradient identical to the
+    single concat buffer."""
+    import unetca_b200
+    from unetca_b200 import model as M
+    sd = port.make_state_dict(seed=5)
+    x, y = port.make_batch(5, 2, H, W)
+    out = []
+    for planar in (False, True):
+        monkeypatch.setattr(M, "PLANAR_CAT", planar)
+        m = _model(sd, "bf16", train=train)
+        if train:
+            loss = m.loss(x.cuda(), y.cuda())
+            loss.backward()
+            out.append((m.last_logits.clone(), loss.detach().clone(), [p.grad.clone() for p in m.parameters()]))
+        else:
+            with torch.no_grad():
+                out.append((m(x.cuda()).clone(), None, []))
+    assert torch.equal(out[0][0], out[1][0])
+    if train:
+        assert torch.equal(out[0][1], out[1][1])
+        for a, b in zip(out[0][2], out[1][2]):
+            assert torch.equal(a, b)

@@ -1029,3 +1029,59 @@ def test_conv3x3_two_destination_epilogue(B, C, O, H, W, split):
          ptr(parts2), ctypes.byref(n2), stream())
     assert torch.equal(y1, y[..., :split]) and torch.equal(y2, y[..., split:])
     assert n2.value == n.value and torch.equal(parts2[: n.value * 2 * O], st_ref)
+
+
+@pytest.mark.parametrize("B,C,O,H,W", [(2, 128, 64, 40, 24), (1, 128, 64, 33, 17), (2, 256, 128, 24, 40), (1, 512, 256, 17, 33),
+                                       (2, 1024, 512, 16, 16), (3, 128, 64, 64, 64), (2, 256, 128, 64, 64)])
+def test_conv3x3_two_source_operand(B, C, O, H, W):
+    """unetca_conv3x3_fwd_cat / _wgrad_cat == the one-tensor entries on torch.cat([skip, up], 1) (UCA:140): the decoder's first
+    conv reading its two input halves from two dense tensors.  Output, statistics and filter gradient bit-identical; also the
+    eval-mode BatchNorm + ReLU (+ SE squeeze) epilogue forms."""
+    dt = BF16
+    rs = np.random.RandomState(C + O + H)
+    call("unetca_set_conv_impl", 0)
+    C1 = C // 2
+    x = to_nhwc(torch.from_numpy(rs.standard_normal((B, C, H, W)).astype(np.float32)), dt)
+    x1, x2 = x[..., :C1].contiguous(), x[..., C1:].contiguous()
+    w = torch.from_numpy((rs.standard_normal((O, C, 3, 3)) / np.sqrt(9 * C)).astype(np.float32)).cuda()
+    wf = torch.empty(O, 9 * C, dtype=TDT[dt], device="cuda")
+    call("unetca_pack_conv3x3_weight", dt, ptr(w), ptr(wf), 9 * C, None, O, C, stream())
+    y = torch.empty(B, H, W, O, dtype=TDT[dt], device="cuda")
+    y2 = torch.full((B, H, W, O), float("nan"), dtype=TDT[dt], device="cuda")
+    parts, n = parts_buf(B), cint()
+    parts2, n2 = parts_buf(B), cint()
+    if O == 64:
+        wk = torch.empty(9 * C, 64, dtype=TDT[dt], device="cuda")
+        call("unetca_pack_conv3x3_kw", dt, ptr(wf), 9 * C, ptr(wk), C, stream())
+        call("unetca_conv3x3_fwd_kw", dt, ptr(x), C, ptr(wk), ptr(y), O, B, H, W, C, ptr(parts), ctypes.byref(n), stream())
+        wsel, layout = wk, 2
+    else:
+        call("unetca_conv3x3_fwd", dt, ptr(x), C, ptr(wf), 9 * C, ptr(y), O, B, H, W, C, O, ptr(parts), ctypes.byref(n), stream())
+        wsel, layout = wf, 0
+    call("unetca_conv3x3_fwd_cat", dt, ptr(x1), C1, ptr(x2), C - C1, C1, ptr(wsel), ptr(y2), O, B, H, W, C, O, ptr(parts2), None, None,
+         None, ctypes.byref(n2), stream())
+    assert torch.equal(y, y2)
+    assert n.value == n2.value and torch.equal(parts[: n.value * 2 * O], parts2[: n.value * 2 * O])
+    # eval-mode epilogue
+    scale = torch.from_numpy(rs.uniform(0.5, 1.5, O).astype(np.float32)).cuda()
+    shift = torch.from_numpy(rs.standard_normal(O).astype(np.float32) * 0.1).cuda()
+    nsm = unetca_b200._lib.load().unetca_num_sms()
+    sq = torch.zeros(B * nsm * O, device="cuda") if O != 64 else None
+    sq2 = torch.zeros(B * nsm * O, device="cuda") if O != 64 else None
+    a = torch.empty_like(y)
+    a2 = torch.full_like(y, float("nan"))
+    call("unetca_conv3x3_bnrelu_fwd", dt, ptr(x), C, ptr(wsel), layout, ptr(a), O, B, H, W, C, O, ptr(scale), ptr(shift),
+         ptr(sq) if sq is not None else None, ctypes.byref(n), stream())
+    call("unetca_conv3x3_fwd_cat", dt, ptr(x1), C1, ptr(x2), C - C1, C1, ptr(wsel), ptr(a2), O, B, H, W, C, O, None, ptr(scale), ptr(shift),
+         ptr(sq2) if sq2 is not None else None, ctypes.byref(n2), stream())
+    assert torch.equal(a, a2)
+    if sq is not None:
+        assert n.value == n2.value and torch.equal(sq, sq2)
+    # filter gradient
+    dy = to_nhwc(torch.from_numpy(rs.standard_normal((B, O, H, W)).astype(np.float32)), dt)
+    ws = torch.empty(16 * 1024 * 1024, device="cuda")
+    dw, dw2 = torch.empty(O, C, 3, 3, device="cuda"), torch.full((O, C, 3, 3), float("nan"), device="cuda")
+    call("unetca_conv3x3_wgrad", dt, ptr(dy), O, ptr(x), C, ptr(ws), ws.numel(), B, H, W, C, O, ptr(dw), stream())
+    call("unetca_conv3x3_wgrad_cat", dt, ptr(dy), O, ptr(x1), C1, ptr(x2), C - C1, C1, ptr(ws), ws.numel(), B, H, W, C, O, ptr(dw2),
+         stream())
+    assert torch.equal(dw, dw2)
