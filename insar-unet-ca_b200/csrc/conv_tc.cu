@@ -1299,7 +1299,7 @@ __global__ void __launch_bounds__(kPnThreads, 1) tc_conv3x3_pixn_kernel(const __
 // Column n = (pair row i = n >> 3, x = n & 7).  FULL: the whole tile lies inside the image (no bounds checks).
 // LDO / LDY: compile-time pixel strides of the output / saved tensor (0 = take the run-time value) — with the two layouts the
 // model uses (dense 64, channel half of a 128-wide concat buffer) every store address is row pointer + immediate.
-template <bool FULL, bool BWD, int LDO, int LDY, bool ACT = false>
+template <bool FULL, bool BWD, int LDO, int LDY, bool ACT = false, bool BIAS = false>
 __device__ __forceinline__ void rp64_drain(uint32_t t_addr, int cb0, bf16* __restrict__ obase, long row_stride, int ldo_rt, int ni,
                                            int nx, bool act_rt, float ea, float eb, const bf16* __restrict__ ybase, long yrow_stride,
                                            int ldy_rt, float ba, float bb, float bm, float& s1, float& s2) {
@@ -1336,6 +1336,7 @@ __device__ __forceinline__ void rp64_drain(uint32_t t_addr, int cb0, bf16* __res
                     f0 = fmaxf(fmaf(ea, f0, eb), 0.f);
                     f1 = fmaxf(fmaf(ea, f1, eb), 0.f);
                 }
+                if (BIAS) { f0 += eb; f1 += eb; }
                 const bool ok0 = rok && (FULL || x < nx), ok1 = rok && (FULL || x + 1 < nx);
                 if (!FULL) { if (!ok0) f0 = 0.f; if (!ok1) f1 = 0.f; }
                 const uint32_t pk = pack_bf16x2(f0, f1);
@@ -1659,6 +1660,139 @@ __global__ void __launch_bounds__(kHpThreads, 1) tc_conv3x3_hpix_kernel(const __
         if (p.stat_parts) {
             float* dst = p.stat_parts + (long)blockIdx.x * 2 * p.N;
             for (int i = ep_tid; i < 2 * p.N; i += 256) dst[i] = sm_stats[i];
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// ConvTranspose2d(k = 2, s = 2) forward (UCA:133..136 up1..up4), sub-pixel channels on M, input pixels on N:
+//   D[(d, e, o)][(i, x)] = sum_c Wt[(d, e, o)][c] * X[h0 + i][x0 + x][c],      out[b][2(h0+i) + d][2(x0+x) + e][o] = D + bias[o]
+// One m-block = 128 of the 4*Cout rows, one pixel tile = 8 x 32 input pixels (N = 256), K = Cin in 64-channel chunks, each one
+// [256 px][64] activation box + one [128][64] weight box.  The generic pixels-on-M kernel this replaces is EPILOGUE-bound on
+// this op — K is short (2..16 chunks) and every accumulator element becomes an output element, which its four epilogue warps
+// drain through a staging tile and four strided TMA stores per tile, one tile at a time; at 128 -> 64 channels it ran at 0.29
+// of the tensor rate and 0.53 of the op's HBM floor.  Here the eight epilogue warps of the haloed conv kernel write straight to
+// global memory (a warp = 32 channels of one output pixel = 64 contiguous bytes; the sub-pixel (d, e) is a per-thread constant
+// folded into the base pointer, the output pixel pitch is 2*ldo) while the next tile's MMAs fill the other accumulator buffer.
+// Work order: m-blocks of one pixel tile are adjacent work items, so the CTAs of a wave re-read the activation tile from L2.
+// Warps: 0 = producer, 1 = MMA issuer, 2..9 = epilogue.
+// ---------------------------------------------------------------------------------------------------------
+struct alignas(64) CtfParams {
+    CUtensorMap mapX, mapW;
+    bf16* out;
+    int ldo;
+    const float* bias;
+    int tilesW, tilesH, nimg, h, w;      // input extents
+    int cchunks, num_m_blocks, Cout;
+};
+constexpr int kCtThreads = 320;
+constexpr int kCtXBytes = 256 * 128, kCtWBytes = 128 * 128, kCtStageBytes = kCtXBytes + kCtWBytes, kCtStages = 4;
+constexpr int kCtSmemBytes = 1024 + kCtStages * kCtStageBytes + 256;
+
+__global__ void __launch_bounds__(kCtThreads, 1) tc_convT_fwd_kernel(const __grid_constant__ CtfParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCtStages * kCtStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kCtStages;
+    uint64_t* tfull_bar = bars + 2 * kCtStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kCtStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+        fence_barrier_init();
+        prefetch_tmap(&p.mapX);
+        prefetch_tmap(&p.mapW);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const long num_work = (long)tiles_per_img * p.nimg * p.num_m_blocks;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int mb = (int)(t % p.num_m_blocks);
+                const int mt = (int)(t / p.num_m_blocks);
+                const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * kCtStageBytes;
+                    mbar_expect_tx(&full_bar[s], kCtStageBytes);
+                    tma_load_4d(&p.mapX, &full_bar[s], st, cc * 64, tw * kHpTW, th * kHpTH, b);
+                    tma_load_4d(&p.mapW, &full_bar[s], st + kCtXBytes, cc * 64, mb * 128, 0, 0);
+                    if (++s == kCtStages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+            int s = 0; uint32_t ph = 0;
+            int as = 0; uint32_t aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 256;
+                for (int cc = 0; cc < p.cchunks; ++cc) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t sb = smem_u32(smem + s * kCtStageBytes);
+                    const uint32_t sa = sb + kCtXBytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(d_tmem, make_smem_desc(sa + k * 32, 16, 1024), make_smem_desc(sb + k * 32, 16, 1024), idesc,
+                                  (cc | k) != 0);
+                    umma_commit(&empty_bar[s]);
+                    if (++s == kCtStages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull_bar[as]);
+                as ^= 1; if (as == 0) aph ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        const int r = q * 32 + lane;
+        const long W2 = 2L * p.w;
+        const int ldo2 = 2 * p.ldo;
+        const long row_stride = 2 * W2 * p.ldo;
+        int as = 0; uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int mb = (int)(t % p.num_m_blocks);
+            const int mt = (int)(t / p.num_m_blocks);
+            const int tw = mt % p.tilesW, th = (mt / p.tilesW) % p.tilesH, b = mt / tiles_per_img;
+            const int x0 = tw * kHpTW, h0 = th * kHpTH;
+            const int nx = p.w - x0 < kHpTW ? p.w - x0 : kHpTW, ni = p.h - h0 < kHpTH ? p.h - h0 : kHpTH;
+            const bool full = nx == kHpTW && ni == kHpTH;
+            const int ch = mb * 128 + r;
+            const int de = ch / p.Cout, o = ch - de * p.Cout;
+            bf16* obase = p.out + (((long)b * 2 * p.h + 2 * h0 + (de >> 1)) * W2 + 2 * x0 + (de & 1)) * p.ldo + o;
+            const float eb = __ldg(p.bias + o);
+            mbar_wait(&tfull_bar[as], aph);
+            tcgen05_fence_after();
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+            float s1, s2;
+            if (full && ldo2 == 256) rp64_drain<true, false, 256, 0, false, true>(t_addr, chalf * 4, obase, row_stride, 256, ni, nx, false, 1.f, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+            else if (full && ldo2 == 512) rp64_drain<true, false, 512, 0, false, true>(t_addr, chalf * 4, obase, row_stride, 512, ni, nx, false, 1.f, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+            else if (full) rp64_drain<true, false, 0, 0, false, true>(t_addr, chalf * 4, obase, row_stride, ldo2, ni, nx, false, 1.f, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+            else rp64_drain<false, false, 0, 0, false, true>(t_addr, chalf * 4, obase, row_stride, ldo2, ni, nx, false, 1.f, eb, nullptr, 0, 0, 0.f, 0.f, 0.f, s1, s2);
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            as ^= 1; if (as == 0) aph ^= 1;
         }
     }
     tcgen05_fence_before();
@@ -2727,10 +2861,42 @@ int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out
     return launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_gemm_nt");
 }
 
+static int g_convT_pix = 1;        // ConvTranspose forward through the dedicated pixels-on-N kernel (0: generic pixels-on-M kernel)
+void unetca_tc_set_convT_pix(int on) { g_convT_pix = on; }
+
+static int launch_convT_fwd_pix(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h, int wd,
+                                int Cin, int Cout, cudaStream_t st) {
+    CtfParams p;
+    memset(&p, 0, sizeof(p));
+    int rc;
+    if ((rc = make_map(&p.mapX, x, Cin, wd, h, B, ldx, (long)wd * ldx, (long)h * wd * ldx, kHpTW, kHpTH)) < 0) return rc;
+    if ((rc = make_map(&p.mapW, w, Cin, 4L * Cout, 1, 1, Cin, 4L * Cout * Cin, 4L * Cout * Cin, 128, 1)) < 0) return rc;
+    p.out = (bf16*)out; p.ldo = ldo; p.bias = bias;
+    p.tilesW = ceil_div(wd, kHpTW); p.tilesH = ceil_div(h, kHpTH); p.nimg = B; p.h = h; p.w = wd;
+    p.cchunks = Cin / 64; p.num_m_blocks = 4 * Cout / 128; p.Cout = Cout;
+    static bool attr_done_dev[kMaxDevices] = {};
+    bool& attr_done = attr_done_dev[device_slot()];
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(tc_convT_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemBytes);
+        if (e != cudaSuccess) { set_error("tc_convT_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+        attr_done = true;
+    }
+    const long num_work = (long)p.tilesW * p.tilesH * B * p.num_m_blocks;
+    long grid = num_work < num_sms() ? num_work : num_sms();
+    if (grid < 1) grid = 1;
+    tc_convT_fwd_kernel<<<(int)grid, kCtThreads, kCtSmemBytes, st>>>(p);
+    return check_launch("tc_convT_fwd (pixels on N)");
+}
+
 // ConvTranspose2d k2 s2: out[b,2i+d,2j+e,o] = sum_c x[b,i,j,c] * w[(d*2+e)*Cout+o][c] + bias[o]
 int unetca_tc_convT_fwd(const void* x, int ldx, const void* w, const float* bias, void* out, int ldo, int B, int h,
                         int wd, int Cin, int Cout, void* stream) {
     UNETCA_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, "tc_convT: Cin=%d Cout=%d must be multiples of 64", Cin, Cout);
+    // tiles of 8 x 32 input pixels: below half a tile of rows the generic kernel's 128-pixel tiles waste less
+    if (g_convT_pix && bias && h >= 16 && wd >= 8) {
+        int r = launch_convT_fwd_pix(x, ldx, w, bias, out, ldo, B, h, wd, Cin, Cout, (cudaStream_t)stream);
+        return r < 0 ? r : 0;
+    }
     TcParams p;
     memset(&p, 0, sizeof(p));
     int TW = 0, TH = 0;

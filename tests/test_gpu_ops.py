@@ -524,9 +524,36 @@ def test_convT_ffma(dt):
     _convT_case(dt, 1, 2, 128, 64, 8, 8)
 
 
-@pytest.mark.parametrize("B,Cin,Cout,h,w_", [(2, 128, 64, 8, 8), (1, 256, 128, 16, 32), (3, 1024, 512, 2, 2)])
+@pytest.mark.parametrize("B,Cin,Cout,h,w_", [(2, 128, 64, 8, 8), (1, 256, 128, 16, 32), (3, 1024, 512, 2, 2),
+                                             # the dedicated pixels-on-N forward kernel (h >= 16, w >= 8): partial tiles in H / W / both
+                                             (2, 128, 64, 40, 24), (1, 256, 128, 33, 17), (2, 512, 256, 64, 8), (1, 1024, 512, 32, 32)])
 def test_convT_tcgen05(B, Cin, Cout, h, w_):
     _convT_case(BF16, 0, B, Cin, Cout, h, w_)
+
+
+@pytest.mark.parametrize("Cin,h,w_", [(128, 64, 64), (256, 33, 17), (512, 32, 16)])
+def test_convT_forward_kernels_agree(Cin, h, w_):
+    """The dedicated ConvTranspose forward kernel (sub-pixel channels on M, direct stores) against the generic pixels-on-M one, into
+    a dense tensor and into the channel half of a concat buffer: same K order, same rounding -> identical bits."""
+    dt, B, Cout = BF16, 2, Cin // 2
+    rs = np.random.RandomState(Cin + h)
+    call("unetca_set_conv_impl", 0)
+    x = to_nhwc(torch.from_numpy(rs.standard_normal((B, Cin, h, w_)).astype(np.float32)), dt)
+    wf = torch.from_numpy((rs.standard_normal((4 * Cout, Cin)) / np.sqrt(Cin)).astype(np.float32)).cuda().to(TDT[dt])
+    bias = torch.from_numpy(rs.standard_normal(Cout).astype(np.float32)).cuda()
+    res = []
+    try:
+        for pix in (0, 1):
+            unetca_b200._lib.load().unetca_tc_set_convT_pix(pix)
+            dense = torch.full((B, 2 * h, 2 * w_, Cout), float("nan"), dtype=TDT[dt], device="cuda")
+            cat = torch.zeros(B, 2 * h, 2 * w_, 2 * Cout, dtype=TDT[dt], device="cuda")
+            call("unetca_convT2x2_fwd", dt, ptr(x), Cin, ptr(wf), ptr(bias), ptr(dense), Cout, B, h, w_, Cin, Cout, stream())
+            call("unetca_convT2x2_fwd", dt, ptr(x), Cin, ptr(wf), ptr(bias), ptr(cat[..., Cout:]), 2 * Cout, B, h, w_, Cin, Cout, stream())
+            assert cat[..., :Cout].abs().max().item() == 0 and torch.equal(cat[..., Cout:], dense)
+            res.append(dense)
+    finally:
+        unetca_b200._lib.load().unetca_tc_set_convT_pix(1)
+    assert torch.equal(res[0], res[1])
 
 
 @pytest.mark.parametrize("dt,impl", [(F32, 1), (BF16, 1), (BF16, 0)])

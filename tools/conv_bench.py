@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--kw64", action="store_true", help="64->64 layers through the kw-stacked kernel instead of the row-pair one")
     ap.add_argument("--convT", action="store_true", help="benchmark the four ConvTranspose2d(k2,s2) layers instead")
     ap.add_argument("--convT-narrow", action="store_true", help="ConvTranspose N blocks confined to one sub-pixel map (A/B)")
+    ap.add_argument("--convT-generic", action="store_true", help="ConvTranspose forward through the generic pixels-on-M kernel (A/B)")
     ap.add_argument("--pixn-cluster", type=int, default=2, help="CTAs per cluster sharing weights by TMA multicast (1|2)")
     ap.add_argument("--wgrad-mode", type=int, default=0, help="0 auto, 1 narrow kernel everywhere, 2 no 256-wide tap-pair kernel")
     ap.add_argument("--no-kw", action="store_true", help="64-output layers through the row-pair kernel instead of the kw-stacked one")
@@ -42,6 +43,7 @@ def main():
     lib.unetca_tc_force_no_halo(1 if a.no_halo else 0)
     lib.unetca_tc_set_pixn_cluster(a.pixn_cluster)
     lib.unetca_tc_set_convT_wide(0 if a.convT_narrow else 1)
+    lib.unetca_tc_set_convT_pix(0 if a.convT_generic else 1)
     layers = LAYERS if a.layers == ["all"] else [tuple(int(v) for v in s.split(",")) for s in a.layers]
     if a.dgrad:
         layers = layers + [(64, 128, 512), (128, 64, 256), (256, 128, 128)]
