@@ -541,6 +541,37 @@ def extra_global_batch(model, opt, buckets, x, y, world, rank, dev, global_batch
             "scaling": "strong", "all_reduces_per_optimizer_step": 1 if world > 1 else 0}
 
 
+def extra_rank_spread(model, opt, buckets, x, y, world, rank, dev, steps=10):
+    """N > 1 diagnostic: every rank runs `steps` train steps AT THE SAME TIME with the all-reduce switched off (no_sync), so
+    no rank waits for another, and reports its own time.  The spread is what the slowest-GPU-sets-the-pace part of the
+    1 -> N loss looks like; the difference between the slowest rank here and the synchronised step is what the exchange
+    itself costs."""
+    import torch.distributed as dist
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        model.loss(x, y).backward()
+        opt.step()
+
+    with buckets.no_sync():
+        for _ in range(3):
+            step()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    ms = sorted(v.item() for v in allt)
+    return {"ms_per_step_by_rank_sorted": [round(v, 2) for v in ms], "min": ms[0], "max": ms[-1], "steps": steps,
+            "what": "all ranks stepping simultaneously without the gradient all-reduce (no_sync): per-rank ms/step"}
+
+
 def extra_ablation(dev, B, S, precision, steps=3):
     """configs[4]'s ablation baseline: the plain U-Net (use_se=False, /root/reference/Unet.py) through the same path."""
     import unetca_b200
@@ -616,6 +647,8 @@ def main():
     ap.add_argument("--kernel-table", default=None, help="write the per-kernel table (JSON) to this path")
     ap.add_argument("--nccl-max-ctas", type=int, default=int(os.environ.get("UNETCA_NCCL_MAX_CTAS", "0")),
                     help="N > 1: cap the CTAs NCCL may use for the gradient all-reduce (0 = NCCL's default)")
+    ap.add_argument("--compute-priority", type=int, default=int(os.environ.get("UNETCA_COMPUTE_PRIORITY", "0")),
+                    help="A/B: run the step on a CUDA stream of this priority (-1 = above NCCL's stream) instead of the default stream")
     ap.add_argument("--timeline", default=None,
                     help="N > 1: rank 0 records one extra step with torch.profiler and writes a per-stream kernel timeline "
                          "summary (JSON) here: NCCL time, overlap with compute, exposed tail")
@@ -656,6 +689,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev, pg_options=pg_opts)
     if args.warmup < 3:
         args.warmup = 3
+    if args.compute_priority:
+        # the persistent contraction kernels want all 148 SMs at every kernel boundary; on a higher-priority stream their CTAs
+        # are placed before the pending CTAs of a bucket all-reduce (which then runs in the shadow of the lighter kernels)
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev, priority=args.compute_priority))
 
     if os.environ.get("UNETCA_BLOCK_N"):                 # tuning knob: force the tcgen05 tile width where it divides N
         _lib.load().unetca_tc_force_block_n(int(os.environ["UNETCA_BLOCK_N"]))
@@ -907,6 +944,7 @@ def main():
         extra["global_batch_512"] = guarded(lambda: extra_global_batch(model, opt, buckets, x, y, world, rank, dev))
         if world > 1:
             if buckets is not None:
+                extra["rank_spread_no_sync"] = guarded(lambda: extra_rank_spread(model, opt, buckets, x, y, world, rank, dev))
                 buckets.detach()
             extra["dp_parity"] = guarded(lambda: extra_dp_parity(dev, rank, world))
     del model, opt, buckets
