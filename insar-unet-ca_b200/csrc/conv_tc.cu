@@ -1802,6 +1802,152 @@ __global__ void __launch_bounds__(kCtThreads, 1) tc_convT_fwd_kernel(const __gri
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// ConvTranspose2d(k = 2, s = 2) weight gradient with a 256 x 256 output tile per work item        (UCA:345 through up1..up4)
+//   dW[c][(d, e, o)] = sum_{b,i,j} X[b,i,j,c] * dOut[b, 2i+d, 2j+e, o]           (K = input pixels, both operands MN-major)
+// The generic split-K kernel (128 x 256 tile) is bound by L2 -> shared-memory fill on this op: nothing is reused across MMAs,
+// every 128x256x16 MMA needs 12 KB of fresh operands, and halving the tile width (BLOCK_N = 128) takes it from 0.47 to 0.71 ms
+// at 1024 -> 512 — time follows the bytes filled.  Here one k-tile of 64 pixels brings four [64 px][64 c] activation boxes and
+// four [64 px][64] gradient boxes (64 KB) for EIGHT MMAs into two 128 x 256 accumulators (all 512 TMEM columns): 8 KB per MMA.
+// The accumulator is single-buffered; an item's mainloop is > 100 k-tiles, its epilogue (256 KB of fp32 partials) ~3 %.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCwStages = 3;
+constexpr int kCwABytes = 4 * kBoxBytesWg, kCwBBytes = 4 * kBoxBytesWg, kCwStageBytes = kCwABytes + kCwBBytes;
+constexpr int kCwSmemBytes = 1024 + kCwStages * kCwStageBytes + 256;
+
+__global__ void __launch_bounds__(kTcThreads, 1) tc_convT_wgrad_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kCwStages * kCwStageBytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + kCwStages;
+    uint64_t* tfull_bar = bars + 2 * kCwStages;
+    uint64_t* tempty_bar = tfull_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 1);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kCwStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        mbar_init(tfull_bar, 1); mbar_init(tempty_bar, 4);
+        fence_barrier_init();
+        prefetch_tmap(&p.mapA[0]);
+        for (int i = 0; i < 4; ++i) prefetch_tmap(&p.mapB[i]);
+    }
+    if (warp == 1) tmem_alloc<512>(tmem_slot);
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_per_img = p.tilesW * p.tilesH;
+    const long mn_items = (long)p.num_m_blocks * p.num_n_blocks;
+    const long num_work = mn_items * p.nsplit;
+    const int kt_per_split = (p.ktiles_total + p.nsplit - 1) / p.nsplit;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int s = 0; uint32_t ph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / mn_items);
+                const int nb = (int)((t % mn_items) % p.num_n_blocks);
+                const int mb = (int)((t % mn_items) / p.num_n_blocks);
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                for (int kt = kt0; kt < kt1; ++kt) {
+                    const int tw = kt % p.tilesW, th = (kt / p.tilesW) % p.tilesH, b = kt / tiles_per_img;
+                    const int w0 = tw * p.TW, h0 = th * p.TH;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * kCwStageBytes;
+                    mbar_expect_tx(&full_bar[s], kCwStageBytes);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        tma_load_4d(&p.mapA[0], &full_bar[s], sa + i * kBoxBytesWg, (mb * 4 + i) * 64, w0, h0, b);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int q = nb * 4 + j;
+                        tma_load_4d(&p.mapB[q / p.b_chunks_per_map], &full_bar[s], sa + kCwABytes + j * kBoxBytesWg,
+                                    (q % p.b_chunks_per_map) * 64, w0, h0, b);
+                    }
+                    if (++s == kCwStages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 256, 1, 1);
+            int s = 0; uint32_t ph = 0;
+            uint32_t aph = 0;
+            for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+                const int z = (int)(t / mn_items);
+                int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+                if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+                const int nk = kt1 - kt0;
+                mbar_wait(tempty_bar, aph ^ 1);
+                tcgen05_fence_after();
+                for (int kb = 0; kb < nk; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * kCwStageBytes);
+                    const uint32_t sb = sa + kCwABytes;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t db = make_smem_desc(sb + k * 2048, kBoxBytesWg, 1024);
+                        umma_bf16(tmem_base, make_smem_desc(sa + k * 2048, kBoxBytesWg, 1024), db, idesc, (kb | k) != 0);
+                        umma_bf16(tmem_base + 256, make_smem_desc(sa + 2 * kBoxBytesWg + k * 2048, kBoxBytesWg, 1024), db, idesc,
+                                  (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == kCwStages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(tfull_bar);
+                aph ^= 1;
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        uint32_t aph = 0;
+        for (long t = blockIdx.x; t < num_work; t += gridDim.x) {
+            const int z = (int)(t / mn_items);
+            const int nb = (int)((t % mn_items) % p.num_n_blocks);
+            const int mb = (int)((t % mn_items) / p.num_n_blocks);
+            int kt0 = z * kt_per_split, kt1 = kt0 + kt_per_split;
+            if (kt1 > p.ktiles_total) kt1 = p.ktiles_total;
+            const bool have = kt1 > kt0;
+            float* wsz = p.ws + (long long)z * p.split_stride;
+            mbar_wait(tfull_bar, aph);
+            tcgen05_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const int m = mb * 256 + h * 128 + r;
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + h * 256;
+#pragma unroll 1
+                for (int c32 = 0; c32 < 8; ++c32) {
+                    uint32_t v[32];
+                    tmem_ld32(t_addr + c32 * 32, v);
+                    tmem_wait_ld();
+                    if (m < p.m_valid) {
+                        float4* dst = reinterpret_cast<float4*>(wsz + (long long)m * p.ldn + nb * 256 + c32 * 32);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                            dst[i] = have ? make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                                        __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar);
+            aph ^= 1;
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    if (warp == 1) tmem_dealloc<512>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // conv3x3 forward / dgrad for 64 -> 64 channels (the two full-resolution DoubleConv layers, 4 launches per step):
 // the row-pair layout of tc_conv3x3_pixn_kernel<P = 2> with the tap reuse of the haloed kernel and a RESIDENT filter.
 //   D[(j, o)][(i, x)] = sum_{vr, kw, c} Wv[(j, o)][vr][kw][c] * X[2(i0+i) + vr - 1][x0 + x + kw - 1][c]
@@ -2861,6 +3007,8 @@ int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out
     return launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_gemm_nt");
 }
 
+static int g_convT_wgrad256 = 1;   // ConvTranspose weight gradient: 256 x 256 tiles where Cin % 256 == 0 (0: generic 128 x 256 kernel)
+void unetca_tc_set_convT_wgrad256(int on) { g_convT_wgrad256 = on; }
 static int g_convT_pix = 1;        // ConvTranspose forward through the dedicated pixels-on-N kernel (0: generic pixels-on-M kernel)
 void unetca_tc_set_convT_pix(int on) { g_convT_pix = on; }
 
@@ -3156,6 +3304,29 @@ int unetca_tc_convT_wgrad(const void* x, int ldx, const void* dout, int ldd, flo
     p.tilesW = ceil_div(wd, TW); p.tilesH = ceil_div(h, TH); p.nimg = B;
     p.TW = TW; p.TH = TH; p.H = h; p.W = wd;
     p.a_chunks = Cin / 64; p.a_cchunks = Cin / 64; p.b_chunks_per_map = Cout / 64;
+    if (g_convT_wgrad256 && Cin % 256 == 0 && g_convT_wide && !g_force_block_n) {
+        // 256 x 256 output tiles (two accumulators): a third less shared-memory fill per MMA than the generic kernel
+        p.num_m_blocks = Cin / 256;
+        p.num_n_blocks = 4 * Cout / 256;
+        p.ktiles_total = p.tilesW * p.tilesH * B;
+        p.split_stride = (long long)Cin * 4 * Cout;
+        p.nsplit = pick_nsplit((long)p.num_m_blocks * p.num_n_blocks, p.ktiles_total, p.split_stride, ws_floats);
+        if (p.nsplit < 1) { set_error("tc_convT_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+        p.ws = ws; p.ldn = 4 * Cout; p.store_transposed = 0; p.m_valid = Cin;
+        static bool attr_done_dev[kMaxDevices] = {};
+        bool& attr_done = attr_done_dev[device_slot()];
+        if (!attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(tc_convT_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCwSmemBytes);
+            if (e != cudaSuccess) { set_error("tc_convT_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return UNETCA_ERR_CUDA; }
+            attr_done = true;
+        }
+        const long num_work = (long)p.num_m_blocks * p.num_n_blocks * p.nsplit;
+        long grid = num_work < num_sms() ? num_work : num_sms();
+        if (grid < 1) grid = 1;
+        tc_convT_wgrad_kernel<<<(int)grid, kTcThreads, kCwSmemBytes, (cudaStream_t)stream>>>(p);
+        int r3 = check_launch("tc_convT_wgrad (256 x 256)");
+        return r3 < 0 ? r3 : p.nsplit;
+    }
     p.num_m_blocks = (p.a_chunks + 1) / 2;
     p.num_n_blocks = 4 * Cout / BN;
     p.ktiles_total = p.tilesW * p.tilesH * B;

@@ -44,6 +44,7 @@ def main():
     lib.unetca_tc_set_pixn_cluster(a.pixn_cluster)
     lib.unetca_tc_set_convT_wide(0 if a.convT_narrow else 1)
     lib.unetca_tc_set_convT_pix(0 if a.convT_generic else 1)
+    lib.unetca_tc_set_convT_wgrad256(0 if a.convT_generic else 1)
     layers = LAYERS if a.layers == ["all"] else [tuple(int(v) for v in s.split(",")) for s in a.layers]
     if a.dgrad:
         layers = layers + [(64, 128, 512), (128, 64, 256), (256, 128, 128)]
