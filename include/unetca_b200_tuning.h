@@ -13,6 +13,7 @@ void unetca_tc_force_block_n(int n);
 void unetca_tc_force_wgrad_narrow(int on);
 void unetca_tc_force_no_halo(int on);
 void unetca_tc_set_convT_wide(int on);
+void unetca_tc_set_first_wgrad_swap(int on); /* 1 (default): first-conv weight gradient with (j, o) on the MMA M side */
 void unetca_tc_set_convT_wgrad256(int on); /* 1 (default): ConvTranspose weight gradient in 256 x 256 tiles where Cin % 256 == 0; 0: generic */
 void unetca_tc_set_convT_pix(int on);     /* 1 (default): ConvTranspose forward through the dedicated pixels-on-N kernel; 0: generic */
 void unetca_tc_force_no_pixn(int on);

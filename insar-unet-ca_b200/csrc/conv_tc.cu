@@ -3007,6 +3007,8 @@ int unetca_tc_gemm_nt(const void* A, int lda, const void* Bw, int ldb, void* out
     return launch_tc_n<false>(BN, p, (long)p.num_m_blocks * p.num_n_blocks, (cudaStream_t)stream, "tc_gemm_nt");
 }
 
+static int g_first_wgrad_swap = 1;  // first-conv weight gradient: (j, o) on M, patch columns on N (0: patch columns on M, duplicate box)
+void unetca_tc_set_first_wgrad_swap(int on) { g_first_wgrad_swap = on; }
 static int g_convT_wgrad256 = 1;   // ConvTranspose weight gradient: 256 x 256 tiles where Cin % 256 == 0 (0: generic 128 x 256 kernel)
 void unetca_tc_set_convT_wgrad256(int on) { g_convT_wgrad256 = on; }
 static int g_convT_pix = 1;        // ConvTranspose forward through the dedicated pixels-on-N kernel (0: generic pixels-on-M kernel)
@@ -3271,17 +3273,33 @@ int unetca_tc_first_pairs_wgrad(const void* dy, int lddy, const void* colp, floa
         const bf16* base = (const bf16*)dy + (long)j * W * lddy;
         if ((rc = make_map(&p.mapB[j], base, O, W, HP, B, lddy, 2L * W * lddy, (long)H * W * lddy, TW, TH)) < 0) return rc;
     }
-    const int BN = pick_block_n(2 * O);
     p.tilesW = ceil_div(W, TW); p.tilesH = ceil_div(HP, TH); p.nimg = B;
     p.TW = TW; p.TH = TH; p.H = HP; p.W = W;
+    p.ktiles_total = p.tilesW * p.tilesH * B;
+    p.split_stride = 64LL * 2 * O;
+    p.ws = ws; p.ldn = 2 * O;
+    if (O == 64 && g_first_wgrad_swap) {
+        // (j, o) on M, the 64 patch columns on N: the two gradient boxes fill all 128 MMA rows.  With the patch columns on M
+        // (below) the second half of every A tile is a duplicate box — a quarter of the shared-memory fill and half of every
+        // MMA wasted on a kernel whose bound is the 3.2 GB it streams.  Output transposed on store, so ws keeps its layout.
+        CUtensorMap col = p.mapA[0];
+        p.mapA[0] = p.mapB[0]; p.mapA[1] = p.mapB[1]; p.mapB[0] = col;
+        p.amap[0] = 0; p.amap[1] = 1;
+        p.a_chunks = 2; p.a_cchunks = 1; p.b_chunks_per_map = 1;
+        p.num_m_blocks = 1; p.num_n_blocks = 1;
+        p.nsplit = pick_nsplit(1, p.ktiles_total, p.split_stride, ws_floats);
+        if (p.nsplit < 1) { set_error("tc_first_pairs_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
+        p.store_transposed = 1; p.m_valid = 128;
+        int r3 = launch_tc_n<true>(64, p, (long)p.nsplit, (cudaStream_t)stream, "tc_first_pairs_wgrad");
+        return r3 < 0 ? r3 : p.nsplit;
+    }
+    const int BN = pick_block_n(2 * O);
     p.a_chunks = 1; p.a_cchunks = 1; p.b_chunks_per_map = O / 64;
     p.num_m_blocks = 1;
     p.num_n_blocks = 2 * O / BN;
-    p.ktiles_total = p.tilesW * p.tilesH * B;
-    p.split_stride = 64LL * 2 * O;
     p.nsplit = pick_nsplit((long)p.num_n_blocks, p.ktiles_total, p.split_stride, ws_floats);
     if (p.nsplit < 1) { set_error("tc_first_pairs_wgrad: workspace too small"); return UNETCA_ERR_WORKSPACE; }
-    p.ws = ws; p.ldn = 2 * O; p.store_transposed = 0; p.m_valid = 64;
+    p.store_transposed = 0; p.m_valid = 64;
     int r2 = launch_tc_n<true>(BN, p, (long)p.num_n_blocks * p.nsplit, (cudaStream_t)stream, "tc_first_pairs_wgrad");
     return r2 < 0 ? r2 : p.nsplit;
 }
