@@ -3,7 +3,8 @@
 Generates tests/golden/*.npz by running the UNMODIFIED reference classes (`UNet`, `nn.CrossEntropyLoss`) imported
 by path from /root/reference/Unet-ChannalAttention.py on CPU, fp32, on the seeded fixtures of
 oracle/unet_ca_port.py (`make_state_dict`, `make_batch`).  Run in the build container only (the GPU box has no
-/root/reference):  python oracle/make_golden.py
+/root/reference):  python oracle/make_golden.py [case ...]      (UNETCA_GOLDEN_OUT=/tmp/g re-generates elsewhere;
+oracle/check_golden.py diffs such a directory against tests/golden)
 
 The reference ships no tests or golden vectors of its own, so these files are what pins the oracle.
 """
@@ -21,7 +22,7 @@ sys.path.insert(0, ROOT)
 from oracle import unet_ca_port as port  # noqa: E402
 
 REF = "/root/reference/Unet-ChannalAttention.py"
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.environ.get("UNETCA_GOLDEN_OUT", os.path.join(ROOT, "tests", "golden"))   # override to re-generate elsewhere and diff
 
 
 def load_reference():
