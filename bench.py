@@ -602,13 +602,26 @@ def extra_ablation(dev, B, S, precision, steps=3):
     return {"value": B / (ms / 1e3), "unit": UNIT, "ms_per_step": ms, "workload": f"plain U-Net (use_se=False), batch {B}, 3x{S}x{S}"}
 
 
-def extra_scene(dev, scene=4096):
+def extra_scene(dev, rank=0, world=1):
+    """BASELINE configs[3]: tiled eval-mode inference, tiles round-robin over the ranks, no data-path collective.  One GPU: a
+    4096^2 scene (16 tiles); 8 GPUs: the 16384^2 scene configs[3] names (256 tiles, 32 per rank); 2 / 4 GPUs: 8192^2."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import scene_bench
-    ms, ones, my_tiles, ntiles, size = scene_bench.run_scene(scene, 1024, 128, 4, "bf16", 2, dev)
-    return {"value": scene * scene / 1e6 / (ms / 1e3), "unit": "Mpx/s", "ms": ms, "tiles": ntiles, "tiles_per_sec": ntiles / (ms / 1e3),
-            "workload": f"BASELINE configs[3] on one GPU at reduced extent: {scene}x{scene} hashed scene, core 1024 + halo 128 -> "
-                        f"{size}^2 windows, 4 per forward, eval mode, bf16, second pass timed", "class1_pixels": ones}
+    scene = {1: 4096, 2: 8192, 4: 8192, 8: 16384}.get(world, 4096)
+    ms, ones, my_tiles, ntiles, size = scene_bench.run_scene(scene, 1024, 128, 4, "bf16", 2, dev, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+        t = torch.tensor([ones], device=dev, dtype=torch.int64)
+        dist.all_reduce(t)
+        ones = int(t.item())
+    return {"value": scene * scene / 1e6 / (ms / 1e3), "unit": "Mpx/s", "ms": ms, "tiles": ntiles, "tiles_per_rank": my_tiles,
+            "tiles_per_sec": ntiles / (ms / 1e3), "n_gpus": world,
+            "workload": f"BASELINE configs[3]{' at reduced extent' if scene != 16384 else ''}: {scene}x{scene} hashed scene, core 1024 + "
+                        f"halo 128 -> {size}^2 windows, {ntiles} tiles round-robin over {world} GPU(s), 4 per forward, eval mode, bf16, "
+                        "second pass timed (max over ranks)", "class1_pixels": ones}
 
 
 def extra_se_sweep():
@@ -949,6 +962,9 @@ def main():
             extra["dp_parity"] = guarded(lambda: extra_dp_parity(dev, rank, world))
     del model, opt, buckets
     torch.cuda.empty_cache()
+    if extra is not None and world > 1:
+        extra["scene_inference"] = guarded(lambda: extra_scene(dev, rank, world))
+        torch.cuda.empty_cache()
     if extra is not None and world == 1:
         extra["ablation_plain_unet"] = guarded(lambda: extra_ablation(dev, B, S, args.precision))
         torch.cuda.empty_cache()
